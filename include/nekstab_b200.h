@@ -1,0 +1,265 @@
+/*
+ * nekstab_b200.h -- C ABI of the B200-native nekStab Arnoldi / Newton-Krylov hot path.
+ *
+ * This is the boundary the reference's Fortran host code binds through ISO_C_BINDING
+ * (see fortran/nek_dvectors.f90 and INTEGRATION.md).  Every entry point names the reference
+ * routine it replaces (paths relative to the nekStab repository root).
+ *
+ * Conventions
+ *  - plain C types only; all handles are opaque pointers owned by the library;
+ *  - every function returns 0 on success and a negative NSB_E* code otherwise, never aborts
+ *    (the reference prints and calls nek_end -- the Fortran shim maps nonzero to that);
+ *    nsb_last_error() gives the message of the last failure on the calling thread;
+ *  - pointers are HOST pointers unless the parameter name ends in _d;
+ *  - indices (columns, k, mstart, mend) are 0-based on this side; the Fortran shim converts;
+ *  - matrices (H, Z, y) are column-major doubles with an explicit leading dimension,
+ *    exactly as Fortran passes them;
+ *  - one CUDA stream per context; calls that return host scalars synchronise that stream,
+ *    the others only enqueue work.
+ *  - there is NO CPU fallback: without a CUDA device nsb_init fails with NSB_ENODEVICE.
+ */
+#ifndef NEKSTAB_B200_H
+#define NEKSTAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_VERSION 100
+
+/* error codes */
+#define NSB_OK 0
+#define NSB_EINVAL (-1)     /* bad argument */
+#define NSB_ECUDA (-2)      /* CUDA runtime error */
+#define NSB_ENODEVICE (-3)  /* no usable CUDA device (there is no CPU fallback) */
+#define NSB_ENAN (-4)       /* NaN in an inner product (reference: nek_end) */
+#define NSB_ENCCL (-5)      /* NCCL error / NCCL not loadable */
+#define NSB_ELAPACK (-6)    /* LAPACK provider missing or LAPACK info != 0 */
+#define NSB_EBREAKDOWN (-7) /* Krylov breakdown (zero residual norm) */
+
+typedef struct nsb_context_s *nsb_context_t;
+typedef struct nsb_layout_s *nsb_layout_t;
+typedef struct nsb_basis_s *nsb_basis_t;
+typedef struct nsb_sem_s *nsb_sem_t;
+typedef struct nsb_op_s *nsb_op_t;
+
+const char *nsb_last_error(void);
+int nsb_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Context: one per process / MPI rank / GPU.  (Reference: the Nek rank, nid/np in SIZE/PARALLEL;
+ * collectives replace gop -> MPI_Allreduce inside glsc3, core/nek_vectors.f90:7-12.)
+ * ------------------------------------------------------------------------------------------- */
+#define NSB_UNIQUE_ID_BYTES 128
+/* rank 0 calls this and broadcasts the bytes with the host's own transport (MPI_Bcast in Nek). */
+int nsb_get_unique_id(void *id_out /* NSB_UNIQUE_ID_BYTES */);
+/* unique_id may be NULL when nranks == 1. */
+int nsb_init(int device, int rank, int nranks, const void *unique_id, nsb_context_t *ctx);
+int nsb_finalize(nsb_context_t ctx);
+int nsb_sync(nsb_context_t ctx);
+int nsb_rank(nsb_context_t ctx, int *rank, int *nranks);
+/* CUDA stream of the context as an integer handle (for event timing by the caller). */
+int nsb_stream(nsb_context_t ctx, uint64_t *stream);
+/* Kernels launched by this context since creation (for the bench's gpu_launches). */
+int nsb_launch_count(nsb_context_t ctx, int64_t *count);
+/* Device-side event timing on the context stream. */
+int nsb_timer_start(nsb_context_t ctx);
+int nsb_timer_stop(nsb_context_t ctx, double *elapsed_ms); /* synchronises */
+/* Sum-allreduce n doubles held on the host across ranks (gop(x,'+')); no-op for one rank. */
+int nsb_allreduce_host(nsb_context_t ctx, double *x, int n);
+/* Write a buffer larger than L2 (bench hygiene). */
+int nsb_flush_l2(nsb_context_t ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout of one state vector = the fields of krylov_vector / real_nek_vector
+ * (core/krylov_subspace.f90:12-17, core/nek_vectors.f90:20-31): vx, vy, [vz], [pr], [t(:,m)], time.
+ *   field_len[i]    active length of field i on this rank (nv, n2, nt ...)
+ *   field_in_dot[i] 1 if the field enters the inner product (velocity, temperature, scalars),
+ *                   0 otherwise (pressure never does: core/krylov_subspace.f90:40-49)
+ *   time_in_dot     1: dot adds time*time (new API always, core/nek_vectors.f90:105-107;
+ *                   legacy only when uparam(1)==2.1, core/krylov_subspace.f90:52-54)
+ * ------------------------------------------------------------------------------------------- */
+int nsb_layout_create(nsb_context_t ctx, int nfields, const int64_t *field_len,
+                      const int *field_in_dot, int time_in_dot, nsb_layout_t *layout);
+int nsb_layout_destroy(nsb_layout_t layout);
+/* rows of one column (padded leading dimension), rows covered by the inner product */
+int nsb_layout_info(nsb_layout_t layout, int64_t *ld, int64_t *ndot, int64_t *ndof_dot);
+/* Inner-product weight bm1s (core/NEKSTAB:86-89; bm1s <- bm1 in core/main.f90:108; zeroed inside
+ * sponges, core/forcing.f90:102-104).  One weight array per in-dot field, field order; pass the
+ * same pointer several times to reuse bm1s for vx, vy, vz like the reference does. */
+int nsb_layout_set_weight(nsb_layout_t layout, const double *const *weight_per_dot_field);
+
+/* ---------------------------------------------------------------------------------------------
+ * Basis: device-resident column-major tall-skinny fp64 array V[ld, ncols]; a (basis, col) pair
+ * is one nek_dvector.  Replaces allocate(Q(k_dim+1)) (core/eigensolvers.f90:149,
+ * core/linear_stab.f90:60) and stand-alone work vectors (f, wrk, sol, dq ...).
+ * ------------------------------------------------------------------------------------------- */
+int nsb_basis_create(nsb_layout_t layout, int ncols, nsb_basis_t *basis);
+int nsb_basis_destroy(nsb_basis_t basis);
+int nsb_basis_ncols(nsb_basis_t basis, int *ncols);
+/* device address of a column (for callers that run their own kernels on it) */
+int nsb_basis_col_ptr(nsb_basis_t basis, int col, uint64_t *ptr_d);
+
+/* host <-> device; fields[i] has field_len[i] doubles (NULL: field zero-filled / skipped) */
+int nsb_vec_upload(nsb_basis_t b, int col, const double *const *fields, double time);
+int nsb_vec_download(nsb_basis_t b, int col, double *const *fields, double *time);
+
+/* BLAS-1 set, one kernel each over the whole column.
+ *   zero   : real_zero / k_zero            (core/nek_vectors.f90:70-78, krylov_subspace.f90:141-150)
+ *   copy   : k_copy(dst, src), dest first  (core/krylov_subspace.f90:152-161)
+ *   scal   : real_scal / k_cmult           (core/nek_vectors.f90:116-125, krylov_subspace.f90:94-104)
+ *   axpby  : self <- alpha*self + beta*vec (core/nek_vectors.f90:127-139, 250-256)
+ *   add2/sub2/sub3 : k_add2, k_sub2, k_sub3 (core/krylov_subspace.f90:106-139)
+ * NSB_AXPBY_SKIP_TIME reproduces real_axpby's quirk of leaving %time untouched. */
+#define NSB_AXPBY_SKIP_TIME 1
+int nsb_vec_zero(nsb_basis_t b, int col);
+int nsb_vec_copy(nsb_basis_t bdst, int cdst, nsb_basis_t bsrc, int csrc);
+int nsb_vec_scal(nsb_basis_t b, int col, double alpha);
+int nsb_vec_axpby(nsb_basis_t bself, int cself, double alpha, nsb_basis_t bvec, int cvec,
+                  double beta, int flags);
+int nsb_vec_add2(nsb_basis_t bp, int cp, nsb_basis_t bq, int cq);
+int nsb_vec_sub2(nsb_basis_t bp, int cp, nsb_basis_t bq, int cq);
+int nsb_vec_sub3(nsb_basis_t bp, int cp, nsb_basis_t bq, int cq, nsb_basis_t br, int cr);
+
+/* BM1-weighted inner product incl. the allreduce over ranks:
+ *   real_dot / k_dot / inner_product (core/nek_vectors.f90:80-114, krylov_subspace.f90:26-60,
+ *   eigensolvers.f90:3-56); NaN -> NSB_ENAN.   norm: k_norm (:62-73); normalize: k_normalize (:75-92). */
+int nsb_vec_dot(nsb_basis_t ba, int ca, nsb_basis_t bb, int cb, double *alpha);
+int nsb_vec_norm(nsb_basis_t b, int col, double *alpha);
+int nsb_vec_normalize(nsb_basis_t b, int col, double *alpha);
+
+/* ---------------------------------------------------------------------------------------------
+ * Orthogonalisation of column col_w against columns 0..k-1 of the same basis, then
+ * normalisation: update_hessenberg_matrix (core/krylov_decomposition.f90:103-189).
+ *   h[0..k-1] = H(1:k,k) (sum over passes), h[k] = H(k+1,k) = ||w|| after orthogonalisation.
+ * Modes:
+ *   NSB_ORTH_MGS2_REF  literal reference: column-by-column MGS, unconditional second pass
+ *                      (2k dots + 2k updates; slow, for parity tests)
+ *   NSB_ORTH_CGS2      fused multi-column: h1 = V^T W w ; w -= V h1 ; h2 = V^T W w ; w -= V h2
+ *                      (same two-pass semantics, H = h1 + h2; 3 all-reduces per step)
+ *   NSB_ORTH_DGKS      as CGS2, second pass only if ||w'|| < eta ||w|| (eta = 1/sqrt 2)
+ * ------------------------------------------------------------------------------------------- */
+#define NSB_ORTH_MGS2_REF 0
+#define NSB_ORTH_CGS2 1
+#define NSB_ORTH_DGKS 2
+int nsb_orthonormalize(nsb_basis_t b, int k, int col_w, int mode, double *h, int *passes);
+/* Asynchronous variant: h stays on the device until nsb_sync / the next synchronising call;
+ * h_pinned must be memory from nsb_host_alloc.  Used by the device-resident Arnoldi loop. */
+int nsb_orthonormalize_async(nsb_basis_t b, int k, int col_w, int mode, double *h_pinned);
+int nsb_host_alloc(void **ptr, int64_t bytes);
+int nsb_host_free(void *ptr);
+/* Gram matrix G = V(:,0:k)^T W V(:,0:k) (k x k, ldg) -- the orthonormality.dat check of
+ * core/eigensolvers.f90:335-345 in one pass. */
+int nsb_basis_gram(nsb_basis_t b, int k, double *G, int ldg);
+
+/* dq = sum_i y_i Q_i: k_matmul (core/krylov_subspace.f90:163-209), Ritz vectors
+ * (core/eigensolvers.f90:565-574, one call for Re and one for Im coefficients). */
+int nsb_basis_gemv(nsb_basis_t b, int k, const double *y, nsb_basis_t bout, int col_out);
+/* Q(:,0:k) <- Q(:,0:k) * Z, in place: schur_condensation (core/eigensolvers.f90:421-442).
+ * With rotate_time == 0 the %time component is left alone, as the reference does. */
+int nsb_basis_rotate(nsb_basis_t b, int k, const double *Z, int ldz, int rotate_time);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spectral-element operator pieces ([UPSTREAM-RECALL] Nek5000, reached by the reference through
+ * nek_advance, core/linear_operators.f90:247).
+ * ------------------------------------------------------------------------------------------- */
+/* GLL nodes, weights, derivative matrix D[i + (N+1)*j] = dl_j/dx(z_i) (Fortran dxm1(i,j)). */
+int nsb_gll(int N, double *z, double *w, double *D);
+
+/* A mesh partition resident on the device.
+ *   dim      2 or 3;  N polynomial order (lx1 = N+1);  nel local elements
+ *   x,y,z    nodal coordinates, element-local Nek layout (i fastest), nel*lx1^dim each (z NULL in 2-D)
+ *   mask     Dirichlet mask (v1mask), 0/1 doubles, or NULL for all ones
+ *   glo_num  global node ids (Nek glo_num, any non-negative int64), identical ids <=> same node
+ * Geometry (jac, bm1, G1..G6, rx..tz) is computed on the device (coef.f glmapm1/geodat1). */
+int nsb_sem_create(nsb_context_t ctx, int dim, int N, int64_t nel, const double *x, const double *y,
+                   const double *z, const double *mask, const int64_t *glo_num, nsb_sem_t *sem);
+int nsb_sem_destroy(nsb_sem_t sem);
+/* which = 0 bm1, 1 jac, 2 binvm1 (1/dssum(bm1)), 3 vmult (1/multiplicity), 4 mask,
+ *         10..15 G1..G6 (2-D: 10,11,13 = G1,G2,G4) ; out has nel*lx1^dim doubles */
+int nsb_sem_get(nsb_sem_t sem, int which, double *out);
+int64_t nsb_sem_npts(nsb_sem_t sem);
+/* Multi-rank: neighbours are found from glo_num; call once after every rank created its sem. */
+int nsb_sem_setup_exchange(nsb_sem_t sem);
+
+/* Kernels on field `field` of column `col` (element-local array of nel*lx1^dim points):
+ *   axhelm : w = h1 * D^T G D u + h2 * bm1 * u                (hmholtz.f axhelm, no dssum)
+ *   dssum  : u <- QQ^T u  incl. the inter-rank exchange        (dssum / gs_op add)
+ *   col2   : u <- u * c with c = mask, binvm1, vmult or bm1    (col2)
+ *   ax     : axhelm + dssum + mask                             (Nek ax(w,x,h1,h2,n)) */
+int nsb_sem_axhelm(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout, int field,
+                   double h1, double h2);
+int nsb_sem_dssum(nsb_sem_t sem, nsb_basis_t b, int col, int field);
+int nsb_sem_col2(nsb_sem_t sem, nsb_basis_t b, int col, int field, int which);
+int nsb_sem_ax(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout, int field,
+               double h1, double h2);
+
+/* ---------------------------------------------------------------------------------------------
+ * Linear operator: the abstract_linop%matvec(vec_in, vec_out) boundary
+ * (core/linear_operators.f90:17-23, 39-44) / legacy matvec(f, q) (core/matvec.f90:56).
+ * ------------------------------------------------------------------------------------------- */
+/* Built-in device operator on every velocity-like field f in [0, nfields_apply):
+ *   out = alpha * in + beta * binvm1 * mask * dssum( h1 * A in + h2 * B in  [+ B (U . grad) in] )
+ * convection velocity (cx,cy,cz element-local arrays, or NULL for none) makes it non-symmetric
+ * (SURVEY.md section 8d operators M1 / M2). */
+int nsb_op_create_sem(nsb_sem_t sem, int nfields_apply, double alpha, double beta, double h1,
+                      double h2, const double *cx, const double *cy, const double *cz,
+                      nsb_op_t *op);
+/* Host operator: the reference's time-stepper (nek_advance on host arrays).  The callback gets
+ * host field pointers (layout order); the library downloads vec_in / uploads vec_out around it. */
+typedef int (*nsb_host_matvec_fn)(void *user, const double *const *in_fields, double in_time,
+                                  double *const *out_fields, double *out_time);
+int nsb_op_create_host(nsb_layout_t layout, nsb_host_matvec_fn fn, void *user, nsb_op_t *op);
+int nsb_op_destroy(nsb_op_t op);
+int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
+int nsb_op_count(nsb_op_t op, int64_t *napply);
+
+/* ---------------------------------------------------------------------------------------------
+ * Krylov drivers (host logic in C++, dense k x k step through the injected LAPACK).
+ * ------------------------------------------------------------------------------------------- */
+/* arnoldi_factorization(Q, H, mstart, mend, ksize) (core/krylov_decomposition.f90:2-99).
+ * Steps mstart..mend (0-based, inclusive): f = op(Q[m]); orthonormalise against Q[0..m];
+ * Q[m+1] = f; column m of H (ldh >= mend+2) is written.  H is host memory; the loop itself is
+ * device-resident (no host synchronisation until the end). */
+int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int orth_mode, double *H,
+                int ldh);
+
+/* LAPACK provider: raw Fortran-ABI entry points, as core/lapack_wrapper.f90 links them
+ * (dgeev :158, dgees :49, dtrsen :108, dgels :288).  The Fortran host passes c_funloc(dgeev)...;
+ * Python passes scipy's cython_lapack pointers. */
+int nsb_set_lapack(void *dgeev, void *dgees, void *dtrsen, void *dgels);
+/* lapack_wrapper mirrors (host, column-major):
+ *   eig   : dgeev + complexification + sort by decreasing |lambda| (:114-228);
+ *           vals/vecs interleaved (re,im) complex*16
+ *   schur : dgees('V','S', |lambda|>0.9) (:3-55), A overwritten by T
+ *   ordschur : dtrsen (:59-111);  lstsq : dgels (:248-300) */
+int nsb_eig(const double *A, int lda, int n, double *vecs_c16, double *vals_c16);
+int nsb_schur(double *A, int lda, int n, double *vecs, double *vals_c16);
+int nsb_ordschur(double *T, int ldt, double *Q, int ldq, const int *selected, int n);
+int nsb_lstsq(const double *A, int lda, int m, int n, const double *b, double *x);
+/* select_eigenvalues (core/eigensolvers.f90:688-754) */
+int nsb_select_eigenvalues(int *selected, int *cnt, const double *vals_c16, double delta, int nev,
+                           int n);
+/* schur_condensation(mstart, H, Q, ksize) (core/eigensolvers.f90:363-468); mstart in/out, 0-based
+ * index of the next Arnoldi step. */
+int nsb_schur_condensation(nsb_basis_t Q, int *mstart, double *H, int ldh, int ksize,
+                           double schur_del, int schur_tgt);
+/* krylov_schur (core/eigensolvers.f90:120-359): Q[0] must hold the unit-norm seed.
+ * Outputs: vals/vecs of H(1:k,1:k) sorted as eig() does, residual(k), number converged,
+ * number of Schur condensations, H ((k+1) x k, ldh). */
+int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur_tgt, double eigen_tol,
+                     double schur_del, int orth_mode, int max_restarts, double *H, int ldh,
+                     double *vals_c16, double *vecs_c16, double *residual, int *cnt,
+                     int *schur_cnt);
+/* ts_gmres(rhs, sol, maxiter, ksize, calls) (core/newton_krylov.f90:170-299).  rhs and sol are
+ * (basis, col) vectors; Q is the caller's Krylov basis with >= ksize+2 columns (last = work). */
+int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int crhs, nsb_basis_t bsol, int csol,
+                 int maxiter, int ksize, double tol, int orth_mode, int *calls,
+                 double *residual_hist, int *nhist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEKSTAB_B200_H */

@@ -1,0 +1,518 @@
+"""Host-side mirror of the reference's vector / operator / solver interface over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference so that tests read like its own
+routines (paths relative to the nekStab repository root):
+
+* ``nek_dvector``                      -- ``real_nek_vector`` (core/nek_vectors.f90:20-31) /
+                                          ``krylov_vector`` (core/krylov_subspace.f90:12-17)
+* ``k_dot, k_norm, k_normalize, ...``  -- core/krylov_subspace.f90:26-209
+* ``arnoldi_factorization``            -- core/krylov_decomposition.f90:2  (1-based mstart/mend)
+* ``krylov_schur, schur_condensation`` -- core/eigensolvers.f90:120, 363
+* ``ts_gmres``                         -- core/newton_krylov.f90:170
+* ``eig, schur, ordschur, lstsq``      -- core/lapack_wrapper.f90
+
+Everything computes on the GPU through libnekstab_b200.so; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, c_double_p, c_i64_p, c_int_p, c_dpp
+
+ORTH_MGS2_REF, ORTH_CGS2, ORTH_DGKS = 0, 1, 2
+AXPBY_SKIP_TIME = 1
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _f64(a, copy=False) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.copy() if copy else a
+
+
+# ------------------------------------------------------------------------------------------------
+# LAPACK provider: scipy's cython_lapack entry points (same routines as lapack_wrapper.f90)
+# ------------------------------------------------------------------------------------------------
+_lapack_set = False
+
+
+def set_lapack_from_scipy():
+    global _lapack_set
+    if _lapack_set:
+        return
+    import scipy.linalg.cython_lapack as cl
+    api = C.pythonapi
+    api.PyCapsule_GetName.restype = C.c_char_p
+    api.PyCapsule_GetName.argtypes = [C.py_object]
+    api.PyCapsule_GetPointer.restype = C.c_void_p
+    api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    ptrs = []
+    for name in ('dgeev', 'dgees', 'dtrsen', 'dgels'):
+        cap = cl.__pyx_capi__[name]
+        ptrs.append(api.PyCapsule_GetPointer(cap, api.PyCapsule_GetName(cap)))
+    check(_capi.load().nsb_set_lapack(*ptrs))
+    _lapack_set = True
+
+
+# ------------------------------------------------------------------------------------------------
+# context / layout / basis
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """One per process / GPU (the Nek rank)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, unique_id: Optional[bytes] = None):
+        self.lib = _capi.load()
+        h = C.c_void_p()
+        buf = None
+        if unique_id is not None:
+            buf = C.create_string_buffer(unique_id, 128)
+        check(self.lib.nsb_init(device, rank, nranks, buf, C.byref(h)))
+        self.h = h
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_capi.load().nsb_get_unique_id(buf))
+        return buf.raw
+
+    def sync(self):
+        check(self.lib.nsb_sync(self.h))
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(self.lib.nsb_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def timer_start(self):
+        check(self.lib.nsb_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        check(self.lib.nsb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(self.lib.nsb_flush_l2(self.h))
+
+    def allreduce(self, x: np.ndarray) -> np.ndarray:
+        x = _f64(x, copy=True).ravel()
+        check(self.lib.nsb_allreduce_host(self.h, _dp(x), x.size))
+        return x
+
+    def close(self):
+        if self.h:
+            self.lib.nsb_finalize(self.h)
+            self.h = None
+
+
+class Layout:
+    """Field lengths of one state vector {vx, vy, [vz], [pr], [t..]} + which enter the dot."""
+
+    def __init__(self, ctx: Context, field_len: Sequence[int], field_in_dot: Sequence[bool],
+                 time_in_dot: bool = False):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.field_len = [int(n) for n in field_len]
+        self.field_in_dot = [bool(b) for b in field_in_dot]
+        self.nfields = len(self.field_len)
+        fl = (C.c_int64 * self.nfields)(*self.field_len)
+        fd = (C.c_int * self.nfields)(*[int(b) for b in self.field_in_dot])
+        h = C.c_void_p()
+        check(self.lib.nsb_layout_create(ctx.h, self.nfields, fl, fd, int(time_in_dot), C.byref(h)))
+        self.h = h
+        ld, ndot, ndof = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.lib.nsb_layout_info(h, C.byref(ld), C.byref(ndot), C.byref(ndof)))
+        self.ld, self.ndot, self.ndof_dot = ld.value, ndot.value, ndof.value
+
+    def set_weight(self, weights: Sequence[np.ndarray]):
+        """One bm1s array per in-dot field (pass the same array several times to reuse it)."""
+        dot_fields = [i for i, b in enumerate(self.field_in_dot) if b]
+        if len(weights) != len(dot_fields):
+            raise ValueError(f'need {len(dot_fields)} weight arrays, got {len(weights)}')
+        keep = []
+        for w, f in zip(weights, dot_fields):
+            a = _f64(w).ravel()
+            if a.size != self.field_len[f]:
+                raise ValueError(f'weight for field {f} has {a.size} entries, expected {self.field_len[f]}')
+            keep.append(a)
+        arr = (c_double_p * len(keep))(*[_dp(a) for a in keep])
+        check(self.lib.nsb_layout_set_weight(self.h, arr))
+
+    def close(self):
+        if self.h:
+            self.lib.nsb_layout_destroy(self.h)
+            self.h = None
+
+
+class Basis:
+    """Device-resident column-major tall-skinny fp64 array; column c is the vector ``self[c]``."""
+
+    def __init__(self, layout: Layout, ncols: int):
+        self.layout, self.lib, self.ncols = layout, layout.lib, int(ncols)
+        h = C.c_void_p()
+        check(self.lib.nsb_basis_create(layout.h, self.ncols, C.byref(h)))
+        self.h = h
+
+    def __getitem__(self, col: int) -> 'nek_dvector':
+        if col < 0:
+            col += self.ncols
+        return nek_dvector(self, col)
+
+    def __len__(self):
+        return self.ncols
+
+    def col_ptr(self, col: int) -> int:
+        p = C.c_uint64()
+        check(self.lib.nsb_basis_col_ptr(self.h, col, C.byref(p)))
+        return p.value
+
+    def gram(self, k: int) -> np.ndarray:
+        G = np.zeros((k, k), order='F')
+        check(self.lib.nsb_basis_gram(self.h, k, _dp(G), k))
+        return G
+
+    def rotate(self, k: int, Z: np.ndarray, rotate_time: bool = False):
+        Zf = np.asfortranarray(Z, dtype=np.float64)
+        check(self.lib.nsb_basis_rotate(self.h, k, _dp(Zf), Zf.shape[0], int(rotate_time)))
+
+    def close(self):
+        if self.h:
+            self.lib.nsb_basis_destroy(self.h)
+            self.h = None
+
+
+class nek_dvector:
+    """A (basis, column) pair: the device vector with the reference's type-bound procedures."""
+
+    __slots__ = ('basis', 'col')
+
+    def __init__(self, basis: Basis, col: int):
+        self.basis, self.col = basis, col
+
+    # -- host transfer ------------------------------------------------------------------------
+    def upload(self, fields: Sequence[Optional[np.ndarray]], time: float = 0.0):
+        L = self.basis.layout
+        keep, ptrs = [], []
+        for f, n in zip(fields, L.field_len):
+            if f is None:
+                ptrs.append(None)
+                continue
+            a = _f64(f).ravel()
+            if a.size != n:
+                raise ValueError(f'field has {a.size} entries, layout expects {n}')
+            keep.append(a)
+            ptrs.append(_dp(a))
+        arr = (c_double_p * L.nfields)(*ptrs)
+        check(self.basis.lib.nsb_vec_upload(self.basis.h, self.col, arr, float(time)))
+        return self
+
+    def download(self):
+        L = self.basis.layout
+        out = [np.empty(n) for n in L.field_len]
+        arr = (c_double_p * L.nfields)(*[_dp(a) for a in out])
+        t = C.c_double()
+        check(self.basis.lib.nsb_vec_download(self.basis.h, self.col, arr, C.byref(t)))
+        return out, t.value
+
+    # -- type-bound procedures (core/nek_vectors.f90:27-30) -----------------------------------
+    def zero(self):
+        check(self.basis.lib.nsb_vec_zero(self.basis.h, self.col))
+
+    def dot(self, vec: 'nek_dvector') -> float:
+        a = C.c_double()
+        check(self.basis.lib.nsb_vec_dot(self.basis.h, self.col, vec.basis.h, vec.col, C.byref(a)))
+        return a.value
+
+    def norm(self) -> float:
+        a = C.c_double()
+        check(self.basis.lib.nsb_vec_norm(self.basis.h, self.col, C.byref(a)))
+        return a.value
+
+    def scal(self, alpha: float):
+        check(self.basis.lib.nsb_vec_scal(self.basis.h, self.col, float(alpha)))
+
+    def axpby(self, alpha: float, vec: 'nek_dvector', beta: float, skip_time: bool = True):
+        """self <- alpha*self + beta*vec; like real_axpby, %time is left alone by default."""
+        check(self.basis.lib.nsb_vec_axpby(self.basis.h, self.col, float(alpha), vec.basis.h, vec.col,
+                                           float(beta), AXPBY_SKIP_TIME if skip_time else 0))
+
+
+# -- legacy free functions (core/krylov_subspace.f90:26-209) -----------------------------------
+def k_dot(p: nek_dvector, q: nek_dvector) -> float:
+    return p.dot(q)
+
+
+def k_norm(p: nek_dvector) -> float:
+    return p.norm()
+
+
+def k_normalize(p: nek_dvector) -> float:
+    a = C.c_double()
+    check(p.basis.lib.nsb_vec_normalize(p.basis.h, p.col, C.byref(a)))
+    return a.value
+
+
+def k_cmult(p: nek_dvector, c: float):
+    p.scal(c)
+
+
+def k_add2(p: nek_dvector, q: nek_dvector):
+    check(p.basis.lib.nsb_vec_add2(p.basis.h, p.col, q.basis.h, q.col))
+
+
+def k_sub2(p: nek_dvector, q: nek_dvector):
+    check(p.basis.lib.nsb_vec_sub2(p.basis.h, p.col, q.basis.h, q.col))
+
+
+def k_sub3(p: nek_dvector, q: nek_dvector, r: nek_dvector):
+    check(p.basis.lib.nsb_vec_sub3(p.basis.h, p.col, q.basis.h, q.col, r.basis.h, r.col))
+
+
+def k_zero(p: nek_dvector):
+    p.zero()
+
+
+def k_copy(p: nek_dvector, q: nek_dvector):
+    """Destination first, like the reference."""
+    check(p.basis.lib.nsb_vec_copy(p.basis.h, p.col, q.basis.h, q.col))
+
+
+def k_matmul(dq: nek_dvector, Q: Basis, yvec: np.ndarray, k: int):
+    y = _f64(yvec).ravel()
+    check(Q.lib.nsb_basis_gemv(Q.h, int(k), _dp(y), dq.basis.h, dq.col))
+
+
+def orthonormalize(Q: Basis, k: int, col_w: int, mode: int = ORTH_CGS2):
+    """update_hessenberg_matrix on the device: returns (h[0..k], passes)."""
+    h = np.zeros(k + 1)
+    passes = C.c_int()
+    check(Q.lib.nsb_orthonormalize(Q.h, int(k), int(col_w), int(mode), _dp(h), C.byref(passes)))
+    return h, passes.value
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral-element mesh + operators
+# ------------------------------------------------------------------------------------------------
+def gll(N: int):
+    lib = _capi.load()
+    z, w, D = np.zeros(N + 1), np.zeros(N + 1), np.zeros((N + 1, N + 1), order='F')
+    check(lib.nsb_gll(N, _dp(z), _dp(w), _dp(D)))
+    return z, w, np.ascontiguousarray(D)  # D[i, j] = dxm1(i, j)
+
+
+class Sem:
+    """A mesh partition on the device: geometry, masks, gather-scatter lists."""
+
+    SEL = dict(bm1=0, jac=1, binvm1=2, vmult=3, mask=4, g1=10, g2=11, g3=12, g4=13, g5=14, g6=15)
+
+    def __init__(self, ctx: Context, N: int, x, y, z=None, mask=None, glo_num=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        x = _f64(x)
+        self.dim = 3 if z is not None else 2
+        self.N, self.lx = N, N + 1
+        self.shape = x.shape
+        self.nel = x.shape[0]
+        glo = np.ascontiguousarray(glo_num, dtype=np.int64)
+        h = C.c_void_p()
+        check(self.lib.nsb_sem_create(ctx.h, self.dim, N, self.nel, _dp(x), _dp(_f64(y)),
+                                      _dp(_f64(z)) if z is not None else None,
+                                      _dp(_f64(mask)) if mask is not None else None,
+                                      glo.ctypes.data_as(c_i64_p), C.byref(h)))
+        self.h = h
+        self.npts = self.lib.nsb_sem_npts(h)
+
+    def setup_exchange(self):
+        check(self.lib.nsb_sem_setup_exchange(self.h))
+
+    def get(self, name: str) -> np.ndarray:
+        out = np.empty(self.npts)
+        check(self.lib.nsb_sem_get(self.h, self.SEL[name], _dp(out)))
+        return out.reshape(self.shape)
+
+    def axhelm(self, vin: nek_dvector, vout: nek_dvector, field: int, h1: float, h2: float):
+        check(self.lib.nsb_sem_axhelm(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col, field, h1, h2))
+
+    def dssum(self, v: nek_dvector, field: int):
+        check(self.lib.nsb_sem_dssum(self.h, v.basis.h, v.col, field))
+
+    def col2(self, v: nek_dvector, field: int, which: str):
+        check(self.lib.nsb_sem_col2(self.h, v.basis.h, v.col, field, self.SEL[which]))
+
+    def ax(self, vin: nek_dvector, vout: nek_dvector, field: int, h1: float, h2: float):
+        check(self.lib.nsb_sem_ax(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col, field, h1, h2))
+
+    def close(self):
+        if self.h:
+            self.lib.nsb_sem_destroy(self.h)
+            self.h = None
+
+
+class LinearOperator:
+    """abstract_linop: ``matvec(vec_in, vec_out)`` (core/linear_operators.f90:17-23)."""
+
+    def __init__(self, lib, h, keep=None):
+        self.lib, self.h, self._keep = lib, h, keep
+
+    def matvec(self, vec_in: nek_dvector, vec_out: nek_dvector):
+        check(self.lib.nsb_op_apply(self.h, vec_in.basis.h, vec_in.col, vec_out.basis.h, vec_out.col))
+
+    def count(self) -> int:
+        n = C.c_int64()
+        check(self.lib.nsb_op_count(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            self.lib.nsb_op_destroy(self.h)
+            self.h = None
+
+
+def sem_operator(sem: Sem, nfields: int, alpha: float, beta: float, h1: float, h2: float,
+                 conv=None) -> LinearOperator:
+    """out = alpha*in + beta * binvm1*mask*dssum(h1 A in + h2 B in [+ B (c.grad) in])."""
+    h = C.c_void_p()
+    cs = [None, None, None]
+    keep = []
+    if conv is not None:
+        for i, c in enumerate(conv):
+            a = _f64(c)
+            keep.append(a)
+            cs[i] = _dp(a)
+    check(sem.lib.nsb_op_create_sem(sem.h, nfields, alpha, beta, h1, h2, cs[0], cs[1], cs[2], C.byref(h)))
+    return LinearOperator(sem.lib, h, keep)
+
+
+def host_operator(layout: Layout, fn) -> LinearOperator:
+    """Wrap a host matvec ``fn(fields_in, time_in) -> (fields_out, time_out)`` (the reference's
+    time-stepper lives on the host); vectors cross PCIe around every call."""
+    lens = layout.field_len
+
+    def tramp(user, pin, tin, pout, tout):
+        try:
+            fin = [np.ctypeslib.as_array(pin[i], shape=(lens[i],)) for i in range(len(lens))]
+            res, t = fn(fin, tin)
+            for i in range(len(lens)):
+                np.ctypeslib.as_array(pout[i], shape=(lens[i],))[:] = np.asarray(res[i]).ravel()
+            tout[0] = t
+            return 0
+        except Exception:  # noqa: BLE001  (must not propagate through the C frame)
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cb = _capi.HOST_MATVEC(tramp)
+    h = C.c_void_p()
+    check(layout.lib.nsb_op_create_host(layout.h, cb, None, C.byref(h)))
+    return LinearOperator(layout.lib, h, keep=cb)
+
+
+# ------------------------------------------------------------------------------------------------
+# solvers
+# ------------------------------------------------------------------------------------------------
+def arnoldi_factorization(Q: Basis, H: np.ndarray, mstart: int, mend: int, ksize: int,
+                          op: LinearOperator, orth_mode: int = ORTH_CGS2):
+    """core/krylov_decomposition.f90:2 -- 1-based mstart/mend like the reference; H is a Fortran-
+    ordered (ksize+1, ksize) array updated in place."""
+    if ksize == 0:
+        raise ValueError('Krylov base dimension == 0! Increase it.')
+    if not (H.flags.f_contiguous and H.dtype == np.float64):
+        raise ValueError('H must be a Fortran-ordered float64 array')
+    check(Q.lib.nsb_arnoldi(Q.h, op.h, mstart - 1, mend - 1, orth_mode, _dp(H), H.shape[0]))
+
+
+def eig(A: np.ndarray):
+    set_lapack_from_scipy()
+    n = A.shape[0]
+    Af = np.asfortranarray(A, dtype=np.float64)
+    vecs = np.zeros((n, n), dtype=np.complex128, order='F')
+    vals = np.zeros(n, dtype=np.complex128)
+    check(_capi.load().nsb_eig(_dp(Af), n, n, vecs.ctypes.data_as(c_double_p), vals.ctypes.data_as(c_double_p)))
+    return vecs, vals
+
+
+def schur(A: np.ndarray):
+    set_lapack_from_scipy()
+    n = A.shape[0]
+    T = np.array(A, dtype=np.float64, order='F')
+    vecs = np.zeros((n, n), order='F')
+    vals = np.zeros(n, dtype=np.complex128)
+    check(_capi.load().nsb_schur(_dp(T), n, n, _dp(vecs), vals.ctypes.data_as(c_double_p)))
+    return T, vecs, vals
+
+
+def ordschur(T: np.ndarray, Qm: np.ndarray, selected):
+    set_lapack_from_scipy()
+    n = T.shape[0]
+    Tf = np.array(T, dtype=np.float64, order='F')
+    Qf = np.array(Qm, dtype=np.float64, order='F')
+    sel = np.ascontiguousarray(selected, dtype=np.int32)
+    check(_capi.load().nsb_ordschur(_dp(Tf), n, _dp(Qf), n, sel.ctypes.data_as(c_int_p), n))
+    return Tf, Qf
+
+
+def lstsq(A: np.ndarray, b: np.ndarray):
+    set_lapack_from_scipy()
+    m, n = A.shape
+    Af = np.asfortranarray(A, dtype=np.float64)
+    bb = _f64(b)
+    x = np.zeros(n)
+    check(_capi.load().nsb_lstsq(_dp(Af), m, m, n, _dp(bb), _dp(x)))
+    return x
+
+
+def select_eigenvalues(vals: np.ndarray, delta: float, nev: int):
+    v = np.ascontiguousarray(vals, dtype=np.complex128)
+    n = v.size
+    sel = np.zeros(n, dtype=np.int32)
+    cnt = C.c_int()
+    check(_capi.load().nsb_select_eigenvalues(sel.ctypes.data_as(c_int_p), C.byref(cnt),
+                                              v.ctypes.data_as(c_double_p), delta, nev, n))
+    return sel.astype(bool), cnt.value
+
+
+def schur_condensation(mstart: int, H: np.ndarray, Q: Basis, ksize: int, schur_del: float,
+                       schur_tgt: int) -> int:
+    """core/eigensolvers.f90:363 -- returns the new 1-based mstart."""
+    set_lapack_from_scipy()
+    m = C.c_int(mstart - 1)
+    check(Q.lib.nsb_schur_condensation(Q.h, C.byref(m), _dp(H), H.shape[0], ksize, schur_del, schur_tgt))
+    return m.value + 1
+
+
+class KSResult:
+    def __init__(self, vals, vecs, residual, cnt, schur_cnt, H):
+        self.vals, self.vecs, self.residual, self.cnt, self.schur_cnt, self.H = \
+            vals, vecs, residual, cnt, schur_cnt, H
+
+
+def krylov_schur(Q: Basis, op: LinearOperator, k_dim: int = 100, schur_tgt: int = 2,
+                 eigen_tol: float = 1e-6, schur_del: float = 0.10, orth_mode: int = ORTH_CGS2,
+                 max_restarts: int = 200) -> KSResult:
+    """core/eigensolvers.f90:120 -- Q[0] holds the unit-norm seed (defaults: core/main.f90:9-31)."""
+    set_lapack_from_scipy()
+    H = np.zeros((k_dim + 1, k_dim), order='F')
+    vals = np.zeros(k_dim, dtype=np.complex128)
+    vecs = np.zeros((k_dim, k_dim), dtype=np.complex128, order='F')
+    res = np.zeros(k_dim)
+    cnt, scnt = C.c_int(), C.c_int()
+    check(Q.lib.nsb_krylov_schur(Q.h, op.h, k_dim, schur_tgt, eigen_tol, schur_del, orth_mode,
+                                 max_restarts, _dp(H), k_dim + 1, vals.ctypes.data_as(c_double_p),
+                                 vecs.ctypes.data_as(c_double_p), _dp(res), C.byref(cnt), C.byref(scnt)))
+    return KSResult(vals, vecs, res, cnt.value, scnt.value, H)
+
+
+def ts_gmres(Q: Basis, op: LinearOperator, rhs: nek_dvector, sol: nek_dvector, maxiter: int,
+             ksize: int, tol: float, orth_mode: int = ORTH_CGS2):
+    """core/newton_krylov.f90:170 -- returns (residual history, calls)."""
+    set_lapack_from_scipy()
+    hist = np.zeros(maxiter)
+    calls, nh = C.c_int(), C.c_int()
+    check(Q.lib.nsb_ts_gmres(Q.h, op.h, rhs.basis.h, rhs.col, sol.basis.h, sol.col, maxiter, ksize,
+                             tol, orth_mode, C.byref(calls), _dp(hist), C.byref(nh)))
+    return hist[:nh.value].copy(), calls.value

@@ -1,0 +1,200 @@
+// Inter-GPU communication: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// Replaces the reference's MPI layer reached through Nek5000: gop -> MPI_Allreduce inside glsc3
+// (core/nek_vectors.f90:7-12, 94-102) and gslib's pairwise exchange inside dssum
+// (core/utils.f90:287, 338).  NCCL is dlopen'ed on first use so a single-GPU process never needs
+// it; the communicator is bootstrapped from an ncclUniqueId the host broadcasts with its own
+// transport (MPI_Bcast in Nek, torch.distributed in the Python tests).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "nsb_internal.h"
+
+namespace nsb {
+
+struct Nccl {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+static Nccl g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return NSB_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) {
+    set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+    return NSB_ENCCL;
+  }
+#define SYM(field, name)                                         \
+  do {                                                           \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                \
+    if (!g_nccl.field) {                                         \
+      set_error("NCCL symbol %s missing", name);                 \
+      return NSB_ENCCL;                                          \
+    }                                                            \
+  } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GetErrorString, "ncclGetErrorString");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+#undef SYM
+  g_nccl.lib = lib;
+  return NSB_OK;
+}
+
+#define NSB_NCCL(call)                                                                        \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess) {                                                                  \
+      set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_));       \
+      return NSB_ENCCL;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+int comm_init(nsb_context_t ctx, const void *unique_id) {
+  NSB_CHECK(load_nccl());
+  static_assert(sizeof(ncclUniqueId) <= NSB_UNIQUE_ID_BYTES, "unique id size");
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  ncclComm_t comm;
+  cudaSetDevice(ctx->device);
+  NSB_NCCL(g_nccl.CommInitRank(&comm, ctx->nranks, id, ctx->rank));
+  ctx->nccl_comm = comm;
+  return NSB_OK;
+}
+
+int comm_destroy(nsb_context_t ctx) {
+  if (ctx->nccl_comm && g_nccl.lib) {
+    g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  return NSB_OK;
+}
+
+int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n) {
+  if (ctx->nranks == 1 || n == 0) return NSB_OK;
+  NSB_REQUIRE(ctx->nccl_comm, "allreduce: no communicator");
+  NSB_NCCL(g_nccl.AllReduce(buf_d, buf_d, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm,
+                            ctx->stream));
+  return NSB_OK;
+}
+
+int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers) {
+  if (peers.empty()) return NSB_OK;
+  NSB_REQUIRE(ctx->nccl_comm, "sendrecv: no communicator");
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  NSB_NCCL(g_nccl.GroupStart());
+  for (const auto &P : peers) {
+    NSB_NCCL(g_nccl.Send(P.send_d, (size_t)P.n, ncclDouble, P.rank, comm, ctx->stream));
+    NSB_NCCL(g_nccl.Recv(P.recv_d, (size_t)P.n, ncclDouble, P.rank, comm, ctx->stream));
+  }
+  NSB_NCCL(g_nccl.GroupEnd());
+  return NSB_OK;
+}
+
+// Discover which gather-scatter nodes are shared with which rank: all-gather the (sorted) global
+// ids of every rank's nodes and intersect.  Both sides order a pair's nodes by global id, so the
+// packed buffers line up without further negotiation.
+int exchange_setup(nsb_sem_t S) {
+  nsb_context_t ctx = S->ctx;
+  NSB_REQUIRE(ctx->nccl_comm, "exchange_setup: no communicator");
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  cudaSetDevice(ctx->device);
+  const int P = ctx->nranks;
+  // 1. counts
+  int64_t *cnt_d = nullptr;
+  NSB_CUDA(cudaMalloc(&cnt_d, sizeof(int64_t) * (P + 1)));
+  int64_t mine = S->nshared;
+  NSB_CUDA(cudaMemcpyAsync(cnt_d + P, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  NSB_NCCL(g_nccl.AllGather(cnt_d + P, cnt_d, 1, ncclInt64, comm, ctx->stream));
+  std::vector<int64_t> cnt(P);
+  NSB_CUDA(cudaMemcpyAsync(cnt.data(), cnt_d, sizeof(int64_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(cnt_d);
+  const int64_t mx = std::max<int64_t>(1, *std::max_element(cnt.begin(), cnt.end()));
+  // 2. sorted ids (with their gs-node index)
+  std::vector<std::pair<int64_t, int32_t>> my(S->nshared);
+  for (int64_t n = 0; n < S->nshared; ++n) my[n] = {S->node_gid[n], (int32_t)n};
+  std::sort(my.begin(), my.end());
+  std::vector<int64_t> send(mx, -1);
+  for (int64_t n = 0; n < S->nshared; ++n) send[n] = my[n].first;
+  int64_t *send_d = nullptr, *all_d = nullptr;
+  NSB_CUDA(cudaMalloc(&send_d, sizeof(int64_t) * mx));
+  NSB_CUDA(cudaMalloc(&all_d, sizeof(int64_t) * mx * P));
+  NSB_CUDA(cudaMemcpyAsync(send_d, send.data(), sizeof(int64_t) * mx, cudaMemcpyHostToDevice, ctx->stream));
+  NSB_NCCL(g_nccl.AllGather(send_d, all_d, (size_t)mx, ncclInt64, comm, ctx->stream));
+  std::vector<int64_t> all((size_t)mx * P);
+  NSB_CUDA(cudaMemcpyAsync(all.data(), all_d, sizeof(int64_t) * mx * P, cudaMemcpyDeviceToHost, ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(send_d);
+  cudaFree(all_d);
+  // 3. intersect
+  for (auto &Pr : S->peers) {
+    cudaFree(Pr.idx_d);
+    cudaFree(Pr.send_d);
+    cudaFree(Pr.recv_d);
+  }
+  S->peers.clear();
+  for (int r = 0; r < P; ++r) {
+    if (r == ctx->rank) continue;
+    const int64_t *other = all.data() + (size_t)r * mx;
+    std::vector<int32_t> nodes;
+    int64_t a = 0, b = 0;
+    while (a < S->nshared && b < cnt[r]) {
+      if (my[a].first < other[b]) ++a;
+      else if (my[a].first > other[b]) ++b;
+      else { nodes.push_back(my[a].second); ++a; ++b; }
+    }
+    if (nodes.empty()) continue;
+    nsb_sem_s::Peer Pr;
+    Pr.rank = r;
+    Pr.n = (int64_t)nodes.size();
+    NSB_CUDA(cudaMalloc(&Pr.idx_d, sizeof(int32_t) * Pr.n));
+    NSB_CUDA(cudaMalloc(&Pr.send_d, sizeof(double) * Pr.n));
+    NSB_CUDA(cudaMalloc(&Pr.recv_d, sizeof(double) * Pr.n));
+    NSB_CUDA(cudaMemcpy(Pr.idx_d, nodes.data(), sizeof(int32_t) * Pr.n, cudaMemcpyHostToDevice));
+    S->peers.push_back(Pr);
+  }
+  return NSB_OK;
+}
+
+}  // namespace nsb
+
+extern "C" int nsb_get_unique_id(void *id_out) {
+  NSB_REQUIRE(id_out, "nsb_get_unique_id: NULL");
+  NSB_CHECK(nsb::load_nccl());
+  ncclUniqueId id;
+  ncclResult_t r = nsb::g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) {
+    nsb::set_error("ncclGetUniqueId: %s", nsb::g_nccl.GetErrorString(r));
+    return NSB_ENCCL;
+  }
+  memset(id_out, 0, NSB_UNIQUE_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return NSB_OK;
+}

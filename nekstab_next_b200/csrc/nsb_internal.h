@@ -1,0 +1,138 @@
+// Internal structures shared by the translation units of libnekstab_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "nekstab_b200.h"
+
+namespace nsb {
+
+void set_error(const char *fmt, ...);
+
+#define NSB_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      nsb::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return NSB_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define NSB_CHECK(call)      \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != NSB_OK) return r_; \
+  } while (0)
+
+#define NSB_REQUIRE(cond, ...)     \
+  do {                             \
+    if (!(cond)) {                 \
+      nsb::set_error(__VA_ARGS__); \
+      return NSB_EINVAL;           \
+    }                              \
+  } while (0)
+
+constexpr int kRowPad = 1024;   // every region of a column is padded to this many rows
+constexpr int kMaxK = 1024;     // largest number of columns one orthogonalisation handles
+constexpr int kNumSM = 148;     // B200
+
+struct Nccl;  // dlopen'ed NCCL entry points (nsb_comm.cu)
+
+}  // namespace nsb
+
+struct nsb_context_s {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  int num_sms = nsb::kNumSM;
+  void *nccl_comm = nullptr;  // ncclComm_t
+  // scratch for reductions: partial sums [max_ctas][kMaxK+1], results, flags
+  double *partial_d = nullptr;
+  int64_t partial_rows = 0;
+  double *hvec_d = nullptr;    // 4 x (kMaxK+8): h1, h2, hsum, scalars
+  double *hpin = nullptr;      // pinned mirror
+  double *flush_d = nullptr;
+  size_t flush_bytes = 0;
+};
+
+struct nsb_layout_s {
+  nsb_context_t ctx = nullptr;
+  int nfields = 0;
+  std::vector<int64_t> len;      // active length of each field
+  std::vector<int> in_dot;
+  std::vector<int64_t> off;      // row offset of each field inside a column
+  int time_in_dot = 0;
+  int64_t time_row = 0;          // row holding %time
+  int64_t ndot = 0;              // rows [0, ndot) are covered by the inner product (padded)
+  int64_t ld = 0;                // rows of a column (padded)
+  int64_t ndof_dot = 0;          // unpadded dofs in the inner product
+  double *w_d = nullptr;         // weight, ndot rows (zeros on pads)
+};
+
+struct nsb_basis_s {
+  nsb_layout_t lay = nullptr;
+  int ncols = 0;
+  double *v_d = nullptr;         // [ld * ncols]
+  inline double *col(int c) const { return v_d + (size_t)c * (size_t)lay->ld; }
+};
+
+struct nsb_sem_s {
+  nsb_context_t ctx = nullptr;
+  int dim = 3, N = 7, lx = 8;
+  int64_t nel = 0, npts = 0;
+  int ng = 6;                    // geometric factors per point (6 in 3-D, 3 in 2-D)
+  double *g_d = nullptr;         // [ng][npts]  G1..G6  (2-D: G1, G2, G4)
+  double *bm1_d = nullptr, *jac_d = nullptr, *binv_d = nullptr, *vmult_d = nullptr,
+         *mask_d = nullptr, *bmask_d = nullptr;  // bmask = binvm1 * mask
+  double *rst_d = nullptr;       // [dim*dim][npts] rx..tz (times jac), for the convective term
+  double *D_d = nullptr;         // (N+1)^2, D[i + lx*j] = dxm1(i,j)
+  std::vector<double> D_h, z_h, w_h;
+  // gather-scatter: unique nodes owning >= 1 element-boundary point, CSR
+  int64_t nshared = 0;           // number of such nodes (local)
+  int64_t *gs_off_d = nullptr;   // [nshared+1]
+  int32_t *gs_idx_d = nullptr;   // local point indices
+  int64_t gs_nnz = 0;
+  double *node_sum_d = nullptr;  // [nshared] scratch for the multi-rank path
+  std::vector<int64_t> node_gid; // global id of each gs node
+  // inter-rank exchange (nsb_sem.cu / nsb_comm.cu)
+  struct Peer {
+    int rank;
+    int64_t n;                   // shared nodes with that rank
+    int32_t *idx_d;              // gs-node index of every node shared with that rank (sorted by gid)
+    double *send_d, *recv_d;
+  };
+  std::vector<Peer> peers;
+  std::vector<int64_t> glo_h;    // kept for exchange setup
+  bool exchange_ready = false;
+};
+
+struct nsb_op_s {
+  int kind = 0;                  // 0 sem, 1 host callback
+  nsb_sem_t sem = nullptr;
+  int nfields_apply = 0;
+  double alpha = 0, beta = 1, h1 = 1, h2 = 0;
+  double *c_d = nullptr;         // [dim][npts] convecting velocity or null
+  nsb_layout_t lay = nullptr;
+  nsb_host_matvec_fn fn = nullptr;
+  void *user = nullptr;
+  std::vector<std::vector<double>> hin, hout;
+  int64_t napply = 0;
+};
+
+namespace nsb {
+// implemented in nsb_core.cu
+int ensure_partial(nsb_context_t ctx, int64_t rows);
+// implemented in nsb_comm.cu
+int comm_init(nsb_context_t ctx, const void *unique_id);
+int comm_destroy(nsb_context_t ctx);
+int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n);  // on ctx->stream, in place
+int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers);
+int exchange_setup(nsb_sem_t sem);
+// implemented in nsb_orth.cu
+int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d);
+}  // namespace nsb

@@ -1,0 +1,360 @@
+// Host-side Krylov drivers over the device-resident basis: Arnoldi, Krylov-Schur, GMRES, and the
+// lapack_wrapper mirror.  The k x k dense step stays on the host through LAPACK, as in the
+// reference (core/lapack_wrapper.f90); the LAPACK entry points are injected by the host program
+// (nsb_set_lapack) because this library must not depend on a particular BLAS/LAPACK build.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "nsb_internal.h"
+
+using namespace nsb;
+
+// ------------------------------------------------------------------------------------------------
+// LAPACK provider (Fortran ABI; trailing hidden character lengths are passed and ignored by C
+// wrappers such as scipy's cython_lapack)
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef int (*select2_fn)(double *, double *);
+typedef void (*dgeev_fn)(char *, char *, int *, double *, int *, double *, double *, double *, int *,
+                         double *, int *, double *, int *, int *, size_t, size_t);
+typedef void (*dgees_fn)(char *, char *, select2_fn, int *, double *, int *, int *, double *, double *,
+                         double *, int *, double *, int *, int *, int *, size_t, size_t);
+typedef void (*dtrsen_fn)(char *, char *, int *, int *, double *, int *, double *, int *, double *,
+                          double *, int *, double *, double *, double *, int *, int *, int *, int *,
+                          size_t, size_t);
+typedef void (*dgels_fn)(char *, int *, int *, int *, double *, int *, double *, int *, double *, int *,
+                         int *, size_t);
+dgeev_fn p_dgeev = nullptr;
+dgees_fn p_dgees = nullptr;
+dtrsen_fn p_dtrsen = nullptr;
+dgels_fn p_dgels = nullptr;
+
+int need_lapack(void *p, const char *name) {
+  if (!p) {
+    set_error("%s: no LAPACK provider registered; call nsb_set_lapack first", name);
+    return NSB_ELAPACK;
+  }
+  return NSB_OK;
+}
+
+// core/lapack_wrapper.f90:232-244
+int select_eigvals(double *wr, double *wi) { return std::sqrt(*wr * *wr + *wi * *wi) > 0.9; }
+}  // namespace
+
+extern "C" int nsb_set_lapack(void *dgeev, void *dgees, void *dtrsen, void *dgels) {
+  p_dgeev = (dgeev_fn)dgeev;
+  p_dgees = (dgees_fn)dgees;
+  p_dtrsen = (dtrsen_fn)dtrsen;
+  p_dgels = (dgels_fn)dgels;
+  return NSB_OK;
+}
+
+// core/lapack_wrapper.f90:114-228
+extern "C" int nsb_eig(const double *A, int lda, int n, double *vecs_c16, double *vals_c16) {
+  NSB_REQUIRE(A && vecs_c16 && vals_c16 && n >= 1 && lda >= n, "nsb_eig: bad argument");
+  NSB_CHECK(need_lapack((void *)p_dgeev, "nsb_eig"));
+  std::vector<double> At((size_t)n * n), wr(n), wi(n), vr((size_t)n * n), vl(1);
+  for (int j = 0; j < n; ++j) memcpy(&At[(size_t)j * n], A + (size_t)j * lda, sizeof(double) * n);
+  char jobvl = 'N', jobvr = 'V';
+  int ldvl = 1, ldvr = n, lwork = -1, info = 0, nn = n;
+  double wq = 0;
+  p_dgeev(&jobvl, &jobvr, &nn, At.data(), &nn, wr.data(), wi.data(), vl.data(), &ldvl, vr.data(), &ldvr,
+          &wq, &lwork, &info, 1, 1);
+  lwork = std::max(4 * n, (int)wq);
+  std::vector<double> work(lwork);
+  p_dgeev(&jobvl, &jobvr, &nn, At.data(), &nn, wr.data(), wi.data(), vl.data(), &ldvl, vr.data(), &ldvr,
+          work.data(), &lwork, &info, 1, 1);
+  if (info != 0) {
+    set_error("nsb_eig: dgeev info=%d", info);
+    return NSB_ELAPACK;
+  }
+  typedef std::complex<double> cd;
+  std::vector<cd> vals(n), vecs((size_t)n * n);
+  for (int i = 0; i < n; ++i) vals[i] = cd(wr[i], wi[i]);
+  for (size_t t = 0; t < (size_t)n * n; ++t) vecs[t] = cd(vr[t], 0.0);
+  for (int i = 0; i < n - 1; ++i) {  // :167-173
+    if (wi[i] > 0) {
+      for (int r = 0; r < n; ++r) {
+        vecs[(size_t)i * n + r] = cd(vr[(size_t)i * n + r], vr[(size_t)(i + 1) * n + r]);
+        vecs[(size_t)(i + 1) * n + r] = cd(vr[(size_t)i * n + r], -vr[(size_t)(i + 1) * n + r]);
+      }
+    } else if (wi[i] == 0) {
+      for (int r = 0; r < n; ++r) vecs[(size_t)i * n + r] = cd(vr[(size_t)i * n + r], 0.0);
+    }
+  }
+  // sort_eigendecomp :181-228 (exchange sort, decreasing magnitude)
+  std::vector<double> nrm(n);
+  for (int i = 0; i < n; ++i) nrm[i] = std::sqrt(vals[i].real() * vals[i].real() + vals[i].imag() * vals[i].imag());
+  for (int k = 0; k < n - 1; ++k)
+    for (int l = k + 1; l < n; ++l)
+      if (nrm[k] < nrm[l]) {
+        std::swap(nrm[k], nrm[l]);
+        std::swap(vals[k], vals[l]);
+        for (int r = 0; r < n; ++r) std::swap(vecs[(size_t)k * n + r], vecs[(size_t)l * n + r]);
+      }
+  memcpy(vals_c16, vals.data(), sizeof(cd) * n);
+  memcpy(vecs_c16, vecs.data(), sizeof(cd) * n * n);
+  return NSB_OK;
+}
+
+// core/lapack_wrapper.f90:3-55
+extern "C" int nsb_schur(double *A, int lda, int n, double *vecs, double *vals_c16) {
+  NSB_REQUIRE(A && vecs && vals_c16 && n >= 1 && lda >= n, "nsb_schur: bad argument");
+  NSB_CHECK(need_lapack((void *)p_dgees, "nsb_schur"));
+  char jobvs = 'V', sort = 'S';
+  int nn = n, ld = lda, sdim = 0, ldvs = n, lwork = -1, info = 0;
+  std::vector<double> wr(n), wi(n);
+  std::vector<int> bwork(n);
+  double wq = 0;
+  p_dgees(&jobvs, &sort, select_eigvals, &nn, A, &ld, &sdim, wr.data(), wi.data(), vecs, &ldvs, &wq,
+          &lwork, bwork.data(), &info, 1, 1);
+  lwork = std::max(3 * n, (int)wq);
+  std::vector<double> work(lwork);
+  p_dgees(&jobvs, &sort, select_eigvals, &nn, A, &ld, &sdim, wr.data(), wi.data(), vecs, &ldvs,
+          work.data(), &lwork, bwork.data(), &info, 1, 1);
+  // info = n+2 only says the reordered eigenvalues changed their selection status after
+  // roundoff; the factorisation is still valid (the reference ignores info altogether).
+  if (info != 0 && info != n + 2) {
+    set_error("nsb_schur: dgees info=%d", info);
+    return NSB_ELAPACK;
+  }
+  for (int i = 0; i < n; ++i) {
+    vals_c16[2 * i] = wr[i];
+    vals_c16[2 * i + 1] = wi[i];
+  }
+  return NSB_OK;
+}
+
+// core/lapack_wrapper.f90:59-111
+extern "C" int nsb_ordschur(double *T, int ldt, double *Q, int ldq, const int *selected, int n) {
+  NSB_REQUIRE(T && Q && selected && n >= 1 && ldt >= n && ldq >= n, "nsb_ordschur: bad argument");
+  NSB_CHECK(need_lapack((void *)p_dtrsen, "nsb_ordschur"));
+  char job = 'N', compq = 'V';
+  int nn = n, lt = ldt, lq = ldq, m = 0, lwork = std::max(1, n), liwork = 1, info = 0;
+  double s = 0, sep = 0;
+  std::vector<double> wr(n), wi(n), work(lwork);
+  std::vector<int> sel(selected, selected + n), iwork(1);
+  p_dtrsen(&job, &compq, sel.data(), &nn, T, &lt, Q, &lq, wr.data(), wi.data(), &m, &s, &sep,
+           work.data(), &lwork, iwork.data(), &liwork, &info, 1, 1);
+  if (info != 0) {
+    set_error("nsb_ordschur: dtrsen info=%d", info);
+    return NSB_ELAPACK;
+  }
+  return NSB_OK;
+}
+
+// core/lapack_wrapper.f90:248-300
+extern "C" int nsb_lstsq(const double *A, int lda, int m, int n, const double *b, double *x) {
+  NSB_REQUIRE(A && b && x && m >= n && n >= 1 && lda >= m, "nsb_lstsq: bad argument");
+  NSB_CHECK(need_lapack((void *)p_dgels, "nsb_lstsq"));
+  std::vector<double> At((size_t)m * n), bt(b, b + m);
+  for (int j = 0; j < n; ++j) memcpy(&At[(size_t)j * m], A + (size_t)j * lda, sizeof(double) * m);
+  char trans = 'N';
+  int mm = m, nn = n, nrhs = 1, ldb = m, lwork = -1, info = 0;
+  double wq = 0;
+  p_dgels(&trans, &mm, &nn, &nrhs, At.data(), &mm, bt.data(), &ldb, &wq, &lwork, &info, 1);
+  lwork = std::max(2 * m * n, (int)wq);
+  std::vector<double> work(lwork);
+  p_dgels(&trans, &mm, &nn, &nrhs, At.data(), &mm, bt.data(), &ldb, work.data(), &lwork, &info, 1);
+  if (info != 0) {
+    set_error("nsb_lstsq: dgels info=%d", info);
+    return NSB_ELAPACK;
+  }
+  memcpy(x, bt.data(), sizeof(double) * n);
+  return NSB_OK;
+}
+
+// core/eigensolvers.f90:688-754
+extern "C" int nsb_select_eigenvalues(int *selected, int *cnt, const double *vals_c16, double delta,
+                                      int nev, int n) {
+  NSB_REQUIRE(selected && cnt && vals_c16, "nsb_select_eigenvalues: NULL argument");
+  NSB_REQUIRE(nev >= 0 && n >= nev + 5, "nsb_select_eigenvalues: need n >= nev+5 (n=%d, nev=%d)", n, nev);
+  std::vector<double> mag(n);
+  for (int i = 0; i < n; ++i) mag[i] = std::hypot(vals_c16[2 * i], vals_c16[2 * i + 1]);
+  std::vector<int> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return mag[a] < mag[b]; });  // quicksort2, ascending
+  for (int i = 0; i < n; ++i) selected[i] = mag[i] >= (1.0 - delta);                         // :743
+  for (int q = n - (nev + 3) - 1; q < n; ++q) selected[idx[q]] = 1;                          // :746
+  const double a = vals_c16[2 * idx[n - (nev + 3) - 1] + 1], b = vals_c16[2 * idx[n - (nev + 4) - 1] + 1];
+  if (a == -b) selected[idx[n - (nev + 4) - 1]] = 1;                                         // :747-749
+  int c = 0;
+  for (int i = 0; i < n; ++i) c += selected[i] ? 1 : 0;
+  *cnt = c;
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arnoldi  (core/krylov_decomposition.f90:2-99)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int orth_mode, double *H,
+                           int ldh) {
+  NSB_REQUIRE(Q && op && H, "nsb_arnoldi: NULL argument");
+  NSB_REQUIRE(mstart >= 0 && mend >= mstart && mend + 1 < Q->ncols,
+              "nsb_arnoldi: steps %d..%d need %d columns, basis has %d", mstart, mend, mend + 2, Q->ncols);
+  NSB_REQUIRE(ldh >= mend + 2, "nsb_arnoldi: ldh=%d < %d", ldh, mend + 2);
+  NSB_REQUIRE(mend + 1 <= kMaxK, "nsb_arnoldi: Krylov dimension above %d", kMaxK);
+  nsb_context_t ctx = Q->lay->ctx;
+  const int nsteps = mend - mstart + 1;
+  const bool async = (orth_mode == NSB_ORTH_CGS2 || orth_mode == NSB_ORTH_MGS2_REF) && op->kind == 0;
+  const size_t stride = (size_t)mend + 2;
+  double *hbuf = nullptr;
+  if (async) NSB_CHECK(nsb_host_alloc((void **)&hbuf, (int64_t)(sizeof(double) * stride * nsteps)));
+  int rc = NSB_OK;
+  for (int m = mstart; m <= mend && rc == NSB_OK; ++m) {
+    // f = M q_m, written straight into column m+1 (saves the k_copy of :81)
+    rc = nsb_op_apply(op, Q, m, Q, m + 1);
+    if (rc != NSB_OK) break;
+    if (async) {
+      rc = nsb_orthonormalize_async(Q, m + 1, m + 1, orth_mode, hbuf + stride * (m - mstart));
+    } else {
+      rc = nsb_orthonormalize(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, nullptr);
+      if (rc == NSB_OK && !(H[(size_t)m * ldh + m + 1] > 0.0)) {
+        set_error("nsb_arnoldi: breakdown at step %d (residual norm %g)", m, H[(size_t)m * ldh + m + 1]);
+        rc = NSB_EBREAKDOWN;
+      }
+    }
+  }
+  if (async) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == NSB_OK && e != cudaSuccess) {
+      set_error("nsb_arnoldi: %s", cudaGetErrorString(e));
+      rc = NSB_ECUDA;
+    }
+    if (rc == NSB_OK)
+      for (int m = mstart; m <= mend; ++m) {
+        const double *h = hbuf + stride * (m - mstart);
+        memcpy(H + (size_t)m * ldh, h, sizeof(double) * (m + 2));
+        for (int i = 0; i < m + 2; ++i)
+          if (std::isnan(h[i])) {
+            set_error("NaN detected in dot product (Arnoldi step %d)", m);
+            rc = NSB_ENAN;
+          }
+        if (rc == NSB_OK && !(h[m + 1] > 0.0)) {
+          set_error("nsb_arnoldi: breakdown at step %d (residual norm %g)", m, h[m + 1]);
+          rc = NSB_EBREAKDOWN;
+        }
+      }
+    nsb_host_free(hbuf);
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Krylov-Schur  (core/eigensolvers.f90:120-359, 363-468)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_schur_condensation(nsb_basis_t Q, int *mstart, double *H, int ldh, int ksize,
+                                      double schur_del, int schur_tgt) {
+  NSB_REQUIRE(Q && mstart && H, "nsb_schur_condensation: NULL argument");
+  NSB_REQUIRE(ksize >= 1 && ksize + 1 <= Q->ncols && ldh >= ksize + 1, "nsb_schur_condensation: bad sizes");
+  const int k = ksize;
+  std::vector<double> b_vec(k, 0.0), vecs((size_t)k * k, 0.0), vals(2 * (size_t)k);
+  b_vec[k - 1] = H[(size_t)(k - 1) * ldh + k];                                  // :403
+  NSB_CHECK(nsb_schur(H, ldh, k, vecs.data(), vals.data()));                    // :407
+  std::vector<int> selected(k);
+  int m = 0;
+  NSB_CHECK(nsb_select_eigenvalues(selected.data(), &m, vals.data(), schur_del, schur_tgt, k));  // :410
+  NSB_CHECK(nsb_ordschur(H, ldh, vecs.data(), k, selected.data(), k));          // :414
+  for (int j = m; j < k; ++j)                                                   // :417
+    for (int i = 0; i < m; ++i) H[(size_t)j * ldh + i] = 0.0;
+  for (int j = 0; j < k; ++j)                                                   // :418
+    for (int i = m; i < k + 1; ++i) H[(size_t)j * ldh + i] = 0.0;
+  NSB_CHECK(nsb_basis_rotate(Q, k, vecs.data(), k, 0));                         // :421-442
+  for (int j = 0; j < k; ++j) {                                                 // :446-447
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += b_vec[i] * vecs[(size_t)j * k + i];
+    H[(size_t)j * ldh + m] = s;
+  }
+  NSB_CHECK(nsb_vec_copy(Q, m, Q, k));                                          // :450-453
+  *mstart = m;
+  return NSB_OK;
+}
+
+extern "C" int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur_tgt, double eigen_tol,
+                                double schur_del, int orth_mode, int max_restarts, double *H, int ldh,
+                                double *vals_c16, double *vecs_c16, double *residual, int *cnt_out,
+                                int *schur_cnt_out) {
+  NSB_REQUIRE(Q && op && H && vals_c16 && vecs_c16 && residual, "nsb_krylov_schur: NULL argument");
+  NSB_REQUIRE(k_dim >= 1 && k_dim + 1 <= Q->ncols && ldh >= k_dim + 1, "nsb_krylov_schur: bad sizes");
+  const int k = k_dim;
+  for (int j = 0; j < k; ++j) memset(H + (size_t)j * ldh, 0, sizeof(double) * (k + 1));
+  int mstart = 0, schur_cnt = 0, cnt = 0;
+  for (;;) {
+    NSB_CHECK(nsb_arnoldi(Q, op, mstart, k - 1, orth_mode, H, ldh));            // :297
+    NSB_CHECK(nsb_eig(H, ldh, k, vecs_c16, vals_c16));                          // :306
+    const double hk = H[(size_t)(k - 1) * ldh + k];
+    cnt = 0;
+    for (int j = 0; j < k; ++j) {                                               // :309-310
+      const double re = vecs_c16[2 * ((size_t)j * k + (k - 1))], im = vecs_c16[2 * ((size_t)j * k + (k - 1)) + 1];
+      residual[j] = std::fabs(hk) * std::hypot(re, im);
+      if (residual[j] < eigen_tol) ++cnt;
+    }
+    if (schur_tgt <= 0 || cnt >= schur_tgt || schur_cnt >= max_restarts) break;  // :314-331
+    ++schur_cnt;
+    NSB_CHECK(nsb_schur_condensation(Q, &mstart, H, ldh, k, schur_del, schur_tgt));
+  }
+  if (cnt_out) *cnt_out = cnt;
+  if (schur_cnt_out) *schur_cnt_out = schur_cnt;
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMRES  (core/newton_krylov.f90:170-326)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int crhs, nsb_basis_t bsol,
+                            int csol, int maxiter, int ksize, double tol, int orth_mode, int *calls_out,
+                            double *residual_hist, int *nhist) {
+  NSB_REQUIRE(Q && op && brhs && bsol, "nsb_ts_gmres: NULL argument");
+  NSB_REQUIRE(ksize >= 1 && Q->ncols >= ksize + 2, "nsb_ts_gmres: basis needs ksize+2 columns");
+  NSB_REQUIRE(maxiter >= 1, "nsb_ts_gmres: maxiter=%d", maxiter);
+  const int k1 = ksize + 1, wrk = ksize + 1, ldh = ksize + 1;
+  std::vector<double> H((size_t)ldh * ksize), yvec(ksize), evec(k1);
+  double beta = 0.0;
+  int calls = 0, nh = 0;
+  NSB_CHECK(nsb_vec_zero(bsol, csol));                                          // :236
+  NSB_CHECK(nsb_vec_copy(Q, 0, brhs, crhs));                                    // :241
+  NSB_CHECK(nsb_vec_normalize(Q, 0, &beta));                                    // :242
+  for (int it = 0; it < maxiter; ++it) {                                        // :245
+    std::fill(H.begin(), H.end(), 0.0);
+    std::fill(yvec.begin(), yvec.end(), 0.0);
+    std::fill(evec.begin(), evec.end(), 0.0);
+    evec[0] = beta;
+    int kk = ksize;
+    for (int k = 1; k <= ksize; ++k) {                                          // :250
+      NSB_CHECK(nsb_arnoldi(Q, op, k - 1, k - 1, orth_mode, H.data(), ldh));    // :252
+      ++calls;
+      NSB_CHECK(nsb_lstsq(H.data(), ldh, k + 1, k, evec.data(), yvec.data()));  // :255
+      double r2 = 0.0;                                                          // :258
+      for (int i = 0; i < k + 1; ++i) {
+        double s = evec[i];
+        for (int j = 0; j < k; ++j) s -= H[(size_t)j * ldh + i] * yvec[j];
+        r2 += s * s;
+      }
+      beta = std::sqrt(r2);
+      if (beta * beta < tol) {                                                  // :266
+        kk = k;
+        break;
+      }
+    }
+    NSB_CHECK(nsb_basis_gemv(Q, kk, yvec.data(), Q, wrk));                      // :279 (min(k, ksize) columns)
+    NSB_CHECK(nsb_vec_add2(bsol, csol, Q, wrk));                                // :280
+    // initialize_gmres_vector :303-326
+    NSB_CHECK(nsb_vec_copy(Q, 0, bsol, csol));
+    NSB_CHECK(nsb_op_apply(op, Q, 0, Q, wrk));
+    ++calls;
+    NSB_CHECK(nsb_vec_sub2(Q, wrk, brhs, crhs));
+    NSB_CHECK(nsb_vec_scal(Q, wrk, -1.0));
+    NSB_CHECK(nsb_vec_normalize(Q, wrk, &beta));
+    NSB_CHECK(nsb_vec_copy(Q, 0, Q, wrk));
+    if (residual_hist) residual_hist[nh] = beta * beta;
+    ++nh;
+    if (beta * beta < tol) break;                                               // :293
+  }
+  if (calls_out) *calls_out = calls;
+  if (nhist) *nhist = nh;
+  return NSB_OK;
+}

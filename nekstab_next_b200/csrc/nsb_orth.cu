@@ -1,0 +1,515 @@
+// Fused BM1-weighted orthogonalisation on the device-resident Krylov basis.
+//
+// Replaces update_hessenberg_matrix (core/krylov_decomposition.f90:103-189): the reference runs
+// 2k {k_copy, k_dot, k_cmult, k_sub2} sweeps (10 n words each, one MPI_Allreduce per component
+// per dot).  Here one orthogonalisation pass is two kernels that each read the basis exactly once:
+//
+//   multidot : h = V_k^T (W o w)       8 n (k+2) algorithmic bytes      (V, w, W read once)
+//   update   : w -= V_k h (+ ||w||_W^2) 8 n (k+3) algorithmic bytes      (V, W read; w read+written)
+//
+// V is column-major [ld, ncols], ld a multiple of 1024 rows with zero pads, so no tail handling.
+// Both kernels are persistent (grid = 2 CTAs per SM), 256 threads, each thread owning 4 rows of a
+// 1024-row chunk as two double2; 8 columns (16 x 128-bit loads per thread) are in flight at once.
+#include <cmath>
+#include <cstring>
+
+#include "nsb_internal.h"
+#include "nsb_device.cuh"
+
+using namespace nsb;
+
+namespace nsb {
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nblk, int pstride,
+                                       int k, double *__restrict__ out, int accumulate_into,
+                                       double *__restrict__ out2);
+}
+
+namespace {
+
+constexpr int KT = 8;          // columns per tile
+constexpr int CHUNK = 1024;    // rows per chunk = 256 threads x 4 rows
+constexpr int NT = 256;
+
+// Reduce 8 per-lane values over the 32 lanes of a warp with 9 shuffles (recursive halving):
+// on return lane L with (L & 3) == 0 holds the warp sum of column (L >> 2).
+__device__ __forceinline__ double warp_reduce8(const double (&a)[KT], int lane) {
+  double b[4], c[2], d;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double send = h16 ? a[i] : a[i + 4];
+    double keep = h16 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    double send = h8 ? b[i] : b[i + 2];
+    double keep = h8 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    double send = h4 ? c[0] : c[1];
+    double keep = h4 ? c[1] : c[0];
+    d = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
+// h_partial[cta][j] = sum over the CTA's chunks of sum_r V[r,j] W[r] w[r];
+// column k of the partial (if WITH_NORM) = sum_r W[r] w[r]^2.
+template <bool WITH_NORM>
+__global__ void __launch_bounds__(NT, 2)
+multidot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ w,
+                const double *__restrict__ W, int64_t nchunks, double *__restrict__ partial,
+                int pstride) {
+  extern __shared__ double accS[];  // [NT/32][kpad]
+  const int kpad = (k + KT) & ~(KT - 1);  // room for the norm slot too
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (NT / 32) * kpad; i += NT) accS[i] = 0.0;
+  __syncthreads();
+  double *myacc = accS + warp * kpad;
+  double nrm = 0.0;
+
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t r0 = chunk * CHUNK + 2 * threadIdx.x;  // rows r0, r0+1, r0+512, r0+513
+    const double2 wa = ld_stream(reinterpret_cast<const double2 *>(w + r0));
+    const double2 wb = ld_stream(reinterpret_cast<const double2 *>(w + r0 + 512));
+    const double2 Wa = ld_stream(reinterpret_cast<const double2 *>(W + r0));
+    const double2 Wb = ld_stream(reinterpret_cast<const double2 *>(W + r0 + 512));
+    const double ww0 = wa.x * Wa.x, ww1 = wa.y * Wa.y, ww2 = wb.x * Wb.x, ww3 = wb.y * Wb.y;
+    if (WITH_NORM) nrm += ww0 * wa.x + ww1 * wa.y + ww2 * wb.x + ww3 * wb.y;
+    const double *vp = V + r0;
+    int j0 = 0;
+    for (; j0 + KT <= k; j0 += KT) {
+      double2 va[KT], vb[KT];
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj) {
+        const double *p = vp + (int64_t)(j0 + jj) * ld;
+        va[jj] = ld_stream(reinterpret_cast<const double2 *>(p));
+        vb[jj] = ld_stream(reinterpret_cast<const double2 *>(p + 512));
+      }
+      double acc[KT];
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj)
+        acc[jj] = fma(va[jj].x, ww0, fma(va[jj].y, ww1, fma(vb[jj].x, ww2, vb[jj].y * ww3)));
+      double s = warp_reduce8(acc, lane);
+      if ((lane & 3) == 0) myacc[j0 + (lane >> 2)] += s;
+    }
+    if (j0 < k) {  // tail tile, guarded loads
+      double acc[KT];
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj) {
+        if (j0 + jj < k) {
+          const double *p = vp + (int64_t)(j0 + jj) * ld;
+          double2 a = ld_stream(reinterpret_cast<const double2 *>(p));
+          double2 b = ld_stream(reinterpret_cast<const double2 *>(p + 512));
+          acc[jj] = fma(a.x, ww0, fma(a.y, ww1, fma(b.x, ww2, b.y * ww3)));
+        } else {
+          acc[jj] = 0.0;
+        }
+      }
+      double s = warp_reduce8(acc, lane);
+      if ((lane & 3) == 0 && j0 + (lane >> 2) < k) myacc[j0 + (lane >> 2)] += s;
+    }
+  }
+  if (WITH_NORM) {
+    nrm = warp_reduce_sum(nrm);
+    if (lane == 0) myacc[k] = nrm;
+  }
+  __syncthreads();
+  const int kout = WITH_NORM ? k + 1 : k;
+  for (int j = threadIdx.x; j < kout; j += NT) {
+    double s = 0.0;
+#pragma unroll
+    for (int wp = 0; wp < NT / 32; ++wp) s += accS[wp * kpad + j];
+    partial[(size_t)blockIdx.x * pstride + j] = s;
+  }
+}
+
+// MODE 0: w -= V h          (rows [0, nrows))        [+ partial norm over rows < ndot if WITH_NORM]
+// MODE 1: out = V y         (k_matmul)
+template <int MODE, bool WITH_NORM>
+__global__ void __launch_bounds__(NT, 2)
+update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h,
+              double *__restrict__ w, const double *__restrict__ W, int64_t nchunks,
+              int64_t ndot_chunks, double *__restrict__ partial) {
+  extern __shared__ double hS[];
+  for (int j = threadIdx.x; j < k; j += NT) hS[j] = h[j];
+  __syncthreads();
+  double nrm = 0.0;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t r0 = chunk * CHUNK + 2 * threadIdx.x;
+    const double *vp = V + r0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j0 = 0;
+    for (; j0 + KT <= k; j0 += KT) {
+      double2 va[KT], vb[KT];
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj) {
+        const double *p = vp + (int64_t)(j0 + jj) * ld;
+        va[jj] = ld_stream(reinterpret_cast<const double2 *>(p));
+        vb[jj] = ld_stream(reinterpret_cast<const double2 *>(p + 512));
+      }
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj) {
+        const double hj = hS[j0 + jj];
+        a0 = fma(va[jj].x, hj, a0);
+        a1 = fma(va[jj].y, hj, a1);
+        a2 = fma(vb[jj].x, hj, a2);
+        a3 = fma(vb[jj].y, hj, a3);
+      }
+    }
+    for (; j0 < k; ++j0) {
+      const double *p = vp + (int64_t)j0 * ld;
+      double2 a = ld_stream(reinterpret_cast<const double2 *>(p));
+      double2 b = ld_stream(reinterpret_cast<const double2 *>(p + 512));
+      const double hj = hS[j0];
+      a0 = fma(a.x, hj, a0);
+      a1 = fma(a.y, hj, a1);
+      a2 = fma(b.x, hj, a2);
+      a3 = fma(b.y, hj, a3);
+    }
+    double2 *wpa = reinterpret_cast<double2 *>(w + r0);
+    double2 *wpb = reinterpret_cast<double2 *>(w + r0 + 512);
+    if (MODE == 0) {
+      double2 wa = *wpa, wb = *wpb;
+      wa.x -= a0; wa.y -= a1; wb.x -= a2; wb.y -= a3;
+      *wpa = wa;
+      *wpb = wb;
+      if (WITH_NORM && chunk < ndot_chunks) {
+        const double2 Wa = ld_stream(reinterpret_cast<const double2 *>(W + r0));
+        const double2 Wb = ld_stream(reinterpret_cast<const double2 *>(W + r0 + 512));
+        nrm += Wa.x * wa.x * wa.x + Wa.y * wa.y * wa.y + Wb.x * wb.x * wb.x + Wb.y * wb.y * wb.y;
+      }
+    } else {
+      *wpa = make_double2(a0, a1);
+      *wpb = make_double2(a2, a3);
+    }
+  }
+  if (WITH_NORM) {
+    nrm = block_reduce_sum<NT>(nrm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = nrm;
+  }
+}
+
+// w *= 1/sqrt(nrm2[0]);  h_out[k] = sqrt(nrm2[0])   (k_normalize, core/krylov_subspace.f90:75-92)
+__global__ void __launch_bounds__(NT)
+normalize_kernel(double2 *__restrict__ w, int64_t n2, const double *__restrict__ nrm2,
+                 double *__restrict__ hk) {
+  const double beta = sqrt(nrm2[0]);
+  const double inv = 1.0 / beta;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hk) *hk = beta;
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n2; base += stride) {
+    double2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n2) v[u] = w[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n2) { v[u].x *= inv; v[u].y *= inv; w[i] = v[u]; }
+    }
+  }
+}
+
+__global__ void add_vec_kernel(double *__restrict__ dst, const double *__restrict__ a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += a[i];
+}
+
+// ---- panel rotation  V(:,0:k) <- V(:,0:k) Z --------------------------------------------------
+// One CTA stages RB rows x k columns in shared memory (column-major, like V), then every thread
+// produces a 2-row x 4-column register tile per step; the in-place write is safe because the whole
+// row panel is staged before the first store.
+template <int RB>
+__global__ void __launch_bounds__(NT)
+rotate_kernel(double *__restrict__ V, int64_t ld, int k, const double *__restrict__ Z, int ldz,
+              int64_t npanels) {
+  extern __shared__ double tile[];  // [k][RB]
+  constexpr int RP = RB / 2;        // row pairs
+  constexpr int CG = NT / RP;       // column groups
+  const int rp = threadIdx.x % RP, cg = threadIdx.x / RP;
+  for (int64_t panel = blockIdx.x; panel < npanels; panel += gridDim.x) {
+    const int64_t r0 = panel * RB;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < k * RP; idx += NT) {
+      int j = idx / RP, r = idx % RP;
+      // plain (coherent) loads: the same kernel overwrites V in place
+      reinterpret_cast<double2 *>(tile)[j * RP + r] =
+          reinterpret_cast<const double2 *>(V + (int64_t)j * ld + r0)[r];
+    }
+    __syncthreads();
+    for (int c0 = 4 * cg; c0 < k; c0 += 4 * CG) {
+      double acc[4][2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = 0.0;
+      const double *z0 = Z + (int64_t)c0 * ldz;
+      const int nc = (k - c0) < 4 ? (k - c0) : 4;
+      for (int j = 0; j < k; ++j) {
+        const double2 v = reinterpret_cast<const double2 *>(tile)[j * RP + rp];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nc) {
+            const double z = __ldg(z0 + (int64_t)c * ldz + j);
+            acc[c][0] = fma(v.x, z, acc[c][0]);
+            acc[c][1] = fma(v.y, z, acc[c][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nc)
+          reinterpret_cast<double2 *>(V + (int64_t)(c0 + c) * ld + r0)[rp] =
+              make_double2(acc[c][0], acc[c][1]);
+    }
+  }
+}
+
+inline int persistent_grid(nsb_context_t ctx, int64_t nchunks) {
+  int64_t g = (int64_t)ctx->num_sms * 2;
+  return (int)(nchunks < g ? nchunks : g);
+}
+
+int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *w,
+                    const double *W, int64_t ndot, double *h_d, bool with_norm, double *hsum_d) {
+  const int64_t nchunks = ndot / CHUNK;
+  const int grid = persistent_grid(ctx, nchunks);
+  const int kpad = (k + KT) & ~(KT - 1);
+  const size_t smem = sizeof(double) * (NT / 32) * kpad;
+  const int pstride = kMaxK + 8;
+  NSB_CHECK(ensure_partial(ctx, grid));
+  cudaSetDevice(ctx->device);
+  if (with_norm)
+    multidot_kernel<true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+  else
+    multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+  const int kout = with_norm ? k + 1 : k;
+  if (kout == 0) return NSB_OK;
+  reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(
+      ctx->partial_d, grid, pstride, kout, h_d, hsum_d != nullptr, hsum_d);
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+template <int MODE>
+int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h_d, double *w,
+                  const double *W, int64_t nrows, int64_t ndot, bool with_norm, double *nrm2_d) {
+  const int64_t nchunks = nrows / CHUNK;
+  const int grid = persistent_grid(ctx, nchunks);
+  const size_t smem = sizeof(double) * (k > 0 ? k : 1);
+  cudaSetDevice(ctx->device);
+  if (with_norm) {
+    update_kernel<MODE, true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
+                                                              ctx->partial_d);
+    reduce_partials_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partial_d, grid, 1, 1, nrm2_d, 0, nullptr);
+    ctx->launches += 2;
+  } else {
+    update_kernel<MODE, false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
+                                                               ctx->partial_d);
+    ctx->launches += 1;
+  }
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm2_d, double *hk_d) {
+  int64_t n2 = ld / 2;
+  int64_t want = (n2 + 1023) / 1024;
+  int64_t cap = (int64_t)ctx->num_sms * 16;
+  int grid = (int)(want < cap ? want : cap);
+  normalize_kernel<<<grid, NT, 0, ctx->stream>>>(reinterpret_cast<double2 *>(w), n2, nrm2_d, hk_d);
+  ctx->launches += 1;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+}  // namespace
+
+namespace nsb {
+int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d) {
+  nsb_layout_t L = b->lay;
+  NSB_CHECK(launch_multidot(L->ctx, b->v_d, L->ld, k, w_col_d, L->w_d, L->ndot, h_d, false, nullptr));
+  if (L->ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(L->ctx, h_d, k));
+  return NSB_OK;
+}
+}  // namespace nsb
+
+// Enqueue the whole orthonormalisation; on return ctx->hvec_d[2*(kMaxK+8) ...] holds h[0..k].
+static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_out) {
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = L->ctx;
+  const int S = kMaxK + 8;
+  double *h1 = ctx->hvec_d, *h2 = ctx->hvec_d + S, *hsum = ctx->hvec_d + 2 * S,
+         *scal = ctx->hvec_d + 3 * S;
+  double *w = B->col(col_w);
+  const double *V = B->v_d;
+  cudaSetDevice(ctx->device);
+  int passes = 2;
+  auto add_into = [&](double *dst, const double *src, int n) -> int {
+    if (n <= 0) return NSB_OK;
+    add_vec_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dst, src, n);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  };
+  if (k == 0) {
+    // nothing to project out: k_normalize only
+    NSB_CHECK(launch_multidot(ctx, w, L->ld, 0, w, L->w_d, L->ndot, scal, true, nullptr));
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+    passes = 0;
+  } else if (mode == NSB_ORTH_MGS2_REF) {
+    // literal core/krylov_decomposition.f90:155-180: one column at a time, two sweeps
+    NSB_CUDA(cudaMemsetAsync(hsum, 0, sizeof(double) * (k + 1), ctx->stream));
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < k; ++i) {
+        NSB_CHECK(launch_multidot(ctx, B->col(i), L->ld, 1, w, L->w_d, L->ndot, h1, false, nullptr));
+        if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, 1));
+        NSB_CHECK(add_into(hsum + i, h1, 1));
+        NSB_CHECK(launch_update<0>(ctx, B->col(i), L->ld, 1, h1, w, L->w_d, L->ld, L->ndot, false, nullptr));
+      }
+    NSB_CHECK(launch_multidot(ctx, w, L->ld, 0, w, L->w_d, L->ndot, scal, true, nullptr));
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+  } else {
+    const bool dgks = (mode == NSB_ORTH_DGKS);
+    // pass 1 (the norm of the incoming w rides along for the DGKS test)
+    NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr));
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, dgks ? k + 1 : k));
+    NSB_CUDA(cudaMemcpyAsync(hsum, h1, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
+    NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, scal));
+    bool second = true;
+    if (dgks) {
+      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+      NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S, h1 + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S + 1, scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+      const double n0 = ctx->hpin[3 * S], n1 = ctx->hpin[3 * S + 1];
+      second = !(n1 >= 0.5 * n0);  // ||w'|| < ||w|| / sqrt 2  (also taken on NaN)
+    }
+    if (second) {
+      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h2, false, nullptr));
+      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, k));
+      NSB_CHECK(add_into(hsum, h2, k));
+      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, scal));
+      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+    } else {
+      passes = 1;
+    }
+  }
+  NSB_CHECK(launch_normalize(ctx, w, L->ld, scal, hsum + k));
+  if (passes_out) *passes_out = passes;
+  return NSB_OK;
+}
+
+extern "C" int nsb_orthonormalize_async(nsb_basis_t B, int k, int col_w, int mode, double *h_pinned) {
+  NSB_REQUIRE(B && h_pinned, "nsb_orthonormalize_async: NULL argument");
+  NSB_REQUIRE(k >= 0 && k <= kMaxK && k <= B->ncols, "nsb_orthonormalize: k=%d out of range", k);
+  NSB_REQUIRE(col_w >= k && col_w < B->ncols, "nsb_orthonormalize: col_w=%d must be >= k and < ncols", col_w);
+  NSB_REQUIRE(mode == NSB_ORTH_CGS2 || mode == NSB_ORTH_MGS2_REF,
+              "nsb_orthonormalize_async: mode %d needs a host decision; use nsb_orthonormalize", mode);
+  nsb_context_t ctx = B->lay->ctx;
+  NSB_CHECK(orth_enqueue(B, k, col_w, mode, nullptr));
+  NSB_CUDA(cudaMemcpyAsync(h_pinned, ctx->hvec_d + 2 * (kMaxK + 8), sizeof(double) * (k + 1),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  return NSB_OK;
+}
+
+extern "C" int nsb_orthonormalize(nsb_basis_t B, int k, int col_w, int mode, double *h, int *passes) {
+  NSB_REQUIRE(B && h, "nsb_orthonormalize: NULL argument");
+  NSB_REQUIRE(k >= 0 && k <= kMaxK && k <= B->ncols, "nsb_orthonormalize: k=%d out of range", k);
+  NSB_REQUIRE(col_w >= k && col_w < B->ncols, "nsb_orthonormalize: col_w=%d must be >= k and < ncols", col_w);
+  NSB_REQUIRE(mode >= 0 && mode <= 2, "nsb_orthonormalize: unknown mode %d", mode);
+  nsb_context_t ctx = B->lay->ctx;
+  NSB_CHECK(orth_enqueue(B, k, col_w, mode, passes));
+  NSB_CUDA(cudaMemcpyAsync(ctx->hpin, ctx->hvec_d + 2 * (kMaxK + 8), sizeof(double) * (k + 1),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(h, ctx->hpin, sizeof(double) * (k + 1));
+  for (int i = 0; i <= k; ++i)
+    if (std::isnan(h[i])) {
+      set_error("NaN detected in dot product");
+      return NSB_ENAN;
+    }
+  return NSB_OK;
+}
+
+extern "C" int nsb_basis_gram(nsb_basis_t B, int k, double *G, int ldg) {
+  NSB_REQUIRE(B && G && k >= 1 && k <= B->ncols && k <= kMaxK && ldg >= k, "nsb_basis_gram: bad argument");
+  nsb_context_t ctx = B->lay->ctx;
+  for (int j = 0; j < k; ++j) {
+    NSB_CHECK(weighted_multidot(B, k, B->col(j), ctx->hvec_d));
+    NSB_CUDA(cudaMemcpyAsync(ctx->hpin, ctx->hvec_d, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(G + (size_t)j * ldg, ctx->hpin, sizeof(double) * k);
+  }
+  return NSB_OK;
+}
+
+extern "C" int nsb_basis_gemv(nsb_basis_t B, int k, const double *y, nsb_basis_t bout, int cout) {
+  NSB_REQUIRE(B && y && bout, "nsb_basis_gemv: NULL argument");
+  NSB_REQUIRE(k >= 1 && k <= B->ncols && k <= kMaxK, "nsb_basis_gemv: k=%d out of range", k);
+  NSB_REQUIRE(cout >= 0 && cout < bout->ncols, "nsb_basis_gemv: column out of range");
+  NSB_REQUIRE(bout->lay == B->lay, "nsb_basis_gemv: different layouts");
+  NSB_REQUIRE(!(bout == B && cout < k), "nsb_basis_gemv: output column aliases an input column");
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = L->ctx;
+  double *y_d = ctx->hvec_d + (kMaxK + 8);
+  memcpy(ctx->hpin + (kMaxK + 8), y, sizeof(double) * k);
+  NSB_CUDA(cudaMemcpyAsync(y_d, ctx->hpin + (kMaxK + 8), sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+  NSB_CHECK(launch_update<1>(ctx, B->v_d, L->ld, k, y_d, bout->col(cout), L->w_d, L->ld, L->ndot, false, nullptr));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));  // hpin is reused by the next call
+  return NSB_OK;
+}
+
+extern "C" int nsb_basis_rotate(nsb_basis_t B, int k, const double *Z, int ldz, int rotate_time) {
+  NSB_REQUIRE(B && Z, "nsb_basis_rotate: NULL argument");
+  NSB_REQUIRE(k >= 1 && k <= B->ncols && ldz >= k, "nsb_basis_rotate: k=%d ldz=%d", k, ldz);
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = L->ctx;
+  cudaSetDevice(ctx->device);
+  double *Z_d = nullptr, *tsave = nullptr;
+  NSB_CUDA(cudaMalloc(&Z_d, sizeof(double) * (size_t)k * k));
+  NSB_CUDA(cudaMemcpy2DAsync(Z_d, sizeof(double) * k, Z, sizeof(double) * ldz, sizeof(double) * k, k,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  if (!rotate_time) {
+    NSB_CUDA(cudaMalloc(&tsave, sizeof(double) * k));
+    NSB_CUDA(cudaMemcpy2DAsync(tsave, sizeof(double), B->v_d + L->time_row, sizeof(double) * L->ld,
+                               sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  // rows per panel chosen so that the staged panel fits in shared memory
+  int rb = 128;
+  while (rb > 32 && (size_t)rb * k * sizeof(double) > 200 * 1024) rb >>= 1;
+  NSB_REQUIRE((size_t)rb * k * sizeof(double) <= 227 * 1024, "nsb_basis_rotate: k=%d too large", k);
+  size_t smem = (size_t)rb * k * sizeof(double);
+  int64_t npanels = L->ld / rb;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int64_t g = (int64_t)ctx->num_sms * per_sm;
+  int grid = (int)(npanels < g ? npanels : g);
+#define LAUNCH_ROT(RB)                                                                              \
+  do {                                                                                              \
+    NSB_CUDA(cudaFuncSetAttribute(rotate_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                  (int)smem));                                                      \
+    rotate_kernel<RB><<<grid, NT, smem, ctx->stream>>>(B->v_d, L->ld, k, Z_d, k, npanels);          \
+  } while (0)
+  if (rb == 128) LAUNCH_ROT(128);
+  else if (rb == 64) LAUNCH_ROT(64);
+  else LAUNCH_ROT(32);
+#undef LAUNCH_ROT
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  if (!rotate_time)
+    NSB_CUDA(cudaMemcpy2DAsync(B->v_d + L->time_row, sizeof(double) * L->ld, tsave, sizeof(double),
+                               sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(Z_d);
+  if (tsave) cudaFree(tsave);
+  return NSB_OK;
+}

@@ -1,0 +1,840 @@
+// Spectral-element operator kernels: geometry, axhelm (tensor-product sum factorisation with
+// geometric factors G1..G6 on GLL points), dssum (gather-scatter), col2, and the fused linear
+// operator used as the Arnoldi matvec on the synthetic configurations.
+//
+// Reference: these are the Nek5000 kernels the reference reaches through nek_advance
+// (core/linear_operators.f90:247, core/matvec.f90:211); in-tree uses of dssum/col2:
+// core/utils.f90:287-290, 338-346.  [UPSTREAM-RECALL] hmholtz.f axhelm, navier5.f local_grad3,
+// coef.f glmapm1/geodat1, speclib.f zwgll/dgll, gslib gs_op.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "nsb_internal.h"
+#include "nsb_device.cuh"
+
+using namespace nsb;
+
+// ------------------------------------------------------------------------------------------------
+// GLL quadrature (host)
+// ------------------------------------------------------------------------------------------------
+static void legendre(int n, double x, double *pn, double *pnm1) {
+  double p0 = 1.0, p1 = x;
+  if (n == 0) { *pn = 1.0; *pnm1 = 0.0; return; }
+  for (int m = 1; m < n; ++m) {
+    double p2 = ((2 * m + 1) * x * p1 - m * p0) / (m + 1);
+    p0 = p1;
+    p1 = p2;
+  }
+  *pn = p1;
+  *pnm1 = p0;
+}
+
+extern "C" int nsb_gll(int N, double *z, double *w, double *D) {
+  NSB_REQUIRE(N >= 1 && N <= 31, "nsb_gll: N=%d out of range", N);
+  const int n1 = N + 1;
+  std::vector<double> x(n1), pn(n1);
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < n1; ++i) x[i] = -std::cos(pi * i / N);
+  for (int i = 1; i < N; ++i) {
+    double xi = x[i];
+    for (int it = 0; it < 100; ++it) {
+      double p, pm;
+      legendre(N, xi, &p, &pm);
+      double q = N * (pm - xi * p);             // (1-x^2) P_N'(x)
+      double dq = -(double)N * (N + 1) * p;     // derivative of q
+      double dx = q / dq;
+      xi -= dx;
+      if (std::fabs(dx) < 1e-16) break;
+    }
+    x[i] = xi;
+  }
+  x[0] = -1.0;
+  x[N] = 1.0;
+  for (int i = 0; i < n1 / 2; ++i) {  // enforce antisymmetry
+    double a = 0.5 * (x[i] - x[N - i]);
+    x[i] = a;
+    x[N - i] = -a;
+  }
+  if (n1 % 2) x[N / 2] = 0.0;
+  for (int i = 0; i < n1; ++i) {
+    double pm;
+    legendre(N, x[i], &pn[i], &pm);
+  }
+  for (int i = 0; i < n1; ++i) {
+    if (z) z[i] = x[i];
+    if (w) w[i] = 2.0 / (N * (N + 1) * pn[i] * pn[i]);
+  }
+  if (D) {
+    for (int j = 0; j < n1; ++j)
+      for (int i = 0; i < n1; ++i)
+        D[i + n1 * j] = (i == j) ? 0.0 : pn[i] / (pn[j] * (x[i] - x[j]));
+    D[0] = -N * (N + 1) / 4.0;
+    D[N + n1 * N] = N * (N + 1) / 4.0;
+  }
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device kernels
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// Geometry: one thread per point, D read through the read-only cache (setup only, not hot).
+__global__ void geom3d_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                              const double *__restrict__ z, const double *__restrict__ D,
+                              const double *__restrict__ wq, int lx, int64_t npts,
+                              double *__restrict__ g, double *__restrict__ bm1,
+                              double *__restrict__ jac_out, double *__restrict__ rst) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  const int n3 = lx * lx * lx;
+  const int64_t e0 = p / n3 * n3;
+  const int loc = (int)(p - e0);
+  const int i = loc % lx, j = (loc / lx) % lx, k = loc / (lx * lx);
+  double d[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // d[c][r] = d coord_c / d (r,s,t)
+  const double *c[3] = {x, y, z};
+  for (int l = 0; l < lx; ++l) {
+    const double dr = D[i + lx * l], ds = D[j + lx * l], dt = D[k + lx * l];
+    const int64_t pr = e0 + l + lx * (j + lx * k), ps = e0 + i + lx * (l + lx * k),
+                  pt = e0 + i + lx * (j + lx * l);
+    for (int a = 0; a < 3; ++a) {
+      d[a][0] = fma(dr, c[a][pr], d[a][0]);
+      d[a][1] = fma(ds, c[a][ps], d[a][1]);
+      d[a][2] = fma(dt, c[a][pt], d[a][2]);
+    }
+  }
+  const double xr = d[0][0], xs = d[0][1], xt = d[0][2], yr = d[1][0], ys = d[1][1], yt = d[1][2],
+               zr = d[2][0], zs = d[2][1], zt = d[2][2];
+  const double jac = xr * (ys * zt - yt * zs) - xs * (yr * zt - yt * zr) + xt * (yr * zs - ys * zr);
+  const double rx = ys * zt - yt * zs, ry = xt * zs - xs * zt, rz = xs * yt - xt * ys;
+  const double sx = yt * zr - yr * zt, sy = xr * zt - xt * zr, sz = xt * yr - xr * yt;
+  const double tx = yr * zs - ys * zr, ty = xs * zr - xr * zs, tz = xr * ys - xs * yr;
+  const double w3 = wq[i] * wq[j] * wq[k];
+  const double sc = w3 / jac;
+  g[0 * npts + p] = (rx * rx + ry * ry + rz * rz) * sc;
+  g[1 * npts + p] = (sx * sx + sy * sy + sz * sz) * sc;
+  g[2 * npts + p] = (tx * tx + ty * ty + tz * tz) * sc;
+  g[3 * npts + p] = (rx * sx + ry * sy + rz * sz) * sc;
+  g[4 * npts + p] = (rx * tx + ry * ty + rz * tz) * sc;
+  g[5 * npts + p] = (sx * tx + sy * ty + sz * tz) * sc;
+  bm1[p] = jac * w3;
+  jac_out[p] = jac;
+  const double r9[9] = {rx, ry, rz, sx, sy, sz, tx, ty, tz};
+  for (int a = 0; a < 9; ++a) rst[a * npts + p] = r9[a];
+}
+
+__global__ void geom2d_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                              const double *__restrict__ D, const double *__restrict__ wq, int lx,
+                              int64_t npts, double *__restrict__ g, double *__restrict__ bm1,
+                              double *__restrict__ jac_out, double *__restrict__ rst) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  const int n2 = lx * lx;
+  const int64_t e0 = p / n2 * n2;
+  const int loc = (int)(p - e0);
+  const int i = loc % lx, j = loc / lx;
+  double xr = 0, xs = 0, yr = 0, ys = 0;
+  for (int l = 0; l < lx; ++l) {
+    const double dr = D[i + lx * l], ds = D[j + lx * l];
+    const int64_t pr = e0 + l + lx * j, ps = e0 + i + lx * l;
+    xr = fma(dr, x[pr], xr);
+    yr = fma(dr, y[pr], yr);
+    xs = fma(ds, x[ps], xs);
+    ys = fma(ds, y[ps], ys);
+  }
+  const double jac = xr * ys - xs * yr;
+  const double rx = ys, ry = -xs, sx = -yr, sy = xr;
+  const double w2 = wq[i] * wq[j];
+  const double sc = w2 / jac;
+  g[0 * npts + p] = (rx * rx + ry * ry) * sc;
+  g[1 * npts + p] = (sx * sx + sy * sy) * sc;
+  g[2 * npts + p] = (rx * sx + ry * sy) * sc;
+  bm1[p] = jac * w2;
+  jac_out[p] = jac;
+  rst[0 * npts + p] = rx;
+  rst[1 * npts + p] = ry;
+  rst[2 * npts + p] = sx;
+  rst[3 * npts + p] = sy;
+}
+
+// ---- axhelm, 3-D -------------------------------------------------------------------------------
+// Thread (i,j) of an element marches over k with its u-column and w-column in registers; the
+// r- and s-derivatives go through one shared plane per element, the t-derivative stays in
+// registers.  D (row-major) and D^T are staged in shared memory once per CTA.
+//   EPI = 0 : w = h1 * D^T G D u + h2 * bm1 * u [+ C . grad u]         (raw, element-local)
+//   EPI = 1 : as 0 on element-boundary points (to be summed by the gather-scatter kernel),
+//             final value alpha*u + beta*bmask*w on element-interior points
+template <int LX, bool CONV, int EPI>
+__global__ void __launch_bounds__((256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1) * LX * LX)
+axhelm3d_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
+                const double *__restrict__ bm1, const double *__restrict__ Dg, int64_t nel,
+                int64_t npts, double h1, double h2, const double *__restrict__ cv, double alpha,
+                double beta, const double *__restrict__ bmask) {
+  constexpr int EPC = (256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1);
+  constexpr int N2 = LX * LX, N3 = LX * LX * LX;
+  __shared__ double sD[LX * LX], sDt[LX * LX];
+  __shared__ double s_u[EPC][LX][LX], s_wr[EPC][LX][LX], s_ws[EPC][LX][LX];
+  const int tid = threadIdx.x;
+  for (int t = tid; t < N2; t += EPC * N2) {
+    const int a = t / LX, b = t % LX;   // Dg[a + LX*b] = D_ab
+    sD[a * LX + b] = Dg[a + LX * b];
+    sDt[b * LX + a] = Dg[a + LX * b];
+  }
+  const int el = tid / N2, ij = tid % N2, i = ij % LX, j = ij / LX;
+  int64_t e = (int64_t)blockIdx.x * EPC + el;
+  const bool active = e < nel;
+  if (!active) e = nel - 1;
+  const int64_t base = e * N3 + ij;
+  double uk[LX], wk[LX];
+#pragma unroll
+  for (int k = 0; k < LX; ++k) {
+    uk[k] = u[base + k * N2];
+    wk[k] = 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < LX; ++k) {
+    const int64_t p = base + k * N2;
+    // geometric factors of this plane: issued before the barrier so they overlap it
+    const double g1 = ld_stream1(g + 0 * npts + p), g2 = ld_stream1(g + 1 * npts + p),
+                 g3 = ld_stream1(g + 2 * npts + p), g4 = ld_stream1(g + 3 * npts + p),
+                 g5 = ld_stream1(g + 4 * npts + p), g6 = ld_stream1(g + 5 * npts + p);
+    double c1 = 0, c2 = 0, c3 = 0;
+    if (CONV) {
+      c1 = ld_stream1(cv + 0 * npts + p);
+      c2 = ld_stream1(cv + 1 * npts + p);
+      c3 = ld_stream1(cv + 2 * npts + p);
+    }
+    s_u[el][j][i] = uk[k];
+    __syncthreads();
+    double ur = 0, us = 0, ut = 0;
+#pragma unroll
+    for (int l = 0; l < LX; ++l) {
+      ur = fma(sDt[l * LX + i], s_u[el][j][l], ur);
+      us = fma(sDt[l * LX + j], s_u[el][l][i], us);
+      ut = fma(sD[k * LX + l], uk[l], ut);
+    }
+    const double wr = h1 * (g1 * ur + g4 * us + g5 * ut);
+    const double ws = h1 * (g2 * us + g4 * ur + g6 * ut);
+    const double wt = h1 * (g3 * ut + g5 * ur + g6 * us);
+    s_wr[el][j][i] = wr;
+    s_ws[el][j][i] = ws;
+    __syncthreads();
+    double acc = CONV ? (c1 * ur + c2 * us + c3 * ut) : 0.0;
+#pragma unroll
+    for (int l = 0; l < LX; ++l) {
+      acc = fma(sD[l * LX + i], s_wr[el][j][l], acc);
+      acc = fma(sD[l * LX + j], s_ws[el][l][i], acc);
+      wk[l] = fma(sD[k * LX + l], wt, wk[l]);
+    }
+    wk[k] += acc;
+  }
+  if (!active) return;
+  const bool ij_bnd = (i == 0 || i == LX - 1 || j == 0 || j == LX - 1);
+#pragma unroll
+  for (int k = 0; k < LX; ++k) {
+    const int64_t p = base + k * N2;
+    double v = wk[k];
+    if (h2 != 0.0) v = fma(h2 * ld_stream1(bm1 + p), uk[k], v);
+    if (EPI == 1) {
+      const bool bnd = ij_bnd || k == 0 || k == LX - 1;
+      if (!bnd) v = alpha * uk[k] + beta * ld_stream1(bmask + p) * v;
+    }
+    w[p] = v;
+  }
+}
+
+// ---- axhelm, 2-D (one thread per point; parity configurations only) --------------------------
+template <bool CONV, int EPI>
+__global__ void axhelm2d_kernel(const double *__restrict__ u, double *__restrict__ w,
+                                const double *__restrict__ g, const double *__restrict__ bm1,
+                                const double *__restrict__ Dg, int lx, int64_t nel, int64_t npts,
+                                double h1, double h2, const double *__restrict__ cv, double alpha,
+                                double beta, const double *__restrict__ bmask) {
+  extern __shared__ double sm[];
+  const int n2 = lx * lx;
+  double *sD = sm, *s_u = sm + n2, *s_wr = sm + 2 * n2, *s_ws = sm + 3 * n2;
+  const int64_t e = blockIdx.x;
+  const int t = threadIdx.x, i = t % lx, j = t / lx;
+  const int64_t p = e * n2 + t;
+  const double uv = u[p];
+  sD[t] = Dg[i + lx * j];  // sD[j*lx + i] = D_ij  -> sD[b*lx + a] = D_ab
+  s_u[t] = uv;
+  __syncthreads();
+  double ur = 0, us = 0;
+  for (int l = 0; l < lx; ++l) {
+    ur = fma(sD[l * lx + i], s_u[j * lx + l], ur);  // D_il u(l,j)
+    us = fma(sD[l * lx + j], s_u[l * lx + i], us);  // D_jl u(i,l)
+  }
+  const double g1 = g[p], g2 = g[npts + p], g4 = g[2 * npts + p];
+  s_wr[t] = h1 * (g1 * ur + g4 * us);
+  s_ws[t] = h1 * (g2 * us + g4 * ur);
+  __syncthreads();
+  double v = CONV ? (cv[p] * ur + cv[npts + p] * us) : 0.0;
+  for (int l = 0; l < lx; ++l) {
+    v = fma(sD[i * lx + l], s_wr[j * lx + l], v);  // D_li wr(l,j)
+    v = fma(sD[j * lx + l], s_ws[l * lx + i], v);  // D_lj ws(i,l)
+  }
+  if (h2 != 0.0) v = fma(h2 * bm1[p], uv, v);
+  if (EPI == 1) {
+    const bool bnd = (i == 0 || i == lx - 1 || j == 0 || j == lx - 1);
+    if (!bnd) v = alpha * uv + beta * bmask[p] * v;
+  }
+  w[p] = v;
+}
+
+// ---- gather-scatter ---------------------------------------------------------------------------
+// One thread per unique node that owns at least one element-boundary point.
+//   EPI = 0 : every copy <- sum of copies                                  (dssum)
+//   EPI = 1 : every copy p <- alpha * uin[p] + beta * bmask[p] * sum       (fused operator tail)
+//   EPI = 2 : only write the node sums to node_sum (multi-rank first phase)
+//   EPI = 3 : scatter node_sum with the EPI=0 rule,  EPI = 4 : scatter with the EPI=1 rule
+template <int EPI>
+__global__ void __launch_bounds__(256)
+gs_kernel(double *__restrict__ v, const int64_t *__restrict__ off, const int32_t *__restrict__ idx,
+          int64_t nnodes, const double *__restrict__ uin, double alpha, double beta,
+          const double *__restrict__ bmask, double *__restrict__ node_sum) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnodes) return;
+  const int64_t a = off[n], b = off[n + 1];
+  double s = 0.0;
+  if (EPI == 3 || EPI == 4) {
+    s = node_sum[n];
+  } else {
+    for (int64_t q = a; q < b; ++q) s += v[idx[q]];
+  }
+  if (EPI == 2) {
+    node_sum[n] = s;
+    return;
+  }
+  for (int64_t q = a; q < b; ++q) {
+    const int32_t p = idx[q];
+    if (EPI == 0 || EPI == 3) v[p] = s;
+    else v[p] = alpha * uin[p] + beta * bmask[p] * s;
+  }
+}
+
+__global__ void pack_kernel(const double *__restrict__ node_sum, const int32_t *__restrict__ nodes,
+                            int64_t n, double *__restrict__ buf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) buf[t] = node_sum[nodes[t]];
+}
+
+__global__ void unpack_add_kernel(double *__restrict__ node_sum, const int32_t *__restrict__ nodes,
+                                  int64_t n, const double *__restrict__ buf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) node_sum[nodes[t]] += buf[t];
+}
+
+__global__ void col2_kernel(double *__restrict__ v, const double *__restrict__ c, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) v[t] *= c[t];
+}
+
+__global__ void recip_kernel(double *__restrict__ v, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) v[t] = 1.0 / v[t];
+}
+
+__global__ void mul3_kernel(double *__restrict__ out, const double *__restrict__ a,
+                            const double *__restrict__ b, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) out[t] = a[t] * b[t];
+}
+
+// contravariant convecting velocity times quadrature weight: C_r = w3 (cx rx + cy ry + cz rz) ...
+__global__ void conv_coeff_kernel(const double *__restrict__ rst, const double *__restrict__ cx,
+                                  const double *__restrict__ cy, const double *__restrict__ cz,
+                                  const double *__restrict__ wq, int dim, int lx, int64_t npts,
+                                  double *__restrict__ cv) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  int nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  const int loc = (int)(p % nloc);
+  const int i = loc % lx, j = (loc / lx) % lx, k = loc / (lx * lx);
+  if (dim == 3) {
+    const double w3 = wq[i] * wq[j] * wq[k];
+    for (int a = 0; a < 3; ++a)
+      cv[a * npts + p] = w3 * (cx[p] * rst[(3 * a + 0) * npts + p] + cy[p] * rst[(3 * a + 1) * npts + p] +
+                               cz[p] * rst[(3 * a + 2) * npts + p]);
+  } else {
+    const double w2 = wq[i] * wq[j];
+    for (int a = 0; a < 2; ++a)
+      cv[a * npts + p] = w2 * (cx[p] * rst[(2 * a + 0) * npts + p] + cy[p] * rst[(2 * a + 1) * npts + p]);
+  }
+}
+
+template <int LX, bool CONV, int EPI>
+void launch_ax3d_t(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
+                   double alpha, double beta, const double *bmask) {
+  constexpr int EPC = (256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1);
+  const int64_t grid = (S->nel + EPC - 1) / EPC;
+  axhelm3d_kernel<LX, CONV, EPI><<<(unsigned)grid, EPC * LX * LX, 0, S->ctx->stream>>>(
+      u, w, S->g_d, S->bm1_d, S->D_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask);
+}
+
+template <bool CONV, int EPI>
+int launch_ax3d(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
+                double alpha, double beta, const double *bmask) {
+  switch (S->lx) {
+#define CASE(L) case L: launch_ax3d_t<L, CONV, EPI>(S, u, w, h1, h2, cv, alpha, beta, bmask); break;
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+    default:
+      set_error("axhelm: lx1=%d not instantiated (2..12)", S->lx);
+      return NSB_EINVAL;
+  }
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+template <bool CONV, int EPI>
+int launch_ax2d(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
+                double alpha, double beta, const double *bmask) {
+  const int n2 = S->lx * S->lx;
+  axhelm2d_kernel<CONV, EPI><<<(unsigned)S->nel, n2, sizeof(double) * 4 * n2, S->ctx->stream>>>(
+      u, w, S->g_d, S->bm1_d, S->D_d, S->lx, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+int launch_axhelm(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
+                  int epi, double alpha, double beta, const double *bmask) {
+  cudaSetDevice(S->ctx->device);
+  if (S->dim == 3) {
+    if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
+                       : launch_ax3d<true, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
+    return epi ? launch_ax3d<false, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
+               : launch_ax3d<false, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
+  }
+  if (cv) return epi ? launch_ax2d<true, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
+                     : launch_ax2d<true, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
+  return epi ? launch_ax2d<false, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
+             : launch_ax2d<false, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
+}
+
+inline unsigned blocks_for(int64_t n, int nt = 256) { return (unsigned)((n + nt - 1) / nt); }
+
+// gather-scatter incl. the inter-rank exchange; epi 0: plain dssum, 1: fused operator tail
+int launch_gs(nsb_sem_t S, double *v, int epi, const double *uin, double alpha, double beta,
+              const double *bmask) {
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  if (S->nshared == 0) return NSB_OK;
+  const unsigned nb = blocks_for(S->nshared);
+  if (ctx->nranks == 1 || S->peers.empty()) {
+    if (ctx->nranks > 1 && !S->exchange_ready) {
+      set_error("dssum: nsb_sem_setup_exchange has not been called on this multi-rank context");
+      return NSB_EINVAL;
+    }
+    if (epi == 0)
+      gs_kernel<0><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, nullptr, 0, 0, nullptr, nullptr);
+    else
+      gs_kernel<1><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, uin, alpha, beta, bmask, nullptr);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
+  // multi-rank: local node sums -> pack -> exchange -> add -> scatter
+  double *ns = S->node_sum_d;
+  gs_kernel<2><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, nullptr, 0, 0, nullptr, ns);
+  ctx->launches++;
+  for (auto &P : S->peers) {
+    pack_kernel<<<blocks_for(P.n), 256, 0, ctx->stream>>>(ns, P.idx_d, P.n, P.send_d);
+    ctx->launches++;
+  }
+  NSB_CUDA(cudaGetLastError());
+  NSB_CHECK(sendrecv_d(ctx, S->peers));
+  for (auto &P : S->peers) {
+    unpack_add_kernel<<<blocks_for(P.n), 256, 0, ctx->stream>>>(ns, P.idx_d, P.n, P.recv_d);
+    ctx->launches++;
+  }
+  if (epi == 0)
+    gs_kernel<3><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, nullptr, 0, 0, nullptr, ns);
+  else
+    gs_kernel<4><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, uin, alpha, beta, bmask, ns);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+int field_ptr(nsb_sem_t S, nsb_basis_t B, int col, int field, double **out, const char *who) {
+  NSB_REQUIRE(S && B, "%s: NULL argument", who);
+  NSB_REQUIRE(col >= 0 && col < B->ncols, "%s: column %d out of range", who, col);
+  nsb_layout_t L = B->lay;
+  NSB_REQUIRE(field >= 0 && field < L->nfields, "%s: field %d out of range", who, field);
+  NSB_REQUIRE(L->len[field] == S->npts, "%s: field %d has %lld points, mesh has %lld", who, field,
+              (long long)L->len[field], (long long)S->npts);
+  NSB_REQUIRE(L->ctx == S->ctx, "%s: basis and mesh live on different contexts", who);
+  *out = B->col(col) + L->off[field];
+  return NSB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// mesh object
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_sem_create(nsb_context_t ctx, int dim, int N, int64_t nel, const double *x,
+                              const double *y, const double *z, const double *mask,
+                              const int64_t *glo_num, nsb_sem_t *out) {
+  NSB_REQUIRE(ctx && out && x && y && glo_num, "nsb_sem_create: NULL argument");
+  NSB_REQUIRE(dim == 2 || dim == 3, "nsb_sem_create: dim=%d", dim);
+  NSB_REQUIRE(dim == 2 || z != nullptr, "nsb_sem_create: z is NULL in 3-D");
+  NSB_REQUIRE(N >= 1 && N <= 11, "nsb_sem_create: N=%d (1..11 supported)", N);
+  NSB_REQUIRE(nel >= 1, "nsb_sem_create: nel=%lld", (long long)nel);
+  const int lx = N + 1;
+  int64_t nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  const int64_t npts = nel * nloc;
+  NSB_REQUIRE(npts < ((int64_t)1 << 31), "nsb_sem_create: %lld points exceed the int32 index range",
+              (long long)npts);
+  cudaSetDevice(ctx->device);
+  nsb_sem_t S = new nsb_sem_s();
+  S->ctx = ctx;
+  S->dim = dim;
+  S->N = N;
+  S->lx = lx;
+  S->nel = nel;
+  S->npts = npts;
+  S->ng = dim == 3 ? 6 : 3;
+  S->D_h.resize(lx * lx);
+  S->z_h.resize(lx);
+  S->w_h.resize(lx);
+  nsb_gll(N, S->z_h.data(), S->w_h.data(), S->D_h.data());
+  const size_t nb = sizeof(double) * npts;
+  double *wq_d = nullptr, *xyz_d = nullptr;
+  NSB_CUDA(cudaMalloc(&S->D_d, sizeof(double) * lx * lx));
+  NSB_CUDA(cudaMalloc(&wq_d, sizeof(double) * lx));
+  NSB_CUDA(cudaMalloc(&xyz_d, nb * dim));
+  NSB_CUDA(cudaMalloc(&S->g_d, nb * S->ng));
+  NSB_CUDA(cudaMalloc(&S->bm1_d, nb));
+  NSB_CUDA(cudaMalloc(&S->jac_d, nb));
+  NSB_CUDA(cudaMalloc(&S->binv_d, nb));
+  NSB_CUDA(cudaMalloc(&S->vmult_d, nb));
+  NSB_CUDA(cudaMalloc(&S->mask_d, nb));
+  NSB_CUDA(cudaMalloc(&S->bmask_d, nb));
+  NSB_CUDA(cudaMalloc(&S->rst_d, nb * dim * dim));
+  cudaStream_t s = ctx->stream;
+  NSB_CUDA(cudaMemcpyAsync(S->D_d, S->D_h.data(), sizeof(double) * lx * lx, cudaMemcpyHostToDevice, s));
+  NSB_CUDA(cudaMemcpyAsync(wq_d, S->w_h.data(), sizeof(double) * lx, cudaMemcpyHostToDevice, s));
+  NSB_CUDA(cudaMemcpyAsync(xyz_d, x, nb, cudaMemcpyHostToDevice, s));
+  NSB_CUDA(cudaMemcpyAsync(xyz_d + npts, y, nb, cudaMemcpyHostToDevice, s));
+  if (dim == 3) NSB_CUDA(cudaMemcpyAsync(xyz_d + 2 * npts, z, nb, cudaMemcpyHostToDevice, s));
+  if (dim == 3)
+    geom3d_kernel<<<blocks_for(npts), 256, 0, s>>>(xyz_d, xyz_d + npts, xyz_d + 2 * npts, S->D_d, wq_d, lx,
+                                                   npts, S->g_d, S->bm1_d, S->jac_d, S->rst_d);
+  else
+    geom2d_kernel<<<blocks_for(npts), 256, 0, s>>>(xyz_d, xyz_d + npts, S->D_d, wq_d, lx, npts, S->g_d,
+                                                   S->bm1_d, S->jac_d, S->rst_d);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+
+  // gather-scatter lists: unique nodes owning at least one element-boundary point, CSR,
+  // ordered by first local index so neighbouring threads touch neighbouring memory.
+  S->glo_h.assign(glo_num, glo_num + npts);
+  std::vector<int32_t> bpts;
+  bpts.reserve((size_t)(npts * 0.6));
+  for (int64_t p = 0; p < npts; ++p) {
+    const int loc = (int)(p % nloc);
+    const int i = loc % lx, j = (loc / lx) % lx, k = dim == 3 ? loc / (lx * lx) : 1;
+    const bool bnd = i == 0 || i == lx - 1 || j == 0 || j == lx - 1 ||
+                     (dim == 3 && (k == 0 || k == lx - 1));
+    if (bnd) bpts.push_back((int32_t)p);
+    if (glo_num[p] < 0) {
+      set_error("nsb_sem_create: negative global id at point %lld", (long long)p);
+      return NSB_EINVAL;
+    }
+  }
+  std::stable_sort(bpts.begin(), bpts.end(),
+                   [&](int32_t a, int32_t b) { return glo_num[a] < glo_num[b]; });
+  std::vector<int64_t> grp_start;
+  for (size_t q = 0; q < bpts.size(); ++q)
+    if (q == 0 || glo_num[bpts[q]] != glo_num[bpts[q - 1]]) grp_start.push_back((int64_t)q);
+  const int64_t ngrp = (int64_t)grp_start.size();
+  grp_start.push_back((int64_t)bpts.size());
+  std::vector<int64_t> order(ngrp);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(),
+            [&](int64_t a, int64_t b) { return bpts[grp_start[a]] < bpts[grp_start[b]]; });
+  std::vector<int64_t> off(ngrp + 1, 0);
+  std::vector<int32_t> idx(bpts.size());
+  S->node_gid.resize(ngrp);
+  std::vector<double> vm(npts, 1.0);
+  int64_t w0 = 0;
+  for (int64_t n = 0; n < ngrp; ++n) {
+    const int64_t gI = order[n];
+    off[n] = w0;
+    const int64_t cnt = grp_start[gI + 1] - grp_start[gI];
+    for (int64_t q = grp_start[gI]; q < grp_start[gI + 1]; ++q) {
+      idx[w0++] = bpts[q];
+      vm[bpts[q]] = 1.0 / (double)cnt;
+      if (mask && mask[bpts[q]] != mask[bpts[grp_start[gI]]]) {
+        set_error("nsb_sem_create: mask differs between copies of global node %lld",
+                  (long long)glo_num[bpts[q]]);
+        return NSB_EINVAL;
+      }
+    }
+    S->node_gid[n] = glo_num[bpts[grp_start[gI]]];
+  }
+  off[ngrp] = w0;
+  S->nshared = ngrp;
+  S->gs_nnz = w0;
+  NSB_CUDA(cudaMalloc(&S->gs_off_d, sizeof(int64_t) * (ngrp + 1)));
+  NSB_CUDA(cudaMalloc(&S->gs_idx_d, sizeof(int32_t) * (w0 > 0 ? w0 : 1)));
+  NSB_CUDA(cudaMalloc(&S->node_sum_d, sizeof(double) * (ngrp > 0 ? ngrp : 1)));
+  NSB_CUDA(cudaMemcpyAsync(S->gs_off_d, off.data(), sizeof(int64_t) * (ngrp + 1), cudaMemcpyHostToDevice, s));
+  NSB_CUDA(cudaMemcpyAsync(S->gs_idx_d, idx.data(), sizeof(int32_t) * w0, cudaMemcpyHostToDevice, s));
+  NSB_CUDA(cudaMemcpyAsync(S->vmult_d, vm.data(), nb, cudaMemcpyHostToDevice, s));
+  if (mask) {
+    NSB_CUDA(cudaMemcpyAsync(S->mask_d, mask, nb, cudaMemcpyHostToDevice, s));
+  } else {
+    std::vector<double> ones(npts, 1.0);
+    NSB_CUDA(cudaMemcpyAsync(S->mask_d, ones.data(), nb, cudaMemcpyHostToDevice, s));
+    NSB_CUDA(cudaStreamSynchronize(s));
+  }
+  NSB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(wq_d);
+  cudaFree(xyz_d);
+  *out = S;
+  if (ctx->nranks == 1) return nsb_sem_setup_exchange(S);
+  return NSB_OK;
+}
+
+// binvm1 = 1/dssum(bm1) and bmask = binvm1*mask need the (possibly inter-rank) dssum
+static int finish_assembled(nsb_sem_t S) {
+  nsb_context_t ctx = S->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t nb = sizeof(double) * S->npts;
+  NSB_CUDA(cudaMemcpyAsync(S->binv_d, S->bm1_d, nb, cudaMemcpyDeviceToDevice, s));
+  NSB_CHECK(launch_gs(S, S->binv_d, 0, nullptr, 0, 0, nullptr));
+  recip_kernel<<<ctx->num_sms * 8, 256, 0, s>>>(S->binv_d, S->npts);
+  mul3_kernel<<<ctx->num_sms * 8, 256, 0, s>>>(S->bmask_d, S->binv_d, S->mask_d, S->npts);
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  if (ctx->nranks > 1) {
+    // vmult = 1/global multiplicity
+    std::vector<double> ones(S->npts, 1.0);
+    NSB_CUDA(cudaMemcpyAsync(S->vmult_d, ones.data(), nb, cudaMemcpyHostToDevice, s));
+    NSB_CHECK(launch_gs(S, S->vmult_d, 0, nullptr, 0, 0, nullptr));
+    recip_kernel<<<ctx->num_sms * 8, 256, 0, s>>>(S->vmult_d, S->npts);
+    ctx->launches++;
+    NSB_CUDA(cudaStreamSynchronize(s));
+  }
+  NSB_CUDA(cudaStreamSynchronize(s));
+  return NSB_OK;
+}
+
+extern "C" int nsb_sem_setup_exchange(nsb_sem_t S) {
+  NSB_REQUIRE(S, "nsb_sem_setup_exchange: NULL");
+  if (S->ctx->nranks > 1) NSB_CHECK(nsb::exchange_setup(S));
+  S->exchange_ready = true;
+  return finish_assembled(S);
+}
+
+extern "C" int nsb_sem_destroy(nsb_sem_t S) {
+  if (!S) return NSB_OK;
+  cudaSetDevice(S->ctx->device);
+  cudaStreamSynchronize(S->ctx->stream);
+  for (auto &P : S->peers) {
+    cudaFree(P.idx_d);
+    cudaFree(P.send_d);
+    cudaFree(P.recv_d);
+  }
+  double *ptrs[] = {S->g_d, S->bm1_d, S->jac_d, S->binv_d, S->vmult_d, S->mask_d, S->bmask_d,
+                    S->rst_d, S->D_d, S->node_sum_d};
+  for (double *p : ptrs)
+    if (p) cudaFree(p);
+  if (S->gs_off_d) cudaFree(S->gs_off_d);
+  if (S->gs_idx_d) cudaFree(S->gs_idx_d);
+  delete S;
+  return NSB_OK;
+}
+
+extern "C" int64_t nsb_sem_npts(nsb_sem_t S) { return S ? S->npts : -1; }
+
+extern "C" int nsb_sem_get(nsb_sem_t S, int which, double *out) {
+  NSB_REQUIRE(S && out, "nsb_sem_get: NULL argument");
+  const double *src = nullptr;
+  switch (which) {
+    case 0: src = S->bm1_d; break;
+    case 1: src = S->jac_d; break;
+    case 2: src = S->binv_d; break;
+    case 3: src = S->vmult_d; break;
+    case 4: src = S->mask_d; break;
+    default:
+      if (which >= 10 && which < 16) {
+        int gi = which - 10;
+        if (S->dim == 2) {
+          NSB_REQUIRE(gi == 0 || gi == 1 || gi == 3, "nsb_sem_get: 2-D has G1, G2, G4 only");
+          gi = gi == 3 ? 2 : gi;
+        }
+        src = S->g_d + (size_t)gi * S->npts;
+      }
+  }
+  NSB_REQUIRE(src, "nsb_sem_get: unknown selector %d", which);
+  cudaSetDevice(S->ctx->device);
+  NSB_CUDA(cudaMemcpyAsync(out, src, sizeof(double) * S->npts, cudaMemcpyDeviceToHost, S->ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(S->ctx->stream));
+  return NSB_OK;
+}
+
+extern "C" int nsb_sem_axhelm(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
+                              int field, double h1, double h2) {
+  double *u, *w;
+  NSB_CHECK(field_ptr(S, bin, cin, field, &u, "nsb_sem_axhelm"));
+  NSB_CHECK(field_ptr(S, bout, cout, field, &w, "nsb_sem_axhelm"));
+  NSB_REQUIRE(u != w, "nsb_sem_axhelm: in-place application is not supported");
+  return launch_axhelm(S, u, w, h1, h2, nullptr, 0, 0, 0, nullptr);
+}
+
+extern "C" int nsb_sem_dssum(nsb_sem_t S, nsb_basis_t B, int col, int field) {
+  double *v;
+  NSB_CHECK(field_ptr(S, B, col, field, &v, "nsb_sem_dssum"));
+  return launch_gs(S, v, 0, nullptr, 0, 0, nullptr);
+}
+
+extern "C" int nsb_sem_col2(nsb_sem_t S, nsb_basis_t B, int col, int field, int which) {
+  double *v;
+  NSB_CHECK(field_ptr(S, B, col, field, &v, "nsb_sem_col2"));
+  const double *c = which == 0 ? S->bm1_d : which == 2 ? S->binv_d : which == 3 ? S->vmult_d
+                    : which == 4 ? S->mask_d : nullptr;
+  NSB_REQUIRE(c, "nsb_sem_col2: unknown selector %d", which);
+  cudaSetDevice(S->ctx->device);
+  col2_kernel<<<S->ctx->num_sms * 8, 256, 0, S->ctx->stream>>>(v, c, S->npts);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+extern "C" int nsb_sem_ax(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
+                          int field, double h1, double h2) {
+  NSB_CHECK(nsb_sem_axhelm(S, bin, cin, bout, cout, field, h1, h2));
+  NSB_CHECK(nsb_sem_dssum(S, bout, cout, field));
+  return nsb_sem_col2(S, bout, cout, field, 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operators
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_op_create_sem(nsb_sem_t S, int nfields_apply, double alpha, double beta, double h1,
+                                 double h2, const double *cx, const double *cy, const double *cz,
+                                 nsb_op_t *out) {
+  NSB_REQUIRE(S && out && nfields_apply >= 1, "nsb_op_create_sem: bad argument");
+  NSB_REQUIRE(S->exchange_ready, "nsb_op_create_sem: call nsb_sem_setup_exchange first");
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 0;
+  op->sem = S;
+  op->nfields_apply = nfields_apply;
+  op->alpha = alpha;
+  op->beta = beta;
+  op->h1 = h1;
+  op->h2 = h2;
+  if (cx) {
+    NSB_REQUIRE(cy && (S->dim == 2 || cz), "nsb_op_create_sem: incomplete convecting velocity");
+    nsb_context_t ctx = S->ctx;
+    cudaSetDevice(ctx->device);
+    const size_t nb = sizeof(double) * S->npts;
+    double *c_in = nullptr, *wq_d = nullptr;
+    NSB_CUDA(cudaMalloc(&c_in, nb * 3));
+    NSB_CUDA(cudaMalloc(&wq_d, sizeof(double) * S->lx));
+    NSB_CUDA(cudaMalloc(&op->c_d, nb * S->dim));
+    NSB_CUDA(cudaMemcpyAsync(c_in, cx, nb, cudaMemcpyHostToDevice, ctx->stream));
+    NSB_CUDA(cudaMemcpyAsync(c_in + S->npts, cy, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (S->dim == 3) NSB_CUDA(cudaMemcpyAsync(c_in + 2 * S->npts, cz, nb, cudaMemcpyHostToDevice, ctx->stream));
+    NSB_CUDA(cudaMemcpyAsync(wq_d, S->w_h.data(), sizeof(double) * S->lx, cudaMemcpyHostToDevice, ctx->stream));
+    conv_coeff_kernel<<<blocks_for(S->npts), 256, 0, ctx->stream>>>(
+        S->rst_d, c_in, c_in + S->npts, c_in + 2 * S->npts, wq_d, S->dim, S->lx, S->npts, op->c_d);
+    ctx->launches++;
+    NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(c_in);
+    cudaFree(wq_d);
+  }
+  *out = op;
+  return NSB_OK;
+}
+
+extern "C" int nsb_op_create_host(nsb_layout_t L, nsb_host_matvec_fn fn, void *user, nsb_op_t *out) {
+  NSB_REQUIRE(L && fn && out, "nsb_op_create_host: NULL argument");
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 1;
+  op->lay = L;
+  op->fn = fn;
+  op->user = user;
+  op->hin.resize(L->nfields);
+  op->hout.resize(L->nfields);
+  for (int f = 0; f < L->nfields; ++f) {
+    op->hin[f].resize(L->len[f]);
+    op->hout[f].resize(L->len[f]);
+  }
+  *out = op;
+  return NSB_OK;
+}
+
+extern "C" int nsb_op_destroy(nsb_op_t op) {
+  if (!op) return NSB_OK;
+  if (op->c_d) cudaFree(op->c_d);
+  delete op;
+  return NSB_OK;
+}
+
+extern "C" int nsb_op_count(nsb_op_t op, int64_t *n) {
+  NSB_REQUIRE(op && n, "nsb_op_count: NULL argument");
+  *n = op->napply;
+  return NSB_OK;
+}
+
+extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  NSB_REQUIRE(op && bin && bout, "nsb_op_apply: NULL argument");
+  NSB_REQUIRE(cin >= 0 && cin < bin->ncols && cout >= 0 && cout < bout->ncols,
+              "nsb_op_apply: column out of range");
+  NSB_REQUIRE(bin->lay == bout->lay, "nsb_op_apply: different layouts");
+  NSB_REQUIRE(!(bin == bout && cin == cout), "nsb_op_apply: in-place application is not supported");
+  op->napply++;
+  if (op->kind == 1) {
+    nsb_layout_t L = bin->lay;
+    std::vector<const double *> pin(L->nfields);
+    std::vector<double *> pout(L->nfields), pdl(L->nfields);
+    for (int f = 0; f < L->nfields; ++f) {
+      pin[f] = op->hin[f].data();
+      pdl[f] = op->hin[f].data();
+      pout[f] = op->hout[f].data();
+    }
+    double tin = 0.0, tout = 0.0;
+    NSB_CHECK(nsb_vec_download(bin, cin, pdl.data(), &tin));
+    int r = op->fn(op->user, pin.data(), tin, pout.data(), &tout);
+    if (r != 0) {
+      set_error("nsb_op_apply: host matvec callback returned %d", r);
+      return NSB_EINVAL;
+    }
+    return nsb_vec_upload(bout, cout, pout.data(), tout);
+  }
+  nsb_sem_t S = op->sem;
+  nsb_layout_t L = bin->lay;
+  NSB_REQUIRE(op->nfields_apply <= L->nfields, "nsb_op_apply: operator covers %d fields, layout has %d",
+              op->nfields_apply, L->nfields);
+  for (int f = 0; f < op->nfields_apply; ++f) {
+    double *u, *w;
+    NSB_CHECK(field_ptr(S, bin, cin, f, &u, "nsb_op_apply"));
+    NSB_CHECK(field_ptr(S, bout, cout, f, &w, "nsb_op_apply"));
+    NSB_CHECK(launch_axhelm(S, u, w, op->h1, op->h2, op->c_d, 1, op->alpha, op->beta, S->bmask_d));
+    NSB_CHECK(launch_gs(S, w, 1, u, op->alpha, op->beta, S->bmask_d));
+  }
+  // fields outside the operator (pressure, scalars, %time) are carried through unchanged
+  if (op->nfields_apply < L->nfields || true) {
+    // copy the rows not covered by the applied fields: time row and remaining fields
+    cudaStream_t s = L->ctx->stream;
+    NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->time_row, bin->col(cin) + L->time_row, sizeof(double),
+                             cudaMemcpyDeviceToDevice, s));
+    for (int f = op->nfields_apply; f < L->nfields; ++f)
+      if (L->len[f] > 0)
+        NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->off[f], bin->col(cin) + L->off[f],
+                                 sizeof(double) * L->len[f], cudaMemcpyDeviceToDevice, s));
+  }
+  return NSB_OK;
+}

@@ -1,0 +1,278 @@
+"""Spectral-element pieces of the oracle (numpy, fp64).  TEST INFRASTRUCTURE ONLY.
+
+Restates the Nek5000 routines the reference reaches through ``nek_advance``
+(reference call site ``core/linear_operators.f90:247``).
+Nek5000 itself is not vendored in /root/reference, so the formulas follow the
+published algorithm ([UPSTREAM-RECALL]: ``speclib.f`` zwgll/dgll, ``coef.f``
+geom1/glmapm1/geodat1, ``hmholtz.f`` axhelm, ``navier5.f`` local_grad3,
+``math.f`` glsc3, gslib gs_op(add) behind ``dssum``).
+
+Array layout is Nek's element-local one: ``u[e, k, j, i]`` with ``i`` fastest
+(C order of shape (nel, lz, ly, lx)), shared nodes duplicated.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------
+# GLL quadrature and derivative matrix  ([UPSTREAM-RECALL] speclib.f zwgll/dgll)
+# ----------------------------------------------------------------------------
+def _legendre(n: int, x: np.ndarray):
+    """P_n(x) and P_{n-1}(x) by the three-term recurrence."""
+    p0 = np.ones_like(x)
+    if n == 0:
+        return p0, np.zeros_like(x)
+    p1 = x.copy()
+    for m in range(1, n):
+        p0, p1 = p1, ((2 * m + 1) * x * p1 - m * p0) / (m + 1)
+    return p1, p0
+
+
+def gll(n: int):
+    """Nodes z[0..n] (ascending, in [-1,1]) and weights w of the (n+1)-point GLL rule.
+
+    Interior nodes are the roots of P_n'(x); w_i = 2 / (n (n+1) P_n(z_i)^2).
+    """
+    if n < 1:
+        raise ValueError("polynomial order must be >= 1")
+    x = -np.cos(np.pi * np.arange(n + 1) / n)  # Chebyshev-Lobatto start
+    for _ in range(100):
+        pn, pnm1 = _legendre(n, x)
+        # q(x) = (1-x^2) P_n'(x) = n (P_{n-1} - x P_n);  q'(x) = -n (n+1) P_n
+        q = n * (pnm1 - x * pn)
+        dq = -n * (n + 1) * pn
+        dx = q / dq
+        dx[0] = dx[-1] = 0.0
+        x = x - dx
+        if np.max(np.abs(dx)) < 1e-16:
+            break
+    x[0], x[-1] = -1.0, 1.0
+    x = 0.5 * (x - x[::-1])  # enforce antisymmetry
+    pn, _ = _legendre(n, x)
+    w = 2.0 / (n * (n + 1) * pn * pn)
+    return x, w
+
+
+def dgll(n: int):
+    """GLL derivative matrix D[i, j] = dl_j/dx (z_i):  (du/dr)_i = sum_j D[i,j] u_j."""
+    z, _ = gll(n)
+    pn, _ = _legendre(n, z)
+    d = np.zeros((n + 1, n + 1))
+    for i in range(n + 1):
+        for j in range(n + 1):
+            if i != j:
+                d[i, j] = pn[i] / (pn[j] * (z[i] - z[j]))
+    d[0, 0] = -n * (n + 1) / 4.0
+    d[n, n] = n * (n + 1) / 4.0
+    return d
+
+
+# ----------------------------------------------------------------------------
+# Meshes
+# ----------------------------------------------------------------------------
+def box_mesh(nelx, nely, nelz, n, deform=0.0, lengths=(1.0, 1.0, 1.0)):
+    """Structured box of nelx*nely*nelz hexahedra of order n on [0,L]^3.
+
+    Returns x, y, z of shape (nel, lx, lx, lx) (element order: ex fastest) and the
+    0-based lexicographic unique-node numbering ``glo`` (int64, same shape).
+    ``deform`` adds the smooth map of SURVEY.md section 8d (variant B).
+    """
+    lx = n + 1
+    zg, _ = gll(n)
+    r = 0.5 * (zg + 1.0)
+
+    def line(nel, length):
+        h = length / nel
+        return (np.arange(nel)[:, None] + r[None, :]) * h  # (nel, lx)
+
+    xl, yl, zl = line(nelx, lengths[0]), line(nely, lengths[1]), line(nelz, lengths[2])
+    nel = nelx * nely * nelz
+    x = np.empty((nelz, nely, nelx, lx, lx, lx))
+    y = np.empty_like(x)
+    z = np.empty_like(x)
+    x[:] = xl[None, None, :, None, None, :]
+    y[:] = yl[None, :, None, None, :, None]
+    z[:] = zl[:, None, None, :, None, None]
+    gi = (np.arange(nelx)[:, None] * n + np.arange(lx)[None, :]).astype(np.int64)
+    gj = (np.arange(nely)[:, None] * n + np.arange(lx)[None, :]).astype(np.int64)
+    gk = (np.arange(nelz)[:, None] * n + np.arange(lx)[None, :]).astype(np.int64)
+    nxg, nyg = nelx * n + 1, nely * n + 1
+    glo = np.empty(x.shape, dtype=np.int64)
+    glo[:] = (gk[:, None, None, :, None, None] * nyg + gj[None, :, None, None, :, None]) * nxg \
+        + gi[None, None, :, None, None, :]
+    x = x.reshape(nel, lx, lx, lx)
+    y = y.reshape(nel, lx, lx, lx)
+    z = z.reshape(nel, lx, lx, lx)
+    glo = glo.reshape(nel, lx, lx, lx)
+    if deform != 0.0:
+        bump = deform * np.sin(np.pi * x / lengths[0]) * np.sin(np.pi * y / lengths[1]) \
+            * np.sin(np.pi * z / lengths[2])
+        x, y, z = x + bump, y + bump, z + bump
+    return x, y, z, glo
+
+
+def box_mesh_2d(nelx, nely, n, deform=0.0, lengths=(1.0, 1.0)):
+    lx = n + 1
+    zg, _ = gll(n)
+    r = 0.5 * (zg + 1.0)
+    xl = (np.arange(nelx)[:, None] + r[None, :]) * (lengths[0] / nelx)
+    yl = (np.arange(nely)[:, None] + r[None, :]) * (lengths[1] / nely)
+    x = np.empty((nely, nelx, lx, lx))
+    y = np.empty_like(x)
+    x[:] = xl[None, :, None, :]
+    y[:] = yl[:, None, :, None]
+    gi = (np.arange(nelx)[:, None] * n + np.arange(lx)[None, :]).astype(np.int64)
+    gj = (np.arange(nely)[:, None] * n + np.arange(lx)[None, :]).astype(np.int64)
+    glo = np.empty(x.shape, dtype=np.int64)
+    glo[:] = gj[:, None, :, None] * (nelx * n + 1) + gi[None, :, None, :]
+    nel = nelx * nely
+    x, y, glo = x.reshape(nel, lx, lx), y.reshape(nel, lx, lx), glo.reshape(nel, lx, lx)
+    if deform != 0.0:
+        bump = deform * np.sin(np.pi * x / lengths[0]) * np.sin(np.pi * y / lengths[1])
+        x, y = x + bump, y + bump
+    return x, y, glo
+
+
+def glo_num_from_coords(coords, tol=1e-8):
+    """Global numbering by coordinate matching (for the Nek field-file fixtures).
+
+    ``coords`` is a tuple of arrays of identical shape; points closer than ``tol``
+    (relative to the domain extent) share an id.  Returns int64 ids, 0-based.
+    """
+    shape = coords[0].shape
+    pts = np.stack([c.ravel() for c in coords], axis=1)
+    span = np.maximum(pts.max(axis=0) - pts.min(axis=0), 1e-300)
+    q = np.round((pts - pts.min(axis=0)) / (span * tol)).astype(np.int64)
+    _, inv = np.unique(q, axis=0, return_inverse=True)
+    return inv.reshape(shape).astype(np.int64)
+
+
+def boundary_mask_box(glo_shape_mesh, x, y, z=None, lengths=(1.0, 1.0, 1.0), tol=1e-12):
+    """Homogeneous-Dirichlet mask: 0 on the box boundary, 1 inside (undeformed coords)."""
+    m = np.ones_like(x)
+    for c, length in zip((x, y, z), lengths):
+        if c is None:
+            continue
+        m[(np.abs(c) < tol) | (np.abs(c - length) < tol)] = 0.0
+    return m
+
+
+# ----------------------------------------------------------------------------
+# Geometry  ([UPSTREAM-RECALL] coef.f glmapm1 / geodat1)
+# ----------------------------------------------------------------------------
+def grad_rst(u, d):
+    """local_grad3 / local_grad2: reference-space derivatives of an element-local field."""
+    if u.ndim == 4:  # (e, k, j, i)
+        ur = np.einsum('il,ekjl->ekji', d, u)
+        us = np.einsum('jl,ekli->ekji', d, u)
+        ut = np.einsum('kl,elji->ekji', d, u)
+        return ur, us, ut
+    ur = np.einsum('il,ejl->eji', d, u)
+    us = np.einsum('jl,eli->eji', d, u)
+    return ur, us
+
+
+def geometry(n, x, y, z=None):
+    """Geometric factors from nodal coordinates.
+
+    3-D returns dict with jac, bm1, g[6] = (G1..G6), and rx..tz (each already times jac
+    as in Nek).  2-D returns g[3] = (G1, G2, G4).
+    """
+    d = dgll(n)
+    _, w = gll(n)
+    if z is not None:
+        xr, xs, xt = grad_rst(x, d)
+        yr, ys, yt = grad_rst(y, d)
+        zr, zs, zt = grad_rst(z, d)
+        jac = xr * (ys * zt - yt * zs) - xs * (yr * zt - yt * zr) + xt * (yr * zs - ys * zr)
+        rx = ys * zt - yt * zs
+        ry = xt * zs - xs * zt
+        rz = xs * yt - xt * ys
+        sx = yt * zr - yr * zt
+        sy = xr * zt - xt * zr
+        sz = xt * yr - xr * yt
+        tx = yr * zs - ys * zr
+        ty = xs * zr - xr * zs
+        tz = xr * ys - xs * yr
+        w3 = w[:, None, None] * w[None, :, None] * w[None, None, :]
+        sc = w3[None] / jac
+        g = np.stack([
+            (rx * rx + ry * ry + rz * rz) * sc,
+            (sx * sx + sy * sy + sz * sz) * sc,
+            (tx * tx + ty * ty + tz * tz) * sc,
+            (rx * sx + ry * sy + rz * sz) * sc,
+            (rx * tx + ry * ty + rz * tz) * sc,
+            (sx * tx + sy * ty + sz * tz) * sc,
+        ])
+        return dict(jac=jac, bm1=jac * w3[None], g=g,
+                    rst=(rx, ry, rz, sx, sy, sz, tx, ty, tz))
+    xr, xs = grad_rst(x, d)
+    yr, ys = grad_rst(y, d)
+    jac = xr * ys - xs * yr
+    rx, ry, sx, sy = ys, -xs, -yr, xr
+    w2 = w[:, None] * w[None, :]
+    sc = w2[None] / jac
+    g = np.stack([(rx * rx + ry * ry) * sc, (sx * sx + sy * sy) * sc, (rx * sx + ry * sy) * sc])
+    return dict(jac=jac, bm1=jac * w2[None], g=g, rst=(rx, ry, sx, sy))
+
+
+# ----------------------------------------------------------------------------
+# Operator kernels
+# ----------------------------------------------------------------------------
+def axhelm(u, g, d, h1=1.0, h2=0.0, bm1=None):
+    """Element-local Helmholtz operator w = h1 * D^T (G (D u)) + h2 * bm1 * u.
+
+    ([UPSTREAM-RECALL] hmholtz.f axhelm, general/deformed branch.)  No dssum, no mask.
+    """
+    if u.ndim == 4:
+        ur, us, ut = grad_rst(u, d)
+        wr = h1 * (g[0] * ur + g[3] * us + g[4] * ut)
+        ws = h1 * (g[1] * us + g[3] * ur + g[5] * ut)
+        wt = h1 * (g[2] * ut + g[4] * ur + g[5] * us)
+        w = np.einsum('li,ekjl->ekji', d, wr) + np.einsum('lj,ekli->ekji', d, ws) \
+            + np.einsum('lk,elji->ekji', d, wt)
+    else:
+        ur, us = grad_rst(u, d)
+        wr = h1 * (g[0] * ur + g[2] * us)
+        ws = h1 * (g[1] * us + g[2] * ur)
+        w = np.einsum('li,ejl->eji', d, wr) + np.einsum('lj,eli->eji', d, ws)
+    if h2 != 0.0:
+        w = w + h2 * bm1 * u
+    return w
+
+
+def dssum(u, glo):
+    """Direct-stiffness summation: every copy of a global node gets the sum of all copies."""
+    flat = glo.ravel()
+    nglob = int(flat.max()) + 1
+    acc = np.bincount(flat, weights=u.ravel(), minlength=nglob)
+    return acc[flat].reshape(u.shape)
+
+
+def multiplicity(glo):
+    flat = glo.ravel()
+    cnt = np.bincount(flat)
+    return cnt[flat].reshape(glo.shape).astype(np.float64)
+
+
+def ax(u, g, d, glo, mask, h1=1.0, h2=0.0, bm1=None):
+    """Nek's ax(w,x,h1,h2,n): axhelm + dssum + col2(mask)."""
+    return dssum(axhelm(u, g, d, h1, h2, bm1), glo) * mask
+
+
+def glsc3(a, b, mult):
+    """sum_i a_i b_i mult_i  ([UPSTREAM-RECALL] math.f glsc3, single rank: no gop)."""
+    return float(np.sum(a.ravel() * b.ravel() * mult.ravel()))
+
+
+def convect(u, vel, rst, d):
+    """Pointwise (times jac) convective derivative  jac * (U . grad) u  via local_grad3."""
+    if u.ndim == 4:
+        ur, us, ut = grad_rst(u, d)
+        rx, ry, rz, sx, sy, sz, tx, ty, tz = rst
+        return (vel[0] * (rx * ur + sx * us + tx * ut) + vel[1] * (ry * ur + sy * us + ty * ut)
+                + vel[2] * (rz * ur + sz * us + tz * ut))
+    ur, us = grad_rst(u, d)
+    rx, ry, sx, sy = rst
+    return vel[0] * (rx * ur + sx * us) + vel[1] * (ry * ur + sy * us)

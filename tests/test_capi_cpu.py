@@ -1,0 +1,111 @@
+"""-m "not gpu": the C-ABI library loads, exports every declared symbol, host-only entry points
+work, and compute entry points fail loudly (no CPU fallback)."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import krylov as okr, sem as osem
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_symbols():
+    txt = (ROOT / 'include' / 'nekstab_b200.h').read_text()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(nsb_[a-z0-9_]+)\s*\(', txt)) - {'nsb_host_matvec_fn'})
+
+
+def test_library_exports_every_header_symbol(lib):
+    from nekstab_next_b200 import _capi
+    syms = header_symbols()
+    assert len(syms) > 50
+    out = subprocess.run(['nm', '-D', '--defined-only', str(_capi.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r' T (nsb_[a-z0-9_]+)', out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, f'header declares but library does not export: {missing}'
+    undeclared = [s for s in syms if s not in _capi.PROTOTYPES]
+    assert not undeclared, f'ctypes binding lacks: {undeclared}'
+    assert lib.nsb_version() == 100
+
+
+def test_library_is_sm100a_only(lib):
+    from nekstab_next_b200 import _capi
+    out = subprocess.run(['cuobjdump', '--list-elf', str(_capi.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_\d+a?', out))
+    assert archs == {'sm_100a'}, archs
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import nekstab_next_b200 as nb
+    with pytest.raises(nb.NsbError) as e:
+        nb.Context(device=0)
+    assert e.value.code == -3 and 'no CPU fallback' in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    for p in (ROOT / 'nekstab_next_b200').rglob('*'):
+        if p.suffix in ('.py', '.cu', '.cuh', '.h', '.cpp'):
+            assert 'oracle' not in p.read_text(), f'{p} mentions the oracle'
+
+
+def test_gll_matches_oracle(lib):
+    import nekstab_next_b200 as nb
+    for n in (1, 2, 3, 5, 7, 9, 11):
+        z, w, D = nb.gll(n)
+        z2, w2 = osem.gll(n)
+        assert np.max(np.abs(z - z2)) < 1e-15 and np.max(np.abs(w - w2)) < 1e-14
+        assert np.max(np.abs(D - osem.dgll(n))) < 1e-12
+
+
+def test_lapack_wrapper_mirrors(lib):
+    import nekstab_next_b200 as nb
+    rng = np.random.default_rng(3)
+    for n in (6, 12, 25):
+        A = rng.standard_normal((n, n)) * (0.9 / np.sqrt(n))
+        v1, l1 = nb.eig(A)
+        v2, l2 = okr.eig(A)
+        assert np.allclose(l1, l2, atol=1e-13) and np.allclose(v1, v2, atol=1e-12)
+        assert np.all(np.diff(np.abs(l1)) <= 1e-14)          # sorted by decreasing magnitude
+        assert np.allclose(A @ v1, v1 * l1[None, :], atol=1e-11)
+        T1, Z1, s1 = nb.schur(A)
+        T2, Z2, s2 = okr.schur(A)
+        assert np.allclose(T1, T2, atol=1e-13) and np.allclose(Z1, Z2, atol=1e-13)
+        assert np.allclose(Z1 @ T1 @ Z1.T, A, atol=1e-12)
+        if n >= 8:
+            sel1, c1 = nb.select_eigenvalues(s1, 0.1, 2)
+            sel2, c2 = okr.select_eigenvalues(s2.copy(), 0.1, 2)
+            assert c1 == c2 and np.array_equal(sel1, sel2) and c1 >= 6
+            T1o, Z1o = nb.ordschur(T1, Z1, sel1)
+            T2o, Z2o = okr.ordschur(T2, Z2, sel2)
+            assert np.allclose(T1o, T2o, atol=1e-12) and np.allclose(Z1o @ T1o @ Z1o.T, A, atol=1e-11)
+        B = rng.standard_normal((n + 1, n))
+        b = rng.standard_normal(n + 1)
+        assert np.allclose(nb.lstsq(B, b), okr.lstsq(B, b), atol=1e-12)
+        assert np.allclose(nb.lstsq(B, b), np.linalg.lstsq(B, b, rcond=None)[0], atol=1e-10)
+
+
+def test_select_eigenvalues_conjugate_pair_kept(lib):
+    import nekstab_next_b200 as nb
+    # the (nev+4)-th largest is half of a conjugate pair -> its partner is selected too (:747-749)
+    vals = np.array([0.99, 0.95, 0.9 + 0.1j, 0.9 - 0.1j, 0.8, 0.7 + 0.2j, 0.7 - 0.2j, 0.5, 0.4, 0.3, 0.2, 0.1],
+                    dtype=np.complex128)
+    sel, cnt = nb.select_eigenvalues(vals, 0.05, 2)   # nev+4 = 6 largest
+    sel2, cnt2 = okr.select_eigenvalues(vals.copy(), 0.05, 2)
+    assert np.array_equal(sel, sel2) and cnt == cnt2
+    assert sel[5] and sel[6]
+
+
+def test_partition_ranges():
+    from nekstab_next_b200.mesh import partition_range
+    for total, gran in ((32768, 1024), (64, 16), (30, 6)):
+        for P in (1, 2, 3, 4, 8):
+            rs = [partition_range(total, r, P, gran) for r in range(P)]
+            assert rs[0][0] == 0 and rs[-1][1] == total // gran * gran
+            for (a, b), (c, d) in zip(rs[:-1], rs[1:]):
+                assert b == c and (b - a) % gran == 0

@@ -1,0 +1,98 @@
+"""GPU parity: SEM geometry, axhelm (sum factorisation with G1..G6), dssum, mask, and the fused
+operator vs the oracle; 1e-12 relative in fp64 (BASELINE.json north_star)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import BoxProblem, upload, download, relerr
+from oracle import sem as osem
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / 'golden'
+TOL = 1e-12
+
+
+@pytest.mark.parametrize('nel,N,deform', [((3, 2, 2), 7, 0.05), ((2, 2, 3), 7, 0.0), ((2, 3, 2), 4, 0.05),
+                                          ((2, 2, 2), 1, 0.02), ((2, 2, 2), 10, 0.03), ((5, 4), 5, 0.04),
+                                          ((3, 3), 7, 0.0)])
+def test_geometry_and_kernels(ctx, nel, N, deform):
+    P = BoxProblem(nel=nel, N=N, deform=deform, nfields=1, seed=N)
+    lay, B, S, op = P.gpu(ctx, 4)
+    # geometry
+    assert relerr(S.get('bm1'), P.bm1) <= TOL
+    assert relerr(S.get('jac'), P.geo['jac']) <= TOL
+    names = ['g1', 'g2', 'g3', 'g4', 'g5', 'g6'] if P.dim == 3 else ['g1', 'g2', 'g4']
+    gscale = np.max(np.abs(P.geo['g']))
+    for i, nm in enumerate(names):
+        assert np.max(np.abs(S.get(nm) - P.geo['g'][i])) <= TOL * gscale
+    assert relerr(S.get('binvm1'), P.binv) <= TOL
+    assert np.array_equal(S.get('vmult'), P.vmult)
+    assert np.array_equal(S.get('mask'), P.mask)
+    # axhelm on a non-continuous random field (element-local operator)
+    u = P.rng.standard_normal(P.shape)
+    B[0].upload([u])
+    for h1, h2 in ((1.0, 0.0), (0.7, 0.3)):
+        S.axhelm(B[0], B[1], 0, h1, h2)
+        ref = osem.axhelm(u, P.geo['g'], P.d, h1, h2, P.bm1)
+        assert relerr(B[1].download()[0][0], ref.ravel()) <= TOL
+    # dssum, col2, ax
+    S.dssum(B[0], 0)
+    assert relerr(B[0].download()[0][0], osem.dssum(u, P.glo).ravel()) <= 1e-14
+    B[0].upload([u])
+    S.ax(B[0], B[2], 0, 1.0, 0.1)
+    ref = osem.ax(u, P.geo['g'], P.d, P.glo, P.mask, 1.0, 0.1, P.bm1)
+    assert relerr(B[2].download()[0][0], ref.ravel()) <= TOL
+    S.col2(B[2], 0, 'binvm1')
+    assert relerr(B[2].download()[0][0], (ref * P.binv).ravel()) <= TOL
+
+
+@pytest.mark.parametrize('conv', [False, True])
+@pytest.mark.parametrize('nel,N', [((3, 2, 2), 7), ((4, 3), 5)])
+def test_fused_operator(ctx, conv, nel, N):
+    P = BoxProblem(nel=nel, N=N, deform=0.05, nfields=len(nel), pressure=True, time_in_dot=True, conv=conv, seed=3)
+    lay, B, S, op = P.gpu(ctx, 3)
+    q = P.random_kvec()
+    upload(B[0], q)
+    op.matvec(B[0], B[1])
+    ref = P.omatvec(q)
+    got = download(B[1])
+    for a, b in zip(got.f, ref.f):
+        assert relerr(a, b.ravel()) <= TOL
+    assert got.time == ref.time
+    assert op.count() == 1
+
+
+@pytest.mark.parametrize('name', ['cyl', 'bfs'])
+def test_reference_meshes(ctx, name):
+    """Config 1: the reference's own curved 2-D meshes (examples/cylinder, examples/back_fstep)."""
+    import nekstab_next_b200 as nb
+    known = json.loads((GOLD / 'known_answers.json').read_text())[name]
+    g = np.load(GOLD / f'{name}_mesh.npz')
+    x, y, u, v, glo = g['x'], g['y'], g['u'], g['v'], g['glo'].astype(np.int64)
+    N = known['N']
+    S = nb.Sem(ctx, N, x, y, None, mask=None, glo_num=glo)
+    bm1 = S.get('bm1')
+    assert abs(bm1.sum() - known['sum_bm1']) <= 1e-12 * known['sum_bm1']
+    geo = osem.geometry(N, x, y)
+    assert relerr(bm1, geo['bm1']) <= TOL
+    lay = nb.Layout(ctx, [x.size, x.size], [True, True])
+    lay.set_weight([bm1, bm1])
+    B = nb.Basis(lay, 3)
+    B[0].upload([u, v])
+    uu = B[0].dot(B[0])
+    assert abs(uu - known['uu']) <= 1e-12 * known['uu']
+    S.ax(B[0], B[1], 0, 1.0, 0.0)
+    ref = osem.ax(u, geo['g'], osem.dgll(N), glo, np.ones_like(u), 1.0, 0.0, geo['bm1'])
+    assert relerr(B[1].download()[0][0], ref.ravel()) <= TOL
+    assert int(glo.max()) + 1 == known['nunique']
+
+
+def test_mask_inconsistency_is_rejected(ctx):
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=3, nfields=1)
+    bad = P.mask.copy()
+    bad[0, -1, 1, 1] = 0.0   # a face node shared with the element above, zeroed on one side only
+    with pytest.raises(nb.NsbError):
+        nb.Sem(ctx, P.N, *P.coords, mask=bad, glo_num=P.glo)
