@@ -108,10 +108,12 @@ def upload(vec, kv):
     vec.upload(kv.f, kv.time)
 
 
-def download(vec):
-    import numpy as np  # noqa: F811
-    from oracle import krylov as okr
+def download(vec, shape=None):
+    """Device vector -> oracle KVec; fields of npts entries are reshaped to ``shape`` if given."""
     f, t = vec.download()
+    if shape is not None:
+        n = int(np.prod(shape))
+        f = [a.reshape(shape) if a.size == n else a for a in f]
     return okr.KVec(f, t)
 
 

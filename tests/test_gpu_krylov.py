@@ -43,7 +43,7 @@ def test_arnoldi_factorization(ctx, conv, mode):
     assert np.max(np.abs(ev[lead] - evo[lead]) / np.abs(evo[lead])) < 1e-6
     # Arnoldi relation on the device data: M q_j = sum_i H_ij q_i
     j = K - 1
-    lhs = P.omatvec(download(B[j]))
+    lhs = P.omatvec(download(B[j], P.shape))
     rhs = sum(H[i, j] * download(B[i]).f[0] for i in range(j + 2))
     assert np.max(np.abs(lhs.f[0].ravel() - rhs)) < 1e-10
 
