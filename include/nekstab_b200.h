@@ -67,6 +67,12 @@ int nsb_launch_count(nsb_context_t ctx, int64_t *count);
 /* Device-side event timing on the context stream. */
 int nsb_timer_start(nsb_context_t ctx);
 int nsb_timer_stop(nsb_context_t ctx, double *elapsed_ms); /* synchronises */
+/* Per-kernel-class device timing for the roofline report: when enabled, every launch is bracketed
+ * by CUDA events on the context stream.  Classes: 0 multidot (h = V^T W w), 1 update (w -= V h),
+ * 2 normalize, 3 axhelm, 4 gather-scatter (dssum), 5 BLAS-1, 6 small reductions, 7 rotate,
+ * 8 gemv, 9 single dot.  bytes = algorithmic bytes summed over the recorded launches. */
+int nsb_prof_enable(nsb_context_t ctx, int on); /* also clears the records */
+int nsb_prof_get(nsb_context_t ctx, int cls, double *ms, int64_t *launches, double *bytes);
 /* Sum-allreduce n doubles held on the host across ranks (gop(x,'+')); no-op for one rank. */
 int nsb_allreduce_host(nsb_context_t ctx, double *x, int n);
 /* Write a buffer larger than L2 (bench hygiene). */
@@ -207,10 +213,12 @@ int nsb_sem_ax(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int co
 int nsb_op_create_sem(nsb_sem_t sem, int nfields_apply, double alpha, double beta, double h1,
                       double h2, const double *cx, const double *cy, const double *cz,
                       nsb_op_t *op);
-/* Host operator: the reference's time-stepper (nek_advance on host arrays).  The callback gets
- * host field pointers (layout order); the library downloads vec_in / uploads vec_out around it. */
+/* Host operator: the reference's time-stepper (nek_advance on host arrays vxp, vyp ...).  The
+ * library downloads vec_in into pinned staging buffers, calls the callback, and uploads vec_out.
+ * out_fields[i] arrives pointing at a pinned staging buffer the callback may fill; it may instead
+ * overwrite out_fields[i] with a pointer to its own array (zero-copy from Nek's vxp ...). */
 typedef int (*nsb_host_matvec_fn)(void *user, const double *const *in_fields, double in_time,
-                                  double *const *out_fields, double *out_time);
+                                  double **out_fields, double *out_time);
 int nsb_op_create_host(nsb_layout_t layout, nsb_host_matvec_fn fn, void *user, nsb_op_t *op);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);

@@ -29,6 +29,8 @@ PROTOTYPES = {
     'nsb_launch_count': (C.c_int, [H, c_i64_p]),
     'nsb_timer_start': (C.c_int, [H]),
     'nsb_timer_stop': (C.c_int, [H, c_double_p]),
+    'nsb_prof_enable': (C.c_int, [H, C.c_int]),
+    'nsb_prof_get': (C.c_int, [H, C.c_int, c_double_p, c_i64_p, c_double_p]),
     'nsb_allreduce_host': (C.c_int, [H, c_double_p, C.c_int]),
     'nsb_flush_l2': (C.c_int, [H]),
     'nsb_layout_create': (C.c_int, [H, C.c_int, c_i64_p, c_int_p, C.c_int, c_void_pp]),

@@ -101,6 +101,22 @@ class Context:
     def flush_l2(self):
         check(self.lib.nsb_flush_l2(self.h))
 
+    PROF_CLASSES = ('multidot', 'update', 'normalize', 'axhelm', 'gather_scatter', 'blas1', 'small',
+                    'rotate', 'gemv', 'dot')
+
+    def prof_enable(self, on: bool = True):
+        check(self.lib.nsb_prof_enable(self.h, int(on)))
+
+    def prof_report(self) -> dict:
+        """{class: dict(ms, launches, bytes)} for the launches recorded since prof_enable."""
+        out = {}
+        for i, name in enumerate(self.PROF_CLASSES):
+            ms, n, b = C.c_double(), C.c_int64(), C.c_double()
+            check(self.lib.nsb_prof_get(self.h, i, C.byref(ms), C.byref(n), C.byref(b)))
+            if n.value:
+                out[name] = dict(ms=ms.value, launches=n.value, bytes=b.value)
+        return out
+
     def allreduce(self, x: np.ndarray) -> np.ndarray:
         x = _f64(x, copy=True).ravel()
         check(self.lib.nsb_allreduce_host(self.h, _dp(x), x.size))
@@ -393,12 +409,23 @@ def host_operator(layout: Layout, fn) -> LinearOperator:
     time-stepper lives on the host); vectors cross PCIe around every call."""
     lens = layout.field_len
 
+    hold = {}
+
     def tramp(user, pin, tin, pout, tout):
         try:
-            fin = [np.ctypeslib.as_array(pin[i], shape=(lens[i],)) for i in range(len(lens))]
+            fin = [np.ctypeslib.as_array(pin[i], shape=(lens[i],)) if lens[i] else np.empty(0)
+                   for i in range(len(lens))]
             res, t = fn(fin, tin)
             for i in range(len(lens)):
-                np.ctypeslib.as_array(pout[i], shape=(lens[i],))[:] = np.asarray(res[i]).ravel()
+                a = res[i]
+                if lens[i] == 0:
+                    continue
+                if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous \
+                        and a.size == lens[i]:
+                    hold[i] = a                       # zero-copy: hand the caller's array over
+                    pout[i] = a.ctypes.data_as(c_double_p)
+                else:
+                    np.ctypeslib.as_array(pout[i], shape=(lens[i],))[:] = np.asarray(a).ravel()
             tout[0] = t
             return 0
         except Exception:  # noqa: BLE001  (must not propagate through the C frame)

@@ -32,9 +32,60 @@ int ensure_partial(nsb_context_t ctx, int64_t rows) {
   return NSB_OK;
 }
 
+ProfScope::ProfScope(nsb_context_t ctx, int cls, double bytes) : c(ctx) {
+  if (!ctx->prof) return;
+  cudaEvent_t e[2];
+  for (int i = 0; i < 2; ++i) {
+    if (!ctx->prof_pool.empty()) {
+      e[i] = ctx->prof_pool.back();
+      ctx->prof_pool.pop_back();
+    } else if (cudaEventCreate(&e[i]) != cudaSuccess) {
+      return;
+    }
+  }
+  cudaEventRecord(e[0], ctx->stream);
+  ctx->prof_recs.push_back({cls, e[0], e[1], bytes});
+  slot = (int)ctx->prof_recs.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(c->prof_recs[slot].e1, c->stream);
+}
+
 }  // namespace nsb
 
 using namespace nsb;
+
+extern "C" int nsb_prof_enable(nsb_context_t ctx, int on) {
+  NSB_REQUIRE(ctx, "nsb_prof_enable: NULL context");
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &r : ctx->prof_recs) {
+    ctx->prof_pool.push_back(r.e0);
+    ctx->prof_pool.push_back(r.e1);
+  }
+  ctx->prof_recs.clear();
+  ctx->prof = on != 0;
+  return NSB_OK;
+}
+
+extern "C" int nsb_prof_get(nsb_context_t ctx, int cls, double *ms, int64_t *launches, double *bytes) {
+  NSB_REQUIRE(ctx && cls >= 0 && cls < PC_COUNT, "nsb_prof_get: bad argument");
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double t = 0, b = 0;
+  int64_t n = 0;
+  for (auto &r : ctx->prof_recs) {
+    if (r.cls != cls) continue;
+    float f = 0.f;
+    NSB_CUDA(cudaEventElapsedTime(&f, r.e0, r.e1));
+    t += f;
+    b += r.bytes;
+    ++n;
+  }
+  if (ms) *ms = t;
+  if (launches) *launches = n;
+  if (bytes) *bytes = b;
+  return NSB_OK;
+}
 
 extern "C" const char *nsb_last_error(void) { return g_err; }
 extern "C" int nsb_version(void) { return NSB_VERSION; }
@@ -93,6 +144,8 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
   if (ctx->hvec_d) cudaFree(ctx->hvec_d);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
   if (ctx->flush_d) cudaFree(ctx->flush_d);
+  for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -213,6 +266,8 @@ extern "C" int nsb_layout_create(nsb_context_t ctx, int nfields, const int64_t *
     row = round_up(row + field_len[f], 16);
   }
   L->ld = round_up(row, kRowPad);
+  L->nact = 1;
+  for (int f = 0; f < nfields; ++f) L->nact += field_len[f];
   cudaSetDevice(ctx->device);
   NSB_CUDA(cudaMalloc(&L->w_d, sizeof(double) * L->ndot));
   NSB_CUDA(cudaMemsetAsync(L->w_d, 0, sizeof(double) * L->ndot, ctx->stream));
@@ -398,6 +453,7 @@ int launch_blas1(nsb_context_t ctx, double *x, const double *y, const double *z,
   int grid = (int)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   cudaSetDevice(ctx->device);
+  ProfScope ps(ctx, PC_BLAS1, 8.0 * n * (OP == OP_SCAL ? 2 : 3));
   blas1_kernel<OP><<<grid, 256, 0, ctx->stream>>>(
       reinterpret_cast<double2 *>(x), reinterpret_cast<const double2 *>(y),
       reinterpret_cast<const double2 *>(z), a, b, n2, skip_row >= 0 ? skip_row / 2 : -1,
@@ -461,6 +517,7 @@ static int dot_device(nsb_basis_t ba, int ca, nsb_basis_t bb, int cb, double *ou
   int64_t cap = (int64_t)ctx->num_sms * 8;
   int grid = (int)(want < cap ? want : cap);
   cudaSetDevice(ctx->device);
+  ProfScope ps(ctx, PC_DOT, 24.0 * (L->ndof_dot + 1));
   wdot_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const double2 *>(ba->col(ca)),
                                              reinterpret_cast<const double2 *>(bb->col(cb)),
                                              reinterpret_cast<const double2 *>(L->w_d), n2,

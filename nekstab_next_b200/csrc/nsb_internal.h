@@ -58,6 +58,11 @@ struct nsb_context_s {
   double *hpin = nullptr;      // pinned mirror
   double *flush_d = nullptr;
   size_t flush_bytes = 0;
+  // per-kernel-class device timing (bench / roofline): events around every launch when enabled
+  bool prof = false;
+  struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
 };
 
 struct nsb_layout_s {
@@ -71,6 +76,7 @@ struct nsb_layout_s {
   int64_t ndot = 0;              // rows [0, ndot) are covered by the inner product (padded)
   int64_t ld = 0;                // rows of a column (padded)
   int64_t ndof_dot = 0;          // unpadded dofs in the inner product
+  int64_t nact = 0;              // unpadded rows of a column (all fields + %time)
   double *w_d = nullptr;         // weight, ndot rows (zeros on pads)
 };
 
@@ -120,11 +126,20 @@ struct nsb_op_s {
   nsb_layout_t lay = nullptr;
   nsb_host_matvec_fn fn = nullptr;
   void *user = nullptr;
-  std::vector<std::vector<double>> hin, hout;
+  std::vector<double *> hin, hout;  // pinned staging buffers of the host operator
   int64_t napply = 0;
 };
 
 namespace nsb {
+enum ProfClass { PC_MULTIDOT = 0, PC_UPDATE, PC_NORMALIZE, PC_AXHELM, PC_GS, PC_BLAS1, PC_SMALL,
+                 PC_ROTATE, PC_GEMV, PC_DOT, PC_COUNT };
+// RAII: records a start event now and a stop event at scope exit on the context stream
+struct ProfScope {
+  nsb_context_t c;
+  int slot = -1;
+  ProfScope(nsb_context_t ctx, int cls, double bytes);
+  ~ProfScope();
+};
 // implemented in nsb_core.cu
 int ensure_partial(nsb_context_t ctx, int64_t rows);
 // implemented in nsb_comm.cu

@@ -277,7 +277,8 @@ inline int persistent_grid(nsb_context_t ctx, int64_t nchunks) {
 }
 
 int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *w,
-                    const double *W, int64_t ndot, double *h_d, bool with_norm, double *hsum_d) {
+                    const double *W, int64_t ndot, double *h_d, bool with_norm, double *hsum_d,
+                    int64_t nalg = -1) {
   const int64_t nchunks = ndot / CHUNK;
   const int grid = persistent_grid(ctx, nchunks);
   const int kpad = (k + KT) & ~(KT - 1);
@@ -285,14 +286,21 @@ int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const
   const int pstride = kMaxK + 8;
   NSB_CHECK(ensure_partial(ctx, grid));
   cudaSetDevice(ctx->device);
-  if (with_norm)
-    multidot_kernel<true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
-  else
-    multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+  {
+    // algorithmic bytes: V once (k columns), w and W once
+    ProfScope ps(ctx, PC_MULTIDOT, 8.0 * (double)(nalg >= 0 ? nalg : ndot) * (k + 2));
+    if (with_norm)
+      multidot_kernel<true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+    else
+      multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+  }
   const int kout = with_norm ? k + 1 : k;
   if (kout == 0) return NSB_OK;
-  reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(
-      ctx->partial_d, grid, pstride, kout, h_d, hsum_d != nullptr, hsum_d);
+  {
+    ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
+    reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->partial_d, grid, pstride, kout, h_d, hsum_d != nullptr, hsum_d);
+  }
   ctx->launches += 2;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -300,17 +308,26 @@ int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const
 
 template <int MODE>
 int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h_d, double *w,
-                  const double *W, int64_t nrows, int64_t ndot, bool with_norm, double *nrm2_d) {
+                  const double *W, int64_t nrows, int64_t ndot, bool with_norm, double *nrm2_d,
+                  int64_t nalg = -1, int64_t nalg_dot = -1) {
   const int64_t nchunks = nrows / CHUNK;
   const int grid = persistent_grid(ctx, nchunks);
   const size_t smem = sizeof(double) * (k > 0 ? k : 1);
   cudaSetDevice(ctx->device);
+  // algorithmic bytes: V once, w read + written (MODE 0) or written (MODE 1), W once with the norm
+  const double na = (double)(nalg >= 0 ? nalg : nrows), nd = (double)(nalg_dot >= 0 ? nalg_dot : ndot);
+  const double bytes = 8.0 * (na * (k + (MODE == 0 ? 2 : 1)) + (with_norm ? nd : 0.0));
   if (with_norm) {
-    update_kernel<MODE, true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
-                                                              ctx->partial_d);
+    {
+      ProfScope ps(ctx, MODE == 0 ? PC_UPDATE : PC_GEMV, bytes);
+      update_kernel<MODE, true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
+                                                                ctx->partial_d);
+    }
+    ProfScope ps(ctx, PC_SMALL, 8.0 * grid);
     reduce_partials_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partial_d, grid, 1, 1, nrm2_d, 0, nullptr);
     ctx->launches += 2;
   } else {
+    ProfScope ps(ctx, MODE == 0 ? PC_UPDATE : PC_GEMV, bytes);
     update_kernel<MODE, false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
                                                                ctx->partial_d);
     ctx->launches += 1;
@@ -324,6 +341,7 @@ int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm
   int64_t want = (n2 + 1023) / 1024;
   int64_t cap = (int64_t)ctx->num_sms * 16;
   int grid = (int)(want < cap ? want : cap);
+  ProfScope ps(ctx, PC_NORMALIZE, 16.0 * ld);
   normalize_kernel<<<grid, NT, 0, ctx->stream>>>(reinterpret_cast<double2 *>(w), n2, nrm2_d, hk_d);
   ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
@@ -379,10 +397,10 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
   } else {
     const bool dgks = (mode == NSB_ORTH_DGKS);
     // pass 1 (the norm of the incoming w rides along for the DGKS test)
-    NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr));
+    NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr, L->ndof_dot + 1));
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, dgks ? k + 1 : k));
     NSB_CUDA(cudaMemcpyAsync(hsum, h1, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
-    NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, scal));
+    NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, scal, L->nact, L->ndof_dot + 1));
     bool second = true;
     if (dgks) {
       if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
@@ -393,10 +411,10 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
       second = !(n1 >= 0.5 * n0);  // ||w'|| < ||w|| / sqrt 2  (also taken on NaN)
     }
     if (second) {
-      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h2, false, nullptr));
+      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h2, false, nullptr, L->ndof_dot + 1));
       if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, k));
       NSB_CHECK(add_into(hsum, h2, k));
-      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, scal));
+      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, scal, L->nact, L->ndof_dot + 1));
       if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
     } else {
       passes = 1;
@@ -497,6 +515,7 @@ extern "C" int nsb_basis_rotate(nsb_basis_t B, int k, const double *Z, int ldz, 
   do {                                                                                              \
     NSB_CUDA(cudaFuncSetAttribute(rotate_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                   (int)smem));                                                      \
+    ProfScope ps(ctx, PC_ROTATE, 16.0 * (double)L->nact * k);                                       \
     rotate_kernel<RB><<<grid, NT, smem, ctx->stream>>>(B->v_d, L->ld, k, Z_d, k, npanels);          \
   } while (0)
   if (rb == 128) LAUNCH_ROT(128);

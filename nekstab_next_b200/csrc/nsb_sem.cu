@@ -406,6 +406,11 @@ int launch_ax2d(nsb_sem_t S, const double *u, double *w, double h1, double h2, c
 int launch_axhelm(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
                   int epi, double alpha, double beta, const double *bmask) {
   cudaSetDevice(S->ctx->device);
+  // algorithmic bytes per point: u, w, G1..G6 (G1,G2,G4 in 2-D), bm1 if h2 != 0, C if convecting,
+  // bmask on element-interior points of the fused epilogue
+  const double fint = std::pow((double)(S->lx - 2) / S->lx, S->dim);
+  const double per_pt = 8.0 * (2 + S->ng + (h2 != 0.0 ? 1 : 0) + (cv ? S->dim : 0) + (epi ? fint : 0.0));
+  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts);
   if (S->dim == 3) {
     if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
                        : launch_ax3d<true, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
@@ -427,6 +432,9 @@ int launch_gs(nsb_sem_t S, double *v, int epi, const double *uin, double alpha, 
   cudaSetDevice(ctx->device);
   if (S->nshared == 0) return NSB_OK;
   const unsigned nb = blocks_for(S->nshared);
+  // algorithmic bytes: every listed point read + written (16), its index (4), node offsets (8 per
+  // node), plus uin and bmask per point in the fused tail
+  ProfScope ps(ctx, PC_GS, (double)S->gs_nnz * (20.0 + (epi ? 16.0 : 0.0)) + 8.0 * (double)S->nshared);
   if (ctx->nranks == 1 || S->peers.empty()) {
     if (ctx->nranks > 1 && !S->exchange_ready) {
       set_error("dssum: nsb_sem_setup_exchange has not been called on this multi-rank context");
@@ -766,11 +774,13 @@ extern "C" int nsb_op_create_host(nsb_layout_t L, nsb_host_matvec_fn fn, void *u
   op->lay = L;
   op->fn = fn;
   op->user = user;
-  op->hin.resize(L->nfields);
-  op->hout.resize(L->nfields);
+  op->hin.assign(L->nfields, nullptr);
+  op->hout.assign(L->nfields, nullptr);
+  cudaSetDevice(L->ctx->device);
   for (int f = 0; f < L->nfields; ++f) {
-    op->hin[f].resize(L->len[f]);
-    op->hout[f].resize(L->len[f]);
+    const size_t nb = sizeof(double) * (size_t)(L->len[f] > 0 ? L->len[f] : 1);
+    NSB_CUDA(cudaMallocHost((void **)&op->hin[f], nb));
+    NSB_CUDA(cudaMallocHost((void **)&op->hout[f], nb));
   }
   *out = op;
   return NSB_OK;
@@ -779,6 +789,8 @@ extern "C" int nsb_op_create_host(nsb_layout_t L, nsb_host_matvec_fn fn, void *u
 extern "C" int nsb_op_destroy(nsb_op_t op) {
   if (!op) return NSB_OK;
   if (op->c_d) cudaFree(op->c_d);
+  for (double *p : op->hin) cudaFreeHost(p);
+  for (double *p : op->hout) cudaFreeHost(p);
   delete op;
   return NSB_OK;
 }
@@ -801,9 +813,9 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
     std::vector<const double *> pin(L->nfields);
     std::vector<double *> pout(L->nfields), pdl(L->nfields);
     for (int f = 0; f < L->nfields; ++f) {
-      pin[f] = op->hin[f].data();
-      pdl[f] = op->hin[f].data();
-      pout[f] = op->hout[f].data();
+      pin[f] = op->hin[f];
+      pdl[f] = op->hin[f];
+      pout[f] = op->hout[f];
     }
     double tin = 0.0, tout = 0.0;
     NSB_CHECK(nsb_vec_download(bin, cin, pdl.data(), &tin));
