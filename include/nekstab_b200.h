@@ -70,7 +70,7 @@ int nsb_timer_stop(nsb_context_t ctx, double *elapsed_ms); /* synchronises */
 /* Per-kernel-class device timing for the roofline report: when enabled, every launch is bracketed
  * by CUDA events on the context stream.  Classes: 0 multidot (h = V^T W w), 1 update (w -= V h),
  * 2 normalize, 3 axhelm, 4 gather-scatter (dssum), 5 BLAS-1, 6 small reductions, 7 rotate,
- * 8 gemv, 9 single dot.  bytes = algorithmic bytes summed over the recorded launches. */
+ * 8 gemv, 9 single dot, 10 fused update+multidot (w -= V h1 ; h2 = V^T W w).  bytes = algorithmic bytes summed over the recorded launches. */
 int nsb_prof_enable(nsb_context_t ctx, int on); /* also clears the records */
 int nsb_prof_get(nsb_context_t ctx, int cls, double *ms, int64_t *launches, double *bytes);
 /* Sum-allreduce n doubles held on the host across ranks (gop(x,'+')); no-op for one rank. */
@@ -143,8 +143,9 @@ int nsb_vec_normalize(nsb_basis_t b, int col, double *alpha);
  * Modes:
  *   NSB_ORTH_MGS2_REF  literal reference: column-by-column MGS, unconditional second pass
  *                      (2k dots + 2k updates; slow, for parity tests)
- *   NSB_ORTH_CGS2      fused multi-column: h1 = V^T W w ; w -= V h1 ; h2 = V^T W w ; w -= V h2
- *                      (same two-pass semantics, H = h1 + h2; 3 all-reduces per step)
+ *   NSB_ORTH_CGS2      fused multi-column: h1 = V^T W w ; {w -= V h1 ; h2 = V^T W w} ; w -= V h2
+ *                      (same two-pass semantics, H = h1 + h2; V crosses HBM three times and there
+ *                      are 3 all-reduces per step)
  *   NSB_ORTH_DGKS      as CGS2, second pass only if ||w'|| < eta ||w|| (eta = 1/sqrt 2)
  * ------------------------------------------------------------------------------------------- */
 #define NSB_ORTH_MGS2_REF 0

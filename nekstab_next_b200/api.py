@@ -102,7 +102,7 @@ class Context:
         check(self.lib.nsb_flush_l2(self.h))
 
     PROF_CLASSES = ('multidot', 'update', 'normalize', 'axhelm', 'gather_scatter', 'blas1', 'small',
-                    'rotate', 'gemv', 'dot')
+                    'rotate', 'gemv', 'dot', 'fused_update_dot')
 
     def prof_enable(self, on: bool = True):
         check(self.lib.nsb_prof_enable(self.h, int(on)))

@@ -6,6 +6,7 @@
 // thread in flight, grid a multiple of the SM count.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 
@@ -118,6 +119,7 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   ctx->rank = rank;
   ctx->nranks = nranks;
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("NSB_NO_FUSED")) ctx->no_fused = e[0] == '1';
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaEventCreate(&ctx->ev0));

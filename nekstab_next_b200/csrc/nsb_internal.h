@@ -59,6 +59,7 @@ struct nsb_context_s {
   double *flush_d = nullptr;
   size_t flush_bytes = 0;
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
+  bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
   bool prof = false;
   struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes; };
   std::vector<ProfRec> prof_recs;
@@ -132,7 +133,7 @@ struct nsb_op_s {
 
 namespace nsb {
 enum ProfClass { PC_MULTIDOT = 0, PC_UPDATE, PC_NORMALIZE, PC_AXHELM, PC_GS, PC_BLAS1, PC_SMALL,
-                 PC_ROTATE, PC_GEMV, PC_DOT, PC_COUNT };
+                 PC_ROTATE, PC_GEMV, PC_DOT, PC_FUSED, PC_COUNT };
 // RAII: records a start event now and a stop event at scope exit on the context stream
 struct ProfScope {
   nsb_context_t c;

@@ -271,6 +271,171 @@ rotate_kernel(double *__restrict__ V, int64_t ld, int k, const double *__restric
   }
 }
 
+// ---- fused  w -= V h1 ; h2 = V^T (W o w)  (middle step of CGS2) ------------------------------
+// The second projection needs the fully updated w, but only row-locally: for a block of RC rows
+// the CTA stages V[r0:r0+RC, 0:k] in shared memory ONCE (TMA bulk copies, one per column,
+// completing on an mbarrier), forms w' for those rows (pass A) and immediately accumulates the
+// block's contribution to h2 from the staged copy (pass B).  V therefore crosses HBM once for the
+// two operations: 8 n (k+3) algorithmic bytes instead of 8 n (2k+5).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int RC, bool WITH_NORM>
+__global__ void __launch_bounds__(NT)
+fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h1,
+                        double *__restrict__ w, const double *__restrict__ W, int64_t nblocks,
+                        int64_t ndot_blocks, double *__restrict__ partial, int pstride) {
+  constexpr int RP = RC / 2;      // row pairs per block
+  constexpr int CG = NT / RP;     // column groups in pass A
+  constexpr int LR = RC / 32;     // rows per lane in pass B
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int kpad = (k + KT) & ~(KT - 1);
+  double *sV = reinterpret_cast<double *>(smem_raw);            // [k][RC]
+  double *accS = sV + (size_t)k * RC;                           // [NT/32][kpad]
+  double *hS = accS + (NT / 32) * kpad;                         // [k]
+  double2 *sP = reinterpret_cast<double2 *>(hS + ((k + 1) & ~1));  // [CG][RP] pass-A partials
+  double *sWW = reinterpret_cast<double *>(sP + CG * RP);       // [RC]  W o w'
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sWW + RC);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < (NT / 32) * kpad; i += NT) accS[i] = 0.0;
+  for (int j = tid; j < k; j += NT) hS[j] = h1[j];
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  const int rp = tid % RP, cg = tid / RP;
+  double *myacc = accS + warp * kpad;
+  double nrm = 0.0;
+  uint32_t phase = 0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t r0 = blk * RC;
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(k * RC * sizeof(double)));
+      __syncwarp();
+      for (int j = lane; j < k; j += 32)
+        tma_bulk_g2s(sV + (size_t)j * RC, V + (int64_t)j * ld + r0, RC * sizeof(double), bar);
+    }
+    const bool in_dot = blk < ndot_blocks;
+    double2 wv = make_double2(0.0, 0.0), Wv = make_double2(0.0, 0.0);
+    if (tid < RP) {
+      wv = *reinterpret_cast<const double2 *>(w + r0 + 2 * tid);
+      if (in_dot) Wv = ld_stream(reinterpret_cast<const double2 *>(W + r0 + 2 * tid));
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    // pass A: partial row sums over this thread's column group
+    double2 acc = make_double2(0.0, 0.0);
+    for (int j = cg; j < k; j += CG) {
+      const double2 v = reinterpret_cast<const double2 *>(sV + (size_t)j * RC)[rp];
+      const double hj = hS[j];
+      acc.x = fma(v.x, hj, acc.x);
+      acc.y = fma(v.y, hj, acc.y);
+    }
+    sP[cg * RP + rp] = acc;
+    __syncthreads();
+    if (tid < RP) {
+      double2 s = sP[tid];
+#pragma unroll
+      for (int c = 1; c < CG; ++c) {
+        const double2 t = sP[c * RP + tid];
+        s.x += t.x;
+        s.y += t.y;
+      }
+      wv.x -= s.x;
+      wv.y -= s.y;
+      *reinterpret_cast<double2 *>(w + r0 + 2 * tid) = wv;
+      const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
+      reinterpret_cast<double2 *>(sWW)[tid] = ww;
+      if (WITH_NORM) nrm += ww.x * wv.x + ww.y * wv.y;
+    }
+    __syncthreads();
+    if (in_dot) {
+      // pass B: warp per 8-column tile, lanes over rows
+      // lane owns row pairs (lane + 32 t): consecutive lanes read consecutive 16 B -> no conflicts
+      double2 wl[LR >= 2 ? LR / 2 : 1];
+      if (LR >= 2) {
+#pragma unroll
+        for (int t = 0; t < LR / 2; ++t) wl[t] = reinterpret_cast<const double2 *>(sWW)[lane + 32 * t];
+      } else {
+        wl[0] = make_double2(sWW[lane], 0.0);
+      }
+      for (int j0 = warp * KT; j0 < k; j0 += (NT / 32) * KT) {
+        double a8[KT];
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+          a8[c] = 0.0;
+          if (j0 + c < k) {
+            const double *col = sV + (size_t)(j0 + c) * RC;
+            if (LR >= 2) {
+#pragma unroll
+              for (int t = 0; t < LR / 2; ++t) {
+                const double2 v = reinterpret_cast<const double2 *>(col)[lane + 32 * t];
+                a8[c] = fma(v.x, wl[t].x, fma(v.y, wl[t].y, a8[c]));
+              }
+            } else {
+              a8[c] = col[lane] * wl[0].x;
+            }
+          }
+        }
+        const double s = warp_reduce8(a8, lane);
+        if ((lane & 3) == 0 && j0 + (lane >> 2) < k) myacc[j0 + (lane >> 2)] += s;
+      }
+    }
+    __syncthreads();  // sV, sP, sWW are reused by the next block
+  }
+  if (WITH_NORM) {
+    nrm = warp_reduce_sum(nrm);
+    if (lane == 0) myacc[k] = nrm;   // only warps holding tid < RP contribute non-zero
+  }
+  __syncthreads();
+  const int kout = WITH_NORM ? k + 1 : k;
+  for (int j = tid; j < kout; j += NT) {
+    double s = 0.0;
+#pragma unroll
+    for (int wp = 0; wp < NT / 32; ++wp) s += accS[wp * kpad + j];
+    partial[(size_t)blockIdx.x * pstride + j] = s;
+  }
+}
+
+inline size_t fused_smem_bytes(int rc, int k) {
+  const int kpad = (k + KT) & ~(KT - 1);
+  const int cg = NT / (rc / 2);
+  return sizeof(double) * ((size_t)k * rc + (NT / 32) * kpad + ((k + 1) & ~1) + 2 * cg * (rc / 2) + rc) + 16;
+}
+
+// rows per block: the largest of 128/64/32 that lets two CTAs share an SM; 0 = does not fit
+inline int fused_rows(int k) {
+  for (int rc : {128, 64, 32})
+    if (fused_smem_bytes(rc, k) <= 113 * 1024) return rc;
+  if (fused_smem_bytes(32, k) <= 226 * 1024) return 32;
+  return 0;
+}
+
 inline int persistent_grid(nsb_context_t ctx, int64_t nchunks) {
   int64_t g = (int64_t)ctx->num_sms * 2;
   return (int)(nchunks < g ? nchunks : g);
@@ -336,6 +501,46 @@ int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const d
   return NSB_OK;
 }
 
+int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h1_d, double *w,
+                 const double *W, int64_t nrows, int64_t ndot, double *h2_d, bool with_norm, int64_t nalg,
+                 int64_t nalg_dot) {
+  const int rc = fused_rows(k);
+  NSB_REQUIRE(rc != 0, "fused update+dot: k=%d does not fit in shared memory", k);
+  const size_t smem = fused_smem_bytes(rc, k);
+  const int64_t nblocks = nrows / rc, ndot_blocks = ndot / rc;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int64_t g = (int64_t)ctx->num_sms * per_sm;
+  const int grid = (int)(nblocks < g ? nblocks : g);
+  const int pstride = kMaxK + 8;
+  NSB_CHECK(ensure_partial(ctx, grid));
+  cudaSetDevice(ctx->device);
+  {
+    // algorithmic bytes: V once, w read + written, W once
+    ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+#define LAUNCH_FUSED(RC, NORM)                                                                          \
+  do {                                                                                                  \
+    NSB_CUDA(cudaFuncSetAttribute(fused_update_dot_kernel<RC, NORM>,                                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    fused_update_dot_kernel<RC, NORM><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h1_d, w, W, nblocks,   \
+                                                                      ndot_blocks, ctx->partial_d, pstride); \
+  } while (0)
+    if (rc == 128) { if (with_norm) LAUNCH_FUSED(128, true); else LAUNCH_FUSED(128, false); }
+    else if (rc == 64) { if (with_norm) LAUNCH_FUSED(64, true); else LAUNCH_FUSED(64, false); }
+    else { if (with_norm) LAUNCH_FUSED(32, true); else LAUNCH_FUSED(32, false); }
+#undef LAUNCH_FUSED
+  }
+  const int kout = with_norm ? k + 1 : k;
+  {
+    ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
+    reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
+                                                                             kout, h2_d, 0, nullptr);
+  }
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm2_d, double *hk_d) {
   int64_t n2 = ld / 2;
   int64_t want = (n2 + 1023) / 1024;
@@ -396,23 +601,35 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
   } else {
     const bool dgks = (mode == NSB_ORTH_DGKS);
+    const bool fused = fused_rows(k) != 0 && !ctx->no_fused;
     // pass 1 (the norm of the incoming w rides along for the DGKS test)
     NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr, L->ndof_dot + 1));
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, dgks ? k + 1 : k));
     NSB_CUDA(cudaMemcpyAsync(hsum, h1, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
-    NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, scal, L->nact, L->ndof_dot + 1));
+    if (fused) {
+      // w -= V h1 and h2 = V^T W w in one sweep over V (h2[k] = ||w'||^2 for the DGKS test)
+      NSB_CHECK(launch_fused(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, h2, dgks, L->nact, L->ndof_dot + 1));
+      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, dgks ? k + 1 : k));
+    } else {
+      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, scal, L->nact, L->ndof_dot + 1));
+      if (dgks && ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+    }
     bool second = true;
     if (dgks) {
-      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+      const double *n1_d = fused ? h2 + k : scal;
       NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S, h1 + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S + 1, scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S + 1, n1_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       NSB_CUDA(cudaStreamSynchronize(ctx->stream));
       const double n0 = ctx->hpin[3 * S], n1 = ctx->hpin[3 * S + 1];
       second = !(n1 >= 0.5 * n0);  // ||w'|| < ||w|| / sqrt 2  (also taken on NaN)
+      if (!second && fused)
+        NSB_CUDA(cudaMemcpyAsync(scal, h2 + k, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (second) {
-      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h2, false, nullptr, L->ndof_dot + 1));
-      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, k));
+      if (!fused) {
+        NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h2, false, nullptr, L->ndof_dot + 1));
+        if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, k));
+      }
       NSB_CHECK(add_into(hsum, h2, k));
       NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, scal, L->nact, L->ndof_dot + 1));
       if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
