@@ -120,6 +120,9 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   ctx->nranks = nranks;
   ctx->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("NSB_NO_FUSED")) ctx->no_fused = e[0] == '1';
+  if (const char *e = getenv("NSB_FUSED_LOADER")) ctx->fused_loader = atoi(e);
+  if (const char *e = getenv("NSB_FUSED_RC")) ctx->fused_rc = atoi(e);
+  if (const char *e = getenv("NSB_FUSED_REG_MIN_K")) ctx->fused_reg_min_k = atoi(e);
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaEventCreate(&ctx->ev0));

@@ -60,6 +60,9 @@ struct nsb_context_s {
   size_t flush_bytes = 0;
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
   bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
+  int fused_loader = 3;        // NSB_FUSED_LOADER: 0 TMA bulk per column, 1 cp.async, 2 registers, 3 TMA 2-D
+  int fused_rc = 0;            // NSB_FUSED_RC: force rows per block (tuning)
+  int fused_reg_min_k = 54;    // NSB_FUSED_REG_MIN_K: smallest k for the register-retention variant
   bool prof = false;
   struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes; };
   std::vector<ProfRec> prof_recs;

@@ -10,6 +10,8 @@
 // V is column-major [ld, ncols], ld a multiple of 1024 rows with zero pads, so no tail handling.
 // Both kernels are persistent (grid = 2 CTAs per SM), 256 threads, each thread owning 4 rows of a
 // 1024-row chunk as two double2; 8 columns (16 x 128-bit loads per thread) are in flight at once.
+#include <cuda.h>
+
 #include <cmath>
 #include <cstring>
 
@@ -307,48 +309,104 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
       : "memory");
 }
 
-template <int RC, bool WITH_NORM>
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Two shared-memory stages per CTA: while block b is processed, the loads of block b + gridDim.x
+// are already in flight.  LOADER 0: one TMA bulk copy per column on an mbarrier per stage;
+// LOADER 1: cp.async (LDGSTS) 16 B per thread;  LOADER 3: one 2-D TMA tensor load per <= 256 columns
+// (box = RC rows x kbox columns, dense [column][row] in shared memory, no swizzle).
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int RC, bool WITH_NORM, int LOADER>
 __global__ void __launch_bounds__(NT)
 fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h1,
                         double *__restrict__ w, const double *__restrict__ W, int64_t nblocks,
-                        int64_t ndot_blocks, double *__restrict__ partial, int pstride) {
+                        int64_t ndot_blocks, double *__restrict__ partial, int pstride,
+                        const __grid_constant__ CUtensorMap tmap, int kbox, int nbox) {
   constexpr int RP = RC / 2;      // row pairs per block
   constexpr int CG = NT / RP;     // column groups in pass A
-  constexpr int LR = RC / 32;     // rows per lane in pass B
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kpad = (k + KT) & ~(KT - 1);
-  double *sV = reinterpret_cast<double *>(smem_raw);            // [k][RC]
-  double *accS = sV + (size_t)k * RC;                           // [NT/32][kpad]
+  const int kst = LOADER == 3 ? kbox * nbox : k;                // columns held per stage
+  double *sV0 = reinterpret_cast<double *>(smem_raw);           // 2 x [kst][RC]
+  double *accS = sV0 + 2 * (size_t)kst * RC;                    // [NT/32][kpad]
   double *hS = accS + (NT / 32) * kpad;                         // [k]
   double2 *sP = reinterpret_cast<double2 *>(hS + ((k + 1) & ~1));  // [CG][RP] pass-A partials
   double *sWW = reinterpret_cast<double *>(sP + CG * RP);       // [RC]  W o w'
-  uint64_t *bar = reinterpret_cast<uint64_t *>(sWW + RC);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sWW + RC);       // [2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < (NT / 32) * kpad; i += NT) accS[i] = 0.0;
   for (int j = tid; j < k; j += NT) hS[j] = h1[j];
-  if (tid == 0) mbar_init(bar, 1);
+  if ((LOADER == 0 || LOADER == 3) && tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+  }
   __syncthreads();
   const int rp = tid % RP, cg = tid / RP;
   double *myacc = accS + warp * kpad;
   double nrm = 0.0;
-  uint32_t phase = 0;
-  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+  uint32_t phase_bits = 0;  // bit s = parity the next wait on stage s expects
+
+  auto issue = [&](int64_t blk, int stage) {
+    double *dst = sV0 + (size_t)stage * kst * RC;
+    const double *src = V + blk * RC;
+    if (LOADER == 3) {
+      if (tid == 0) {
+        mbar_expect_tx(bar + stage, (uint32_t)(kst * RC * sizeof(double)));
+        for (int b = 0; b < nbox; ++b)
+          tma_load_2d(dst + (size_t)b * kbox * RC, &tmap, (int)(blk * RC), b * kbox, bar + stage);
+      }
+    } else if (LOADER == 0) {
+      if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bar + stage, (uint32_t)(k * RC * sizeof(double)));
+        __syncwarp();
+        for (int j = lane; j < k; j += 32)
+          tma_bulk_g2s(dst + (size_t)j * RC, src + (int64_t)j * ld, RC * sizeof(double), bar + stage);
+      }
+    } else {
+      const int npieces = k * RP;   // 16-byte pieces
+      for (int p = tid; p < npieces; p += NT) {
+        const int j = p / RP, r = p % RP;
+        cp_async16(dst + (size_t)j * RC + 2 * r, src + (int64_t)j * ld + 2 * r);
+      }
+      cp_async_commit();
+    }
+  };
+
+  int stage = 0;
+  int64_t blk = blockIdx.x;
+  if (blk < nblocks) issue(blk, 0);
+  for (; blk < nblocks; blk += gridDim.x, stage ^= 1) {
     const int64_t r0 = blk * RC;
-    if (warp == 0) {
-      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(k * RC * sizeof(double)));
-      __syncwarp();
-      for (int j = lane; j < k; j += 32)
-        tma_bulk_g2s(sV + (size_t)j * RC, V + (int64_t)j * ld + r0, RC * sizeof(double), bar);
-    }
+    const int64_t nxt = blk + gridDim.x;
+    if (nxt < nblocks) issue(nxt, stage ^ 1);
+    else if (LOADER == 1) cp_async_commit();   // keep the group count uniform
+    const double *sV = sV0 + (size_t)stage * kst * RC;
     const bool in_dot = blk < ndot_blocks;
-    double2 wv = make_double2(0.0, 0.0), Wv = make_double2(0.0, 0.0);
-    if (tid < RP) {
-      wv = *reinterpret_cast<const double2 *>(w + r0 + 2 * tid);
-      if (in_dot) Wv = ld_stream(reinterpret_cast<const double2 *>(W + r0 + 2 * tid));
+    // every thread loads w / W for its own row pair (the CG copies of a row pair hit L1)
+    double2 wv = *reinterpret_cast<const double2 *>(w + r0 + 2 * rp);
+    double2 Wv = in_dot ? *reinterpret_cast<const double2 *>(W + r0 + 2 * rp) : make_double2(0.0, 0.0);
+    if (LOADER == 0 || LOADER == 3) {
+      mbar_wait(bar + stage, (phase_bits >> stage) & 1u);
+      phase_bits ^= 1u << stage;
+    } else {
+      cp_async_wait<1>();
+      __syncthreads();
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    // pass A: partial row sums over this thread's column group
+    // pass A: partial row sums over this thread's column group (columns j = cg mod CG)
     double2 acc = make_double2(0.0, 0.0);
     for (int j = cg; j < k; j += CG) {
       const double2 v = reinterpret_cast<const double2 *>(sV + (size_t)j * RC)[rp];
@@ -358,56 +416,55 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
     }
     sP[cg * RP + rp] = acc;
     __syncthreads();
-    if (tid < RP) {
-      double2 s = sP[tid];
+    // every thread completes the row sum of its row pair: w' and W o w' stay in registers
+    double2 s = sP[rp];
 #pragma unroll
-      for (int c = 1; c < CG; ++c) {
-        const double2 t = sP[c * RP + tid];
-        s.x += t.x;
-        s.y += t.y;
-      }
-      wv.x -= s.x;
-      wv.y -= s.y;
-      *reinterpret_cast<double2 *>(w + r0 + 2 * tid) = wv;
-      const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
-      reinterpret_cast<double2 *>(sWW)[tid] = ww;
-      if (WITH_NORM) nrm += ww.x * wv.x + ww.y * wv.y;
+    for (int c = 1; c < CG; ++c) {
+      const double2 t = sP[c * RP + rp];
+      s.x += t.x;
+      s.y += t.y;
     }
-    __syncthreads();
+    wv.x -= s.x;
+    wv.y -= s.y;
+    if (cg == 0) *reinterpret_cast<double2 *>(w + r0 + 2 * rp) = wv;
+    const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
+    if (WITH_NORM && cg == 0) nrm += ww.x * wv.x + ww.y * wv.y;
     if (in_dot) {
-      // pass B: warp per 8-column tile, lanes over rows
-      // lane owns row pairs (lane + 32 t): consecutive lanes read consecutive 16 B -> no conflicts
-      double2 wl[LR >= 2 ? LR / 2 : 1];
-      if (LR >= 2) {
+      if (RP >= 32) {
+        // pass B, balanced: the same (row pair, column group) mapping as pass A; 8 of the thread's
+        // columns at a time are reduced over the warp's 32 row pairs
+        for (int jb = 0; cg + CG * KT * jb < k; ++jb) {
+          double a8[KT];
 #pragma unroll
-        for (int t = 0; t < LR / 2; ++t) wl[t] = reinterpret_cast<const double2 *>(sWW)[lane + 32 * t];
-      } else {
-        wl[0] = make_double2(sWW[lane], 0.0);
-      }
-      for (int j0 = warp * KT; j0 < k; j0 += (NT / 32) * KT) {
-        double a8[KT];
-#pragma unroll
-        for (int c = 0; c < KT; ++c) {
-          a8[c] = 0.0;
-          if (j0 + c < k) {
-            const double *col = sV + (size_t)(j0 + c) * RC;
-            if (LR >= 2) {
-#pragma unroll
-              for (int t = 0; t < LR / 2; ++t) {
-                const double2 v = reinterpret_cast<const double2 *>(col)[lane + 32 * t];
-                a8[c] = fma(v.x, wl[t].x, fma(v.y, wl[t].y, a8[c]));
-              }
-            } else {
-              a8[c] = col[lane] * wl[0].x;
+          for (int c = 0; c < KT; ++c) {
+            const int j = cg + CG * (KT * jb + c);
+            a8[c] = 0.0;
+            if (j < k) {
+              const double2 v = reinterpret_cast<const double2 *>(sV + (size_t)j * RC)[rp];
+              a8[c] = fma(v.x, ww.x, v.y * ww.y);
             }
           }
+          const double red = warp_reduce8(a8, lane);
+          const int j = cg + CG * (KT * jb + (lane >> 2));
+          if ((lane & 3) == 0 && j < k) myacc[j] += red;
         }
-        const double s = warp_reduce8(a8, lane);
-        if ((lane & 3) == 0 && j0 + (lane >> 2) < k) myacc[j0 + (lane >> 2)] += s;
+      } else {
+        // RC = 32: a warp spans two column groups; go through shared memory for W o w'
+        if (cg == 0) reinterpret_cast<double2 *>(sWW)[rp] = ww;
+        __syncthreads();
+        const double wl = sWW[lane];
+        for (int j0 = warp * KT; j0 < k; j0 += (NT / 32) * KT) {
+          double a8[KT];
+#pragma unroll
+          for (int c = 0; c < KT; ++c) a8[c] = (j0 + c < k) ? sV[(size_t)(j0 + c) * RC + lane] * wl : 0.0;
+          const double red = warp_reduce8(a8, lane);
+          if ((lane & 3) == 0 && j0 + (lane >> 2) < k) myacc[j0 + (lane >> 2)] += red;
+        }
       }
     }
-    __syncthreads();  // sV, sP, sWW are reused by the next block
+    __syncthreads();  // this stage, sP and sWW are reused two iterations / one iteration from now
   }
+  if (LOADER == 1) cp_async_wait<0>();
   if (WITH_NORM) {
     nrm = warp_reduce_sum(nrm);
     if (lane == 0) myacc[k] = nrm;   // only warps holding tid < RP contribute non-zero
@@ -422,17 +479,260 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
   }
 }
 
+// ---- fused update + multidot, register-resident variant ---------------------------------------
+// Block = 64 rows.  Warp c (of 8) owns the columns j = c (mod 8), lane l owns the row pair l: the
+// thread keeps its NJ = ceil(k/8) double2 of V in registers from the moment they arrive.
+//   pass A  partial row sums over the warp's columns -> shared [8][32] double2, ONE __syncthreads
+//   every thread then forms the full row sum for its row pair, w' and W o w' in registers
+//   pass B  the retained V values times W o w', reduced over the lanes (rows) with warp_reduce8;
+//           warp c accumulates its own columns, so no cross-warp reduction is needed.
+// V crosses HBM once and never touches shared memory; the pass-A buffer is double buffered so a
+// block costs a single barrier.
+template <int NJ, bool WITH_NORM>
+__global__ void __launch_bounds__(NT, (NJ <= 13 ? 2 : 1))
+fused_reg_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h1,
+                 double *__restrict__ w, const double *__restrict__ W, int64_t nblocks,
+                 int64_t ndot_blocks, double *__restrict__ partial, int pstride) {
+  constexpr int RC = 64, NW = NT / 32;
+  __shared__ double2 sP[2][NW][32];
+  __shared__ double accS[NW * NJ + 8];   // accS[jj * NW + warp] = column warp + 8 jj ; last slot: norm
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double hreg[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = warp + NW * jj;
+    hreg[jj] = j < k ? h1[j] : 0.0;
+  }
+  double acc2[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) acc2[jj] = 0.0;
+  double nrm = 0.0;
+  int buf = 0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1) {
+    const int64_t r = blk * RC + 2 * lane;
+    const double *vp = V + r;
+    double2 v[NJ];
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = warp + NW * jj;
+      v[jj] = j < k ? ld_stream(reinterpret_cast<const double2 *>(vp + (int64_t)j * ld))
+                    : make_double2(0.0, 0.0);
+    }
+    const bool in_dot = blk < ndot_blocks;
+    double2 wv = *reinterpret_cast<const double2 *>(w + r);
+    double2 Wv = in_dot ? *reinterpret_cast<const double2 *>(W + r) : make_double2(0.0, 0.0);
+    double2 a = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      a.x = fma(v[jj].x, hreg[jj], a.x);
+      a.y = fma(v[jj].y, hreg[jj], a.y);
+    }
+    sP[buf][warp][lane] = a;
+    __syncthreads();
+    double2 s = sP[buf][0][lane];
+#pragma unroll
+    for (int c = 1; c < NW; ++c) {
+      const double2 t = sP[buf][c][lane];
+      s.x += t.x;
+      s.y += t.y;
+    }
+    wv.x -= s.x;
+    wv.y -= s.y;
+    if (warp == 0) *reinterpret_cast<double2 *>(w + r) = wv;
+    const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
+    if (WITH_NORM && warp == 0) nrm += ww.x * wv.x + ww.y * wv.y;
+    if (in_dot) {
+#pragma unroll
+      for (int j0 = 0; j0 < NJ; j0 += KT) {
+        double a8[KT];
+#pragma unroll
+        for (int c = 0; c < KT; ++c)
+          a8[c] = (j0 + c < NJ) ? fma(v[(j0 + c < NJ) ? j0 + c : 0].x, ww.x, v[(j0 + c < NJ) ? j0 + c : 0].y * ww.y)
+                                : 0.0;
+        const double red = warp_reduce8(a8, lane);
+        // lane L with (L & 3) == 0 holds local column j0 + (L >> 2); keep it in that lane's slot
+#pragma unroll
+        for (int c = 0; c < KT; ++c)
+          if (j0 + c < NJ && lane == 4 * c) acc2[j0 + c] += red;
+      }
+    }
+  }
+  // every column's running sum lives in one lane of its warp
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj)
+    if (lane == 4 * (jj % KT)) accS[jj * NW + warp] = acc2[jj];
+  if (WITH_NORM) {
+    nrm = warp_reduce_sum(nrm);
+    if (tid == 0) accS[NW * NJ] = nrm;
+  }
+  __syncthreads();
+  for (int j = tid; j < k; j += NT) partial[(size_t)blockIdx.x * pstride + j] = accS[(j / NW) * NW + (j % NW)];
+  if (WITH_NORM && tid == 0) partial[(size_t)blockIdx.x * pstride + k] = accS[NW * NJ];
+}
+
+// ---- fused update + multidot: 2-D TMA prefetch + register retention ---------------------------
+// ncu on the shared-memory variant above showed the L1/shared pipe at 80 %: the staged block is
+// written once by TMA and read twice (pass A, pass B).  Here every thread reads its part of the
+// block from shared memory ONCE into registers and uses it for both passes, halving the read
+// traffic, while the 2-D TMA keeps one block of prefetch in flight per CTA.
+// Block = 64 rows; warp c owns the columns j = c (mod 8), lane l the row pair l; NJ = ceil(k/8).
+template <int NJ, bool WITH_NORM>
+__global__ void __launch_bounds__(NT, 2)
+fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ w,
+                     const double *__restrict__ W, int64_t nblocks, int64_t ndot_blocks,
+                     double *__restrict__ partial, int pstride, const __grid_constant__ CUtensorMap tmap,
+                     int kbox, int nbox) {
+  constexpr int RC = 64, NW = NT / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int kst = kbox * nbox;
+  double *sV0 = reinterpret_cast<double *>(smem_raw);            // 2 x [kst][RC]
+  double *accS = sV0 + 2 * (size_t)kst * RC;                     // [NW * NJ] column sums (+ norm)
+  double *hS = accS + NW * NJ + 8;                               // [NW * NJ]
+  double2 *sP = reinterpret_cast<double2 *>(hS + NW * NJ);       // [NW][32]
+  double2 *sWW = sP + NW * 32;                                   // [32]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sWW + 32);        // [2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < NW * NJ + 8; j += NT) accS[j] = 0.0;
+  for (int j = tid; j < NW * NJ; j += NT) hS[j] = j < k ? h1[j] : 0.0;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+  }
+  __syncthreads();
+  double nrm = 0.0;
+  uint32_t phase_bits = 0;
+  auto issue = [&](int64_t blk, int stage) {
+    if (tid == 0) {
+      double *dst = sV0 + (size_t)stage * kst * RC;
+      mbar_expect_tx(bar + stage, (uint32_t)(kst * RC * sizeof(double)));
+      for (int b = 0; b < nbox; ++b)
+        tma_load_2d(dst + (size_t)b * kbox * RC, &tmap, (int)(blk * RC), b * kbox, bar + stage);
+    }
+  };
+  int stage = 0;
+  int64_t blk = blockIdx.x;
+  if (blk < nblocks) issue(blk, 0);
+  for (; blk < nblocks; blk += gridDim.x, stage ^= 1) {
+    const int64_t r = blk * RC + 2 * lane;
+    const int64_t nxt = blk + gridDim.x;
+    if (nxt < nblocks) issue(nxt, stage ^ 1);
+    const double *sV = sV0 + (size_t)stage * kst * RC;
+    const bool in_dot = blk < ndot_blocks;
+    double2 wv = make_double2(0.0, 0.0), Wv = make_double2(0.0, 0.0);
+    if (warp == 0) {
+      wv = *reinterpret_cast<const double2 *>(w + r);
+      if (in_dot) Wv = ld_stream(reinterpret_cast<const double2 *>(W + r));
+    }
+    mbar_wait(bar + stage, (phase_bits >> stage) & 1u);
+    phase_bits ^= 1u << stage;
+    double2 v[NJ];
+    double2 a = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = warp + NW * jj;   // j >= k: hS is 0 and the staged column is either valid data or OOB zero fill
+      v[jj] = j < kst ? reinterpret_cast<const double2 *>(sV + (size_t)j * RC)[lane] : make_double2(0.0, 0.0);
+      const double hj = hS[j];
+      a.x = fma(v[jj].x, hj, a.x);
+      a.y = fma(v[jj].y, hj, a.y);
+    }
+    sP[warp * 32 + lane] = a;
+    __syncthreads();
+    if (warp == 0) {
+      double2 s = sP[lane];
+#pragma unroll
+      for (int c = 1; c < NW; ++c) {
+        const double2 t = sP[c * 32 + lane];
+        s.x += t.x;
+        s.y += t.y;
+      }
+      wv.x -= s.x;
+      wv.y -= s.y;
+      *reinterpret_cast<double2 *>(w + r) = wv;
+      const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
+      sWW[lane] = ww;
+      if (WITH_NORM) nrm += ww.x * wv.x + ww.y * wv.y;
+    }
+    __syncthreads();
+    if (in_dot) {
+      const double2 ww = sWW[lane];
+#pragma unroll
+      for (int j0 = 0; j0 < NJ; j0 += KT) {
+        double a8[KT];
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+          const int jj = (j0 + c < NJ) ? j0 + c : 0;
+          a8[c] = (j0 + c < NJ) ? fma(v[jj].x, ww.x, v[jj].y * ww.y) : 0.0;
+        }
+        const double red = warp_reduce8(a8, lane);
+        const int jj = j0 + (lane >> 2);
+        if ((lane & 3) == 0 && jj < NJ) accS[warp + NW * jj] += red;   // column warp + 8 jj, owned by this warp
+      }
+    }
+  }
+  if (WITH_NORM) {
+    nrm = warp_reduce_sum(nrm);
+    if (tid == 0) accS[NW * NJ] = nrm;
+  }
+  __syncthreads();
+  for (int j = tid; j < k; j += NT) partial[(size_t)blockIdx.x * pstride + j] = accS[j];
+  if (WITH_NORM && tid == 0) partial[(size_t)blockIdx.x * pstride + k] = accS[NW * NJ];
+}
+
+inline size_t fused_tma_reg_smem(int k, int nj) {
+  int kbox, nbox;
+  kbox = 0; nbox = (k + 255) / 256; kbox = (k + nbox - 1) / nbox;
+  const size_t kst = (size_t)kbox * nbox;
+  return sizeof(double) * (2 * kst * 64 + 2 * 8 * nj + 8) + sizeof(double2) * (8 * 32 + 32) + 32;
+}
+
+inline void fused_boxes(int k, int *kbox, int *nbox) {
+  *nbox = (k + 255) / 256;
+  *kbox = (k + *nbox - 1) / *nbox;
+}
+
 inline size_t fused_smem_bytes(int rc, int k) {
   const int kpad = (k + KT) & ~(KT - 1);
   const int cg = NT / (rc / 2);
-  return sizeof(double) * ((size_t)k * rc + (NT / 32) * kpad + ((k + 1) & ~1) + 2 * cg * (rc / 2) + rc) + 16;
+  int kbox, nbox;
+  fused_boxes(k, &kbox, &nbox);
+  const size_t kst = (size_t)kbox * nbox;   // >= k
+  return sizeof(double) * (2 * kst * rc + (NT / 32) * kpad + ((k + 1) & ~1) + 2 * cg * (rc / 2) + rc) + 32;
 }
 
-// rows per block: the largest of 128/64/32 that lets two CTAs share an SM; 0 = does not fit
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+// 2-D tensor map over the first k columns of V: dim0 = rows (contiguous), dim1 = columns
+int make_basis_tmap(CUtensorMap *tm, const double *V, int64_t ld, int k, int rc, int kbox) {
+  static encode_tiled_fn enc = nullptr;
+  if (!enc) {
+    cudaDriverEntryPointQueryResult q;
+    void *fn = nullptr;
+    NSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    NSB_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    enc = (encode_tiled_fn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)k};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)rc, (cuuint32_t)kbox};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)V, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (ld=%lld k=%d box=%dx%d)", (int)r,
+              (long long)ld, k, rc, kbox);
+  return NSB_OK;
+}
+
+// rows per block: the largest of 128/64/32 whose two stages let two CTAs share an SM, else the
+// largest that fits alone; 0 = does not fit
 inline int fused_rows(int k) {
   for (int rc : {128, 64, 32})
     if (fused_smem_bytes(rc, k) <= 113 * 1024) return rc;
-  if (fused_smem_bytes(32, k) <= 226 * 1024) return 32;
+  for (int rc : {128, 64, 32})
+    if (fused_smem_bytes(rc, k) <= 226 * 1024) return rc;
   return 0;
 }
 
@@ -504,9 +804,106 @@ int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const d
 int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h1_d, double *w,
                  const double *W, int64_t nrows, int64_t ndot, double *h2_d, bool with_norm, int64_t nalg,
                  int64_t nalg_dot) {
-  const int rc = fused_rows(k);
+  if (ctx->fused_loader == 2 && k <= 8 * 32) {
+    // register-resident variant
+    const int64_t nblocks = nrows / 64, ndot_blocks = ndot / 64;
+    const int nj = (k + 7) / 8;
+    const int per_sm = nj <= 13 ? 2 : 1;
+    const int64_t g = (int64_t)ctx->num_sms * per_sm;
+    const int grid = (int)(nblocks < g ? nblocks : g);
+    const int pstride = kMaxK + 8;
+    NSB_CHECK(ensure_partial(ctx, grid));
+    cudaSetDevice(ctx->device);
+    {
+      ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+#define LAUNCH_REG(NJ)                                                                                    \
+  do {                                                                                                    \
+    if (with_norm)                                                                                        \
+      fused_reg_kernel<NJ, true><<<grid, NT, 0, ctx->stream>>>(V, ld, k, h1_d, w, W, nblocks, ndot_blocks, \
+                                                               ctx->partial_d, pstride);                  \
+    else                                                                                                  \
+      fused_reg_kernel<NJ, false><<<grid, NT, 0, ctx->stream>>>(V, ld, k, h1_d, w, W, nblocks, ndot_blocks, \
+                                                                ctx->partial_d, pstride);                 \
+  } while (0)
+      if (nj <= 2) LAUNCH_REG(2);
+      else if (nj <= 4) LAUNCH_REG(4);
+      else if (nj <= 7) LAUNCH_REG(7);
+      else if (nj <= 10) LAUNCH_REG(10);
+      else if (nj <= 13) LAUNCH_REG(13);
+      else if (nj <= 16) LAUNCH_REG(16);
+      else if (nj <= 20) LAUNCH_REG(20);
+      else if (nj <= 26) LAUNCH_REG(26);
+      else LAUNCH_REG(32);
+#undef LAUNCH_REG
+    }
+    const int kout = with_norm ? k + 1 : k;
+    {
+      ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
+      reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
+                                                                               kout, h2_d, 0, nullptr);
+    }
+    ctx->launches += 2;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
+  if (ctx->fused_loader == 3 && k >= ctx->fused_reg_min_k && k <= 8 * 26 &&
+      fused_tma_reg_smem(k, (k + 7) / 8) <= 226 * 1024) {
+    // 2-D TMA prefetch + register retention, 64-row blocks
+    const int64_t nblocks = nrows / 64, ndot_blocks = ndot / 64;
+    const int njr = (k + 7) / 8;
+    const int nj = njr <= 4 ? 4 : njr <= 7 ? 7 : njr <= 10 ? 10 : njr <= 13 ? 13 : njr <= 16 ? 16 : njr <= 20 ? 20 : 26;
+    const size_t smem = fused_tma_reg_smem(k, nj);
+    int kbox, nbox;
+    fused_boxes(k, &kbox, &nbox);
+    CUtensorMap tmap;
+    NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, 64, kbox));
+    const int64_t g = (int64_t)ctx->num_sms * 2;
+    const int grid = (int)(nblocks < g ? nblocks : g);
+    const int pstride = kMaxK + 8;
+    NSB_CHECK(ensure_partial(ctx, grid));
+    cudaSetDevice(ctx->device);
+    {
+      ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+#define LAUNCH_TR2(NJ, NORM)                                                                            \
+  do {                                                                                                  \
+    NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg_kernel<NJ, NORM>,                                       \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    fused_tma_reg_kernel<NJ, NORM><<<grid, NT, smem, ctx->stream>>>(k, h1_d, w, W, nblocks, ndot_blocks, \
+                                                                   ctx->partial_d, pstride, tmap, kbox, nbox); \
+  } while (0)
+#define LAUNCH_TR(NJ) do { if (with_norm) LAUNCH_TR2(NJ, true); else LAUNCH_TR2(NJ, false); } while (0)
+      switch (nj) {
+        case 4: LAUNCH_TR(4); break;
+        case 7: LAUNCH_TR(7); break;
+        case 10: LAUNCH_TR(10); break;
+        case 13: LAUNCH_TR(13); break;
+        case 16: LAUNCH_TR(16); break;
+        case 20: LAUNCH_TR(20); break;
+        default: LAUNCH_TR(26); break;
+      }
+#undef LAUNCH_TR
+#undef LAUNCH_TR2
+    }
+    const int kout = with_norm ? k + 1 : k;
+    {
+      ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
+      reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
+                                                                               kout, h2_d, 0, nullptr);
+    }
+    ctx->launches += 2;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
+  int rc = fused_rows(k);
   NSB_REQUIRE(rc != 0, "fused update+dot: k=%d does not fit in shared memory", k);
+  if (ctx->fused_rc && fused_smem_bytes(ctx->fused_rc, k) <= 226 * 1024) rc = ctx->fused_rc;
+  const int loader = ctx->fused_loader;
   const size_t smem = fused_smem_bytes(rc, k);
+  int kbox, nbox;
+  fused_boxes(k, &kbox, &nbox);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (loader == 3) NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, rc, kbox));
   const int64_t nblocks = nrows / rc, ndot_blocks = ndot / rc;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
@@ -518,17 +915,24 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
   {
     // algorithmic bytes: V once, w read + written, W once
     ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
-#define LAUNCH_FUSED(RC, NORM)                                                                          \
+#define LAUNCH_FUSED2(RC, NORM, LD)                                                                     \
   do {                                                                                                  \
-    NSB_CUDA(cudaFuncSetAttribute(fused_update_dot_kernel<RC, NORM>,                                    \
+    NSB_CUDA(cudaFuncSetAttribute(fused_update_dot_kernel<RC, NORM, LD>,                                \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    fused_update_dot_kernel<RC, NORM><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h1_d, w, W, nblocks,   \
-                                                                      ndot_blocks, ctx->partial_d, pstride); \
+    fused_update_dot_kernel<RC, NORM, LD><<<grid, NT, smem, ctx->stream>>>(                             \
+        V, ld, k, h1_d, w, W, nblocks, ndot_blocks, ctx->partial_d, pstride, tmap, kbox, nbox);         \
+  } while (0)
+#define LAUNCH_FUSED(RC, NORM)                                                \
+  do {                                                                        \
+    if (loader == 0) LAUNCH_FUSED2(RC, NORM, 0);                              \
+    else if (loader == 1) LAUNCH_FUSED2(RC, NORM, 1);                         \
+    else LAUNCH_FUSED2(RC, NORM, 3);                                          \
   } while (0)
     if (rc == 128) { if (with_norm) LAUNCH_FUSED(128, true); else LAUNCH_FUSED(128, false); }
     else if (rc == 64) { if (with_norm) LAUNCH_FUSED(64, true); else LAUNCH_FUSED(64, false); }
     else { if (with_norm) LAUNCH_FUSED(32, true); else LAUNCH_FUSED(32, false); }
 #undef LAUNCH_FUSED
+#undef LAUNCH_FUSED2
   }
   const int kout = with_norm ? k + 1 : k;
   {
