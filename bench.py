@@ -215,7 +215,9 @@ def run_native(a):
         if world == 1 and a.gpus > 1:
             raise SystemExit('launch with torch.distributed.run --nproc-per-node N for --gpus N > 1')
     if rank == 0:
-        ge.build()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):   # stdout carries the one JSON line only
+            ge.build()
     torch.cuda.set_device(local)
     uid = None
     if world > 1:

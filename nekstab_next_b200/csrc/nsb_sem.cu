@@ -246,6 +246,152 @@ axhelm3d_kernel(const double *__restrict__ u, double *__restrict__ w, const doub
   }
 }
 
+// ---- axhelm, 3-D, N = 7: one warp per element -------------------------------------------------
+// ncu on the kernel above (64 threads per element, two CTA-wide barriers per plane) showed 25 %
+// warps active, 3.75 shared wavefronts per point and 36 % DRAM.  Here a single warp owns an
+// element, so planes are separated by __syncwarp only: lane (i = lane % 8, jp = lane / 8) holds
+// the two u/w columns (i, jp, :) and (i, jp + 4, :) in registers, which lets the r-derivative
+// share its D row and the s-derivative its u value between the two points (3 shared loads per
+// point per l instead of 4); D(k,l) for the register-resident t-derivative comes from constant
+// memory with compile-time indices; plane rows are padded to 10 doubles (conflict-free).
+__constant__ double c_D8[64];    // c_D8[a * 8 + b] = D_ab for N = 7
+
+template <bool CONV, int EPI>
+__global__ void __launch_bounds__(128, 3)
+axhelm3d_warp8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
+                      const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
+                      const double *__restrict__ cv, double alpha, double beta,
+                      const double *__restrict__ bmask) {
+  constexpr int LX = 8, N2 = 64, N3 = 512, PS = 10, WPC = 4;   // PS: padded plane row stride
+  __shared__ double sD[LX * LX], sDt[LX * LX];
+  __shared__ double s_u[WPC][LX * PS], s_wr[WPC][LX * PS], s_ws[WPC][LX * PS];
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  if (tid < N2) {
+    const int a = tid / LX, b = tid % LX;
+    sD[a * LX + b] = c_D8[a * LX + b];
+    sDt[b * LX + a] = c_D8[a * LX + b];
+  }
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * WPC + wp;
+  if (e >= nel) return;
+  const int i = lane & 7, jp = lane >> 3, j0 = jp, j1 = jp + 4;
+  const int64_t base0 = e * N3 + j0 * LX + i, base1 = e * N3 + j1 * LX + i;
+  double *su = s_u[wp], *swr = s_wr[wp], *sws = s_ws[wp];
+  double uk0[LX], uk1[LX], wk0[LX], wk1[LX];
+#pragma unroll
+  for (int k = 0; k < LX; ++k) {
+    uk0[k] = u[base0 + k * N2];
+    uk1[k] = u[base1 + k * N2];
+    wk0[k] = 0.0;
+    wk1[k] = 0.0;
+  }
+  // geometric factors are prefetched one plane ahead so that a warp always has two planes of
+  // loads in flight (ncu on the first warp-per-element version: 80 % of cycles with no eligible
+  // warp, stalled on the loads issued at the top of each plane)
+  double gn_a[6], gn_b[6], cn_a[3] = {0, 0, 0}, cn_b[3] = {0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    gn_a[c] = ld_stream1(g + c * npts + base0);
+    gn_b[c] = ld_stream1(g + c * npts + base1);
+  }
+  if (CONV) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      cn_a[c] = ld_stream1(cv + c * npts + base0);
+      cn_b[c] = ld_stream1(cv + c * npts + base1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LX; ++k) {
+    double ga[6], gb[6], ca[3], cb[3];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      ga[c] = gn_a[c];
+      gb[c] = gn_b[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ca[c] = cn_a[c];
+      cb[c] = cn_b[c];
+    }
+    if (k + 1 < LX) {
+      const int64_t q0 = base0 + (k + 1) * N2, q1 = base1 + (k + 1) * N2;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        gn_a[c] = ld_stream1(g + c * npts + q0);
+        gn_b[c] = ld_stream1(g + c * npts + q1);
+      }
+      if (CONV) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          cn_a[c] = ld_stream1(cv + c * npts + q0);
+          cn_b[c] = ld_stream1(cv + c * npts + q1);
+        }
+      }
+    }
+    su[j0 * PS + i] = uk0[k];
+    su[j1 * PS + i] = uk1[k];
+    __syncwarp();
+    double ur0 = 0, ur1 = 0, us0 = 0, us1 = 0, ut0 = 0, ut1 = 0;
+#pragma unroll
+    for (int l = 0; l < LX; ++l) {
+      const double di = sDt[l * LX + i];          // D(i,l)
+      ur0 = fma(di, su[j0 * PS + l], ur0);
+      ur1 = fma(di, su[j1 * PS + l], ur1);
+      const double b = su[l * PS + i];            // u(i,l,k)
+      us0 = fma(sDt[l * LX + j0], b, us0);        // D(j0,l)
+      us1 = fma(sDt[l * LX + j1], b, us1);
+      const double dk = c_D8[k * LX + l];         // D(k,l), compile-time constant-bank address
+      ut0 = fma(dk, uk0[l], ut0);
+      ut1 = fma(dk, uk1[l], ut1);
+    }
+    const double wr0 = h1 * (ga[0] * ur0 + ga[3] * us0 + ga[4] * ut0);
+    const double ws0 = h1 * (ga[1] * us0 + ga[3] * ur0 + ga[5] * ut0);
+    const double wt0 = h1 * (ga[2] * ut0 + ga[4] * ur0 + ga[5] * us0);
+    const double wr1 = h1 * (gb[0] * ur1 + gb[3] * us1 + gb[4] * ut1);
+    const double ws1 = h1 * (gb[1] * us1 + gb[3] * ur1 + gb[5] * ut1);
+    const double wt1 = h1 * (gb[2] * ut1 + gb[4] * ur1 + gb[5] * us1);
+    swr[j0 * PS + i] = wr0;
+    swr[j1 * PS + i] = wr1;
+    sws[j0 * PS + i] = ws0;
+    sws[j1 * PS + i] = ws1;
+    __syncwarp();
+    double a0 = CONV ? (ca[0] * ur0 + ca[1] * us0 + ca[2] * ut0) : 0.0;
+    double a1 = CONV ? (cb[0] * ur1 + cb[1] * us1 + cb[2] * ut1) : 0.0;
+#pragma unroll
+    for (int l = 0; l < LX; ++l) {
+      const double ci = sD[l * LX + i];           // D(l,i)
+      a0 = fma(ci, swr[j0 * PS + l], a0);
+      a1 = fma(ci, swr[j1 * PS + l], a1);
+      const double ev = sws[l * PS + i];
+      a0 = fma(sD[l * LX + j0], ev, a0);          // D(l,j0)
+      a1 = fma(sD[l * LX + j1], ev, a1);
+      const double dk = c_D8[k * LX + l];
+      wk0[l] = fma(dk, wt0, wk0[l]);
+      wk1[l] = fma(dk, wt1, wk1[l]);
+    }
+    wk0[k] += a0;
+    wk1[k] += a1;
+  }
+  const bool b0 = (i == 0 || i == LX - 1 || j0 == 0), b1 = (i == 0 || i == LX - 1 || j1 == LX - 1);
+#pragma unroll
+  for (int k = 0; k < LX; ++k) {
+    const int64_t p0 = base0 + k * N2, p1 = base1 + k * N2;
+    double v0 = wk0[k], v1 = wk1[k];
+    if (h2 != 0.0) {
+      v0 = fma(h2 * ld_stream1(bm1 + p0), uk0[k], v0);
+      v1 = fma(h2 * ld_stream1(bm1 + p1), uk1[k], v1);
+    }
+    if (EPI == 1) {
+      const bool kb = (k == 0 || k == LX - 1);
+      if (!(b0 || kb)) v0 = alpha * uk0[k] + beta * ld_stream1(bmask + p0) * v0;
+      if (!(b1 || kb)) v1 = alpha * uk1[k] + beta * ld_stream1(bmask + p1) * v1;
+    }
+    w[p0] = v0;
+    w[p1] = v1;
+  }
+}
+
 // ---- axhelm, 2-D (one thread per point; parity configurations only) --------------------------
 template <bool CONV, int EPI>
 __global__ void axhelm2d_kernel(const double *__restrict__ u, double *__restrict__ w,
@@ -379,6 +525,14 @@ void launch_ax3d_t(nsb_sem_t S, const double *u, double *w, double h1, double h2
 template <bool CONV, int EPI>
 int launch_ax3d(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
                 double alpha, double beta, const double *bmask) {
+  if (S->lx == 8 && !S->ctx->ax_generic) {
+    const int64_t grid = (S->nel + 3) / 4;
+    axhelm3d_warp8_kernel<CONV, EPI><<<(unsigned)grid, 128, 0, S->ctx->stream>>>(
+        u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask);
+    S->ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
   switch (S->lx) {
 #define CASE(L) case L: launch_ax3d_t<L, CONV, EPI>(S, u, w, h1, h2, cv, alpha, beta, bmask); break;
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
@@ -515,6 +669,12 @@ extern "C" int nsb_sem_create(nsb_context_t ctx, int dim, int N, int64_t nel, co
   S->z_h.resize(lx);
   S->w_h.resize(lx);
   nsb_gll(N, S->z_h.data(), S->w_h.data(), S->D_h.data());
+  if (lx == 8) {
+    double Drm[64];  // row-major D_ab
+    for (int a = 0; a < 8; ++a)
+      for (int b = 0; b < 8; ++b) Drm[a * 8 + b] = S->D_h[a + 8 * b];
+    NSB_CUDA(cudaMemcpyToSymbol(c_D8, Drm, sizeof(Drm)));
+  }
   const size_t nb = sizeof(double) * npts;
   double *wq_d = nullptr, *xyz_d = nullptr;
   NSB_CUDA(cudaMalloc(&S->D_d, sizeof(double) * lx * lx));
