@@ -399,4 +399,28 @@ def run_native(a):
 
 if __name__ == '__main__':
     args = parse()
-    sys.exit(run_reference(args) if args.impl == 'reference' else run_native(args))
+    # stdout must carry exactly one JSON line: libraries (NCCL banner, build logs) that write to
+    # fd 1 are diverted to stderr until the result is printed.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _line = []
+    _print = print
+
+    def print(*a, **k):  # noqa: A001  (the run_* functions print the JSON line last)
+        _line.append(' '.join(str(x) for x in a))
+
+    import builtins
+    builtins.print = print
+    try:
+        rc = run_reference(args) if args.impl == 'reference' else run_native(args)
+    finally:
+        builtins.print = _print
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+    for ln in _line:
+        if ln.startswith('{'):
+            _print(ln, flush=True)
+        else:
+            _print(ln, file=sys.stderr, flush=True)
+    sys.exit(rc)

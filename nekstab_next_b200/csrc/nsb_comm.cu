@@ -104,14 +104,14 @@ int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n) {
   return NSB_OK;
 }
 
-int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers) {
+int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int nf, cudaStream_t st) {
   if (peers.empty()) return NSB_OK;
   NSB_REQUIRE(ctx->nccl_comm, "sendrecv: no communicator");
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   NSB_NCCL(g_nccl.GroupStart());
   for (const auto &P : peers) {
-    NSB_NCCL(g_nccl.Send(P.send_d, (size_t)P.n, ncclDouble, P.rank, comm, ctx->stream));
-    NSB_NCCL(g_nccl.Recv(P.recv_d, (size_t)P.n, ncclDouble, P.rank, comm, ctx->stream));
+    NSB_NCCL(g_nccl.Send(P.send_d, (size_t)P.n * nf, ncclDouble, P.rank, comm, st));
+    NSB_NCCL(g_nccl.Recv(P.recv_d, (size_t)P.n * nf, ncclDouble, P.rank, comm, st));
   }
   NSB_NCCL(g_nccl.GroupEnd());
   return NSB_OK;
@@ -153,30 +153,63 @@ int exchange_setup(nsb_sem_t S) {
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(send_d);
   cudaFree(all_d);
-  // 3. intersect
+  // 3. intersect: which of my nodes does each other rank also hold?
   for (auto &Pr : S->peers) {
     cudaFree(Pr.idx_d);
     cudaFree(Pr.send_d);
     cudaFree(Pr.recv_d);
   }
   S->peers.clear();
+  std::vector<std::vector<int32_t>> shared_with(P);
+  std::vector<char> is_ifc(S->nshared, 0);
   for (int r = 0; r < P; ++r) {
     if (r == ctx->rank) continue;
     const int64_t *other = all.data() + (size_t)r * mx;
-    std::vector<int32_t> nodes;
     int64_t a = 0, b = 0;
     while (a < S->nshared && b < cnt[r]) {
       if (my[a].first < other[b]) ++a;
       else if (my[a].first > other[b]) ++b;
-      else { nodes.push_back(my[a].second); ++a; ++b; }
+      else { shared_with[r].push_back(my[a].second); is_ifc[my[a].second] = 1; ++a; ++b; }
     }
-    if (nodes.empty()) continue;
+  }
+  // 4. reorder the gather-scatter lists: private nodes first, interface nodes last
+  std::vector<int64_t> newpos(S->nshared);
+  int64_t nloc = 0;
+  for (int64_t n = 0; n < S->nshared; ++n) if (!is_ifc[n]) newpos[n] = nloc++;
+  int64_t w = nloc;
+  for (int64_t n = 0; n < S->nshared; ++n) if (is_ifc[n]) newpos[n] = w++;
+  std::vector<int64_t> off2(S->nshared + 1), gid2(S->nshared), inv(S->nshared);
+  for (int64_t n = 0; n < S->nshared; ++n) inv[newpos[n]] = n;
+  std::vector<int32_t> idx2(S->gs_idx_h.size());
+  int64_t q = 0;
+  for (int64_t m = 0; m < S->nshared; ++m) {
+    const int64_t n = inv[m];
+    off2[m] = q;
+    for (int64_t t = S->gs_off_h[n]; t < S->gs_off_h[n + 1]; ++t) idx2[q++] = S->gs_idx_h[t];
+    gid2[m] = S->node_gid[n];
+  }
+  off2[S->nshared] = q;
+  S->gs_off_h.swap(off2);
+  S->gs_idx_h.swap(idx2);
+  S->node_gid.swap(gid2);
+  S->n_local = nloc;
+  NSB_CUDA(cudaMemcpy(S->gs_off_d, S->gs_off_h.data(), sizeof(int64_t) * (S->nshared + 1), cudaMemcpyHostToDevice));
+  NSB_CUDA(cudaMemcpy(S->gs_idx_d, S->gs_idx_h.data(), sizeof(int32_t) * S->gs_idx_h.size(), cudaMemcpyHostToDevice));
+  const int64_t nifc = S->nshared - nloc;
+  if (S->node_sum_d) cudaFree(S->node_sum_d);
+  S->node_sum_d = nullptr;
+  NSB_CUDA(cudaMalloc(&S->node_sum_d, sizeof(double) * S->ns_fields * (nifc > 0 ? nifc : 1)));
+  for (int r = 0; r < P; ++r) {
+    if (shared_with[r].empty()) continue;
+    // both sides list a pair's nodes in ascending global id (shared_with was built that way)
+    std::vector<int32_t> nodes(shared_with[r].size());
+    for (size_t t = 0; t < nodes.size(); ++t) nodes[t] = (int32_t)(newpos[shared_with[r][t]] - nloc);
     nsb_sem_s::Peer Pr;
     Pr.rank = r;
     Pr.n = (int64_t)nodes.size();
     NSB_CUDA(cudaMalloc(&Pr.idx_d, sizeof(int32_t) * Pr.n));
-    NSB_CUDA(cudaMalloc(&Pr.send_d, sizeof(double) * Pr.n));
-    NSB_CUDA(cudaMalloc(&Pr.recv_d, sizeof(double) * Pr.n));
+    NSB_CUDA(cudaMalloc(&Pr.send_d, sizeof(double) * Pr.n * S->ns_fields));
+    NSB_CUDA(cudaMalloc(&Pr.recv_d, sizeof(double) * Pr.n * S->ns_fields));
     NSB_CUDA(cudaMemcpy(Pr.idx_d, nodes.data(), sizeof(int32_t) * Pr.n, cudaMemcpyHostToDevice));
     S->peers.push_back(Pr);
   }

@@ -108,13 +108,18 @@ struct nsb_sem_s {
   int64_t *gs_off_d = nullptr;   // [nshared+1]
   int32_t *gs_idx_d = nullptr;   // local point indices
   int64_t gs_nnz = 0;
-  double *node_sum_d = nullptr;  // [nshared] scratch for the multi-rank path
+  int64_t n_local = 0;           // nodes [0, n_local) are private to this rank, the rest are interface nodes
+  int ns_fields = 8;             // fields one batched gather-scatter can carry
+  double *node_sum_d = nullptr;  // [ns_fields][nshared - n_local] interface node sums (multi-rank)
   std::vector<int64_t> node_gid; // global id of each gs node
+  std::vector<int64_t> gs_off_h; // host copies of the CSR lists (reordered by exchange_setup)
+  std::vector<int32_t> gs_idx_h;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   // inter-rank exchange (nsb_sem.cu / nsb_comm.cu)
   struct Peer {
     int rank;
     int64_t n;                   // shared nodes with that rank
-    int32_t *idx_d;              // gs-node index of every node shared with that rank (sorted by gid)
+    int32_t *idx_d;              // interface-node index (node - n_local) of every node shared with that rank, sorted by gid
     double *send_d, *recv_d;
   };
   std::vector<Peer> peers;
@@ -151,7 +156,7 @@ int ensure_partial(nsb_context_t ctx, int64_t rows);
 int comm_init(nsb_context_t ctx, const void *unique_id);
 int comm_destroy(nsb_context_t ctx);
 int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n);  // on ctx->stream, in place
-int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers);
+int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int nf, cudaStream_t st);
 int exchange_setup(nsb_sem_t sem);
 // implemented in nsb_orth.cu
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d);

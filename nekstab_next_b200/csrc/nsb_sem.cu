@@ -171,7 +171,9 @@ __global__ void __launch_bounds__((256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1) * 
 axhelm3d_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
                 const double *__restrict__ bm1, const double *__restrict__ Dg, int64_t nel,
                 int64_t npts, double h1, double h2, const double *__restrict__ cv, double alpha,
-                double beta, const double *__restrict__ bmask) {
+                double beta, const double *__restrict__ bmask, int64_t fstride) {
+  u += (int64_t)blockIdx.y * fstride;
+  w += (int64_t)blockIdx.y * fstride;
   constexpr int EPC = (256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1);
   constexpr int N2 = LX * LX, N3 = LX * LX * LX;
   __shared__ double sD[LX * LX], sDt[LX * LX];
@@ -261,7 +263,9 @@ __global__ void __launch_bounds__(128, 3)
 axhelm3d_warp8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
                       const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
                       const double *__restrict__ cv, double alpha, double beta,
-                      const double *__restrict__ bmask) {
+                      const double *__restrict__ bmask, int64_t fstride) {
+  u += (int64_t)blockIdx.y * fstride;
+  w += (int64_t)blockIdx.y * fstride;
   constexpr int LX = 8, N2 = 64, N3 = 512, PS = 10, WPC = 4;   // PS: padded plane row stride
   __shared__ double sD[LX * LX], sDt[LX * LX];
   __shared__ double s_u[WPC][LX * PS], s_wr[WPC][LX * PS], s_ws[WPC][LX * PS];
@@ -398,7 +402,9 @@ __global__ void axhelm2d_kernel(const double *__restrict__ u, double *__restrict
                                 const double *__restrict__ g, const double *__restrict__ bm1,
                                 const double *__restrict__ Dg, int lx, int64_t nel, int64_t npts,
                                 double h1, double h2, const double *__restrict__ cv, double alpha,
-                                double beta, const double *__restrict__ bmask) {
+                                double beta, const double *__restrict__ bmask, int64_t fstride) {
+  u += (int64_t)blockIdx.y * fstride;
+  w += (int64_t)blockIdx.y * fstride;
   extern __shared__ double sm[];
   const int n2 = lx * lx;
   double *sD = sm, *s_u = sm + n2, *s_wr = sm + 2 * n2, *s_ws = sm + 3 * n2;
@@ -440,19 +446,24 @@ __global__ void axhelm2d_kernel(const double *__restrict__ u, double *__restrict
 template <int EPI>
 __global__ void __launch_bounds__(256)
 gs_kernel(double *__restrict__ v, const int64_t *__restrict__ off, const int32_t *__restrict__ idx,
-          int64_t nnodes, const double *__restrict__ uin, double alpha, double beta,
-          const double *__restrict__ bmask, double *__restrict__ node_sum) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnodes) return;
+          int64_t n0, int64_t n1, const double *__restrict__ uin, double alpha, double beta,
+          const double *__restrict__ bmask, double *__restrict__ node_sum, int64_t fstride,
+          int64_t ns_stride) {
+  const int64_t n = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n1) return;
+  const int f = blockIdx.y;             // field (velocity component) handled by this grid row
+  v += (int64_t)f * fstride;
+  if (uin) uin += (int64_t)f * fstride;
+  if (node_sum) node_sum += (int64_t)f * ns_stride;
   const int64_t a = off[n], b = off[n + 1];
   double s = 0.0;
   if (EPI == 3 || EPI == 4) {
-    s = node_sum[n];
+    s = node_sum[n - n0];
   } else {
     for (int64_t q = a; q < b; ++q) s += v[idx[q]];
   }
   if (EPI == 2) {
-    node_sum[n] = s;
+    node_sum[n - n0] = s;
     return;
   }
   for (int64_t q = a; q < b; ++q) {
@@ -462,16 +473,19 @@ gs_kernel(double *__restrict__ v, const int64_t *__restrict__ off, const int32_t
   }
 }
 
+// interface buffers hold nf fields back to back: buf[f * n + t]
 __global__ void pack_kernel(const double *__restrict__ node_sum, const int32_t *__restrict__ nodes,
-                            int64_t n, double *__restrict__ buf) {
+                            int64_t n, double *__restrict__ buf, int64_t ns_stride) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) buf[t] = node_sum[nodes[t]];
+  const int f = blockIdx.y;
+  if (t < n) buf[(int64_t)f * n + t] = node_sum[(int64_t)f * ns_stride + nodes[t]];
 }
 
 __global__ void unpack_add_kernel(double *__restrict__ node_sum, const int32_t *__restrict__ nodes,
-                                  int64_t n, const double *__restrict__ buf) {
+                                  int64_t n, const double *__restrict__ buf, int64_t ns_stride) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) node_sum[nodes[t]] += buf[t];
+  const int f = blockIdx.y;
+  if (t < n) node_sum[(int64_t)f * ns_stride + nodes[t]] += buf[(int64_t)f * n + t];
 }
 
 __global__ void col2_kernel(double *__restrict__ v, const double *__restrict__ c, int64_t n) {
@@ -514,27 +528,27 @@ __global__ void conv_coeff_kernel(const double *__restrict__ rst, const double *
 }
 
 template <int LX, bool CONV, int EPI>
-void launch_ax3d_t(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
-                   double alpha, double beta, const double *bmask) {
+void launch_ax3d_t(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                   const double *cv, double alpha, double beta, const double *bmask) {
   constexpr int EPC = (256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1);
   const int64_t grid = (S->nel + EPC - 1) / EPC;
-  axhelm3d_kernel<LX, CONV, EPI><<<(unsigned)grid, EPC * LX * LX, 0, S->ctx->stream>>>(
-      u, w, S->g_d, S->bm1_d, S->D_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask);
+  axhelm3d_kernel<LX, CONV, EPI><<<dim3((unsigned)grid, nf), EPC * LX * LX, 0, S->ctx->stream>>>(
+      u, w, S->g_d, S->bm1_d, S->D_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
 }
 
 template <bool CONV, int EPI>
-int launch_ax3d(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
-                double alpha, double beta, const double *bmask) {
+int launch_ax3d(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                const double *cv, double alpha, double beta, const double *bmask) {
   if (S->lx == 8 && !S->ctx->ax_generic) {
     const int64_t grid = (S->nel + 3) / 4;
-    axhelm3d_warp8_kernel<CONV, EPI><<<(unsigned)grid, 128, 0, S->ctx->stream>>>(
-        u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask);
+    axhelm3d_warp8_kernel<CONV, EPI><<<dim3((unsigned)grid, nf), 128, 0, S->ctx->stream>>>(
+        u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
     S->ctx->launches++;
     NSB_CUDA(cudaGetLastError());
     return NSB_OK;
   }
   switch (S->lx) {
-#define CASE(L) case L: launch_ax3d_t<L, CONV, EPI>(S, u, w, h1, h2, cv, alpha, beta, bmask); break;
+#define CASE(L) case L: launch_ax3d_t<L, CONV, EPI>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask); break;
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
 #undef CASE
     default:
@@ -547,80 +561,94 @@ int launch_ax3d(nsb_sem_t S, const double *u, double *w, double h1, double h2, c
 }
 
 template <bool CONV, int EPI>
-int launch_ax2d(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
-                double alpha, double beta, const double *bmask) {
+int launch_ax2d(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                const double *cv, double alpha, double beta, const double *bmask) {
   const int n2 = S->lx * S->lx;
-  axhelm2d_kernel<CONV, EPI><<<(unsigned)S->nel, n2, sizeof(double) * 4 * n2, S->ctx->stream>>>(
-      u, w, S->g_d, S->bm1_d, S->D_d, S->lx, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask);
+  axhelm2d_kernel<CONV, EPI><<<dim3((unsigned)S->nel, nf), n2, sizeof(double) * 4 * n2, S->ctx->stream>>>(
+      u, w, S->g_d, S->bm1_d, S->D_d, S->lx, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
 }
 
-int launch_axhelm(nsb_sem_t S, const double *u, double *w, double h1, double h2, const double *cv,
-                  int epi, double alpha, double beta, const double *bmask) {
+// axhelm on nf fields that sit fstride doubles apart (velocity components of one column)
+int launch_axhelm(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                  const double *cv, int epi, double alpha, double beta, const double *bmask) {
   cudaSetDevice(S->ctx->device);
   // algorithmic bytes per point: u, w, G1..G6 (G1,G2,G4 in 2-D), bm1 if h2 != 0, C if convecting,
   // bmask on element-interior points of the fused epilogue
   const double fint = std::pow((double)(S->lx - 2) / S->lx, S->dim);
   const double per_pt = 8.0 * (2 + S->ng + (h2 != 0.0 ? 1 : 0) + (cv ? S->dim : 0) + (epi ? fint : 0.0));
-  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts);
+  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts * nf);
   if (S->dim == 3) {
-    if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
-                       : launch_ax3d<true, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
-    return epi ? launch_ax3d<false, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
-               : launch_ax3d<false, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
+    if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
+                       : launch_ax3d<true, 0>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask);
+    return epi ? launch_ax3d<false, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
+               : launch_ax3d<false, 0>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask);
   }
-  if (cv) return epi ? launch_ax2d<true, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
-                     : launch_ax2d<true, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
-  return epi ? launch_ax2d<false, 1>(S, u, w, h1, h2, cv, alpha, beta, bmask)
-             : launch_ax2d<false, 0>(S, u, w, h1, h2, cv, alpha, beta, bmask);
+  if (cv) return epi ? launch_ax2d<true, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
+                     : launch_ax2d<true, 0>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask);
+  return epi ? launch_ax2d<false, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
+             : launch_ax2d<false, 0>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask);
 }
 
 inline unsigned blocks_for(int64_t n, int nt = 256) { return (unsigned)((n + nt - 1) / nt); }
 
-// gather-scatter incl. the inter-rank exchange; epi 0: plain dssum, 1: fused operator tail
-int launch_gs(nsb_sem_t S, double *v, int epi, const double *uin, double alpha, double beta,
-              const double *bmask) {
+template <int EPI>
+void gs_launch(nsb_sem_t S, cudaStream_t st, double *v, int64_t n0, int64_t n1, int nf, int64_t fstride,
+               const double *uin, double alpha, double beta, const double *bmask, double *ns, int64_t ns_stride) {
+  if (n1 <= n0) return;
+  gs_kernel<EPI><<<dim3(blocks_for(n1 - n0), nf), 256, 0, st>>>(v, S->gs_off_d, S->gs_idx_d, n0, n1, uin, alpha,
+                                                              beta, bmask, ns, fstride, ns_stride);
+  S->ctx->launches++;
+}
+
+// Gather-scatter on nf fields incl. the inter-rank exchange; epi 0: plain dssum, 1: fused operator
+// tail.  Nodes [0, n_local) are private to this rank and go through one fused kernel; the
+// interface nodes [n_local, nshared) take the sum -> pack -> NCCL send/recv -> add -> scatter path
+// on a second stream, overlapped with the private part.
+int launch_gs(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const double *uin, double alpha,
+              double beta, const double *bmask) {
   nsb_context_t ctx = S->ctx;
   cudaSetDevice(ctx->device);
   if (S->nshared == 0) return NSB_OK;
-  const unsigned nb = blocks_for(S->nshared);
+  if (ctx->nranks > 1 && !S->exchange_ready) {
+    set_error("dssum: nsb_sem_setup_exchange has not been called on this multi-rank context");
+    return NSB_EINVAL;
+  }
   // algorithmic bytes: every listed point read + written (16), its index (4), node offsets (8 per
   // node), plus uin and bmask per point in the fused tail
-  ProfScope ps(ctx, PC_GS, (double)S->gs_nnz * (20.0 + (epi ? 16.0 : 0.0)) + 8.0 * (double)S->nshared);
-  if (ctx->nranks == 1 || S->peers.empty()) {
-    if (ctx->nranks > 1 && !S->exchange_ready) {
-      set_error("dssum: nsb_sem_setup_exchange has not been called on this multi-rank context");
-      return NSB_EINVAL;
-    }
-    if (epi == 0)
-      gs_kernel<0><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, nullptr, 0, 0, nullptr, nullptr);
-    else
-      gs_kernel<1><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, uin, alpha, beta, bmask, nullptr);
-    ctx->launches++;
+  ProfScope ps(ctx, PC_GS, nf * ((double)S->gs_nnz * (20.0 + (epi ? 16.0 : 0.0)) + 8.0 * (double)S->nshared));
+  const int64_t nloc = S->n_local, nifc = S->nshared - S->n_local;
+  if (ctx->nranks == 1 || nifc == 0 || S->peers.empty()) {
+    if (epi == 0) gs_launch<0>(S, ctx->stream, v, 0, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, nullptr, 0);
+    else gs_launch<1>(S, ctx->stream, v, 0, S->nshared, nf, fstride, uin, alpha, beta, bmask, nullptr, 0);
     NSB_CUDA(cudaGetLastError());
     return NSB_OK;
   }
-  // multi-rank: local node sums -> pack -> exchange -> add -> scatter
+  NSB_REQUIRE(nf <= S->ns_fields, "dssum: %d fields in one call, interface buffers hold %d", nf, S->ns_fields);
+  cudaStream_t s2 = ctx->copy_stream;
   double *ns = S->node_sum_d;
-  gs_kernel<2><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, nullptr, 0, 0, nullptr, ns);
-  ctx->launches++;
+  NSB_CUDA(cudaEventRecord(S->ev_a, ctx->stream));
+  NSB_CUDA(cudaStreamWaitEvent(s2, S->ev_a, 0));
+  gs_launch<2>(S, s2, v, nloc, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, ns, nifc);
   for (auto &P : S->peers) {
-    pack_kernel<<<blocks_for(P.n), 256, 0, ctx->stream>>>(ns, P.idx_d, P.n, P.send_d);
+    pack_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.send_d, nifc);
     ctx->launches++;
   }
   NSB_CUDA(cudaGetLastError());
-  NSB_CHECK(sendrecv_d(ctx, S->peers));
+  NSB_CHECK(sendrecv_d(ctx, S->peers, nf, s2));
   for (auto &P : S->peers) {
-    unpack_add_kernel<<<blocks_for(P.n), 256, 0, ctx->stream>>>(ns, P.idx_d, P.n, P.recv_d);
+    unpack_add_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.recv_d, nifc);
     ctx->launches++;
   }
-  if (epi == 0)
-    gs_kernel<3><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, nullptr, 0, 0, nullptr, ns);
-  else
-    gs_kernel<4><<<nb, 256, 0, ctx->stream>>>(v, S->gs_off_d, S->gs_idx_d, S->nshared, uin, alpha, beta, bmask, ns);
-  ctx->launches++;
+  if (epi == 0) gs_launch<3>(S, s2, v, nloc, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, ns, nifc);
+  else gs_launch<4>(S, s2, v, nloc, S->nshared, nf, fstride, uin, alpha, beta, bmask, ns, nifc);
+  NSB_CUDA(cudaEventRecord(S->ev_b, s2));
+  // private nodes, concurrently on the main stream
+  if (epi == 0) gs_launch<0>(S, ctx->stream, v, 0, nloc, nf, fstride, nullptr, 0, 0, nullptr, nullptr, 0);
+  else gs_launch<1>(S, ctx->stream, v, 0, nloc, nf, fstride, uin, alpha, beta, bmask, nullptr, 0);
+  NSB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_b, 0));
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
 }
@@ -752,10 +780,15 @@ extern "C" int nsb_sem_create(nsb_context_t ctx, int dim, int N, int64_t nel, co
   }
   off[ngrp] = w0;
   S->nshared = ngrp;
+  S->n_local = ngrp;
   S->gs_nnz = w0;
+  S->gs_off_h = off;
+  S->gs_idx_h = idx;
+  NSB_CUDA(cudaEventCreateWithFlags(&S->ev_a, cudaEventDisableTiming));
+  NSB_CUDA(cudaEventCreateWithFlags(&S->ev_b, cudaEventDisableTiming));
   NSB_CUDA(cudaMalloc(&S->gs_off_d, sizeof(int64_t) * (ngrp + 1)));
   NSB_CUDA(cudaMalloc(&S->gs_idx_d, sizeof(int32_t) * (w0 > 0 ? w0 : 1)));
-  NSB_CUDA(cudaMalloc(&S->node_sum_d, sizeof(double) * (ngrp > 0 ? ngrp : 1)));
+
   NSB_CUDA(cudaMemcpyAsync(S->gs_off_d, off.data(), sizeof(int64_t) * (ngrp + 1), cudaMemcpyHostToDevice, s));
   NSB_CUDA(cudaMemcpyAsync(S->gs_idx_d, idx.data(), sizeof(int32_t) * w0, cudaMemcpyHostToDevice, s));
   NSB_CUDA(cudaMemcpyAsync(S->vmult_d, vm.data(), nb, cudaMemcpyHostToDevice, s));
@@ -780,7 +813,7 @@ static int finish_assembled(nsb_sem_t S) {
   cudaStream_t s = ctx->stream;
   const size_t nb = sizeof(double) * S->npts;
   NSB_CUDA(cudaMemcpyAsync(S->binv_d, S->bm1_d, nb, cudaMemcpyDeviceToDevice, s));
-  NSB_CHECK(launch_gs(S, S->binv_d, 0, nullptr, 0, 0, nullptr));
+  NSB_CHECK(launch_gs(S, S->binv_d, 1, 0, 0, nullptr, 0, 0, nullptr));
   recip_kernel<<<ctx->num_sms * 8, 256, 0, s>>>(S->binv_d, S->npts);
   mul3_kernel<<<ctx->num_sms * 8, 256, 0, s>>>(S->bmask_d, S->binv_d, S->mask_d, S->npts);
   ctx->launches += 2;
@@ -789,7 +822,7 @@ static int finish_assembled(nsb_sem_t S) {
     // vmult = 1/global multiplicity
     std::vector<double> ones(S->npts, 1.0);
     NSB_CUDA(cudaMemcpyAsync(S->vmult_d, ones.data(), nb, cudaMemcpyHostToDevice, s));
-    NSB_CHECK(launch_gs(S, S->vmult_d, 0, nullptr, 0, 0, nullptr));
+    NSB_CHECK(launch_gs(S, S->vmult_d, 1, 0, 0, nullptr, 0, 0, nullptr));
     recip_kernel<<<ctx->num_sms * 8, 256, 0, s>>>(S->vmult_d, S->npts);
     ctx->launches++;
     NSB_CUDA(cudaStreamSynchronize(s));
@@ -820,6 +853,8 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
     if (p) cudaFree(p);
   if (S->gs_off_d) cudaFree(S->gs_off_d);
   if (S->gs_idx_d) cudaFree(S->gs_idx_d);
+  if (S->ev_a) cudaEventDestroy(S->ev_a);
+  if (S->ev_b) cudaEventDestroy(S->ev_b);
   delete S;
   return NSB_OK;
 }
@@ -858,13 +893,13 @@ extern "C" int nsb_sem_axhelm(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t
   NSB_CHECK(field_ptr(S, bin, cin, field, &u, "nsb_sem_axhelm"));
   NSB_CHECK(field_ptr(S, bout, cout, field, &w, "nsb_sem_axhelm"));
   NSB_REQUIRE(u != w, "nsb_sem_axhelm: in-place application is not supported");
-  return launch_axhelm(S, u, w, h1, h2, nullptr, 0, 0, 0, nullptr);
+  return launch_axhelm(S, u, w, 1, 0, h1, h2, nullptr, 0, 0, 0, nullptr);
 }
 
 extern "C" int nsb_sem_dssum(nsb_sem_t S, nsb_basis_t B, int col, int field) {
   double *v;
   NSB_CHECK(field_ptr(S, B, col, field, &v, "nsb_sem_dssum"));
-  return launch_gs(S, v, 0, nullptr, 0, 0, nullptr);
+  return launch_gs(S, v, 1, 0, 0, nullptr, 0, 0, nullptr);
 }
 
 extern "C" int nsb_sem_col2(nsb_sem_t S, nsb_basis_t B, int col, int field, int which) {
@@ -990,12 +1025,23 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
   nsb_layout_t L = bin->lay;
   NSB_REQUIRE(op->nfields_apply <= L->nfields, "nsb_op_apply: operator covers %d fields, layout has %d",
               op->nfields_apply, L->nfields);
-  for (int f = 0; f < op->nfields_apply; ++f) {
+  // the applied fields are equally long, hence equally spaced inside a column: one batched
+  // launch per kernel (grid.y = field) and one interface exchange for all components
+  const int nfa = op->nfields_apply;
+  const int64_t fstride = nfa > 1 ? L->off[1] - L->off[0] : 0;
+  bool uniform = nfa <= S->ns_fields;
+  for (int f = 1; f < nfa; ++f) uniform = uniform && (L->off[f] - L->off[f - 1] == fstride);
+  const int step = uniform ? nfa : 1;
+  for (int f = 0; f < nfa; f += step) {
     double *u, *w;
+    for (int g = f; g < f + step; ++g) {
+      NSB_CHECK(field_ptr(S, bin, cin, g, &u, "nsb_op_apply"));
+      NSB_CHECK(field_ptr(S, bout, cout, g, &w, "nsb_op_apply"));
+    }
     NSB_CHECK(field_ptr(S, bin, cin, f, &u, "nsb_op_apply"));
     NSB_CHECK(field_ptr(S, bout, cout, f, &w, "nsb_op_apply"));
-    NSB_CHECK(launch_axhelm(S, u, w, op->h1, op->h2, op->c_d, 1, op->alpha, op->beta, S->bmask_d));
-    NSB_CHECK(launch_gs(S, w, 1, u, op->alpha, op->beta, S->bmask_d));
+    NSB_CHECK(launch_axhelm(S, u, w, step, fstride, op->h1, op->h2, op->c_d, 1, op->alpha, op->beta, S->bmask_d));
+    NSB_CHECK(launch_gs(S, w, step, fstride, 1, u, op->alpha, op->beta, S->bmask_d));
   }
   // fields outside the operator (pressure, scalars, %time) are carried through unchanged
   if (op->nfields_apply < L->nfields || true) {

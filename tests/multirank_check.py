@@ -1,0 +1,100 @@
+"""Multi-rank parity check, launched by torchrun (one process per GPU, NCCL):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multirank_check.py
+
+Every rank owns a z-slab of the box mesh (element partition like Nek's MPI ranks); inner products
+go through the NCCL all-reduce and dssum through the interface exchange.  Results are compared with
+the single-rank numpy oracle evaluated on the whole mesh.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests'))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import nekstab_next_b200 as nb
+    from helpers import BoxProblem
+    from oracle import krylov as okr, sem as osem
+    box = [nb.Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx = nb.Context(device=local, rank=rank, nranks=world, unique_id=box[0])
+
+    nel, N, nc, K = (3, 2, 2 * world), 5, 2, 12
+    P = BoxProblem(nel=nel, N=N, deform=0.04, nfields=nc, conv=True, time_in_dot=True, seed=21)  # whole mesh
+    c = P.octx()
+    per = nel[0] * nel[1]
+    e0, e1 = nb.mesh.partition_range(P.shape[0], rank, world, granule=per)
+    sl = slice(e0, e1)
+    x, y, z = (a[sl] for a in P.coords)
+    sem = nb.Sem(ctx, N, x, y, z, mask=P.mask[sl], glo_num=P.glo[sl])
+    sem.setup_exchange()
+    npts = sem.npts
+    errs = {}
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    errs['binvm1'] = rel(sem.get('binvm1'), P.binv[sl])
+    errs['vmult'] = rel(sem.get('vmult'), P.vmult[sl])
+    lay = nb.Layout(ctx, [npts] * nc, [True] * nc, time_in_dot=True)
+    lay.set_weight([P.bm1[sl]] * nc)
+    Q = nb.Basis(lay, K + 1)
+    conv = tuple(a[sl] for a in P.conv)
+    op = nb.sem_operator(sem, nc, P.alpha, P.beta, P.h1, P.h2, conv=conv)
+    # dssum / ax on a discontinuous field
+    u = P.rng.standard_normal(P.shape)
+    Q[0].upload([u[sl], u[sl]])
+    sem.dssum(Q[0], 0)
+    errs['dssum'] = rel(Q[0].download()[0][0], osem.dssum(u, P.glo)[sl].ravel())
+    Q[0].upload([u[sl], u[sl]])
+    sem.ax(Q[0], Q[1], 1, 1.0, 0.1)
+    errs['ax'] = rel(Q[1].download()[0][1], osem.ax(u, P.geo['g'], P.d, P.glo, P.mask, 1.0, 0.1, P.bm1)[sl].ravel())
+    # weighted dot with %time (counted once globally)
+    a, b = P.random_kvec(), P.random_kvec()
+    a.time, b.time = 1.5, -2.0
+    Q[0].upload([f[sl] for f in a.f], a.time)
+    Q[1].upload([f[sl] for f in b.f], b.time)
+    ref = okr.k_dot(c, a, b)
+    errs['dot'] = abs(Q[0].dot(Q[1]) - ref) / abs(ref)
+    # Arnoldi: H identical on every rank and equal to the oracle's
+    q0 = P.random_kvec()
+    okr.k_normalize(c, q0)
+    Qo = [okr.k_zero_like(q0) for _ in range(K + 1)]
+    okr.k_copy(Qo[0], q0)
+    Ho = np.zeros((K + 1, K))
+    okr.arnoldi_factorization(c, P.omatvec, Qo, Ho, 1, K, K)
+    Q[0].upload([f[sl] for f in q0.f], q0.time)
+    H = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(Q, H, 1, K, K, op)
+    errs['arnoldi_H'] = rel(H, Ho)
+    errs['arnoldi_Q'] = rel(Q[K].download()[0][0], Qo[K].f[0][sl].ravel())
+    G = Q.gram(K + 1)
+    errs['orth'] = float(np.max(np.abs(G - np.eye(K + 1))))
+    Hall = [None] * world
+    dist.all_gather_object(Hall, H)
+    errs['H_replicated'] = max(float(np.max(np.abs(h - Hall[0]))) for h in Hall)
+    tol = dict(binvm1=1e-12, vmult=0, dssum=1e-13, ax=1e-12, dot=1e-12, arnoldi_H=1e-10, arnoldi_Q=1e-9,
+               orth=1e-10, H_replicated=0)
+    bad = {k: v for k, v in errs.items() if not (v <= tol[k])}
+    print(f'[rank {rank}/{world}] ' + ' '.join(f'{k}={v:.2e}' for k, v in errs.items()), flush=True)
+    op.close()
+    ctx.close()
+    dist.destroy_process_group()
+    if bad:
+        print(f'[rank {rank}] FAILED: {bad}', flush=True)
+        sys.exit(1)
+
+
+if __name__ == '__main__':
+    main()
