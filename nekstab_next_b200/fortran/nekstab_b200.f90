@@ -1,0 +1,454 @@
+!> ISO_C_BINDING layer over include/nekstab_b200.h for the nekStab host code.
+!!
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (SURVEY.md
+!! section 0.5).  The file is deliberately declarative -- bind(C) interfaces plus thin type-bound
+!! wrappers -- so that the only logic that cannot be tested here is argument marshalling.
+!! INTEGRATION.md shows where each piece replaces reference code.
+!!
+!! Replaces / mirrors (paths relative to the nekStab repository root):
+!!   type nek_dvector          <- real_nek_vector (core/nek_vectors.f90:20-31),
+!!                                krylov_vector   (core/krylov_subspace.f90:12-17)
+!!   k_dot, k_norm, ...        <- core/krylov_subspace.f90:26-209
+!!   arnoldi_factorization     <- core/krylov_decomposition.f90:2
+!!   krylov_schur (driver part)<- core/eigensolvers.f90:120
+!!   ts_gmres                  <- core/newton_krylov.f90:170
+module nekstab_b200
+   use, intrinsic :: iso_c_binding
+   implicit none
+   private
+
+   integer(c_int), parameter, public :: NSB_ORTH_MGS2_REF = 0, NSB_ORTH_CGS2 = 1, NSB_ORTH_DGKS = 2
+   integer(c_int), parameter, public :: NSB_AXPBY_SKIP_TIME = 1
+
+   !> One per MPI rank: device context, state-vector layout, Krylov basis, work vectors.
+   type(c_ptr), save, public :: nsb_ctx = c_null_ptr, nsb_layout = c_null_ptr
+   type(c_ptr), save, public :: nsb_Q = c_null_ptr      !< Krylov basis, k_dim+1 columns
+   type(c_ptr), save, public :: nsb_work = c_null_ptr   !< pool of stand-alone vectors (f, wrk, sol, dq ...)
+
+   !> The device vector: a (basis, column) pair with the reference's type-bound procedures.
+   type, public :: nek_dvector
+      type(c_ptr) :: basis = c_null_ptr
+      integer(c_int) :: col = 0            !< 0-based column
+   contains
+      procedure, pass(self), public :: zero => dv_zero
+      procedure, pass(self), public :: dot => dv_dot
+      procedure, pass(self), public :: norm => dv_norm
+      procedure, pass(self), public :: scal => dv_scal
+      procedure, pass(self), public :: axpby => dv_axpby
+   end type nek_dvector
+
+   public :: nsb_check, nsb_startup, nsb_shutdown, nsb_upload, nsb_download
+   public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
+   public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d
+
+   interface
+      function nsb_last_error() bind(C, name='nsb_last_error') result(msg)
+         import :: c_ptr
+         type(c_ptr) :: msg
+      end function
+      function nsb_get_unique_id(id) bind(C, name='nsb_get_unique_id') result(ierr)
+         import :: c_int, c_char
+         character(kind=c_char) :: id(128)
+         integer(c_int) :: ierr
+      end function
+      function nsb_init(device, rank, nranks, id, ctx) bind(C, name='nsb_init') result(ierr)
+         import :: c_int, c_char, c_ptr
+         integer(c_int), value :: device, rank, nranks
+         character(kind=c_char) :: id(128)
+         type(c_ptr) :: ctx
+         integer(c_int) :: ierr
+      end function
+      function nsb_finalize(ctx) bind(C, name='nsb_finalize') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int) :: ierr
+      end function
+      function nsb_layout_create(ctx, nfields, field_len, field_in_dot, time_in_dot, layout) &
+         bind(C, name='nsb_layout_create') result(ierr)
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: nfields, time_in_dot
+         integer(c_int64_t) :: field_len(*)
+         integer(c_int) :: field_in_dot(*)
+         type(c_ptr) :: layout
+         integer(c_int) :: ierr
+      end function
+      function nsb_layout_set_weight(layout, w) bind(C, name='nsb_layout_set_weight') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: layout
+         type(c_ptr) :: w(*)            !< c_loc(bm1s) once per in-dot field
+         integer(c_int) :: ierr
+      end function
+      function nsb_basis_create(layout, ncols, basis) bind(C, name='nsb_basis_create') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: layout
+         integer(c_int), value :: ncols
+         type(c_ptr) :: basis
+         integer(c_int) :: ierr
+      end function
+      function nsb_basis_destroy(basis) bind(C, name='nsb_basis_destroy') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: basis
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_upload(b, col, fields, time) bind(C, name='nsb_vec_upload') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: col
+         type(c_ptr) :: fields(*)       !< c_loc(vx), c_loc(vy), ...
+         real(c_double), value :: time
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_download(b, col, fields, time) bind(C, name='nsb_vec_download') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: col
+         type(c_ptr) :: fields(*)
+         real(c_double) :: time
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_zero(b, col) bind(C, name='nsb_vec_zero') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: b
+         integer(c_int), value :: col
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_copy(bd, cd, bs, cs) bind(C, name='nsb_vec_copy') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: bd, bs
+         integer(c_int), value :: cd, cs
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_scal(b, col, alpha) bind(C, name='nsb_vec_scal') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: col
+         real(c_double), value :: alpha
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_axpby(bx, cx, alpha, by, cy, beta, flags) bind(C, name='nsb_vec_axpby') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: bx, by
+         integer(c_int), value :: cx, cy, flags
+         real(c_double), value :: alpha, beta
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_add2(bp, cp, bq, cq) bind(C, name='nsb_vec_add2') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: bp, bq
+         integer(c_int), value :: cp, cq
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_sub2(bp, cp, bq, cq) bind(C, name='nsb_vec_sub2') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: bp, bq
+         integer(c_int), value :: cp, cq
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_sub3(bp, cp, bq, cq, br, cr) bind(C, name='nsb_vec_sub3') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: bp, bq, br
+         integer(c_int), value :: cp, cq, cr
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_dot(ba, ca, bb, cb, alpha) bind(C, name='nsb_vec_dot') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ba, bb
+         integer(c_int), value :: ca, cb
+         real(c_double) :: alpha
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_normalize(b, col, alpha) bind(C, name='nsb_vec_normalize') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: col
+         real(c_double) :: alpha
+         integer(c_int) :: ierr
+      end function
+      function nsb_basis_gemv(b, k, y, bout, cout) bind(C, name='nsb_basis_gemv') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b, bout
+         integer(c_int), value :: k, cout
+         real(c_double) :: y(*)
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_create_host(layout, fn, user, op) bind(C, name='nsb_op_create_host') result(ierr)
+         import :: c_int, c_ptr, c_funptr
+         type(c_ptr), value :: layout, user
+         type(c_funptr), value :: fn
+         type(c_ptr) :: op
+         integer(c_int) :: ierr
+      end function
+      function nsb_arnoldi(Q, op, mstart, mend, mode, H, ldh) bind(C, name='nsb_arnoldi') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: Q, op
+         integer(c_int), value :: mstart, mend, mode, ldh
+         real(c_double) :: H(ldh, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_set_lapack(dgeev, dgees, dtrsen, dgels) bind(C, name='nsb_set_lapack') result(ierr)
+         import :: c_int, c_funptr
+         type(c_funptr), value :: dgeev, dgees, dtrsen, dgels
+         integer(c_int) :: ierr
+      end function
+      function nsb_schur_condensation(Q, mstart, H, ldh, ksize, schur_del, schur_tgt) &
+         bind(C, name='nsb_schur_condensation') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: Q
+         integer(c_int) :: mstart
+         integer(c_int), value :: ldh, ksize, schur_tgt
+         real(c_double) :: H(ldh, *)
+         real(c_double), value :: schur_del
+         integer(c_int) :: ierr
+      end function
+      function nsb_krylov_schur(Q, op, k_dim, schur_tgt, eigen_tol, schur_del, mode, max_restarts, H, ldh, &
+                                vals, vecs, residual, cnt, schur_cnt) bind(C, name='nsb_krylov_schur') result(ierr)
+         import :: c_int, c_ptr, c_double, c_double_complex
+         type(c_ptr), value :: Q, op
+         integer(c_int), value :: k_dim, schur_tgt, mode, max_restarts, ldh
+         real(c_double), value :: eigen_tol, schur_del
+         real(c_double) :: H(ldh, *), residual(*)
+         complex(c_double_complex) :: vals(*), vecs(k_dim, *)
+         integer(c_int) :: cnt, schur_cnt, ierr
+      end function
+      function nsb_ts_gmres(Q, op, brhs, crhs, bsol, csol, maxiter, ksize, tol, mode, calls, hist, nhist) &
+         bind(C, name='nsb_ts_gmres') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: Q, op, brhs, bsol
+         integer(c_int), value :: crhs, csol, maxiter, ksize, mode
+         real(c_double), value :: tol
+         integer(c_int) :: calls, nhist
+         real(c_double) :: hist(*)
+         integer(c_int) :: ierr
+      end function
+   end interface
+
+contains
+
+   !> The reference prints and calls nek_end on fatal conditions (core/nek_vectors.f90:108-111);
+   !! the C ABI returns a code instead, mapped back here.
+   subroutine nsb_check(ierr, where)
+      integer(c_int), intent(in) :: ierr
+      character(len=*), intent(in) :: where
+      character(kind=c_char), pointer :: msg(:)
+      integer :: n
+      if (ierr == 0) return
+      call c_f_pointer(nsb_last_error(), msg, [1024])
+      n = 1
+      do while (n < 1024 .and. msg(n) /= c_null_char)
+         n = n + 1
+      end do
+      write (6, *) 'nekstab_b200 error ', ierr, ' in ', where, ': ', msg(1:n - 1)
+      call nek_end
+   end subroutine nsb_check
+
+   !> Called once from nekStab_init (core/main.f90:77-136) after bm1s <- bm1 (:108).
+   !! nid/np_ are Nek's rank and size; the unique id travels through Nek's own bcast.
+   subroutine nsb_startup(nid, np_, local_device, nfields, field_len, field_in_dot, time_in_dot, bm1s, k_dim, nwork)
+      integer, intent(in) :: nid, np_, local_device, nfields, time_in_dot, k_dim, nwork
+      integer(c_int64_t), intent(in) :: field_len(nfields)
+      integer(c_int), intent(in) :: field_in_dot(nfields)
+      real(c_double), target, intent(in) :: bm1s(*)
+      character(kind=c_char) :: id(128)
+      type(c_ptr) :: w(nfields)
+      integer :: i, nd
+      external :: dgeev, dgees, dtrsen, dgels
+      if (nid == 0) call nsb_check(nsb_get_unique_id(id), 'nsb_get_unique_id')
+      call bcast(id, 128)                                   ! Nek5000 comm_mpi.f
+      call nsb_check(nsb_init(int(local_device, c_int), int(nid, c_int), int(np_, c_int), id, nsb_ctx), 'nsb_init')
+      call nsb_check(nsb_layout_create(nsb_ctx, int(nfields, c_int), field_len, field_in_dot, &
+                                       int(time_in_dot, c_int), nsb_layout), 'nsb_layout_create')
+      nd = 0
+      do i = 1, nfields                                     ! the same bm1s for vx, vy, vz, t (k_dot)
+         if (field_in_dot(i) /= 0) then
+            nd = nd + 1
+            w(nd) = c_loc(bm1s)
+         end if
+      end do
+      call nsb_check(nsb_layout_set_weight(nsb_layout, w), 'nsb_layout_set_weight')
+      ! k_dim + 1 Krylov vectors + one work column (ts_gmres needs ksize + 2)
+      call nsb_check(nsb_basis_create(nsb_layout, int(k_dim + 2, c_int), nsb_Q), 'nsb_basis_create Q')
+      call nsb_check(nsb_basis_create(nsb_layout, int(nwork, c_int), nsb_work), 'nsb_basis_create work')
+      ! the k x k dense step stays on the host through the LAPACK the case already links
+      ! (core/lapack_wrapper.f90:49,108,158,288)
+      call nsb_check(nsb_set_lapack(c_funloc(dgeev), c_funloc(dgees), c_funloc(dtrsen), c_funloc(dgels)), &
+                     'nsb_set_lapack')
+   end subroutine nsb_startup
+
+   subroutine nsb_shutdown()
+      integer(c_int) :: ierr
+      ierr = nsb_basis_destroy(nsb_Q)
+      ierr = nsb_basis_destroy(nsb_work)
+      ierr = nsb_finalize(nsb_ctx)
+   end subroutine nsb_shutdown
+
+   !> krylov_vector -> device column (fields in layout order) and back.
+   subroutine nsb_upload(v, vx, vy, vz, pr, t, time)
+      type(nek_dvector), intent(in) :: v
+      real(c_double), target, intent(in) :: vx(*), vy(*), vz(*), pr(*), t(*)
+      real(c_double), intent(in) :: time
+      type(c_ptr) :: f(5)
+      f = [c_loc(vx), c_loc(vy), c_loc(vz), c_loc(pr), c_loc(t)]
+      call nsb_check(nsb_vec_upload(v%basis, v%col, f, time), 'nsb_vec_upload')
+   end subroutine nsb_upload
+
+   subroutine nsb_download(v, vx, vy, vz, pr, t, time)
+      type(nek_dvector), intent(in) :: v
+      real(c_double), target, intent(inout) :: vx(*), vy(*), vz(*), pr(*), t(*)
+      real(c_double), intent(out) :: time
+      type(c_ptr) :: f(5)
+      f = [c_loc(vx), c_loc(vy), c_loc(vz), c_loc(pr), c_loc(t)]
+      call nsb_check(nsb_vec_download(v%basis, v%col, f, time), 'nsb_vec_download')
+   end subroutine nsb_download
+
+   ! ---- type-bound procedures (core/nek_vectors.f90:27-30) ------------------------------------
+   subroutine dv_zero(self)
+      class(nek_dvector), intent(inout) :: self
+      call nsb_check(nsb_vec_zero(self%basis, self%col), 'zero')
+   end subroutine dv_zero
+
+   real(c_double) function dv_dot(self, vec) result(alpha)
+      class(nek_dvector), intent(in) :: self
+      class(nek_dvector), intent(in) :: vec
+      call nsb_check(nsb_vec_dot(self%basis, self%col, vec%basis, vec%col, alpha), 'dot')
+   end function dv_dot
+
+   real(c_double) function dv_norm(self) result(alpha)
+      class(nek_dvector), intent(in) :: self
+      call nsb_check(nsb_vec_dot(self%basis, self%col, self%basis, self%col, alpha), 'norm')
+      alpha = sqrt(alpha)
+   end function dv_norm
+
+   subroutine dv_scal(self, alpha)
+      class(nek_dvector), intent(inout) :: self
+      real(c_double), intent(in) :: alpha
+      call nsb_check(nsb_vec_scal(self%basis, self%col, alpha), 'scal')
+   end subroutine dv_scal
+
+   !> self <- alpha*self + beta*vec; %time untouched, like real_axpby (core/nek_vectors.f90:127-139)
+   subroutine dv_axpby(self, alpha, vec, beta)
+      class(nek_dvector), intent(inout) :: self
+      class(nek_dvector), intent(in) :: vec
+      real(c_double), intent(in) :: alpha, beta
+      call nsb_check(nsb_vec_axpby(self%basis, self%col, alpha, vec%basis, vec%col, beta, NSB_AXPBY_SKIP_TIME), 'axpby')
+   end subroutine dv_axpby
+
+   ! ---- legacy free functions (core/krylov_subspace.f90:26-209), same argument order ----------
+   subroutine k_dot(alpha, p, q)
+      real(c_double), intent(out) :: alpha
+      type(nek_dvector), intent(in) :: p, q
+      call nsb_check(nsb_vec_dot(p%basis, p%col, q%basis, q%col, alpha), 'k_dot')
+   end subroutine k_dot
+
+   subroutine k_norm(alpha, p)
+      real(c_double), intent(out) :: alpha
+      type(nek_dvector), intent(in) :: p
+      call k_dot(alpha, p, p)
+      alpha = dsqrt(alpha)
+   end subroutine k_norm
+
+   subroutine k_normalize(p, alpha)
+      type(nek_dvector), intent(inout) :: p
+      real(c_double), intent(out) :: alpha
+      call nsb_check(nsb_vec_normalize(p%basis, p%col, alpha), 'k_normalize')
+   end subroutine k_normalize
+
+   subroutine k_cmult(p, c)
+      type(nek_dvector), intent(inout) :: p
+      real(c_double), intent(in) :: c
+      call nsb_check(nsb_vec_scal(p%basis, p%col, c), 'k_cmult')
+   end subroutine k_cmult
+
+   subroutine k_add2(p, q)
+      type(nek_dvector), intent(inout) :: p
+      type(nek_dvector), intent(in) :: q
+      call nsb_check(nsb_vec_add2(p%basis, p%col, q%basis, q%col), 'k_add2')
+   end subroutine k_add2
+
+   subroutine k_sub2(p, q)
+      type(nek_dvector), intent(inout) :: p
+      type(nek_dvector), intent(in) :: q
+      call nsb_check(nsb_vec_sub2(p%basis, p%col, q%basis, q%col), 'k_sub2')
+   end subroutine k_sub2
+
+   subroutine k_sub3(p, q, r)
+      type(nek_dvector), intent(inout) :: p
+      type(nek_dvector), intent(in) :: q, r
+      call nsb_check(nsb_vec_sub3(p%basis, p%col, q%basis, q%col, r%basis, r%col), 'k_sub3')
+   end subroutine k_sub3
+
+   subroutine k_zero(p)
+      type(nek_dvector), intent(inout) :: p
+      call nsb_check(nsb_vec_zero(p%basis, p%col), 'k_zero')
+   end subroutine k_zero
+
+   subroutine k_copy(p, q)        ! destination first, like the reference
+      type(nek_dvector), intent(inout) :: p
+      type(nek_dvector), intent(in) :: q
+      call nsb_check(nsb_vec_copy(p%basis, p%col, q%basis, q%col), 'k_copy')
+   end subroutine k_copy
+
+   !> dq = Q(1:k) * yvec (core/krylov_subspace.f90:163-209); Q is the device basis.
+   subroutine k_matmul(dq, yvec, k)
+      type(nek_dvector), intent(inout) :: dq
+      integer, intent(in) :: k
+      real(c_double), intent(in) :: yvec(k)
+      call nsb_check(nsb_basis_gemv(nsb_Q, int(k, c_int), yvec, dq%basis, dq%col), 'k_matmul')
+   end subroutine k_matmul
+
+   ! ---- solver entry points -------------------------------------------------------------------
+   !> arnoldi_factorization(Q, H, mstart, mend, ksize) (core/krylov_decomposition.f90:2-99):
+   !! 1-based mstart/mend as in the reference; `op` wraps the host matvec (nsb_op_create_host).
+   subroutine arnoldi_factorization_d(op, H, mstart, mend, ksize)
+      type(c_ptr), intent(in) :: op
+      integer, intent(in) :: mstart, mend, ksize
+      real(c_double), intent(inout) :: H(ksize + 1, ksize)
+      call nsb_check(nsb_arnoldi(nsb_Q, op, int(mstart - 1, c_int), int(mend - 1, c_int), NSB_ORTH_CGS2, &
+                                 H, int(ksize + 1, c_int)), 'arnoldi_factorization')
+   end subroutine arnoldi_factorization_d
+
+   !> schur_condensation(mstart, H, Q, ksize) (core/eigensolvers.f90:363-468)
+   subroutine schur_condensation_d(mstart, H, ksize, schur_del, schur_tgt)
+      integer, intent(inout) :: mstart
+      integer, intent(in) :: ksize, schur_tgt
+      real(c_double), intent(inout) :: H(ksize + 1, ksize)
+      real(c_double), intent(in) :: schur_del
+      integer(c_int) :: m
+      m = int(mstart - 1, c_int)
+      call nsb_check(nsb_schur_condensation(nsb_Q, m, H, int(ksize + 1, c_int), int(ksize, c_int), schur_del, &
+                                            int(schur_tgt, c_int)), 'schur_condensation')
+      mstart = m + 1
+   end subroutine schur_condensation_d
+
+   !> The restart loop of krylov_schur (core/eigensolvers.f90:295-333); Q(1) must hold the seed.
+   subroutine krylov_schur_d(op, k_dim, schur_tgt, eigen_tol, schur_del, H, vals, vecs, residual, cnt, schur_cnt)
+      type(c_ptr), intent(in) :: op
+      integer, intent(in) :: k_dim, schur_tgt
+      real(c_double), intent(in) :: eigen_tol, schur_del
+      real(c_double), intent(inout) :: H(k_dim + 1, k_dim), residual(k_dim)
+      complex(c_double_complex), intent(out) :: vals(k_dim), vecs(k_dim, k_dim)
+      integer, intent(out) :: cnt, schur_cnt
+      integer(c_int) :: c1, c2
+      call nsb_check(nsb_krylov_schur(nsb_Q, op, int(k_dim, c_int), int(schur_tgt, c_int), eigen_tol, schur_del, &
+                                      NSB_ORTH_CGS2, 200_c_int, H, int(k_dim + 1, c_int), vals, vecs, residual, &
+                                      c1, c2), 'krylov_schur')
+      cnt = c1
+      schur_cnt = c2
+   end subroutine krylov_schur_d
+
+   !> ts_gmres(rhs, sol, maxiter, ksize, calls) (core/newton_krylov.f90:170-299)
+   subroutine ts_gmres_d(op, rhs, sol, maxiter, ksize, tol, calls)
+      type(c_ptr), intent(in) :: op
+      type(nek_dvector), intent(in) :: rhs
+      type(nek_dvector), intent(inout) :: sol
+      integer, intent(in) :: maxiter, ksize
+      real(c_double), intent(in) :: tol
+      integer, intent(out) :: calls
+      real(c_double) :: hist(maxiter)
+      integer(c_int) :: c, nh
+      call nsb_check(nsb_ts_gmres(nsb_Q, op, rhs%basis, rhs%col, sol%basis, sol%col, int(maxiter, c_int), &
+                                  int(ksize, c_int), tol, NSB_ORTH_CGS2, c, hist, nh), 'ts_gmres')
+      calls = c
+   end subroutine ts_gmres_d
+
+end module nekstab_b200
