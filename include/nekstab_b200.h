@@ -191,6 +191,21 @@ int64_t nsb_sem_npts(nsb_sem_t sem);
 /* Multi-rank: neighbours are found from glo_num; call once after every rank created its sem. */
 int nsb_sem_setup_exchange(nsb_sem_t sem);
 
+/* Host-only planning steps of the gather-scatter (no CUDA, no NCCL): the same code the device
+ * path runs inside nsb_sem_create / nsb_sem_setup_exchange, exposed so the multi-rank logic can be
+ * tested on CPU-only machines.
+ *   gs_plan: unique nodes owning >= 1 element-boundary point as CSR lists (call with off/idx/gid
+ *            NULL to get nnodes/nnz first);
+ *   exchange_plan: given every rank's sorted node ids, which of my nodes are interface nodes,
+ *            their position after the private-first reorder, and per peer the interface-relative
+ *            node indices in ascending global id (the order of the packed exchange buffers). */
+int nsb_host_gs_plan(int dim, int N, int64_t nel, const int64_t *glo_num, int64_t *nnodes,
+                     int64_t *nnz, int64_t *off, int32_t *idx, int64_t *gid);
+int nsb_host_exchange_plan(int rank, int nranks, int64_t nnodes, const int64_t *gid,
+                           const int64_t *counts, const int64_t *all_sorted, int64_t mx,
+                           int64_t *newpos, int64_t *n_local, int64_t *peer_count,
+                           int32_t *peer_nodes);
+
 /* Kernels on field `field` of column `col` (element-local array of nel*lx1^dim points):
  *   axhelm : w = h1 * D^T G D u + h2 * bm1 * u                (hmholtz.f axhelm, no dssum)
  *   dssum  : u <- QQ^T u  incl. the inter-rank exchange        (dssum / gs_op add)

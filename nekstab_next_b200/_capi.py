@@ -67,6 +67,10 @@ PROTOTYPES = {
     'nsb_sem_get': (C.c_int, [H, C.c_int, c_double_p]),
     'nsb_sem_npts': (C.c_int64, [H]),
     'nsb_sem_setup_exchange': (C.c_int, [H]),
+    'nsb_host_gs_plan': (C.c_int, [C.c_int, C.c_int, C.c_int64, c_i64_p, c_i64_p, c_i64_p, c_i64_p,
+                                   C.POINTER(C.c_int32), c_i64_p]),
+    'nsb_host_exchange_plan': (C.c_int, [C.c_int, C.c_int, C.c_int64, c_i64_p, c_i64_p, c_i64_p, C.c_int64,
+                                         c_i64_p, c_i64_p, c_i64_p, C.POINTER(C.c_int32)]),
     'nsb_sem_axhelm': (C.c_int, [H, H, C.c_int, H, C.c_int, C.c_int, C.c_double, C.c_double]),
     'nsb_sem_dssum': (C.c_int, [H, H, C.c_int, C.c_int]),
     'nsb_sem_col2': (C.c_int, [H, H, C.c_int, C.c_int, C.c_int]),

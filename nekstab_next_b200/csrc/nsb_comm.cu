@@ -117,6 +117,42 @@ int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int
   return NSB_OK;
 }
 
+// Pure host part of the exchange set-up: intersect this rank's node ids with every other rank's
+// sorted id list, move interface nodes behind the private ones, and list each peer's shared nodes
+// in ascending global id (both sides of a pair then agree on the order of the packed buffer).
+int exchange_plan(int rank, int nranks, const std::vector<int64_t> &gid, const std::vector<int64_t> &cnt,
+                  const int64_t *all_sorted, int64_t mx, ExchangePlan &plan) {
+  const int64_t nn = (int64_t)gid.size();
+  std::vector<std::pair<int64_t, int32_t>> my(nn);
+  for (int64_t n = 0; n < nn; ++n) my[n] = {gid[n], (int32_t)n};
+  std::sort(my.begin(), my.end());
+  std::vector<std::vector<int32_t>> shared_with(nranks);
+  std::vector<char> is_ifc(nn, 0);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) continue;
+    const int64_t *other = all_sorted + (size_t)r * mx;
+    int64_t a = 0, b = 0;
+    while (a < nn && b < cnt[r]) {
+      if (my[a].first < other[b]) ++a;
+      else if (my[a].first > other[b]) ++b;
+      else { shared_with[r].push_back(my[a].second); is_ifc[my[a].second] = 1; ++a; ++b; }
+    }
+  }
+  plan.newpos.assign(nn, 0);
+  int64_t nloc = 0;
+  for (int64_t n = 0; n < nn; ++n) if (!is_ifc[n]) plan.newpos[n] = nloc++;
+  int64_t w = nloc;
+  for (int64_t n = 0; n < nn; ++n) if (is_ifc[n]) plan.newpos[n] = w++;
+  plan.n_local = nloc;
+  plan.peer_nodes.assign(nranks, {});
+  for (int r = 0; r < nranks; ++r) {
+    plan.peer_nodes[r].resize(shared_with[r].size());
+    for (size_t t = 0; t < shared_with[r].size(); ++t)
+      plan.peer_nodes[r][t] = (int32_t)(plan.newpos[shared_with[r][t]] - nloc);
+  }
+  return NSB_OK;
+}
+
 // Discover which gather-scatter nodes are shared with which rank: all-gather the (sorted) global
 // ids of every rank's nodes and intersect.  Both sides order a pair's nodes by global id, so the
 // packed buffers line up without further negotiation.
@@ -137,12 +173,10 @@ int exchange_setup(nsb_sem_t S) {
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(cnt_d);
   const int64_t mx = std::max<int64_t>(1, *std::max_element(cnt.begin(), cnt.end()));
-  // 2. sorted ids (with their gs-node index)
-  std::vector<std::pair<int64_t, int32_t>> my(S->nshared);
-  for (int64_t n = 0; n < S->nshared; ++n) my[n] = {S->node_gid[n], (int32_t)n};
-  std::sort(my.begin(), my.end());
-  std::vector<int64_t> send(mx, -1);
-  for (int64_t n = 0; n < S->nshared; ++n) send[n] = my[n].first;
+  // 2. all-gather every rank's sorted ids
+  std::vector<int64_t> send(S->node_gid.begin(), S->node_gid.end());
+  std::sort(send.begin(), send.end());
+  send.resize(mx, -1);
   int64_t *send_d = nullptr, *all_d = nullptr;
   NSB_CUDA(cudaMalloc(&send_d, sizeof(int64_t) * mx));
   NSB_CUDA(cudaMalloc(&all_d, sizeof(int64_t) * mx * P));
@@ -153,31 +187,18 @@ int exchange_setup(nsb_sem_t S) {
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(send_d);
   cudaFree(all_d);
-  // 3. intersect: which of my nodes does each other rank also hold?
+  // 3. host plan: intersect, private nodes first / interface nodes last
   for (auto &Pr : S->peers) {
     cudaFree(Pr.idx_d);
     cudaFree(Pr.send_d);
     cudaFree(Pr.recv_d);
   }
   S->peers.clear();
-  std::vector<std::vector<int32_t>> shared_with(P);
-  std::vector<char> is_ifc(S->nshared, 0);
-  for (int r = 0; r < P; ++r) {
-    if (r == ctx->rank) continue;
-    const int64_t *other = all.data() + (size_t)r * mx;
-    int64_t a = 0, b = 0;
-    while (a < S->nshared && b < cnt[r]) {
-      if (my[a].first < other[b]) ++a;
-      else if (my[a].first > other[b]) ++b;
-      else { shared_with[r].push_back(my[a].second); is_ifc[my[a].second] = 1; ++a; ++b; }
-    }
-  }
-  // 4. reorder the gather-scatter lists: private nodes first, interface nodes last
-  std::vector<int64_t> newpos(S->nshared);
-  int64_t nloc = 0;
-  for (int64_t n = 0; n < S->nshared; ++n) if (!is_ifc[n]) newpos[n] = nloc++;
-  int64_t w = nloc;
-  for (int64_t n = 0; n < S->nshared; ++n) if (is_ifc[n]) newpos[n] = w++;
+  ExchangePlan plan;
+  NSB_CHECK(exchange_plan(ctx->rank, P, S->node_gid, cnt, all.data(), mx, plan));
+  const std::vector<int64_t> &newpos = plan.newpos;
+  const int64_t nloc = plan.n_local;
+  // 4. reorder the gather-scatter lists accordingly
   std::vector<int64_t> off2(S->nshared + 1), gid2(S->nshared), inv(S->nshared);
   for (int64_t n = 0; n < S->nshared; ++n) inv[newpos[n]] = n;
   std::vector<int32_t> idx2(S->gs_idx_h.size());
@@ -200,10 +221,8 @@ int exchange_setup(nsb_sem_t S) {
   S->node_sum_d = nullptr;
   NSB_CUDA(cudaMalloc(&S->node_sum_d, sizeof(double) * S->ns_fields * (nifc > 0 ? nifc : 1)));
   for (int r = 0; r < P; ++r) {
-    if (shared_with[r].empty()) continue;
-    // both sides list a pair's nodes in ascending global id (shared_with was built that way)
-    std::vector<int32_t> nodes(shared_with[r].size());
-    for (size_t t = 0; t < nodes.size(); ++t) nodes[t] = (int32_t)(newpos[shared_with[r][t]] - nloc);
+    const std::vector<int32_t> &nodes = plan.peer_nodes[r];
+    if (nodes.empty()) continue;
     nsb_sem_s::Peer Pr;
     Pr.rank = r;
     Pr.n = (int64_t)nodes.size();
@@ -217,6 +236,31 @@ int exchange_setup(nsb_sem_t S) {
 }
 
 }  // namespace nsb
+
+// Host-only (no CUDA / NCCL): the exchange plan for CPU tests of the multi-rank logic.
+//   gid[nnodes]            this rank's node ids in gather-scatter order
+//   counts[nranks]         nodes per rank;  all_sorted[nranks][mx] every rank's ids, ascending
+//   newpos[nnodes]         out: position of each node after the private/interface reorder
+//   peer_count[nranks]     out: nodes shared with each rank
+//   peer_nodes[nranks][mx] out: interface-relative node indices per rank, ascending global id
+extern "C" int nsb_host_exchange_plan(int rank, int nranks, int64_t nnodes, const int64_t *gid,
+                                      const int64_t *counts, const int64_t *all_sorted, int64_t mx,
+                                      int64_t *newpos, int64_t *n_local, int64_t *peer_count,
+                                      int32_t *peer_nodes) {
+  NSB_REQUIRE(gid && counts && all_sorted && newpos && n_local && peer_count && peer_nodes && nranks >= 1 &&
+                  rank >= 0 && rank < nranks && nnodes >= 0 && mx >= 1,
+              "nsb_host_exchange_plan: bad argument");
+  std::vector<int64_t> g(gid, gid + nnodes), c(counts, counts + nranks);
+  nsb::ExchangePlan plan;
+  NSB_CHECK(nsb::exchange_plan(rank, nranks, g, c, all_sorted, mx, plan));
+  memcpy(newpos, plan.newpos.data(), sizeof(int64_t) * nnodes);
+  *n_local = plan.n_local;
+  for (int r = 0; r < nranks; ++r) {
+    peer_count[r] = (int64_t)plan.peer_nodes[r].size();
+    memcpy(peer_nodes + (size_t)r * mx, plan.peer_nodes[r].data(), sizeof(int32_t) * plan.peer_nodes[r].size());
+  }
+  return NSB_OK;
+}
 
 extern "C" int nsb_get_unique_id(void *id_out) {
   NSB_REQUIRE(id_out, "nsb_get_unique_id: NULL");

@@ -158,6 +158,16 @@ int comm_destroy(nsb_context_t ctx);
 int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n);  // on ctx->stream, in place
 int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int nf, cudaStream_t st);
 int exchange_setup(nsb_sem_t sem);
+// host-only plans (also reachable through nsb_host_gs_plan / nsb_host_exchange_plan for CPU tests)
+int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
+            std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult);
+struct ExchangePlan {
+  std::vector<int64_t> newpos;                   // node -> position after the private/interface reorder
+  int64_t n_local = 0;                           // private nodes
+  std::vector<std::vector<int32_t>> peer_nodes;  // per rank: interface-relative node indices, ascending gid
+};
+int exchange_plan(int rank, int nranks, const std::vector<int64_t> &gid, const std::vector<int64_t> &cnt,
+                  const int64_t *all_sorted, int64_t mx, ExchangePlan &plan);
 // implemented in nsb_orth.cu
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d);
 }  // namespace nsb

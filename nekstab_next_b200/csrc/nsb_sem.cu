@@ -667,6 +667,79 @@ int field_ptr(nsb_sem_t S, nsb_basis_t B, int col, int field, double **out, cons
 
 }  // namespace
 
+namespace nsb {
+// Host plan of the gather-scatter: unique nodes owning at least one element-boundary point, CSR,
+// ordered by first local index so neighbouring threads touch neighbouring memory.
+int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
+            std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult) {
+  int64_t nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  const int64_t npts = nel * nloc;
+  std::vector<int32_t> bpts;
+  bpts.reserve((size_t)(npts * 0.6));
+  for (int64_t p = 0; p < npts; ++p) {
+    const int loc = (int)(p % nloc);
+    const int i = loc % lx, j = (loc / lx) % lx, k = dim == 3 ? loc / (lx * lx) : 1;
+    const bool bnd = i == 0 || i == lx - 1 || j == 0 || j == lx - 1 ||
+                     (dim == 3 && (k == 0 || k == lx - 1));
+    if (bnd) bpts.push_back((int32_t)p);
+    if (glo_num[p] < 0) {
+      set_error("gather-scatter plan: negative global id at point %lld", (long long)p);
+      return NSB_EINVAL;
+    }
+  }
+  std::stable_sort(bpts.begin(), bpts.end(),
+                   [&](int32_t a, int32_t b) { return glo_num[a] < glo_num[b]; });
+  std::vector<int64_t> grp_start;
+  for (size_t q = 0; q < bpts.size(); ++q)
+    if (q == 0 || glo_num[bpts[q]] != glo_num[bpts[q - 1]]) grp_start.push_back((int64_t)q);
+  const int64_t ngrp = (int64_t)grp_start.size();
+  grp_start.push_back((int64_t)bpts.size());
+  std::vector<int64_t> order(ngrp);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(),
+            [&](int64_t a, int64_t b) { return bpts[grp_start[a]] < bpts[grp_start[b]]; });
+  off.assign(ngrp + 1, 0);
+  idx.resize(bpts.size());
+  gid.resize(ngrp);
+  if (vmult) vmult->assign(npts, 1.0);
+  int64_t w0 = 0;
+  for (int64_t n = 0; n < ngrp; ++n) {
+    const int64_t gI = order[n];
+    off[n] = w0;
+    const int64_t cnt = grp_start[gI + 1] - grp_start[gI];
+    for (int64_t q = grp_start[gI]; q < grp_start[gI + 1]; ++q) {
+      idx[w0++] = bpts[q];
+      if (vmult) (*vmult)[bpts[q]] = 1.0 / (double)cnt;
+      if (mask && mask[bpts[q]] != mask[bpts[grp_start[gI]]]) {
+        set_error("nsb_sem_create: mask differs between copies of global node %lld",
+                  (long long)glo_num[bpts[q]]);
+        return NSB_EINVAL;
+      }
+    }
+    gid[n] = glo_num[bpts[grp_start[gI]]];
+  }
+  off[ngrp] = w0;
+  return NSB_OK;
+}
+}  // namespace nsb
+
+// Host-only (no CUDA): sizes first (off/idx/gid NULL), then the lists.
+extern "C" int nsb_host_gs_plan(int dim, int N, int64_t nel, const int64_t *glo_num, int64_t *nnodes,
+                                int64_t *nnz, int64_t *off, int32_t *idx, int64_t *gid) {
+  NSB_REQUIRE(glo_num && nnodes && nnz && (dim == 2 || dim == 3) && N >= 1 && nel >= 1,
+              "nsb_host_gs_plan: bad argument");
+  std::vector<int64_t> o, g;
+  std::vector<int32_t> ix;
+  NSB_CHECK(nsb::gs_plan(dim, N + 1, nel, glo_num, nullptr, o, ix, g, nullptr));
+  *nnodes = (int64_t)g.size();
+  *nnz = (int64_t)ix.size();
+  if (off) memcpy(off, o.data(), sizeof(int64_t) * o.size());
+  if (idx) memcpy(idx, ix.data(), sizeof(int32_t) * ix.size());
+  if (gid) memcpy(gid, g.data(), sizeof(int64_t) * g.size());
+  return NSB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // mesh object
 // ------------------------------------------------------------------------------------------------
@@ -731,54 +804,14 @@ extern "C" int nsb_sem_create(nsb_context_t ctx, int dim, int N, int64_t nel, co
   ctx->launches++;
   NSB_CUDA(cudaGetLastError());
 
-  // gather-scatter lists: unique nodes owning at least one element-boundary point, CSR,
-  // ordered by first local index so neighbouring threads touch neighbouring memory.
+  // gather-scatter lists (host plan shared with the CPU-testable entry point nsb_host_gs_plan)
   S->glo_h.assign(glo_num, glo_num + npts);
-  std::vector<int32_t> bpts;
-  bpts.reserve((size_t)(npts * 0.6));
-  for (int64_t p = 0; p < npts; ++p) {
-    const int loc = (int)(p % nloc);
-    const int i = loc % lx, j = (loc / lx) % lx, k = dim == 3 ? loc / (lx * lx) : 1;
-    const bool bnd = i == 0 || i == lx - 1 || j == 0 || j == lx - 1 ||
-                     (dim == 3 && (k == 0 || k == lx - 1));
-    if (bnd) bpts.push_back((int32_t)p);
-    if (glo_num[p] < 0) {
-      set_error("nsb_sem_create: negative global id at point %lld", (long long)p);
-      return NSB_EINVAL;
-    }
-  }
-  std::stable_sort(bpts.begin(), bpts.end(),
-                   [&](int32_t a, int32_t b) { return glo_num[a] < glo_num[b]; });
-  std::vector<int64_t> grp_start;
-  for (size_t q = 0; q < bpts.size(); ++q)
-    if (q == 0 || glo_num[bpts[q]] != glo_num[bpts[q - 1]]) grp_start.push_back((int64_t)q);
-  const int64_t ngrp = (int64_t)grp_start.size();
-  grp_start.push_back((int64_t)bpts.size());
-  std::vector<int64_t> order(ngrp);
-  std::iota(order.begin(), order.end(), 0);
-  std::sort(order.begin(), order.end(),
-            [&](int64_t a, int64_t b) { return bpts[grp_start[a]] < bpts[grp_start[b]]; });
-  std::vector<int64_t> off(ngrp + 1, 0);
-  std::vector<int32_t> idx(bpts.size());
-  S->node_gid.resize(ngrp);
-  std::vector<double> vm(npts, 1.0);
-  int64_t w0 = 0;
-  for (int64_t n = 0; n < ngrp; ++n) {
-    const int64_t gI = order[n];
-    off[n] = w0;
-    const int64_t cnt = grp_start[gI + 1] - grp_start[gI];
-    for (int64_t q = grp_start[gI]; q < grp_start[gI + 1]; ++q) {
-      idx[w0++] = bpts[q];
-      vm[bpts[q]] = 1.0 / (double)cnt;
-      if (mask && mask[bpts[q]] != mask[bpts[grp_start[gI]]]) {
-        set_error("nsb_sem_create: mask differs between copies of global node %lld",
-                  (long long)glo_num[bpts[q]]);
-        return NSB_EINVAL;
-      }
-    }
-    S->node_gid[n] = glo_num[bpts[grp_start[gI]]];
-  }
-  off[ngrp] = w0;
+  std::vector<int64_t> off;
+  std::vector<int32_t> idx;
+  std::vector<double> vm;
+  NSB_CHECK(nsb::gs_plan(dim, lx, nel, glo_num, mask, off, idx, S->node_gid, &vm));
+  const int64_t ngrp = (int64_t)S->node_gid.size();
+  const int64_t w0 = (int64_t)idx.size();
   S->nshared = ngrp;
   S->n_local = ngrp;
   S->gs_nnz = w0;
