@@ -396,6 +396,188 @@ axhelm3d_warp8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
   }
 }
 
+// ---- axhelm, 3-D, N = 7: TMA ring, geometric factors shared by the velocity components ----------
+// ncu on the warp-per-element kernel: 51 % DRAM, 80 % of cycles without an eligible warp, stalled
+// on the loads of G1..G6 that every plane issues into registers.  Here a producer warp streams
+// whole elements (u of NF fields, G1..G6, bm1, bmask: 4 KB bulk copies) into a ring of NSTAGE
+// shared-memory stages on mbarriers, so NSTAGE-1 elements of loads are always in flight without
+// occupying registers; the NF consumer warps of a stage each take one velocity component of that
+// element and all read the SAME staged geometric factors: G, bm1 and bmask cross HBM once per
+// element instead of once per component (8 (8 + 2 NF) bytes per point for NF fields).
+template <int NF, bool CONV, int EPI, int NSTAGE>
+__global__ void __launch_bounds__((NF * NSTAGE + 1) * 32, 1)
+axhelm3d_ring8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
+                      const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
+                      const double *__restrict__ cv, double alpha, double beta,
+                      const double *__restrict__ bmask, int64_t fstride) {
+  constexpr int LX = 8, N2 = 64, N3 = 512, PS = 10, NCW = NF * NSTAGE;
+  constexpr int NARR = 6 + 2 + (CONV ? 3 : 0) + NF;       // arrays per stage: G1..G6, bm1, bmask, [C], u
+  constexpr int STAGE = NARR * N3;                        // doubles per stage
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stage0 = reinterpret_cast<double *>(smem_raw);
+  double *planes = stage0 + (size_t)NSTAGE * STAGE;       // [NCW][3][LX*PS]
+  double *sD = planes + NCW * 3 * LX * PS;                // [64] D_ab, then [64] D_ba
+  double *sDt = sD + 64;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sDt + 64);   // [NSTAGE]
+  uint64_t *empty = full + NSTAGE;                           // [NSTAGE]
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  if (tid < N2) {
+    const int a = tid / LX, b = tid % LX;
+    sD[a * LX + b] = c_D8[a * LX + b];
+    sDt[b * LX + a] = c_D8[a * LX + b];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NF);
+    }
+  }
+  __syncthreads();
+  const int64_t nit = (nel - blockIdx.x + gridDim.x - 1) / gridDim.x;   // elements of this CTA
+
+  if (wp == NCW) {
+    // ===== producer warp: one lane per array =====
+    for (int64_t it = 0; it < nit; ++it) {
+      const int s = (int)(it % NSTAGE);
+      const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+      mbar_wait(empty + s, ph ^ 1u);                       // fresh barrier: passes immediately
+      const int64_t e = blockIdx.x + it * gridDim.x;
+      double *dst = stage0 + (size_t)s * STAGE;
+      if (lane == 0) mbar_expect_tx(full + s, (uint32_t)(STAGE * sizeof(double)));
+      __syncwarp();
+      if (lane < NARR) {
+        const double *src;
+        if (lane < 6) src = g + (int64_t)lane * npts + e * N3;
+        else if (lane == 6) src = bm1 + e * N3;
+        else if (lane == 7) src = bmask + e * N3;
+        else if (CONV && lane < 11) src = cv + (int64_t)(lane - 8) * npts + e * N3;
+        else src = u + (int64_t)(lane - (CONV ? 11 : 8)) * fstride + e * N3;
+        tma_bulk_g2s(dst + lane * N3, src, N3 * sizeof(double), full + s);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps: stage = wp / NF, velocity component = wp % NF =====
+  const int s = wp / NF, f = wp % NF;
+  const int i = lane & 7, jp = lane >> 3, j0 = jp, j1 = jp + 4;
+  const int q0 = j0 * LX + i, q1 = j1 * LX + i;             // in-plane offsets of the two points
+  double *su = planes + (size_t)wp * 3 * LX * PS, *swr = su + LX * PS, *sws = swr + LX * PS;
+  const double *sG = stage0 + (size_t)s * STAGE;
+  const double *sB = sG + 6 * N3, *sM = sG + 7 * N3, *sC = sG + 8 * N3;
+  const double *sU = sG + (size_t)(8 + (CONV ? 3 : 0) + f) * N3;
+  double *wout = w + (int64_t)f * fstride;
+  const bool b0 = (i == 0 || i == LX - 1 || j0 == 0), b1 = (i == 0 || i == LX - 1 || j1 == LX - 1);
+  for (int64_t it = s; it < nit; it += NSTAGE) {
+    const int64_t e = blockIdx.x + it * gridDim.x;
+    mbar_wait(full + s, (uint32_t)((it / NSTAGE) & 1));
+    double uk0[LX], uk1[LX], wk0[LX], wk1[LX];
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      uk0[k] = sU[k * N2 + q0];
+      uk1[k] = sU[k * N2 + q1];
+      wk0[k] = 0.0;
+      wk1[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      su[j0 * PS + i] = uk0[k];
+      su[j1 * PS + i] = uk1[k];
+      __syncwarp();
+      double ur0 = 0, ur1 = 0, us0 = 0, us1 = 0, ut0 = 0, ut1 = 0;
+#pragma unroll
+      for (int l = 0; l < LX; ++l) {
+        const double di = sDt[l * LX + i];
+        ur0 = fma(di, su[j0 * PS + l], ur0);
+        ur1 = fma(di, su[j1 * PS + l], ur1);
+        const double b = su[l * PS + i];
+        us0 = fma(sDt[l * LX + j0], b, us0);
+        us1 = fma(sDt[l * LX + j1], b, us1);
+        const double dk = c_D8[k * LX + l];
+        ut0 = fma(dk, uk0[l], ut0);
+        ut1 = fma(dk, uk1[l], ut1);
+      }
+      const int p0 = k * N2 + q0, p1 = k * N2 + q1;
+      double wt0, wt1;
+      {
+        const double g1 = sG[p0], g2 = sG[N3 + p0], g3 = sG[2 * N3 + p0], g4 = sG[3 * N3 + p0],
+                     g5 = sG[4 * N3 + p0], g6 = sG[5 * N3 + p0];
+        swr[j0 * PS + i] = h1 * (g1 * ur0 + g4 * us0 + g5 * ut0);
+        sws[j0 * PS + i] = h1 * (g2 * us0 + g4 * ur0 + g6 * ut0);
+        wt0 = h1 * (g3 * ut0 + g5 * ur0 + g6 * us0);
+      }
+      {
+        const double g1 = sG[p1], g2 = sG[N3 + p1], g3 = sG[2 * N3 + p1], g4 = sG[3 * N3 + p1],
+                     g5 = sG[4 * N3 + p1], g6 = sG[5 * N3 + p1];
+        swr[j1 * PS + i] = h1 * (g1 * ur1 + g4 * us1 + g5 * ut1);
+        sws[j1 * PS + i] = h1 * (g2 * us1 + g4 * ur1 + g6 * ut1);
+        wt1 = h1 * (g3 * ut1 + g5 * ur1 + g6 * us1);
+      }
+      __syncwarp();
+      double a0 = 0.0, a1 = 0.0;
+      if (CONV) {
+        a0 = sC[p0] * ur0 + sC[N3 + p0] * us0 + sC[2 * N3 + p0] * ut0;
+        a1 = sC[p1] * ur1 + sC[N3 + p1] * us1 + sC[2 * N3 + p1] * ut1;
+      }
+#pragma unroll
+      for (int l = 0; l < LX; ++l) {
+        const double ci = sD[l * LX + i];
+        a0 = fma(ci, swr[j0 * PS + l], a0);
+        a1 = fma(ci, swr[j1 * PS + l], a1);
+        const double ev = sws[l * PS + i];
+        a0 = fma(sD[l * LX + j0], ev, a0);
+        a1 = fma(sD[l * LX + j1], ev, a1);
+        const double dk = c_D8[k * LX + l];
+        wk0[l] = fma(dk, wt0, wk0[l]);
+        wk1[l] = fma(dk, wt1, wk1[l]);
+      }
+      wk0[k] += a0;
+      wk1[k] += a1;
+    }
+    double *we = wout + e * N3;
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      const int p0 = k * N2 + q0, p1 = k * N2 + q1;
+      double v0 = wk0[k], v1 = wk1[k];
+      if (h2 != 0.0) {
+        v0 = fma(h2 * sB[p0], uk0[k], v0);
+        v1 = fma(h2 * sB[p1], uk1[k], v1);
+      }
+      if (EPI == 1) {
+        const bool kb = (k == 0 || k == LX - 1);
+        if (!(b0 || kb)) v0 = alpha * uk0[k] + beta * sM[p0] * v0;
+        if (!(b1 || kb)) v1 = alpha * uk1[k] + beta * sM[p1] * v1;
+      }
+      we[p0] = v0;
+      we[p1] = v1;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the stage
+  }
+}
+
+template <int NF, bool CONV, int NSTAGE>
+constexpr size_t ring8_smem() {
+  return sizeof(double) * ((size_t)NSTAGE * (6 + 2 + (CONV ? 3 : 0) + NF) * 512 + NF * NSTAGE * 3 * 80 + 128) +
+         sizeof(uint64_t) * 2 * NSTAGE + 128;
+}
+
+template <int NF, bool CONV, int EPI>
+int launch_ring8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
+                 const double *cv, double alpha, double beta, const double *bmask) {
+  constexpr int NSTAGE = CONV ? 3 : 4;
+  constexpr size_t smem = ring8_smem<NF, CONV, NSTAGE>();
+  static_assert(smem <= 227 * 1024, "axhelm ring does not fit in shared memory");
+  auto kfn = axhelm3d_ring8_kernel<NF, CONV, EPI, NSTAGE>;
+  NSB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = S->nel < S->ctx->num_sms ? S->nel : S->ctx->num_sms;
+  kfn<<<(unsigned)grid, (NF * NSTAGE + 1) * 32, smem, S->ctx->stream>>>(u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1,
+                                                                       h2, cv, alpha, beta, bmask, fstride);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 // ---- axhelm, 2-D (one thread per point; parity configurations only) --------------------------
 template <bool CONV, int EPI>
 __global__ void axhelm2d_kernel(const double *__restrict__ u, double *__restrict__ w,
@@ -539,6 +721,13 @@ void launch_ax3d_t(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstr
 template <bool CONV, int EPI>
 int launch_ax3d(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
                 const double *cv, double alpha, double beta, const double *bmask) {
+  if (S->lx == 8 && !S->ctx->ax_generic && S->ctx->ax_ring && nf <= 3) {
+    // bmask / bm1 are staged unconditionally: hand the kernel valid arrays even when unused
+    const double *bmk = bmask ? bmask : S->bmask_d;
+    if (nf == 3) return launch_ring8<3, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmk);
+    if (nf == 2) return launch_ring8<2, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmk);
+    return launch_ring8<1, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmk);
+  }
   if (S->lx == 8 && !S->ctx->ax_generic) {
     const int64_t grid = (S->nel + 3) / 4;
     axhelm3d_warp8_kernel<CONV, EPI><<<dim3((unsigned)grid, nf), 128, 0, S->ctx->stream>>>(
@@ -578,8 +767,12 @@ int launch_axhelm(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstri
   // algorithmic bytes per point: u, w, G1..G6 (G1,G2,G4 in 2-D), bm1 if h2 != 0, C if convecting,
   // bmask on element-interior points of the fused epilogue
   const double fint = std::pow((double)(S->lx - 2) / S->lx, S->dim);
-  const double per_pt = 8.0 * (2 + S->ng + (h2 != 0.0 ? 1 : 0) + (cv ? S->dim : 0) + (epi ? fint : 0.0));
-  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts * nf);
+  // SURVEY.md section 8d counts these bytes per component (64 n general + 8 n for the h2 B term);
+  // the ring kernel actually moves fewer because G, bm1, bmask and C are staged once per element
+  // and shared by the nf components (8 (8 + 2 nf) bytes per point instead of 8 * 10 nf).
+  const double geo = 8.0 * (S->ng + (h2 != 0.0 ? 1 : 0) + (cv ? S->dim : 0) + (epi ? fint : 0.0));
+  const double per_pt = (geo + 16.0) * nf;
+  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts);
   if (S->dim == 3) {
     if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
                        : launch_ax3d<true, 0>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask);
