@@ -279,6 +279,75 @@ rotate_kernel(double *__restrict__ V, int64_t ld, int k, const double *__restric
 // completing on an mbarrier), forms w' for those rows (pass A) and immediately accumulates the
 // block's contribution to h2 from the staged copy (pass B).  V therefore crosses HBM once for the
 // two operations: 8 n (k+3) algorithmic bytes instead of 8 n (2k+5).
+// Register-tiled variant (used when the panel and at least 64 columns of Z fit in shared memory):
+// warp = group of 8 output columns (Z values are warp-uniform broadcasts), lane = 4 rows
+// {2l, 2l+1, 64+2l, 64+2l+1} of a 128-row panel (2 rows for 64-row panels), i.e. a 4 x 8 register
+// tile per thread: 10 shared loads per 32 FMAs instead of 5 loads per 8.  Z is resident in shared
+// memory (all of it when it fits, otherwise 64 columns at a time).
+template <int RB>
+__global__ void __launch_bounds__(NT, 1)
+rotate_tiled_kernel(double *__restrict__ V, int64_t ld, int k, const double *__restrict__ Z, int ldz,
+                    int64_t npanels, int ct) {
+  extern __shared__ __align__(16) double rsm[];
+  constexpr int RP = RB / 2, NR = RB / 64;     // row pairs per panel, row-pair slots per lane
+  double *tile = rsm;                          // [k][RB]
+  double *Zs = rsm + (size_t)k * RB;           // [ct][k], column-major like Z
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  const bool whole = ct >= k;                  // all of Z resident: load it once
+  if (whole) {
+    for (int t = tid; t < k * k; t += NT) Zs[t] = Z[(int64_t)(t / k) * ldz + (t % k)];
+  }
+  for (int64_t panel = blockIdx.x; panel < npanels; panel += gridDim.x) {
+    const int64_t r0 = panel * RB;
+    __syncthreads();
+    for (int t = tid; t < k * RP; t += NT) {
+      const int j = t / RP, r = t % RP;
+      reinterpret_cast<double2 *>(tile)[j * RP + r] =
+          reinterpret_cast<const double2 *>(V + (int64_t)j * ld + r0)[r];
+    }
+    for (int c0 = 0; c0 < k; c0 += ct) {
+      const int nc = (k - c0) < ct ? (k - c0) : ct;
+      if (!whole) {
+        __syncthreads();
+        for (int t = tid; t < nc * k; t += NT) Zs[t] = Z[(int64_t)(c0 + t / k) * ldz + (t % k)];
+      }
+      __syncthreads();
+      for (int cg = wq; cg * 8 < nc; cg += NT / 32) {
+        double acc[NR][2][8];
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[a][0][c] = acc[a][1][c] = 0.0;
+        const double *zc = Zs + (size_t)(cg * 8) * k;
+        const int ncol = (nc - cg * 8) < 8 ? (nc - cg * 8) : 8;
+#pragma unroll 4
+        for (int j = 0; j < k; ++j) {
+          double2 v[NR];
+#pragma unroll
+          for (int a = 0; a < NR; ++a) v[a] = reinterpret_cast<const double2 *>(tile)[j * RP + lane + 32 * a];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double z = c < ncol ? zc[(size_t)c * k + j] : 0.0;
+#pragma unroll
+            for (int a = 0; a < NR; ++a) {
+              acc[a][0][c] = fma(v[a].x, z, acc[a][0][c]);
+              acc[a][1][c] = fma(v[a].y, z, acc[a][1][c]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < ncol) {
+            double *col = V + (int64_t)(c0 + cg * 8 + c) * ld + r0;
+#pragma unroll
+            for (int a = 0; a < NR; ++a)
+              reinterpret_cast<double2 *>(col)[lane + 32 * a] = make_double2(acc[a][0][c], acc[a][1][c]);
+          }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
@@ -1091,7 +1160,41 @@ extern "C" int nsb_basis_rotate(nsb_basis_t B, int k, const double *Z, int ldz, 
     NSB_CUDA(cudaMemcpy2DAsync(tsave, sizeof(double), B->v_d + L->time_row, sizeof(double) * L->ld,
                                sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  // rows per panel chosen so that the staged panel fits in shared memory
+  // register-tiled kernel when the panel plus (part of) Z fit in shared memory
+  {
+    const size_t lim = 226 * 1024;
+    int trb = 0, ct = 0;
+    for (int rbc : {128, 64}) {
+      const size_t panel = (size_t)rbc * k * sizeof(double);
+      if (panel + (size_t)k * k * sizeof(double) <= lim) { trb = rbc; ct = k; break; }
+      if (panel + (size_t)64 * k * sizeof(double) <= lim) { trb = rbc; ct = 64; break; }
+    }
+    if (trb && !ctx->rotate_simple) {
+      const size_t smem = ((size_t)trb * k + (size_t)ct * k) * sizeof(double);
+      const int64_t npanels = L->ld / trb;
+      const int grid = (int)(npanels < ctx->num_sms ? npanels : ctx->num_sms);
+      {
+        ProfScope ps(ctx, PC_ROTATE, 16.0 * (double)L->nact * k);
+        if (trb == 128) {
+          NSB_CUDA(cudaFuncSetAttribute(rotate_tiled_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          rotate_tiled_kernel<128><<<grid, NT, smem, ctx->stream>>>(B->v_d, L->ld, k, Z_d, k, npanels, ct);
+        } else {
+          NSB_CUDA(cudaFuncSetAttribute(rotate_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          rotate_tiled_kernel<64><<<grid, NT, smem, ctx->stream>>>(B->v_d, L->ld, k, Z_d, k, npanels, ct);
+        }
+      }
+      ctx->launches++;
+      NSB_CUDA(cudaGetLastError());
+      if (!rotate_time)
+        NSB_CUDA(cudaMemcpy2DAsync(B->v_d + L->time_row, sizeof(double) * L->ld, tsave, sizeof(double),
+                                   sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
+      NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(Z_d);
+      if (tsave) cudaFree(tsave);
+      return NSB_OK;
+    }
+  }
+  // fallback: rows per panel chosen so that the staged panel fits in shared memory
   int rb = 128;
   while (rb > 32 && (size_t)rb * k * sizeof(double) > 200 * 1024) rb >>= 1;
   NSB_REQUIRE((size_t)rb * k * sizeof(double) <= 227 * 1024, "nsb_basis_rotate: k=%d too large", k);
