@@ -229,6 +229,13 @@ def run_native(a):
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
     ctx = nb.Context(device=local, rank=rank, nranks=world, unique_id=uid)
+    p2p = False
+    if world > 1 and os.environ.get('NSB_NO_P2P', '0') != '1':
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        p2p = ctx.connect_peers(allgather)      # NVLink peer-memory all-reduce / halo exchange
 
     def barrier():
         ctx.sync()
@@ -379,7 +386,9 @@ def run_native(a):
                                 orthogonalisation='CGS2 (two fused passes, H = h1 + h2)',
                                 bench_step='one k_dim-step Arnoldi factorisation',
                                 l2='inputs (basis >= 0.4 GB per column) exceed the 126 MB L2; no flush needed',
-                                partition=f'{world} z-slab(s) of elements'),
+                                partition=f'{world} z-slab(s) of elements',
+                                collectives=('NVLink peer-memory kernels (one-shot all-reduce, halo stores)' if p2p
+                                             else 'NCCL' if world > 1 else 'none')),
                     arnoldi_ms_per_step=ms / a.steps / K, matvec_gdof_per_s=matvec_gdofs,
                     matvec_ms=mv_ms, roofline=roofline, clocks=clocks, gpu_launches=int(launches))
         if e2e:

@@ -58,6 +58,17 @@ int nsb_get_unique_id(void *id_out /* NSB_UNIQUE_ID_BYTES */);
 /* unique_id may be NULL when nranks == 1. */
 int nsb_init(int device, int rank, int nranks, const void *unique_id, nsb_context_t *ctx);
 int nsb_finalize(nsb_context_t ctx);
+/* NVLink peer-memory mailbox (optional, single node, <= 16 ranks).  Every rank creates a mailbox and
+ * gets a 64-byte CUDA IPC handle; the host all-gathers the handles with its own transport
+ * (MPI_Allgather in Nek) and every rank maps all of them.  Afterwards the all-reduces of the inner
+ * products (gop -> MPI_Allreduce in the reference) and the dssum interface exchange are kernels
+ * that store straight into the peers' memory -- no NCCL launch on the hot path.  halo_bytes sizes
+ * the interface area (2 slots x 8 fields x shared nodes x 8 B per neighbour; falls back to NCCL if
+ * too small).  Call before nsb_sem_setup_exchange. */
+#define NSB_IPC_HANDLE_BYTES 64
+int nsb_p2p_mailbox_create(nsb_context_t ctx, int64_t halo_bytes, void *handle_out);
+int nsb_p2p_mailbox_connect(nsb_context_t ctx, const void *all_handles /* nranks x 64 B */);
+int nsb_p2p_enabled(nsb_context_t ctx, int *enabled);
 int nsb_sync(nsb_context_t ctx);
 int nsb_rank(nsb_context_t ctx, int *rank, int *nranks);
 /* CUDA stream of the context as an integer handle (for event timing by the caller). */

@@ -23,6 +23,9 @@ PROTOTYPES = {
     'nsb_get_unique_id': (C.c_int, [C.c_void_p]),
     'nsb_init': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, c_void_pp]),
     'nsb_finalize': (C.c_int, [H]),
+    'nsb_p2p_mailbox_create': (C.c_int, [H, C.c_int64, C.c_void_p]),
+    'nsb_p2p_mailbox_connect': (C.c_int, [H, C.c_void_p]),
+    'nsb_p2p_enabled': (C.c_int, [H, c_int_p]),
     'nsb_sync': (C.c_int, [H]),
     'nsb_rank': (C.c_int, [H, c_int_p, c_int_p]),
     'nsb_stream': (C.c_int, [H, c_u64_p]),

@@ -82,6 +82,23 @@ class Context:
         check(_capi.load().nsb_get_unique_id(buf))
         return buf.raw
 
+    def connect_peers(self, allgather, halo_bytes: int = 64 << 20):
+        """Map every rank's NVLink mailbox.  ``allgather(bytes) -> list[bytes]`` is the host's own
+        transport (torch.distributed.all_gather_object in the tests, MPI_Allgather in Nek)."""
+        if self.nranks == 1:
+            return False
+        buf = C.create_string_buffer(64)
+        check(self.lib.nsb_p2p_mailbox_create(self.h, int(halo_bytes), buf))
+        handles = allgather(buf.raw)
+        allb = C.create_string_buffer(b''.join(handles), 64 * self.nranks)
+        check(self.lib.nsb_p2p_mailbox_connect(self.h, allb))
+        return True
+
+    def p2p_enabled(self) -> bool:
+        v = C.c_int()
+        check(self.lib.nsb_p2p_enabled(self.h, C.byref(v)))
+        return bool(v.value)
+
     def sync(self):
         check(self.lib.nsb_sync(self.h))
 

@@ -76,6 +76,113 @@ static int load_nccl() {
     }                                                                                         \
   } while (0)
 
+// ------------------------------------------------------------------------------------------------
+// NVLink peer-memory path.  Every rank exports one "mailbox" allocation through CUDA IPC and maps
+// all the others (NVSwitch gives every GPU a direct path to every peer).  Collectives on the hot
+// path then are plain kernels:
+//   all-reduce of <= 1032 doubles (the H column): each rank STORES its vector into slot
+//     [seq&1][rank] of every mailbox, publishes seq with a release store, waits until all peers'
+//     flags show seq, and sums the P vectors in rank order (bitwise identical on every rank);
+//   halo exchange: the pack kernel stores the interface sums straight into the peer's mailbox.
+// Two slots suffice: a rank can only be one collective ahead of the slowest one, because finishing
+// collective s+1 needs everybody's contribution to it, which they issue after finishing s.
+// NCCL stays for bootstrap, set-up and as the fallback when no mailbox is connected.
+// ------------------------------------------------------------------------------------------------
+constexpr int ARN = kMaxK + 8;                    // doubles per all-reduce vector slot
+struct PeerPtrs { double *p[nsb_context_s::kMaxPeers]; };
+
+// mailbox layout (in doubles): [ar data 2*P*ARN][ar flags 2*P][halo flags 2*P][halo data ...]
+__host__ __device__ inline size_t mb_ar_data(int P, int slot, int r) { return ((size_t)slot * P + r) * ARN; }
+__host__ __device__ inline size_t mb_ar_flag(int P, int slot, int r) { return (size_t)2 * P * ARN + (size_t)slot * P + r; }
+__host__ __device__ inline size_t mb_hx_flag(int P, int slot, int r) { return (size_t)2 * P * ARN + 2 * P + (size_t)slot * P + r; }
+__host__ __device__ inline size_t mb_halo_base(int P) { return (((size_t)2 * P * ARN + 4 * P) + 31) & ~(size_t)31; }
+
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(double *__restrict__ buf, int n, uint64_t seq, int rank, int P, PeerPtrs mail) {
+  const int slot = (int)(seq & 1);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = buf[j];
+    for (int r = 0; r < P; ++r) mail.p[r][mb_ar_data(P, slot, rank) + j] = v;   // peer stores over NVLink
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < P)
+    st_release_sys(reinterpret_cast<uint64_t *>(mail.p[threadIdx.x] + mb_ar_flag(P, slot, rank)), seq);
+  if (threadIdx.x < P) {
+    const uint64_t *f = reinterpret_cast<const uint64_t *>(mail.p[rank] + mb_ar_flag(P, slot, threadIdx.x));
+    while (ld_acquire_sys(f) != seq) { }
+  }
+  __syncthreads();
+  const double *mine = mail.p[rank];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < P; ++r) s += mine[mb_ar_data(P, slot, r) + j];
+    buf[j] = s;
+  }
+}
+
+// pack the interface sums of nf fields straight into the peer's mailbox
+__global__ void pack_p2p_kernel(const double *__restrict__ node_sum, const int32_t *__restrict__ nodes, int64_t n,
+                                double *__restrict__ dst, int64_t ns_stride) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (t < n) dst[(int64_t)f * n + t] = node_sum[(int64_t)f * ns_stride + nodes[t]];
+}
+
+struct HaloFlags { uint64_t *p[nsb_context_s::kMaxPeers]; int n; };
+__global__ void p2p_flags_kernel(HaloFlags fl, uint64_t seq) {
+  if ((int)threadIdx.x < fl.n) st_release_sys(fl.p[threadIdx.x], seq);
+}
+
+__global__ void unpack_wait_add_kernel(double *__restrict__ node_sum, const int32_t *__restrict__ nodes, int64_t n,
+                                       const double *__restrict__ src, int64_t ns_stride,
+                                       const uint64_t *__restrict__ flag, uint64_t seq) {
+  if (threadIdx.x == 0)
+    while (ld_acquire_sys(flag) != seq) { }
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (t < n) node_sum[(int64_t)f * ns_stride + nodes[t]] += src[(int64_t)f * n + t];
+}
+
+int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st) {
+  nsb_context_t ctx = S->ctx;
+  const int P = ctx->nranks;
+  const uint64_t seq = ++ctx->hx_seq;
+  const int slot = (int)(seq & 1);
+  const int64_t nifc = S->nshared - S->n_local;
+  HaloFlags fl;
+  fl.n = 0;
+  for (auto &Pr : S->peers) {
+    const unsigned nb = (unsigned)((Pr.n + 255) / 256);
+    double *dst = ctx->peer_mail[Pr.rank] + mb_halo_base(P) + Pr.peer_off + (int64_t)slot * S->ns_fields * Pr.n;
+    pack_p2p_kernel<<<dim3(nb, nf), 256, 0, st>>>(S->node_sum_d, Pr.idx_d, Pr.n, dst, nifc);
+    fl.p[fl.n++] = reinterpret_cast<uint64_t *>(ctx->peer_mail[Pr.rank] + mb_hx_flag(P, slot, ctx->rank));
+    ctx->launches++;
+  }
+  // stores of the pack kernels are complete at the kernel boundary; then publish the sequence number
+  p2p_flags_kernel<<<1, 32, 0, st>>>(fl, seq);
+  ctx->launches++;
+  for (auto &Pr : S->peers) {
+    const unsigned nb = (unsigned)((Pr.n + 255) / 256);
+    const double *src = ctx->mail_d + mb_halo_base(P) + Pr.my_off + (int64_t)slot * S->ns_fields * Pr.n;
+    const uint64_t *flag = reinterpret_cast<const uint64_t *>(ctx->mail_d + mb_hx_flag(P, slot, Pr.rank));
+    unpack_wait_add_kernel<<<dim3(nb, nf), 256, 0, st>>>(S->node_sum_d, Pr.idx_d, Pr.n, src, nifc, flag, seq);
+    ctx->launches++;
+  }
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 int comm_init(nsb_context_t ctx, const void *unique_id) {
   NSB_CHECK(load_nccl());
   static_assert(sizeof(ncclUniqueId) <= NSB_UNIQUE_ID_BYTES, "unique id size");
@@ -98,6 +205,16 @@ int comm_destroy(nsb_context_t ctx) {
 
 int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n) {
   if (ctx->nranks == 1 || n == 0) return NSB_OK;
+  if (ctx->p2p && n <= kMaxK + 8) {
+    PeerPtrs mail;
+    for (int r = 0; r < ctx->nranks; ++r) mail.p[r] = ctx->peer_mail[r];
+    const uint64_t seq = ++ctx->ar_seq;
+    ProfScope ps(ctx, PC_SMALL, 8.0 * n * ctx->nranks);
+    p2p_allreduce_kernel<<<1, 256, 0, ctx->stream>>>(buf_d, n, seq, ctx->rank, ctx->nranks, mail);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
   NSB_REQUIRE(ctx->nccl_comm, "allreduce: no communicator");
   NSB_NCCL(g_nccl.AllReduce(buf_d, buf_d, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm,
                             ctx->stream));
@@ -232,6 +349,37 @@ int exchange_setup(nsb_sem_t S) {
     NSB_CUDA(cudaMemcpy(Pr.idx_d, nodes.data(), sizeof(int32_t) * Pr.n, cudaMemcpyHostToDevice));
     S->peers.push_back(Pr);
   }
+  // 5. peer-memory halo: lay out one region per peer in MY mailbox and tell every peer where its
+  //    data goes (all-gather of the offset tables)
+  S->p2p_halo = false;
+  if (ctx->p2p) {
+    std::vector<int64_t> mine_off(P, -1);
+    int64_t cur = 0;
+    for (auto &Pr : S->peers) {
+      Pr.my_off = cur;
+      mine_off[Pr.rank] = cur;
+      cur += 2 * (int64_t)S->ns_fields * Pr.n;           // two slots
+      cur = (cur + 31) & ~(int64_t)31;
+    }
+    int64_t fits = (mb_halo_base(P) + (size_t)cur) * sizeof(double) <= ctx->mail_bytes ? 1 : 0;
+    int64_t *tab_d = nullptr;
+    NSB_CUDA(cudaMalloc(&tab_d, sizeof(int64_t) * (size_t)(P + 1) * (P + 1)));
+    std::vector<int64_t> sendt(mine_off);
+    sendt.push_back(fits);
+    NSB_CUDA(cudaMemcpyAsync(tab_d + (size_t)P * (P + 1), sendt.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    NSB_NCCL(g_nccl.AllGather(tab_d + (size_t)P * (P + 1), tab_d, (size_t)(P + 1), ncclInt64, comm, ctx->stream));
+    std::vector<int64_t> tab((size_t)P * (P + 1));
+    NSB_CUDA(cudaMemcpyAsync(tab.data(), tab_d, sizeof(int64_t) * tab.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tab_d);
+    bool all_fit = true;
+    for (int r = 0; r < P; ++r) all_fit = all_fit && tab[(size_t)r * (P + 1) + P] == 1;
+    if (all_fit) {
+      for (auto &Pr : S->peers) Pr.peer_off = tab[(size_t)Pr.rank * (P + 1) + ctx->rank];
+      S->p2p_halo = true;
+    }
+  }
   return NSB_OK;
 }
 
@@ -259,6 +407,52 @@ extern "C" int nsb_host_exchange_plan(int rank, int nranks, int64_t nnodes, cons
     peer_count[r] = (int64_t)plan.peer_nodes[r].size();
     memcpy(peer_nodes + (size_t)r * mx, plan.peer_nodes[r].data(), sizeof(int32_t) * plan.peer_nodes[r].size());
   }
+  return NSB_OK;
+}
+
+// Peer-memory mailbox: create + export (64-byte CUDA IPC handle), then map every rank's mailbox.
+extern "C" int nsb_p2p_mailbox_create(nsb_context_t ctx, int64_t halo_bytes, void *handle_out) {
+  NSB_REQUIRE(ctx && handle_out && halo_bytes >= 0, "nsb_p2p_mailbox_create: bad argument");
+  NSB_REQUIRE(ctx->nranks <= nsb_context_s::kMaxPeers, "nsb_p2p_mailbox_create: more than %d ranks",
+              nsb_context_s::kMaxPeers);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaSetDevice(ctx->device);
+  if (ctx->mail_d) cudaFree(ctx->mail_d);
+  ctx->halo_bytes = (size_t)halo_bytes;
+  ctx->mail_bytes = nsb::mb_halo_base(ctx->nranks) * sizeof(double) + (size_t)halo_bytes;
+  NSB_CUDA(cudaMalloc(&ctx->mail_d, ctx->mail_bytes));
+  NSB_CUDA(cudaMemset(ctx->mail_d, 0, ctx->mail_bytes));
+  cudaIpcMemHandle_t h;
+  NSB_CUDA(cudaIpcGetMemHandle(&h, ctx->mail_d));
+  memcpy(handle_out, &h, sizeof(h));
+  return NSB_OK;
+}
+
+extern "C" int nsb_p2p_mailbox_connect(nsb_context_t ctx, const void *all_handles) {
+  NSB_REQUIRE(ctx && all_handles && ctx->mail_d, "nsb_p2p_mailbox_connect: create the mailbox first");
+  cudaSetDevice(ctx->device);
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == ctx->rank) {
+      ctx->peer_mail[r] = ctx->mail_d;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)all_handles + (size_t)r * 64, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      nsb::set_error("nsb_p2p_mailbox_connect: cannot map the mailbox of rank %d: %s", r, cudaGetErrorString(e));
+      return NSB_ECUDA;
+    }
+    ctx->peer_mail[r] = (double *)p;
+  }
+  ctx->p2p = true;
+  return NSB_OK;
+}
+
+extern "C" int nsb_p2p_enabled(nsb_context_t ctx, int *allreduce_p2p) {
+  NSB_REQUIRE(ctx && allreduce_p2p, "nsb_p2p_enabled: NULL argument");
+  *allreduce_p2p = ctx->p2p ? 1 : 0;
   return NSB_OK;
 }
 

@@ -147,6 +147,9 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
   if (!ctx) return NSB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < ctx->nranks && r < nsb_context_s::kMaxPeers; ++r)
+    if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
+  if (ctx->mail_d) cudaFree(ctx->mail_d);
   comm_destroy(ctx);
   if (ctx->partial_d) cudaFree(ctx->partial_d);
   if (ctx->hvec_d) cudaFree(ctx->hvec_d);

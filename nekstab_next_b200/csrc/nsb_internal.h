@@ -58,6 +58,14 @@ struct nsb_context_s {
   double *hpin = nullptr;      // pinned mirror
   double *flush_d = nullptr;
   size_t flush_bytes = 0;
+  // NVLink peer-memory mailbox (nsb_comm.cu): one-shot all-reduce and halo exchange written
+  // straight into the peers' memory instead of NCCL launches
+  static constexpr int kMaxPeers = 16;
+  bool p2p = false;
+  double *mail_d = nullptr;            // own mailbox (cudaMalloc, IPC-exported)
+  size_t mail_bytes = 0, halo_bytes = 0;
+  double *peer_mail[kMaxPeers] = {};   // every rank's mailbox mapped here ([rank] = own)
+  uint64_t ar_seq = 0, hx_seq = 0;     // sequence numbers of the all-reduces / halo exchanges
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
   bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
   int fused_loader = 3;        // NSB_FUSED_LOADER: 0 TMA bulk per column, 1 cp.async, 2 registers, 3 TMA 2-D
@@ -123,10 +131,13 @@ struct nsb_sem_s {
     int64_t n;                   // shared nodes with that rank
     int32_t *idx_d;              // interface-node index (node - n_local) of every node shared with that rank, sorted by gid
     double *send_d, *recv_d;
+    int64_t my_off = -1;         // P2P: offset (doubles) of this peer's region in MY mailbox halo area
+    int64_t peer_off = -1;       // P2P: offset of MY region in the PEER's mailbox halo area
   };
   std::vector<Peer> peers;
   std::vector<int64_t> glo_h;    // kept for exchange setup
   bool exchange_ready = false;
+  bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
 };
 
 struct nsb_op_s {
@@ -160,6 +171,7 @@ int comm_destroy(nsb_context_t ctx);
 int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n);  // on ctx->stream, in place
 int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int nf, cudaStream_t st);
 int exchange_setup(nsb_sem_t sem);
+int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st);  // pack -> peer stores -> flags -> wait -> add
 // host-only plans (also reachable through nsb_host_gs_plan / nsb_host_exchange_plan for CPU tests)
 int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
             std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult);

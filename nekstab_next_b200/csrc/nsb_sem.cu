@@ -825,15 +825,19 @@ int launch_gs(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const do
   NSB_CUDA(cudaEventRecord(S->ev_a, ctx->stream));
   NSB_CUDA(cudaStreamWaitEvent(s2, S->ev_a, 0));
   gs_launch<2>(S, s2, v, nloc, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, ns, nifc);
-  for (auto &P : S->peers) {
-    pack_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.send_d, nifc);
-    ctx->launches++;
-  }
-  NSB_CUDA(cudaGetLastError());
-  NSB_CHECK(sendrecv_d(ctx, S->peers, nf, s2));
-  for (auto &P : S->peers) {
-    unpack_add_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.recv_d, nifc);
-    ctx->launches++;
+  if (S->p2p_halo) {
+    NSB_CHECK(halo_exchange_p2p(S, nf, s2));   // stores into the peers' mailboxes, no NCCL launch
+  } else {
+    for (auto &P : S->peers) {
+      pack_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.send_d, nifc);
+      ctx->launches++;
+    }
+    NSB_CUDA(cudaGetLastError());
+    NSB_CHECK(sendrecv_d(ctx, S->peers, nf, s2));
+    for (auto &P : S->peers) {
+      unpack_add_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.recv_d, nifc);
+      ctx->launches++;
+    }
   }
   if (epi == 0) gs_launch<3>(S, s2, v, nloc, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, ns, nifc);
   else gs_launch<4>(S, s2, v, nloc, S->nshared, nf, fstride, uin, alpha, beta, bmask, ns, nifc);

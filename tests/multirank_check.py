@@ -29,6 +29,12 @@ def main():
     box = [nb.Context.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     ctx = nb.Context(device=local, rank=rank, nranks=world, unique_id=box[0])
+    if os.environ.get('NSB_TEST_P2P', '0') == '1':
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        assert ctx.connect_peers(allgather, halo_bytes=8 << 20) and ctx.p2p_enabled()
 
     nel, N, nc, K = (3, 2, 2 * world), 5, 2, 12
     P = BoxProblem(nel=nel, N=N, deform=0.04, nfields=nc, conv=True, time_in_dot=True, seed=21)  # whole mesh
