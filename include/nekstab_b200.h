@@ -84,6 +84,9 @@ int nsb_timer_stop(nsb_context_t ctx, double *elapsed_ms); /* synchronises */
  * 8 gemv, 9 single dot, 10 fused update+multidot (w -= V h1 ; h2 = V^T W w).  bytes = algorithmic bytes summed over the recorded launches. */
 int nsb_prof_enable(nsb_context_t ctx, int on); /* also clears the records */
 int nsb_prof_get(nsb_context_t ctx, int cls, double *ms, int64_t *launches, double *bytes);
+/* cudaProfilerStart / Stop, so `ncu --profile-from-start off` captures only a delimited region. */
+int nsb_profiler_start(void);
+int nsb_profiler_stop(void);
 /* Sum-allreduce n doubles held on the host across ranks (gop(x,'+')); no-op for one rank. */
 int nsb_allreduce_host(nsb_context_t ctx, double *x, int n);
 /* Write a buffer larger than L2 (bench hygiene). */

@@ -12,6 +12,6 @@ from .api import (  # noqa: F401
     k_zero, k_copy, k_matmul, orthonormalize, arnoldi_factorization, eig, schur, ordschur, lstsq,
     select_eigenvalues, schur_condensation, krylov_schur, ts_gmres, set_lapack_from_scipy, KSResult,
 )
-from . import mesh  # noqa: F401
+from . import mesh, seed, checkpoint  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith('_')]

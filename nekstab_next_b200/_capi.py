@@ -34,6 +34,8 @@ PROTOTYPES = {
     'nsb_timer_stop': (C.c_int, [H, c_double_p]),
     'nsb_prof_enable': (C.c_int, [H, C.c_int]),
     'nsb_prof_get': (C.c_int, [H, C.c_int, c_double_p, c_i64_p, c_double_p]),
+    'nsb_profiler_start': (C.c_int, []),
+    'nsb_profiler_stop': (C.c_int, []),
     'nsb_allreduce_host': (C.c_int, [H, c_double_p, C.c_int]),
     'nsb_flush_l2': (C.c_int, [H]),
     'nsb_layout_create': (C.c_int, [H, C.c_int, c_i64_p, c_int_p, C.c_int, c_void_pp]),

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cmath>
 
+#include <cuda_profiler_api.h>
+
 #include "nsb_internal.h"
 #include "nsb_device.cuh"
 
@@ -85,6 +87,16 @@ extern "C" int nsb_prof_get(nsb_context_t ctx, int cls, double *ms, int64_t *lau
   if (ms) *ms = t;
   if (launches) *launches = n;
   if (bytes) *bytes = b;
+  return NSB_OK;
+}
+
+// Delimit the region a profiler captures (ncu --profile-from-start off).
+extern "C" int nsb_profiler_start(void) {
+  NSB_CUDA(cudaProfilerStart());
+  return NSB_OK;
+}
+extern "C" int nsb_profiler_stop(void) {
+  NSB_CUDA(cudaProfilerStop());
   return NSB_OK;
 }
 

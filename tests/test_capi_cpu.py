@@ -109,3 +109,22 @@ def test_partition_ranges():
             assert rs[0][0] == 0 and rs[-1][1] == total // gran * gran
             for (a, b), (c, d) in zip(rs[:-1], rs[1:]):
                 assert b == c and (b - a) % gran == 0
+
+
+def test_seed_noise_matches_reference_formula():
+    """mth_rand / op_add_noise (core/utils.f90:297-359, 408-418): product vs oracle restatement."""
+    from nekstab_next_b200 import seed
+    x, y, z, glo = osem.box_mesh(2, 2, 2, 3, deform=0.02)
+    a = seed.noise_fields((x, y, z))
+    b = okr.op_add_noise((x, y, z), if3d=True)
+    for p, q in zip(a, b):
+        assert np.array_equal(p, q) and np.all(np.abs(p) <= 1.0)
+    x2, y2, glo2 = osem.box_mesh_2d(3, 2, 4)
+    a = seed.noise_fields((x2, y2))
+    b = okr.op_add_noise((x2, y2), if3d=False)
+    assert len(a) == 2 and all(np.array_equal(p, q) for p, q in zip(a, b))
+    # spot value computed by hand from the formula: element 1, point (1,1,1) at the origin
+    fc = seed.NOISE_FC[0]
+    r = fc[0] * (1 + 0.0) + fc[1] * 1 + fc[2] * 1
+    r = fc[0] * (1 + 0.0 * np.sin(r)) + fc[1] * 1 + fc[2] * 1
+    assert abs(seed.noise_fields((x, y, z))[0][0, 0, 0, 0] - np.cos(1e3 * np.sin(1e3 * np.sin(r)))) < 1e-12

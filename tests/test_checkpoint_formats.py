@@ -1,0 +1,83 @@
+"""Checkpoint / restart wire formats (HES*, Spectre_*, KRY* field files) against the reference's
+own files and format statements."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from nekstab_next_b200 import checkpoint as ck
+from oracle import nekfld
+
+REF = Path('/root/reference/examples')
+
+
+def test_fortran_e_format():
+    # values as gfortran prints them with E15.7
+    assert ck.fortran_e(1.0) == '  0.1000000E+01'
+    assert ck.fortran_e(-0.5) == ' -0.5000000E+00'
+    assert ck.fortran_e(0.0) == '  0.0000000E+00'
+    assert ck.fortran_e(123456.789) == '  0.1234568E+06'
+    assert ck.fortran_e(9.99999999) == '  0.1000000E+02'       # mantissa rounds up to 1.0
+    assert ck.fortran_e(-3.1e-7) == ' -0.3100000E-06'
+    assert all(len(ck.fortran_e(v)) == 15 for v in (1e-30, -1e30, 7.0))
+
+
+def test_spectrum_roundtrip(tmp_path):
+    vals = np.array([0.98 + 0.1j, 0.98 - 0.1j, -0.5 + 0j])
+    res = np.array([1e-9, 1e-9, 3.2e-4])
+    p = tmp_path / 'Spectre_Hd0100.dat'
+    ck.write_spectrum(p, vals, res)
+    lines = p.read_text().splitlines()
+    assert all(len(l) == 45 for l in lines)
+    v2, r2 = ck.read_spectrum(p)
+    assert np.allclose(v2, vals, rtol=1e-6) and np.allclose(r2, res, rtol=1e-6)
+
+
+def test_hessenberg_roundtrip_and_subsample(tmp_path):
+    rng = np.random.default_rng(0)
+    k = 7
+    H = np.triu(rng.standard_normal((k + 1, k)), -1)
+    p = tmp_path / ck.hessenberg_name('1cyl', k)
+    assert p.name == 'HES1cyl0007'
+    ck.write_hessenberg(p, H, k)
+    H2 = ck.read_hessenberg(p, k_dim=10, mstart=k)
+    assert H2.shape == (11, 10) and np.array_equal(H2[:k + 1, :k], H) and not H2[k + 1:].any()
+    H3 = ck.read_hessenberg(p, k_dim=5, mstart=k)     # k_dim < mstart: subsample (core/eigensolvers.f90:248-254)
+    assert np.array_equal(H3, H[:6, :5])
+    with pytest.raises(ValueError):
+        ck.read_hessenberg(p, k_dim=10, mstart=k + 1)
+
+
+def test_field_file_roundtrip(tmp_path):
+    rng = np.random.default_rng(1)
+    nel, lx = 5, 4
+    for nz in (1, lx):
+        shp = (nel, nz, lx, lx) if nz > 1 else (nel, lx, lx)
+        nd = 3 if nz > 1 else 2
+        x = [rng.standard_normal(shp) for _ in range(nd)]
+        u = [rng.standard_normal(shp) for _ in range(nd)]
+        pr = rng.standard_normal(shp)
+        p = tmp_path / ck.field_name('KRY', 'box', 12)
+        assert p.name == 'KRYbox0.f00012'
+        ck.write_fld(p, dict(x=x, u=u, p=pr), lx, lx, nz, time=3.5, istep=7)
+        for reader in (ck.read_fld, nekfld.read_fld):          # product reader and oracle reader agree
+            f = reader(p)
+            assert f['rdcode'] == 'XUP' and f['nel'] == nel and f['time'] == 3.5 and f['istep'] == 7
+            assert all(np.array_equal(a, b) for a, b in zip(f['x'], x))
+            assert all(np.array_equal(a, b) for a, b in zip(f['u'], u)) and np.array_equal(f['p'], pr)
+        ck.write_fld(p, dict(u=u), lx, lx, nz, wdsize=4)
+        f = ck.read_fld(p)
+        assert f['wdsize'] == 4 and np.allclose(f['u'][0], u[0], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.skipif(not REF.exists(), reason='reference tree not present (GPU box)')
+def test_reads_reference_field_files_and_rewrites_them_identically(tmp_path):
+    src = REF / 'cylinder/BF_1cyl0.f00001'
+    f = ck.read_fld(src)
+    g = nekfld.read_fld(src)
+    assert f['nel'] == 1996 and f['rdcode'] == 'XUP'
+    assert np.array_equal(f['x'][1], g['x'][1]) and np.array_equal(f['u'][0], g['u'][0]) and np.array_equal(f['p'], g['p'])
+    out = tmp_path / 'BF_copy0.f00001'
+    ck.write_fld(out, dict(x=f['x'], u=f['u'], p=f['p']), f['nx'], f['ny'], f['nz'], time=f['time'], istep=f['istep'],
+                 elmap=f['elmap'])
+    assert src.read_bytes() == out.read_bytes()               # header and payload bit-identical
