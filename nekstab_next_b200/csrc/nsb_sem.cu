@@ -468,6 +468,17 @@ axhelm3d_ring8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
   const double *sU = sG + (size_t)(8 + (CONV ? 3 : 0) + f) * N3;
   double *wout = w + (int64_t)f * fstride;
   const bool b0 = (i == 0 || i == LX - 1 || j0 == 0), b1 = (i == 0 || i == LX - 1 || j1 == LX - 1);
+  // row i and column i of D never change for this lane: keep them in registers (ncu: the shared
+  // pipe is the limiter of this kernel, 87 % busy, and D reads are 40 % of its loads)
+  constexpr bool CACHE_D = (NSTAGE <= 3);   // 10 warps leave 168 registers per thread, 13 warps only 128
+  double dri[CACHE_D ? LX : 1], dci[CACHE_D ? LX : 1];
+  if (CACHE_D) {
+#pragma unroll
+    for (int l = 0; l < LX; ++l) {
+      dri[l % (CACHE_D ? LX : 1)] = sDt[l * LX + i];   // D(i,l)
+      dci[l % (CACHE_D ? LX : 1)] = sD[l * LX + i];    // D(l,i)
+    }
+  }
   for (int64_t it = s; it < nit; it += NSTAGE) {
     const int64_t e = blockIdx.x + it * gridDim.x;
     mbar_wait(full + s, (uint32_t)((it / NSTAGE) & 1));
@@ -487,7 +498,7 @@ axhelm3d_ring8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
       double ur0 = 0, ur1 = 0, us0 = 0, us1 = 0, ut0 = 0, ut1 = 0;
 #pragma unroll
       for (int l = 0; l < LX; ++l) {
-        const double di = sDt[l * LX + i];
+        const double di = CACHE_D ? dri[l % (CACHE_D ? LX : 1)] : sDt[l * LX + i];
         ur0 = fma(di, su[j0 * PS + l], ur0);
         ur1 = fma(di, su[j1 * PS + l], ur1);
         const double b = su[l * PS + i];
@@ -521,7 +532,7 @@ axhelm3d_ring8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
       }
 #pragma unroll
       for (int l = 0; l < LX; ++l) {
-        const double ci = sD[l * LX + i];
+        const double ci = CACHE_D ? dci[l % (CACHE_D ? LX : 1)] : sD[l * LX + i];
         a0 = fma(ci, swr[j0 * PS + l], a0);
         a1 = fma(ci, swr[j1 * PS + l], a1);
         const double ev = sws[l * PS + i];
@@ -562,10 +573,9 @@ constexpr size_t ring8_smem() {
          sizeof(uint64_t) * 2 * NSTAGE + 128;
 }
 
-template <int NF, bool CONV, int EPI>
-int launch_ring8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
-                 const double *cv, double alpha, double beta, const double *bmask) {
-  constexpr int NSTAGE = CONV ? 3 : 4;
+template <int NF, bool CONV, int EPI, int NSTAGE>
+int launch_ring8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
+                   const double *cv, double alpha, double beta, const double *bmask) {
   constexpr size_t smem = ring8_smem<NF, CONV, NSTAGE>();
   static_assert(smem <= 227 * 1024, "axhelm ring does not fit in shared memory");
   auto kfn = axhelm3d_ring8_kernel<NF, CONV, EPI, NSTAGE>;
@@ -576,6 +586,14 @@ int launch_ring8(nsb_sem_t S, const double *u, double *w, int64_t fstride, doubl
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
+}
+
+template <int NF, bool CONV, int EPI>
+int launch_ring8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
+                 const double *cv, double alpha, double beta, const double *bmask) {
+  if (CONV || S->ctx->ax_stages == 3)
+    return launch_ring8_s<NF, CONV, EPI, 3>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
+  return launch_ring8_s<NF, CONV, EPI, CONV ? 3 : 4>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
 }
 
 // ---- axhelm, 2-D (one thread per point; parity configurations only) --------------------------
