@@ -66,6 +66,11 @@ struct nsb_context_s {
   size_t mail_bytes = 0, halo_bytes = 0;
   double *peer_mail[kMaxPeers] = {};   // every rank's mailbox mapped here ([rank] = own)
   uint64_t ar_seq = 0, hx_seq = 0;     // sequence numbers of the all-reduces / halo exchanges
+  // pipelined host upload (nsb_orth.cu): h1 computed chunk by chunk while the vector arrives
+  std::vector<cudaEvent_t> chunk_ev;
+  int h1_ready_k = -1;
+  const double *h1_ready_col = nullptr;
+  bool pipeline_upload = true;   // NSB_PIPELINE_UPLOAD=0: plain upload, then the usual first sweep
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
   bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
   int fused_loader = 3;        // NSB_FUSED_LOADER: 0 TMA bulk per column, 1 cp.async, 2 registers, 3 TMA 2-D
@@ -185,4 +190,5 @@ int exchange_plan(int rank, int nranks, const std::vector<int64_t> &gid, const s
                   const int64_t *all_sorted, int64_t mx, ExchangePlan &plan);
 // implemented in nsb_orth.cu
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d);
+int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k);
 }  // namespace nsb

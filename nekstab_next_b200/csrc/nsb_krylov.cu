@@ -207,7 +207,31 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
   int rc = NSB_OK;
   for (int m = mstart; m <= mend && rc == NSB_OK; ++m) {
     // f = M q_m, written straight into column m+1 (saves the k_copy of :81)
-    rc = nsb_op_apply(op, Q, m, Q, m + 1);
+    if (op->kind == 1 && orth_mode == NSB_ORTH_CGS2 && ctx->pipeline_upload) {
+      // host operator: download q_m, call the host matvec, then upload f in row chunks with the
+      // first projection running on every chunk as it lands
+      nsb_layout_t L = Q->lay;
+      std::vector<const double *> pin(L->nfields);
+      std::vector<double *> pout(L->nfields), pdl(L->nfields);
+      for (int f = 0; f < L->nfields; ++f) {
+        pin[f] = op->hin[f];
+        pdl[f] = op->hin[f];
+        pout[f] = op->hout[f];
+      }
+      double tin = 0.0, tout = 0.0;
+      rc = nsb_vec_download(Q, m, pdl.data(), &tin);
+      if (rc != NSB_OK) break;
+      op->napply++;
+      if (op->fn(op->user, pin.data(), tin, pout.data(), &tout) != 0) {
+        set_error("nsb_arnoldi: host matvec callback failed at step %d", m);
+        rc = NSB_EINVAL;
+        break;
+      }
+      std::vector<const double *> pup(pout.begin(), pout.end());
+      rc = upload_multidot_pipelined(Q, m + 1, pup.data(), tout, m + 1);
+    } else {
+      rc = nsb_op_apply(op, Q, m, Q, m + 1);
+    }
     if (rc != NSB_OK) break;
     if (async) {
       rc = nsb_orthonormalize_async(Q, m + 1, m + 1, orth_mode, hbuf + stride * (m - mstart));

@@ -12,6 +12,7 @@
 // 1024-row chunk as two double2; 8 columns (16 x 128-bit loads per thread) are in flight at once.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -780,6 +781,25 @@ inline int persistent_grid(nsb_context_t ctx, int64_t nchunks) {
   return (int)(nchunks < g ? nchunks : g);
 }
 
+// Row-range variant used by the pipelined upload: rows [r0, r1) only, partial sums written from
+// partial row `prow` on; returns the number of partial rows produced (no second-stage reduction).
+int launch_multidot_rows(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *w, const double *W,
+                         int64_t r0, int64_t r1, int prow, int *nrows_out) {
+  const int64_t nchunks = (r1 - r0) / CHUNK;
+  const int grid = persistent_grid(ctx, nchunks);
+  const int kpad = (k + KT) & ~(KT - 1);
+  const size_t smem = sizeof(double) * (NT / 32) * kpad;
+  const int pstride = kMaxK + 8;
+  cudaSetDevice(ctx->device);
+  ProfScope ps(ctx, PC_MULTIDOT, 8.0 * (double)(r1 - r0) * (k + 2));
+  multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V + r0, ld, k, w + r0, W + r0, nchunks,
+                                                         ctx->partial_d + (size_t)prow * pstride, pstride);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  *nrows_out = grid;
+  return NSB_OK;
+}
+
 int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *w,
                     const double *W, int64_t ndot, double *h_d, bool with_norm, double *hsum_d,
                     int64_t nalg = -1) {
@@ -999,6 +1019,65 @@ int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm
 }  // namespace
 
 namespace nsb {
+// Host vector -> column col_w in row chunks on the copy stream; the first projection
+// h1 = V_k^T (W o w) of every chunk starts as soon as that chunk has landed, so the H2D transfer
+// of f (the output of the host's matvec) overlaps the first sweep over the basis.
+int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k) {
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = L->ctx;
+  cudaSetDevice(ctx->device);
+  const int C = 8;
+  const int S = kMaxK + 8;
+  double *w = B->col(col_w);
+  double *h1 = ctx->hvec_d;
+  NSB_CHECK(ensure_partial(ctx, (int64_t)(C + 1) * ctx->num_sms * 2));
+  while ((int)ctx->chunk_ev.size() < C + 1) {
+    cudaEvent_t e;
+    NSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(e);
+  }
+  // the copy stream starts after everything already queued on the compute stream (column reuse)
+  NSB_CUDA(cudaEventRecord(ctx->chunk_ev[C], ctx->stream));
+  NSB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[C], 0));
+  ctx->hpin[3 * S + 8] = time;
+  const int64_t nchk = L->ndot / CHUNK;              // 1024-row chunks of the inner-product prefix
+  int prow = 0;
+  for (int c = 0; c < C; ++c) {
+    const int64_t r0 = (nchk * c / C) * CHUNK;
+    const int64_t r1 = (c == C - 1) ? L->ld : (nchk * (c + 1) / C) * CHUNK;   // last chunk: rest of the column
+    for (int f = 0; f < L->nfields; ++f) {
+      const int64_t a = std::max<int64_t>(L->off[f], r0), b = std::min<int64_t>(L->off[f] + L->len[f], r1);
+      if (b <= a) continue;
+      if (fields[f])
+        NSB_CUDA(cudaMemcpyAsync(w + a, fields[f] + (a - L->off[f]), sizeof(double) * (b - a), cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+      else
+        NSB_CUDA(cudaMemsetAsync(w + a, 0, sizeof(double) * (b - a), ctx->copy_stream));
+    }
+    if (L->time_row >= r0 && L->time_row < r1)
+      NSB_CUDA(cudaMemcpyAsync(w + L->time_row, ctx->hpin + 3 * S + 8, sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+    NSB_CUDA(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    NSB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+    const int64_t d1 = std::min<int64_t>(r1, L->ndot);
+    if (k > 0 && d1 > r0) {
+      int nr = 0;
+      NSB_CHECK(launch_multidot_rows(ctx, B->v_d, L->ld, k, w, L->w_d, r0, d1, prow, &nr));
+      prow += nr;
+    }
+  }
+  if (k > 0) {
+    ProfScope ps(ctx, PC_SMALL, 8.0 * prow * k);
+    reduce_partials_kernel<<<(k * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, prow, S, k, h1, 0, nullptr);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, k));
+    ctx->h1_ready_k = k;      // the next CGS2 orthonormalisation of this column skips its first sweep
+    ctx->h1_ready_col = w;
+  }
+  return NSB_OK;
+}
+
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d) {
   nsb_layout_t L = b->lay;
   NSB_CHECK(launch_multidot(L->ctx, b->v_d, L->ld, k, w_col_d, L->w_d, L->ndot, h_d, false, nullptr));
@@ -1018,6 +1097,11 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
   const double *V = B->v_d;
   cudaSetDevice(ctx->device);
   int passes = 2;
+  struct ClearH1 {   // the pipelined h1 is valid for exactly one orthonormalisation
+    nsb_context_t c;
+    ~ClearH1() { c->h1_ready_k = -1; c->h1_ready_col = nullptr; }
+  } clear_h1{ctx};
+  if (k == 0 || mode == NSB_ORTH_MGS2_REF) { ctx->h1_ready_k = -1; }
   auto add_into = [&](double *dst, const double *src, int n) -> int {
     if (n <= 0) return NSB_OK;
     add_vec_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dst, src, n);
@@ -1045,9 +1129,13 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
   } else {
     const bool dgks = (mode == NSB_ORTH_DGKS);
     const bool fused = fused_rows(k) != 0 && !ctx->no_fused;
-    // pass 1 (the norm of the incoming w rides along for the DGKS test)
-    NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr, L->ndof_dot + 1));
-    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, dgks ? k + 1 : k));
+    // pass 1 (the norm of the incoming w rides along for the DGKS test); already done chunk by chunk
+    // during the upload when the vector came from the host (upload_multidot_pipelined)
+    const bool have_h1 = !dgks && ctx->h1_ready_k == k && ctx->h1_ready_col == w;
+    if (!have_h1) {
+      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr, L->ndof_dot + 1));
+      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, dgks ? k + 1 : k));
+    }
     NSB_CUDA(cudaMemcpyAsync(hsum, h1, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
     if (fused) {
       // w -= V h1 and h2 = V^T W w in one sweep over V (h2[k] = ||w'||^2 for the DGKS test)
