@@ -725,6 +725,106 @@ inline size_t fused_tma_reg_smem(int k, int nj) {
   return sizeof(double) * (2 * kst * 64 + 2 * 8 * nj + 8) + sizeof(double2) * (8 * 32 + 32) + 32;
 }
 
+// Large-k variant (209 <= k <= 440): 32-row blocks, 16 warps (512 threads), lane = one row,
+// warp c owns the columns j = c (mod 16); otherwise identical to fused_tma_reg_kernel.
+template <int NJ, bool WITH_NORM>
+__global__ void __launch_bounds__(512, 1)
+fused_tma_reg32_kernel(int k, const double *__restrict__ h1, double *__restrict__ w,
+                       const double *__restrict__ W, int64_t nblocks, int64_t ndot_blocks,
+                       double *__restrict__ partial, int pstride, const __grid_constant__ CUtensorMap tmap,
+                       int kbox, int nbox) {
+  constexpr int RC = 32, NW = 16, NTH = 512;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int kst = kbox * nbox;
+  double *sV0 = reinterpret_cast<double *>(smem_raw);            // 2 x [kst][RC]
+  double *accS = sV0 + 2 * (size_t)kst * RC;                     // [NW * NJ] (+ norm)
+  double *hS = accS + NW * NJ + 8;                               // [NW * NJ]
+  double *sP = hS + NW * NJ;                                     // [NW][32]
+  double *sWW = sP + NW * 32;                                    // [32]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sWW + 32);        // [2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < NW * NJ + 8; j += NTH) accS[j] = 0.0;
+  for (int j = tid; j < NW * NJ; j += NTH) hS[j] = j < k ? h1[j] : 0.0;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+  }
+  __syncthreads();
+  double nrm = 0.0;
+  uint32_t phase_bits = 0;
+  auto issue = [&](int64_t blk, int stage) {
+    if (tid == 0) {
+      double *dst = sV0 + (size_t)stage * kst * RC;
+      mbar_expect_tx(bar + stage, (uint32_t)(kst * RC * sizeof(double)));
+      for (int b = 0; b < nbox; ++b)
+        tma_load_2d(dst + (size_t)b * kbox * RC, &tmap, (int)(blk * RC), b * kbox, bar + stage);
+    }
+  };
+  int stage = 0;
+  int64_t blk = blockIdx.x;
+  if (blk < nblocks) issue(blk, 0);
+  for (; blk < nblocks; blk += gridDim.x, stage ^= 1) {
+    const int64_t r = blk * RC + lane;
+    const int64_t nxt = blk + gridDim.x;
+    if (nxt < nblocks) issue(nxt, stage ^ 1);
+    const double *sV = sV0 + (size_t)stage * kst * RC;
+    const bool in_dot = blk < ndot_blocks;
+    double wv = 0.0, Wv = 0.0;
+    if (warp == 0) {
+      wv = w[r];
+      if (in_dot) Wv = ld_stream1(W + r);
+    }
+    mbar_wait(bar + stage, (phase_bits >> stage) & 1u);
+    phase_bits ^= 1u << stage;
+    double v[NJ];
+    double a = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = warp + NW * jj;
+      v[jj] = j < kst ? sV[(size_t)j * RC + lane] : 0.0;
+      a = fma(v[jj], hS[j], a);
+    }
+    sP[warp * 32 + lane] = a;
+    __syncthreads();
+    if (warp == 0) {
+      double s = sP[lane];
+#pragma unroll
+      for (int c = 1; c < NW; ++c) s += sP[c * 32 + lane];
+      wv -= s;
+      w[r] = wv;
+      const double ww = Wv * wv;
+      sWW[lane] = ww;
+      if (WITH_NORM) nrm += ww * wv;
+    }
+    __syncthreads();
+    if (in_dot) {
+      const double ww = sWW[lane];
+#pragma unroll
+      for (int j0 = 0; j0 < NJ; j0 += KT) {
+        double a8[KT];
+#pragma unroll
+        for (int c = 0; c < KT; ++c) a8[c] = (j0 + c < NJ) ? v[(j0 + c < NJ) ? j0 + c : 0] * ww : 0.0;
+        const double red = warp_reduce8(a8, lane);
+        const int jj = j0 + (lane >> 2);
+        if ((lane & 3) == 0 && jj < NJ) accS[warp + NW * jj] += red;
+      }
+    }
+  }
+  if (WITH_NORM) {
+    nrm = warp_reduce_sum(nrm);
+    if (tid == 0) accS[NW * NJ] = nrm;
+  }
+  __syncthreads();
+  for (int j = tid; j < k; j += NTH) partial[(size_t)blockIdx.x * pstride + j] = accS[j];
+  if (WITH_NORM && tid == 0) partial[(size_t)blockIdx.x * pstride + k] = accS[NW * NJ];
+}
+
+inline size_t fused_tma_reg32_smem(int k, int nj) {
+  const int nbox = (k + 255) / 256, kbox = (k + nbox - 1) / nbox;
+  const size_t kst = (size_t)kbox * nbox;
+  return sizeof(double) * (2 * kst * 32 + 2 * 16 * nj + 8 + 16 * 32 + 32) + 32;
+}
+
 inline void fused_boxes(int k, int *kbox, int *nbox) {
   *nbox = (k + 255) / 256;
   *kbox = (k + *nbox - 1) / *nbox;
@@ -953,6 +1053,49 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
     NSB_CUDA(cudaGetLastError());
     return NSB_OK;
   }
+  if (ctx->fused_loader == 3 && k > 8 * 26 && k <= 16 * 28 &&
+      fused_tma_reg32_smem(k, (k + 15) / 16) <= 226 * 1024) {
+    const int64_t nblocks = nrows / 32, ndot_blocks = ndot / 32;
+    const int njr = (k + 15) / 16;
+    const int nj = njr <= 16 ? 16 : njr <= 20 ? 20 : njr <= 24 ? 24 : 28;
+    const size_t smem = fused_tma_reg32_smem(k, nj);
+    int kbox, nbox;
+    fused_boxes(k, &kbox, &nbox);
+    CUtensorMap tmap;
+    NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, 32, kbox));
+    const int grid = (int)(nblocks < ctx->num_sms ? nblocks : ctx->num_sms);
+    const int pstride = kMaxK + 8;
+    NSB_CHECK(ensure_partial(ctx, grid));
+    cudaSetDevice(ctx->device);
+    {
+      ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+#define LAUNCH_T32B(NJ, NORM)                                                                            \
+  do {                                                                                                   \
+    NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg32_kernel<NJ, NORM>,                                      \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    fused_tma_reg32_kernel<NJ, NORM><<<grid, 512, smem, ctx->stream>>>(k, h1_d, w, W, nblocks, ndot_blocks, \
+                                                                      ctx->partial_d, pstride, tmap, kbox, nbox); \
+  } while (0)
+#define LAUNCH_T32(NJ) do { if (with_norm) LAUNCH_T32B(NJ, true); else LAUNCH_T32B(NJ, false); } while (0)
+      switch (nj) {
+        case 16: LAUNCH_T32(16); break;
+        case 20: LAUNCH_T32(20); break;
+        case 24: LAUNCH_T32(24); break;
+        default: LAUNCH_T32(28); break;
+      }
+#undef LAUNCH_T32
+#undef LAUNCH_T32B
+    }
+    const int kout = with_norm ? k + 1 : k;
+    {
+      ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
+      reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
+                                                                               kout, h2_d, 0, nullptr);
+    }
+    ctx->launches += 2;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
   int rc = fused_rows(k);
   NSB_REQUIRE(rc != 0, "fused update+dot: k=%d does not fit in shared memory", k);
   if (ctx->fused_rc && fused_smem_bytes(ctx->fused_rc, k) <= 226 * 1024) rc = ctx->fused_rc;
@@ -1128,7 +1271,9 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
   } else {
     const bool dgks = (mode == NSB_ORTH_DGKS);
-    const bool fused = fused_rows(k) != 0 && !ctx->no_fused;
+    const bool fused = !ctx->no_fused &&
+                       (fused_rows(k) != 0 || (ctx->fused_loader == 3 && k > 8 * 26 && k <= 16 * 28 &&
+                                               fused_tma_reg32_smem(k, (k + 15) / 16) <= 226 * 1024));
     // pass 1 (the norm of the incoming w rides along for the DGKS test); already done chunk by chunk
     // during the upload when the vector came from the host (upload_multidot_pipelined)
     const bool have_h1 = !dgks && ctx->h1_ready_k == k && ctx->h1_ready_col == w;

@@ -26,14 +26,14 @@ def build_basis(P, c, k):
     return Q
 
 
-@pytest.mark.parametrize('k', [1, 3, 8, 9, 17, 40, 54, 61, 100, 131, 208, 209, 260])
+@pytest.mark.parametrize('k', [1, 3, 8, 9, 17, 40, 54, 61, 100, 131, 208, 209, 260, 400, 450])
 @pytest.mark.parametrize('mode', ['cgs2', 'mgs2', 'dgks'])
 def test_orthonormalize_matches_mgs2(ctx, k, mode):
     import nekstab_next_b200 as nb
     if mode == 'mgs2' and k > 100:
         pytest.skip('literal column-by-column mode: covered up to k = 100')
     # k in {54..208} runs the TMA + register-retention kernel, k <= 53 the shared-memory variant,
-    # k >= 209 the unfused multidot / update pair
+    # 209..~420 the 32-row / 16-warp variant, larger k the unfused multidot / update pair
     P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, pressure=True, time_in_dot=True, seed=10 + k)
     c = P.octx()
     lay, B, semg, op = P.gpu(ctx, k + 1)
