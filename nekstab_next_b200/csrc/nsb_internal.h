@@ -79,6 +79,7 @@ struct nsb_context_s {
   bool ax_generic = false;     // NSB_AX_GENERIC=1: use the generic-order axhelm kernel for N = 7 too
   bool rotate_simple = false;  // NSB_ROTATE_SIMPLE=1: first (untiled) rotation kernel
   int ax_stages = 3;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernel (3: D row/column cached in registers)
+  bool ax_dmma = true;         // NSB_AX_DMMA=0: vector-FMA contraction in the ring kernel instead of DMMA
   bool ax_ring = true;         // NSB_AX_RING=0: warp-per-element kernel instead of the TMA ring (N = 7)
   bool prof = false;
   struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes; };

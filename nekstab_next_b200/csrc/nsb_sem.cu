@@ -567,6 +567,192 @@ axhelm3d_ring8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
   }
 }
 
+// D (8x8, fp64) += A (8x4) * B (4x8) on the fp64 tensor cores (SASS: DMMA.884).  Fragments per lane
+// (g = lane / 4, t = lane % 4): a = A[g][t], b = B[t][g], d = {D[g][2t], D[g][2t+1]}.
+__device__ __forceinline__ void dmma884(double2 &d, double a, double b) {
+  double d0 = d.x, d1 = d.y;
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+  d.x = d0;
+  d.y = d1;
+}
+
+// ---- axhelm, 3-D, N = 7: TMA ring + fp64 tensor-core contraction -------------------------------
+// ncu on the ring kernel above: DRAM 35 %, shared pipe 87 % -- the r/s contractions read D rows and
+// plane values from shared memory for every FMA.  BASELINE.json's north-star allows fp64 tensor
+// cores exactly in this case.  Each 8x8 plane contraction becomes two DMMA m8n8k4; the only shared
+// traffic left is one 128-bit store and four 64-bit loads per plane matrix to change fragment
+// layout (plus the staged G1..G6, now read as 128-bit pairs).
+template <int NF, bool CONV, int EPI, int NSTAGE>
+__global__ void __launch_bounds__((NF * NSTAGE + 1) * 32, 1)
+axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
+                      const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
+                      const double *__restrict__ cv, double alpha, double beta,
+                      const double *__restrict__ bmask, int64_t fstride) {
+  constexpr int LX = 8, N2 = 64, N3 = 512, PS = 12, NCW = NF * NSTAGE;
+  constexpr int NARR = 6 + 2 + (CONV ? 3 : 0) + NF;       // arrays per stage: G1..G6, bm1, bmask, [C], u
+  constexpr int STAGE = NARR * N3;                        // doubles per stage
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stage0 = reinterpret_cast<double *>(smem_raw);
+  double *planes = stage0 + (size_t)NSTAGE * STAGE;       // [NCW][3][LX*PS]
+  double *sD = planes + NCW * 3 * LX * PS;                // [64] D_ab, then [64] D_ba
+  double *sDt = sD + 64;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sDt + 64);   // [NSTAGE]
+  uint64_t *empty = full + NSTAGE;                           // [NSTAGE]
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  if (tid < N2) {
+    const int a = tid / LX, b = tid % LX;
+    sD[a * LX + b] = c_D8[a * LX + b];
+    sDt[b * LX + a] = c_D8[a * LX + b];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NF);
+    }
+  }
+  __syncthreads();
+  const int64_t nit = (nel - blockIdx.x + gridDim.x - 1) / gridDim.x;   // elements of this CTA
+
+  if (wp == NCW) {
+    // ===== producer warp: one lane per array =====
+    for (int64_t it = 0; it < nit; ++it) {
+      const int s = (int)(it % NSTAGE);
+      const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+      mbar_wait(empty + s, ph ^ 1u);                       // fresh barrier: passes immediately
+      const int64_t e = blockIdx.x + it * gridDim.x;
+      double *dst = stage0 + (size_t)s * STAGE;
+      if (lane == 0) mbar_expect_tx(full + s, (uint32_t)(STAGE * sizeof(double)));
+      __syncwarp();
+      if (lane < NARR) {
+        const double *src;
+        if (lane < 6) src = g + (int64_t)lane * npts + e * N3;
+        else if (lane == 6) src = bm1 + e * N3;
+        else if (lane == 7) src = bmask + e * N3;
+        else if (CONV && lane < 11) src = cv + (int64_t)(lane - 8) * npts + e * N3;
+        else src = u + (int64_t)(lane - (CONV ? 11 : 8)) * fstride + e * N3;
+        tma_bulk_g2s(dst + lane * N3, src, N3 * sizeof(double), full + s);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps: stage = wp / NF, velocity component = wp % NF =====
+  // Plane matrices are handled TRANSPOSED, M~[j][i] = m(i,j), in the fragment layouts of
+  // mma.m8n8k4.f64 (gq = lane / 4, t = lane % 4):
+  //   C / accumulator : rows j = gq, columns i = 2t, 2t+1   -> the lane OWNS points (2t..2t+1, gq, k):
+  //                     two adjacent doubles in memory, so stage reads and the final store are 128-bit
+  //   A operand       : M~[gq][t] and M~[gq][4+t]   (two k-halves)
+  //   B operand       : M~[t][gq] and M~[4+t][gq]
+  // r-derivative  UR~ = U~ D^T   (A = U~,  B = D^T : lane constants D[gq][t], D[gq][4+t])
+  // s-derivative  US~ = D  U~    (A = D    : the same lane constants,  B = U~)
+  // transposed:   W~ += WR~ D  +  D^T WS~   (constants D[t][gq], D[4+t][gq])
+  // Layout changes C -> A / B go through a padded 8 x 12 plane per warp (conflict-free).
+  const int s = wp / NF, f = wp % NF;
+  const int gq = lane >> 2, t = lane & 3;
+  const int q = gq * LX + 2 * t;                              // in-plane offset of the lane's point pair
+  double *pu = planes + (size_t)wp * 3 * LX * PS, *pwr = pu + LX * PS, *pws = pwr + LX * PS;
+  const double *sG = stage0 + (size_t)s * STAGE;
+  const double *sB = sG + 6 * N3, *sM = sG + 7 * N3, *sC = sG + 8 * N3;
+  const double *sU = sG + (size_t)(8 + (CONV ? 3 : 0) + f) * N3;
+  double *wout = w + (int64_t)f * fstride;
+  const double dA0 = sD[gq * LX + t], dA1 = sD[gq * LX + 4 + t];     // D[gq][t], D[gq][4+t]
+  const double dB0 = sD[t * LX + gq], dB1 = sD[(4 + t) * LX + gq];   // D[t][gq], D[4+t][gq]
+  // element-boundary flags of the two points (i = 2t, 2t+1 ; j = gq)
+  const bool bj = (gq == 0 || gq == LX - 1);
+  const bool bx = bj || (2 * t == 0), by = bj || (2 * t + 1 == LX - 1);
+  for (int64_t it = s; it < nit; it += NSTAGE) {
+    const int64_t e = blockIdx.x + it * gridDim.x;
+    mbar_wait(full + s, (uint32_t)((it / NSTAGE) & 1));
+    // always 0, but opaque to the compiler: keeps the 64 D(k,l) constant loads inside the loop
+    // (hoisted out of it they occupy 128 registers and spill)
+    const int zoff = (int)(it >> 40);
+    double2 uk[LX], wk[LX];
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      uk[k] = *reinterpret_cast<const double2 *>(sU + k * N2 + q);
+      wk[k] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      *reinterpret_cast<double2 *>(pu + gq * PS + 2 * t) = uk[k];
+      __syncwarp();
+      const double a0 = pu[gq * PS + t], a1 = pu[gq * PS + 4 + t];       // A layout of U~
+      const double b0 = pu[t * PS + gq], b1 = pu[(4 + t) * PS + gq];     // B layout of U~
+      double2 ur = make_double2(0.0, 0.0), us = make_double2(0.0, 0.0);
+      dmma884(ur, a0, dA0);
+      dmma884(ur, a1, dA1);
+      dmma884(us, dA0, b0);
+      dmma884(us, dA1, b1);
+      double2 ut = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int l = 0; l < LX; ++l) {
+        const double dk = c_D8[k * LX + l + zoff];
+        ut.x = fma(dk, uk[l].x, ut.x);
+        ut.y = fma(dk, uk[l].y, ut.y);
+      }
+      const int p = k * N2 + q;
+      const double2 g1 = *reinterpret_cast<const double2 *>(sG + p), g2 = *reinterpret_cast<const double2 *>(sG + N3 + p),
+                    g3 = *reinterpret_cast<const double2 *>(sG + 2 * N3 + p),
+                    g4 = *reinterpret_cast<const double2 *>(sG + 3 * N3 + p),
+                    g5 = *reinterpret_cast<const double2 *>(sG + 4 * N3 + p),
+                    g6 = *reinterpret_cast<const double2 *>(sG + 5 * N3 + p);
+      double2 wr, ws, wt;
+      wr.x = h1 * (g1.x * ur.x + g4.x * us.x + g5.x * ut.x);
+      wr.y = h1 * (g1.y * ur.y + g4.y * us.y + g5.y * ut.y);
+      ws.x = h1 * (g2.x * us.x + g4.x * ur.x + g6.x * ut.x);
+      ws.y = h1 * (g2.y * us.y + g4.y * ur.y + g6.y * ut.y);
+      wt.x = h1 * (g3.x * ut.x + g5.x * ur.x + g6.x * us.x);
+      wt.y = h1 * (g3.y * ut.y + g5.y * ur.y + g6.y * us.y);
+      *reinterpret_cast<double2 *>(pwr + gq * PS + 2 * t) = wr;
+      *reinterpret_cast<double2 *>(pws + gq * PS + 2 * t) = ws;
+      __syncwarp();
+      double2 acc = make_double2(0.0, 0.0);
+      if (CONV) {
+        const double2 c1 = *reinterpret_cast<const double2 *>(sC + p), c2 = *reinterpret_cast<const double2 *>(sC + N3 + p),
+                      c3 = *reinterpret_cast<const double2 *>(sC + 2 * N3 + p);
+        acc.x = c1.x * ur.x + c2.x * us.x + c3.x * ut.x;
+        acc.y = c1.y * ur.y + c2.y * us.y + c3.y * ut.y;
+      }
+      const double ar0 = pwr[gq * PS + t], ar1 = pwr[gq * PS + 4 + t];   // A layout of WR~
+      const double bs0 = pws[t * PS + gq], bs1 = pws[(4 + t) * PS + gq]; // B layout of WS~
+      dmma884(acc, ar0, dB0);
+      dmma884(acc, ar1, dB1);
+      dmma884(acc, dB0, bs0);
+      dmma884(acc, dB1, bs1);
+#pragma unroll
+      for (int l = 0; l < LX; ++l) {
+        const double dk = c_D8[k * LX + l + zoff];
+        wk[l].x = fma(dk, wt.x, wk[l].x);
+        wk[l].y = fma(dk, wt.y, wk[l].y);
+      }
+      wk[k].x += acc.x;
+      wk[k].y += acc.y;
+    }
+    double *we = wout + e * N3;
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      const int p = k * N2 + q;
+      double2 v = wk[k];
+      if (h2 != 0.0) {
+        const double2 bm = *reinterpret_cast<const double2 *>(sB + p);
+        v.x = fma(h2 * bm.x, uk[k].x, v.x);
+        v.y = fma(h2 * bm.y, uk[k].y, v.y);
+      }
+      if (EPI == 1) {
+        const bool kb = (k == 0 || k == LX - 1);
+        const double2 mk = *reinterpret_cast<const double2 *>(sM + p);
+        if (!(bx || kb)) v.x = alpha * uk[k].x + beta * mk.x * v.x;
+        if (!(by || kb)) v.y = alpha * uk[k].y + beta * mk.y * v.y;
+      }
+      *reinterpret_cast<double2 *>(we + p) = v;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the stage
+  }
+}
+
 template <int NF, bool CONV, int NSTAGE>
 constexpr size_t ring8_smem() {
   return sizeof(double) * ((size_t)NSTAGE * (6 + 2 + (CONV ? 3 : 0) + NF) * 512 + NF * NSTAGE * 3 * 80 + 128) +
@@ -588,9 +774,34 @@ int launch_ring8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, dou
   return NSB_OK;
 }
 
+template <int NF, bool CONV, int EPI, int NSTAGE>
+int launch_dmma8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
+                   const double *cv, double alpha, double beta, const double *bmask) {
+  constexpr size_t smem = sizeof(double) * ((size_t)NSTAGE * (6 + 2 + (CONV ? 3 : 0) + NF) * 512 +
+                                            NF * NSTAGE * 3 * 96 + 128) + sizeof(uint64_t) * 2 * NSTAGE + 128;
+  static_assert(smem <= 227 * 1024, "axhelm dmma ring does not fit in shared memory");
+  auto kfn = axhelm3d_dmma8_kernel<NF, CONV, EPI, NSTAGE>;
+  NSB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = S->nel < S->ctx->num_sms ? S->nel : S->ctx->num_sms;
+  kfn<<<(unsigned)grid, (NF * NSTAGE + 1) * 32, smem, S->ctx->stream>>>(u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1,
+                                                                       h2, cv, alpha, beta, bmask, fstride);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+template <int NF, bool CONV, int EPI>
+int launch_dmma8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
+                 const double *cv, double alpha, double beta, const double *bmask) {
+  if (S->ctx->ax_stages == 2)
+    return launch_dmma8_s<NF, CONV, EPI, 2>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
+  return launch_dmma8_s<NF, CONV, EPI, 3>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
+}
+
 template <int NF, bool CONV, int EPI>
 int launch_ring8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
                  const double *cv, double alpha, double beta, const double *bmask) {
+  if (S->ctx->ax_dmma) return launch_dmma8<NF, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
   if (CONV || S->ctx->ax_stages == 3)
     return launch_ring8_s<NF, CONV, EPI, 3>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
   return launch_ring8_s<NF, CONV, EPI, CONV ? 3 : 4>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
@@ -785,11 +996,13 @@ int launch_axhelm(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstri
   // algorithmic bytes per point: u, w, G1..G6 (G1,G2,G4 in 2-D), bm1 if h2 != 0, C if convecting,
   // bmask on element-interior points of the fused epilogue
   const double fint = std::pow((double)(S->lx - 2) / S->lx, S->dim);
-  // SURVEY.md section 8d counts these bytes per component (64 n general + 8 n for the h2 B term);
-  // the ring kernel actually moves fewer because G, bm1, bmask and C are staged once per element
-  // and shared by the nf components (8 (8 + 2 nf) bytes per point instead of 8 * 10 nf).
+  // Algorithmic bytes of what is launched: the N = 7 ring kernels stage G, bm1, bmask and C once per
+  // element for all nf components, 8 (geo + 2 nf) bytes per point; the other kernels read them per
+  // component, 8 (geo + 2) nf.  (SURVEY.md section 8d's per-component figure, 64 n + 8 n for the
+  // h2 B term, would credit the ring kernels with about twice the bytes they move.)
+  const bool shared_geo = S->dim == 3 && S->lx == 8 && !S->ctx->ax_generic && S->ctx->ax_ring && nf <= 3;
   const double geo = 8.0 * (S->ng + (h2 != 0.0 ? 1 : 0) + (cv ? S->dim : 0) + (epi ? fint : 0.0));
-  const double per_pt = (geo + 16.0) * nf;
+  const double per_pt = shared_geo ? geo + 16.0 * nf : (geo + 16.0) * nf;
   ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts);
   if (S->dim == 3) {
     if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
