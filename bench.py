@@ -335,8 +335,15 @@ def run_native(a):
         kernels[name] = dict(ms=round(v['ms'], 3), launches=v['launches'], share=round(v['ms'] / tot, 4),
                              achieved_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
     dom = max(rep, key=lambda n: rep[n]['ms'])
+    # DRAM traffic / algorithmic bytes measured once with `ncu --set full` at k = 100
+    # (profiles/ncu_r01_final_kernels_k100.md): the sweeps move exactly their algorithmic bytes
+    ncu_ratio = dict(multidot=1.000, fused_update_dot=1.000, update=0.999)
+    traffic = (rep[dom]['bytes'] / rep[dom]['launches'] * ncu_ratio[dom]) if dom in ncu_ratio else None
     roofline = dict(bound='hbm', kernel=dom, achieved=kernels[dom]['achieved_gbs'], peak=peak, unit='GB/s',
-                    frac=kernels[dom]['frac'], traffic=None, peak_source=peak_src,
+                    frac=kernels[dom]['frac'], traffic=traffic,
+                    traffic_source='ncu dram read+write / algorithmic = %.3f at k=100, applied to the mean '
+                                   'algorithmic bytes per launch' % ncu_ratio[dom] if traffic else None,
+                    peak_source=peak_src,
                     avg_launch_ms=round(rep[dom]['ms'] / rep[dom]['launches'], 4),
                     algorithmic_bytes_per_launch=rep[dom]['bytes'] / rep[dom]['launches'],
                     share_of_step=kernels[dom]['share'], kernels=kernels,

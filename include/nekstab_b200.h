@@ -250,6 +250,10 @@ int nsb_op_create_sem(nsb_sem_t sem, int nfields_apply, double alpha, double bet
 typedef int (*nsb_host_matvec_fn)(void *user, const double *const *in_fields, double in_time,
                                   double **out_fields, double *out_time);
 int nsb_op_create_host(nsb_layout_t layout, nsb_host_matvec_fn fn, void *user, nsb_op_t *op);
+/* out = outer(inner(in)): the reference's composite maps are built this way from the basic solvers,
+ * e.g. transient_growth_map = adjoint_linearized_map(forward_linearized_map(q))
+ * (core/matvec.f90:478-495).  The component operators stay owned by the caller. */
+int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, nsb_op_t *op);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_op_count(nsb_op_t op, int64_t *napply);

@@ -421,6 +421,13 @@ def sem_operator(sem: Sem, nfields: int, alpha: float, beta: float, h1: float, h
     return LinearOperator(sem.lib, h, keep)
 
 
+def compose_operators(layout: Layout, outer: LinearOperator, inner: LinearOperator) -> LinearOperator:
+    """out = outer(inner(in)) -- e.g. transient_growth_map = adjoint(forward(q)) (core/matvec.f90:478-495)."""
+    h = C.c_void_p()
+    check(layout.lib.nsb_op_create_compose(layout.h, outer.h, inner.h, C.byref(h)))
+    return LinearOperator(layout.lib, h, keep=(outer, inner))
+
+
 def host_operator(layout: Layout, fn) -> LinearOperator:
     """Wrap a host matvec ``fn(fields_in, time_in) -> (fields_out, time_out)`` (the reference's
     time-stepper lives on the host); vectors cross PCIe around every call."""

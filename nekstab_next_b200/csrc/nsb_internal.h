@@ -148,7 +148,9 @@ struct nsb_sem_s {
 };
 
 struct nsb_op_s {
-  int kind = 0;                  // 0 sem, 1 host callback
+  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.))
+  nsb_op_t outer = nullptr, inner = nullptr;
+  nsb_basis_t tmp = nullptr;     // work vector of the composition
   nsb_sem_t sem = nullptr;
   int nfields_apply = 0;
   double alpha = 0, beta = 1, h1 = 1, h2 = 0;

@@ -200,7 +200,10 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
   NSB_REQUIRE(mend + 1 <= kMaxK, "nsb_arnoldi: Krylov dimension above %d", kMaxK);
   nsb_context_t ctx = Q->lay->ctx;
   const int nsteps = mend - mstart + 1;
-  const bool async = (orth_mode == NSB_ORTH_CGS2 || orth_mode == NSB_ORTH_MGS2_REF) && op->kind == 0;
+  // device-resident operators (SEM, or compositions of them) allow a factorisation without host syncs
+  bool dev_op = op->kind == 0;
+  if (op->kind == 2) dev_op = op->outer->kind == 0 && op->inner->kind == 0;
+  const bool async = (orth_mode == NSB_ORTH_CGS2 || orth_mode == NSB_ORTH_MGS2_REF) && dev_op;
   const size_t stride = (size_t)mend + 2;
   double *hbuf = nullptr;
   if (async) NSB_CHECK(nsb_host_alloc((void **)&hbuf, (int64_t)(sizeof(double) * stride * nsteps)));

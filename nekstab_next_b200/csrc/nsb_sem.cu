@@ -1442,8 +1442,27 @@ extern "C" int nsb_op_create_host(nsb_layout_t L, nsb_host_matvec_fn fn, void *u
   return NSB_OK;
 }
 
+// out = outer(inner(in)): the reference's composite maps -- transient_growth_map = adjoint(forward(q))
+// (core/matvec.f90:478-495), newton_linearized_map etc. are built this way from the basic solvers.
+extern "C" int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, nsb_op_t *out) {
+  NSB_REQUIRE(layout && outer && inner && out, "nsb_op_create_compose: NULL argument");
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 2;
+  op->lay = layout;
+  op->outer = outer;
+  op->inner = inner;
+  int r = nsb_basis_create(layout, 1, &op->tmp);
+  if (r != NSB_OK) {
+    delete op;
+    return r;
+  }
+  *out = op;
+  return NSB_OK;
+}
+
 extern "C" int nsb_op_destroy(nsb_op_t op) {
   if (!op) return NSB_OK;
+  if (op->tmp) nsb_basis_destroy(op->tmp);
   if (op->c_d) cudaFree(op->c_d);
   for (double *p : op->hin) cudaFreeHost(p);
   for (double *p : op->hout) cudaFreeHost(p);
@@ -1464,6 +1483,11 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
   NSB_REQUIRE(bin->lay == bout->lay, "nsb_op_apply: different layouts");
   NSB_REQUIRE(!(bin == bout && cin == cout), "nsb_op_apply: in-place application is not supported");
   op->napply++;
+  if (op->kind == 2) {
+    NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: composite operator built for another layout");
+    NSB_CHECK(nsb_op_apply(op->inner, bin, cin, op->tmp, 0));
+    return nsb_op_apply(op->outer, op->tmp, 0, bout, cout);
+  }
   if (op->kind == 1) {
     nsb_layout_t L = bin->lay;
     std::vector<const double *> pin(L->nfields);
