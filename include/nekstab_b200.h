@@ -175,6 +175,10 @@ int nsb_host_free(void *ptr);
  * core/eigensolvers.f90:335-345 in one pass. */
 int nsb_basis_gram(nsb_basis_t b, int k, double *G, int ldg);
 
+/* BM1-weighted QR of the first k columns, in place (X = Q R): qr_dec of BoostConv
+ * (core/fixedp.f90:331-385) on the same weighted Gram-Schmidt kernels; R is k x k upper triangular
+ * (ldr).  Columns with residual norm^2 < 1e-60 are zeroed with R(j,j) = 1, like the reference. */
+int nsb_basis_qr(nsb_basis_t b, int k, int orth_mode, double *R, int ldr);
 /* dq = sum_i y_i Q_i: k_matmul (core/krylov_subspace.f90:163-209), Ritz vectors
  * (core/eigensolvers.f90:565-574, one call for Re and one for Im coefficients). */
 int nsb_basis_gemv(nsb_basis_t b, int k, const double *y, nsb_basis_t bout, int col_out);

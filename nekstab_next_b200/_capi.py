@@ -63,6 +63,7 @@ PROTOTYPES = {
     'nsb_host_alloc': (C.c_int, [c_void_pp, C.c_int64]),
     'nsb_host_free': (C.c_int, [C.c_void_p]),
     'nsb_basis_gram': (C.c_int, [H, C.c_int, c_double_p, C.c_int]),
+    'nsb_basis_qr': (C.c_int, [H, C.c_int, C.c_int, c_double_p, C.c_int]),
     'nsb_basis_gemv': (C.c_int, [H, C.c_int, c_double_p, H, C.c_int]),
     'nsb_basis_rotate': (C.c_int, [H, C.c_int, c_double_p, C.c_int, C.c_int]),
     'nsb_gll': (C.c_int, [C.c_int, c_double_p, c_double_p, c_double_p]),

@@ -210,6 +210,12 @@ class Basis:
         check(self.lib.nsb_basis_gram(self.h, k, _dp(G), k))
         return G
 
+    def qr(self, k: int, mode: int = ORTH_CGS2) -> np.ndarray:
+        """In-place BM1-weighted QR of the first k columns (qr_dec, core/fixedp.f90:331-385); returns R."""
+        R = np.zeros((k, k), order='F')
+        check(self.lib.nsb_basis_qr(self.h, k, mode, _dp(R), k))
+        return R
+
     def rotate(self, k: int, Z: np.ndarray, rotate_time: bool = False):
         Zf = np.asfortranarray(Z, dtype=np.float64)
         check(self.lib.nsb_basis_rotate(self.h, k, _dp(Zf), Zf.shape[0], int(rotate_time)))

@@ -272,6 +272,31 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// BM1-weighted QR of the first k columns, in place: qr_dec of BoostConv (core/fixedp.f90:331-385),
+// the same weighted Gram-Schmidt kernels as the Arnoldi orthogonalisation.  X = Q R, R upper
+// triangular (k x k, ldr).  A column whose residual norm^2 is below 1e-60 is zeroed and gets
+// R(j,j) = 1, as in the reference (:371-374).
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_basis_qr(nsb_basis_t B, int k, int orth_mode, double *R, int ldr) {
+  NSB_REQUIRE(B && R && k >= 1 && k <= B->ncols && ldr >= k, "nsb_basis_qr: bad argument");
+  std::vector<double> h(k + 1);
+  for (int j = 0; j < k; ++j) {
+    for (int i = 0; i < k; ++i) R[(size_t)j * ldr + i] = 0.0;
+    int rc = nsb_orthonormalize(B, j, j, orth_mode, h.data(), nullptr);
+    if (rc == NSB_ENAN && !(h[j] * h[j] >= 1e-60)) rc = NSB_OK;   // 0/0 from a vanishing column
+    NSB_CHECK(rc);
+    for (int i = 0; i < j; ++i) R[(size_t)j * ldr + i] = h[i];
+    if (!(h[j] * h[j] >= 1e-60)) {
+      NSB_CHECK(nsb_vec_zero(B, j));
+      R[(size_t)j * ldr + j] = 1.0;
+    } else {
+      R[(size_t)j * ldr + j] = h[j];
+    }
+  }
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Krylov-Schur  (core/eigensolvers.f90:120-359, 363-468)
 // ------------------------------------------------------------------------------------------------
 extern "C" int nsb_schur_condensation(nsb_basis_t Q, int *mstart, double *H, int ldh, int ksize,

@@ -363,3 +363,31 @@ def op_add_noise(coords, if3d=True):
     for c in range(3 if if3d else 2):
         out.append(mth_rand(ix, iy, iz, ieg, coords, NOISE_FC[c], if3d) + np.zeros_like(x))
     return out
+
+
+# ----------------------------------------------------------------------------
+# BM1-weighted QR of BoostConv  (core/fixedp.f90:331-385)
+# ----------------------------------------------------------------------------
+def qr_dec(bm1, X):
+    """X: list of KVec (velocity fields only).  Single-pass MGS with the bm1 weight; returns Q (list of
+    KVec) and rr (k x k) exactly as the reference loops do (norm^2 < 1e-60 -> zero column, rr(j,j) = 1)."""
+    k = len(X)
+    ctx = Ctx(bm1s=bm1, in_dot=[True] * len(X[0].f))
+    rr = np.zeros((k, k))
+    Q = []
+    for j in range(k):
+        dum = X[j].copy()
+        for i in range(j):
+            rr[i, j] = k_dot(ctx, dum, Q[i])
+            t = Q[i].copy()
+            k_cmult(t, rr[i, j])
+            k_sub2(dum, t)
+        norma = k_dot(ctx, dum, dum)
+        if norma < 1e-60:
+            norma = 1.0
+            dum = k_zero_like(dum)
+        else:
+            k_cmult(dum, 1.0 / math.sqrt(norma))
+        Q.append(dum)
+        rr[j, j] = math.sqrt(norma)
+    return Q, rr

@@ -101,3 +101,27 @@ def test_gemv_and_rotate(ctx):
         assert got.time == Q[j].time
     got = download(B[k])   # column k untouched
     assert np.array_equal(got.f[0], Q[k].f[0].ravel())
+
+
+def test_weighted_qr_matches_qr_dec(ctx):
+    """nsb_basis_qr vs the literal qr_dec of BoostConv (core/fixedp.f90:331-385)."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=3, seed=31)
+    k = 9
+    lay, B, semg, op = P.gpu(ctx, k)
+    X = [P.random_kvec() for _ in range(k)]
+    X[5] = okr.k_zero_like(X[0])               # a vanishing snapshot: zero column, rr(j,j) = 1
+    for i, x in enumerate(X):
+        upload(B[i], x)
+    Qo, rro = okr.qr_dec(P.bm1, [x.copy() for x in X])
+    R = B.qr(k)
+    assert np.allclose(np.tril(R, -1), 0.0) and R[5, 5] == 1.0
+    assert np.max(np.abs(R - rro)) <= 1e-11 * np.max(np.abs(rro))
+    for j in range(k):
+        got = download(B[j])
+        for a, b in zip(got.f, Qo[j].f):
+            assert np.max(np.abs(a - b.ravel())) <= 1e-11 * max(np.max(np.abs(b)), 1.0)
+    # X = Q R
+    for j in range(k):
+        rec = sum(R[i, j] * download(B[i]).f[0] for i in range(j + 1))
+        assert np.max(np.abs(rec - X[j].f[0].ravel())) <= 1e-11 * max(np.max(np.abs(X[j].f[0])), 1.0)
