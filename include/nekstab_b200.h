@@ -236,6 +236,13 @@ int nsb_sem_col2(nsb_sem_t sem, nsb_basis_t b, int col, int field, int which);
 int nsb_sem_ax(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout, int field,
                double h1, double h2);
 
+/* Jacobi-preconditioned conjugate gradients for (h1 A + h2 B) x = rhs on one field: Nek5000's
+ * hmholtz/cggo with setprec ([UPSTREAM-RECALL]; the solve nek_advance runs per velocity component,
+ * SURVEY.md section 8 f-3), i.e. the loop {axhelm, dssum, mask, glsc3 with vmult}.  Stops when the
+ * preconditioned residual norm sqrt((r, D r)_mult) has dropped by `tol` or after maxit iterations. */
+int nsb_sem_hmholtz(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field,
+                    double h1, double h2, double tol, int maxit, int *iters, double *res);
+
 /* ---------------------------------------------------------------------------------------------
  * Linear operator: the abstract_linop%matvec(vec_in, vec_out) boundary
  * (core/linear_operators.f90:17-23, 39-44) / legacy matvec(f, q) (core/matvec.f90:56).

@@ -383,6 +383,14 @@ class Sem:
     def col2(self, v: nek_dvector, field: int, which: str):
         check(self.lib.nsb_sem_col2(self.h, v.basis.h, v.col, field, self.SEL[which]))
 
+    def hmholtz(self, rhs: nek_dvector, x: nek_dvector, field: int, h1: float, h2: float, tol: float = 1e-10,
+                maxit: int = 500):
+        """Jacobi-PCG solve of (h1 A + h2 B) x = rhs (Nek's hmholtz/cggo); returns (iterations, residual drop)."""
+        it, res = C.c_int(), C.c_double()
+        check(self.lib.nsb_sem_hmholtz(self.h, rhs.basis.h, rhs.col, x.basis.h, x.col, field, h1, h2, tol, maxit,
+                                       C.byref(it), C.byref(res)))
+        return it.value, res.value
+
     def ax(self, vin: nek_dvector, vout: nek_dvector, field: int, h1: float, h2: float):
         check(self.lib.nsb_sem_ax(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col, field, h1, h2))
 

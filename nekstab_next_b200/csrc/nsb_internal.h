@@ -144,6 +144,7 @@ struct nsb_sem_s {
   std::vector<Peer> peers;
   std::vector<int64_t> glo_h;    // kept for exchange setup
   bool exchange_ready = false;
+  double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z, d)
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
 };
 

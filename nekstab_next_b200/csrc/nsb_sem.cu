@@ -16,6 +16,12 @@
 
 using namespace nsb;
 
+namespace nsb {
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nblk, int pstride, int k,
+                                       double *__restrict__ out, int accumulate_into, double *__restrict__ out2);
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // GLL quadrature (host)
 // ------------------------------------------------------------------------------------------------
@@ -1314,6 +1320,7 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
     if (p) cudaFree(p);
   if (S->gs_off_d) cudaFree(S->gs_off_d);
   if (S->gs_idx_d) cudaFree(S->gs_idx_d);
+  if (S->pcg_d) cudaFree(S->pcg_d);
   if (S->ev_a) cudaEventDestroy(S->ev_a);
   if (S->ev_b) cudaEventDestroy(S->ev_b);
   delete S;
@@ -1381,6 +1388,148 @@ extern "C" int nsb_sem_ax(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t bou
   NSB_CHECK(nsb_sem_axhelm(S, bin, cin, bout, cout, field, h1, h2));
   NSB_CHECK(nsb_sem_dssum(S, bout, cout, field));
   return nsb_sem_col2(S, bout, cout, field, 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobi-preconditioned conjugate gradients for the Helmholtz problem (h1 A + h2 B) x = rhs:
+// [UPSTREAM-RECALL] Nek5000 hmholtz.f `cggo` + `setprec`, the solver nek_advance runs for every
+// velocity component of every time step.  It is the loop
+// { axhelm -> dssum -> mask -> glsc3 } built from the kernels above; inner products carry the
+// inverse multiplicity (`mult` = vmult) so that duplicated nodes count once.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// diagonal of h1 A + h2 B per local point (no cross terms, like setprec away from deformed boundaries)
+__global__ void helm_diag_kernel(const double *__restrict__ g, const double *__restrict__ bm1,
+                                 const double *__restrict__ D, int dim, int lx, int64_t npts, double h1, double h2,
+                                 double *__restrict__ diag) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  int nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  const int64_t e0 = p / nloc * nloc;
+  const int loc = (int)(p - e0);
+  const int i = loc % lx, j = (loc / lx) % lx, k = dim == 3 ? loc / (lx * lx) : 0;
+  double s = 0.0;
+  for (int q = 0; q < lx; ++q) {
+    const double di = D[q + lx * i], dj = D[q + lx * j];           // D(q,i), D(q,j)
+    s += di * di * g[0 * npts + e0 + q + lx * (j + lx * k)];
+    s += dj * dj * g[1 * npts + e0 + i + lx * (q + lx * k)];
+    if (dim == 3) {
+      const double dk = D[q + lx * k];
+      s += dk * dk * g[2 * npts + e0 + i + lx * (j + lx * q)];
+    }
+  }
+  diag[p] = h1 * s + h2 * bm1[p];
+}
+
+// generic weighted dot partials: sum a b c
+__global__ void __launch_bounds__(256) dot3_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                                   const double *__restrict__ c, int64_t n,
+                                                   double *__restrict__ partial) {
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) acc = fma(a[t] * b[t], c[t], acc);
+  acc = block_reduce_sum<256>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// x += alpha p ; r -= alpha w ; z = d r ; partial += r z mult     (one pass over five vectors)
+__global__ void __launch_bounds__(256) pcg_update_kernel(double *__restrict__ x, double *__restrict__ r,
+                                                         double *__restrict__ z, const double *__restrict__ p,
+                                                         const double *__restrict__ w, const double *__restrict__ d,
+                                                         const double *__restrict__ mult, double alpha, int64_t n,
+                                                         double *__restrict__ partial) {
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    x[t] = fma(alpha, p[t], x[t]);
+    const double rv = fma(-alpha, w[t], r[t]);
+    r[t] = rv;
+    const double zv = d[t] * rv;
+    z[t] = zv;
+    acc = fma(rv * zv, mult[t], acc);
+  }
+  acc = block_reduce_sum<256>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void pcg_p_kernel(double *__restrict__ p, const double *__restrict__ z, double beta, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) p[t] = fma(beta, p[t], z[t]);
+}
+
+int reduce_scalar(nsb_context_t ctx, int nblk, double *out_host, bool allreduce) {
+  double *out_d = ctx->hvec_d + 3 * (kMaxK + 8) + 16;
+  reduce_partials_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partial_d, nblk, 1, 1, out_d, 0, nullptr);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  if (allreduce && ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, out_d, 1));
+  NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 16, out_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out_host = ctx->hpin[16];
+  return NSB_OK;
+}
+
+}  // namespace
+
+extern "C" int nsb_sem_hmholtz(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field,
+                               double h1, double h2, double tol, int maxit, int *iters, double *res) {
+  double *f, *x;
+  NSB_CHECK(field_ptr(S, brhs, crhs, field, &f, "nsb_sem_hmholtz"));
+  NSB_CHECK(field_ptr(S, bx, cx, field, &x, "nsb_sem_hmholtz"));
+  NSB_REQUIRE(f != x && maxit >= 1, "nsb_sem_hmholtz: bad argument");
+  NSB_REQUIRE(S->exchange_ready, "nsb_sem_hmholtz: call nsb_sem_setup_exchange first");
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int64_t n = S->npts;
+  const size_t nb = sizeof(double) * n;
+  if (!S->pcg_d) NSB_CUDA(cudaMalloc(&S->pcg_d, nb * 5));
+  double *r = S->pcg_d, *p = r + n, *w = p + n, *z = w + n, *d = z + n;
+  const int grid = ctx->num_sms * 8;
+  NSB_CHECK(ensure_partial(ctx, grid));
+  // setprec: d = mask / dssum(diag)
+  helm_diag_kernel<<<blocks_for(n), 256, 0, st>>>(S->g_d, S->bm1_d, S->D_d, S->dim, S->lx, n, h1, h2, d);
+  ctx->launches++;
+  NSB_CHECK(launch_gs(S, d, 1, 0, 0, nullptr, 0, 0, nullptr));
+  recip_kernel<<<grid, 256, 0, st>>>(d, n);
+  col2_kernel<<<grid, 256, 0, st>>>(d, S->mask_d, n);
+  ctx->launches += 2;
+  NSB_CUDA(cudaMemsetAsync(x, 0, nb, st));
+  NSB_CUDA(cudaMemsetAsync(p, 0, nb, st));
+  NSB_CUDA(cudaMemcpyAsync(r, f, nb, cudaMemcpyDeviceToDevice, st));
+  col2_kernel<<<grid, 256, 0, st>>>(r, S->mask_d, n);           // the right-hand side lives in the masked space
+  mul3_kernel<<<grid, 256, 0, st>>>(z, d, r, n);                // z = D r
+  dot3_kernel<<<grid, 256, 0, st>>>(r, z, S->vmult_d, n, ctx->partial_d);
+  ctx->launches += 3;
+  double rtz1 = 0.0, rtz2 = 1.0, rho = 0.0, r0 = -1.0, rn = 0.0;
+  NSB_CHECK(reduce_scalar(ctx, grid, &rtz1, true));
+  int it = 0;
+  for (it = 1; it <= maxit; ++it) {
+    const double beta = it == 1 ? 0.0 : rtz1 / rtz2;
+    pcg_p_kernel<<<grid, 256, 0, st>>>(p, z, beta, n);                                   // p = z + beta p
+    ctx->launches++;
+    NSB_CHECK(launch_axhelm(S, p, w, 1, 0, h1, h2, nullptr, 0, 0, 0, nullptr));          // w = H p
+    NSB_CHECK(launch_gs(S, w, 1, 0, 0, nullptr, 0, 0, nullptr));                          // dssum
+    col2_kernel<<<grid, 256, 0, st>>>(w, S->mask_d, n);                                   // mask
+    dot3_kernel<<<grid, 256, 0, st>>>(w, p, S->vmult_d, n, ctx->partial_d);               // rho = (w, p)
+    ctx->launches += 2;
+    NSB_CHECK(reduce_scalar(ctx, grid, &rho, true));
+    if (!(rho > 0.0)) break;                                                              // converged to round-off / singular
+    const double alpha = rtz1 / rho;
+    pcg_update_kernel<<<grid, 256, 0, st>>>(x, r, z, p, w, d, S->vmult_d, alpha, n, ctx->partial_d);
+    ctx->launches++;
+    rtz2 = rtz1;
+    NSB_CHECK(reduce_scalar(ctx, grid, &rtz1, true));
+    // convergence on the preconditioned residual norm sqrt((r, D r)) relative to the first one
+    rn = std::sqrt(std::fabs(rtz1));
+    if (r0 < 0.0) r0 = std::sqrt(std::fabs(rtz2));
+    if (rn <= tol * r0) break;
+  }
+  if (iters) *iters = it > maxit ? maxit : it;
+  if (res) *res = r0 > 0.0 ? rn / r0 : 0.0;
+  return NSB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -276,3 +276,48 @@ def convect(u, vel, rst, d):
     ur, us = grad_rst(u, d)
     rx, ry, sx, sy = rst
     return vel[0] * (rx * ur + sx * us) + vel[1] * (ry * ur + sy * us)
+
+
+# ----------------------------------------------------------------------------
+# Helmholtz solve  ([UPSTREAM-RECALL] hmholtz.f cggo + setprec)
+# ----------------------------------------------------------------------------
+def helm_diag(g, d, bm1, h1, h2):
+    """Diagonal of h1 A + h2 B per local point (setprec without the deformed-boundary cross terms)."""
+    d2 = d * d                       # d2[q, i] = D(q,i)^2
+    if g.shape[0] == 6:
+        s = np.einsum('qi,ekjq->ekji', d2, g[0]) + np.einsum('qj,ekqi->ekji', d2, g[1]) \
+            + np.einsum('qk,eqji->ekji', d2, g[2])
+    else:
+        s = np.einsum('qi,ejq->eji', d2, g[0]) + np.einsum('qj,eqi->eji', d2, g[1])
+    return h1 * s + h2 * bm1
+
+
+def cggo(rhs, g, d, glo, mask, bm1, h1, h2, tol=1e-10, maxit=500):
+    """Jacobi-PCG of Nek's cggo: z = D r ; rtz = (r,z)_mult ; p = z + beta p ; w = mask dssum axhelm p ;
+    alpha = rtz / (w,p)_mult ; x += alpha p ; r -= alpha w.  Returns (x, iterations, residual drop)."""
+    mult = 1.0 / multiplicity(glo)
+    dinv = mask / dssum(helm_diag(g, d, bm1, h1, h2), glo)
+    x = np.zeros_like(rhs)
+    p = np.zeros_like(rhs)
+    r = rhs * mask
+    z = dinv * r
+    rtz1, rtz2 = float(np.sum(r * z * mult)), 1.0
+    r0, rn, it = -1.0, 0.0, 0
+    for it in range(1, maxit + 1):
+        beta = 0.0 if it == 1 else rtz1 / rtz2
+        p = z + beta * p
+        w = dssum(axhelm(p, g, d, h1, h2, bm1), glo) * mask
+        rho = float(np.sum(w * p * mult))
+        if not rho > 0.0:
+            break
+        alpha = rtz1 / rho
+        x = x + alpha * p
+        r = r - alpha * w
+        z = dinv * r
+        rtz2, rtz1 = rtz1, float(np.sum(r * z * mult))
+        rn = np.sqrt(abs(rtz1))
+        if r0 < 0.0:
+            r0 = np.sqrt(abs(rtz2))
+        if rn <= tol * r0:
+            break
+    return x, it, (rn / r0 if r0 > 0 else 0.0)

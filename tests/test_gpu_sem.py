@@ -96,3 +96,23 @@ def test_mask_inconsistency_is_rejected(ctx):
     bad[0, -1, 1, 1] = 0.0   # a face node shared with the element above, zeroed on one side only
     with pytest.raises(nb.NsbError):
         nb.Sem(ctx, P.N, *P.coords, mask=bad, glo_num=P.glo)
+
+
+@pytest.mark.parametrize('nel,N,deform', [((3, 2, 2), 7, 0.05), ((2, 2, 2), 4, 0.0), ((4, 3), 5, 0.04)])
+def test_helmholtz_pcg(ctx, nel, N, deform):
+    """nsb_sem_hmholtz vs the oracle restatement of Nek's cggo: same iteration count, same solution,
+    and the solution satisfies the assembled Helmholtz problem."""
+    P = BoxProblem(nel=nel, N=N, deform=deform, nfields=1, seed=5)
+    lay, B, S, op = P.gpu(ctx, 4)
+    h1, h2 = 0.7, 2.0
+    # right-hand side in the range of the assembled operator: B f, summed over copies, masked
+    f = P.random_field()
+    rhs = osem.dssum(P.bm1 * f, P.glo) * P.mask
+    xo, ito, reso = osem.cggo(rhs, P.geo['g'], P.d, P.glo, P.mask, P.bm1, h1, h2, tol=1e-11, maxit=400)
+    B[0].upload([rhs])
+    it, res = S.hmholtz(B[0], B[1], 0, h1, h2, tol=1e-11, maxit=400)
+    x = B[1].download()[0][0].reshape(P.shape)
+    assert abs(it - ito) <= 1 and res <= 1e-11
+    assert relerr(x, xo) <= 1e-8
+    lhs = osem.dssum(osem.axhelm(x, P.geo['g'], P.d, h1, h2, P.bm1), P.glo) * P.mask
+    assert relerr(lhs, rhs) <= 1e-8
