@@ -359,8 +359,9 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // Two shared-memory stages per CTA: while block b is processed, the loads of block b + gridDim.x
-// are already in flight.  LOADER 0: one TMA bulk copy per column on an mbarrier per stage;
-// LOADER 1: cp.async (LDGSTS) 16 B per thread;  LOADER 3: one 2-D TMA tensor load per <= 256 columns
+// are already in flight.  LOADER 1: cp.async (LDGSTS) 16 B per thread;  LOADER 3: one 2-D TMA tensor
+// load per <= 256 columns on an mbarrier per stage (per-column bulk copies and a registers-only variant
+// were measured and dropped, profiles/tune_orth_r01.md)
 // (box = RC rows x kbox columns, dense [column][row] in shared memory, no swizzle).
 __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1,
                                             uint64_t *bar) {
@@ -390,7 +391,7 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < (NT / 32) * kpad; i += NT) accS[i] = 0.0;
   for (int j = tid; j < k; j += NT) hS[j] = h1[j];
-  if ((LOADER == 0 || LOADER == 3) && tid == 0) {
+  if (LOADER == 3 && tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
   }
@@ -408,13 +409,6 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
         mbar_expect_tx(bar + stage, (uint32_t)(kst * RC * sizeof(double)));
         for (int b = 0; b < nbox; ++b)
           tma_load_2d(dst + (size_t)b * kbox * RC, &tmap, (int)(blk * RC), b * kbox, bar + stage);
-      }
-    } else if (LOADER == 0) {
-      if (warp == 0) {
-        if (lane == 0) mbar_expect_tx(bar + stage, (uint32_t)(k * RC * sizeof(double)));
-        __syncwarp();
-        for (int j = lane; j < k; j += 32)
-          tma_bulk_g2s(dst + (size_t)j * RC, src + (int64_t)j * ld, RC * sizeof(double), bar + stage);
       }
     } else {
       const int npieces = k * RP;   // 16-byte pieces
@@ -439,7 +433,7 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
     // every thread loads w / W for its own row pair (the CG copies of a row pair hit L1)
     double2 wv = *reinterpret_cast<const double2 *>(w + r0 + 2 * rp);
     double2 Wv = in_dot ? *reinterpret_cast<const double2 *>(W + r0 + 2 * rp) : make_double2(0.0, 0.0);
-    if (LOADER == 0 || LOADER == 3) {
+    if (LOADER == 3) {
       mbar_wait(bar + stage, (phase_bits >> stage) & 1u);
       phase_bits ^= 1u << stage;
     } else {
@@ -517,97 +511,6 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
     for (int wp = 0; wp < NT / 32; ++wp) s += accS[wp * kpad + j];
     partial[(size_t)blockIdx.x * pstride + j] = s;
   }
-}
-
-// ---- fused update + multidot, register-resident variant ---------------------------------------
-// Block = 64 rows.  Warp c (of 8) owns the columns j = c (mod 8), lane l owns the row pair l: the
-// thread keeps its NJ = ceil(k/8) double2 of V in registers from the moment they arrive.
-//   pass A  partial row sums over the warp's columns -> shared [8][32] double2, ONE __syncthreads
-//   every thread then forms the full row sum for its row pair, w' and W o w' in registers
-//   pass B  the retained V values times W o w', reduced over the lanes (rows) with warp_reduce8;
-//           warp c accumulates its own columns, so no cross-warp reduction is needed.
-// V crosses HBM once and never touches shared memory; the pass-A buffer is double buffered so a
-// block costs a single barrier.
-template <int NJ, bool WITH_NORM>
-__global__ void __launch_bounds__(NT, (NJ <= 13 ? 2 : 1))
-fused_reg_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h1,
-                 double *__restrict__ w, const double *__restrict__ W, int64_t nblocks,
-                 int64_t ndot_blocks, double *__restrict__ partial, int pstride) {
-  constexpr int RC = 64, NW = NT / 32;
-  __shared__ double2 sP[2][NW][32];
-  __shared__ double accS[NW * NJ + 8];   // accS[jj * NW + warp] = column warp + 8 jj ; last slot: norm
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double hreg[NJ];
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    const int j = warp + NW * jj;
-    hreg[jj] = j < k ? h1[j] : 0.0;
-  }
-  double acc2[NJ];
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) acc2[jj] = 0.0;
-  double nrm = 0.0;
-  int buf = 0;
-  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1) {
-    const int64_t r = blk * RC + 2 * lane;
-    const double *vp = V + r;
-    double2 v[NJ];
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      const int j = warp + NW * jj;
-      v[jj] = j < k ? ld_stream(reinterpret_cast<const double2 *>(vp + (int64_t)j * ld))
-                    : make_double2(0.0, 0.0);
-    }
-    const bool in_dot = blk < ndot_blocks;
-    double2 wv = *reinterpret_cast<const double2 *>(w + r);
-    double2 Wv = in_dot ? *reinterpret_cast<const double2 *>(W + r) : make_double2(0.0, 0.0);
-    double2 a = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      a.x = fma(v[jj].x, hreg[jj], a.x);
-      a.y = fma(v[jj].y, hreg[jj], a.y);
-    }
-    sP[buf][warp][lane] = a;
-    __syncthreads();
-    double2 s = sP[buf][0][lane];
-#pragma unroll
-    for (int c = 1; c < NW; ++c) {
-      const double2 t = sP[buf][c][lane];
-      s.x += t.x;
-      s.y += t.y;
-    }
-    wv.x -= s.x;
-    wv.y -= s.y;
-    if (warp == 0) *reinterpret_cast<double2 *>(w + r) = wv;
-    const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
-    if (WITH_NORM && warp == 0) nrm += ww.x * wv.x + ww.y * wv.y;
-    if (in_dot) {
-#pragma unroll
-      for (int j0 = 0; j0 < NJ; j0 += KT) {
-        double a8[KT];
-#pragma unroll
-        for (int c = 0; c < KT; ++c)
-          a8[c] = (j0 + c < NJ) ? fma(v[(j0 + c < NJ) ? j0 + c : 0].x, ww.x, v[(j0 + c < NJ) ? j0 + c : 0].y * ww.y)
-                                : 0.0;
-        const double red = warp_reduce8(a8, lane);
-        // lane L with (L & 3) == 0 holds local column j0 + (L >> 2); keep it in that lane's slot
-#pragma unroll
-        for (int c = 0; c < KT; ++c)
-          if (j0 + c < NJ && lane == 4 * c) acc2[j0 + c] += red;
-      }
-    }
-  }
-  // every column's running sum lives in one lane of its warp
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj)
-    if (lane == 4 * (jj % KT)) accS[jj * NW + warp] = acc2[jj];
-  if (WITH_NORM) {
-    nrm = warp_reduce_sum(nrm);
-    if (tid == 0) accS[NW * NJ] = nrm;
-  }
-  __syncthreads();
-  for (int j = tid; j < k; j += NT) partial[(size_t)blockIdx.x * pstride + j] = accS[(j / NW) * NW + (j % NW)];
-  if (WITH_NORM && tid == 0) partial[(size_t)blockIdx.x * pstride + k] = accS[NW * NJ];
 }
 
 // ---- fused update + multidot: 2-D TMA prefetch + register retention ---------------------------
@@ -963,48 +866,6 @@ int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const d
 int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h1_d, double *w,
                  const double *W, int64_t nrows, int64_t ndot, double *h2_d, bool with_norm, int64_t nalg,
                  int64_t nalg_dot) {
-  if (ctx->fused_loader == 2 && k <= 8 * 32) {
-    // register-resident variant
-    const int64_t nblocks = nrows / 64, ndot_blocks = ndot / 64;
-    const int nj = (k + 7) / 8;
-    const int per_sm = nj <= 13 ? 2 : 1;
-    const int64_t g = (int64_t)ctx->num_sms * per_sm;
-    const int grid = (int)(nblocks < g ? nblocks : g);
-    const int pstride = kMaxK + 8;
-    NSB_CHECK(ensure_partial(ctx, grid));
-    cudaSetDevice(ctx->device);
-    {
-      ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
-#define LAUNCH_REG(NJ)                                                                                    \
-  do {                                                                                                    \
-    if (with_norm)                                                                                        \
-      fused_reg_kernel<NJ, true><<<grid, NT, 0, ctx->stream>>>(V, ld, k, h1_d, w, W, nblocks, ndot_blocks, \
-                                                               ctx->partial_d, pstride);                  \
-    else                                                                                                  \
-      fused_reg_kernel<NJ, false><<<grid, NT, 0, ctx->stream>>>(V, ld, k, h1_d, w, W, nblocks, ndot_blocks, \
-                                                                ctx->partial_d, pstride);                 \
-  } while (0)
-      if (nj <= 2) LAUNCH_REG(2);
-      else if (nj <= 4) LAUNCH_REG(4);
-      else if (nj <= 7) LAUNCH_REG(7);
-      else if (nj <= 10) LAUNCH_REG(10);
-      else if (nj <= 13) LAUNCH_REG(13);
-      else if (nj <= 16) LAUNCH_REG(16);
-      else if (nj <= 20) LAUNCH_REG(20);
-      else if (nj <= 26) LAUNCH_REG(26);
-      else LAUNCH_REG(32);
-#undef LAUNCH_REG
-    }
-    const int kout = with_norm ? k + 1 : k;
-    {
-      ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
-      reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
-                                                                               kout, h2_d, 0, nullptr);
-    }
-    ctx->launches += 2;
-    NSB_CUDA(cudaGetLastError());
-    return NSB_OK;
-  }
   if (ctx->fused_loader == 3 && k >= ctx->fused_reg_min_k && k <= 8 * 26 &&
       fused_tma_reg_smem(k, (k + 7) / 8) <= 226 * 1024) {
     // 2-D TMA prefetch + register retention, 64-row blocks
@@ -1126,8 +987,7 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
   } while (0)
 #define LAUNCH_FUSED(RC, NORM)                                                \
   do {                                                                        \
-    if (loader == 0) LAUNCH_FUSED2(RC, NORM, 0);                              \
-    else if (loader == 1) LAUNCH_FUSED2(RC, NORM, 1);                         \
+    if (loader == 1) LAUNCH_FUSED2(RC, NORM, 1);                              \
     else LAUNCH_FUSED2(RC, NORM, 3);                                          \
   } while (0)
     if (rc == 128) { if (with_norm) LAUNCH_FUSED(128, true); else LAUNCH_FUSED(128, false); }
