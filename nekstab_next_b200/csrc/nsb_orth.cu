@@ -145,6 +145,19 @@ update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__r
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int64_t r0 = chunk * CHUNK + 2 * threadIdx.x;
     const double *vp = V + r0;
+    double2 *wpa = reinterpret_cast<double2 *>(w + r0);
+    double2 *wpb = reinterpret_cast<double2 *>(w + r0 + 512);
+    // w (and W for the norm) are requested before the sweep over the columns, so the
+    // read-modify-write at the end of the chunk does not wait on a fresh load
+    double2 wa = make_double2(0.0, 0.0), wb = wa, Wa = wa, Wb = wa;
+    if (MODE == 0) {
+      wa = *wpa;
+      wb = *wpb;
+      if (WITH_NORM && chunk < ndot_chunks) {
+        Wa = ld_stream(reinterpret_cast<const double2 *>(W + r0));
+        Wb = ld_stream(reinterpret_cast<const double2 *>(W + r0 + 512));
+      }
+    }
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int j0 = 0;
     for (; j0 + KT <= k; j0 += KT) {
@@ -174,18 +187,12 @@ update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__r
       a2 = fma(b.x, hj, a2);
       a3 = fma(b.y, hj, a3);
     }
-    double2 *wpa = reinterpret_cast<double2 *>(w + r0);
-    double2 *wpb = reinterpret_cast<double2 *>(w + r0 + 512);
     if (MODE == 0) {
-      double2 wa = *wpa, wb = *wpb;
       wa.x -= a0; wa.y -= a1; wb.x -= a2; wb.y -= a3;
       *wpa = wa;
       *wpb = wb;
-      if (WITH_NORM && chunk < ndot_chunks) {
-        const double2 Wa = ld_stream(reinterpret_cast<const double2 *>(W + r0));
-        const double2 Wb = ld_stream(reinterpret_cast<const double2 *>(W + r0 + 512));
+      if (WITH_NORM && chunk < ndot_chunks)
         nrm += Wa.x * wa.x * wa.x + Wa.y * wa.y * wa.y + Wb.x * wb.x * wb.x + Wb.y * wb.y * wb.y;
-      }
     } else {
       *wpa = make_double2(a0, a1);
       *wpb = make_double2(a2, a3);

@@ -38,6 +38,7 @@ module nekstab_b200
    end type nek_dvector
 
    public :: nsb_check, nsb_startup, nsb_shutdown, nsb_upload, nsb_download
+   public :: nsb_p2p_mailbox_create, nsb_p2p_mailbox_connect
    public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
    public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d
 
@@ -56,6 +57,19 @@ module nekstab_b200
          integer(c_int), value :: device, rank, nranks
          character(kind=c_char) :: id(128)
          type(c_ptr) :: ctx
+         integer(c_int) :: ierr
+      end function
+      function nsb_p2p_mailbox_create(ctx, halo_bytes, handle) bind(C, name='nsb_p2p_mailbox_create') result(ierr)
+         import :: c_int, c_int64_t, c_char, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: halo_bytes
+         character(kind=c_char) :: handle(64)
+         integer(c_int) :: ierr
+      end function
+      function nsb_p2p_mailbox_connect(ctx, all_handles) bind(C, name='nsb_p2p_mailbox_connect') result(ierr)
+         import :: c_int, c_char, c_ptr
+         type(c_ptr), value :: ctx
+         character(kind=c_char) :: all_handles(64, *)
          integer(c_int) :: ierr
       end function
       function nsb_finalize(ctx) bind(C, name='nsb_finalize') result(ierr)
