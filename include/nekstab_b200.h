@@ -306,6 +306,13 @@ int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur_tgt, doubl
                      double schur_del, int orth_mode, int max_restarts, double *H, int ldh,
                      double *vals_c16, double *vecs_c16, double *residual, int *cnt,
                      int *schur_cnt);
+/* Step-wise eigensolver of the LightKrylov path, the call linear_stability_analysis makes
+ * (core/linear_stab.f90:66: eigs(A, X, eigvecs, eigvals, residuals, info, nev, tolerance)):
+ * one Arnoldi step at a time, eig(H(1:k,1:k)) and residuals |H(k+1,k) y_k| after every step, stop
+ * when nev Ritz pairs are below tol.  [UPSTREAM-RECALL: LightKrylov is not vendored.]  vecs_c16 has
+ * leading dimension k_dim; *kused = Krylov dimension reached. */
+int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double tol, int orth_mode, double *H,
+             int ldh, double *vals_c16, double *vecs_c16, double *residual, int *kused, int *nconv);
 /* ts_gmres(rhs, sol, maxiter, ksize, calls) (core/newton_krylov.f90:170-299).  rhs and sol are
  * (basis, col) vectors; Q is the caller's Krylov basis with >= ksize+2 columns (last = work). */
 int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int crhs, nsb_basis_t bsol, int csol,

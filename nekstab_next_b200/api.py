@@ -572,6 +572,22 @@ def krylov_schur(Q: Basis, op: LinearOperator, k_dim: int = 100, schur_tgt: int 
     return KSResult(vals, vecs, res, cnt.value, scnt.value, H)
 
 
+def eigs(Q: Basis, op: LinearOperator, k_dim: int, nev: int, tol: float, orth_mode: int = ORTH_CGS2):
+    """LightKrylov-style step-wise eigensolver (call site core/linear_stab.f90:66); Q[0] = unit seed.
+    Returns (vals[k], vecs[k, k], residual[k], k, nconv, H)."""
+    set_lapack_from_scipy()
+    H = np.zeros((k_dim + 1, k_dim), order='F')
+    vals = np.zeros(k_dim, dtype=np.complex128)
+    vecs = np.zeros((k_dim, k_dim), dtype=np.complex128, order='F')
+    res = np.zeros(k_dim)
+    ku, nc = C.c_int(), C.c_int()
+    check(Q.lib.nsb_eigs(Q.h, op.h, k_dim, nev, tol, orth_mode, _dp(H), k_dim + 1,
+                         vals.ctypes.data_as(c_double_p), vecs.ctypes.data_as(c_double_p), _dp(res),
+                         C.byref(ku), C.byref(nc)))
+    k = ku.value
+    return vals[:k].copy(), vecs[:k, :k].copy(), res[:k].copy(), k, nc.value, H
+
+
 def ts_gmres(Q: Basis, op: LinearOperator, rhs: nek_dvector, sol: nek_dvector, maxiter: int,
              ksize: int, tol: float, orth_mode: int = ORTH_CGS2):
     """core/newton_krylov.f90:170 -- returns (residual history, calls)."""

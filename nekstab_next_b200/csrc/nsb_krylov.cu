@@ -355,6 +355,42 @@ extern "C" int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur
 }
 
 // ------------------------------------------------------------------------------------------------
+// Step-wise eigensolver of the LightKrylov path: linear_stability_analysis calls
+// eigs(A, X, eigvecs, eigvals, residuals, info, nev=schur_tgt, tolerance=eigen_tol)
+// (core/linear_stab.f90:66).  [UPSTREAM-RECALL, LightKrylov is not vendored]: one Arnoldi step at a
+// time, eig(H(1:k,1:k)) and residuals |H(k+1,k) y_k| after every step, stop once nev Ritz pairs
+// are below the tolerance.  Returns the Krylov dimension reached in *kused.
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double tol, int orth_mode, double *H,
+                        int ldh, double *vals_c16, double *vecs_c16, double *residual, int *kused, int *nconv) {
+  NSB_REQUIRE(Q && op && H && vals_c16 && vecs_c16 && residual && kused, "nsb_eigs: NULL argument");
+  NSB_REQUIRE(k_dim >= 1 && k_dim + 1 <= Q->ncols && ldh >= k_dim + 1 && nev >= 1, "nsb_eigs: bad sizes");
+  for (int j = 0; j < k_dim; ++j) memset(H + (size_t)j * ldh, 0, sizeof(double) * (k_dim + 1));
+  int k = 0, cnt = 0;
+  std::vector<double> vecs, vals;
+  for (k = 1; k <= k_dim; ++k) {
+    NSB_CHECK(nsb_arnoldi(Q, op, k - 1, k - 1, orth_mode, H, ldh));
+    vecs.assign((size_t)2 * k * k, 0.0);
+    vals.assign((size_t)2 * k, 0.0);
+    NSB_CHECK(nsb_eig(H, ldh, k, vecs.data(), vals.data()));
+    const double hk = std::fabs(H[(size_t)(k - 1) * ldh + k]);
+    cnt = 0;
+    for (int j = 0; j < k; ++j) {
+      residual[j] = hk * std::hypot(vecs[2 * ((size_t)j * k + (k - 1))], vecs[2 * ((size_t)j * k + (k - 1)) + 1]);
+      if (residual[j] < tol) ++cnt;
+    }
+    if (cnt >= nev) break;
+  }
+  if (k > k_dim) k = k_dim;
+  memcpy(vals_c16, vals.data(), sizeof(double) * 2 * k);
+  for (int j = 0; j < k; ++j)   // k x k eigenvector block into the caller's k_dim-leading-dimension array
+    memcpy(vecs_c16 + 2 * (size_t)j * k_dim, vecs.data() + 2 * (size_t)j * k, sizeof(double) * 2 * k);
+  *kused = k;
+  if (nconv) *nconv = cnt;
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // GMRES  (core/newton_krylov.f90:170-326)
 // ------------------------------------------------------------------------------------------------
 extern "C" int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int crhs, nsb_basis_t bsol,

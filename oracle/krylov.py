@@ -391,3 +391,23 @@ def qr_dec(bm1, X):
         Q.append(dum)
         rr[j, j] = math.sqrt(norma)
     return Q, rr
+
+
+# ----------------------------------------------------------------------------
+# LightKrylov-style step-wise eigensolver (call site core/linear_stab.f90:66)
+# ----------------------------------------------------------------------------
+def eigs(ctx, matvec, q0: KVec, k_dim: int, nev: int, tol: float):
+    """[UPSTREAM-RECALL] LightKrylov eigs (not vendored; parity unpinned): Arnoldi one step at a time,
+    eig(H_k) and residuals |H(k+1,k) y_k| after every step, stop when nev pairs are below tol."""
+    Q = [k_zero_like(q0) for _ in range(k_dim + 1)]
+    k_copy(Q[0], q0)
+    H = np.zeros((k_dim + 1, k_dim))
+    vecs = vals = residual = None
+    k = 0
+    for k in range(1, k_dim + 1):
+        arnoldi_factorization(ctx, matvec, Q, H, k, k, k_dim)
+        vecs, vals = eig(H[:k, :k])
+        residual = np.abs(H[k, k - 1] * vecs[k - 1, :])
+        if int(np.count_nonzero(residual < tol)) >= nev:
+            break
+    return vals, vecs, residual, k, H

@@ -148,3 +148,22 @@ def test_ts_gmres(ctx):
         assert relerr(a, b.ravel()) <= 1e-8
     assert np.allclose(hist, hist_ref, rtol=1e-6, atol=1e-300)
     assert hist[-1] < hist[0]
+
+
+def test_eigs_stepwise(ctx):
+    """The LightKrylov-path eigensolver (core/linear_stab.f90:66): same stopping step, same Ritz values."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=1, conv=True, seed=17)
+    c = P.octx()
+    kd, tol = 60, 1e-5
+    lay, B, S, op = P.gpu(ctx, kd + 1)
+    q0 = seed(P, c)
+    vals_o, vecs_o, res_o, k_o, H_o = okr.eigs(c, P.omatvec, q0.copy(), kd, nev=2, tol=tol)
+    upload(B[0], q0)
+    vals, vecs, res, k, nconv, H = nb.eigs(B, op, kd, nev=2, tol=tol)
+    assert k == k_o and k < kd and nconv >= 2
+    assert np.max(np.abs(H[:k + 1, :k] - H_o[:k + 1, :k])) <= 1e-10 * np.max(np.abs(H_o))
+    conv = np.where(res_o < tol)[0]
+    for i in conv:
+        assert np.min(np.abs(vals - vals_o[i])) <= 1e-6 * abs(vals_o[i])
+    assert np.allclose(np.sort(res), np.sort(res_o), rtol=1e-3, atol=1e-10)
