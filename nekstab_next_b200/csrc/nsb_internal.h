@@ -78,7 +78,7 @@ struct nsb_context_s {
   int fused_reg_min_k = 54;    // NSB_FUSED_REG_MIN_K: smallest k for the register-retention variant
   bool ax_generic = false;     // NSB_AX_GENERIC=1: use the generic-order axhelm kernel for N = 7 too
   bool rotate_simple = false;  // NSB_ROTATE_SIMPLE=1: first (untiled) rotation kernel
-  int ax_stages = 3;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernel (3: D row/column cached in registers)
+  int ax_stages = 0;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernels (0: default; DMMA: = warp groups pins one buffer per group)
   bool ax_dmma = true;         // NSB_AX_DMMA=0: vector-FMA contraction in the ring kernel instead of DMMA
   bool ax_ring = true;         // NSB_AX_RING=0: warp-per-element kernel instead of the TMA ring (N = 7)
   bool prof = false;

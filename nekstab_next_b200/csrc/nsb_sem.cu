@@ -588,32 +588,43 @@ __device__ __forceinline__ void dmma884(double2 &d, double a, double b) {
 // ncu on the ring kernel above: DRAM 35 %, shared pipe 87 % -- the r/s contractions read D rows and
 // plane values from shared memory for every FMA.  BASELINE.json's north-star allows fp64 tensor
 // cores exactly in this case.  Each 8x8 plane contraction becomes two DMMA m8n8k4; the only shared
-// traffic left is one 128-bit store and four 64-bit loads per plane matrix to change fragment
-// layout (plus the staged G1..G6, now read as 128-bit pairs).
-template <int NF, bool CONV, int EPI, int NSTAGE>
-__global__ void __launch_bounds__((NF * NSTAGE + 1) * 32, 1)
+// traffic left is one 128-bit store and two 64-bit loads per B-operand plane (plus the staged
+// G1..G6, read as 128-bit pairs).
+//
+// Ring: NBUF element buffers serve NG warp groups (NF warps each, one per velocity component).
+// Element `it` of the CTA lives in buffer it % NBUF and is processed by group it % NG; with
+// NBUF = NG + 1 one buffer is always loading while every group computes.
+template <int NF, bool CONV>
+struct Dmma8Cfg {
+  static constexpr int NARR = 6 + 2 + (CONV ? 3 : 0) + NF;      // arrays per buffer: G1..G6, bm1, bmask, [C], u
+  static constexpr int NG = NF == 3 ? 3 : (NF == 2 ? 4 : 5);    // warp groups
+  static constexpr int PLANE = 80;                              // doubles per conversion plane
+  static constexpr size_t fixed = sizeof(double) * ((size_t)NF * NG * 2 * PLANE + 128) + 256;
+  static constexpr int fit = (int)((227 * 1024 - fixed) / (sizeof(double) * NARR * 512 + 16));
+  static constexpr int NBUF = fit < NG + 1 ? fit : NG + 1;
+  static constexpr size_t smem = fixed + (size_t)NBUF * (sizeof(double) * NARR * 512 + 16);
+};
+
+template <int NF, bool CONV, int EPI, int NBUF>
+__global__ void __launch_bounds__((NF * Dmma8Cfg<NF, CONV>::NG + 1) * 32, 1)
 axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
                       const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
                       const double *__restrict__ cv, double alpha, double beta,
                       const double *__restrict__ bmask, int64_t fstride) {
-  constexpr int LX = 8, N2 = 64, N3 = 512, PS = 12, NCW = NF * NSTAGE;
-  constexpr int NARR = 6 + 2 + (CONV ? 3 : 0) + NF;       // arrays per stage: G1..G6, bm1, bmask, [C], u
-  constexpr int STAGE = NARR * N3;                        // doubles per stage
+  using Cfg = Dmma8Cfg<NF, CONV>;
+  constexpr int LX = 8, N2 = 64, N3 = 512, NG = Cfg::NG, NCW = NF * NG, PLANE = Cfg::PLANE;
+  constexpr int NARR = Cfg::NARR;
+  constexpr int STAGE = NARR * N3;                        // doubles per buffer
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stage0 = reinterpret_cast<double *>(smem_raw);
-  double *planes = stage0 + (size_t)NSTAGE * STAGE;       // [NCW][3][LX*PS]
-  double *sD = planes + NCW * 3 * LX * PS;                // [64] D_ab, then [64] D_ba
-  double *sDt = sD + 64;
-  uint64_t *full = reinterpret_cast<uint64_t *>(sDt + 64);   // [NSTAGE]
-  uint64_t *empty = full + NSTAGE;                           // [NSTAGE]
+  double *planes = stage0 + (size_t)NBUF * STAGE;         // [NCW][2][PLANE]
+  double *sD = planes + NCW * 2 * PLANE;                  // [64] D
+  uint64_t *full = reinterpret_cast<uint64_t *>(sD + 128);   // [NBUF]
+  uint64_t *empty = full + NBUF;                             // [NBUF]
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  if (tid < N2) {
-    const int a = tid / LX, b = tid % LX;
-    sD[a * LX + b] = c_D8[a * LX + b];
-    sDt[b * LX + a] = c_D8[a * LX + b];
-  }
+  if (tid < N2) sD[tid] = c_D8[tid];
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NBUF; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, NF);
     }
@@ -624,8 +635,8 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
   if (wp == NCW) {
     // ===== producer warp: one lane per array =====
     for (int64_t it = 0; it < nit; ++it) {
-      const int s = (int)(it % NSTAGE);
-      const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+      const int s = (int)(it % NBUF);
+      const uint32_t ph = (uint32_t)((it / NBUF) & 1);
       mbar_wait(empty + s, ph ^ 1u);                       // fresh barrier: passes immediately
       const int64_t e = blockIdx.x + it * gridDim.x;
       double *dst = stage0 + (size_t)s * STAGE;
@@ -644,33 +655,40 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
     return;
   }
 
-  // ===== consumer warps: stage = wp / NF, velocity component = wp % NF =====
+  // ===== consumer warps: group = wp / NF, velocity component = wp % NF =====
   // Plane matrices are handled TRANSPOSED, M~[j][i] = m(i,j), in the fragment layouts of
   // mma.m8n8k4.f64 (gq = lane / 4, t = lane % 4):
   //   C / accumulator : rows j = gq, columns i = 2t, 2t+1   -> the lane OWNS points (2t..2t+1, gq, k):
   //                     two adjacent doubles in memory, so stage reads and the final store are 128-bit
-  //   A operand       : M~[gq][t] and M~[gq][4+t]   (two k-halves)
-  //   B operand       : M~[t][gq] and M~[4+t][gq]
-  // r-derivative  UR~ = U~ D^T   (A = U~,  B = D^T : lane constants D[gq][t], D[gq][4+t])
-  // s-derivative  US~ = D  U~    (A = D    : the same lane constants,  B = U~)
-  // transposed:   W~ += WR~ D  +  D^T WS~   (constants D[t][gq], D[4+t][gq])
-  // Layout changes C -> A / B go through a padded 8 x 12 plane per warp (conflict-free).
-  const int s = wp / NF, f = wp % NF;
+  // The two m8n8k4 of a plane product split the contraction index into EVEN (0,2,4,6) and ODD
+  // (1,3,5,7) instead of low / high halves.  Lane (gq, t) then supplies A[gq][2t] to the first and
+  // A[gq][2t+1] to the second -- exactly the two accumulator values it owns -- so a matrix that is
+  // an A operand (U~ in UR~ = U~ D^T, WR~ in WR~ D) never leaves registers.  Only the B operands
+  // (U~ in US~ = D U~, WS~ in D^T WS~) change layout: lane (gq, t) needs M~[2t][gq], M~[2t+1][gq].
+  // They go through one padded plane each, address(row, col) = 20 (row / 2) + 8 (row % 2) + col:
+  // the 128-bit row stores and the 64-bit column loads are both bank-conflict-free.
+  //   r-derivative  UR~ = U~ D^T   (A = U~ registers,  B = D^T : lane constants D[gq][2t], D[gq][2t+1])
+  //   s-derivative  US~ = D  U~    (A = D    : the same lane constants,  B = U~ via the plane)
+  //   transposed:   W~ += WR~ D  +  D^T WS~   (constants D[2t][gq], D[2t+1][gq])
+  const int grp = wp / NF, f = wp % NF;
   const int gq = lane >> 2, t = lane & 3;
   const int q = gq * LX + 2 * t;                              // in-plane offset of the lane's point pair
-  double *pu = planes + (size_t)wp * 3 * LX * PS, *pwr = pu + LX * PS, *pws = pwr + LX * PS;
-  const double *sG = stage0 + (size_t)s * STAGE;
-  const double *sB = sG + 6 * N3, *sM = sG + 7 * N3, *sC = sG + 8 * N3;
-  const double *sU = sG + (size_t)(8 + (CONV ? 3 : 0) + f) * N3;
+  double *pu = planes + (size_t)wp * 2 * PLANE, *pws = pu + PLANE;
+  const int st_off = 20 * (gq >> 1) + 8 * (gq & 1) + 2 * t;   // C layout: row gq, columns 2t, 2t+1
+  const int ld_off0 = 20 * t + gq, ld_off1 = ld_off0 + 8;     // B layout: rows 2t, 2t+1, column gq
   double *wout = w + (int64_t)f * fstride;
-  const double dA0 = sD[gq * LX + t], dA1 = sD[gq * LX + 4 + t];     // D[gq][t], D[gq][4+t]
-  const double dB0 = sD[t * LX + gq], dB1 = sD[(4 + t) * LX + gq];   // D[t][gq], D[4+t][gq]
+  const double dR0 = sD[gq * LX + 2 * t], dR1 = sD[gq * LX + 2 * t + 1];     // D[gq][2t], D[gq][2t+1]
+  const double dT0 = sD[2 * t * LX + gq], dT1 = sD[(2 * t + 1) * LX + gq];   // D[2t][gq], D[2t+1][gq]
   // element-boundary flags of the two points (i = 2t, 2t+1 ; j = gq)
   const bool bj = (gq == 0 || gq == LX - 1);
   const bool bx = bj || (2 * t == 0), by = bj || (2 * t + 1 == LX - 1);
-  for (int64_t it = s; it < nit; it += NSTAGE) {
+  for (int64_t it = grp; it < nit; it += NG) {
     const int64_t e = blockIdx.x + it * gridDim.x;
-    mbar_wait(full + s, (uint32_t)((it / NSTAGE) & 1));
+    const int s = (int)(it % NBUF);
+    const double *sG = stage0 + (size_t)s * STAGE;
+    const double *sB = sG + 6 * N3, *sM = sG + 7 * N3, *sC = sG + 8 * N3;
+    const double *sU = sG + (size_t)(8 + (CONV ? 3 : 0) + f) * N3;
+    mbar_wait(full + s, (uint32_t)((it / NBUF) & 1));
     // always 0, but opaque to the compiler: keeps the 64 D(k,l) constant loads inside the loop
     // (hoisted out of it they occupy 128 registers and spill)
     const int zoff = (int)(it >> 40);
@@ -682,15 +700,10 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
     }
 #pragma unroll
     for (int k = 0; k < LX; ++k) {
-      *reinterpret_cast<double2 *>(pu + gq * PS + 2 * t) = uk[k];
-      __syncwarp();
-      const double a0 = pu[gq * PS + t], a1 = pu[gq * PS + 4 + t];       // A layout of U~
-      const double b0 = pu[t * PS + gq], b1 = pu[(4 + t) * PS + gq];     // B layout of U~
+      *reinterpret_cast<double2 *>(pu + st_off) = uk[k];
       double2 ur = make_double2(0.0, 0.0), us = make_double2(0.0, 0.0);
-      dmma884(ur, a0, dA0);
-      dmma884(ur, a1, dA1);
-      dmma884(us, dA0, b0);
-      dmma884(us, dA1, b1);
+      dmma884(ur, uk[k].x, dR0);
+      dmma884(ur, uk[k].y, dR1);
       double2 ut = make_double2(0.0, 0.0);
 #pragma unroll
       for (int l = 0; l < LX; ++l) {
@@ -698,6 +711,10 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
         ut.x = fma(dk, uk[l].x, ut.x);
         ut.y = fma(dk, uk[l].y, ut.y);
       }
+      __syncwarp();
+      const double b0 = pu[ld_off0], b1 = pu[ld_off1];                   // B layout of U~
+      dmma884(us, dR0, b0);
+      dmma884(us, dR1, b1);
       const int p = k * N2 + q;
       const double2 g1 = *reinterpret_cast<const double2 *>(sG + p), g2 = *reinterpret_cast<const double2 *>(sG + N3 + p),
                     g3 = *reinterpret_cast<const double2 *>(sG + 2 * N3 + p),
@@ -705,15 +722,13 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
                     g5 = *reinterpret_cast<const double2 *>(sG + 4 * N3 + p),
                     g6 = *reinterpret_cast<const double2 *>(sG + 5 * N3 + p);
       double2 wr, ws, wt;
-      wr.x = h1 * (g1.x * ur.x + g4.x * us.x + g5.x * ut.x);
-      wr.y = h1 * (g1.y * ur.y + g4.y * us.y + g5.y * ut.y);
       ws.x = h1 * (g2.x * us.x + g4.x * ur.x + g6.x * ut.x);
       ws.y = h1 * (g2.y * us.y + g4.y * ur.y + g6.y * ut.y);
+      *reinterpret_cast<double2 *>(pws + st_off) = ws;
+      wr.x = h1 * (g1.x * ur.x + g4.x * us.x + g5.x * ut.x);
+      wr.y = h1 * (g1.y * ur.y + g4.y * us.y + g5.y * ut.y);
       wt.x = h1 * (g3.x * ut.x + g5.x * ur.x + g6.x * us.x);
       wt.y = h1 * (g3.y * ut.y + g5.y * ur.y + g6.y * us.y);
-      *reinterpret_cast<double2 *>(pwr + gq * PS + 2 * t) = wr;
-      *reinterpret_cast<double2 *>(pws + gq * PS + 2 * t) = ws;
-      __syncwarp();
       double2 acc = make_double2(0.0, 0.0);
       if (CONV) {
         const double2 c1 = *reinterpret_cast<const double2 *>(sC + p), c2 = *reinterpret_cast<const double2 *>(sC + N3 + p),
@@ -721,18 +736,18 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
         acc.x = c1.x * ur.x + c2.x * us.x + c3.x * ut.x;
         acc.y = c1.y * ur.y + c2.y * us.y + c3.y * ut.y;
       }
-      const double ar0 = pwr[gq * PS + t], ar1 = pwr[gq * PS + 4 + t];   // A layout of WR~
-      const double bs0 = pws[t * PS + gq], bs1 = pws[(4 + t) * PS + gq]; // B layout of WS~
-      dmma884(acc, ar0, dB0);
-      dmma884(acc, ar1, dB1);
-      dmma884(acc, dB0, bs0);
-      dmma884(acc, dB1, bs1);
+      dmma884(acc, wr.x, dT0);
+      dmma884(acc, wr.y, dT1);
 #pragma unroll
       for (int l = 0; l < LX; ++l) {
         const double dk = c_D8[k * LX + l + zoff];
         wk[l].x = fma(dk, wt.x, wk[l].x);
         wk[l].y = fma(dk, wt.y, wk[l].y);
       }
+      __syncwarp();
+      const double bs0 = pws[ld_off0], bs1 = pws[ld_off1];               // B layout of WS~
+      dmma884(acc, dT0, bs0);
+      dmma884(acc, dT1, bs1);
       wk[k].x += acc.x;
       wk[k].y += acc.y;
     }
@@ -755,7 +770,7 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
       *reinterpret_cast<double2 *>(we + p) = v;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the stage
+    if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the buffer
   }
 }
 
@@ -780,16 +795,16 @@ int launch_ring8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, dou
   return NSB_OK;
 }
 
-template <int NF, bool CONV, int EPI, int NSTAGE>
+template <int NF, bool CONV, int EPI, int NBUF>
 int launch_dmma8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
                    const double *cv, double alpha, double beta, const double *bmask) {
-  constexpr size_t smem = sizeof(double) * ((size_t)NSTAGE * (6 + 2 + (CONV ? 3 : 0) + NF) * 512 +
-                                            NF * NSTAGE * 3 * 96 + 128) + sizeof(uint64_t) * 2 * NSTAGE + 128;
+  using Cfg = Dmma8Cfg<NF, CONV>;
+  constexpr size_t smem = Cfg::fixed + (size_t)NBUF * (sizeof(double) * Cfg::NARR * 512 + 16);
   static_assert(smem <= 227 * 1024, "axhelm dmma ring does not fit in shared memory");
-  auto kfn = axhelm3d_dmma8_kernel<NF, CONV, EPI, NSTAGE>;
+  auto kfn = axhelm3d_dmma8_kernel<NF, CONV, EPI, NBUF>;
   NSB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = S->nel < S->ctx->num_sms ? S->nel : S->ctx->num_sms;
-  kfn<<<(unsigned)grid, (NF * NSTAGE + 1) * 32, smem, S->ctx->stream>>>(u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1,
+  kfn<<<(unsigned)grid, (NF * Cfg::NG + 1) * 32, smem, S->ctx->stream>>>(u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1,
                                                                        h2, cv, alpha, beta, bmask, fstride);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
@@ -799,16 +814,20 @@ int launch_dmma8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, dou
 template <int NF, bool CONV, int EPI>
 int launch_dmma8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
                  const double *cv, double alpha, double beta, const double *bmask) {
-  if (S->ctx->ax_stages == 2)
-    return launch_dmma8_s<NF, CONV, EPI, 2>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
-  return launch_dmma8_s<NF, CONV, EPI, 3>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
+  using Cfg = Dmma8Cfg<NF, CONV>;
+  // NSB_AX_STAGES=<NG> pins the ring to one buffer per warp group (the pre-decoupling behaviour)
+  if constexpr (Cfg::NBUF > Cfg::NG) {
+    if (S->ctx->ax_stages == Cfg::NG)
+      return launch_dmma8_s<NF, CONV, EPI, Cfg::NG>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
+  }
+  return launch_dmma8_s<NF, CONV, EPI, Cfg::NBUF>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
 }
 
 template <int NF, bool CONV, int EPI>
 int launch_ring8(nsb_sem_t S, const double *u, double *w, int64_t fstride, double h1, double h2,
                  const double *cv, double alpha, double beta, const double *bmask) {
   if (S->ctx->ax_dmma) return launch_dmma8<NF, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
-  if (CONV || S->ctx->ax_stages == 3)
+  if (CONV || S->ctx->ax_stages != 4)
     return launch_ring8_s<NF, CONV, EPI, 3>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
   return launch_ring8_s<NF, CONV, EPI, CONV ? 3 : 4>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmask);
 }
