@@ -283,6 +283,10 @@ int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int orth_mode,
  * (dgeev :158, dgees :49, dtrsen :108, dgels :288).  The Fortran host passes c_funloc(dgeev)...;
  * Python passes scipy's cython_lapack pointers. */
 int nsb_set_lapack(void *dgeev, void *dgees, void *dtrsen, void *dgels);
+/* dgesvd for nsb_svd / nsb_svds (LightKrylov's svd wrapper calls the same routine). */
+int nsb_set_lapack_svd(void *dgesvd);
+/* Thin SVD A(m x n) = U diag(S) V^T; U is m x min(m,n), V is n x min(m,n) (untransposed). */
+int nsb_svd(const double *A, int lda, int m, int n, double *U, double *S, double *V);
 /* lapack_wrapper mirrors (host, column-major):
  *   eig   : dgeev + complexification + sort by decreasing |lambda| (:114-228);
  *           vals/vecs interleaved (re,im) complex*16
@@ -313,6 +317,16 @@ int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur_tgt, doubl
  * leading dimension k_dim; *kused = Krylov dimension reached. */
 int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double tol, int orth_mode, double *H,
              int ldh, double *vals_c16, double *vecs_c16, double *residual, int *kused, int *nconv);
+/* Step-wise singular-value solver, the call transient_growth_analysis makes
+ * (core/linear_stab.f90:112: svds(A, U, V, uvecs, vvecs, sigma, residuals, info, nev, tolerance)):
+ * Golub-Kahan bidiagonalisation with full re-orthogonalisation, v_k = A^T u_k, u_k+1 = A v_k,
+ * B(k,k) = |v_k|, B(k+1,k) = |u_k+1|, svd(B(1:k,1:k)) and residuals |B(k+1,k) vvecs(k,:)| after
+ * every step.  [UPSTREAM-RECALL: LightKrylov is not vendored.]  U[0] must hold the unit-norm seed;
+ * U needs k_dim+1 columns, V k_dim.  op_adj applies the adjoint (A%rmatvec).  B is (k_dim+1) x k_dim
+ * (ldb); uvecs / vvecs have leading dimension k_dim; *kused = Krylov dimension reached. */
+int nsb_svds(nsb_basis_t U, nsb_basis_t V, nsb_op_t op, nsb_op_t op_adj, int k_dim, int nev, double tol,
+             int orth_mode, double *B, int ldb, double *sigma, double *uvecs, double *vvecs,
+             double *residual, int *kused, int *nconv);
 /* ts_gmres(rhs, sol, maxiter, ksize, calls) (core/newton_krylov.f90:170-299).  rhs and sol are
  * (basis, col) vectors; Q is the caller's Krylov basis with >= ksize+2 columns (last = work). */
 int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int crhs, nsb_basis_t bsol, int csol,

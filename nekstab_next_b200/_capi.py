@@ -92,6 +92,8 @@ PROTOTYPES = {
     'nsb_op_count': (C.c_int, [H, c_i64_p]),
     'nsb_arnoldi': (C.c_int, [H, H, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int]),
     'nsb_set_lapack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'nsb_set_lapack_svd': (C.c_int, [C.c_void_p]),
+    'nsb_svd': (C.c_int, [c_double_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
     'nsb_eig': (C.c_int, [c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     'nsb_schur': (C.c_int, [c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     'nsb_ordschur': (C.c_int, [c_double_p, C.c_int, c_double_p, C.c_int, c_int_p, C.c_int]),
@@ -103,6 +105,8 @@ PROTOTYPES = {
                                    c_int_p]),
     'nsb_eigs': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p, C.c_int, c_double_p,
                            c_double_p, c_double_p, c_int_p, c_int_p]),
+    'nsb_svds': (C.c_int, [H, H, H, H, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p, C.c_int, c_double_p,
+                           c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
     'nsb_ts_gmres': (C.c_int, [H, H, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                c_int_p, c_double_p, c_int_p]),
 }

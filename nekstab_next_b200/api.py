@@ -53,10 +53,11 @@ def set_lapack_from_scipy():
     api.PyCapsule_GetPointer.restype = C.c_void_p
     api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
     ptrs = []
-    for name in ('dgeev', 'dgees', 'dtrsen', 'dgels'):
+    for name in ('dgeev', 'dgees', 'dtrsen', 'dgels', 'dgesvd'):
         cap = cl.__pyx_capi__[name]
         ptrs.append(api.PyCapsule_GetPointer(cap, api.PyCapsule_GetName(cap)))
-    check(_capi.load().nsb_set_lapack(*ptrs))
+    check(_capi.load().nsb_set_lapack(*ptrs[:4]))
+    check(_capi.load().nsb_set_lapack_svd(ptrs[4]))
     _lapack_set = True
 
 
@@ -586,6 +587,37 @@ def eigs(Q: Basis, op: LinearOperator, k_dim: int, nev: int, tol: float, orth_mo
                          C.byref(ku), C.byref(nc)))
     k = ku.value
     return vals[:k].copy(), vecs[:k, :k].copy(), res[:k].copy(), k, nc.value, H
+
+
+def svd(A):
+    """Thin SVD through the injected dgesvd: returns (U, S, V) with A = U diag(S) V^T."""
+    set_lapack_from_scipy()
+    m, n = A.shape
+    r = min(m, n)
+    Af = np.asfortranarray(A, dtype=np.float64)
+    U = np.zeros((m, r), order='F')
+    S = np.zeros(r)
+    V = np.zeros((n, r), order='F')
+    check(_capi.load().nsb_svd(_dp(Af), m, m, n, _dp(U), _dp(S), _dp(V)))
+    return U, S, V
+
+
+def svds(U: Basis, V: Basis, op: LinearOperator, op_adj: LinearOperator, k_dim: int, nev: int, tol: float,
+         orth_mode: int = ORTH_CGS2):
+    """LightKrylov-style step-wise singular-value solver (call site core/linear_stab.f90:112);
+    U[0] = unit seed, op_adj = A%rmatvec.  Returns (sigma[k], uvecs[k, k], vvecs[k, k], residual[k],
+    k, nconv, B)."""
+    set_lapack_from_scipy()
+    B = np.zeros((k_dim + 1, k_dim), order='F')
+    sigma = np.zeros(k_dim)
+    uv = np.zeros((k_dim, k_dim), order='F')
+    vv = np.zeros((k_dim, k_dim), order='F')
+    res = np.zeros(k_dim)
+    ku, nc = C.c_int(), C.c_int()
+    check(U.lib.nsb_svds(U.h, V.h, op.h, op_adj.h, k_dim, nev, tol, orth_mode, _dp(B), k_dim + 1, _dp(sigma),
+                         _dp(uv), _dp(vv), _dp(res), C.byref(ku), C.byref(nc)))
+    k = ku.value
+    return sigma[:k].copy(), uv[:k, :k].copy(), vv[:k, :k].copy(), res[:k].copy(), k, nc.value, B
 
 
 def ts_gmres(Q: Basis, op: LinearOperator, rhs: nek_dvector, sol: nek_dvector, maxiter: int,

@@ -31,7 +31,10 @@ typedef void (*dgels_fn)(char *, int *, int *, int *, double *, int *, double *,
 dgeev_fn p_dgeev = nullptr;
 dgees_fn p_dgees = nullptr;
 dtrsen_fn p_dtrsen = nullptr;
+typedef void (*dgesvd_fn)(char *, char *, int *, int *, double *, int *, double *, double *, int *, double *,
+                          int *, double *, int *, int *, size_t, size_t);
 dgels_fn p_dgels = nullptr;
+dgesvd_fn p_dgesvd = nullptr;
 
 int need_lapack(void *p, const char *name) {
   if (!p) {
@@ -50,6 +53,36 @@ extern "C" int nsb_set_lapack(void *dgeev, void *dgees, void *dtrsen, void *dgel
   p_dgees = (dgees_fn)dgees;
   p_dtrsen = (dtrsen_fn)dtrsen;
   p_dgels = (dgels_fn)dgels;
+  return NSB_OK;
+}
+
+extern "C" int nsb_set_lapack_svd(void *dgesvd) {
+  p_dgesvd = (dgesvd_fn)dgesvd;
+  return NSB_OK;
+}
+
+// Thin SVD A = U diag(S) V^T (dgesvd, 'S','S'); V is returned untransposed, as LightKrylov's svd
+// wrapper hands it to svds.  U: m x min(m,n) (ldu = m), V: n x min(m,n) (ldv = n).
+extern "C" int nsb_svd(const double *A, int lda, int m, int n, double *U, double *S, double *V) {
+  NSB_REQUIRE(A && U && S && V && m >= 1 && n >= 1 && lda >= m, "nsb_svd: bad argument");
+  NSB_CHECK(need_lapack((void *)p_dgesvd, "nsb_svd"));
+  const int r = std::min(m, n);
+  std::vector<double> At((size_t)m * n), vt((size_t)r * n);
+  for (int j = 0; j < n; ++j) memcpy(&At[(size_t)j * m], A + (size_t)j * lda, sizeof(double) * m);
+  char jobu = 'S', jobvt = 'S';
+  int mm = m, nn = n, ldu = m, ldvt = r, lwork = -1, info = 0;
+  double wq = 0;
+  p_dgesvd(&jobu, &jobvt, &mm, &nn, At.data(), &mm, S, U, &ldu, vt.data(), &ldvt, &wq, &lwork, &info, 1, 1);
+  lwork = std::max(std::max(3 * r + std::max(m, n), 5 * r), (int)wq);
+  std::vector<double> work(lwork);
+  p_dgesvd(&jobu, &jobvt, &mm, &nn, At.data(), &mm, S, U, &ldu, vt.data(), &ldvt, work.data(), &lwork, &info, 1,
+           1);
+  if (info != 0) {
+    set_error("nsb_svd: dgesvd info=%d", info);
+    return NSB_ELAPACK;
+  }
+  for (int j = 0; j < r; ++j)
+    for (int i = 0; i < n; ++i) V[(size_t)j * n + i] = vt[(size_t)i * r + j];
   return NSB_OK;
 }
 
@@ -385,6 +418,59 @@ extern "C" int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double t
   memcpy(vals_c16, vals.data(), sizeof(double) * 2 * k);
   for (int j = 0; j < k; ++j)   // k x k eigenvector block into the caller's k_dim-leading-dimension array
     memcpy(vecs_c16 + 2 * (size_t)j * k_dim, vecs.data() + 2 * (size_t)j * k, sizeof(double) * 2 * k);
+  *kused = k;
+  if (nconv) *nconv = cnt;
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// svds: the call transient_growth_analysis makes (core/linear_stab.f90:112:
+// svds(A, U, V, uvecs, vvecs, sigma, residuals, info, nev, tolerance)).  [UPSTREAM-RECALL:
+// LightKrylov's Golub-Kahan Lanczos bidiagonalisation with full re-orthogonalisation, one step at a
+// time:  v_k = A^T u_k  (orthogonalised against V(1:k-1)), alpha = |v_k| = B(k,k);
+//        u_k+1 = A v_k  (orthogonalised against U(1:k)),   beta  = |u_k+1| = B(k+1,k);
+// then svd(B(1:k,1:k)), residual_i = |beta * vvecs(k,i)|, stop once nev triplets are below tol.]
+// The re-orthogonalisation is the same fused BM1-weighted kernel sequence as the Arnoldi step.
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_svds(nsb_basis_t U, nsb_basis_t V, nsb_op_t op, nsb_op_t op_adj, int k_dim, int nev, double tol,
+                        int orth_mode, double *B, int ldb, double *sigma, double *uvecs, double *vvecs,
+                        double *residual, int *kused, int *nconv) {
+  NSB_REQUIRE(U && V && op && op_adj && B && sigma && uvecs && vvecs && residual && kused, "nsb_svds: NULL argument");
+  NSB_REQUIRE(k_dim >= 1 && k_dim + 1 <= U->ncols && k_dim <= V->ncols && ldb >= k_dim + 1 && nev >= 1,
+              "nsb_svds: bad sizes (U needs k_dim+1 columns, V k_dim)");
+  NSB_REQUIRE(k_dim <= kMaxK, "nsb_svds: k_dim=%d exceeds %d", k_dim, kMaxK);
+  for (int j = 0; j < k_dim; ++j) memset(B + (size_t)j * ldb, 0, sizeof(double) * (k_dim + 1));
+  std::vector<double> h(k_dim + 2), bu, bv, bs;
+  int k = 0, kdone = 0, cnt = 0;
+  for (k = 1; k <= k_dim; ++k) {
+    const int c = k - 1;
+    NSB_CHECK(nsb_op_apply(op_adj, U, c, V, c));
+    NSB_CHECK(nsb_orthonormalize(V, c, c, orth_mode, h.data(), nullptr));
+    const double alpha = h[c];
+    B[(size_t)c * ldb + c] = alpha;
+    if (!(alpha > tol)) break;                                   // invariant subspace
+    NSB_CHECK(nsb_op_apply(op, V, c, U, k));
+    NSB_CHECK(nsb_orthonormalize(U, k, k, orth_mode, h.data(), nullptr));
+    const double beta = h[k];
+    B[(size_t)c * ldb + k] = beta;
+    kdone = k;
+    bu.assign((size_t)k * k, 0.0);
+    bv.assign((size_t)k * k, 0.0);
+    bs.assign(k, 0.0);
+    NSB_CHECK(nsb_svd(B, ldb, k, k, bu.data(), bs.data(), bv.data()));
+    cnt = 0;
+    for (int j = 0; j < k; ++j) {
+      residual[j] = std::fabs(beta * bv[(size_t)j * k + (k - 1)]);
+      if (residual[j] < tol) ++cnt;
+    }
+    if (cnt >= nev || !(beta > tol)) break;
+  }
+  k = kdone;
+  for (int j = 0; j < k; ++j) {
+    sigma[j] = bs[j];
+    memcpy(uvecs + (size_t)j * k_dim, bu.data() + (size_t)j * k, sizeof(double) * k);
+    memcpy(vvecs + (size_t)j * k_dim, bv.data() + (size_t)j * k, sizeof(double) * k);
+  }
   *kused = k;
   if (nconv) *nconv = cnt;
   return NSB_OK;

@@ -40,7 +40,7 @@ module nekstab_b200
    public :: nsb_check, nsb_startup, nsb_shutdown, nsb_upload, nsb_download
    public :: nsb_p2p_mailbox_create, nsb_p2p_mailbox_connect
    public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
-   public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d
+   public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d, eigs_d, svds_d
 
    interface
       function nsb_last_error() bind(C, name='nsb_last_error') result(msg)
@@ -225,6 +225,30 @@ module nekstab_b200
          complex(c_double_complex) :: vals(*), vecs(k_dim, *)
          integer(c_int) :: cnt, schur_cnt, ierr
       end function
+      function nsb_eigs(Q, op, k_dim, nev, tol, mode, H, ldh, vals, vecs, residual, kused, nconv) &
+         bind(C, name='nsb_eigs') result(ierr)
+         import :: c_int, c_ptr, c_double, c_double_complex
+         type(c_ptr), value :: Q, op
+         integer(c_int), value :: k_dim, nev, mode, ldh
+         real(c_double), value :: tol
+         real(c_double) :: H(ldh, *), residual(*)
+         complex(c_double_complex) :: vals(*), vecs(k_dim, *)
+         integer(c_int) :: kused, nconv, ierr
+      end function
+      function nsb_set_lapack_svd(dgesvd) bind(C, name='nsb_set_lapack_svd') result(ierr)
+         import :: c_int, c_funptr
+         type(c_funptr), value :: dgesvd
+         integer(c_int) :: ierr
+      end function
+      function nsb_svds(U, V, op, op_adj, k_dim, nev, tol, mode, B, ldb, sigma, uvecs, vvecs, residual, &
+                        kused, nconv) bind(C, name='nsb_svds') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: U, V, op, op_adj
+         integer(c_int), value :: k_dim, nev, mode, ldb
+         real(c_double), value :: tol
+         real(c_double) :: B(ldb, *), sigma(*), uvecs(k_dim, *), vvecs(k_dim, *), residual(*)
+         integer(c_int) :: kused, nconv, ierr
+      end function
       function nsb_ts_gmres(Q, op, brhs, crhs, bsol, csol, maxiter, ksize, tol, mode, calls, hist, nhist) &
          bind(C, name='nsb_ts_gmres') result(ierr)
          import :: c_int, c_ptr, c_double
@@ -266,7 +290,7 @@ contains
       character(kind=c_char) :: id(128)
       type(c_ptr) :: w(nfields)
       integer :: i, nd
-      external :: dgeev, dgees, dtrsen, dgels
+      external :: dgeev, dgees, dtrsen, dgels, dgesvd
       if (nid == 0) call nsb_check(nsb_get_unique_id(id), 'nsb_get_unique_id')
       call bcast(id, 128)                                   ! Nek5000 comm_mpi.f
       call nsb_check(nsb_init(int(local_device, c_int), int(nid, c_int), int(np_, c_int), id, nsb_ctx), 'nsb_init')
@@ -287,6 +311,7 @@ contains
       ! (core/lapack_wrapper.f90:49,108,158,288)
       call nsb_check(nsb_set_lapack(c_funloc(dgeev), c_funloc(dgees), c_funloc(dtrsen), c_funloc(dgels)), &
                      'nsb_set_lapack')
+      call nsb_check(nsb_set_lapack_svd(c_funloc(dgesvd)), 'nsb_set_lapack_svd')   ! svds (LightKrylov's svd)
    end subroutine nsb_startup
 
    subroutine nsb_shutdown()
@@ -449,6 +474,42 @@ contains
       cnt = c1
       schur_cnt = c2
    end subroutine krylov_schur_d
+
+   !> eigs(A, X, eigvecs, eigvals, residuals, info, nev, tolerance) (call site core/linear_stab.f90:66)
+   subroutine eigs_d(op, k_dim, eigvecs, eigvals, residuals, info, nev, tolerance)
+      type(c_ptr), intent(in) :: op
+      integer, intent(in) :: k_dim
+      complex(c_double_complex), intent(out) :: eigvecs(k_dim, k_dim), eigvals(k_dim)
+      real(c_double), intent(out) :: residuals(k_dim)
+      integer, intent(out) :: info
+      integer, intent(in) :: nev
+      real(c_double), intent(in) :: tolerance
+      real(c_double), allocatable :: H(:, :)
+      integer(c_int) :: ku, nc
+      allocate (H(k_dim + 1, k_dim))
+      call nsb_check(nsb_eigs(nsb_Q, op, int(k_dim, c_int), int(nev, c_int), tolerance, NSB_ORTH_CGS2, H, &
+                              int(k_dim + 1, c_int), eigvals, eigvecs, residuals, ku, nc), 'eigs')
+      info = ku
+      deallocate (H)
+   end subroutine eigs_d
+
+   !> svds(A, U, V, uvecs, vvecs, sigma, residuals, info, nev, tolerance) (call site core/linear_stab.f90:112);
+   !> U, V are device bases (k_dim+1 and k_dim columns), op_adj applies A%rmatvec
+   subroutine svds_d(op, op_adj, U, V, k_dim, uvecs, vvecs, sigma, residuals, info, nev, tolerance)
+      type(c_ptr), intent(in) :: op, op_adj, U, V
+      integer, intent(in) :: k_dim
+      real(c_double), intent(out) :: uvecs(k_dim, k_dim), vvecs(k_dim, k_dim), sigma(k_dim), residuals(k_dim)
+      integer, intent(out) :: info
+      integer, intent(in) :: nev
+      real(c_double), intent(in) :: tolerance
+      real(c_double), allocatable :: B(:, :)
+      integer(c_int) :: ku, nc
+      allocate (B(k_dim + 1, k_dim))
+      call nsb_check(nsb_svds(U, V, op, op_adj, int(k_dim, c_int), int(nev, c_int), tolerance, NSB_ORTH_CGS2, B, &
+                              int(k_dim + 1, c_int), sigma, uvecs, vvecs, residuals, ku, nc), 'svds')
+      info = ku
+      deallocate (B)
+   end subroutine svds_d
 
    !> ts_gmres(rhs, sol, maxiter, ksize, calls) (core/newton_krylov.f90:170-299)
    subroutine ts_gmres_d(op, rhs, sol, maxiter, ksize, tol, calls)

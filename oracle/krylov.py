@@ -411,3 +411,46 @@ def eigs(ctx, matvec, q0: KVec, k_dim: int, nev: int, tol: float):
         if int(np.count_nonzero(residual < tol)) >= nev:
             break
     return vals, vecs, residual, k, H
+
+
+# ----------------------------------------------------------------------------
+# LightKrylov-style step-wise singular-value solver (call site core/linear_stab.f90:112)
+# ----------------------------------------------------------------------------
+def svds(ctx, matvec, rmatvec, u0: KVec, k_dim: int, nev: int, tol: float):
+    """[UPSTREAM-RECALL] LightKrylov svds + lanczos_bidiagonalization (not vendored; parity unpinned):
+    v_k = A^T u_k, one modified Gram-Schmidt sweep against V(1:k-1), alpha = |v_k| = B(k,k);
+    u_k+1 = A v_k, one sweep against U(1:k), beta = |u_k+1| = B(k+1,k); svd(B(1:k,1:k)) and residuals
+    |beta * vvecs(k,:)| after every step, stop when nev triplets are below tol."""
+    U = [k_zero_like(u0) for _ in range(k_dim + 1)]
+    V = [k_zero_like(u0) for _ in range(k_dim)]
+    k_copy(U[0], u0)
+    B = np.zeros((k_dim + 1, k_dim))
+    sig = uv = vv = residual = None
+    kdone = 0
+    for k in range(1, k_dim + 1):
+        v = rmatvec(U[k - 1])
+        for j in range(k - 1):
+            g = k_dot(ctx, v, V[j])
+            axpby(v, 1.0, V[j], -g, skip_time=False)
+        alpha = k_norm(ctx, v)
+        B[k - 1, k - 1] = alpha
+        if not alpha > tol:
+            break
+        k_cmult(v, 1.0 / alpha)
+        k_copy(V[k - 1], v)
+        u = matvec(V[k - 1])
+        for j in range(k):
+            g = k_dot(ctx, u, U[j])
+            axpby(u, 1.0, U[j], -g, skip_time=False)
+        beta = k_norm(ctx, u)
+        B[k, k - 1] = beta
+        if beta > tol:
+            k_cmult(u, 1.0 / beta)
+        k_copy(U[k], u)
+        kdone = k
+        uv, sig, vt = np.linalg.svd(B[:k, :k])
+        vv = vt.T
+        residual = np.abs(beta * vv[k - 1, :])
+        if int(np.count_nonzero(residual < tol)) >= nev or not beta > tol:
+            break
+    return sig, uv, vv, residual, kdone, B

@@ -90,6 +90,17 @@ def test_lapack_wrapper_mirrors(lib):
         assert np.allclose(nb.lstsq(B, b), np.linalg.lstsq(B, b, rcond=None)[0], atol=1e-10)
 
 
+def test_svd_mirror(lib):
+    import nekstab_next_b200 as nb
+    rng = np.random.default_rng(5)
+    for m, n in ((7, 7), (9, 5), (4, 8)):
+        A = rng.standard_normal((m, n))
+        U, S, V = nb.svd(A)
+        assert np.allclose(S, np.linalg.svd(A, compute_uv=False), atol=1e-13)
+        assert np.allclose(U @ np.diag(S) @ V.T, A, atol=1e-12)
+        assert np.allclose(U.T @ U, np.eye(min(m, n)), atol=1e-12)
+
+
 def test_select_eigenvalues_conjugate_pair_kept(lib):
     import nekstab_next_b200 as nb
     # the (nev+4)-th largest is half of a conjugate pair -> its partner is selected too (:747-749)
