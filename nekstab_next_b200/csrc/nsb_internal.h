@@ -126,6 +126,7 @@ struct nsb_sem_s {
   int32_t *gs_idx_d = nullptr;   // local point indices
   int64_t gs_nnz = 0;
   int64_t n_local = 0;           // nodes [0, n_local) are private to this rank, the rest are interface nodes
+  double *bnode_d = nullptr;     // [nshared] bmask of every node (all copies of a node carry the same value)
   int ns_fields = 8;             // fields one batched gather-scatter can carry
   double *node_sum_d = nullptr;  // [ns_fields][nshared - n_local] interface node sums (multi-rank)
   std::vector<int64_t> node_gid; // global id of each gs node
