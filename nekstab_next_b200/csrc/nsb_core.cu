@@ -138,6 +138,7 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   if (const char *e = getenv("NSB_AX_GENERIC")) ctx->ax_generic = e[0] == '1';
   if (const char *e = getenv("NSB_AX_RING")) ctx->ax_ring = e[0] != '0';
   if (const char *e = getenv("NSB_AX_STAGES")) ctx->ax_stages = atoi(e);
+  if (const char *e = getenv("NSB_FUSED_PRIV")) ctx->fused_priv = e[0] != '0';
   if (const char *e = getenv("NSB_AX_DMMA")) ctx->ax_dmma = e[0] != '0';
   if (const char *e = getenv("NSB_PIPELINE_UPLOAD")) ctx->pipeline_upload = e[0] != '0';
   if (const char *e = getenv("NSB_ROTATE_SIMPLE")) ctx->rotate_simple = e[0] == '1';

@@ -79,6 +79,7 @@ struct nsb_context_s {
   bool ax_generic = false;     // NSB_AX_GENERIC=1: use the generic-order axhelm kernel for N = 7 too
   bool rotate_simple = false;  // NSB_ROTATE_SIMPLE=1: first (untiled) rotation kernel
   int ax_stages = 0;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernels (0: default; DMMA: = warp groups pins one buffer per group)
+  bool fused_priv = true;      // NSB_FUSED_PRIV=0: per-block warp reduction in the fused kernel's second projection
   bool ax_dmma = true;         // NSB_AX_DMMA=0: vector-FMA contraction in the ring kernel instead of DMMA
   bool ax_ring = true;         // NSB_AX_RING=0: warp-per-element kernel instead of the TMA ring (N = 7)
   bool prof = false;

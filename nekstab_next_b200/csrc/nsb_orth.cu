@@ -526,7 +526,9 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
 // block from shared memory ONCE into registers and uses it for both passes, halving the read
 // traffic, while the 2-D TMA keeps one block of prefetch in flight per CTA.
 // Block = 64 rows; warp c owns the columns j = c (mod 8), lane l the row pair l; NJ = ceil(k/8).
-template <int NJ, bool WITH_NORM>
+// PRIV: the second projection accumulates in lane-private registers over the CTA's blocks and crosses
+// lanes once at the end, instead of one warp_reduce8 per 8 columns and block.
+template <int NJ, bool WITH_NORM, bool PRIV>
 __global__ void __launch_bounds__(NT, 2)
 fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ w,
                      const double *__restrict__ W, int64_t nblocks, int64_t ndot_blocks,
@@ -550,6 +552,9 @@ fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ 
   }
   __syncthreads();
   double nrm = 0.0;
+  double accp[PRIV ? NJ : 1];
+#pragma unroll
+  for (int jj = 0; jj < (PRIV ? NJ : 1); ++jj) accp[jj] = 0.0;
   uint32_t phase_bits = 0;
   auto issue = [&](int64_t blk, int stage) {
     if (tid == 0) {
@@ -605,18 +610,34 @@ fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ 
     __syncthreads();
     if (in_dot) {
       const double2 ww = sWW[lane];
+      if constexpr (PRIV) {
 #pragma unroll
-      for (int j0 = 0; j0 < NJ; j0 += KT) {
-        double a8[KT];
+        for (int jj = 0; jj < NJ; ++jj) accp[jj] = fma(v[jj].x, ww.x, fma(v[jj].y, ww.y, accp[jj]));
+      } else {
 #pragma unroll
-        for (int c = 0; c < KT; ++c) {
-          const int jj = (j0 + c < NJ) ? j0 + c : 0;
-          a8[c] = (j0 + c < NJ) ? fma(v[jj].x, ww.x, v[jj].y * ww.y) : 0.0;
+        for (int j0 = 0; j0 < NJ; j0 += KT) {
+          double a8[KT];
+#pragma unroll
+          for (int c = 0; c < KT; ++c) {
+            const int jj = (j0 + c < NJ) ? j0 + c : 0;
+            a8[c] = (j0 + c < NJ) ? fma(v[jj].x, ww.x, v[jj].y * ww.y) : 0.0;
+          }
+          const double red = warp_reduce8(a8, lane);
+          const int jj = j0 + (lane >> 2);
+          if ((lane & 3) == 0 && jj < NJ) accS[warp + NW * jj] += red;   // column warp + 8 jj, owned by this warp
         }
-        const double red = warp_reduce8(a8, lane);
-        const int jj = j0 + (lane >> 2);
-        if ((lane & 3) == 0 && jj < NJ) accS[warp + NW * jj] += red;   // column warp + 8 jj, owned by this warp
       }
+    }
+  }
+  if constexpr (PRIV) {
+#pragma unroll
+    for (int j0 = 0; j0 < NJ; j0 += KT) {
+      double a8[KT];
+#pragma unroll
+      for (int c = 0; c < KT; ++c) a8[c] = (j0 + c < NJ) ? accp[(j0 + c < NJ) ? j0 + c : 0] : 0.0;
+      const double red = warp_reduce8(a8, lane);
+      const int jj = j0 + (lane >> 2);
+      if ((lane & 3) == 0 && jj < NJ) accS[warp + NW * jj] = red;
     }
   }
   if (WITH_NORM) {
@@ -891,12 +912,17 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
     cudaSetDevice(ctx->device);
     {
       ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+#define LAUNCH_TR3(NJ, NORM, PRIV)                                                                      \
+  do {                                                                                                  \
+    NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg_kernel<NJ, NORM, PRIV>,                                 \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    fused_tma_reg_kernel<NJ, NORM, PRIV><<<grid, NT, smem, ctx->stream>>>(                              \
+        k, h1_d, w, W, nblocks, ndot_blocks, ctx->partial_d, pstride, tmap, kbox, nbox);                \
+  } while (0)
 #define LAUNCH_TR2(NJ, NORM)                                                                            \
   do {                                                                                                  \
-    NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg_kernel<NJ, NORM>,                                       \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    fused_tma_reg_kernel<NJ, NORM><<<grid, NT, smem, ctx->stream>>>(k, h1_d, w, W, nblocks, ndot_blocks, \
-                                                                   ctx->partial_d, pstride, tmap, kbox, nbox); \
+    if ((NJ) <= 13 && ctx->fused_priv) LAUNCH_TR3(NJ, NORM, ((NJ) <= 13));                              \
+    else LAUNCH_TR3(NJ, NORM, false);                                                                   \
   } while (0)
 #define LAUNCH_TR(NJ) do { if (with_norm) LAUNCH_TR2(NJ, true); else LAUNCH_TR2(NJ, false); } while (0)
       switch (nj) {
@@ -910,6 +936,7 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
       }
 #undef LAUNCH_TR
 #undef LAUNCH_TR2
+#undef LAUNCH_TR3
     }
     const int kout = with_norm ? k + 1 : k;
     {
