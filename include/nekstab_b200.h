@@ -243,6 +243,26 @@ int nsb_sem_ax(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int co
 int nsb_sem_hmholtz(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field,
                     double h1, double h2, double tol, int maxit, int *iters, double *res);
 
+/* Dealiased convection of Nek5000's perturbation step ([UPSTREAM-RECALL] convect.f set_dealias_rx /
+ * set_convect_new / convect_new: the terms advabp adds for (U.grad)u' and (u'.grad)U; SURVEY.md
+ * section 8 f-3).  3-D.  The fine mesh has lxd Gauss-Legendre points per direction (lxd <= 0: Nek's
+ * 3 lx1 / 2).
+ *   dealias_setup : metrics rxm1..tzm1 interpolated to the fine mesh times the Gauss weights
+ *   set_convect   : slot (0 or 1) <- contravariant fine-mesh form of the velocity in fields
+ *                   field0..field0+2 of (b, col)
+ *   convect       : out(field f) (+)= scale * J^T [ (c_slot . grad_rst)(J in(field f)) ],
+ *                   f = field0..field0+nf-1; the mass matrix and the Jacobian are inside c */
+int nsb_sem_dealias_setup(nsb_sem_t sem, int lxd);
+int nsb_sem_set_convect(nsb_sem_t sem, int slot, nsb_basis_t b, int col, int field0);
+int nsb_sem_convect(nsb_sem_t sem, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
+                    int field0, int nf, double scale, int accumulate);
+/* EXT / BDF sums of the same step ([UPSTREAM-RECALL] perturb.f makextp + makebdfp) in one pass over
+ * fields field0..field0+nf-1 of columns of b:
+ *   ta = ab[1] e1 + ab[2] e2 ; e2 <- e1 ; e1 <- bf ; bf <- ab[0] bf + ta ;
+ *   bf += rho_over_dt * bm1 * sum_{i<nbd} bd[i+1] * v(col_vlag[i])     (col_vlag[0] = current velocity) */
+int nsb_sem_bdf_ext(nsb_sem_t sem, nsb_basis_t b, int col_bf, int col_e1, int col_e2, const int *col_vlag,
+                    int nbd, int field0, int nf, const double *ab, const double *bd, double rho_over_dt);
+
 /* ---------------------------------------------------------------------------------------------
  * Linear operator: the abstract_linop%matvec(vec_in, vec_out) boundary
  * (core/linear_operators.f90:17-23, 39-44) / legacy matvec(f, q) (core/matvec.f90:56).

@@ -395,6 +395,30 @@ class Sem:
     def ax(self, vin: nek_dvector, vout: nek_dvector, field: int, h1: float, h2: float):
         check(self.lib.nsb_sem_ax(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col, field, h1, h2))
 
+    # -- time-stepper pieces around ax ([UPSTREAM-RECALL] convect.f, perturb.f) --
+    def dealias_setup(self, lxd: int = 0):
+        """Fine-mesh metrics for the dealiased convection (lxd Gauss-Legendre points; 0 = 3 lx1 / 2)."""
+        check(self.lib.nsb_sem_dealias_setup(self.h, int(lxd)))
+
+    def set_convect(self, slot: int, vel: nek_dvector, field0: int = 0):
+        """set_convect_new: slot <- contravariant fine-mesh form of the velocity in fields field0..field0+2."""
+        check(self.lib.nsb_sem_set_convect(self.h, int(slot), vel.basis.h, vel.col, int(field0)))
+
+    def convect(self, slot: int, vin: nek_dvector, vout: nek_dvector, field0: int = 0, nf: int = 1,
+                scale: float = 1.0, accumulate: bool = False):
+        """convect_new: vout (+)= scale * J^T[(c_slot . grad)(J vin)] on nf fields from field0."""
+        check(self.lib.nsb_sem_convect(self.h, int(slot), vin.basis.h, vin.col, vout.basis.h, vout.col,
+                                       int(field0), int(nf), float(scale), int(accumulate)))
+
+    def bdf_ext(self, bf: nek_dvector, e1: nek_dvector, e2: nek_dvector, vlag, ab, bd, rho_over_dt: float,
+                field0: int = 0, nf: int = 1):
+        """makextp + makebdfp in one pass; all vectors are columns of the same basis, vlag[0] = current."""
+        cols = (C.c_int * len(vlag))(*[v.col for v in vlag])
+        abv, bdv = _f64(ab), _f64(bd)
+        assert abv.size >= 3 and bdv.size >= len(vlag) + 1
+        check(self.lib.nsb_sem_bdf_ext(self.h, bf.basis.h, bf.col, e1.col, e2.col, cols, len(vlag), int(field0),
+                                       int(nf), _dp(abv), _dp(bdv), float(rho_over_dt)))
+
     def close(self):
         if self.h:
             self.lib.nsb_sem_destroy(self.h)

@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libnekstab_b200.so'
-SOURCES = ['nsb_core.cu', 'nsb_orth.cu', 'nsb_sem.cu', 'nsb_comm.cu', 'nsb_krylov.cu']
+SOURCES = ['nsb_core.cu', 'nsb_orth.cu', 'nsb_sem.cu', 'nsb_conv.cu', 'nsb_comm.cu', 'nsb_krylov.cu']
 HEADERS = [CSRC / 'nsb_internal.h', CSRC / 'nsb_device.cuh', ROOT / 'include' / 'nekstab_b200.h']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '-diag-suppress', '128']

@@ -1,0 +1,453 @@
+// Time-stepper pieces either side of `ax`, on the device:
+//   * dealiased convection of Nek5000's perturbation step  [UPSTREAM-RECALL convect.f:
+//     set_dealias_rx, set_convect_new, convect_new, intp_rstd, grad_rst] -- the term advabp adds
+//     for (U.grad)u' and (u'.grad)U, evaluated on the lxd = 3 lx1 / 2 Gauss-Legendre mesh;
+//   * the EXT / BDF sums of the same step  [UPSTREAM-RECALL perturb.f: makextp, makebdfp] as one
+//     fused streaming pass.
+// Nek5000 is not vendored in the reference tree: the kernels are checked against a CPU restatement
+// of those routines held by the test suite (tests/test_gpu_conv.py); parity unpinned.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "nsb_internal.h"
+#include "nsb_device.cuh"
+
+using namespace nsb;
+
+namespace {
+
+// ---- host: Gauss-Legendre nodes, interpolation and derivative matrices --------------------------
+void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w) {
+  x.assign(n, 0.0);
+  w.assign(n, 0.0);
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    double z = std::cos(pi * (i + 0.75) / (n + 0.5));
+    double pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+      }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (std::fabs(dz) < 1e-16) break;
+    }
+    x[i] = -z;
+    x[n - 1 - i] = z;
+    w[i] = w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+  if (n % 2) x[n / 2] = 0.0;
+}
+
+std::vector<double> bary_weights(const std::vector<double> &z) {
+  const int n = (int)z.size();
+  std::vector<double> w(n, 1.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (i != j) w[i] /= (z[i] - z[j]);
+  return w;
+}
+
+// J[I * nf + i] = l_i(zto_I)
+std::vector<double> interp_matrix(const std::vector<double> &zfrom, const std::vector<double> &zto) {
+  const int nf = (int)zfrom.size(), nt = (int)zto.size();
+  const std::vector<double> bw = bary_weights(zfrom);
+  std::vector<double> J((size_t)nt * nf, 0.0);
+  for (int I = 0; I < nt; ++I) {
+    int hit = -1;
+    for (int i = 0; i < nf; ++i)
+      if (std::fabs(zto[I] - zfrom[i]) < 1e-15) hit = i;
+    if (hit >= 0) {
+      J[(size_t)I * nf + hit] = 1.0;
+      continue;
+    }
+    double s = 0.0;
+    for (int i = 0; i < nf; ++i) {
+      J[(size_t)I * nf + i] = bw[i] / (zto[I] - zfrom[i]);
+      s += J[(size_t)I * nf + i];
+    }
+    for (int i = 0; i < nf; ++i) J[(size_t)I * nf + i] /= s;
+  }
+  return J;
+}
+
+// D[i * n + j] = l_j'(z_i)
+std::vector<double> deriv_matrix(const std::vector<double> &z) {
+  const int n = (int)z.size();
+  const std::vector<double> bw = bary_weights(z);
+  std::vector<double> D((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      D[(size_t)i * n + j] = (bw[j] / bw[i]) / (z[i] - z[j]);
+      s += D[(size_t)i * n + j];
+    }
+    D[(size_t)i * n + i] = -s;
+  }
+  return D;
+}
+
+// ---- device: tensor-product interpolation of one element, whole CTA ------------------------------
+// Shared layout of a work area (doubles): src [LX^3] | t1 [LX^2 LD] + t2 [LX LD^2] | fine [LD^3].
+template <int LX, int LD>
+struct ConvSmem {
+  static constexpr int NC = LX * LX * LX, NF = LD * LD * LD;
+  static constexpr int T1 = LX * LX * LD, T2 = LX * LD * LD;
+  static constexpr int SRC = 0, TMP = NC, FINE = NC + T1 + T2, MAT = FINE + NF;
+  static constexpr int TOTAL = MAT + LD * LX + LD * LD;   // + J + Dg
+  static_assert(T1 + T2 >= NF, "the second fine buffer aliases the temporaries");
+};
+
+// fine[K][J][I] = sum_kji Jm[K][k] Jm[J][j] Jm[I][i] src[k][j][i]   (intp_rstd, idir = 0)
+template <int LX, int LD>
+__device__ __forceinline__ void interp3(const double *__restrict__ src, double *__restrict__ t1,
+                                        double *__restrict__ t2, double *__restrict__ fine,
+                                        const double *__restrict__ Jm) {
+  for (int o = threadIdx.x; o < LX * LX * LD; o += blockDim.x) {     // t1[k][j][I]
+    const int I = o % LD, kj = o / LD;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < LX; ++i) s = fma(Jm[I * LX + i], src[kj * LX + i], s);
+    t1[o] = s;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < LX * LD * LD; o += blockDim.x) {     // t2[k][J][I]
+    const int I = o % LD, Jx = (o / LD) % LD, k = o / (LD * LD);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < LX; ++j) s = fma(Jm[Jx * LX + j], t1[(k * LX + j) * LD + I], s);
+    t2[o] = s;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < LD * LD * LD; o += blockDim.x) {     // fine[K][J][I]
+    const int JI = o % (LD * LD), K = o / (LD * LD);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < LX; ++k) s = fma(Jm[K * LX + k], t2[k * LD * LD + JI], s);
+    fine[o] = s;
+  }
+  __syncthreads();
+}
+
+template <int LX, int LD>
+__device__ __forceinline__ void load_mats(double *sm, const double *__restrict__ Jg, const double *__restrict__ Dgg) {
+  using L = ConvSmem<LX, LD>;
+  for (int i = threadIdx.x; i < LD * LX; i += blockDim.x) sm[L::MAT + i] = Jg[i];
+  for (int i = threadIdx.x; i < LD * LD; i += blockDim.x) sm[L::MAT + LD * LX + i] = Dgg[i];
+}
+
+// set_dealias_rx: rxf[a][e] = (w_I w_J w_K) * J(rst[a][e]);  grid (nel, 9)
+template <int LX, int LD>
+__global__ void __launch_bounds__(256)
+dealias_rx_kernel(const double *__restrict__ rst, int64_t npts, int64_t nfine, const double *__restrict__ Jg,
+                  const double *__restrict__ Dgg, const double *__restrict__ wd, double *__restrict__ rxf) {
+  using L = ConvSmem<LX, LD>;
+  extern __shared__ double sm[];
+  const int64_t e = blockIdx.x;
+  const int a = blockIdx.y;
+  load_mats<LX, LD>(sm, Jg, Dgg);
+  for (int i = threadIdx.x; i < L::NC; i += blockDim.x) sm[L::SRC + i] = rst[(int64_t)a * npts + e * L::NC + i];
+  __syncthreads();
+  interp3<LX, LD>(sm + L::SRC, sm + L::TMP, sm + L::TMP + L::T1, sm + L::FINE, sm + L::MAT);
+  for (int o = threadIdx.x; o < L::NF; o += blockDim.x) {
+    const int I = o % LD, Jx = (o / LD) % LD, K = o / (LD * LD);
+    rxf[(int64_t)a * nfine + e * L::NF + o] = wd[I] * wd[Jx] * wd[K] * sm[L::FINE + o];
+  }
+}
+
+// set_convect_new: c_a = sum_b rxf[3a+b] * J(v_b);  one CTA per element
+template <int LX, int LD>
+__global__ void __launch_bounds__(256)
+set_convect_kernel(const double *__restrict__ v, int64_t fstride, int64_t nfine, const double *__restrict__ Jg,
+                   const double *__restrict__ Dgg, const double *__restrict__ rxf, double *__restrict__ cf) {
+  using L = ConvSmem<LX, LD>;
+  constexpr int PT = (L::NF + 255) / 256;
+  extern __shared__ double sm[];
+  const int64_t e = blockIdx.x;
+  load_mats<LX, LD>(sm, Jg, Dgg);
+  double acc[3][PT];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int t = 0; t < PT; ++t) acc[a][t] = 0.0;
+  for (int b = 0; b < 3; ++b) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < L::NC; i += blockDim.x) sm[L::SRC + i] = v[(int64_t)b * fstride + e * L::NC + i];
+    __syncthreads();
+    interp3<LX, LD>(sm + L::SRC, sm + L::TMP, sm + L::TMP + L::T1, sm + L::FINE, sm + L::MAT);
+#pragma unroll
+    for (int t = 0; t < PT; ++t) {
+      const int o = threadIdx.x + t * 256;
+      if (o < L::NF) {
+        const double f = sm[L::FINE + o];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a][t] = fma(rxf[(int64_t)(3 * a + b) * nfine + e * L::NF + o], f, acc[a][t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < PT; ++t) {
+    const int o = threadIdx.x + t * 256;
+    if (o < L::NF) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) cf[(int64_t)a * nfine + e * L::NF + o] = acc[a][t];
+    }
+  }
+}
+
+// convect_new: out (+)= scale * J^T [ (c . grad_rst)(J u) ];  grid (nel, nf)
+template <int LX, int LD>
+__global__ void __launch_bounds__(256)
+convect_kernel(const double *__restrict__ u, double *__restrict__ out, int64_t fstride_in, int64_t fstride_out,
+               int64_t nfine, const double *__restrict__ Jg, const double *__restrict__ Dgg,
+               const double *__restrict__ cf, double scale, int accumulate) {
+  using L = ConvSmem<LX, LD>;
+  extern __shared__ double sm[];
+  const int64_t e = blockIdx.x;
+  const int f = blockIdx.y;
+  const double *Jm = sm + L::MAT, *Dg = sm + L::MAT + LD * LX;
+  load_mats<LX, LD>(sm, Jg, Dgg);
+  for (int i = threadIdx.x; i < L::NC; i += blockDim.x) sm[L::SRC + i] = u[(int64_t)f * fstride_in + e * L::NC + i];
+  __syncthreads();
+  double *uf = sm + L::FINE, *wf = sm + L::TMP;     // wf aliases t1/t2 once the interpolation is done
+  interp3<LX, LD>(sm + L::SRC, sm + L::TMP, sm + L::TMP + L::T1, uf, Jm);
+  // fine-mesh gradient and the pointwise contraction with the contravariant convecting field
+  const double *cr = cf + e * L::NF, *cs = cr + nfine, *ct = cs + nfine;
+  for (int o = threadIdx.x; o < L::NF; o += blockDim.x) {
+    const int I = o % LD, Jx = (o / LD) % LD, K = o / (LD * LD);
+    double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+    for (int m = 0; m < LD; ++m) {
+      ur = fma(Dg[I * LD + m], uf[(K * LD + Jx) * LD + m], ur);
+      us = fma(Dg[Jx * LD + m], uf[(K * LD + m) * LD + I], us);
+      ut = fma(Dg[K * LD + m], uf[(m * LD + Jx) * LD + I], ut);
+    }
+    wf[o] = cr[o] * ur + cs[o] * us + ct[o] * ut;
+  }
+  __syncthreads();
+  // project back (intp_rstd, idir = 1): p1[K][J][i], p2[K][j][i], out[k][j][i]
+  double *p1 = uf, *p2 = wf;      // uf is free after the gradient; wf is free once p1 is complete
+  static_assert(LD * LD * LX <= L::NF && LD * LX * LX <= L::T1 + L::T2, "projection temporaries fit");
+  for (int o = threadIdx.x; o < LD * LD * LX; o += blockDim.x) {
+    const int i = o % LX, KJ = o / LX;
+    double s = 0.0;
+#pragma unroll
+    for (int I = 0; I < LD; ++I) s = fma(Jm[I * LX + i], wf[KJ * LD + I], s);
+    p1[o] = s;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < LD * LX * LX; o += blockDim.x) {
+    const int i = o % LX, j = (o / LX) % LX, K = o / (LX * LX);
+    double s = 0.0;
+#pragma unroll
+    for (int Jx = 0; Jx < LD; ++Jx) s = fma(Jm[Jx * LX + j], p1[(K * LD + Jx) * LX + i], s);
+    p2[o] = s;
+  }
+  __syncthreads();
+  double *dst = out + (int64_t)f * fstride_out + e * L::NC;
+  for (int o = threadIdx.x; o < L::NC; o += blockDim.x) {
+    const int ji = o % (LX * LX), k = o / (LX * LX);
+    double s = 0.0;
+#pragma unroll
+    for (int K = 0; K < LD; ++K) s = fma(Jm[K * LX + k], p2[K * LX * LX + ji], s);
+    dst[o] = accumulate ? fma(scale, s, dst[o]) : scale * s;
+  }
+}
+
+// makextp + makebdfp, one pass; grid-stride over the points of one field, grid.y = field
+__global__ void __launch_bounds__(256)
+bdf_ext_kernel(double *__restrict__ bf, double *__restrict__ e1, double *__restrict__ e2, const double *v0,
+               const double *v1, const double *v2, const double *__restrict__ bm1, int64_t npts, int64_t fstride,
+               double ab0, double ab1, double ab2, double bd1, double bd2, double bd3, double rho_dt) {
+  const int64_t off = (int64_t)blockIdx.y * fstride;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = off + p;
+    const double b = bf[q], x1 = e1[q], x2 = e2[q];
+    const double ta = ab1 * x1 + ab2 * x2;
+    e2[q] = x1;
+    e1[q] = b;
+    double r = ab0 * b + ta;
+    const double m = bm1[p];
+    double tb = bd1 * m * v0[q];
+    if (v1) tb = tb + bd2 * m * v1[q];
+    if (v2) tb = tb + bd3 * m * v2[q];
+    bf[q] = r + rho_dt * tb;
+  }
+}
+
+int conv_field_ptr(nsb_sem_t S, nsb_basis_t B, int col, int field, int nf, double **out, int64_t *fstride,
+                   const char *who) {
+  NSB_REQUIRE(S && B, "%s: NULL argument", who);
+  NSB_REQUIRE(col >= 0 && col < B->ncols, "%s: column %d out of range", who, col);
+  nsb_layout_t L = B->lay;
+  NSB_REQUIRE(field >= 0 && nf >= 1 && field + nf <= L->nfields, "%s: fields %d..%d out of range", who, field,
+              field + nf - 1);
+  NSB_REQUIRE(L->ctx == S->ctx, "%s: basis and mesh live on different contexts", who);
+  for (int f = field; f < field + nf; ++f)
+    NSB_REQUIRE(L->len[f] == S->npts, "%s: field %d has %lld points, mesh has %lld", who, f, (long long)L->len[f],
+                (long long)S->npts);
+  for (int f = field + 1; f < field + nf; ++f)
+    NSB_REQUIRE(L->off[f] - L->off[f - 1] == L->off[field + 1] - L->off[field], "%s: fields are not equally spaced",
+                who);
+  *out = B->col(col) + L->off[field];
+  *fstride = nf > 1 ? L->off[field + 1] - L->off[field] : 0;
+  return NSB_OK;
+}
+
+template <int LX, int LD>
+int dealias_setup_t(nsb_sem_t S, const double *wd_d) {
+  using L = ConvSmem<LX, LD>;
+  const size_t smem = sizeof(double) * L::TOTAL;
+  const int64_t nfine = S->nel * L::NF;
+  NSB_CUDA(cudaFuncSetAttribute(dealias_rx_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(set_convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dealias_rx_kernel<LX, LD><<<dim3((unsigned)S->nel, 9), 256, smem, S->ctx->stream>>>(S->rst_d, S->npts, nfine, S->J_d,
+                                                                                  S->Dg_d, wd_d, S->rxf_d);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+template <int LX, int LD>
+int set_convect_t(nsb_sem_t S, const double *v, int64_t fstride, double *cf) {
+  using L = ConvSmem<LX, LD>;
+  set_convect_kernel<LX, LD><<<(unsigned)S->nel, 256, sizeof(double) * L::TOTAL, S->ctx->stream>>>(
+      v, fstride, S->nel * L::NF, S->J_d, S->Dg_d, S->rxf_d, cf);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+template <int LX, int LD>
+int convect_t(nsb_sem_t S, const double *u, double *out, int64_t fsi, int64_t fso, int nf, const double *cf,
+              double scale, int accumulate) {
+  using L = ConvSmem<LX, LD>;
+  convect_kernel<LX, LD><<<dim3((unsigned)S->nel, nf), 256, sizeof(double) * L::TOTAL, S->ctx->stream>>>(
+      u, out, fsi, fso, S->nel * L::NF, S->J_d, S->Dg_d, cf, scale, accumulate);
+  S->ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+// (lx, lxd) pairs with compiled kernels: Nek's lxd = 3 lx1 / 2 for lx1 = 4, 6, 8 (+ lx1 = 5 with lxd = 8)
+#define NSB_CONV_DISPATCH(S, CALL)                                                       \
+  do {                                                                                   \
+    if ((S)->lx == 8 && (S)->lxd == 12) return CALL(8, 12);                              \
+    if ((S)->lx == 6 && (S)->lxd == 9) return CALL(6, 9);                                \
+    if ((S)->lx == 5 && (S)->lxd == 8) return CALL(5, 8);                                \
+    if ((S)->lx == 4 && (S)->lxd == 6) return CALL(4, 6);                                \
+    set_error("dealiased convection: no kernel for lx1=%d, lxd=%d", (S)->lx, (S)->lxd);  \
+    return NSB_EINVAL;                                                                   \
+  } while (0)
+
+}  // namespace
+
+extern "C" int nsb_sem_dealias_setup(nsb_sem_t S, int lxd) {
+  NSB_REQUIRE(S, "nsb_sem_dealias_setup: NULL");
+  NSB_REQUIRE(S->dim == 3, "nsb_sem_dealias_setup: 3-D meshes only (dim=%d)", S->dim);
+  if (lxd <= 0) lxd = S->lx == 5 ? 8 : 3 * S->lx / 2;
+  cudaSetDevice(S->ctx->device);
+  if (S->lxd == lxd && S->rxf_d) return NSB_OK;
+  const int lx = S->lx;
+  std::vector<double> zd, wd;
+  gauss_legendre(lxd, zd, wd);
+  const std::vector<double> J = interp_matrix(S->z_h, zd), Dg = deriv_matrix(zd);
+  for (double **p : {&S->J_d, &S->Dg_d, &S->rxf_d, &S->cfine_d[0], &S->cfine_d[1]}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  S->lxd = lxd;
+  const int64_t nfine = S->nel * (int64_t)lxd * lxd * lxd;
+  double *wd_d = nullptr;
+  NSB_CUDA(cudaMalloc(&S->J_d, sizeof(double) * lxd * lx));
+  NSB_CUDA(cudaMalloc(&S->Dg_d, sizeof(double) * lxd * lxd));
+  NSB_CUDA(cudaMalloc(&wd_d, sizeof(double) * lxd));
+  NSB_CUDA(cudaMalloc(&S->rxf_d, sizeof(double) * 9 * nfine));
+  NSB_CUDA(cudaMemcpy(S->J_d, J.data(), sizeof(double) * lxd * lx, cudaMemcpyHostToDevice));
+  NSB_CUDA(cudaMemcpy(S->Dg_d, Dg.data(), sizeof(double) * lxd * lxd, cudaMemcpyHostToDevice));
+  NSB_CUDA(cudaMemcpy(wd_d, wd.data(), sizeof(double) * lxd, cudaMemcpyHostToDevice));
+  int rc;
+  {
+    auto run = [&]() -> int {
+#define CALL_SETUP(A, B) dealias_setup_t<A, B>(S, wd_d)
+      NSB_CONV_DISPATCH(S, CALL_SETUP);
+#undef CALL_SETUP
+    };
+    rc = run();
+  }
+  cudaStreamSynchronize(S->ctx->stream);
+  cudaFree(wd_d);
+  if (rc != NSB_OK) {
+    S->lxd = 0;
+    return rc;
+  }
+  return NSB_OK;
+}
+
+extern "C" int nsb_sem_set_convect(nsb_sem_t S, int slot, nsb_basis_t B, int col, int field0) {
+  NSB_REQUIRE(S && B, "nsb_sem_set_convect: NULL argument");
+  NSB_REQUIRE(slot == 0 || slot == 1, "nsb_sem_set_convect: slot %d (0 or 1)", slot);
+  NSB_REQUIRE(S->lxd > 0 && S->rxf_d, "nsb_sem_set_convect: call nsb_sem_dealias_setup first");
+  double *v;
+  int64_t fs;
+  NSB_CHECK(conv_field_ptr(S, B, col, field0, 3, &v, &fs, "nsb_sem_set_convect"));
+  cudaSetDevice(S->ctx->device);
+  const int64_t nfine = S->nel * (int64_t)S->lxd * S->lxd * S->lxd;
+  if (!S->cfine_d[slot]) NSB_CUDA(cudaMalloc(&S->cfine_d[slot], sizeof(double) * 3 * nfine));
+  double *cf = S->cfine_d[slot];
+#define CALL_SC(A, B) set_convect_t<A, B>(S, v, fs, cf)
+  NSB_CONV_DISPATCH(S, CALL_SC);
+#undef CALL_SC
+}
+
+extern "C" int nsb_sem_convect(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
+                               int field0, int nf, double scale, int accumulate) {
+  NSB_REQUIRE(S && bin && bout, "nsb_sem_convect: NULL argument");
+  NSB_REQUIRE(slot == 0 || slot == 1, "nsb_sem_convect: slot %d (0 or 1)", slot);
+  NSB_REQUIRE(S->lxd > 0 && S->cfine_d[slot], "nsb_sem_convect: slot %d has no convecting field (nsb_sem_set_convect)",
+              slot);
+  double *u, *w;
+  int64_t fsi, fso;
+  NSB_CHECK(conv_field_ptr(S, bin, cin, field0, nf, &u, &fsi, "nsb_sem_convect"));
+  NSB_CHECK(conv_field_ptr(S, bout, cout, field0, nf, &w, &fso, "nsb_sem_convect"));
+  NSB_REQUIRE(u != w, "nsb_sem_convect: input and output are the same vector");
+  cudaSetDevice(S->ctx->device);
+  const double *cf = S->cfine_d[slot];
+#define CALL_CV(A, B) convect_t<A, B>(S, u, w, fsi, fso, nf, cf, scale, accumulate)
+  NSB_CONV_DISPATCH(S, CALL_CV);
+#undef CALL_CV
+}
+
+extern "C" int nsb_sem_bdf_ext(nsb_sem_t S, nsb_basis_t B, int col_bf, int col_e1, int col_e2, const int *col_vlag,
+                               int nbd, int field0, int nf, const double *ab, const double *bd,
+                               double rho_over_dt) {
+  NSB_REQUIRE(S && B && col_vlag && ab && bd, "nsb_sem_bdf_ext: NULL argument");
+  NSB_REQUIRE(nbd >= 1 && nbd <= 3, "nsb_sem_bdf_ext: nbd=%d (1..3)", nbd);
+  double *bf, *e1, *e2, *v[3] = {nullptr, nullptr, nullptr};
+  int64_t fs, fs2;
+  NSB_CHECK(conv_field_ptr(S, B, col_bf, field0, nf, &bf, &fs, "nsb_sem_bdf_ext"));
+  NSB_CHECK(conv_field_ptr(S, B, col_e1, field0, nf, &e1, &fs2, "nsb_sem_bdf_ext"));
+  NSB_CHECK(conv_field_ptr(S, B, col_e2, field0, nf, &e2, &fs2, "nsb_sem_bdf_ext"));
+  for (int i = 0; i < nbd; ++i) NSB_CHECK(conv_field_ptr(S, B, col_vlag[i], field0, nf, &v[i], &fs2, "nsb_sem_bdf_ext"));
+  NSB_REQUIRE(col_bf != col_e1 && col_bf != col_e2 && col_e1 != col_e2, "nsb_sem_bdf_ext: bf, e1, e2 must differ");
+  for (int i = 0; i < nbd; ++i)
+    NSB_REQUIRE(col_vlag[i] != col_bf && col_vlag[i] != col_e1 && col_vlag[i] != col_e2,
+                "nsb_sem_bdf_ext: a velocity column aliases bf / e1 / e2");
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  // bf, e1, e2 read + written, nbd velocities and bm1 read
+  ProfScope ps(ctx, PC_BLAS1, 8.0 * (double)S->npts * (nf * (6.0 + nbd) + 1.0));
+  bdf_ext_kernel<<<dim3(ctx->num_sms * 8, nf), 256, 0, ctx->stream>>>(bf, e1, e2, v[0], v[1], v[2], S->bm1_d, S->npts, fs,
+                                                                     ab[0], ab[1], ab[2], bd[1], nbd > 1 ? bd[2] : 0.0,
+                                                                     nbd > 2 ? bd[3] : 0.0, rho_over_dt);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}

@@ -148,6 +148,11 @@ struct nsb_sem_s {
   bool exchange_ready = false;
   double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z, d)
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
+  // dealiased convection (nsb_conv.cu): lxd Gauss-Legendre points per direction
+  int lxd = 0;
+  double *J_d = nullptr, *Dg_d = nullptr;     // [lxd][lx] GLL -> GL interpolation, [lxd][lxd] derivative on GL
+  double *rxf_d = nullptr;                    // [9][nel lxd^3] Gauss weights x metrics on the fine mesh
+  double *cfine_d[2] = {nullptr, nullptr};    // [3][nel lxd^3] contravariant convecting fields (two slots)
 };
 
 struct nsb_op_s {

@@ -1385,6 +1385,8 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   if (S->gs_off_d) cudaFree(S->gs_off_d);
   if (S->gs_idx_d) cudaFree(S->gs_idx_d);
   if (S->bnode_d) cudaFree(S->bnode_d);
+  for (double *q : {S->J_d, S->Dg_d, S->rxf_d, S->cfine_d[0], S->cfine_d[1]})
+    if (q) cudaFree(q);
   if (S->pcg_d) cudaFree(S->pcg_d);
   if (S->ev_a) cudaEventDestroy(S->ev_a);
   if (S->ev_b) cudaEventDestroy(S->ev_b);

@@ -321,3 +321,110 @@ def cggo(rhs, g, d, glo, mask, bm1, h1, h2, tol=1e-10, maxit=500):
         if rn <= tol * r0:
             break
     return x, it, (rn / r0 if r0 > 0 else 0.0)
+
+
+# ----------------------------------------------------------------------------
+# Dealiased convection  ([UPSTREAM-RECALL] Nek5000 convect.f: set_dealias_rx, set_convect_new,
+# convect_new, intp_rstd, grad_rst on the lxd Gauss-Legendre mesh; parity unpinned)
+# ----------------------------------------------------------------------------
+def gl(n: int):
+    """n Gauss-Legendre nodes and weights on [-1, 1] (Nek zwgl)."""
+    x, w = np.polynomial.legendre.leggauss(n)
+    return x, w
+
+
+def _bary_weights(z):
+    n = len(z)
+    w = np.ones(n)
+    for i in range(n):
+        for j in range(n):
+            if i != j:
+                w[i] /= (z[i] - z[j])
+    return w
+
+
+def interp_matrix(zfrom, zto):
+    """J[I, i] = l_i(zto_I), the Lagrange interpolant through zfrom evaluated at zto (Nek igllm)."""
+    bw = _bary_weights(zfrom)
+    J = np.zeros((len(zto), len(zfrom)))
+    for I, x in enumerate(zto):
+        d = x - zfrom
+        hit = np.where(np.abs(d) < 1e-15)[0]
+        if hit.size:
+            J[I, hit[0]] = 1.0
+        else:
+            t = bw / d
+            J[I] = t / t.sum()
+    return J
+
+
+def deriv_matrix(z):
+    """D[i, j] = l_j'(z_i) on arbitrary nodes (Nek gen_dgl on the Gauss points)."""
+    n = len(z)
+    bw = _bary_weights(z)
+    D = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if i != j:
+                D[i, j] = (bw[j] / bw[i]) / (z[i] - z[j])
+        D[i, i] = -np.sum(D[i])
+    return D
+
+
+def interp_fine(u, J):
+    """intp_rstd(.., idir = 0): element-local field on lx1^d GLL points -> lxd^d Gauss points."""
+    if u.ndim == 4:
+        return np.einsum('Kk,Jj,Ii,ekji->eKJI', J, J, J, u, optimize=True)
+    return np.einsum('Jj,Ii,eji->eJI', J, J, u, optimize=True)
+
+
+def project_coarse(uf, J):
+    """intp_rstd(.., idir = 1): the transpose of interp_fine."""
+    if uf.ndim == 4:
+        return np.einsum('Kk,Jj,Ii,eKJI->ekji', J, J, J, uf, optimize=True)
+    return np.einsum('Jj,Ii,eJI->eji', J, J, uf, optimize=True)
+
+
+def dealias_setup(n, lxd, rst):
+    """set_dealias_rx: the metrics rxm1.. (already times the Jacobian) interpolated to the fine mesh and
+    multiplied by the Gauss weights, plus the interpolation and fine-mesh derivative matrices."""
+    zg, _ = gll(n)
+    zd, wd = gl(lxd)
+    J = interp_matrix(zg, zd)
+    Dg = deriv_matrix(zd)
+    dim = 3 if len(rst) == 9 else 2
+    w = wd[:, None, None] * wd[None, :, None] * wd[None, None, :] if dim == 3 else wd[:, None] * wd[None, :]
+    rxf = [interp_fine(m, J) * w[None] for m in rst]
+    return dict(J=J, Dg=Dg, rxf=rxf, lxd=lxd, dim=dim)
+
+
+def set_convect(vel, dl):
+    """set_convect_new: contravariant convecting field on the fine mesh, (c_r, c_s[, c_t])."""
+    f = [interp_fine(v, dl['J']) for v in vel]
+    d, rxf = dl['dim'], dl['rxf']
+    return [sum(rxf[a * d + b] * f[b] for b in range(d)) for a in range(d)]
+
+
+def convect_dealiased(u, cf, dl):
+    """convect_new(bdu, u, .false., cr, cs, ct, .true.): J^T [ (c . grad_rst)(J u) ] -- the mass matrix and
+    the Jacobian are inside c."""
+    uf = interp_fine(u, dl['J'])
+    g = grad_rst(uf, dl['Dg'])
+    return project_coarse(sum(c * gi for c, gi in zip(cf, g)), dl['J'])
+
+
+# ----------------------------------------------------------------------------
+# EXT / BDF sums of the perturbation step  ([UPSTREAM-RECALL] Nek5000 perturb.f makextp, makebdfp)
+# ----------------------------------------------------------------------------
+def bdf_ext(bf, e1, e2, vlag, bm1, ab, bd, rho_over_dt):
+    """In place:  ta = ab1 e1 + ab2 e2 ; e2 <- e1 ; e1 <- bf ; bf <- ab0 bf + ta   (makextp)
+                  bf += (rho/dt) bm1 sum_i bd[i+1] vlag[i]                         (makebdfp; vlag[0] = current)."""
+    ta = ab[1] * e1 + ab[2] * e2
+    e2[...] = e1
+    e1[...] = bf
+    bf[...] = ab[0] * bf + ta
+    tb = bd[1] * bm1 * vlag[0]
+    for i in range(1, len(vlag)):
+        tb = tb + bd[i + 1] * bm1 * vlag[i]
+    bf += rho_over_dt * tb
+    return bf

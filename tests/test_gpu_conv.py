@@ -1,0 +1,133 @@
+"""Time-stepper pieces around ax against the oracle restatement of Nek5000's
+convect.f / perturb.f routines ([UPSTREAM-RECALL], parity unpinned): dealiased convection on the
+lxd Gauss-Legendre mesh and the fused EXT / BDF sums.  fp64, tolerance 1e-12 relative."""
+import numpy as np
+import pytest
+
+from helpers import relerr
+from oracle import sem as osem
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(nel, N, deform):
+    x, y, z, glo = osem.box_mesh(*nel, N, deform=deform)
+    return x, y, z, glo, osem.geometry(N, x, y, z)
+
+
+@pytest.mark.parametrize('nel,N,deform', [((2, 2, 2), 7, 0.05), ((3, 2, 1), 7, 0.0), ((2, 2, 2), 5, 0.04),
+                                          ((2, 1, 2), 3, 0.05), ((2, 2, 1), 4, 0.03)])
+def test_dealiased_convection_matches_oracle(ctx, nel, N, deform):
+    import nekstab_next_b200 as nb
+    x, y, z, glo, geo = _mesh(nel, N, deform)
+    lxd = 8 if N == 4 else 3 * (N + 1) // 2
+    dl = osem.dealias_setup(N, lxd, geo['rst'])
+    rng = np.random.default_rng(N)
+    vel = [np.sin(2 * x) * np.cos(y) + 0.3, 0.5 * np.cos(x + z), rng.standard_normal(x.shape)]
+    u = [rng.standard_normal(x.shape) for _ in range(3)]
+    cf = osem.set_convect(vel, dl)
+    ref = [osem.convect_dealiased(a, cf, dl) for a in u]
+
+    sem = nb.Sem(ctx, N, x, y, z, glo_num=glo)
+    lay = nb.Layout(ctx, [x.size] * 3, [True] * 3)
+    lay.set_weight([geo['bm1']] * 3)
+    B = nb.Basis(lay, 3)
+    sem.dealias_setup()
+    B[0].upload(vel)
+    sem.set_convect(0, B[0])
+    B[1].upload(u)
+    sem.convect(0, B[1], B[2], field0=0, nf=3)
+    out, _ = B[2].download()
+    for f in range(3):
+        assert relerr(out[f].reshape(x.shape), ref[f]) <= 1e-12
+    # second slot, a single field, scaled accumulation:  out_1 += -0.5 * conv(u_1 ; c = u)
+    B[0].upload(u)
+    sem.set_convect(1, B[0])
+    cf2 = osem.set_convect(u, dl)
+    sem.convect(1, B[1], B[2], field0=1, nf=1, scale=-0.5, accumulate=True)
+    out2, _ = B[2].download()
+    assert relerr(out2[1].reshape(x.shape), ref[1] - 0.5 * osem.convect_dealiased(u[1], cf2, dl)) <= 1e-12
+    assert np.array_equal(out2[0], out[0]) and np.array_equal(out2[2], out[2])
+    # slot 0 is untouched by the second set_convect
+    sem.convect(0, B[1], B[2], field0=2, nf=1)
+    out3, _ = B[2].download()
+    assert relerr(out3[2].reshape(x.shape), ref[2]) <= 1e-12
+    B.close()
+    sem.close()
+
+
+def test_dealiased_convection_is_exact_for_polynomials(ctx):
+    """On an affine mesh the 3/2 rule integrates (c . grad u) v exactly for c, u, v of degree N:
+    sum_p [J^T (c.grad)(J u)]_p = integral of c . grad u."""
+    import nekstab_next_b200 as nb
+    N = 7
+    x, y, z, glo, geo = _mesh((2, 2, 2), N, 0.0)
+    sem = nb.Sem(ctx, N, x, y, z, glo_num=glo)
+    lay = nb.Layout(ctx, [x.size] * 3, [True] * 3)
+    lay.set_weight([geo['bm1']] * 3)
+    B = nb.Basis(lay, 3)
+    sem.dealias_setup()
+    B[0].upload([x ** 3, y * x, 1.0 + z ** 2])              # c
+    sem.set_convect(0, B[0])
+    B[1].upload([x ** 4 * y, z ** 3 + x, y ** 2 * z ** 2])  # u
+    sem.convect(0, B[1], B[2], 0, 3)
+    out, _ = B[2].download()
+    # integrals over [0,1]^3 of c . grad u, by hand:
+    #  u0 = x^4 y : c.grad = x^3 * 4 x^3 y + y x * x^4            -> 4/7 * 1/2 + 1/2 * 1/6
+    #  u1 = z^3+x : c.grad = x^3 * 1 + (1 + z^2) * 3 z^2          -> 1/4 + 1 + 3/5
+    #  u2 = y^2 z^2: c.grad = y x * 2 y z^2 + (1 + z^2) * 2 y^2 z -> 2 * 1/2 * 1/3 * 1/3 + 2 * 1/3 * (1/2 + 1/4)
+    exact = [4 / 7 / 2 + 1 / 12, 1 / 4 + 1 + 3 / 5, 1 / 9 + 0.5]
+    for f in range(3):
+        assert abs(out[f].sum() - exact[f]) <= 1e-12
+    B.close()
+    sem.close()
+
+
+def test_dealias_errors(ctx):
+    import nekstab_next_b200 as nb
+    x, y, z, glo, geo = _mesh((1, 1, 1), 7, 0.0)
+    sem = nb.Sem(ctx, 7, x, y, z, glo_num=glo)
+    lay = nb.Layout(ctx, [x.size] * 3, [True] * 3)
+    B = nb.Basis(lay, 2)
+    with pytest.raises(nb.NsbError):
+        sem.set_convect(0, B[0])                 # no dealias_setup yet
+    with pytest.raises(nb.NsbError):
+        sem.dealias_setup(11)                    # no kernel for (8, 11)
+    sem.dealias_setup()
+    with pytest.raises(nb.NsbError):
+        sem.convect(0, B[0], B[1])               # slot never set
+    sem.set_convect(0, B[0])
+    with pytest.raises(nb.NsbError):
+        sem.convect(0, B[0], B[0])               # in place
+    with pytest.raises(nb.NsbError):
+        sem.convect(2, B[0], B[1])
+    B.close()
+    sem.close()
+
+
+@pytest.mark.parametrize('nbd', [1, 2, 3])
+def test_bdf_ext_matches_oracle(ctx, nbd):
+    import nekstab_next_b200 as nb
+    N = 7
+    x, y, z, glo, geo = _mesh((2, 2, 1), N, 0.05)
+    sem = nb.Sem(ctx, N, x, y, z, glo_num=glo)
+    lay = nb.Layout(ctx, [x.size] * 3, [True] * 3)
+    lay.set_weight([geo['bm1']] * 3)
+    B = nb.Basis(lay, 6)
+    rng = np.random.default_rng(nbd)
+    host = [[rng.standard_normal(x.shape) for _ in range(3)] for _ in range(6)]   # bf e1 e2 v0 v1 v2
+    for c in range(6):
+        B[c].upload(host[c])
+    ab = np.array([23.0 / 12, -16.0 / 12, 5.0 / 12])
+    bd = np.array([11.0 / 6, -3.0, 1.5, -1.0 / 3])[:nbd + 1] if nbd == 3 else \
+        (np.array([1.5, -2.0, 0.5]) if nbd == 2 else np.array([1.0, -1.0]))
+    rho_dt = 1.0 / 2e-3
+    sem.bdf_ext(B[0], B[1], B[2], [B[3 + i] for i in range(nbd)], ab, bd, rho_dt, field0=0, nf=3)
+    for f in range(3):
+        bf, e1, e2 = host[0][f].copy(), host[1][f].copy(), host[2][f].copy()
+        osem.bdf_ext(bf, e1, e2, [host[3 + i][f] for i in range(nbd)], geo['bm1'], ab, bd, rho_dt)
+        for col, ref in ((0, bf), (1, e1), (2, e2)):
+            got = B[col].download()[0][f].reshape(x.shape)
+            assert relerr(got, ref) <= 1e-13
+    B.close()
+    sem.close()
