@@ -161,101 +161,217 @@ dealias_rx_kernel(const double *__restrict__ rst, int64_t npts, int64_t nfine, c
   }
 }
 
+// ---- line kernels: one thread owns a whole grid line of a contraction ---------------------------
+// The first version of convect (one output value per thread, both operands of every FMA read from
+// shared memory) ran at 4.7 TFLOP/s.  Here a thread loads the LX or LD values of one grid line into
+// registers once and produces every output of that line from them; the small matrices J (GLL -> GL)
+// and Dg (derivative on GL) sit in constant memory and, with the loops fully unrolled, become
+// immediate constant operands of the DFMAs: no shared-memory load per FMA.  Lines run along i, then
+// j, then k, so every stage changes line ownership through shared memory; the fastest dimension is
+// padded by one double (stride LX+1 / LD+1) so that line reads along i are conflict-free.
+// CTA = LD x LD threads (one per (J, I) fine-mesh column), one (element, field) per CTA, fields of an
+// element on consecutive CTAs so that the contravariant field c is re-read from L2, not DRAM.
+template <int LX, int LD>
+__constant__ double c_convJ[LD * LX];    // J[I][i]
+template <int LX, int LD>
+__constant__ double c_convD[LD * LD];    // Dg[I][m]
+
+template <int LX, int LD>
+struct LineSmem {
+  static constexpr int LXp = LX + 1, LDp = LD + 1, NT = LD * LD;
+  static constexpr int NSRC = LX * LX * LXp, NA1 = LX * LX * LDp, NA2 = LX * LD * LDp, NUF = LD * LD * LDp;
+  static constexpr int SRC = 0, TMP = NSRC, UF = NSRC + NA1 + NA2, TOTAL = UF + NUF;
+  static_assert(NA1 + NA2 >= NUF, "wf aliases the interpolation temporaries");
+  static_assert(NA2 <= NUF && NA1 <= NA1 + NA2, "projection temporaries fit");
+};
+
+template <int LX, int LD>
+__device__ __forceinline__ void load_src(double *__restrict__ src, const double *__restrict__ g) {
+  using L = LineSmem<LX, LD>;
+  for (int o = threadIdx.x; o < LX * LX * LX; o += L::NT) src[(o / LX) * L::LXp + o % LX] = g[o];
+}
+
+// uf[K][J][I] = (J x J x J) src, line by line; on return thread (J, I) = (tid / LD, tid % LD) also
+// holds its fine-mesh column uf[0..LD)[J][I] in col[].
+template <int LX, int LD>
+__device__ __forceinline__ void interp_lines(const double *__restrict__ src, double *__restrict__ a1,
+                                             double *__restrict__ a2, double *__restrict__ uf, double (&col)[LD]) {
+  using L = LineSmem<LX, LD>;
+  const int tid = threadIdx.x;
+  if (tid < LX * LX) {                                       // line (k, j) along i
+    double in[LX];
+#pragma unroll
+    for (int i = 0; i < LX; ++i) in[i] = src[tid * L::LXp + i];
+#pragma unroll
+    for (int I = 0; I < LD; ++I) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < LX; ++i) s = fma(c_convJ<LX, LD>[I * LX + i], in[i], s);
+      a1[tid * L::LDp + I] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < LX * LD) {                                       // line (k, I) along j
+    const int k = tid / LD, I = tid % LD;
+    double in[LX];
+#pragma unroll
+    for (int j = 0; j < LX; ++j) in[j] = a1[(k * LX + j) * L::LDp + I];
+#pragma unroll
+    for (int Jx = 0; Jx < LD; ++Jx) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < LX; ++j) s = fma(c_convJ<LX, LD>[Jx * LX + j], in[j], s);
+      a2[(k * LD + Jx) * L::LDp + I] = s;
+    }
+  }
+  __syncthreads();
+  {                                                          // line (J, I) along k
+    const int Jx = tid / LD, I = tid % LD;
+    double in[LX];
+#pragma unroll
+    for (int k = 0; k < LX; ++k) in[k] = a2[(k * LD + Jx) * L::LDp + I];
+#pragma unroll
+    for (int K = 0; K < LD; ++K) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < LX; ++k) s = fma(c_convJ<LX, LD>[K * LX + k], in[k], s);
+      col[K] = s;
+      uf[(K * LD + Jx) * L::LDp + I] = s;
+    }
+  }
+  __syncthreads();
+}
+
 // set_convect_new: c_a = sum_b rxf[3a+b] * J(v_b);  one CTA per element
 template <int LX, int LD>
-__global__ void __launch_bounds__(256)
-set_convect_kernel(const double *__restrict__ v, int64_t fstride, int64_t nfine, const double *__restrict__ Jg,
-                   const double *__restrict__ Dgg, const double *__restrict__ rxf, double *__restrict__ cf) {
-  using L = ConvSmem<LX, LD>;
-  constexpr int PT = (L::NF + 255) / 256;
+__global__ void __launch_bounds__(LD * LD)
+set_convect_kernel(const double *__restrict__ v, int64_t fstride, int64_t nfine, const double *__restrict__ rxf,
+                   double *__restrict__ cf) {
+  using L = LineSmem<LX, LD>;
+  constexpr int NC = LX * LX * LX, NF = LD * LD * LD;
   extern __shared__ double sm[];
   const int64_t e = blockIdx.x;
-  load_mats<LX, LD>(sm, Jg, Dgg);
-  double acc[3][PT];
+  const int tid = threadIdx.x;                               // = J * LD + I
+  double acc[3][LD];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int t = 0; t < PT; ++t) acc[a][t] = 0.0;
+    for (int K = 0; K < LD; ++K) acc[a][K] = 0.0;
   for (int b = 0; b < 3; ++b) {
+    load_src<LX, LD>(sm + L::SRC, v + (int64_t)b * fstride + e * NC);
     __syncthreads();
-    for (int i = threadIdx.x; i < L::NC; i += blockDim.x) sm[L::SRC + i] = v[(int64_t)b * fstride + e * L::NC + i];
-    __syncthreads();
-    interp3<LX, LD>(sm + L::SRC, sm + L::TMP, sm + L::TMP + L::T1, sm + L::FINE, sm + L::MAT);
+    double col[LD];
+    interp_lines<LX, LD>(sm + L::SRC, sm + L::TMP, sm + L::TMP + L::NA1, sm + L::UF, col);
 #pragma unroll
-    for (int t = 0; t < PT; ++t) {
-      const int o = threadIdx.x + t * 256;
-      if (o < L::NF) {
-        const double f = sm[L::FINE + o];
+    for (int K = 0; K < LD; ++K) {
+      const int64_t o = e * NF + K * LD * LD + tid;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) acc[a][t] = fma(rxf[(int64_t)(3 * a + b) * nfine + e * L::NF + o], f, acc[a][t]);
-      }
+      for (int a = 0; a < 3; ++a) acc[a][K] = fma(rxf[(int64_t)(3 * a + b) * nfine + o], col[K], acc[a][K]);
     }
   }
 #pragma unroll
-  for (int t = 0; t < PT; ++t) {
-    const int o = threadIdx.x + t * 256;
-    if (o < L::NF) {
+  for (int K = 0; K < LD; ++K) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) cf[(int64_t)a * nfine + e * L::NF + o] = acc[a][t];
-    }
+    for (int a = 0; a < 3; ++a) cf[(int64_t)a * nfine + e * NF + K * LD * LD + tid] = acc[a][K];
   }
 }
 
-// convect_new: out (+)= scale * J^T [ (c . grad_rst)(J u) ];  grid (nel, nf)
+// convect_new: out (+)= scale * J^T [ (c . grad_rst)(J u) ];  CTA = (element, field), field fastest
 template <int LX, int LD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LD * LD)
 convect_kernel(const double *__restrict__ u, double *__restrict__ out, int64_t fstride_in, int64_t fstride_out,
-               int64_t nfine, const double *__restrict__ Jg, const double *__restrict__ Dgg,
-               const double *__restrict__ cf, double scale, int accumulate) {
-  using L = ConvSmem<LX, LD>;
+               int64_t nfine, int nf, const double *__restrict__ cf, double scale, int accumulate) {
+  using L = LineSmem<LX, LD>;
+  constexpr int NC = LX * LX * LX, NF = LD * LD * LD;
   extern __shared__ double sm[];
-  const int64_t e = blockIdx.x;
-  const int f = blockIdx.y;
-  const double *Jm = sm + L::MAT, *Dg = sm + L::MAT + LD * LX;
-  load_mats<LX, LD>(sm, Jg, Dgg);
-  for (int i = threadIdx.x; i < L::NC; i += blockDim.x) sm[L::SRC + i] = u[(int64_t)f * fstride_in + e * L::NC + i];
+  const int64_t e = blockIdx.x / nf;
+  const int f = (int)(blockIdx.x % nf);
+  const int tid = threadIdx.x;
+  double *src = sm + L::SRC, *uf = sm + L::UF, *wf = sm + L::TMP;   // wf aliases a1/a2 after the interpolation
+  load_src<LX, LD>(src, u + (int64_t)f * fstride_in + e * NC);
   __syncthreads();
-  double *uf = sm + L::FINE, *wf = sm + L::TMP;     // wf aliases t1/t2 once the interpolation is done
-  interp3<LX, LD>(sm + L::SRC, sm + L::TMP, sm + L::TMP + L::T1, uf, Jm);
-  // fine-mesh gradient and the pointwise contraction with the contravariant convecting field
-  const double *cr = cf + e * L::NF, *cs = cr + nfine, *ct = cs + nfine;
-  for (int o = threadIdx.x; o < L::NF; o += blockDim.x) {
-    const int I = o % LD, Jx = (o / LD) % LD, K = o / (LD * LD);
-    double ur = 0.0, us = 0.0, ut = 0.0;
+  double col[LD];
+  interp_lines<LX, LD>(src, sm + L::TMP, sm + L::TMP + L::NA1, uf, col);
+  const double *cr = cf + e * NF, *cs = cr + nfine, *ct = cs + nfine;
+  {                                                          // r: line (K, J) = tid along I
+    double in[LD];
 #pragma unroll
-    for (int m = 0; m < LD; ++m) {
-      ur = fma(Dg[I * LD + m], uf[(K * LD + Jx) * LD + m], ur);
-      us = fma(Dg[Jx * LD + m], uf[(K * LD + m) * LD + I], us);
-      ut = fma(Dg[K * LD + m], uf[(m * LD + Jx) * LD + I], ut);
+    for (int I = 0; I < LD; ++I) in[I] = uf[tid * L::LDp + I];
+#pragma unroll
+    for (int I = 0; I < LD; ++I) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[I * LD + m], in[m], s);
+      wf[tid * L::LDp + I] = cr[tid * LD + I] * s;
     }
-    wf[o] = cr[o] * ur + cs[o] * us + ct[o] * ut;
   }
   __syncthreads();
-  // project back (intp_rstd, idir = 1): p1[K][J][i], p2[K][j][i], out[k][j][i]
-  double *p1 = uf, *p2 = wf;      // uf is free after the gradient; wf is free once p1 is complete
-  static_assert(LD * LD * LX <= L::NF && LD * LX * LX <= L::T1 + L::T2, "projection temporaries fit");
-  for (int o = threadIdx.x; o < LD * LD * LX; o += blockDim.x) {
-    const int i = o % LX, KJ = o / LX;
-    double s = 0.0;
+  {                                                          // s: line (K, I) along J
+    const int K = tid / LD, I = tid % LD;
+    double in[LD];
 #pragma unroll
-    for (int I = 0; I < LD; ++I) s = fma(Jm[I * LX + i], wf[KJ * LD + I], s);
-    p1[o] = s;
+    for (int Jx = 0; Jx < LD; ++Jx) in[Jx] = uf[(K * LD + Jx) * L::LDp + I];
+#pragma unroll
+    for (int Jx = 0; Jx < LD; ++Jx) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[Jx * LD + m], in[m], s);
+      wf[(K * LD + Jx) * L::LDp + I] += cs[(K * LD + Jx) * LD + I] * s;
+    }
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < LD * LX * LX; o += blockDim.x) {
-    const int i = o % LX, j = (o / LX) % LX, K = o / (LX * LX);
-    double s = 0.0;
+  {                                                          // t: line (J, I) along K, from the registers
+    const int Jx = tid / LD, I = tid % LD;
+    double w[LD];
 #pragma unroll
-    for (int Jx = 0; Jx < LD; ++Jx) s = fma(Jm[Jx * LX + j], p1[(K * LD + Jx) * LX + i], s);
-    p2[o] = s;
+    for (int K = 0; K < LD; ++K) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[K * LD + m], col[m], s);
+      w[K] = wf[(K * LD + Jx) * L::LDp + I] + ct[(K * LD + Jx) * LD + I] * s;
+    }
+    // project back along k at once: the thread owns the whole (J, I) column of w
+    double *b2 = uf;                                         // [k][J][I], uf is dead (other threads' s/r reads are done)
+#pragma unroll
+    for (int k = 0; k < LX; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int K = 0; K < LD; ++K) s = fma(c_convJ<LX, LD>[K * LX + k], w[K], s);
+      b2[(k * LD + Jx) * L::LDp + I] = s;
+    }
   }
   __syncthreads();
-  double *dst = out + (int64_t)f * fstride_out + e * L::NC;
-  for (int o = threadIdx.x; o < L::NC; o += blockDim.x) {
-    const int ji = o % (LX * LX), k = o / (LX * LX);
-    double s = 0.0;
+  double *b1 = wf;                                           // [k][j][I]; wf is dead
+  if (tid < LX * LD) {                                       // line (k, I) along J
+    const int k = tid / LD, I = tid % LD;
+    double in[LD];
 #pragma unroll
-    for (int K = 0; K < LD; ++K) s = fma(Jm[K * LX + k], p2[K * LX * LX + ji], s);
+    for (int Jx = 0; Jx < LD; ++Jx) in[Jx] = uf[(k * LD + Jx) * L::LDp + I];
+#pragma unroll
+    for (int j = 0; j < LX; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int Jx = 0; Jx < LD; ++Jx) s = fma(c_convJ<LX, LD>[Jx * LX + j], in[Jx], s);
+      b1[(k * LX + j) * L::LDp + I] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < LX * LX) {                                       // line (k, j) along I
+    double in[LD];
+#pragma unroll
+    for (int I = 0; I < LD; ++I) in[I] = b1[tid * L::LDp + I];
+#pragma unroll
+    for (int i = 0; i < LX; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int I = 0; I < LD; ++I) s = fma(c_convJ<LX, LD>[I * LX + i], in[I], s);
+      src[tid * L::LXp + i] = s;
+    }
+  }
+  __syncthreads();
+  double *dst = out + (int64_t)f * fstride_out + e * NC;
+  for (int o = tid; o < NC; o += L::NT) {
+    const double s = src[(o / LX) * L::LXp + o % LX];
     dst[o] = accumulate ? fma(scale, s, dst[o]) : scale * s;
   }
 }
@@ -301,13 +417,16 @@ int conv_field_ptr(nsb_sem_t S, nsb_basis_t B, int col, int field, int nf, doubl
 }
 
 template <int LX, int LD>
-int dealias_setup_t(nsb_sem_t S, const double *wd_d) {
+int dealias_setup_t(nsb_sem_t S, const double *wd_d, const double *J_h, const double *Dg_h) {
   using L = ConvSmem<LX, LD>;
-  const size_t smem = sizeof(double) * L::TOTAL;
+  using LL = LineSmem<LX, LD>;
+  const size_t smem = sizeof(double) * L::TOTAL, smem_l = sizeof(double) * LL::TOTAL;
   const int64_t nfine = S->nel * L::NF;
+  NSB_CUDA(cudaMemcpyToSymbol(c_convJ<LX, LD>, J_h, sizeof(double) * LD * LX));
+  NSB_CUDA(cudaMemcpyToSymbol(c_convD<LX, LD>, Dg_h, sizeof(double) * LD * LD));
   NSB_CUDA(cudaFuncSetAttribute(dealias_rx_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NSB_CUDA(cudaFuncSetAttribute(set_convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NSB_CUDA(cudaFuncSetAttribute(convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(set_convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+  NSB_CUDA(cudaFuncSetAttribute(convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
   dealias_rx_kernel<LX, LD><<<dim3((unsigned)S->nel, 9), 256, smem, S->ctx->stream>>>(S->rst_d, S->npts, nfine, S->J_d,
                                                                                   S->Dg_d, wd_d, S->rxf_d);
   S->ctx->launches++;
@@ -317,9 +436,9 @@ int dealias_setup_t(nsb_sem_t S, const double *wd_d) {
 
 template <int LX, int LD>
 int set_convect_t(nsb_sem_t S, const double *v, int64_t fstride, double *cf) {
-  using L = ConvSmem<LX, LD>;
-  set_convect_kernel<LX, LD><<<(unsigned)S->nel, 256, sizeof(double) * L::TOTAL, S->ctx->stream>>>(
-      v, fstride, S->nel * L::NF, S->J_d, S->Dg_d, S->rxf_d, cf);
+  using LL = LineSmem<LX, LD>;
+  set_convect_kernel<LX, LD><<<(unsigned)S->nel, LL::NT, sizeof(double) * LL::TOTAL, S->ctx->stream>>>(
+      v, fstride, S->nel * (int64_t)(LD * LD * LD), S->rxf_d, cf);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -328,9 +447,9 @@ int set_convect_t(nsb_sem_t S, const double *v, int64_t fstride, double *cf) {
 template <int LX, int LD>
 int convect_t(nsb_sem_t S, const double *u, double *out, int64_t fsi, int64_t fso, int nf, const double *cf,
               double scale, int accumulate) {
-  using L = ConvSmem<LX, LD>;
-  convect_kernel<LX, LD><<<dim3((unsigned)S->nel, nf), 256, sizeof(double) * L::TOTAL, S->ctx->stream>>>(
-      u, out, fsi, fso, S->nel * L::NF, S->J_d, S->Dg_d, cf, scale, accumulate);
+  using LL = LineSmem<LX, LD>;
+  convect_kernel<LX, LD><<<(unsigned)(S->nel * nf), LL::NT, sizeof(double) * LL::TOTAL, S->ctx->stream>>>(
+      u, out, fsi, fso, S->nel * (int64_t)(LD * LD * LD), nf, cf, scale, accumulate);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -376,7 +495,7 @@ extern "C" int nsb_sem_dealias_setup(nsb_sem_t S, int lxd) {
   int rc;
   {
     auto run = [&]() -> int {
-#define CALL_SETUP(A, B) dealias_setup_t<A, B>(S, wd_d)
+#define CALL_SETUP(A, B) dealias_setup_t<A, B>(S, wd_d, J.data(), Dg.data())
       NSB_CONV_DISPATCH(S, CALL_SETUP);
 #undef CALL_SETUP
     };
