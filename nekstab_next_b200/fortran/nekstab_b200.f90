@@ -261,6 +261,223 @@ module nekstab_b200
       end function
    end interface
 
+   !> Device-side operators, dense mirrors and stand-alone kernels (same header, include/nekstab_b200.h).
+   !> Not bound here because they serve the C / Python test and bench harness only: nsb_prof_*, nsb_profiler_*,
+   !> nsb_timer_*, nsb_flush_l2, nsb_launch_count, nsb_stream, nsb_rank, nsb_version, nsb_gll, nsb_host_alloc /
+   !> nsb_host_free, nsb_host_gs_plan, nsb_host_exchange_plan, nsb_allreduce_host, nsb_orthonormalize_async,
+   !> nsb_p2p_enabled, nsb_basis_ncols, nsb_basis_col_ptr, nsb_layout_info, nsb_layout_destroy, nsb_sem_get,
+   !> nsb_sem_npts.
+   interface
+      function nsb_sync(ctx) bind(C, name='nsb_sync') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int) :: ierr
+      end function
+      function nsb_vec_norm(b, col, alpha) bind(C, name='nsb_vec_norm') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: col
+         real(c_double) :: alpha
+         integer(c_int) :: ierr
+      end function
+      function nsb_orthonormalize(b, k, col_w, mode, h, passes) bind(C, name='nsb_orthonormalize') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: k, col_w, mode
+         real(c_double) :: h(*)
+         integer(c_int) :: passes, ierr
+      end function
+      function nsb_basis_gram(b, k, G, ldg) bind(C, name='nsb_basis_gram') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: k, ldg
+         real(c_double) :: G(ldg, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_basis_qr(b, k, mode, R, ldr) bind(C, name='nsb_basis_qr') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: k, mode, ldr
+         real(c_double) :: R(ldr, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_basis_rotate(b, k, Z, ldz, rotate_time) bind(C, name='nsb_basis_rotate') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: b
+         integer(c_int), value :: k, ldz, rotate_time
+         real(c_double) :: Z(ldz, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_create(ctx, dim, N, nel, x, y, z, mask, glo_num, sem) bind(C, name='nsb_sem_create') &
+         result(ierr)
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: dim, N
+         integer(c_int64_t), value :: nel
+         real(c_double) :: x(*), y(*), z(*), mask(*)
+         integer(c_int64_t) :: glo_num(*)
+         type(c_ptr) :: sem
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_destroy(sem) bind(C, name='nsb_sem_destroy') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: sem
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_setup_exchange(sem) bind(C, name='nsb_sem_setup_exchange') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: sem
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_axhelm(sem, bin, cin, bout, cout, field, h1, h2) bind(C, name='nsb_sem_axhelm') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, bin, bout
+         integer(c_int), value :: cin, cout, field
+         real(c_double), value :: h1, h2
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_ax(sem, bin, cin, bout, cout, field, h1, h2) bind(C, name='nsb_sem_ax') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, bin, bout
+         integer(c_int), value :: cin, cout, field
+         real(c_double), value :: h1, h2
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_dssum(sem, b, col, field) bind(C, name='nsb_sem_dssum') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: sem, b
+         integer(c_int), value :: col, field
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_col2(sem, b, col, field, which) bind(C, name='nsb_sem_col2') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: sem, b
+         integer(c_int), value :: col, field, which
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_hmholtz(sem, brhs, crhs, bx, cx, field, h1, h2, tol, maxit, iters, res) &
+         bind(C, name='nsb_sem_hmholtz') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, brhs, bx
+         integer(c_int), value :: crhs, cx, field, maxit
+         real(c_double), value :: h1, h2, tol
+         integer(c_int) :: iters
+         real(c_double) :: res
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_dealias_setup(sem, lxd) bind(C, name='nsb_sem_dealias_setup') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: sem
+         integer(c_int), value :: lxd
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_set_convect(sem, slot, b, col, field0) bind(C, name='nsb_sem_set_convect') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: sem, b
+         integer(c_int), value :: slot, col, field0
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_convect(sem, slot, bin, cin, bout, cout, field0, nf, scale, accumulate) &
+         bind(C, name='nsb_sem_convect') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, bin, bout
+         integer(c_int), value :: slot, cin, cout, field0, nf, accumulate
+         real(c_double), value :: scale
+         integer(c_int) :: ierr
+      end function
+      function nsb_sem_bdf_ext(sem, b, col_bf, col_e1, col_e2, col_vlag, nbd, field0, nf, ab, bd, rho_over_dt) &
+         bind(C, name='nsb_sem_bdf_ext') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, b
+         integer(c_int), value :: col_bf, col_e1, col_e2, nbd, field0, nf
+         integer(c_int) :: col_vlag(*)
+         real(c_double) :: ab(*), bd(*)
+         real(c_double), value :: rho_over_dt
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_create_sem(sem, nfields_apply, alpha, beta, h1, h2, cx, cy, cz, op) &
+         bind(C, name='nsb_op_create_sem') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem
+         integer(c_int), value :: nfields_apply
+         real(c_double), value :: alpha, beta, h1, h2
+         type(c_ptr), value :: cx, cy, cz        !< c_loc of the convecting velocity, or c_null_ptr
+         type(c_ptr) :: op
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_create_compose(layout, outer, inner, op) bind(C, name='nsb_op_create_compose') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: layout, outer, inner
+         type(c_ptr) :: op
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_apply(op, bin, cin, bout, cout) bind(C, name='nsb_op_apply') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: op, bin, bout
+         integer(c_int), value :: cin, cout
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_destroy(op) bind(C, name='nsb_op_destroy') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: op
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_count(op, napply) bind(C, name='nsb_op_count') result(ierr)
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: op
+         integer(c_int64_t) :: napply
+         integer(c_int) :: ierr
+      end function
+      function nsb_eig(A, lda, n, vecs, vals) bind(C, name='nsb_eig') result(ierr)
+         import :: c_int, c_double, c_double_complex
+         integer(c_int), value :: lda, n
+         real(c_double) :: A(lda, *)
+         complex(c_double_complex) :: vecs(n, *), vals(*)
+         integer(c_int) :: ierr
+      end function
+      function nsb_schur(A, lda, n, vecs, vals) bind(C, name='nsb_schur') result(ierr)
+         import :: c_int, c_double, c_double_complex
+         integer(c_int), value :: lda, n
+         real(c_double) :: A(lda, *), vecs(n, *)
+         complex(c_double_complex) :: vals(*)
+         integer(c_int) :: ierr
+      end function
+      function nsb_ordschur(T, ldt, Q, ldq, selected, n) bind(C, name='nsb_ordschur') result(ierr)
+         import :: c_int, c_double
+         integer(c_int), value :: ldt, ldq, n
+         real(c_double) :: T(ldt, *), Q(ldq, *)
+         integer(c_int) :: selected(*)
+         integer(c_int) :: ierr
+      end function
+      function nsb_lstsq(A, lda, m, n, b, x) bind(C, name='nsb_lstsq') result(ierr)
+         import :: c_int, c_double
+         integer(c_int), value :: lda, m, n
+         real(c_double) :: A(lda, *), b(*), x(*)
+         integer(c_int) :: ierr
+      end function
+      function nsb_svd(A, lda, m, n, U, S, V) bind(C, name='nsb_svd') result(ierr)
+         import :: c_int, c_double
+         integer(c_int), value :: lda, m, n
+         real(c_double) :: A(lda, *), U(m, *), S(*), V(n, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_select_eigenvalues(selected, cnt, vals, delta, nev, n) bind(C, name='nsb_select_eigenvalues') &
+         result(ierr)
+         import :: c_int, c_double, c_double_complex
+         integer(c_int) :: selected(*), cnt
+         complex(c_double_complex) :: vals(*)
+         real(c_double), value :: delta
+         integer(c_int), value :: nev, n
+         integer(c_int) :: ierr
+      end function
+   end interface
+   public :: nsb_sync, nsb_vec_norm, nsb_orthonormalize, nsb_basis_gram, nsb_basis_qr, nsb_basis_rotate
+   public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
+   public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
+   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_compose, nsb_op_apply, nsb_op_destroy, nsb_op_count
+   public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues
+
+
 contains
 
    !> The reference prints and calls nek_end on fatal conditions (core/nek_vectors.f90:108-111);
