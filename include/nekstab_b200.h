@@ -245,8 +245,9 @@ int nsb_sem_hmholtz(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, i
 
 /* Dealiased convection of Nek5000's perturbation step ([UPSTREAM-RECALL] convect.f set_dealias_rx /
  * set_convect_new / convect_new: the terms advabp adds for (U.grad)u' and (u'.grad)U; SURVEY.md
- * section 8 f-3).  3-D.  The fine mesh has lxd Gauss-Legendre points per direction (lxd <= 0: Nek's
- * 3 lx1 / 2).
+ * section 8 f-3).  The fine mesh has lxd Gauss-Legendre points per direction (lxd <= 0: Nek's 3 lx1 / 2).
+ * 3-D: line kernels for (lx1, lxd) = (8,12), (6,9), (5,8), (4,6); 2-D (the reference's cylinder and
+ * backward-facing-step meshes): any lxd, `dim` velocity fields instead of three.
  *   dealias_setup : metrics rxm1..tzm1 interpolated to the fine mesh times the Gauss weights
  *   set_convect   : slot (0 or 1) <- contravariant fine-mesh form of the velocity in fields
  *                   field0..field0+2 of (b, col)

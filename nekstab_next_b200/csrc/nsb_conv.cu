@@ -376,6 +376,105 @@ convect_kernel(const double *__restrict__ u, double *__restrict__ out, int64_t f
   }
 }
 
+// ---- 2-D (the reference's cylinder / backward-facing-step cases): runtime sizes, one output per
+// thread; these meshes have a few thousand elements of 36 points, the kernels are not hot -----------
+// shared layout: Jm [ld*lx] | Dg [ld*ld] | src [lx*lx] | t1 [lx*ld] | uf [ld*ld] | wf [ld*ld]
+__device__ __forceinline__ void interp2(int lx, int ld, const double *Jm, const double *src, double *t1, double *uf) {
+  for (int o = threadIdx.x; o < lx * ld; o += blockDim.x) {      // t1[j][I]
+    const int I = o % ld, j = o / ld;
+    double s = 0.0;
+    for (int i = 0; i < lx; ++i) s = fma(Jm[I * lx + i], src[j * lx + i], s);
+    t1[o] = s;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < ld * ld; o += blockDim.x) {      // uf[J][I]
+    const int I = o % ld, Jx = o / ld;
+    double s = 0.0;
+    for (int j = 0; j < lx; ++j) s = fma(Jm[Jx * lx + j], t1[j * ld + I], s);
+    uf[o] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_mats2(int lx, int ld, double *sm, const double *__restrict__ Jg,
+                                           const double *__restrict__ Dgg) {
+  for (int i = threadIdx.x; i < ld * lx; i += blockDim.x) sm[i] = Jg[i];
+  for (int i = threadIdx.x; i < ld * ld; i += blockDim.x) sm[ld * lx + i] = Dgg[i];
+}
+
+// mode 0: rxf[a][e] = (w_I w_J) J(rst[a][e]), grid (nel, 4)
+// mode 1: c_a = sum_b rxf[2a+b] J(v_b), grid (nel, 1)
+// mode 2: out (+)= scale J^T[(c . grad)(J u)], grid (nel, nf)
+__global__ void __launch_bounds__(128)
+conv2d_kernel(int mode, int lx, int ld, const double *__restrict__ in, double *__restrict__ out, int64_t npts,
+              int64_t nfine, int64_t fs_in, int64_t fs_out, const double *__restrict__ Jg,
+              const double *__restrict__ Dgg, const double *__restrict__ wd, const double *__restrict__ fine_in,
+              double scale, int accumulate) {
+  extern __shared__ double sm[];
+  const int nc = lx * lx, nf2 = ld * ld;
+  double *Jm = sm, *Dg = Jm + ld * lx, *src = Dg + ld * ld, *t1 = src + nc, *uf = t1 + lx * ld, *wf = uf + nf2;
+  const int64_t e = blockIdx.x;
+  const int y = blockIdx.y;
+  load_mats2(lx, ld, sm, Jg, Dgg);
+  if (mode == 0) {
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) src[i] = in[(int64_t)y * npts + e * nc + i];
+    __syncthreads();
+    interp2(lx, ld, Jm, src, t1, uf);
+    for (int o = threadIdx.x; o < nf2; o += blockDim.x)
+      out[(int64_t)y * nfine + e * nf2 + o] = wd[o % ld] * wd[o / ld] * uf[o];
+    return;
+  }
+  if (mode == 1) {
+    for (int b = 0; b < 2; ++b) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < nc; i += blockDim.x) src[i] = in[(int64_t)b * fs_in + e * nc + i];
+      __syncthreads();
+      interp2(lx, ld, Jm, src, t1, uf);
+      for (int o = threadIdx.x; o < nf2; o += blockDim.x) {
+        const int64_t q = e * nf2 + o;
+        for (int a = 0; a < 2; ++a) {
+          const double t = fine_in[(int64_t)(2 * a + b) * nfine + q] * uf[o];
+          out[(int64_t)a * nfine + q] = b == 0 ? t : out[(int64_t)a * nfine + q] + t;
+        }
+      }
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) src[i] = in[(int64_t)y * fs_in + e * nc + i];
+  __syncthreads();
+  interp2(lx, ld, Jm, src, t1, uf);
+  const double *cr = fine_in + e * nf2, *cs = cr + nfine;
+  for (int o = threadIdx.x; o < nf2; o += blockDim.x) {
+    const int I = o % ld, Jx = o / ld;
+    double ur = 0.0, us = 0.0;
+    for (int m = 0; m < ld; ++m) {
+      ur = fma(Dg[I * ld + m], uf[Jx * ld + m], ur);
+      us = fma(Dg[Jx * ld + m], uf[m * ld + I], us);
+    }
+    wf[o] = cr[o] * ur + cs[o] * us;
+  }
+  __syncthreads();
+  double *p1 = uf;                                               // [J][i]
+  for (int o = threadIdx.x; o < ld * lx; o += blockDim.x) {
+    const int i = o % lx, Jx = o / lx;
+    double s = 0.0;
+    for (int I = 0; I < ld; ++I) s = fma(Jm[I * lx + i], wf[Jx * ld + I], s);
+    p1[o] = s;
+  }
+  __syncthreads();
+  double *dst = out + (int64_t)y * fs_out + e * nc;
+  for (int o = threadIdx.x; o < nc; o += blockDim.x) {
+    const int i = o % lx, j = o / lx;
+    double s = 0.0;
+    for (int Jx = 0; Jx < ld; ++Jx) s = fma(Jm[Jx * lx + j], p1[Jx * lx + i], s);
+    dst[o] = accumulate ? fma(scale, s, dst[o]) : scale * s;
+  }
+}
+
+inline size_t conv2d_smem(int lx, int ld) {
+  return sizeof(double) * ((size_t)ld * lx + (size_t)ld * ld + (size_t)lx * lx + (size_t)lx * ld + 2 * (size_t)ld * ld);
+}
+
 // makextp + makebdfp, one pass; grid-stride over the points of one field, grid.y = field
 __global__ void __launch_bounds__(256)
 bdf_ext_kernel(double *__restrict__ bf, double *__restrict__ e1, double *__restrict__ e2, const double *v0,
@@ -470,8 +569,8 @@ int convect_t(nsb_sem_t S, const double *u, double *out, int64_t fsi, int64_t fs
 
 extern "C" int nsb_sem_dealias_setup(nsb_sem_t S, int lxd) {
   NSB_REQUIRE(S, "nsb_sem_dealias_setup: NULL");
-  NSB_REQUIRE(S->dim == 3, "nsb_sem_dealias_setup: 3-D meshes only (dim=%d)", S->dim);
-  if (lxd <= 0) lxd = S->lx == 5 ? 8 : 3 * S->lx / 2;
+  if (lxd <= 0) lxd = (S->dim == 3 && S->lx == 5) ? 8 : 3 * S->lx / 2;
+  NSB_REQUIRE(S->dim == 3 || (lxd >= S->lx && lxd <= 24), "nsb_sem_dealias_setup: lxd=%d out of range", lxd);
   cudaSetDevice(S->ctx->device);
   if (S->lxd == lxd && S->rxf_d) return NSB_OK;
   const int lx = S->lx;
@@ -483,17 +582,23 @@ extern "C" int nsb_sem_dealias_setup(nsb_sem_t S, int lxd) {
     *p = nullptr;
   }
   S->lxd = lxd;
-  const int64_t nfine = S->nel * (int64_t)lxd * lxd * lxd;
+  const int64_t nfine = S->nel * (int64_t)lxd * lxd * (S->dim == 3 ? lxd : 1);
   double *wd_d = nullptr;
   NSB_CUDA(cudaMalloc(&S->J_d, sizeof(double) * lxd * lx));
   NSB_CUDA(cudaMalloc(&S->Dg_d, sizeof(double) * lxd * lxd));
   NSB_CUDA(cudaMalloc(&wd_d, sizeof(double) * lxd));
-  NSB_CUDA(cudaMalloc(&S->rxf_d, sizeof(double) * 9 * nfine));
+  NSB_CUDA(cudaMalloc(&S->rxf_d, sizeof(double) * S->dim * S->dim * nfine));
   NSB_CUDA(cudaMemcpy(S->J_d, J.data(), sizeof(double) * lxd * lx, cudaMemcpyHostToDevice));
   NSB_CUDA(cudaMemcpy(S->Dg_d, Dg.data(), sizeof(double) * lxd * lxd, cudaMemcpyHostToDevice));
   NSB_CUDA(cudaMemcpy(wd_d, wd.data(), sizeof(double) * lxd, cudaMemcpyHostToDevice));
   int rc;
-  {
+  if (S->dim == 2) {
+    conv2d_kernel<<<dim3((unsigned)S->nel, 4), 128, conv2d_smem(lx, lxd), S->ctx->stream>>>(
+        0, lx, lxd, S->rst_d, S->rxf_d, S->npts, nfine, 0, 0, S->J_d, S->Dg_d, wd_d, nullptr, 1.0, 0);
+    S->ctx->launches++;
+    rc = cudaGetLastError() == cudaSuccess ? NSB_OK : NSB_ECUDA;
+    if (rc != NSB_OK) set_error("nsb_sem_dealias_setup: 2-D metric kernel failed to launch");
+  } else {
     auto run = [&]() -> int {
 #define CALL_SETUP(A, B) dealias_setup_t<A, B>(S, wd_d, J.data(), Dg.data())
       NSB_CONV_DISPATCH(S, CALL_SETUP);
@@ -516,11 +621,18 @@ extern "C" int nsb_sem_set_convect(nsb_sem_t S, int slot, nsb_basis_t B, int col
   NSB_REQUIRE(S->lxd > 0 && S->rxf_d, "nsb_sem_set_convect: call nsb_sem_dealias_setup first");
   double *v;
   int64_t fs;
-  NSB_CHECK(conv_field_ptr(S, B, col, field0, 3, &v, &fs, "nsb_sem_set_convect"));
+  NSB_CHECK(conv_field_ptr(S, B, col, field0, S->dim, &v, &fs, "nsb_sem_set_convect"));
   cudaSetDevice(S->ctx->device);
-  const int64_t nfine = S->nel * (int64_t)S->lxd * S->lxd * S->lxd;
-  if (!S->cfine_d[slot]) NSB_CUDA(cudaMalloc(&S->cfine_d[slot], sizeof(double) * 3 * nfine));
+  const int64_t nfine = S->nel * (int64_t)S->lxd * S->lxd * (S->dim == 3 ? S->lxd : 1);
+  if (!S->cfine_d[slot]) NSB_CUDA(cudaMalloc(&S->cfine_d[slot], sizeof(double) * S->dim * nfine));
   double *cf = S->cfine_d[slot];
+  if (S->dim == 2) {
+    conv2d_kernel<<<dim3((unsigned)S->nel, 1), 128, conv2d_smem(S->lx, S->lxd), S->ctx->stream>>>(
+        1, S->lx, S->lxd, v, cf, S->npts, nfine, fs, 0, S->J_d, S->Dg_d, nullptr, S->rxf_d, 1.0, 0);
+    S->ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
 #define CALL_SC(A, B) set_convect_t<A, B>(S, v, fs, cf)
   NSB_CONV_DISPATCH(S, CALL_SC);
 #undef CALL_SC
@@ -539,6 +651,14 @@ extern "C" int nsb_sem_convect(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, 
   NSB_REQUIRE(u != w, "nsb_sem_convect: input and output are the same vector");
   cudaSetDevice(S->ctx->device);
   const double *cf = S->cfine_d[slot];
+  if (S->dim == 2) {
+    conv2d_kernel<<<dim3((unsigned)S->nel, nf), 128, conv2d_smem(S->lx, S->lxd), S->ctx->stream>>>(
+        2, S->lx, S->lxd, u, w, S->npts, S->nel * (int64_t)S->lxd * S->lxd, fsi, fso, S->J_d, S->Dg_d, nullptr, cf, scale,
+        accumulate);
+    S->ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
 #define CALL_CV(A, B) convect_t<A, B>(S, u, w, fsi, fso, nf, cf, scale, accumulate)
   NSB_CONV_DISPATCH(S, CALL_CV);
 #undef CALL_CV

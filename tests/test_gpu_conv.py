@@ -206,3 +206,62 @@ def test_scalar_diffusion_decay_rate(ctx):
     T, _ = _device_scalar_steps(ctx, x, y, z, glo, mask, geo['bm1'], [0 * x, 0 * x, 0 * x], T0, kappa, dt, nsteps)
     amp = float(np.sum(T * T0 * geo['bm1']) / np.sum(T0 * T0 * geo['bm1']))
     assert abs(amp - np.exp(-3 * np.pi ** 2 * kappa * dt * nsteps)) <= 2e-5
+
+
+# ---- 2-D: the reference's own meshes and base flows (tests/golden/*_mesh.npz) ----------------------------
+@pytest.mark.parametrize('name', ['cyl', 'bfs'])
+def test_dealiased_convection_2d_reference_base_flows(ctx, name):
+    """(U . grad) U of the committed base flow on the reference's curved 2-D mesh, lxd = 3 lx1 / 2."""
+    import json
+    from pathlib import Path
+    import nekstab_next_b200 as nb
+    gold = Path(__file__).resolve().parent / 'golden'
+    N = json.loads((gold / 'known_answers.json').read_text())[name]['N']
+    g = np.load(gold / f'{name}_mesh.npz')
+    x, y, u, v, glo = g['x'], g['y'], g['u'], g['v'], g['glo'].astype(np.int64)
+    geo = osem.geometry(N, x, y)
+    dl = osem.dealias_setup(N, 3 * (N + 1) // 2, geo['rst'])
+    cf = osem.set_convect([u, v], dl)
+    ref = [osem.convect_dealiased(a, cf, dl) for a in (u, v)]
+    sem = nb.Sem(ctx, N, x, y, None, mask=None, glo_num=glo)
+    lay = nb.Layout(ctx, [x.size, x.size], [True, True])
+    lay.set_weight([geo['bm1'], geo['bm1']])
+    B = nb.Basis(lay, 2)
+    sem.dealias_setup()
+    B[0].upload([u, v])
+    sem.set_convect(0, B[0])
+    sem.convect(0, B[0], B[1], field0=0, nf=2)
+    out, _ = B[1].download()
+    for f in range(2):
+        assert relerr(out[f].reshape(x.shape), ref[f]) <= 1e-12
+    # accumulate with a scale on one field
+    sem.convect(0, B[0], B[1], field0=1, nf=1, scale=2.5, accumulate=True)
+    out2, _ = B[1].download()
+    assert relerr(out2[1].reshape(x.shape), 3.5 * ref[1]) <= 1e-12
+    assert np.array_equal(out2[0], out[0])
+    B.close()
+    sem.close()
+
+
+def test_dealiased_convection_2d_box_other_orders(ctx):
+    import nekstab_next_b200 as nb
+    for N, lxd in ((3, 0), (6, 0), (5, 10)):
+        x, y, glo = osem.box_mesh_2d(3, 2, N, deform=0.04)
+        geo = osem.geometry(N, x, y)
+        ld = lxd if lxd else 3 * (N + 1) // 2
+        dl = osem.dealias_setup(N, ld, geo['rst'])
+        rng = np.random.default_rng(N)
+        vel = [rng.standard_normal(x.shape), np.cos(x) * y]
+        w = rng.standard_normal(x.shape)
+        ref = osem.convect_dealiased(w, osem.set_convect(vel, dl), dl)
+        sem = nb.Sem(ctx, N, x, y, None, glo_num=glo)
+        lay = nb.Layout(ctx, [x.size, x.size], [True, True])
+        B = nb.Basis(lay, 3)
+        sem.dealias_setup(lxd)
+        B[0].upload(vel)
+        sem.set_convect(1, B[0])
+        B[1].upload([w, w])
+        sem.convect(1, B[1], B[2], field0=1, nf=1)
+        assert relerr(B[2].download()[0][1].reshape(x.shape), ref) <= 1e-12
+        B.close()
+        sem.close()
