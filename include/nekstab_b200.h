@@ -286,6 +286,16 @@ int nsb_op_create_host(nsb_layout_t layout, nsb_host_matvec_fn fn, void *user, n
  * e.g. transient_growth_map = adjoint_linearized_map(forward_linearized_map(q))
  * (core/matvec.f90:478-495).  The component operators stay owned by the caller. */
 int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, nsb_op_t *op);
+/* Device time-stepper operator, the structure of exponential_prop%matvec
+ * (core/linear_operators.f90:225-274: integrate over tau from a cold start, return the final state) for
+ * Nek's scalar step cdscal [UPSTREAM-RECALL]: nsteps BDF/EXT steps (order ramp 1, 2, 3) of
+ *     rho dT/dt + rho (U.grad) T = kappa lap T,   T = 0 where the mesh mask is 0,
+ * applied independently to the first nfields_apply fields; U = the convecting field in `slot`
+ * (nsb_sem_set_convect; -1: no convection).  Each step = nsb_sem_convect, nsb_sem_bdf_ext,
+ * nsb_sem_dssum, nsb_sem_hmholtz(kappa, rho bd1/dt, tol, maxit).  The pressure-coupled velocity
+ * step is not available. */
+int nsb_op_create_stepper(nsb_sem_t sem, nsb_layout_t layout, int nfields_apply, int slot, double kappa,
+                          double rho, double dt, int nsteps, double tol, int maxit, nsb_op_t *op);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_op_count(nsb_op_t op, int64_t *napply);

@@ -92,6 +92,8 @@ PROTOTYPES = {
                                     c_double_p, c_double_p, c_double_p, c_void_pp]),
     'nsb_op_create_host': (C.c_int, [H, HOST_MATVEC, C.c_void_p, c_void_pp]),
     'nsb_op_create_compose': (C.c_int, [H, H, H, c_void_pp]),
+    'nsb_op_create_stepper': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        C.c_double, C.c_int, c_void_pp]),
     'nsb_op_destroy': (C.c_int, [H]),
     'nsb_op_apply': (C.c_int, [H, H, C.c_int, H, C.c_int]),
     'nsb_op_count': (C.c_int, [H, c_i64_p]),

@@ -460,6 +460,16 @@ def sem_operator(sem: Sem, nfields: int, alpha: float, beta: float, h1: float, h
     return LinearOperator(sem.lib, h, keep)
 
 
+def stepper_operator(sem: Sem, layout: Layout, nfields: int, slot: int, kappa: float, dt: float, nsteps: int,
+                     rho: float = 1.0, tol: float = 1e-12, maxit: int = 1000) -> LinearOperator:
+    """Device time-stepper operator: nsteps BDF3/EXT3 advection-diffusion steps from a cold start (the structure
+    of exponential_prop%matvec, core/linear_operators.f90:225-274, for Nek's scalar step); slot -1 = no flow."""
+    h = C.c_void_p()
+    check(sem.lib.nsb_op_create_stepper(sem.h, layout.h, int(nfields), int(slot), float(kappa), float(rho),
+                                        float(dt), int(nsteps), float(tol), int(maxit), C.byref(h)))
+    return LinearOperator(sem.lib, h, keep=(sem, layout))
+
+
 def compose_operators(layout: Layout, outer: LinearOperator, inner: LinearOperator) -> LinearOperator:
     """out = outer(inner(in)) -- e.g. transient_growth_map = adjoint(forward(q)) (core/matvec.f90:478-495)."""
     h = C.c_void_p()

@@ -690,3 +690,91 @@ extern "C" int nsb_sem_bdf_ext(nsb_sem_t S, nsb_basis_t B, int col_bf, int col_e
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device time-stepper operator: the structure of exponential_prop%matvec
+// (core/linear_operators.f90:225-274 -- integrate the linearised equations over tau from a cold start,
+// return the final state) for Nek's scalar step cdscal [UPSTREAM-RECALL]:
+//     per step: bq = -rho (U.grad) T  ->  makeabq / makebdq (EXT/BDF, order ramp 1, 2, 3)
+//               -> dssum -> hmholtz (kappa A + rho bd1/dt B) T_new = bq
+// applied independently to the first nfields_apply fields.  Every piece is a kernel sequence above /
+// in nsb_sem.cu; only the k = O(10) scalars of the CG recurrences visit the host.
+// ------------------------------------------------------------------------------------------------
+namespace {
+const double kBD[4][4] = {{0, 0, 0, 0}, {1.0, 1.0, 0, 0}, {1.5, 2.0, -0.5, 0}, {11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0}};
+const double kAB[4][3] = {{0, 0, 0}, {1.0, 0, 0}, {2.0, -1.0, 0}, {3.0, -3.0, 1.0}};
+}  // namespace
+
+extern "C" int nsb_op_create_stepper(nsb_sem_t S, nsb_layout_t layout, int nfields_apply, int slot, double kappa,
+                                     double rho, double dt, int nsteps, double tol, int maxit, nsb_op_t *out) {
+  NSB_REQUIRE(S && layout && out, "nsb_op_create_stepper: NULL argument");
+  NSB_REQUIRE(nfields_apply >= 1 && nfields_apply <= layout->nfields, "nsb_op_create_stepper: nfields_apply=%d",
+              nfields_apply);
+  NSB_REQUIRE(slot >= -1 && slot <= 1, "nsb_op_create_stepper: slot %d (-1: no convection, 0, 1)", slot);
+  NSB_REQUIRE(slot < 0 || (S->lxd > 0 && S->cfine_d[slot]),
+              "nsb_op_create_stepper: slot %d has no convecting field (nsb_sem_dealias_setup, nsb_sem_set_convect)", slot);
+  NSB_REQUIRE(kappa > 0.0 && rho > 0.0 && dt > 0.0 && nsteps >= 1 && maxit >= 1 && tol > 0.0,
+              "nsb_op_create_stepper: bad parameter");
+  NSB_REQUIRE(S->exchange_ready, "nsb_op_create_stepper: call nsb_sem_setup_exchange first");
+  NSB_REQUIRE(layout->ctx == S->ctx, "nsb_op_create_stepper: layout and mesh live on different contexts");
+  for (int f = 0; f < nfields_apply; ++f)
+    NSB_REQUIRE(layout->len[f] == S->npts, "nsb_op_create_stepper: field %d has %lld points, mesh has %lld", f,
+                (long long)layout->len[f], (long long)S->npts);
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 3;
+  op->sem = S;
+  op->lay = layout;
+  op->nfields_apply = nfields_apply;
+  op->slot = slot;
+  op->kappa = kappa;
+  op->rho = rho;
+  op->dt = dt;
+  op->nsteps = nsteps;
+  op->tol = tol;
+  op->maxit = maxit;
+  int r = nsb_basis_create(layout, 7, &op->tmp);
+  if (r != NSB_OK) {
+    delete op;
+    return r;
+  }
+  *out = op;
+  return NSB_OK;
+}
+
+int nsb::stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: time-stepper operator built for another layout");
+  nsb_sem_t S = op->sem;
+  nsb_basis_t W = op->tmp;
+  nsb_layout_t L = op->lay;
+  const int nfa = op->nfields_apply;
+  for (int c = 0; c < 7; ++c) NSB_CHECK(nsb_vec_zero(W, c));
+  NSB_CHECK(nsb_vec_copy(W, 0, bin, cin));
+  int lag[3] = {0, 1, 2}, nw = 6;
+  const int bq = 3, e1 = 4, e2 = 5;
+  for (int n = 1; n <= op->nsteps; ++n) {
+    const int o = n < 3 ? n : 3;
+    if (op->slot >= 0) NSB_CHECK(nsb_sem_convect(S, op->slot, W, lag[0], W, bq, 0, nfa, -op->rho, 0));
+    else NSB_CHECK(nsb_vec_zero(W, bq));
+    NSB_CHECK(nsb_sem_bdf_ext(S, W, bq, e1, e2, lag, o, 0, nfa, kAB[o], kBD[o], op->rho / op->dt));
+    for (int f = 0; f < nfa; ++f) {
+      int it = 0;
+      double res = 0.0;
+      NSB_CHECK(nsb_sem_dssum(S, W, bq, f));
+      NSB_CHECK(nsb_sem_hmholtz(S, W, bq, W, nw, f, op->kappa, op->rho * kBD[o][0] / op->dt, op->tol, op->maxit, &it,
+                                &res));
+      op->helm_iters += it;
+    }
+    const int freed = lag[2];
+    lag[2] = lag[1];
+    lag[1] = lag[0];
+    lag[0] = nw;
+    nw = freed;
+  }
+  // fields outside the operator and %time are carried through; the stepped fields come from the last lag
+  NSB_CHECK(nsb_vec_copy(bout, cout, bin, cin));
+  cudaStream_t s = L->ctx->stream;
+  for (int f = 0; f < nfa; ++f)
+    NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->off[f], W->col(lag[0]) + L->off[f], sizeof(double) * L->len[f],
+                             cudaMemcpyDeviceToDevice, s));
+  return NSB_OK;
+}

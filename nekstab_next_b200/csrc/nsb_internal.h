@@ -156,7 +156,7 @@ struct nsb_sem_s {
 };
 
 struct nsb_op_s {
-  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.))
+  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.)), 3 device time-stepper
   nsb_op_t outer = nullptr, inner = nullptr;
   nsb_basis_t tmp = nullptr;     // work vector of the composition
   nsb_sem_t sem = nullptr;
@@ -168,9 +168,14 @@ struct nsb_op_s {
   void *user = nullptr;
   std::vector<double *> hin, hout;  // pinned staging buffers of the host operator
   int64_t napply = 0;
+  // kind 3 (nsb_conv.cu): nsteps BDF3/EXT3 advection-diffusion steps; tmp holds the 7 work columns
+  int slot = -1, nsteps = 0, maxit = 0;
+  double kappa = 0, rho = 1, dt = 0, tol = 0;
+  int64_t helm_iters = 0;        // Helmholtz iterations spent so far
 };
 
 namespace nsb {
+int stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);   // nsb_conv.cu
 enum ProfClass { PC_MULTIDOT = 0, PC_UPDATE, PC_NORMALIZE, PC_AXHELM, PC_GS, PC_BLAS1, PC_SMALL,
                  PC_ROTATE, PC_GEMV, PC_DOT, PC_FUSED, PC_COUNT };
 // RAII: records a start event now and a stop event at scope exit on the context stream

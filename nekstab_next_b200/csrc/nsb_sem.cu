@@ -1699,6 +1699,7 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
   NSB_REQUIRE(bin->lay == bout->lay, "nsb_op_apply: different layouts");
   NSB_REQUIRE(!(bin == bout && cin == cout), "nsb_op_apply: in-place application is not supported");
   op->napply++;
+  if (op->kind == 3) return nsb::stepper_apply(op, bin, cin, bout, cout);
   if (op->kind == 2) {
     NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: composite operator built for another layout");
     NSB_CHECK(nsb_op_apply(op->inner, bin, cin, op->tmp, 0));

@@ -265,3 +265,82 @@ def test_dealiased_convection_2d_box_other_orders(ctx):
         assert relerr(B[2].download()[0][1].reshape(x.shape), ref) <= 1e-12
         B.close()
         sem.close()
+
+
+# ---- the device time-stepper as the Arnoldi operator (exponential_prop%matvec structure) --------------------
+def _ramp_amplification(lam, dt, nsteps):
+    """y_nsteps / y_0 of the BDF1 -> BDF2 -> BDF3 start-up sequence for y' = -lam y."""
+    y = [1.0]
+    for n in range(1, nsteps + 1):
+        o = min(n, 3)
+        rhs = sum(BD[o][i + 1] * y[-1 - i] for i in range(o)) / dt
+        y.append(rhs / (BD[o][0] / dt + lam))
+    return y[-1]
+
+
+def test_stepper_operator_arnoldi_matches_oracle(ctx):
+    """Arnoldi on Phi = (3 advection-diffusion steps): H against the oracle's Arnoldi on the same composition."""
+    import nekstab_next_b200 as nb
+    from oracle import krylov as okr
+    N, K, nsteps, kappa, dt = 7, 4, 3, 0.05, 5e-3
+    x, y, z, glo, geo = _mesh((2, 2, 2), N, 0.04)
+    x0, y0, z0, _ = osem.box_mesh(2, 2, 2, N)
+    mask = osem.boundary_mask_box(None, x0, y0, z0)
+    vel = [np.sin(np.pi * x) * np.cos(np.pi * y), -np.cos(np.pi * x) * np.sin(np.pi * y), 0.2 * np.sin(np.pi * z)]
+    rng = np.random.default_rng(3)
+    q0 = osem.dssum(rng.standard_normal(x.shape), glo) / osem.multiplicity(glo) * mask
+    c = okr.Ctx(bm1s=geo['bm1'], in_dot=[True], time_in_dot=False)
+
+    def omatvec(q):
+        return okr.KVec([_oracle_scalar_steps(x, y, z, glo, mask, geo, vel, q.f[0], kappa, dt, nsteps)], q.time)
+
+    seed = okr.KVec([q0.copy()], 0.0)
+    okr.k_normalize(c, seed)
+    Qo = [okr.k_zero_like(seed) for _ in range(K + 1)]
+    okr.k_copy(Qo[0], seed)
+    Ho = np.zeros((K + 1, K))
+    okr.arnoldi_factorization(c, omatvec, Qo, Ho, 1, K, K)
+
+    sem = nb.Sem(ctx, N, x, y, z, mask=mask, glo_num=glo)
+    lay3 = nb.Layout(ctx, [x.size] * 3, [True] * 3)
+    Bv = nb.Basis(lay3, 1)
+    sem.dealias_setup()
+    Bv[0].upload(vel)
+    sem.set_convect(0, Bv[0])
+    lay = nb.Layout(ctx, [x.size], [True])
+    lay.set_weight([geo['bm1']])
+    Q = nb.Basis(lay, K + 1)
+    op = nb.stepper_operator(sem, lay, 1, 0, kappa, dt, nsteps, tol=1e-13)
+    Q[0].upload(seed.f)
+    H = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(Q, H, 1, K, K, op)
+    assert np.max(np.abs(H - Ho)) <= 1e-8 * np.max(np.abs(Ho))
+    assert op.count() == K
+    op.close(); Q.close(); Bv.close(); sem.close()
+
+
+def test_stepper_operator_leading_growth_rate(ctx):
+    """Pure diffusion: the leading Ritz value of the propagator is the BDF-ramp amplification of the slowest mode,
+    and log(lambda)/tau recovers its decay rate -3 pi^2 kappa (what linear_stability_analysis prints,
+    core/linear_stab.f90:72)."""
+    import nekstab_next_b200 as nb
+    N, kappa, dt, nsteps = 7, 1.0, 2.5e-3, 40
+    x, y, z, glo, geo = _mesh((2, 2, 2), N, 0.0)
+    mask = osem.boundary_mask_box(None, x, y, z)
+    sem = nb.Sem(ctx, N, x, y, z, mask=mask, glo_num=glo)
+    lay = nb.Layout(ctx, [x.size], [True])
+    lay.set_weight([geo['bm1']])
+    Q = nb.Basis(lay, 9)
+    op = nb.stepper_operator(sem, lay, 1, -1, kappa, dt, nsteps, tol=1e-13)
+    rng = np.random.default_rng(0)
+    q0 = osem.dssum(rng.standard_normal(x.shape), glo) / osem.multiplicity(glo) * mask
+    Q[0].upload([q0])
+    nb.k_normalize(Q[0])
+    vals, vecs, res, k, nconv, H = nb.eigs(Q, op, 8, nev=1, tol=1e-9)
+    lead = vals[np.argmin(res)]
+    lam = 3 * np.pi ** 2 * kappa
+    assert nconv >= 1 and abs(lead.imag) <= 1e-10
+    assert abs(lead.real - _ramp_amplification(lam, dt, nsteps)) <= 1e-7
+    tau = dt * nsteps
+    assert abs(np.log(lead.real) / tau + lam) <= 0.02 * lam      # time-discretisation error of the start-up steps
+    op.close(); Q.close(); sem.close()
