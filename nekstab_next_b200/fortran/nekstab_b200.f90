@@ -405,6 +405,15 @@ module nekstab_b200
          type(c_ptr) :: op
          integer(c_int) :: ierr
       end function
+      function nsb_op_create_stepper(sem, layout, nfields_apply, slot, kappa, rho, dt, nsteps, tol, maxit, op) &
+         bind(C, name='nsb_op_create_stepper') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, layout
+         integer(c_int), value :: nfields_apply, slot, nsteps, maxit
+         real(c_double), value :: kappa, rho, dt, tol
+         type(c_ptr) :: op
+         integer(c_int) :: ierr
+      end function
       function nsb_op_create_compose(layout, outer, inner, op) bind(C, name='nsb_op_create_compose') result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: layout, outer, inner
@@ -474,7 +483,7 @@ module nekstab_b200
    public :: nsb_sync, nsb_vec_norm, nsb_orthonormalize, nsb_basis_gram, nsb_basis_qr, nsb_basis_rotate
    public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
    public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
-   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_compose, nsb_op_apply, nsb_op_destroy, nsb_op_count
+   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose, nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues
 
 
