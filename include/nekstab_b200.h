@@ -242,6 +242,12 @@ int nsb_sem_ax(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int co
  * preconditioned residual norm sqrt((r, D r)_mult) has dropped by `tol` or after maxit iterations. */
 int nsb_sem_hmholtz(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field,
                     double h1, double h2, double tol, int maxit, int *iters, double *res);
+/* The same solve for nf <= 3 fields field0..field0+nf-1 side by side (Nek's ophinv: the three velocity
+ * components): one axhelm and one gather-scatter launch per iteration read the geometric factors once for
+ * all systems; every system keeps its own CG scalars and convergence test (iters[nf], res[nf]) and follows
+ * exactly the iteration sequence it would follow alone. */
+int nsb_sem_hmholtz_vec(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field0, int nf,
+                        double h1, double h2, double tol, int maxit, int *iters, double *res);
 
 /* Dealiased convection of Nek5000's perturbation step ([UPSTREAM-RECALL] convect.f set_dealias_rx /
  * set_convect_new / convect_new: the terms advabp adds for (U.grad)u' and (u'.grad)U; SURVEY.md

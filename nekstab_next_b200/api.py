@@ -392,6 +392,15 @@ class Sem:
                                        C.byref(it), C.byref(res)))
         return it.value, res.value
 
+    def hmholtz_vec(self, rhs: nek_dvector, x: nek_dvector, field0: int, nf: int, h1: float, h2: float,
+                    tol: float = 1e-10, maxit: int = 500):
+        """nf <= 3 Helmholtz systems side by side (Nek's ophinv); returns (iterations[nf], residual drops[nf])."""
+        it = (C.c_int * nf)()
+        res = (C.c_double * nf)()
+        check(self.lib.nsb_sem_hmholtz_vec(self.h, rhs.basis.h, rhs.col, x.basis.h, x.col, int(field0), int(nf), h1, h2,
+                                           tol, maxit, it, res))
+        return list(it), list(res)
+
     def ax(self, vin: nek_dvector, vout: nek_dvector, field: int, h1: float, h2: float):
         check(self.lib.nsb_sem_ax(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col, field, h1, h2))
 

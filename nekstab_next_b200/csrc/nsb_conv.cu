@@ -756,13 +756,14 @@ int nsb::stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, 
     if (op->slot >= 0) NSB_CHECK(nsb_sem_convect(S, op->slot, W, lag[0], W, bq, 0, nfa, -op->rho, 0));
     else NSB_CHECK(nsb_vec_zero(W, bq));
     NSB_CHECK(nsb_sem_bdf_ext(S, W, bq, e1, e2, lag, o, 0, nfa, kAB[o], kBD[o], op->rho / op->dt));
-    for (int f = 0; f < nfa; ++f) {
-      int it = 0;
-      double res = 0.0;
-      NSB_CHECK(nsb_sem_dssum(S, W, bq, f));
-      NSB_CHECK(nsb_sem_hmholtz(S, W, bq, W, nw, f, op->kappa, op->rho * kBD[o][0] / op->dt, op->tol, op->maxit, &it,
-                                &res));
-      op->helm_iters += it;
+    for (int f = 0; f < nfa; ++f) NSB_CHECK(nsb_sem_dssum(S, W, bq, f));
+    for (int f = 0; f < nfa; f += 3) {                       // up to three systems side by side
+      const int nb3 = nfa - f < 3 ? nfa - f : 3;
+      int it[3] = {0, 0, 0};
+      double res[3];
+      NSB_CHECK(nsb_sem_hmholtz_vec(S, W, bq, W, nw, f, nb3, op->kappa, op->rho * kBD[o][0] / op->dt, op->tol, op->maxit,
+                                    it, res));
+      for (int g = 0; g < nb3; ++g) op->helm_iters += it[g];
     }
     const int freed = lag[2];
     lag[2] = lag[1];

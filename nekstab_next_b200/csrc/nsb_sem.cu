@@ -688,7 +688,15 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
     const double *sG = stage0 + (size_t)s * STAGE;
     const double *sB = sG + 6 * N3, *sM = sG + 7 * N3, *sC = sG + 8 * N3;
     const double *sU = sG + (size_t)(8 + (CONV ? 3 : 0) + f) * N3;
-    mbar_wait(full + s, (uint32_t)((it / NBUF) & 1));
+    // A parity wait is only unambiguous when the waiter is at most one phase ahead of the barrier.  With
+    // NBUF > NG consecutive uses of a buffer belong to DIFFERENT warps: the warp of use u can get here
+    // while use u-1 is still being loaded, full[s] is then two phases behind and its parity already
+    // matches (seen as launch failures on large meshes with NF = 1).  Waiting first for the previous
+    // user's release (empty[s], phase u-1) pins full[s] to phase u.
+    const uint32_t use = (uint32_t)(it / NBUF);
+    if (use > 0) mbar_wait(empty + s, (use - 1u) & 1u);
+    mbar_wait(full + s, use & 1u);
+    __syncwarp();   // the spin loops may leave the lanes diverged; mma.sync.aligned below needs the full warp
     // always 0, but opaque to the compiler: keeps the 64 D(k,l) constant loads inside the loop
     // (hoisted out of it they occupy 128 registers and spill)
     const int zoff = (int)(it >> 40);
@@ -1490,71 +1498,131 @@ __global__ void helm_diag_kernel(const double *__restrict__ g, const double *__r
   diag[p] = h1 * s + h2 * bm1[p];
 }
 
-// generic weighted dot partials: sum a b c
-__global__ void __launch_bounds__(256) dot3_kernel(const double *__restrict__ a, const double *__restrict__ b,
-                                                   const double *__restrict__ c, int64_t n,
-                                                   double *__restrict__ partial) {
-  double acc = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) acc = fma(a[t] * b[t], c[t], acc);
-  acc = block_reduce_sum<256>(acc);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
-}
+// Per-field scalars of the batched solver, passed by value (up to kPcgFields systems at once)
+constexpr int kPcgFields = 3;
+struct PcgScal {
+  double v[kPcgFields];
+};
 
-// x += alpha p ; r -= alpha w ; z = d r ; partial += r z mult     (one pass over five vectors)
-__global__ void __launch_bounds__(256) pcg_update_kernel(double *__restrict__ x, double *__restrict__ r,
-                                                         double *__restrict__ z, const double *__restrict__ p,
-                                                         const double *__restrict__ w, const double *__restrict__ d,
-                                                         const double *__restrict__ mult, double alpha, int64_t n,
-                                                         double *__restrict__ partial) {
+// z = d r ; partial[f] += r z mult      (grid.y = field; the work vectors have field stride n)
+__global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict__ f, int64_t fs_f, double *__restrict__ r,
+                                                       double *__restrict__ z, const double *__restrict__ d,
+                                                       const double *__restrict__ mask, const double *__restrict__ mult,
+                                                       int64_t n, int nf, double *__restrict__ partial) {
+  const int fi = blockIdx.y;
+  const double *ff = f + (int64_t)fi * fs_f;
+  double *rr = r + (int64_t)fi * n, *zz = z + (int64_t)fi * n;
   double acc = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-    x[t] = fma(alpha, p[t], x[t]);
-    const double rv = fma(-alpha, w[t], r[t]);
-    r[t] = rv;
+    const double rv = ff[t] * mask[t];        // the right-hand side lives in the masked space
     const double zv = d[t] * rv;
-    z[t] = zv;
+    rr[t] = rv;
+    zz[t] = zv;
     acc = fma(rv * zv, mult[t], acc);
   }
   acc = block_reduce_sum<256>(acc);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + fi] = acc;
 }
 
-__global__ void pcg_p_kernel(double *__restrict__ p, const double *__restrict__ z, double beta, int64_t n) {
+// partial[f] = sum w p mult
+__global__ void __launch_bounds__(256) pcg_dot_kernel(const double *__restrict__ w, const double *__restrict__ p,
+                                                      const double *__restrict__ mult, int64_t n, int nf,
+                                                      double *__restrict__ partial) {
+  const int fi = blockIdx.y;
+  const double *ww = w + (int64_t)fi * n, *pp = p + (int64_t)fi * n;
+  double acc = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) p[t] = fma(beta, p[t], z[t]);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+    acc = fma(ww[t] * pp[t], mult[t], acc);
+  acc = block_reduce_sum<256>(acc);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + fi] = acc;
 }
 
-int reduce_scalar(nsb_context_t ctx, int nblk, double *out_host, bool allreduce) {
+// x += alpha p ; r -= alpha w ; z = d r ; partial[f] = r z mult     (one pass over five vectors per field)
+__global__ void __launch_bounds__(256) pcg_update_kernel(double *__restrict__ x, int64_t fs_x, double *__restrict__ r,
+                                                         double *__restrict__ z, const double *__restrict__ p,
+                                                         const double *__restrict__ w, const double *__restrict__ d,
+                                                         const double *__restrict__ mult, PcgScal alpha, int64_t n,
+                                                         int nf, double *__restrict__ partial) {
+  const int fi = blockIdx.y;
+  const double al = alpha.v[fi];
+  double *xx = x + (int64_t)fi * fs_x, *rr = r + (int64_t)fi * n, *zz = z + (int64_t)fi * n;
+  const double *pp = p + (int64_t)fi * n, *ww = w + (int64_t)fi * n;
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    xx[t] = fma(al, pp[t], xx[t]);
+    const double rv = fma(-al, ww[t], rr[t]);
+    rr[t] = rv;
+    const double zv = d[t] * rv;
+    zz[t] = zv;
+    acc = fma(rv * zv, mult[t], acc);
+  }
+  acc = block_reduce_sum<256>(acc);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + fi] = acc;
+}
+
+// p = z + beta p
+__global__ void pcg_p_kernel(double *__restrict__ p, const double *__restrict__ z, PcgScal beta, int64_t n) {
+  const int fi = blockIdx.y;
+  const double be = beta.v[fi];
+  double *pp = p + (int64_t)fi * n;
+  const double *zz = z + (int64_t)fi * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) pp[t] = fma(be, pp[t], zz[t]);
+}
+
+// partial[grid][nf] -> nf host scalars (summed over ranks)
+int reduce_scalars(nsb_context_t ctx, int nblk, int nf, double *out_host) {
   double *out_d = ctx->hvec_d + 3 * (kMaxK + 8) + 16;
-  reduce_partials_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partial_d, nblk, 1, 1, out_d, 0, nullptr);
+  reduce_partials_kernel<<<1, 32 * kPcgFields, 0, ctx->stream>>>(ctx->partial_d, nblk, nf, nf, out_d, 0, nullptr);
   ctx->launches++;
   NSB_CUDA(cudaGetLastError());
-  if (allreduce && ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, out_d, 1));
-  NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 16, out_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, out_d, nf));
+  NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 16, out_d, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-  *out_host = ctx->hpin[16];
+  for (int f = 0; f < nf; ++f) out_host[f] = ctx->hpin[16 + f];
   return NSB_OK;
 }
 
 }  // namespace
 
-extern "C" int nsb_sem_hmholtz(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field,
-                               double h1, double h2, double tol, int maxit, int *iters, double *res) {
+// nf independent systems (h1 A + h2 B) x_f = rhs_f solved side by side: the matrix-vector product reads
+// the geometric factors once for all of them (one axhelm + one gather-scatter launch per iteration),
+// every system keeps its own alpha / beta / convergence test and is frozen (alpha = 0) once converged,
+// so each follows exactly the iteration sequence it would follow alone.
+// Nek masks w after the dssum; that pass is skipped here: d carries the mask, so z, p and x stay zero on
+// the masked nodes whatever r collects there, and every inner product has an exact zero factor there.
+extern "C" int nsb_sem_hmholtz_vec(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field0,
+                                   int nf, double h1, double h2, double tol, int maxit, int *iters, double *res) {
+  NSB_REQUIRE(S && brhs && bx, "nsb_sem_hmholtz: NULL argument");
+  NSB_REQUIRE(nf >= 1 && nf <= kPcgFields, "nsb_sem_hmholtz: %d systems at once (1..%d)", nf, kPcgFields);
   double *f, *x;
-  NSB_CHECK(field_ptr(S, brhs, crhs, field, &f, "nsb_sem_hmholtz"));
-  NSB_CHECK(field_ptr(S, bx, cx, field, &x, "nsb_sem_hmholtz"));
+  for (int g = field0; g < field0 + nf; ++g) {
+    NSB_CHECK(field_ptr(S, brhs, crhs, g, &f, "nsb_sem_hmholtz"));
+    NSB_CHECK(field_ptr(S, bx, cx, g, &x, "nsb_sem_hmholtz"));
+  }
+  NSB_CHECK(field_ptr(S, brhs, crhs, field0, &f, "nsb_sem_hmholtz"));
+  NSB_CHECK(field_ptr(S, bx, cx, field0, &x, "nsb_sem_hmholtz"));
   NSB_REQUIRE(f != x && maxit >= 1, "nsb_sem_hmholtz: bad argument");
   NSB_REQUIRE(S->exchange_ready, "nsb_sem_hmholtz: call nsb_sem_setup_exchange first");
+  const nsb_layout_t Lf = brhs->lay, Lx = bx->lay;
+  const int64_t fs_f = nf > 1 ? Lf->off[field0 + 1] - Lf->off[field0] : 0;
+  const int64_t fs_x = nf > 1 ? Lx->off[field0 + 1] - Lx->off[field0] : 0;
+  for (int g = field0 + 1; g < field0 + nf; ++g)
+    NSB_REQUIRE(Lf->off[g] - Lf->off[g - 1] == fs_f && Lx->off[g] - Lx->off[g - 1] == fs_x,
+                "nsb_sem_hmholtz: fields are not equally spaced");
   nsb_context_t ctx = S->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   const int64_t n = S->npts;
   const size_t nb = sizeof(double) * n;
-  if (!S->pcg_d) NSB_CUDA(cudaMalloc(&S->pcg_d, nb * 5));
-  double *r = S->pcg_d, *p = r + n, *w = p + n, *z = w + n, *d = z + n;
+  if (!S->pcg_d) NSB_CUDA(cudaMalloc(&S->pcg_d, nb * (4 * kPcgFields + 1)));
+  double *r = S->pcg_d, *p = r + kPcgFields * n, *w = p + kPcgFields * n, *z = w + kPcgFields * n,
+         *d = z + kPcgFields * n;
   const int grid = ctx->num_sms * 8;
+  const dim3 g2(grid, nf);
   NSB_CHECK(ensure_partial(ctx, grid));
   // setprec: d = mask / dssum(diag)
   helm_diag_kernel<<<blocks_for(n), 256, 0, st>>>(S->g_d, S->bm1_d, S->D_d, S->dim, S->lx, n, h1, h2, d);
@@ -1563,40 +1631,74 @@ extern "C" int nsb_sem_hmholtz(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basi
   recip_kernel<<<grid, 256, 0, st>>>(d, n);
   col2_kernel<<<grid, 256, 0, st>>>(d, S->mask_d, n);
   ctx->launches += 2;
-  NSB_CUDA(cudaMemsetAsync(x, 0, nb, st));
-  NSB_CUDA(cudaMemsetAsync(p, 0, nb, st));
-  NSB_CUDA(cudaMemcpyAsync(r, f, nb, cudaMemcpyDeviceToDevice, st));
-  col2_kernel<<<grid, 256, 0, st>>>(r, S->mask_d, n);           // the right-hand side lives in the masked space
-  mul3_kernel<<<grid, 256, 0, st>>>(z, d, r, n);                // z = D r
-  dot3_kernel<<<grid, 256, 0, st>>>(r, z, S->vmult_d, n, ctx->partial_d);
-  ctx->launches += 3;
-  double rtz1 = 0.0, rtz2 = 1.0, rho = 0.0, r0 = -1.0, rn = 0.0;
-  NSB_CHECK(reduce_scalar(ctx, grid, &rtz1, true));
-  int it = 0;
-  for (it = 1; it <= maxit; ++it) {
-    const double beta = it == 1 ? 0.0 : rtz1 / rtz2;
-    pcg_p_kernel<<<grid, 256, 0, st>>>(p, z, beta, n);                                   // p = z + beta p
-    ctx->launches++;
-    NSB_CHECK(launch_axhelm(S, p, w, 1, 0, h1, h2, nullptr, 0, 0, 0, nullptr));          // w = H p
-    NSB_CHECK(launch_gs(S, w, 1, 0, 0, nullptr, 0, 0, nullptr));                          // dssum
-    col2_kernel<<<grid, 256, 0, st>>>(w, S->mask_d, n);                                   // mask
-    dot3_kernel<<<grid, 256, 0, st>>>(w, p, S->vmult_d, n, ctx->partial_d);               // rho = (w, p)
-    ctx->launches += 2;
-    NSB_CHECK(reduce_scalar(ctx, grid, &rho, true));
-    if (!(rho > 0.0)) break;                                                              // converged to round-off / singular
-    const double alpha = rtz1 / rho;
-    pcg_update_kernel<<<grid, 256, 0, st>>>(x, r, z, p, w, d, S->vmult_d, alpha, n, ctx->partial_d);
-    ctx->launches++;
-    rtz2 = rtz1;
-    NSB_CHECK(reduce_scalar(ctx, grid, &rtz1, true));
-    // convergence on the preconditioned residual norm sqrt((r, D r)) relative to the first one
-    rn = std::sqrt(std::fabs(rtz1));
-    if (r0 < 0.0) r0 = std::sqrt(std::fabs(rtz2));
-    if (rn <= tol * r0) break;
+  for (int g = 0; g < nf; ++g) NSB_CUDA(cudaMemsetAsync(x + g * fs_x, 0, nb, st));
+  NSB_CUDA(cudaMemsetAsync(p, 0, nb * nf, st));
+  pcg_init_kernel<<<g2, 256, 0, st>>>(f, fs_f, r, z, d, S->mask_d, S->vmult_d, n, nf, ctx->partial_d);
+  ctx->launches++;
+  double rtz1[kPcgFields], rtz2[kPcgFields], rho[kPcgFields], r0[kPcgFields], rn[kPcgFields];
+  bool done[kPcgFields];
+  int itf[kPcgFields];
+  NSB_CHECK(reduce_scalars(ctx, grid, nf, rtz1));
+  for (int g = 0; g < nf; ++g) {
+    rtz2[g] = 1.0;
+    r0[g] = -1.0;
+    rn[g] = 0.0;
+    done[g] = false;
+    itf[g] = maxit;
   }
-  if (iters) *iters = it > maxit ? maxit : it;
-  if (res) *res = r0 > 0.0 ? rn / r0 : 0.0;
+  for (int it = 1; it <= maxit; ++it) {
+    PcgScal beta, alpha;
+    for (int g = 0; g < kPcgFields; ++g) beta.v[g] = (g < nf && it > 1 && !done[g]) ? rtz1[g] / rtz2[g] : 0.0;
+    pcg_p_kernel<<<g2, 256, 0, st>>>(p, z, beta, n);                                     // p = z + beta p
+    ctx->launches++;
+    NSB_CHECK(launch_axhelm(S, p, w, nf, n, h1, h2, nullptr, 0, 0, 0, nullptr));         // w = H p
+    NSB_CHECK(launch_gs(S, w, nf, n, 0, nullptr, 0, 0, nullptr));                        // dssum
+    pcg_dot_kernel<<<g2, 256, 0, st>>>(w, p, S->vmult_d, n, nf, ctx->partial_d);         // rho = (w, p)
+    ctx->launches++;
+    NSB_CHECK(reduce_scalars(ctx, grid, nf, rho));
+    bool any = false;
+    for (int g = 0; g < kPcgFields; ++g) {
+      alpha.v[g] = 0.0;
+      if (g >= nf || done[g]) continue;
+      if (!(rho[g] > 0.0)) {                                                             // converged to round-off / singular
+        done[g] = true;
+        itf[g] = it;
+        continue;
+      }
+      alpha.v[g] = rtz1[g] / rho[g];
+      any = true;
+    }
+    if (!any) break;
+    pcg_update_kernel<<<g2, 256, 0, st>>>(x, fs_x, r, z, p, w, d, S->vmult_d, alpha, n, nf, ctx->partial_d);
+    ctx->launches++;
+    double rtzn[kPcgFields];
+    NSB_CHECK(reduce_scalars(ctx, grid, nf, rtzn));
+    bool all = true;
+    for (int g = 0; g < nf; ++g) {
+      if (done[g]) continue;
+      rtz2[g] = rtz1[g];
+      rtz1[g] = rtzn[g];
+      // convergence on the preconditioned residual norm sqrt((r, D r)) relative to the first one
+      rn[g] = std::sqrt(std::fabs(rtz1[g]));
+      if (r0[g] < 0.0) r0[g] = std::sqrt(std::fabs(rtz2[g]));
+      if (rn[g] <= tol * r0[g]) {
+        done[g] = true;
+        itf[g] = it;
+      }
+      all = all && done[g];
+    }
+    if (all) break;
+  }
+  for (int g = 0; g < nf; ++g) {
+    if (iters) iters[g] = itf[g];
+    if (res) res[g] = r0[g] > 0.0 ? rn[g] / r0[g] : 0.0;
+  }
   return NSB_OK;
+}
+
+extern "C" int nsb_sem_hmholtz(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field,
+                               double h1, double h2, double tol, int maxit, int *iters, double *res) {
+  return nsb_sem_hmholtz_vec(S, brhs, crhs, bx, cx, field, 1, h1, h2, tol, maxit, iters, res);
 }
 
 // ------------------------------------------------------------------------------------------------

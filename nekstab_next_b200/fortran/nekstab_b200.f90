@@ -365,6 +365,16 @@ module nekstab_b200
          real(c_double) :: res
          integer(c_int) :: ierr
       end function
+      function nsb_sem_hmholtz_vec(sem, brhs, crhs, bx, cx, field0, nf, h1, h2, tol, maxit, iters, res) &
+         bind(C, name='nsb_sem_hmholtz_vec') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, brhs, bx
+         integer(c_int), value :: crhs, cx, field0, nf, maxit
+         real(c_double), value :: h1, h2, tol
+         integer(c_int) :: iters(*)
+         real(c_double) :: res(*)
+         integer(c_int) :: ierr
+      end function
       function nsb_sem_dealias_setup(sem, lxd) bind(C, name='nsb_sem_dealias_setup') result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: sem
@@ -482,7 +492,7 @@ module nekstab_b200
    end interface
    public :: nsb_sync, nsb_vec_norm, nsb_orthonormalize, nsb_basis_gram, nsb_basis_qr, nsb_basis_rotate
    public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
-   public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
+   public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_hmholtz_vec, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
    public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose, nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues
 

@@ -28,3 +28,19 @@ for tol, maxit in ((1e-30, 50), (1e-8, 2000)):
     dt = time.perf_counter() - t0
     print(f'npts={npts} tol={tol:g}: {it} iterations, residual drop {res:.2e}, {dt * 1e3:.1f} ms, '
           f'{dt / it * 1e3:.3f} ms/iteration, {npts * it / dt / 1e9:.2f} GDOF/s per iteration')
+
+# three systems side by side (Nek's ophinv): one axhelm + one gather-scatter launch per iteration for all
+lay3 = nb.Layout(ctx, [npts] * 3, [True] * 3)
+B3 = nb.Basis(lay3, 2)
+B3[0].upload([rng.standard_normal(npts) for _ in range(3)])
+for f in range(3):
+    sem.dssum(B3[0], f)
+    sem.col2(B3[0], f, 'mask')
+for _ in range(2):
+    ctx.sync()
+    t0 = time.perf_counter()
+    its, ress = sem.hmholtz_vec(B3[0], B3[1], 0, 3, 1.0 / 100.0, 1.0 / 1e-2, tol=1e-30, maxit=50)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+print(f'3 systems side by side: {max(its)} iterations, {dt * 1e3:.1f} ms, {dt / max(its) * 1e3:.3f} ms/iteration '
+      f'({dt / max(its) / 3 * 1e3:.3f} ms per system and iteration)')

@@ -116,3 +116,25 @@ def test_helmholtz_pcg(ctx, nel, N, deform):
     assert relerr(x, xo) <= 1e-8
     lhs = osem.dssum(osem.axhelm(x, P.geo['g'], P.d, h1, h2, P.bm1), P.glo) * P.mask
     assert relerr(lhs, rhs) <= 1e-8
+
+
+def test_helmholtz_pcg_three_systems_side_by_side(ctx):
+    """nsb_sem_hmholtz_vec: each of the three systems follows the iteration sequence of its own single solve."""
+    P = BoxProblem(nel=(3, 2, 2), N=7, deform=0.05, nfields=3, seed=9)
+    lay, B, S, op = P.gpu(ctx, 3)
+    h1, h2 = 0.3, 5.0
+    rhs = [osem.dssum(P.bm1 * P.random_field(), P.glo) * P.mask * s for s in (1.0, 1e-3, 40.0)]
+    rhs[1] = rhs[1] * (np.sin(7 * P.coords[0]) + 1.2)          # a different, rougher right-hand side
+    rhs[1] = osem.dssum(rhs[1] * P.vmult, P.glo) * P.mask
+    B[0].upload(rhs)
+    its, ress = S.hmholtz_vec(B[0], B[1], 0, 3, h1, h2, tol=1e-11, maxit=400)
+    xs = B[1].download()[0]
+    single_its = []
+    for f in range(3):
+        xo, ito, _ = osem.cggo(rhs[f], P.geo['g'], P.d, P.glo, P.mask, P.bm1, h1, h2, tol=1e-11, maxit=400)
+        assert abs(its[f] - ito) <= 1 and ress[f] <= 1e-11
+        assert relerr(xs[f].reshape(P.shape), xo) <= 1e-8
+        it1, _ = S.hmholtz(B[0], B[2], f, h1, h2, tol=1e-11, maxit=400)
+        single_its.append(it1)
+        assert np.array_equal(B[2].download()[0][f], xs[f])      # bit-identical to the stand-alone solve
+    assert its == single_its and len(set(its)) > 1               # the systems stop at different iterations
