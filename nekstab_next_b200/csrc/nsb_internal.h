@@ -146,7 +146,8 @@ struct nsb_sem_s {
   std::vector<Peer> peers;
   std::vector<int64_t> glo_h;    // kept for exchange setup
   bool exchange_ready = false;
-  double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z, d)
+  double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z per system, d)
+  double *diagA_d = nullptr;     // diagonal of A per local point (setprec), computed at the first solve
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
   // dealiased convection (nsb_conv.cu): lxd Gauss-Legendre points per direction
   int lxd = 0;

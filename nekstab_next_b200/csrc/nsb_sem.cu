@@ -1393,6 +1393,7 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   if (S->gs_off_d) cudaFree(S->gs_off_d);
   if (S->gs_idx_d) cudaFree(S->gs_idx_d);
   if (S->bnode_d) cudaFree(S->bnode_d);
+  if (S->diagA_d) cudaFree(S->diagA_d);
   for (double *q : {S->J_d, S->Dg_d, S->rxf_d, S->cfine_d[0], S->cfine_d[1]})
     if (q) cudaFree(q);
   if (S->pcg_d) cudaFree(S->pcg_d);
@@ -1496,6 +1497,13 @@ __global__ void helm_diag_kernel(const double *__restrict__ g, const double *__r
     }
   }
   diag[p] = h1 * s + h2 * bm1[p];
+}
+
+// out = a x + b y
+__global__ void axpby_fields_kernel(double *__restrict__ out, const double *__restrict__ x, const double *__restrict__ y,
+                                    double a, double b, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) out[t] = a * x[t] + b * y[t];
 }
 
 // Per-field scalars of the batched solver, passed by value (up to kPcgFields systems at once)
@@ -1624,8 +1632,13 @@ extern "C" int nsb_sem_hmholtz_vec(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_
   const int grid = ctx->num_sms * 8;
   const dim3 g2(grid, nf);
   NSB_CHECK(ensure_partial(ctx, grid));
-  // setprec: d = mask / dssum(diag)
-  helm_diag_kernel<<<blocks_for(n), 256, 0, st>>>(S->g_d, S->bm1_d, S->D_d, S->dim, S->lx, n, h1, h2, d);
+  // setprec: d = mask / dssum(h1 diag(A) + h2 bm1); diag(A) depends on the mesh only and is kept
+  if (!S->diagA_d) {
+    NSB_CUDA(cudaMalloc(&S->diagA_d, nb));
+    helm_diag_kernel<<<blocks_for(n), 256, 0, st>>>(S->g_d, S->bm1_d, S->D_d, S->dim, S->lx, n, 1.0, 0.0, S->diagA_d);
+    ctx->launches++;
+  }
+  axpby_fields_kernel<<<grid, 256, 0, st>>>(d, S->diagA_d, S->bm1_d, h1, h2, n);
   ctx->launches++;
   NSB_CHECK(launch_gs(S, d, 1, 0, 0, nullptr, 0, 0, nullptr));
   recip_kernel<<<grid, 256, 0, st>>>(d, n);
