@@ -2,7 +2,7 @@
  * nekstab_b200.h -- C ABI of the B200-native nekStab Arnoldi / Newton-Krylov hot path.
  *
  * This is the boundary the reference's Fortran host code binds through ISO_C_BINDING
- * (see fortran/nek_dvectors.f90 and INTEGRATION.md).  Every entry point names the reference
+ * (see nekstab_next_b200/fortran/nekstab_b200.f90 and INTEGRATION.md).  Every entry point names the reference
  * routine it replaces (paths relative to the nekStab repository root).
  *
  * Conventions

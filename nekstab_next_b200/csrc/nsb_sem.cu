@@ -1860,16 +1860,14 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
     NSB_CHECK(launch_axhelm(S, u, w, step, fstride, op->h1, op->h2, op->c_d, 1, op->alpha, op->beta, S->bmask_d));
     NSB_CHECK(launch_gs(S, w, step, fstride, 1, u, op->alpha, op->beta, S->bmask_d));
   }
-  // fields outside the operator (pressure, scalars, %time) are carried through unchanged
-  if (op->nfields_apply < L->nfields || true) {
-    // copy the rows not covered by the applied fields: time row and remaining fields
-    cudaStream_t s = L->ctx->stream;
-    NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->time_row, bin->col(cin) + L->time_row, sizeof(double),
-                             cudaMemcpyDeviceToDevice, s));
-    for (int f = op->nfields_apply; f < L->nfields; ++f)
-      if (L->len[f] > 0)
-        NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->off[f], bin->col(cin) + L->off[f],
-                                 sizeof(double) * L->len[f], cudaMemcpyDeviceToDevice, s));
-  }
+  // the rows outside the operator are carried through unchanged: %time and the remaining fields
+  // (pressure, scalars)
+  cudaStream_t s = L->ctx->stream;
+  NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->time_row, bin->col(cin) + L->time_row, sizeof(double),
+                           cudaMemcpyDeviceToDevice, s));
+  for (int f = op->nfields_apply; f < L->nfields; ++f)
+    if (L->len[f] > 0)
+      NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->off[f], bin->col(cin) + L->off[f], sizeof(double) * L->len[f],
+                               cudaMemcpyDeviceToDevice, s));
   return NSB_OK;
 }
