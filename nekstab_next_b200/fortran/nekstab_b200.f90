@@ -40,6 +40,7 @@ module nekstab_b200
    public :: nsb_check, nsb_startup, nsb_shutdown, nsb_upload, nsb_download
    public :: nsb_p2p_mailbox_create, nsb_p2p_mailbox_connect
    public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
+   public :: nsb_vec_zero, nsb_vec_copy, nsb_vec_scal, nsb_vec_axpby, nsb_vec_dot   ! for nekstab_b200_lightkrylov
    public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d, eigs_d, svds_d
 
    interface
