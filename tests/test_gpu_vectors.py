@@ -125,3 +125,30 @@ def test_empty_and_ragged_fields(ctx):
     assert all(np.array_equal(o, f) for o, f in zip(out, fb)) and t == -3.0
     B.close()
     lay.close()
+
+
+def test_complex_vector_is_a_layout(ctx):
+    """cmplx_nek_vector (core/nek_vectors.f90:33-43, 140-201) = two real vectors; its dot is
+    real_dot(re, re) + real_dot(im, im), scal / axpby act on both parts: on the device that is simply a
+    layout listing the fields of the real part followed by those of the imaginary part (resolvent path,
+    core/linear_stab.f90:124-160)."""
+    import nekstab_next_b200 as nb
+    rng = np.random.default_rng(12)
+    n, n2 = 3000, 1700                      # velocity points, pressure points
+    bm1 = rng.random(n) + 0.1
+    lens = [n, n, n2, n, n, n2]             # re: vx vy pr | im: vx vy pr
+    dots = [True, True, False, True, True, False]
+    lay = nb.Layout(ctx, lens, dots)
+    lay.set_weight([bm1] * 4)
+    B = nb.Basis(lay, 2)
+    a = [rng.standard_normal(m) for m in lens]
+    b = [rng.standard_normal(m) for m in lens]
+    B[0].upload(a)
+    B[1].upload(b)
+    ref = sum(np.sum(a[i] * bm1 * b[i]) for i in (0, 1, 3, 4))
+    assert abs(B[0].dot(B[1]) - ref) <= TOL * abs(ref)
+    B[0].axpby(0.25, B[1], -3.0)
+    got, _ = B[0].download()
+    for i in range(6):
+        assert relerr(got[i], 0.25 * a[i] - 3.0 * b[i]) <= 1e-15
+    B.close()
