@@ -1,0 +1,102 @@
+"""The oracle restatements that have no reference fixture to pin them ([UPSTREAM-RECALL] pieces) checked
+against independent mathematics on the CPU: Gauss-Legendre dealiasing operators, EXT/BDF coefficients,
+the LightKrylov-style eigs / svds drivers against numpy's dense solvers."""
+import numpy as np
+
+from oracle import krylov as okr
+from oracle import sem as osem
+
+
+def test_gauss_legendre_and_interpolation_operators():
+    for lxd in (6, 9, 12):
+        z, w = osem.gl(lxd)
+        for p in range(2 * lxd):                       # exact to degree 2 lxd - 1
+            exact = 0.0 if p % 2 else 2.0 / (p + 1)
+            assert abs(np.sum(w * z ** p) - exact) < 1e-13
+        D = osem.deriv_matrix(z)
+        for p in range(lxd):                           # derivative matrix exact on P_{lxd-1}
+            assert np.max(np.abs(D @ z ** p - (p * z ** (p - 1) if p else 0 * z))) < 1e-10
+    zg, _ = osem.gll(7)
+    zd, _ = osem.gl(12)
+    J = osem.interp_matrix(zg, zd)
+    for p in range(8):                                 # interpolation reproduces P_7
+        assert np.max(np.abs(J @ zg ** p - zd ** p)) < 1e-13
+    assert np.allclose(osem.interp_matrix(zg, zg), np.eye(8))
+
+
+def test_dealiased_convection_equals_the_weak_form_integral():
+    """sum_p [J^T (c . grad)(J u)]_p = integral of c . grad u, here for polynomials the 3/2 rule integrates
+    exactly (3-D and 2-D, affine elements), and v^T [..] = integral of v c . grad u for a test function v."""
+    N = 7
+    x, y, z, _ = osem.box_mesh(2, 1, 2, N)
+    geo = osem.geometry(N, x, y, z)
+    dl = osem.dealias_setup(N, 12, geo['rst'])
+    cf = osem.set_convect([x ** 3, y * x, 1.0 + z ** 2], dl)
+    r = osem.convect_dealiased(x ** 4 * y, cf, dl)
+    assert abs(r.sum() - (4 / 7 / 2 + 1 / 12)) < 1e-13
+    v = x * z + y ** 2                                  # integral of v * (4 x^6 y + x^5 y) over the unit cube
+    exact = (4 / 8) * (1 / 2) * (1 / 2) + (1 / 7) * (1 / 2) * (1 / 2) + (4 / 7) * (1 / 4) + (1 / 6) * (1 / 4)
+    assert abs(np.sum(v * r) - exact) < 1e-13
+    x2, y2, _ = osem.box_mesh_2d(2, 3, 5)
+    g2 = osem.geometry(5, x2, y2)
+    dl2 = osem.dealias_setup(5, 9, g2['rst'])
+    r2 = osem.convect_dealiased(x2 ** 3 * y2, osem.set_convect([y2 ** 2, x2 + 1.0], dl2), dl2)
+    # y^2 * 3 x^2 y + (x + 1) x^3 -> 3 * (1/3) * (1/4) + 1/5 + 1/4
+    assert abs(r2.sum() - (0.25 + 0.2 + 0.25)) < 1e-13
+
+
+def test_bdf_ext_coefficients_and_update():
+    # Nek's convention: bd[0] u^{n+1} = sum_i bd[i] u^{n+1-i} + dt f ; consistency and order conditions
+    for o, bd in ((1, [1.0, 1.0]), (2, [1.5, 2.0, -0.5]), (3, [11 / 6, 3.0, -1.5, 1 / 3])):
+        i = np.arange(1, o + 1)
+        b = np.array(bd[1:])
+        assert abs(bd[0] - b.sum()) < 1e-15                       # constants are reproduced
+        # u(t) = t^p sampled at t = 0 (new), -1, -2, ..: bd0 * 0 - sum_i b_i (-i)^p = derivative at 0 * dt
+        for p in range(1, o + 1):
+            lhs = bd[0] * 0.0 - np.sum(b * (-i.astype(float)) ** p)
+            assert abs(lhs - (1.0 if p == 1 else 0.0)) < 1e-14
+    for o, ab in ((1, [1.0, 0, 0]), (2, [2.0, -1.0, 0]), (3, [3.0, -3.0, 1.0])):
+        i = np.arange(1, 4)
+        for p in range(o):                                        # extrapolation to t = 0 exact on P_{o-1}
+            assert abs(np.sum(np.array(ab) * (-i.astype(float)) ** p) - (1.0 if p == 0 else 0.0)) < 1e-14
+    rng = np.random.default_rng(0)
+    bf, e1, e2, v0, v1, v2, bm1 = (rng.standard_normal(50) for _ in range(7))
+    bf0, e10, e20 = bf.copy(), e1.copy(), e2.copy()
+    ab, bd = [3.0, -3.0, 1.0], [11 / 6, 3.0, -1.5, 1 / 3]
+    osem.bdf_ext(bf, e1, e2, [v0, v1, v2], bm1, ab, bd, 7.0)
+    assert np.array_equal(e2, e10) and np.array_equal(e1, bf0)
+    assert np.allclose(bf, 3 * bf0 - 3 * e10 + e20 + 7.0 * bm1 * (3 * v0 - 1.5 * v1 + v2 / 3), rtol=1e-14)
+
+
+def _dense_problem(n, seed, sym=False):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)) / np.sqrt(n)
+    if sym:
+        A = 0.5 * (A + A.T)
+    w = rng.random(n) + 0.5                                      # inner-product weight
+    c = okr.Ctx(bm1s=w, in_dot=[True], time_in_dot=False)
+    return A, w, c, okr.KVec([rng.standard_normal(n)], 0.0)
+
+
+def test_oracle_eigs_against_dense_eigenvalues():
+    n = 60
+    A, w, c, q0 = _dense_problem(n, 4)
+    okr.k_normalize(c, q0)
+    vals, vecs, res, k, H = okr.eigs(c, lambda q: okr.KVec([A @ q.f[0]], q.time), q0, n, nev=3, tol=1e-10)
+    ev = np.linalg.eigvals(A)
+    for i in np.where(res < 1e-10)[0]:
+        assert np.min(np.abs(ev - vals[i])) < 1e-8
+    assert np.count_nonzero(res < 1e-10) >= 3
+
+
+def test_oracle_svds_against_dense_svd_in_the_weighted_inner_product():
+    """svds with rmatvec = the adjoint in the W inner product: singular values of W^1/2 A W^-1/2."""
+    n = 50
+    A, w, c, u0 = _dense_problem(n, 7)
+    okr.k_normalize(c, u0)
+    adj = (A.T * w[None, :]) / w[:, None]                        # W^-1 A^T W
+    sig, uv, vv, res, k, B = okr.svds(c, lambda q: okr.KVec([A @ q.f[0]], q.time),
+                                      lambda q: okr.KVec([adj @ q.f[0]], q.time), u0, n, nev=3, tol=1e-10)
+    ref = np.linalg.svd(np.sqrt(w)[:, None] * A / np.sqrt(w)[None, :], compute_uv=False)
+    conv = np.sort(sig[res < 1e-10])[::-1]
+    assert len(conv) >= 3 and np.allclose(conv[:3], ref[:3], rtol=1e-9)
