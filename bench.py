@@ -171,6 +171,11 @@ def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 for multi-rank launches; rank 0 alone works here and may use
+        # every host core, like the single-process launch
+        from oracle import cref
+        cref.set_num_threads(os.cpu_count() or 1)
     rates, info = [], None
     for _ in range(max(1, a.warmup)):
         cpu_arnoldi_rate(a, sample_ks=(10,))

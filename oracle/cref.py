@@ -44,6 +44,10 @@ def num_threads():
     return load().ref_num_threads()
 
 
+def set_num_threads(n):
+    load().ref_set_num_threads(C.c_int(int(n)))
+
+
 def axhelm3d(u, g, bm1, D, h1, h2):
     lib = load()
     nel, lx = u.shape[0], u.shape[-1]

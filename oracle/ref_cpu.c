@@ -30,6 +30,15 @@ int ref_num_threads(void) {
 #endif
 }
 
+/* the launcher may have pinned OMP_NUM_THREADS to 1 (torchrun does for N > 1 ranks) */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* math.f glsc3: tmp += a(i)*b(i)*mult(i); then gop(+) -- the gop is the OpenMP reduction */
 double ref_glsc3(const double *a, const double *b, const double *mult, int64_t n) {
   double tmp = 0.0;
