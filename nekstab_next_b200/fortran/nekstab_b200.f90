@@ -494,7 +494,8 @@ module nekstab_b200
    public :: nsb_sync, nsb_vec_norm, nsb_orthonormalize, nsb_basis_gram, nsb_basis_qr, nsb_basis_rotate
    public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
    public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_hmholtz_vec, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
-   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose, nsb_op_apply, nsb_op_destroy, nsb_op_count
+   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose
+   public :: nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues
 
 

@@ -1,0 +1,126 @@
+"""There is no Fortran compiler in the image, so the ISO_C_BINDING layer cannot be compiled here.  This test
+checks what a compiler would NOT even catch -- that every bind(C) interface matches the C prototype it binds
+(argument count, by-value vs by-reference, C kind of every by-value scalar) -- plus the cheap syntax invariants
+(balanced blocks, free-form line length)."""
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+F90 = ROOT / 'nekstab_next_b200' / 'fortran'
+HDR = (ROOT / 'include' / 'nekstab_b200.h').read_text()
+
+BYVAL_KIND = {'int': 'integer(c_int)', 'double': 'real(c_double)', 'int64_t': 'integer(c_int64_t)',
+              'uint64_t': 'integer(c_int64_t)'}
+
+
+def c_prototypes():
+    text = re.sub(r'/\*.*?\*/', ' ', HDR, flags=re.S)
+    out = {}
+    for m in re.finditer(r'\b(?:int|int64_t|const char \*)\s*(nsb_\w+)\s*\(([^;{]*)\)\s*;', text):
+        name, args = m.group(1), ' '.join(m.group(2).split())
+        params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+        out[name] = params
+    return out
+
+
+def classify_c(param):
+    """-> ('ref', None) for pointers, ('val', fortran type) for by-value arguments"""
+    if '*' in param:
+        return 'ref', None
+    toks = param.replace('const', '').split()
+    ctype = ' '.join(toks[:-1])
+    if re.fullmatch(r'nsb_\w+_t', ctype):
+        return 'val', 'type(c_ptr)'
+    if ctype == 'nsb_host_matvec_fn':
+        return 'val', 'type(c_funptr)'
+    return 'val', BYVAL_KIND[ctype]
+
+
+def fortran_interfaces(src):
+    lines, buf = [], ''
+    for raw in src.splitlines():
+        line = raw.split('!')[0].rstrip() if "'" not in raw.split('!')[0] or raw.count("'") % 2 == 0 else raw.rstrip()
+        line = raw if "name='" in raw else line
+        line = line.split('!<')[0].rstrip()
+        if line.rstrip().endswith('&'):
+            buf += line.rstrip()[:-1] + ' '
+            continue
+        lines.append(buf + line)
+        buf = ''
+    out, i = {}, 0
+    while i < len(lines):
+        m = re.search(r"function\s+(\w+)\s*\(([^)]*)\)\s*.*bind\(C,\s*name='(\w+)'\)", lines[i])
+        if not m:
+            i += 1
+            continue
+        fname, args, cname = m.group(1), [a.strip() for a in m.group(2).split(',') if a.strip()], m.group(3)
+        decl = {}
+        i += 1
+        while not re.match(r'\s*end function', lines[i]):
+            d = re.match(r'\s*([\w() ,=*:]+?)\s*::\s*(.+)$', lines[i])
+            if d and not lines[i].strip().startswith('import'):
+                spec = d.group(1)
+                base = spec.split(',')[0].strip().replace(' ', '')
+                val = bool(re.search(r',\s*value\b', spec))
+                for nm in re.split(r',\s*(?![^()]*\))', d.group(2)):
+                    decl[re.sub(r'\(.*', '', nm).strip()] = (base, val)
+            i += 1
+        out[cname] = (fname, args, decl)
+        i += 1
+    return out
+
+
+def test_every_binding_matches_its_c_prototype():
+    protos = c_prototypes()
+    assert len(protos) > 80
+    src = (F90 / 'nekstab_b200.f90').read_text()
+    ifs = fortran_interfaces(src)
+    assert len(ifs) >= 60
+    for cname, (fname, args, decl) in ifs.items():
+        assert cname in protos, f'{cname} is bound but not declared in the header'
+        assert fname == cname
+        cpar = protos[cname]
+        assert len(args) == len(cpar), f'{cname}: {len(args)} Fortran dummies, {len(cpar)} C parameters'
+        for a, cp in zip(args, cpar):
+            assert a in decl, f'{cname}: dummy {a} has no declaration'
+            base, val = decl[a]
+            kind, ftype = classify_c(cp)
+            if kind == 'val':
+                assert val, f'{cname}: `{cp}` is passed by value in C, dummy {a} lacks VALUE'
+                assert base == ftype.replace(' ', ''), f'{cname}: `{cp}` needs {ftype}, dummy {a} is {base}'
+            else:
+                # a C pointer: by-reference dummy of any type, or a c_ptr / c_funptr handed over by value
+                assert (not val) or base in ('type(c_ptr)', 'type(c_funptr)'), \
+                    f'{cname}: `{cp}` is a pointer, dummy {a} is a by-value {base}'
+        if cname != 'nsb_last_error' and cname != 'nsb_sem_npts':
+            assert decl.get('ierr', ('', False))[0] == 'integer(c_int)', f'{cname}: result is not integer(c_int)'
+
+
+def test_free_form_invariants():
+    for f in F90.glob('*.f90'):
+        src = f.read_text()
+        for n, line in enumerate(src.splitlines(), 1):
+            assert len(line) <= 132, f'{f.name}:{n} is {len(line)} characters long'
+        code = '\n'.join(ln.split('!')[0] for ln in src.splitlines()).lower()
+        for kw in ('function', 'subroutine', 'interface', 'module', 'type'):
+            opens = len(re.findall(rf'^\s*(?:[\w()]+\s+)*{kw}\s+\w+', code, flags=re.M)) if kw != 'interface' \
+                else len(re.findall(r'^\s*interface\s*$', code, flags=re.M))
+            ends = len(re.findall(rf'^\s*end\s+{kw}\b', code, flags=re.M))
+            if kw == 'type':       # `type(c_ptr) :: x` declarations are not blocks
+                opens = len(re.findall(r'^\s*type\s*(?:,[^:\n]*)?(?:::)?\s*\w+\s*$', code, flags=re.M))
+            if kw == 'module':
+                opens = len(re.findall(r'^\s*module\s+(?!procedure)\w+\s*$', code, flags=re.M))
+            if kw == 'function':
+                opens = len(re.findall(r'^\s*(?:[\w()]+\s+)*function\s+\w+\s*\(', code, flags=re.M))
+            if kw == 'subroutine':
+                opens = len(re.findall(r'^\s*subroutine\s+\w+', code, flags=re.M))
+            assert opens == ends, f'{f.name}: {opens} `{kw}` blocks opened, {ends} closed'
+
+
+def test_adapter_mirrors_the_reference_type_bound_names():
+    src = (F90 / 'nekstab_b200_lightkrylov.f90').read_text()
+    for proc in ('zero', 'dot', 'scal', 'axpby'):           # core/nek_vectors.f90:27-30
+        assert re.search(rf'procedure, pass\(self\), public :: {proc} =>', src)
+    for proc in ('matvec', 'rmatvec'):                       # core/linear_operators.f90:21-22
+        assert re.search(rf'procedure, pass\(self\), public :: {proc} =>', src)
+    assert 'extends(abstract_vector)' in src and 'extends(abstract_linop)' in src
