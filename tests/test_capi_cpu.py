@@ -31,6 +31,35 @@ def test_library_exports_every_header_symbol(lib):
     assert lib.nsb_version() == 100
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every ctypes signature against its C prototype: argument count, by-value scalar kinds, pointer-ness."""
+    import ctypes as C
+    from nekstab_next_b200 import _capi
+    text = re.sub(r'/\*.*?\*/', ' ', (ROOT / 'include' / 'nekstab_b200.h').read_text(), flags=re.S)
+    byval = {'int': C.c_int, 'double': C.c_double, 'int64_t': C.c_int64, 'uint64_t': C.c_uint64}
+    seen = 0
+    for m in re.finditer(r'\b(int|int64_t|const char \*)\s*(nsb_\w+)\s*\(([^;{]*)\)\s*;', text):
+        ret, name, args = m.group(1), m.group(2), ' '.join(m.group(3).split())
+        params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+        res, argtypes = _capi.PROTOTYPES[name]
+        assert len(argtypes) == len(params), f'{name}: {len(argtypes)} ctypes arguments, {len(params)} C parameters'
+        assert res is {'int': C.c_int, 'int64_t': C.c_int64, 'const char *': C.c_char_p}[ret], name
+        for at, cp in zip(argtypes, params):
+            if '*' in cp:
+                assert at is C.c_void_p or at is C.c_char_p or hasattr(at, '_type_') and not issubclass(at, C._SimpleCData) \
+                    or issubclass(at, C._Pointer), f'{name}: `{cp}` is a pointer, ctypes has {at}'
+                continue
+            ctype = ' '.join(cp.replace('const', '').split()[:-1])
+            if re.fullmatch(r'nsb_\w+_t', ctype):
+                assert at is C.c_void_p, f'{name}: handle `{cp}` must be c_void_p, ctypes has {at}'
+            elif ctype == 'nsb_host_matvec_fn':
+                assert at is _capi.HOST_MATVEC, name
+            else:
+                assert at is byval[ctype], f'{name}: `{cp}` needs {byval[ctype].__name__}, ctypes has {at}'
+        seen += 1
+    assert seen == len(_capi.PROTOTYPES), 'a ctypes prototype has no C declaration'
+
+
 def test_library_is_sm100a_only(lib):
     from nekstab_next_b200 import _capi
     out = subprocess.run(['cuobjdump', '--list-elf', str(_capi.LIB_PATH)], capture_output=True, text=True).stdout
