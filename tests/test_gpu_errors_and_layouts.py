@@ -105,3 +105,44 @@ def test_random_layouts_roundtrip_dot_axpby(ctx, lens, dots, tdot, seed):
     assert lay.ld % 1024 == 0 and lay.ndot % 1024 == 0 and lay.ndof_dot == sum(n for n, d in zip(lens, dots) if d)
     B.close()
     lay.close()
+
+
+def test_errors_of_the_widened_entry_points(ctx):
+    """svds / Helmholtz / EXT-BDF / time-stepper operator: bad arguments come back as NSB_EINVAL, and the
+    library keeps working afterwards."""
+    import nekstab_next_b200 as nb
+    from helpers import BoxProblem
+    P = BoxProblem(nel=(2, 1, 1), N=3, nfields=3)
+    lay, B, S, op = P.gpu(ctx, 6)
+    V = nb.Basis(lay, 2)
+    cases = [
+        lambda: nb.svds(B, V, op, op, 5, 1, 1e-8),                       # V has fewer than k_dim columns
+        lambda: nb.svds(B, V, op, op, 0, 1, 1e-8),
+        lambda: nb.eigs(B, op, 9, 1, 1e-8),                              # basis has 6 columns
+        lambda: S.hmholtz_vec(B[0], B[1], 0, 4, 1.0, 1.0),               # more than three systems
+        lambda: S.hmholtz_vec(B[0], B[1], 1, 3, 1.0, 1.0),               # fields 1..3 do not exist
+        lambda: S.hmholtz(B[0], B[0], 0, 1.0, 1.0),                      # in place
+        lambda: S.bdf_ext(B[0], B[1], B[1], [B[3]], [1, 0, 0], [1, 1], 1.0),          # e1 == e2
+        lambda: S.bdf_ext(B[0], B[1], B[2], [B[0]], [1, 0, 0], [1, 1], 1.0),          # velocity aliases bf
+        lambda: S.bdf_ext(B[0], B[1], B[2], [B[3]] * 4, [1, 0, 0], [1] * 5, 1.0),     # nbd > 3
+        lambda: nb.stepper_operator(S, lay, 1, 0, 0.1, 1e-3, 3),         # slot 0 was never set
+        lambda: nb.stepper_operator(S, lay, 1, -1, -0.1, 1e-3, 3),       # negative diffusivity
+        lambda: nb.stepper_operator(S, lay, 4, -1, 0.1, 1e-3, 3),        # more fields than the layout has
+        lambda: nb.stepper_operator(S, lay, 1, -1, 0.1, 1e-3, 0),        # no steps
+    ]
+    for fn in cases:
+        with pytest.raises(nb.NsbError) as e:
+            fn()
+        assert e.value.code == -1 and str(e.value)
+    step = nb.stepper_operator(S, lay, 2, -1, 0.1, 1e-3, 2)
+    wrong = nb.Basis(nb.Layout(ctx, [P.npts] * 3, [True] * 3), 2)
+    with pytest.raises(nb.NsbError):
+        step.matvec(wrong[0], wrong[1])                                  # operator built for another layout
+    q = P.random_kvec()
+    from helpers import upload
+    upload(B[0], q)
+    step.matvec(B[0], B[1])                                              # still works; third field carried through
+    out = B[1].download()[0]
+    assert np.array_equal(out[2], q.f[2].ravel()) and not np.array_equal(out[0], q.f[0].ravel())
+    assert np.all(np.isfinite(out[0])) and np.all(np.isfinite(out[1]))
+    step.close()
