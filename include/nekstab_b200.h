@@ -354,6 +354,12 @@ int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur_tgt, doubl
  * leading dimension k_dim; *kused = Krylov dimension reached. */
 int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double tol, int orth_mode, double *H,
              int ldh, double *vals_c16, double *vecs_c16, double *residual, int *kused, int *nconv);
+/* Ritz-vector assembly (core/eigensolvers.f90:565-585, 609-615; get_vec, core/linear_stab.f90:362):
+ * fp = Q(:,1:k) y for complex y (interleaved re,im): column cre <- Q Re(y), column cim <- Q Im(y) of bout;
+ * alpha_re / alpha_im = their BM1 norms (before scaling); normalize != 0 scales both parts by
+ * 1 / sqrt(alpha_re^2 + alpha_im^2) as the reference does before writing the mode. */
+int nsb_ritz_vector(nsb_basis_t Q, int k, const double *y_c16, nsb_basis_t bout, int cre, int cim,
+                    int normalize, double *alpha_re, double *alpha_im);
 /* Step-wise singular-value solver, the call transient_growth_analysis makes
  * (core/linear_stab.f90:112: svds(A, U, V, uvecs, vvecs, sigma, residuals, info, nev, tolerance)):
  * Golub-Kahan bidiagonalisation with full re-orthogonalisation, v_k = A^T u_k, u_k+1 = A v_k,

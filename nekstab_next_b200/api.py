@@ -632,6 +632,17 @@ def eigs(Q: Basis, op: LinearOperator, k_dim: int, nev: int, tol: float, orth_mo
     return vals[:k].copy(), vecs[:k, :k].copy(), res[:k].copy(), k, nc.value, H
 
 
+def ritz_vector(Q: Basis, k: int, y, out_re: nek_dvector, out_im: nek_dvector, normalize: bool = True):
+    """fp = Q(:,1:k) y for complex y (core/eigensolvers.f90:565-585): real part -> out_re, imaginary part ->
+    out_im (columns of the same basis), both scaled by 1/sqrt(|Re|^2 + |Im|^2); returns (|Re|, |Im|)."""
+    yc = np.ascontiguousarray(y, dtype=np.complex128).ravel()
+    assert out_re.basis is out_im.basis and yc.size >= k
+    ar, ai = C.c_double(), C.c_double()
+    check(Q.lib.nsb_ritz_vector(Q.h, int(k), yc.ctypes.data_as(c_double_p), out_re.basis.h, out_re.col, out_im.col,
+                                int(normalize), C.byref(ar), C.byref(ai)))
+    return ar.value, ai.value
+
+
 def svd(A):
     """Thin SVD through the injected dgesvd: returns (U, S, V) with A = U diag(S) V^T."""
     set_lapack_from_scipy()

@@ -424,6 +424,42 @@ extern "C" int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ritz-vector assembly (core/eigensolvers.f90:565-585, 609-615; get_vec core/linear_stab.f90:362):
+// fp = Q(:,1:k) y with complex y -> real part = Q Re(y), imaginary part = Q Im(y) (two device GEMVs over
+// the basis), alpha_r = |Re fp|, alpha_i = |Im fp| in the BM1 norm, and the reference's scaling of both
+// parts by beta = 1 / sqrt(alpha_r^2 + alpha_i^2) so that the volume integral of fp conj(fp) is 1.
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_ritz_vector(nsb_basis_t Q, int k, const double *y_c16, nsb_basis_t bout, int cre, int cim,
+                               int normalize, double *alpha_re, double *alpha_im) {
+  NSB_REQUIRE(Q && y_c16 && bout, "nsb_ritz_vector: NULL argument");
+  NSB_REQUIRE(k >= 1 && k <= Q->ncols, "nsb_ritz_vector: k=%d out of range", k);
+  NSB_REQUIRE(cre != cim, "nsb_ritz_vector: real and imaginary part need different columns");
+  std::vector<double> yre(k), yim(k);
+  for (int i = 0; i < k; ++i) {
+    yre[i] = y_c16[2 * i];
+    yim[i] = y_c16[2 * i + 1];
+  }
+  NSB_CHECK(nsb_basis_gemv(Q, k, yre.data(), bout, cre));
+  NSB_CHECK(nsb_basis_gemv(Q, k, yim.data(), bout, cim));
+  double ar = 0.0, ai = 0.0;
+  NSB_CHECK(nsb_vec_norm(bout, cre, &ar));
+  NSB_CHECK(nsb_vec_norm(bout, cim, &ai));
+  if (normalize) {
+    const double a2 = ar * ar + ai * ai;
+    if (!(a2 > 0.0)) {
+      set_error("nsb_ritz_vector: zero vector");
+      return NSB_EBREAKDOWN;
+    }
+    const double beta = 1.0 / std::sqrt(a2);
+    NSB_CHECK(nsb_vec_scal(bout, cre, beta));
+    NSB_CHECK(nsb_vec_scal(bout, cim, beta));
+  }
+  if (alpha_re) *alpha_re = ar;
+  if (alpha_im) *alpha_im = ai;
+  return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // svds: the call transient_growth_analysis makes (core/linear_stab.f90:112:
 // svds(A, U, V, uvecs, vvecs, sigma, residuals, info, nev, tolerance)).  [UPSTREAM-RECALL:
 // LightKrylov's Golub-Kahan Lanczos bidiagonalisation with full re-orthogonalisation, one step at a

@@ -42,6 +42,7 @@ module nekstab_b200
    public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
    public :: nsb_vec_zero, nsb_vec_copy, nsb_vec_scal, nsb_vec_axpby, nsb_vec_dot   ! for nekstab_b200_lightkrylov
    public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d, eigs_d, svds_d
+   public :: nsb_ritz_vector
 
    interface
       function nsb_last_error() bind(C, name='nsb_last_error') result(msg)
@@ -235,6 +236,15 @@ module nekstab_b200
          real(c_double) :: H(ldh, *), residual(*)
          complex(c_double_complex) :: vals(*), vecs(k_dim, *)
          integer(c_int) :: kused, nconv, ierr
+      end function
+      function nsb_ritz_vector(Q, k, y, bout, cre, cim, normalize, alpha_re, alpha_im) &
+         bind(C, name='nsb_ritz_vector') result(ierr)
+         import :: c_int, c_ptr, c_double, c_double_complex
+         type(c_ptr), value :: Q, bout
+         integer(c_int), value :: k, cre, cim, normalize
+         complex(c_double_complex) :: y(*)
+         real(c_double) :: alpha_re, alpha_im
+         integer(c_int) :: ierr
       end function
       function nsb_set_lapack_svd(dgesvd) bind(C, name='nsb_set_lapack_svd') result(ierr)
          import :: c_int, c_funptr

@@ -223,3 +223,31 @@ def test_svds_host_operator_pair(ctx):
     Uk = np.stack([U[j].download()[0][0] for j in range(k)], axis=1)
     x = Uk @ uv[:, i0]
     assert min(np.linalg.norm(x - Uo[:, 0]), np.linalg.norm(x + Uo[:, 0])) < 1e-7
+
+
+def test_ritz_vector_assembly(ctx):
+    """fp = Q y with complex y (core/eigensolvers.f90:565-585): real / imaginary parts and the unit scaling."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 1), N=4, nfields=2, conv=True, seed=5)
+    c = P.octx()
+    K = 6
+    lay, B, S, op = P.gpu(ctx, K + 3)
+    q0 = seed(P, c)
+    upload(B[0], q0)
+    H = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(B, H, 1, K, K, op)
+    vecs, vals = nb.eig(H[:K, :K])
+    y = vecs[:, 0]
+    ar, ai = nb.ritz_vector(B, K, y, B[K + 1], B[K + 2])
+    Qh = [download(B[j], P.shape) for j in range(K)]
+    re = okr.k_matmul(Qh, np.ascontiguousarray(y.real), K)
+    im = okr.k_matmul(Qh, np.ascontiguousarray(y.imag), K)
+    nr, ni = okr.k_norm(c, re), okr.k_norm(c, im)
+    assert abs(ar - nr) <= 1e-12 * max(nr, 1e-300) + 1e-15 and abs(ai - ni) <= 1e-12 * max(ni, 1.0)
+    beta = 1.0 / np.sqrt(nr ** 2 + ni ** 2)
+    for col, ref in ((K + 1, re), (K + 2, im)):
+        got = download(B[col], P.shape)
+        for f in range(2):
+            assert np.max(np.abs(got.f[f] - beta * ref.f[f])) <= 1e-12 * beta * max(nr, ni)
+    # Re/Im parts together have unit norm
+    assert abs(nb.k_norm(B[K + 1]) ** 2 + nb.k_norm(B[K + 2]) ** 2 - 1.0) <= 1e-12
