@@ -354,6 +354,14 @@ int nsb_krylov_schur(nsb_basis_t Q, nsb_op_t op, int k_dim, int schur_tgt, doubl
  * leading dimension k_dim; *kused = Krylov dimension reached. */
 int nsb_eigs(nsb_basis_t Q, nsb_op_t op, int k_dim, int nev, double tol, int orth_mode, double *H,
              int ldh, double *vals_c16, double *vecs_c16, double *residual, int *kused, int *nconv);
+/* newton_krylov (core/newton_krylov.f90:1-168): f = F(q); residual = |f|^2; stop when residual < tol;
+ * dq = ts_gmres(J, f); q -= dq.  fop applies the (nonlinear) forward map F, jop the linearisation about the
+ * current q -- in the reference both are the host time-stepper, i.e. host-callback operators whose owner
+ * re-linearises when F is called.  (bw, cf), (bw, cdq): two work vectors; Q: GMRES basis with >= ksize+2
+ * columns; residual_hist: maxiter_newton entries; *iters = Newton iterations performed. */
+int nsb_newton_krylov(nsb_basis_t Q, nsb_op_t fop, nsb_op_t jop, nsb_basis_t bq, int cq, nsb_basis_t bw, int cf,
+                      int cdq, int maxiter_newton, int maxiter_gmres, int ksize, double tol, int orth_mode,
+                      int *iters, double *residual_hist, int *calls);
 /* Ritz-vector assembly (core/eigensolvers.f90:565-585, 609-615; get_vec, core/linear_stab.f90:362):
  * fp = Q(:,1:k) y for complex y (interleaved re,im): column cre <- Q Re(y), column cim <- Q Im(y) of bout;
  * alpha_re / alpha_im = their BM1 norms (before scaling); normalize != 0 scales both parts by

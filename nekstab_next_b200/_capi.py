@@ -114,6 +114,8 @@ PROTOTYPES = {
                                    c_int_p]),
     'nsb_eigs': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p, C.c_int, c_double_p,
                            c_double_p, c_double_p, c_int_p, c_int_p]),
+    'nsb_newton_krylov': (C.c_int, [H, H, H, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                    C.c_int, c_int_p, c_double_p, c_int_p]),
     'nsb_ritz_vector': (C.c_int, [H, C.c_int, c_double_p, H, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
     'nsb_svds': (C.c_int, [H, H, H, H, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p, C.c_int, c_double_p,
                            c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),

@@ -632,6 +632,21 @@ def eigs(Q: Basis, op: LinearOperator, k_dim: int, nev: int, tol: float, orth_mo
     return vals[:k].copy(), vecs[:k, :k].copy(), res[:k].copy(), k, nc.value, H
 
 
+def newton_krylov(Q: Basis, fop: LinearOperator, jop: LinearOperator, q: nek_dvector, f: nek_dvector,
+                  dq: nek_dvector, maxiter_newton: int, maxiter_gmres: int, ksize: int, tol: float,
+                  orth_mode: int = ORTH_CGS2):
+    """core/newton_krylov.f90:1 -- q is updated in place; returns (residual history, linear-solver calls).
+    fop = forward map F (may be nonlinear), jop = its linearisation about the current q (the owner of the two
+    host callbacks re-linearises when F is called); f and dq are work vectors of one basis."""
+    set_lapack_from_scipy()
+    assert f.basis is dq.basis
+    hist = np.zeros(maxiter_newton)
+    it, calls = C.c_int(), C.c_int()
+    check(Q.lib.nsb_newton_krylov(Q.h, fop.h, jop.h, q.basis.h, q.col, f.basis.h, f.col, dq.col, maxiter_newton,
+                                  maxiter_gmres, ksize, tol, orth_mode, C.byref(it), _dp(hist), C.byref(calls)))
+    return hist[:it.value].copy(), calls.value
+
+
 def ritz_vector(Q: Basis, k: int, y, out_re: nek_dvector, out_im: nek_dvector, normalize: bool = True):
     """fp = Q(:,1:k) y for complex y (core/eigensolvers.f90:565-585): real part -> out_re, imaginary part ->
     out_im (columns of the same basis), both scaled by 1/sqrt(|Re|^2 + |Im|^2); returns (|Re|, |Im|)."""

@@ -568,3 +568,36 @@ extern "C" int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int cr
   if (nhist) *nhist = nh;
   return NSB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Newton-Krylov fixed-point iteration  (core/newton_krylov.f90:1-168): f = F(q) (:102), residual = |f|^2
+// (:107), stop when residual < tol (:117), dq = ts_gmres(J, f) (:125), q -= dq (:130).  F and J are operator
+// handles: in the reference both are the host time-stepper (nonlinear_forward_map and the linearised
+// solver set up about the current q by prepare_linearized_solver, :71), i.e. host callbacks whose owner
+// re-linearises inside F; all vectors, the GMRES basis and its orthogonalisation stay on the device.
+// (bw, cf) and (bw, cdq) are two work vectors.  residual_hist holds maxiter_newton entries.
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_newton_krylov(nsb_basis_t Q, nsb_op_t fop, nsb_op_t jop, nsb_basis_t bq, int cq, nsb_basis_t bw,
+                                 int cf, int cdq, int maxiter_newton, int maxiter_gmres, int ksize, double tol,
+                                 int orth_mode, int *iters, double *residual_hist, int *calls) {
+  NSB_REQUIRE(Q && fop && jop && bq && bw, "nsb_newton_krylov: NULL argument");
+  NSB_REQUIRE(maxiter_newton >= 1 && maxiter_gmres >= 1, "nsb_newton_krylov: bad iteration limits");
+  NSB_REQUIRE(cf != cdq && !(bq == bw && (cq == cf || cq == cdq)), "nsb_newton_krylov: q, f and dq must be distinct");
+  int ncalls = 0, it = 0;
+  NSB_CHECK(nsb_vec_zero(bw, cf));                                              // :53
+  NSB_CHECK(nsb_vec_zero(bw, cdq));
+  for (it = 1; it <= maxiter_newton; ++it) {                                    // :59
+    NSB_CHECK(nsb_op_apply(fop, bq, cq, bw, cf));                               // :102
+    double residual = 0.0;
+    NSB_CHECK(nsb_vec_dot(bw, cf, bw, cf, &residual));                          // :107
+    if (residual_hist) residual_hist[it - 1] = residual;
+    if (residual < tol) break;                                                  // :117
+    int c = 0;
+    NSB_CHECK(nsb_ts_gmres(Q, jop, bw, cf, bw, cdq, maxiter_gmres, ksize, tol, orth_mode, &c, nullptr, nullptr));  // :125
+    ncalls += c;
+    NSB_CHECK(nsb_vec_sub2(bq, cq, bw, cdq));                                   // :130
+  }
+  if (iters) *iters = it > maxiter_newton ? maxiter_newton : it;
+  if (calls) *calls = ncalls;
+  return NSB_OK;
+}

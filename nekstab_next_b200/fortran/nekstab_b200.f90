@@ -42,7 +42,7 @@ module nekstab_b200
    public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
    public :: nsb_vec_zero, nsb_vec_copy, nsb_vec_scal, nsb_vec_axpby, nsb_vec_dot   ! for nekstab_b200_lightkrylov
    public :: arnoldi_factorization_d, schur_condensation_d, krylov_schur_d, ts_gmres_d, eigs_d, svds_d
-   public :: nsb_ritz_vector
+   public :: nsb_ritz_vector, nsb_newton_krylov
 
    interface
       function nsb_last_error() bind(C, name='nsb_last_error') result(msg)
@@ -236,6 +236,16 @@ module nekstab_b200
          real(c_double) :: H(ldh, *), residual(*)
          complex(c_double_complex) :: vals(*), vecs(k_dim, *)
          integer(c_int) :: kused, nconv, ierr
+      end function
+      function nsb_newton_krylov(Q, fop, jop, bq, cq, bw, cf, cdq, maxiter_newton, maxiter_gmres, ksize, tol, mode, &
+                                 iters, hist, calls) bind(C, name='nsb_newton_krylov') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: Q, fop, jop, bq, bw
+         integer(c_int), value :: cq, cf, cdq, maxiter_newton, maxiter_gmres, ksize, mode
+         real(c_double), value :: tol
+         integer(c_int) :: iters, calls
+         real(c_double) :: hist(*)
+         integer(c_int) :: ierr
       end function
       function nsb_ritz_vector(Q, k, y, bout, cre, cim, normalize, alpha_re, alpha_im) &
          bind(C, name='nsb_ritz_vector') result(ierr)

@@ -335,6 +335,27 @@ def ts_gmres(ctx, matvec, rhs: KVec, maxiter: int, ksize: int, tol: float):
 
 
 # ----------------------------------------------------------------------------
+# Newton-Krylov fixed-point iteration  (core/newton_krylov.f90:1-168)
+# ----------------------------------------------------------------------------
+def newton_krylov(ctx, forward_map, jacobian_for, q: KVec, maxiter_newton: int, maxiter_gmres: int, ksize: int,
+                  tol: float):
+    """core/newton_krylov.f90:52-133: f = F(q) (:102); residual = |f|^2 (:107); stop when residual < tol (:117);
+    dq = ts_gmres(J, f) (:125); q -= dq (:130).  ``jacobian_for(q)`` returns the matvec of the linearisation
+    about q (prepare_linearized_solver, :71).  Returns (q, residual history, linear-solver calls)."""
+    hist, calls = [], 0
+    for _ in range(maxiter_newton):
+        f = forward_map(q)
+        residual = k_norm(ctx, f) ** 2
+        hist.append(residual)
+        if residual < tol:
+            break
+        dq, _, c = ts_gmres(ctx, jacobian_for(q), f, maxiter_gmres, ksize, tol)
+        calls += c
+        k_sub2(q, dq)
+    return q, hist, calls
+
+
+# ----------------------------------------------------------------------------
 # Seed noise  (core/utils.f90:297-359, 408-418)
 # ----------------------------------------------------------------------------
 def mth_rand(ix, iy, iz, ieg, xl, fc, if3d):

@@ -251,3 +251,48 @@ def test_ritz_vector_assembly(ctx):
             assert np.max(np.abs(got.f[f] - beta * ref.f[f])) <= 1e-12 * beta * max(nr, ni)
     # Re/Im parts together have unit norm
     assert abs(nb.k_norm(B[K + 1]) ** 2 + nb.k_norm(B[K + 2]) ** 2 - 1.0) <= 1e-12
+
+
+def test_newton_krylov_fixed_point(ctx):
+    """newton_krylov (core/newton_krylov.f90:1-168) with host callbacks for the nonlinear map F and its
+    linearisation (the reference's time-stepper on both sides): same Newton residual history as the oracle
+    restatement, quadratic convergence to the root."""
+    import nekstab_next_b200 as nb
+    n, ksize = 200, 30
+    rng = np.random.default_rng(2)
+    A = np.eye(n) + 0.3 * rng.standard_normal((n, n)) / np.sqrt(n)
+    b = rng.standard_normal(n)
+    w = rng.random(n) + 0.5
+    state = {}
+
+    def F(x):
+        return A @ x + 0.1 * x ** 3 - b
+
+    lay = nb.Layout(ctx, [n], [True])
+    lay.set_weight([w])
+    Q = nb.Basis(lay, ksize + 2)
+    Wk = nb.Basis(lay, 3)
+
+    def fcb(fields, t):
+        state['q'] = fields[0].copy()            # the host re-linearises about the q it is handed
+        return [F(fields[0])], t
+
+    def jcb(fields, t):
+        return [A @ fields[0] + 0.3 * state['q'] ** 2 * fields[0]], t
+
+    fop, jop = nb.host_operator(lay, fcb), nb.host_operator(lay, jcb)
+    x0 = rng.standard_normal(n)
+    Wk[0].upload([x0])
+    tol = 1e-20
+    hist, calls = nb.newton_krylov(Q, fop, jop, Wk[0], Wk[1], Wk[2], 20, 50, ksize, tol)
+    x = Wk[0].download()[0][0]
+    c = okr.Ctx(bm1s=w, in_dot=[True], time_in_dot=False)
+    qo, hist_o, calls_o = okr.newton_krylov(
+        c, lambda q: okr.KVec([F(q.f[0])], q.time),
+        lambda q0: (lambda v, J=A + 0.3 * np.diag(q0.f[0] ** 2): okr.KVec([J @ v.f[0]], v.time)),
+        okr.KVec([x0.copy()], 0.0), 20, 50, ksize, tol)
+    assert len(hist) == len(hist_o) and calls == calls_o
+    assert np.allclose(hist[:-1], hist_o[:-1], rtol=1e-6) and hist[-1] < tol
+    assert np.max(np.abs(x - qo.f[0])) <= 1e-9 and np.max(np.abs(F(x))) < 1e-9
+    assert len(hist) <= 8                                   # Newton, not a fixed-point crawl
+    fop.close(); jop.close()
