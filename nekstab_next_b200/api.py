@@ -16,12 +16,12 @@ Everything computes on the GPU through libnekstab_b200.so; there is no CPU fallb
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 
 from . import _capi
-from ._capi import check, c_double_p, c_i64_p, c_int_p, c_dpp
+from ._capi import check, c_double_p, c_i64_p, c_int_p
 
 ORTH_MGS2_REF, ORTH_CGS2, ORTH_DGKS = 0, 1, 2
 AXPBY_SKIP_TIME = 1
