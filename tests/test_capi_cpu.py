@@ -67,6 +67,28 @@ def test_library_is_sm100a_only(lib):
     assert archs == {'sm_100a'}, archs
 
 
+def test_sass_shows_tma_mbarrier_and_fp64_tensor_cores(lib):
+    """What the hot kernels claim to use is in the machine code: 2-D tensor TMA loads (fused orthogonalisation),
+    bulk TMA copies and mbarrier waits (axhelm ring), fp64 tensor-core MMAs (axhelm contraction)."""
+    from nekstab_next_b200 import _capi
+    sass = subprocess.run(['cuobjdump', '-sass', str(_capi.LIB_PATH)], capture_output=True, text=True).stdout
+    fn = None
+    seen = {}
+    for line in sass.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            fn = m.group(1)
+            continue
+        for op in ('UTMALDG', 'UBLKCP', 'DMMA', 'SYNCS.PHASECHK'):
+            if op in line:
+                seen.setdefault(op, set()).add(fn)
+    assert any('fused_tma_reg' in f for f in seen.get('UTMALDG', ()))
+    assert any('axhelm3d_dmma8' in f for f in seen.get('UBLKCP', ()))
+    assert any('axhelm3d_dmma8' in f for f in seen.get('DMMA', ()))
+    assert any('axhelm3d_dmma8' in f for f in seen.get('SYNCS.PHASECHK', ()))
+    assert 'HGMMA' not in sass and 'HMMA' not in sass          # no legacy / Hopper tensor paths
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
