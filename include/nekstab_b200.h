@@ -260,6 +260,10 @@ int nsb_sem_hmholtz_vec(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t b
  *   convect       : out(field f) (+)= scale * J^T [ (c_slot . grad_rst)(J in(field f)) ],
  *                   f = field0..field0+nf-1; the mass matrix and the Jacobian are inside c */
 int nsb_sem_dealias_setup(nsb_sem_t sem, int lxd);
+/* Host only: lxd Gauss-Legendre nodes / weights, the GLL(N) -> GL(lxd) interpolation matrix J[lxd][N+1] and the
+ * derivative matrix on the Gauss nodes Dg[lxd][lxd] (both row-major) that the kernels above use; any output
+ * may be NULL. */
+int nsb_dealias_matrices(int N, int lxd, double *zd, double *wd, double *J, double *Dg);
 int nsb_sem_set_convect(nsb_sem_t sem, int slot, nsb_basis_t b, int col, int field0);
 int nsb_sem_convect(nsb_sem_t sem, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
                     int field0, int nf, double scale, int accumulate);

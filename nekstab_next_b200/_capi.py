@@ -85,6 +85,7 @@ PROTOTYPES = {
                                   c_int_p, c_double_p]),
     'nsb_sem_hmholtz_vec': (C.c_int, [H, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                       C.c_int, c_int_p, c_double_p]),
+    'nsb_dealias_matrices': (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     'nsb_sem_dealias_setup': (C.c_int, [H, C.c_int]),
     'nsb_sem_set_convect': (C.c_int, [H, C.c_int, H, C.c_int, C.c_int]),
     'nsb_sem_convect': (C.c_int, [H, C.c_int, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),

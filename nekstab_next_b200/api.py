@@ -454,6 +454,14 @@ class LinearOperator:
             self.h = None
 
 
+def dealias_matrices(N: int, lxd: int):
+    """Host only: (zd, wd, J[lxd, N+1], Dg[lxd, lxd]) of the dealiased convection (Gauss-Legendre fine mesh)."""
+    zd, wd = np.zeros(lxd), np.zeros(lxd)
+    J, Dg = np.zeros((lxd, N + 1)), np.zeros((lxd, lxd))
+    check(_capi.load().nsb_dealias_matrices(int(N), int(lxd), _dp(zd), _dp(wd), _dp(J), _dp(Dg)))
+    return zd, wd, J, Dg
+
+
 def sem_operator(sem: Sem, nfields: int, alpha: float, beta: float, h1: float, h2: float,
                  conv=None) -> LinearOperator:
     """out = alpha*in + beta * binvm1*mask*dssum(h1 A in + h2 B in [+ B (c.grad) in])."""

@@ -567,6 +567,25 @@ int convect_t(nsb_sem_t S, const double *u, double *out, int64_t fsi, int64_t fs
 
 }  // namespace
 
+// Host only (no CUDA): the small matrices of the dealiasing operators, for checking them without a device.
+extern "C" int nsb_dealias_matrices(int N, int lxd, double *zd, double *wd, double *J, double *Dg) {
+  NSB_REQUIRE(N >= 1 && N <= 31 && lxd >= 1 && lxd <= 64, "nsb_dealias_matrices: N=%d, lxd=%d out of range", N, lxd);
+  std::vector<double> zg(N + 1), z, w;
+  NSB_CHECK(nsb_gll(N, zg.data(), nullptr, nullptr));
+  gauss_legendre(lxd, z, w);
+  if (zd) memcpy(zd, z.data(), sizeof(double) * lxd);
+  if (wd) memcpy(wd, w.data(), sizeof(double) * lxd);
+  if (J) {
+    const std::vector<double> Jm = interp_matrix(zg, z);      // [lxd][N+1], row-major
+    memcpy(J, Jm.data(), sizeof(double) * Jm.size());
+  }
+  if (Dg) {
+    const std::vector<double> D = deriv_matrix(z);            // [lxd][lxd], row-major
+    memcpy(Dg, D.data(), sizeof(double) * D.size());
+  }
+  return NSB_OK;
+}
+
 extern "C" int nsb_sem_dealias_setup(nsb_sem_t S, int lxd) {
   NSB_REQUIRE(S, "nsb_sem_dealias_setup: NULL");
   if (lxd <= 0) lxd = (S->dim == 3 && S->lx == 5) ? 8 : 3 * S->lx / 2;

@@ -284,7 +284,8 @@ module nekstab_b200
 
    !> Device-side operators, dense mirrors and stand-alone kernels (same header, include/nekstab_b200.h).
    !> Not bound here because they serve the C / Python test and bench harness only: nsb_prof_*, nsb_profiler_*,
-   !> nsb_timer_*, nsb_flush_l2, nsb_launch_count, nsb_stream, nsb_rank, nsb_version, nsb_gll, nsb_host_alloc /
+   !> nsb_timer_*, nsb_flush_l2, nsb_launch_count, nsb_stream, nsb_rank, nsb_version, nsb_gll, nsb_dealias_matrices,
+   !> nsb_host_alloc /
    !> nsb_host_free, nsb_host_gs_plan, nsb_host_exchange_plan, nsb_allreduce_host, nsb_orthonormalize_async,
    !> nsb_p2p_enabled, nsb_basis_ncols, nsb_basis_col_ptr, nsb_layout_info, nsb_layout_destroy, nsb_sem_get,
    !> nsb_sem_npts.

@@ -114,6 +114,17 @@ def test_gll_matches_oracle(lib):
         assert np.max(np.abs(D - osem.dgll(n))) < 1e-12
 
 
+def test_dealias_matrices_match_oracle(lib):
+    import nekstab_next_b200 as nb
+    for N, lxd in ((7, 12), (5, 9), (4, 8), (3, 6), (7, 10)):
+        zd, wd, J, Dg = nb.dealias_matrices(N, lxd)
+        z2, w2 = osem.gl(lxd)
+        assert np.max(np.abs(zd - z2)) < 1e-15 and np.max(np.abs(wd - w2)) < 1e-15
+        zg, _ = osem.gll(N)
+        assert np.max(np.abs(J - osem.interp_matrix(zg, z2))) < 1e-14
+        assert np.max(np.abs(Dg - osem.deriv_matrix(z2))) < 1e-11
+
+
 def test_lapack_wrapper_mirrors(lib):
     import nekstab_next_b200 as nb
     rng = np.random.default_rng(3)
