@@ -43,6 +43,20 @@ def write_spectrum(path, vals: np.ndarray, residual: np.ndarray):
             f.write(fortran_e(v.real) + fortran_e(v.imag) + fortran_e(float(r)) + '\n')
 
 
+def log_transform(x):
+    """core/eigensolvers.f90:860-869: log(x); a real argument gives a real result (the imaginary part of
+    log of a negative real, pi, is dropped exactly as the reference does)."""
+    x = np.asarray(x, dtype=np.complex128)
+    y = np.log(x)
+    return np.where(x.imag == 0, y.real + 0j, y)
+
+
+def write_ns_spectrum(path, vals: np.ndarray, residual: np.ndarray, speriod: float):
+    """The log-transformed spectrum of the linearised operator (unit 20 of outpost_ks,
+    core/eigensolvers.f90:547-548; core/linear_stab.f90:72): log(lambda) / T per Ritz value."""
+    write_spectrum(path, log_transform(vals) / speriod, residual)
+
+
 def read_spectrum(path):
     a = np.loadtxt(path, ndmin=2)
     return a[:, 0] + 1j * a[:, 1], a[:, 2]

@@ -81,3 +81,20 @@ def test_reads_reference_field_files_and_rewrites_them_identically(tmp_path):
     ck.write_fld(out, dict(x=f['x'], u=f['u'], p=f['p']), f['nx'], f['ny'], f['nz'], time=f['time'], istep=f['istep'],
                  elmap=f['elmap'])
     assert src.read_bytes() == out.read_bytes()               # header and payload bit-identical
+
+
+def test_log_transform_and_ns_spectrum(tmp_path):
+    """eigenvalue of the propagator -> growth rate / frequency of the linearised operator
+    (core/eigensolvers.f90:547-548, 860-869)."""
+    T = 2.5
+    mu = np.array([0.1 + 0.7j, 0.1 - 0.7j, -0.3 + 0j, 0.05 + 0j])
+    lam = np.exp(mu * T)
+    lam[2] = -abs(lam[2])                       # a negative real Ritz value: the reference keeps only log|x|
+    lt = ck.log_transform(lam)
+    assert np.allclose(lt[:2] / T, mu[:2]) and lt[3].imag == 0 and abs(lt[3].real / T - 0.05) < 1e-14
+    assert lt[2].imag == 0 and abs(lt[2].real - np.log(abs(lam[2]))) < 1e-14
+    p = tmp_path / 'Spectre_NSd.dat'
+    ck.write_ns_spectrum(p, lam, np.array([1e-8, 1e-8, 2e-3, 5e-7]), T)
+    v, r = ck.read_spectrum(p)
+    assert np.allclose(v[:2], mu[:2], atol=1e-6) and np.allclose(r, [1e-8, 1e-8, 2e-3, 5e-7])
+    assert all(len(line) == 46 for line in open(p))           # (3E15.7) + newline
