@@ -57,6 +57,18 @@ def write_ns_spectrum(path, vals: np.ndarray, residual: np.ndarray, speriod: flo
     write_spectrum(path, log_transform(vals) / speriod, residual)
 
 
+def write_singvals(path, sigma: np.ndarray, residual: np.ndarray):
+    """outpost_singvals (core/linear_stab.f90:313-329): two columns sigma, residual in (2E15.7)."""
+    with open(path, 'w') as f:
+        for v, r in zip(np.asarray(sigma, dtype=float), np.asarray(residual, dtype=float)):
+            f.write(fortran_e(float(v)) + fortran_e(float(r)) + '\n')
+
+
+def read_singvals(path):
+    a = np.loadtxt(path, ndmin=2)
+    return a[:, 0], a[:, 1]
+
+
 def read_spectrum(path):
     a = np.loadtxt(path, ndmin=2)
     return a[:, 0] + 1j * a[:, 1], a[:, 2]

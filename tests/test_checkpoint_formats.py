@@ -98,3 +98,15 @@ def test_log_transform_and_ns_spectrum(tmp_path):
     v, r = ck.read_spectrum(p)
     assert np.allclose(v[:2], mu[:2], atol=1e-6) and np.allclose(r, [1e-8, 1e-8, 2e-3, 5e-7])
     assert all(len(line) == 46 for line in open(p))           # (3E15.7) + newline
+
+
+def test_singvals_roundtrip(tmp_path):
+    """Spectrum_S*.dat of transient_growth_analysis: sigma**2 and residual, (2E15.7) (core/linear_stab.f90:113-114)."""
+    sig = np.array([63151.984, 12.5, 0.75]) ** 0.5
+    res = np.array([1e-9, 3e-7, 1e-2])
+    p = tmp_path / 'Spectrum_Sp.dat'
+    ck.write_singvals(p, sig ** 2, res)
+    s2, r2 = ck.read_singvals(p)
+    assert np.allclose(s2, sig ** 2, rtol=1e-7) and np.allclose(r2, res, rtol=1e-7)
+    lines = open(p).read().splitlines()
+    assert all(len(ln) == 30 for ln in lines) and lines[0].split()[0] == '0.6315198E+05'
