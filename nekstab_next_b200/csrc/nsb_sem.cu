@@ -597,12 +597,19 @@ __device__ __forceinline__ void dmma884(double2 &d, double a, double b) {
 template <int NF, bool CONV>
 struct Dmma8Cfg {
   static constexpr int NARR = 6 + 2 + (CONV ? 3 : 0) + NF;      // arrays per buffer: G1..G6, bm1, bmask, [C], u
-  static constexpr int NG = NF == 3 ? 3 : (NF == 2 ? 4 : 5);    // warp groups
   static constexpr int PLANE = 80;                              // doubles per conversion plane
-  static constexpr size_t fixed = sizeof(double) * ((size_t)NF * NG * 2 * PLANE + 128) + 256;
-  static constexpr int fit = (int)((227 * 1024 - fixed) / (sizeof(double) * NARR * 512 + 16));
+  static constexpr size_t per_buf = sizeof(double) * NARR * 512 + 16;
+  static constexpr size_t fixed_for(int ng) { return sizeof(double) * ((size_t)NF * ng * 2 * PLANE + 128) + 256; }
+  static constexpr int fit_for(int ng) { return (int)((227 * 1024 - fixed_for(ng)) / per_buf); }
+  // Warp groups: as many as pay off, but never more than buffers -- with NG > NBUF a group waits for a
+  // buffer several uses ahead and the parity waits become ambiguous (tests/test_ring_protocol.py).
+  static constexpr int NG0 = NF == 3 ? 3 : (NF == 2 ? 4 : 5);
+  static constexpr int NG = fit_for(NG0) < NG0 ? fit_for(NG0) : NG0;
+  static constexpr size_t fixed = fixed_for(NG);
+  static constexpr int fit = fit_for(NG);
   static constexpr int NBUF = fit < NG + 1 ? fit : NG + 1;
-  static constexpr size_t smem = fixed + (size_t)NBUF * (sizeof(double) * NARR * 512 + 16);
+  static constexpr size_t smem = fixed + (size_t)NBUF * per_buf;
+  static_assert(NG >= 1 && NBUF >= NG, "every warp group needs a buffer of its own");
 };
 
 template <int NF, bool CONV, int EPI, int NBUF>

@@ -56,7 +56,8 @@ def simulate(NG, NBUF, nit, seed, guarded):
     return 'deadlock'
 
 
-@pytest.mark.parametrize('NG,NBUF', [(3, 4), (4, 5), (5, 6), (3, 3), (5, 5)])
+# (warp groups, buffers) of every instantiation the library ships: NF = 3 / 2 / 1 without and with convection
+@pytest.mark.parametrize('NG,NBUF', [(3, 4), (4, 5), (5, 6), (3, 3), (4, 4), (5, 5)])
 def test_shipped_protocol_never_aliases(NG, NBUF):
     for seed in range(60):
         assert simulate(NG, NBUF, 90, seed, guarded=True) == 'ok'
@@ -67,3 +68,9 @@ def test_parity_only_protocol_aliases_when_buffers_outnumber_groups():
     assert any(r != 'ok' for r in bad)
     # one buffer per group (the same warp owns consecutive uses) is safe without the guard
     assert all(simulate(3, 3, 90, seed, guarded=False) == 'ok' for seed in range(20))
+
+
+def test_more_groups_than_buffers_is_unsafe_even_with_the_guard():
+    """Why Dmma8Cfg caps the warp groups at the number of buffers that fit (the single-component kernel with
+    convection fits 4 buffers, so it runs 4 groups, not 5)."""
+    assert any(simulate(5, 4, 90, seed, guarded=True) != 'ok' for seed in range(20))
