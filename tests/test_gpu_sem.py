@@ -64,6 +64,21 @@ def test_fused_operator(ctx, conv, nel, N):
     assert op.count() == 1
 
 
+@pytest.mark.parametrize('nf', [1, 2])
+def test_fused_operator_one_and_two_components_with_convection(ctx, nf):
+    """The N = 7 tensor-core kernel has one instantiation per component count; these two (with the convective
+    term staged in the ring) are not reached by the three-component cases above."""
+    P = BoxProblem(nel=(3, 2, 2), N=7, deform=0.05, nfields=nf, conv=True, seed=4)
+    lay, B, S, op = P.gpu(ctx, 3)
+    q = P.random_kvec()
+    upload(B[0], q)
+    op.matvec(B[0], B[1])
+    ref = P.omatvec(q)
+    got = download(B[1])
+    for a, b in zip(got.f, ref.f):
+        assert relerr(a, b.ravel()) <= TOL
+
+
 @pytest.mark.parametrize('name', ['cyl', 'bfs'])
 def test_reference_meshes(ctx, name):
     """Config 1: the reference's own curved 2-D meshes (examples/cylinder, examples/back_fstep)."""
