@@ -56,3 +56,42 @@ def test_two_slots_suffice():
 def test_one_slot_is_not_enough():
     outcomes = [run(4, 12, 1, seed) for seed in range(40)]
     assert any(o != 'ok' for o in outcomes)
+
+
+def run_halo(P, nex, nslots, seed):
+    """Pairwise halo exchange of a 1-D chain of ranks (nsb_comm.cu, halo_exchange_p2p): per exchange `seq` a rank
+    packs its interface data into slot seq % nslots of each neighbour's mailbox, raises the matching flag there,
+    then -- one neighbour after the other -- waits for that neighbour's flag in its own mailbox and reads.
+    No global synchronisation between exchanges (finish_assembled runs two dssums back to back)."""
+    rnd = random.Random(seed)
+    nb = [[q for q in (r - 1, r + 1) if 0 <= q < P] for r in range(P)]
+    data = [[[None] * P for _ in range(nslots)] for _ in range(P)]
+    flag = [[[0] * P for _ in range(nslots)] for _ in range(P)]
+    pc = [[1, 0, 0] for _ in range(P)]          # seq, phase (0 pack, 1 flags, 2 wait+read), neighbour index
+    for _ in range(400000):
+        live = [r for r in range(P) if pc[r][0] <= nex]
+        if not live:
+            return 'ok'
+        r = rnd.choice(live)
+        seq, ph, i = pc[r]
+        s = seq % nslots
+        if ph == 0:
+            data[nb[r][i]][s][r] = seq
+            pc[r] = [seq, 0, i + 1] if i + 1 < len(nb[r]) else [seq, 1, 0]
+        elif ph == 1:
+            flag[nb[r][i]][s][r] = seq
+            pc[r] = [seq, 1, i + 1] if i + 1 < len(nb[r]) else [seq, 2, 0]
+        else:
+            q = nb[r][i]
+            if flag[r][s][q] == seq:
+                if data[r][s][q] != seq:
+                    return f'rank {r} read exchange {data[r][s][q]} from {q} while expecting {seq}'
+                pc[r] = [seq, 2, i + 1] if i + 1 < len(nb[r]) else [seq + 1, 0, 0]
+    return 'deadlock'
+
+
+def test_halo_exchange_two_slots():
+    for P in (2, 3, 5, 8):
+        for seed in range(30):
+            assert run_halo(P, 10, 2, seed) == 'ok'
+    assert any(run_halo(4, 10, 1, seed) != 'ok' for seed in range(30))
