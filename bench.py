@@ -52,6 +52,8 @@ def parse():
     ap.add_argument('--conv', action='store_true', help='add the Taylor-Green convective term (M2)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-dgks', action='store_true')
+    ap.add_argument('--no-single-rank-check', action='store_true')
     ap.add_argument('--cpu-nelx', type=int, default=16, help='elements per direction of the CPU sample')
     return ap.parse_args()
 
@@ -120,17 +122,17 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: C restatement of the reference path on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_arnoldi_rate(a, sample_ks=(10, 50, 90), verbose=False):
-    """Arnoldi steps/s of the reference algorithm (MGS2 sweeps + ax/dssum matvec) on the host cores.
+_CPU_SETUP = {}
 
-    Sample: Arnoldi steps at Krylov index k in sample_ks on a cpu_nelx^3 mesh (same N, ncomp);
-    the step time is linear in k (MGS2 reads 20 k n words) and proportional to the number of
-    elements, so the mean over k = 1..k_dim on the full mesh is the least-squares line evaluated at
-    (k_dim+1)/2, scaled by E / E_sample.
-    """
+
+def cpu_setup(a, nes, kmax):
+    """Mesh, geometry, gather-scatter lists and kmax+2 distinct vectors of the CPU sample (cached per size)."""
+    key = (nes, a.order, a.ncomp, a.deform)
+    st = _CPU_SETUP.get(key)
+    if st is not None and st['kmax'] >= kmax:
+        return st
     from oracle import cref, sem as osem
-    nes, N, nc = a.cpu_nelx, a.order, a.ncomp
-    lx = N + 1
+    N, nc = a.order, a.ncomp
     x, y, z, glo = osem.box_mesh(nes, nes, nes, N, deform=a.deform)
     geo = osem.geometry(N, x, y, z)
     g = np.ascontiguousarray(geo['g'])
@@ -139,30 +141,72 @@ def cpu_arnoldi_rate(a, sample_ks=(10, 50, 90), verbose=False):
     binv = 1.0 / osem.dssum(bm1, glo)
     x0, y0, z0, _ = osem.box_mesh(nes, nes, nes, N)
     mask = osem.boundary_mask_box(None, x0, y0, z0)
-    D = osem.dgll(N)
     npts = x.size
     n = nc * npts
-    kmax = max(sample_ks)
+    del x, y, z, x0, y0, z0, geo, glo
     Q = np.empty((kmax + 2, n))
-    rng = np.random.default_rng(0)
-    base = rng.standard_normal(1 << 16)
-    for i in range(kmax + 2):                      # timing sample: content only has to be finite
+    base = np.random.default_rng(0).standard_normal(1 << 16)
+    for i in range(kmax + 2):                      # timing sample: content only has to be finite and distinct
         Q[i] = np.resize(np.roll(base, i), n) * 1e-3
-    H = np.zeros((kmax + 2, kmax + 1), order='F')
-    ts = []
-    for k in sample_ks:
-        t0 = time.perf_counter()
-        cref.arnoldi(Q, H, k - 1, k - 1, bm1, g, bm1, binv, mask, D, lx, nes ** 3, nc, off, idx, 1.0, 0.1,
-                     1.0, -1e-4)
-        ts.append(time.perf_counter() - t0)
+    st = dict(kmax=kmax, Q=Q, g=g, bm1=bm1, binv=binv, mask=mask, D=osem.dgll(N), off=off, idx=idx, nes=nes,
+              H=np.zeros((kmax + 2, kmax + 1), order='F'))
+    _CPU_SETUP.clear()
+    _CPU_SETUP[key] = st
+    return st
+
+
+def cpu_step_seconds(a, st, k):
+    """One Arnoldi step of the reference algorithm at Krylov index k: matvec (ax + dssum + mask + binvm1) and the
+    two MGS sweeps of update_hessenberg_matrix over k vectors (core/krylov_decomposition.f90:155-180)."""
+    from oracle import cref
+    t0 = time.perf_counter()
+    cref.arnoldi(st['Q'], st['H'], k - 1, k - 1, st['bm1'], st['g'], st['bm1'], st['binv'], st['mask'], st['D'],
+                 a.order + 1, st['nes'] ** 3, a.ncomp, st['off'], st['idx'], 1.0, 0.1, 1.0, -1e-4)
+    return time.perf_counter() - t0
+
+
+def cpu_arnoldi_rate(a, sample_ks=(10, 40, 70), verbose=False):
+    """Arnoldi steps/s of the reference algorithm (MGS2 sweeps + ax/dssum matvec) on the host cores.
+
+    Preferred sample: Arnoldi steps at Krylov index k in sample_ks on the FULL mesh of the workload (the
+    configuration itself, nothing scaled in the element count); the step time is linear in k (MGS2 reads
+    20 k n words), so the mean over k = 1..k_dim is the least-squares line evaluated at (k_dim+1)/2.
+    When the host lacks the memory for max(k)+2 full-size vectors, the k-fit runs on a cpu_nelx^3 mesh and the
+    element scaling is MEASURED with one full-mesh step at k = min(sample_ks) instead of assumed.
+    """
+    from oracle import cref
+    N, nc = a.order, a.ncomp
+    n_full = nc * a.nelx ** 3 * (N + 1) ** 3
+    kmax = max(sample_ks)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        avail = 0
+    need = lambda k, n: 8.0 * n * (k + 2 + 14) * 1.25          # vectors + mesh arrays + transient copies
+    if avail > need(kmax, n_full) + (8 << 30):
+        st = cpu_setup(a, a.nelx, kmax)
+        ts = [cpu_step_seconds(a, st, k) for k in sample_ks]
+        scale, how = 1.0, (f'Arnoldi steps at k={list(sample_ks)} on the full mesh box{a.nelx}^3 '
+                           f'(E={a.nelx ** 3}, N={N}, ncomp={nc}); linear-in-k fit evaluated at k={(a.kdim + 1) / 2:g}')
+    else:
+        nes = a.cpu_nelx
+        st = cpu_setup(a, nes, kmax)
+        ts = [cpu_step_seconds(a, st, k) for k in sample_ks]
+        k0 = min(sample_ks)
+        t_small = ts[list(sample_ks).index(k0)]
+        st = None
+        stf = cpu_setup(a, a.nelx, k0)
+        t_full = cpu_step_seconds(a, stf, k0)
+        scale = t_full / t_small
+        how = (f'Arnoldi steps at k={list(sample_ks)} on box{nes}^3 (E={nes ** 3}, N={N}, ncomp={nc}); linear-in-k fit '
+               f'evaluated at k={(a.kdim + 1) / 2:g}; element scaling measured with one step at k={k0} on the full '
+               f'box{a.nelx}^3 mesh: x{scale:.2f} (element ratio {(a.nelx / nes) ** 3:g})')
     A = np.vstack([np.ones(len(sample_ks)), np.array(sample_ks, dtype=float)]).T
     coef, *_ = np.linalg.lstsq(A, np.array(ts), rcond=None)
-    mean_t = coef[0] + coef[1] * (a.kdim + 1) / 2.0
-    scale = (a.nelx / nes) ** 3
-    rate = 1.0 / (mean_t * scale)
-    info = dict(sample=f'Arnoldi steps at k={list(sample_ks)} on box{nes}^3 (E={nes ** 3}, N={N}, ncomp={nc}); '
-                       f'linear-in-k fit evaluated at k={(a.kdim + 1) / 2:g}, scaled x{scale:g} to E={a.nelx ** 3}',
-                step_seconds_sample=[float(t) for t in ts], cores=cref.num_threads(),
+    mean_t = (coef[0] + coef[1] * (a.kdim + 1) / 2.0) * scale
+    rate = 1.0 / mean_t
+    info = dict(sample=how, step_seconds_sample=[float(t) for t in ts], cores=cref.num_threads(),
                 host_cpus=os.cpu_count())
     return rate, info
 
@@ -178,7 +222,7 @@ def run_reference(a):
         cref.set_num_threads(os.cpu_count() or 1)
     rates, info = [], None
     for _ in range(max(1, a.warmup)):
-        cpu_arnoldi_rate(a, sample_ks=(10,))
+        cpu_arnoldi_rate(a, sample_ks=(10, 70))
     t0 = time.perf_counter()
     for _ in range(a.steps):
         r, info = cpu_arnoldi_rate(a)
@@ -189,7 +233,7 @@ def run_reference(a):
                 ms_per_step=1e3 * a.kdim / value, higher_is_better=True, scaling='strong', vs_baseline=None,
                 dtype='f64', data='synthetic', impl='reference',
                 config=dict(workload=workload_name(a), note='one bench step = one k_dim-step factorisation; '
-                            'CPU figure extrapolated from a bounded sample (see cpu_baseline.sample)'),
+                            'CPU figure = mean over k from a bounded sample of steps (see cpu_baseline.sample)'),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=info['cores'], kind='port',
                                   sample=info['sample'], host_cpus=info['host_cpus']),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -273,14 +317,17 @@ def run_native(a):
     lay.set_weight([bm1] * nc)
     Q = nb.Basis(lay, K + 1)
     conv = nb.mesh.taylor_green(m['x'], m['y'], m['z']) if a.conv else None
-    # seed: random, made C0 (dssum * vmult) and masked, unit norm
     rng = np.random.default_rng(1234 + rank)
-    Q[0].upload([rng.standard_normal(npts) for _ in range(nc)])
-    for f in range(nc):
-        sem.dssum(Q[0], f)
-        sem.col2(Q[0], f, 'vmult')
-        sem.col2(Q[0], f, 'mask')
-    nb.k_normalize(Q[0])
+
+    # seed: pseudo-random in the GLOBAL node id (continuous by construction, independent of the partition,
+    # so every N starts from the same vector), masked, unit norm
+    def set_seed(sem_, vec, glo):
+        vec.upload([nb.seed.hashed_field(glo, c) for c in range(nc)])
+        for f in range(nc):
+            sem_.col2(vec, f, 'mask')
+        nb.k_normalize(vec)
+
+    set_seed(sem, Q[0], m['glo'])
     # spectral radius of L = B^-1 mask QQ^T (A + 0.1 B) by power iteration -> M = I - L / (1.05 rho)
     Lop = nb.sem_operator(sem, nc, 0.0, 1.0, 1.0, 0.1, conv=conv)
     nb.k_copy(Q[1], Q[0])
@@ -290,30 +337,96 @@ def run_native(a):
         rho = nb.k_normalize(Q[2])
         nb.k_copy(Q[1], Q[2])
     Lop.close()
-    op = nb.sem_operator(sem, nc, 1.0, -1.0 / (1.05 * rho), 1.0, 0.1, conv=conv)
+    beta_op = -1.0 / (1.05 * rho)
+    op = nb.sem_operator(sem, nc, 1.0, beta_op, 1.0, 0.1, conv=conv)
+    glo_local = m['glo']
     del m
     H = np.zeros((K + 1, K), order='F')
 
-    def factorise():
-        nb.arnoldi_factorization(Q, H, 1, K, K, op, nb.ORTH_CGS2)
+    def factorise(mode=nb.ORTH_CGS2):
+        nb.arnoldi_factorization(Q, H, 1, K, K, op, mode)
 
-    for _ in range(a.warmup):
-        factorise()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    l0 = ctx.launch_count()
-    ctx.timer_start()
-    for _ in range(a.steps):
-        factorise()
-    ms = ctx.timer_stop()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = sumall(float(ctx.launch_count() - l0))
-    ms = maxall(ms)
+    def timed(mode, warm, steps, sample_clocks=False):
+        for _ in range(warm):
+            factorise(mode)
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        for _ in range(steps):
+            factorise(mode)
+        t = ctx.timer_stop()
+        barrier()
+        clk = sampler.stop() if (rank == 0 and sample_clocks) else None
+        return maxall(t), sumall(float(ctx.launch_count() - l0)), clk
+
+    ms, launches, clocks = timed(nb.ORTH_CGS2, a.warmup, a.steps, sample_clocks=True)
     value = K * a.steps / (ms * 1e-3)
     ndof = sumall(float(nc * npts))
+
+    # ---- parity block: computed on the factorisation the timed region just produced ----------------
+    #   orth        max |V^T B V - I| over all k_dim+1 columns (the reference's orthonormality.dat check,
+    #               core/eigensolvers.f90:335-345; north-star bound 1e-10)
+    #   arnoldi_res ||M q_j - V h_j|| / ||h_j|| for j in {0, k_dim/2, k_dim-1}
+    #   H_replicated  max over ranks of |H - H_rank0| (must be exactly 0: rank-ordered all-reduce sums)
+    #   H8_vs_single_rank  (N > 1) relative difference of H(:, 0:8) against a 1-rank run of the same seed on
+    #               the whole mesh, run on rank 0's GPU
+    parity = {}
+    G = Q.gram(K + 1)
+    parity['orth'] = float(np.max(np.abs(G - np.eye(K + 1))))
+    Wk = nb.Basis(lay, 2)
+    res = []
+    for j in (0, K // 2, K - 1):
+        op.matvec(Q[j], Wk[0])
+        nb.k_matmul(Wk[1], Q, H[:j + 2, j], j + 2)
+        nb.k_sub2(Wk[0], Wk[1])
+        res.append(nb.k_norm(Wk[0]) / float(np.linalg.norm(H[:j + 2, j])))
+    parity['arnoldi_res'] = [float(r) for r in res]
+    Wk.close()
+    if world > 1:
+        Hall = [None] * world
+        dist.all_gather_object(Hall, H)
+        parity['H_replicated'] = max(float(np.max(np.abs(h - Hall[0]))) for h in Hall)
+    else:
+        parity['H_replicated'] = 0.0
+    if world > 1 and not a.no_single_rank_check:
+        k8 = min(8, K)
+        if rank == 0:
+            c1 = nb.Context(device=local)
+            m1 = nb.mesh.box_mesh(a.nelx, a.nelx, a.nelx, N, deform=a.deform)
+            s1 = nb.Sem(c1, N, m1['x'], m1['y'], m1['z'], mask=m1['mask'], glo_num=m1['glo'])
+            l1 = nb.Layout(c1, [s1.npts] * nc, [True] * nc)
+            l1.set_weight([s1.get('bm1')] * nc)
+            Q1 = nb.Basis(l1, k8 + 1)
+            set_seed(s1, Q1[0], m1['glo'])
+            conv1 = nb.mesh.taylor_green(m1['x'], m1['y'], m1['z']) if a.conv else None
+            o1 = nb.sem_operator(s1, nc, 1.0, beta_op, 1.0, 0.1, conv=conv1)
+            H1 = np.zeros((k8 + 1, k8), order='F')
+            nb.arnoldi_factorization(Q1, H1, 1, k8, k8, o1, nb.ORTH_CGS2)
+            parity['H8_vs_single_rank'] = float(np.max(np.abs(H1 - H[:k8 + 1, :k8])) / np.max(np.abs(H1)))
+            for o in (o1, Q1, l1, s1, c1):
+                o.close()
+            del m1
+        barrier()
+    parity['bounds'] = dict(orth=1e-10, arnoldi_res=1e-10, H_replicated=0.0, H8_vs_single_rank=1e-10)
+    parity['ok'] = bool(parity['orth'] < 1e-10 and max(parity['arnoldi_res']) < 1e-10 and
+                        parity['H_replicated'] == 0.0 and parity.get('H8_vs_single_rank', 0.0) < 1e-10)
+
+    # ---- DGKS: the same factorisation with the second projection decided on the device -------------
+    dgks = None
+    if not a.no_dgks:
+        set_seed(sem, Q[0], glo_local)
+        d_ms, _, _ = timed(nb.ORTH_DGKS, 1, a.steps)
+        passes = nb.arnoldi_passes(Q, 1, K, nb.ORTH_DGKS)
+        Gd = Q.gram(K + 1)
+        dgks = dict(value_dgks=K * a.steps / (d_ms * 1e-3), ms_per_arnoldi_step=d_ms / a.steps / K,
+                    passes_mean=float(np.mean(passes)), orth=float(np.max(np.abs(Gd - np.eye(K + 1)))),
+                    note='second projection only where |w\'| < |w|/sqrt 2 (device-side predicate); the headline '
+                         'value keeps the reference\'s unconditional second pass')
+        set_seed(sem, Q[0], glo_local)
+        factorise()                                  # basis of the headline mode again for what follows
 
     # ---- matvec alone (GDOF/s) ---------------------------------------------------------------
     barrier()
@@ -330,8 +443,16 @@ def run_native(a):
     ctx.timer_start()
     factorise()
     prof_ms = ctx.timer_stop()
+    # BLAS-1 set of the nek_dvector type (K4): not part of the fused Arnoldi step, timed here for the table
+    Wb = nb.Basis(lay, 3)
+    nb.k_copy(Wb[0], Q[1]); nb.k_copy(Wb[1], Q[2])
+    for _ in range(5):
+        Wb[0].axpby(0.5, Wb[1], 0.25, skip_time=False)
+        nb.k_sub3(Wb[2], Wb[0], Wb[1])
+        Wb[2].scal(1.0001)
     rep = ctx.prof_report()
     ctx.prof_enable(False)
+    Wb.close()
     peak, peak_src = peaks()
     tot = sum(v['ms'] for v in rep.values())
     kernels = {}
@@ -339,15 +460,23 @@ def run_native(a):
         gbs = v['bytes'] / (v['ms'] * 1e-3) / 1e9 if v['ms'] > 0 else 0.0
         kernels[name] = dict(ms=round(v['ms'], 3), launches=v['launches'], share=round(v['ms'] / tot, 4),
                              achieved_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
-    dom = max(rep, key=lambda n: rep[n]['ms'])
-    # DRAM traffic / algorithmic bytes measured once with `ncu --set full` at k = 100
-    # (profiles/ncu_r01_final_kernels_k100.md): the sweeps move exactly their algorithmic bytes
-    ncu_ratio = dict(multidot=1.000, fused_update_dot=1.000, update=0.999)
-    traffic = (rep[dom]['bytes'] / rep[dom]['launches'] * ncu_ratio[dom]) if dom in ncu_ratio else None
+    dom = max((n for n in rep if n != 'blas1'), key=lambda n: rep[n]['ms'])
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    # capture, kept as a committed file (profiles/ncu_traffic.json: per kernel the measured bytes of the captured
+    # launch and its algorithmic bytes); scaled to this run's mean algorithmic bytes per launch.  null when the
+    # file has no entry for the kernel -- never a hard-coded ratio.
+    traffic, traffic_src = None, None
+    tf = ROOT / 'profiles' / 'ncu_traffic.json'
+    if tf.exists():
+        ent = json.loads(tf.read_text()).get(dom)
+        if ent and ent.get('algorithmic_bytes'):
+            ratio = ent['dram_bytes'] / ent['algorithmic_bytes']
+            traffic = rep[dom]['bytes'] / rep[dom]['launches'] * ratio
+            traffic_src = (f"{ent.get('source', 'profiles/ncu_traffic.json')}: dram read+write {ent['dram_bytes']:.4g} B "
+                           f"for {ent['algorithmic_bytes']:.4g} algorithmic B at k={ent.get('k')} (ratio {ratio:.3f}), "
+                           'applied to the mean algorithmic bytes per launch of this run')
     roofline = dict(bound='hbm', kernel=dom, achieved=kernels[dom]['achieved_gbs'], peak=peak, unit='GB/s',
-                    frac=kernels[dom]['frac'], traffic=traffic,
-                    traffic_source='ncu dram read+write / algorithmic = %.3f at k=100, applied to the mean '
-                                   'algorithmic bytes per launch' % ncu_ratio[dom] if traffic else None,
+                    frac=kernels[dom]['frac'], traffic=traffic, traffic_source=traffic_src,
                     peak_source=peak_src,
                     avg_launch_ms=round(rep[dom]['ms'] / rep[dom]['launches'], 4),
                     algorithmic_bytes_per_launch=rep[dom]['bytes'] / rep[dom]['launches'],
@@ -402,7 +531,13 @@ def run_native(a):
                                 collectives=('NVLink peer-memory kernels (one-shot all-reduce, halo stores)' if p2p
                                              else 'NCCL' if world > 1 else 'none')),
                     arnoldi_ms_per_step=ms / a.steps / K, matvec_gdof_per_s=matvec_gdofs,
-                    matvec_ms=mv_ms, roofline=roofline, clocks=clocks, gpu_launches=int(launches))
+                    matvec_ms=mv_ms, roofline=roofline, clocks=clocks, gpu_launches=int(launches),
+                    parity=parity, build_id=nb.build_id(),
+                    build_mode='in-tree nvcc -gencode arch=compute_100a,code=sm_100a; content hash of csrc/ + '
+                               'include/ embedded in the binary (nsb_build_id) and compared by build.stale()',
+                    launch_mode=os.environ.get('NSB_GRAPH', '1') != '0' and 'one CUDA graph per Arnoldi step' or 'plain launches')
+        if dgks:
+            line.update(value_dgks=dgks['value_dgks'], passes_mean=dgks['passes_mean'], dgks=dgks)
         if e2e:
             line['e2e'] = e2e
     if rank == 0 and world == 1 and not a.no_cpu:

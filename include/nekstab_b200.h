@@ -47,6 +47,9 @@ typedef struct nsb_op_s *nsb_op_t;
 
 const char *nsb_last_error(void);
 int nsb_version(void);
+/* Hash of the sources this binary was compiled from (sha256 over csrc/ and this header, first 16 hex digits),
+ * so that a measured number can be tied to a source tree: bench.py prints it, build.py compares it. */
+const char *nsb_build_id(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Context: one per process / MPI rank / GPU.  (Reference: the Nek rank, nid/np in SIZE/PARALLEL;
@@ -160,14 +163,18 @@ int nsb_vec_normalize(nsb_basis_t b, int col, double *alpha);
  *   NSB_ORTH_CGS2      fused multi-column: h1 = V^T W w ; {w -= V h1 ; h2 = V^T W w} ; w -= V h2
  *                      (same two-pass semantics, H = h1 + h2; V crosses HBM three times and there
  *                      are 3 all-reduces per step)
- *   NSB_ORTH_DGKS      as CGS2, second pass only if ||w'|| < eta ||w|| (eta = 1/sqrt 2)
+ *   NSB_ORTH_DGKS      as CGS2, second pass only if ||w'|| < eta ||w|| (eta = 1/sqrt 2).  The test is a
+ *                      device-side predicate: the last CTA of the fused sweep compares the two norms and
+ *                      the third sweep exits at once when the flag says so -- no host round trip, V
+ *                      crosses HBM twice instead of three times in the common case
  * ------------------------------------------------------------------------------------------- */
 #define NSB_ORTH_MGS2_REF 0
 #define NSB_ORTH_CGS2 1
 #define NSB_ORTH_DGKS 2
 int nsb_orthonormalize(nsb_basis_t b, int k, int col_w, int mode, double *h, int *passes);
 /* Asynchronous variant: h stays on the device until nsb_sync / the next synchronising call;
- * h_pinned must be memory from nsb_host_alloc.  Used by the device-resident Arnoldi loop. */
+ * h_pinned must be memory from nsb_host_alloc with room for k + 2 doubles (h[0..k], and for NSB_ORTH_DGKS
+ * the number of passes taken in h_pinned[k+1]).  Used by the device-resident Arnoldi loop. */
 int nsb_orthonormalize_async(nsb_basis_t b, int k, int col_w, int mode, double *h_pinned);
 int nsb_host_alloc(void **ptr, int64_t bytes);
 int nsb_host_free(void *ptr);
@@ -319,6 +326,9 @@ int nsb_op_count(nsb_op_t op, int64_t *napply);
  * device-resident (no host synchronisation until the end). */
 int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int orth_mode, double *H,
                 int ldh);
+/* Projection passes the orthogonalisation took in steps mstart..mend of the last device-resident nsb_arnoldi
+ * on this basis' context: 1 or 2 per step for NSB_ORTH_DGKS (the decision is taken on the device), 2 otherwise. */
+int nsb_arnoldi_passes(nsb_basis_t Q, int mstart, int mend, int orth_mode, int *passes);
 
 /* LAPACK provider: raw Fortran-ABI entry points, as core/lapack_wrapper.f90 links them
  * (dgeev :158, dgees :49, dtrsen :108, dgels :288).  The Fortran host passes c_funloc(dgeev)...;

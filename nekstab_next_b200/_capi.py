@@ -20,6 +20,7 @@ HOST_MATVEC = C.CFUNCTYPE(C.c_int, C.c_void_p, c_dpp, C.c_double, c_dpp, c_doubl
 PROTOTYPES = {
     'nsb_last_error': (C.c_char_p, []),
     'nsb_version': (C.c_int, []),
+    'nsb_build_id': (C.c_char_p, []),
     'nsb_get_unique_id': (C.c_int, [C.c_void_p]),
     'nsb_init': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, c_void_pp]),
     'nsb_finalize': (C.c_int, [H]),
@@ -101,6 +102,7 @@ PROTOTYPES = {
     'nsb_op_apply': (C.c_int, [H, H, C.c_int, H, C.c_int]),
     'nsb_op_count': (C.c_int, [H, c_i64_p]),
     'nsb_arnoldi': (C.c_int, [H, H, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int]),
+    'nsb_arnoldi_passes': (C.c_int, [H, C.c_int, C.c_int, C.c_int, c_int_p]),
     'nsb_set_lapack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'nsb_set_lapack_svd': (C.c_int, [C.c_void_p]),
     'nsb_svd': (C.c_int, [c_double_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),

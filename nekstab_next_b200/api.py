@@ -543,6 +543,17 @@ def arnoldi_factorization(Q: Basis, H: np.ndarray, mstart: int, mend: int, ksize
     check(Q.lib.nsb_arnoldi(Q.h, op.h, mstart - 1, mend - 1, orth_mode, _dp(H), H.shape[0]))
 
 
+def arnoldi_passes(Q: Basis, mstart: int, mend: int, orth_mode: int) -> np.ndarray:
+    """Projection passes per step (1-based mstart..mend) of the last device-resident factorisation."""
+    out = np.zeros(mend - mstart + 1, dtype=np.int32)
+    check(Q.lib.nsb_arnoldi_passes(Q.h, mstart - 1, mend - 1, orth_mode, out.ctypes.data_as(c_int_p)))
+    return out
+
+
+def build_id() -> str:
+    return _capi.load().nsb_build_id().decode()
+
+
 def eig(A: np.ndarray):
     set_lapack_from_scipy()
     n = A.shape[0]

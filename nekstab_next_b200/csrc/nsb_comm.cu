@@ -9,9 +9,11 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "nsb_internal.h"
+#include "nsb_tail.cuh"
 
 namespace nsb {
 
@@ -88,95 +90,79 @@ static int load_nccl() {
 // collective s+1 needs everybody's contribution to it, which they issue after finishing s.
 // NCCL stays for bootstrap, set-up and as the fallback when no mailbox is connected.
 // ------------------------------------------------------------------------------------------------
-constexpr int ARN = kMaxK + 8;                    // doubles per all-reduce vector slot
-struct PeerPtrs { double *p[nsb_context_s::kMaxPeers]; };
+// (mailbox layout, flag loads / stores and the block-level all-reduce live in nsb_tail.cuh: the sweep kernels
+// of the orthogonalisation run the same exchange in their own tails)
 
-// mailbox layout (in doubles): [ar data 2*P*ARN][ar flags 2*P][halo flags 2*P][halo data ...]
-__host__ __device__ inline size_t mb_ar_data(int P, int slot, int r) { return ((size_t)slot * P + r) * ARN; }
-__host__ __device__ inline size_t mb_ar_flag(int P, int slot, int r) { return (size_t)2 * P * ARN + (size_t)slot * P + r; }
-__host__ __device__ inline size_t mb_hx_flag(int P, int slot, int r) { return (size_t)2 * P * ARN + 2 * P + (size_t)slot * P + r; }
-__host__ __device__ inline size_t mb_halo_base(int P) { return (((size_t)2 * P * ARN + 4 * P) + 31) & ~(size_t)31; }
-
-__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+// stand-alone all-reduce of n <= ARN doubles for the callers without a tail (single dots, CG scalars)
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(double *buf, int n, PeerComm comm) {
+  p2p_allreduce_block(buf, n, comm);
 }
 
-__global__ void __launch_bounds__(256)
-p2p_allreduce_kernel(double *__restrict__ buf, int n, uint64_t seq, int rank, int P, PeerPtrs mail) {
-  const int slot = (int)(seq & 1);
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const double v = buf[j];
-    for (int r = 0; r < P; ++r) mail.p[r][mb_ar_data(P, slot, rank) + j] = v;   // peer stores over NVLink
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < P)
-    st_release_sys(reinterpret_cast<uint64_t *>(mail.p[threadIdx.x] + mb_ar_flag(P, slot, rank)), seq);
-  if (threadIdx.x < P) {
-    const uint64_t *f = reinterpret_cast<const uint64_t *>(mail.p[rank] + mb_ar_flag(P, slot, threadIdx.x));
-    while (ld_acquire_sys(f) != seq) { }
-  }
-  __syncthreads();
-  const double *mine = mail.p[rank];
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < P; ++r) s += mine[mb_ar_data(P, slot, r) + j];
-    buf[j] = s;
-  }
-}
-
-// pack the interface sums of nf fields straight into the peer's mailbox
+// ---- halo exchange of the gather-scatter through the mailboxes ---------------------------------
+// Every mesh (nsb_sem_t) owns a reservation in the halo area of the mailbox: its flag words [2][P] and one
+// data region per neighbour (two slots each), plus its own device-resident sequence number -- two meshes on
+// one context (velocity and pressure mesh) neither overlap nor share a sequence.
+//   pack   : interface sums -> the neighbour's region (peer stores), slot = (seq + 1) & 1
+//   flags  : seq += 1; release-store seq into every neighbour's flag word for this rank
+//   unpack : acquire-spin on the neighbour's flag word in MY mailbox, then add its data
 __global__ void pack_p2p_kernel(const double *__restrict__ node_sum, const int32_t *__restrict__ nodes, int64_t n,
-                                double *__restrict__ dst, int64_t ns_stride) {
+                                double *__restrict__ dst0, int64_t slot_stride, int64_t ns_stride,
+                                const unsigned long long *__restrict__ seq_d) {
+  const int slot = (int)((*seq_d + 1ull) & 1ull);
+  double *dst = dst0 + (int64_t)slot * slot_stride;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (t < n) dst[(int64_t)f * n + t] = node_sum[(int64_t)f * ns_stride + nodes[t]];
 }
 
-struct HaloFlags { uint64_t *p[nsb_context_s::kMaxPeers]; int n; };
-__global__ void p2p_flags_kernel(HaloFlags fl, uint64_t seq) {
-  if ((int)threadIdx.x < fl.n) st_release_sys(fl.p[threadIdx.x], seq);
+struct HaloFlags { uint64_t *p[nsb_context_s::kMaxPeers]; int n; int P; };   // p[i]: slot-0 flag word at peer i
+__global__ void p2p_flags_kernel(HaloFlags fl, unsigned long long *seq_d) {
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) s_seq = ++(*seq_d);
+  __syncthreads();
+  const uint64_t seq = s_seq;
+  if ((int)threadIdx.x < fl.n) st_release_sys(fl.p[threadIdx.x] + (seq & 1) * fl.P, seq);
 }
 
 __global__ void unpack_wait_add_kernel(double *__restrict__ node_sum, const int32_t *__restrict__ nodes, int64_t n,
-                                       const double *__restrict__ src, int64_t ns_stride,
-                                       const uint64_t *__restrict__ flag, uint64_t seq) {
-  if (threadIdx.x == 0)
-    while (ld_acquire_sys(flag) != seq) { }
+                                       const double *src0, int64_t slot_stride, int64_t ns_stride,
+                                       const uint64_t *flag0, int P, const unsigned long long *__restrict__ seq_d,
+                                       int *err) {
+  const uint64_t seq = *seq_d;
+  const int slot = (int)(seq & 1);
+  if (threadIdx.x == 0) spin_until(flag0 + (size_t)slot * P, seq, err, DEVERR_HALO_TIMEOUT);
   __syncthreads();
+  const double *src = src0 + (int64_t)slot * slot_stride;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
-  if (t < n) node_sum[(int64_t)f * ns_stride + nodes[t]] += src[(int64_t)f * n + t];
+  if (t < n) node_sum[(int64_t)f * ns_stride + nodes[t]] += ld_relaxed_sys(src + (int64_t)f * n + t);
 }
 
 int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st) {
   nsb_context_t ctx = S->ctx;
   const int P = ctx->nranks;
-  const uint64_t seq = ++ctx->hx_seq;
-  const int slot = (int)(seq & 1);
   const int64_t nifc = S->nshared - S->n_local;
   HaloFlags fl;
   fl.n = 0;
+  fl.P = P;
   for (auto &Pr : S->peers) {
     const unsigned nb = (unsigned)((Pr.n + 255) / 256);
-    double *dst = ctx->peer_mail[Pr.rank] + mb_halo_base(P) + Pr.peer_off + (int64_t)slot * S->ns_fields * Pr.n;
-    pack_p2p_kernel<<<dim3(nb, nf), 256, 0, st>>>(S->node_sum_d, Pr.idx_d, Pr.n, dst, nifc);
-    fl.p[fl.n++] = reinterpret_cast<uint64_t *>(ctx->peer_mail[Pr.rank] + mb_hx_flag(P, slot, ctx->rank));
+    double *dst = ctx->peer_mail[Pr.rank] + mb_halo_base(P) + Pr.peer_off;
+    pack_p2p_kernel<<<dim3(nb, nf), 256, 0, st>>>(S->node_sum_d, Pr.idx_d, Pr.n, dst, (int64_t)S->ns_fields * Pr.n, nifc,
+                                                  S->hx_seq_d);
+    fl.p[fl.n++] = reinterpret_cast<uint64_t *>(ctx->peer_mail[Pr.rank] + mb_halo_base(P) + S->peer_flag_off[Pr.rank]) +
+                   ctx->rank;
     ctx->launches++;
   }
   // stores of the pack kernels are complete at the kernel boundary; then publish the sequence number
-  p2p_flags_kernel<<<1, 32, 0, st>>>(fl, seq);
+  p2p_flags_kernel<<<1, 32, 0, st>>>(fl, S->hx_seq_d);
   ctx->launches++;
   for (auto &Pr : S->peers) {
     const unsigned nb = (unsigned)((Pr.n + 255) / 256);
-    const double *src = ctx->mail_d + mb_halo_base(P) + Pr.my_off + (int64_t)slot * S->ns_fields * Pr.n;
-    const uint64_t *flag = reinterpret_cast<const uint64_t *>(ctx->mail_d + mb_hx_flag(P, slot, Pr.rank));
-    unpack_wait_add_kernel<<<dim3(nb, nf), 256, 0, st>>>(S->node_sum_d, Pr.idx_d, Pr.n, src, nifc, flag, seq);
+    const double *src = ctx->mail_d + mb_halo_base(P) + Pr.my_off;
+    const uint64_t *flag = reinterpret_cast<const uint64_t *>(ctx->mail_d + mb_halo_base(P) + S->halo_flag_off) + Pr.rank;
+    unpack_wait_add_kernel<<<dim3(nb, nf), 256, 0, st>>>(S->node_sum_d, Pr.idx_d, Pr.n, src, (int64_t)S->ns_fields * Pr.n,
+                                                         nifc, flag, P, S->hx_seq_d, ctx->dev_err_d);
     ctx->launches++;
   }
   NSB_CUDA(cudaGetLastError());
@@ -206,11 +192,14 @@ int comm_destroy(nsb_context_t ctx) {
 int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n) {
   if (ctx->nranks == 1 || n == 0) return NSB_OK;
   if (ctx->p2p && n <= kMaxK + 8) {
-    PeerPtrs mail;
-    for (int r = 0; r < ctx->nranks; ++r) mail.p[r] = ctx->peer_mail[r];
-    const uint64_t seq = ++ctx->ar_seq;
+    PeerComm comm;
+    comm.P = ctx->nranks;
+    comm.rank = ctx->rank;
+    comm.seq = ctx->seq_d;
+    comm.err = ctx->dev_err_d;
+    for (int r = 0; r < nsb_context_s::kMaxPeers; ++r) comm.mail.p[r] = r < ctx->nranks ? ctx->peer_mail[r] : nullptr;
     ProfScope ps(ctx, PC_SMALL, 8.0 * n * ctx->nranks);
-    p2p_allreduce_kernel<<<1, 256, 0, ctx->stream>>>(buf_d, n, seq, ctx->rank, ctx->nranks, mail);
+    p2p_allreduce_kernel<<<1, 256, 0, ctx->stream>>>(buf_d, n, comm);
     ctx->launches++;
     NSB_CUDA(cudaGetLastError());
     return NSB_OK;
@@ -349,37 +338,71 @@ int exchange_setup(nsb_sem_t S) {
     NSB_CUDA(cudaMemcpy(Pr.idx_d, nodes.data(), sizeof(int32_t) * Pr.n, cudaMemcpyHostToDevice));
     S->peers.push_back(Pr);
   }
-  // 5. peer-memory halo: lay out one region per peer in MY mailbox and tell every peer where its
-  //    data goes (all-gather of the offset tables)
+  // 5. peer-memory halo: reserve this mesh's flag words and one data region per peer in MY mailbox (bump
+  //    allocator over the halo area, so several meshes on one context never overlap) and tell every peer
+  //    where its data and its flag go (all-gather of the offset tables)
   S->p2p_halo = false;
   if (ctx->p2p) {
+    const int64_t flag_doubles = ((int64_t)2 * P + 31) & ~(int64_t)31;
+    int64_t need = flag_doubles;
+    for (auto &Pr : S->peers) need += ((2 * (int64_t)S->ns_fields * Pr.n) + 31) & ~(int64_t)31;
+    const bool reuse = S->halo_flag_off >= 0 && need <= S->halo_region_doubles;   // repeated set-up of this mesh
+    const int64_t base = reuse ? S->halo_flag_off : (int64_t)ctx->halo_used;
     std::vector<int64_t> mine_off(P, -1);
-    int64_t cur = 0;
+    int64_t cur = base + flag_doubles;
     for (auto &Pr : S->peers) {
       Pr.my_off = cur;
       mine_off[Pr.rank] = cur;
-      cur += 2 * (int64_t)S->ns_fields * Pr.n;           // two slots
-      cur = (cur + 31) & ~(int64_t)31;
+      cur += ((2 * (int64_t)S->ns_fields * Pr.n) + 31) & ~(int64_t)31;   // two slots
     }
-    int64_t fits = (mb_halo_base(P) + (size_t)cur) * sizeof(double) <= ctx->mail_bytes ? 1 : 0;
+    const int64_t fits = (mb_halo_base(P) + (size_t)cur) * sizeof(double) <= ctx->mail_bytes ? 1 : 0;
+    if (!S->hx_seq_d) NSB_CUDA(cudaMalloc(&S->hx_seq_d, sizeof(unsigned long long)));
+    NSB_CUDA(cudaMemsetAsync(S->hx_seq_d, 0, sizeof(unsigned long long), ctx->stream));
+    // flags (and data) of the reservation start from zero BEFORE any peer can learn the offsets
+    if (fits) NSB_CUDA(cudaMemsetAsync(ctx->mail_d + mb_halo_base(P) + base, 0, sizeof(double) * (size_t)(cur - base), ctx->stream));
+    const int W = P + 2;   // per rank: P data offsets, the flag offset, fits
     int64_t *tab_d = nullptr;
-    NSB_CUDA(cudaMalloc(&tab_d, sizeof(int64_t) * (size_t)(P + 1) * (P + 1)));
+    NSB_CUDA(cudaMalloc(&tab_d, sizeof(int64_t) * (size_t)(P + 1) * W));
     std::vector<int64_t> sendt(mine_off);
+    sendt.push_back(base);
     sendt.push_back(fits);
-    NSB_CUDA(cudaMemcpyAsync(tab_d + (size_t)P * (P + 1), sendt.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice,
-                             ctx->stream));
-    NSB_NCCL(g_nccl.AllGather(tab_d + (size_t)P * (P + 1), tab_d, (size_t)(P + 1), ncclInt64, comm, ctx->stream));
-    std::vector<int64_t> tab((size_t)P * (P + 1));
+    NSB_CUDA(cudaMemcpyAsync(tab_d + (size_t)P * W, sendt.data(), sizeof(int64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
+    NSB_NCCL(g_nccl.AllGather(tab_d + (size_t)P * W, tab_d, (size_t)W, ncclInt64, comm, ctx->stream));
+    std::vector<int64_t> tab((size_t)P * W);
     NSB_CUDA(cudaMemcpyAsync(tab.data(), tab_d, sizeof(int64_t) * tab.size(), cudaMemcpyDeviceToHost, ctx->stream));
     NSB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(tab_d);
     bool all_fit = true;
-    for (int r = 0; r < P; ++r) all_fit = all_fit && tab[(size_t)r * (P + 1) + P] == 1;
+    for (int r = 0; r < P; ++r) all_fit = all_fit && tab[(size_t)r * W + P + 1] == 1;
     if (all_fit) {
-      for (auto &Pr : S->peers) Pr.peer_off = tab[(size_t)Pr.rank * (P + 1) + ctx->rank];
+      for (auto &Pr : S->peers) Pr.peer_off = tab[(size_t)Pr.rank * W + ctx->rank];
+      S->peer_flag_off.assign(P, -1);
+      for (int r = 0; r < P; ++r) S->peer_flag_off[r] = tab[(size_t)r * W + P];
+      if (!reuse) {
+        if (S->halo_flag_off < 0) ctx->halo_users++;
+        S->halo_flag_off = base;
+        S->halo_region_doubles = cur - base;
+        ctx->halo_used = (size_t)cur;
+      }
       S->p2p_halo = true;
     }
   }
+  clear_step_graphs(ctx);
+  return NSB_OK;
+}
+
+// MIN over all ranks of a host flag (set-up only, NCCL)
+int allreduce_min_int(nsb_context_t ctx, int mine, int *out) {
+  *out = mine;
+  if (ctx->nranks == 1) return NSB_OK;
+  NSB_REQUIRE(ctx->nccl_comm, "allreduce_min_int: no communicator");
+  int *v_d = nullptr;
+  NSB_CUDA(cudaMalloc(&v_d, sizeof(int)));
+  NSB_CUDA(cudaMemcpyAsync(v_d, &mine, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NSB_NCCL(g_nccl.AllReduce(v_d, v_d, 1, ncclInt32, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  NSB_CUDA(cudaMemcpyAsync(out, v_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(v_d);
   return NSB_OK;
 }
 
@@ -431,6 +454,8 @@ extern "C" int nsb_p2p_mailbox_create(nsb_context_t ctx, int64_t halo_bytes, voi
 extern "C" int nsb_p2p_mailbox_connect(nsb_context_t ctx, const void *all_handles) {
   NSB_REQUIRE(ctx && all_handles && ctx->mail_d, "nsb_p2p_mailbox_connect: create the mailbox first");
   cudaSetDevice(ctx->device);
+  int ok = 1;
+  char why[256] = "";
   for (int r = 0; r < ctx->nranks; ++r) {
     if (r == ctx->rank) {
       ctx->peer_mail[r] = ctx->mail_d;
@@ -441,12 +466,31 @@ extern "C" int nsb_p2p_mailbox_connect(nsb_context_t ctx, const void *all_handle
     void *p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
-      nsb::set_error("nsb_p2p_mailbox_connect: cannot map the mailbox of rank %d: %s", r, cudaGetErrorString(e));
-      return NSB_ECUDA;
+      snprintf(why, sizeof(why), "cannot map the mailbox of rank %d: %s", r, cudaGetErrorString(e));
+      cudaGetLastError();
+      ok = 0;
+      break;
     }
     ctx->peer_mail[r] = (double *)p;
   }
+  // The peer-memory path is used only if EVERY rank mapped EVERY mailbox: a rank left on NCCL while the others
+  // spin on its flag would hang them.  The verdict is a MIN all-reduce over the NCCL communicator, so all
+  // ranks also agree on the number of collectives issued during set-up.
+  int all_ok = ok;
+  NSB_CHECK(nsb::allreduce_min_int(ctx, ok, &all_ok));
+  if (!all_ok) {
+    for (int r = 0; r < ctx->nranks; ++r) {
+      if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
+      ctx->peer_mail[r] = nullptr;
+    }
+    ctx->p2p = false;
+    if (!ok) nsb::set_error("nsb_p2p_mailbox_connect: %s; all ranks stay on NCCL", why);
+    return NSB_OK;   // not an error: NCCL remains the transport on every rank (query nsb_p2p_enabled)
+  }
   ctx->p2p = true;
+  ctx->halo_used = 0;
+  ctx->halo_users = 0;
+  nsb::clear_step_graphs(ctx);
   return NSB_OK;
 }
 

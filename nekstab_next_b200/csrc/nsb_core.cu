@@ -28,11 +28,28 @@ void set_error(const char *fmt, ...) {
 
 int ensure_partial(nsb_context_t ctx, int64_t rows) {
   if (rows <= ctx->partial_rows) return NSB_OK;
+  clear_step_graphs(ctx);   // captured steps hold the old address
   if (ctx->partial_d) NSB_CUDA(cudaFree(ctx->partial_d));
   ctx->partial_d = nullptr;
   NSB_CUDA(cudaMalloc(&ctx->partial_d, sizeof(double) * rows * (kMaxK + 8)));
   ctx->partial_rows = rows;
   return NSB_OK;
+}
+
+int check_dev_err(nsb_context_t ctx) {
+  if (!ctx->dev_err) return NSB_OK;
+  const int e = *(volatile int *)ctx->dev_err;
+  if (e == 0) return NSB_OK;
+  *(volatile int *)ctx->dev_err = 0;
+  set_error("device-side wait timed out (%s): a peer rank never published its contribution",
+            e == 1 ? "peer-memory all-reduce" : "halo exchange");
+  return NSB_ECUDA;
+}
+
+void clear_step_graphs(nsb_context_t ctx) {
+  for (auto &kv : ctx->step_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  ctx->step_graphs.clear();
 }
 
 ProfScope::ProfScope(nsb_context_t ctx, int cls, double bytes) : c(ctx) {
@@ -142,6 +159,9 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   if (const char *e = getenv("NSB_AX_DMMA")) ctx->ax_dmma = e[0] != '0';
   if (const char *e = getenv("NSB_PIPELINE_UPLOAD")) ctx->pipeline_upload = e[0] != '0';
   if (const char *e = getenv("NSB_ROTATE_SIMPLE")) ctx->rotate_simple = e[0] == '1';
+  if (const char *e = getenv("NSB_FUSED_ALLWARPS")) ctx->fused_allwarps = e[0] != '0';
+  if (const char *e = getenv("NSB_TAIL")) ctx->tail = e[0] != '0';
+  if (const char *e = getenv("NSB_GRAPH")) ctx->use_graph = e[0] != '0';
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaEventCreate(&ctx->ev0));
@@ -149,6 +169,15 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   NSB_CUDA(cudaMalloc(&ctx->hvec_d, sizeof(double) * 4 * (kMaxK + 8)));
   NSB_CUDA(cudaMemset(ctx->hvec_d, 0, sizeof(double) * 4 * (kMaxK + 8)));
   NSB_CUDA(cudaMallocHost(&ctx->hpin, sizeof(double) * 4 * (kMaxK + 8)));
+  NSB_CUDA(cudaMalloc(&ctx->ticket_d, sizeof(unsigned int) * 8));
+  NSB_CUDA(cudaMemset(ctx->ticket_d, 0, sizeof(unsigned int) * 8));
+  NSB_CUDA(cudaMalloc(&ctx->flag_d, sizeof(int) * 4));
+  NSB_CUDA(cudaMemset(ctx->flag_d, 0, sizeof(int) * 4));
+  NSB_CUDA(cudaMalloc(&ctx->seq_d, sizeof(unsigned long long) * 2));
+  NSB_CUDA(cudaMemset(ctx->seq_d, 0, sizeof(unsigned long long) * 2));
+  NSB_CUDA(cudaHostAlloc((void **)&ctx->dev_err, sizeof(int) * 4, cudaHostAllocMapped));
+  ctx->dev_err[0] = 0;
+  NSB_CUDA(cudaHostGetDevicePointer((void **)&ctx->dev_err_d, ctx->dev_err, 0));
   NSB_CHECK(ensure_partial(ctx, (int64_t)ctx->num_sms * 8));
   if (nranks > 1) {
     NSB_REQUIRE(unique_id != nullptr, "nsb_init: unique_id required for nranks > 1");
@@ -167,6 +196,12 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
     if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
   if (ctx->mail_d) cudaFree(ctx->mail_d);
   comm_destroy(ctx);
+  clear_step_graphs(ctx);
+  if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  if (ctx->ticket_d) cudaFree(ctx->ticket_d);
+  if (ctx->flag_d) cudaFree(ctx->flag_d);
+  if (ctx->seq_d) cudaFree(ctx->seq_d);
+  if (ctx->dev_err) cudaFreeHost(ctx->dev_err);
   if (ctx->partial_d) cudaFree(ctx->partial_d);
   if (ctx->hvec_d) cudaFree(ctx->hvec_d);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
@@ -185,7 +220,7 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
 extern "C" int nsb_sync(nsb_context_t ctx) {
   NSB_REQUIRE(ctx, "nsb_sync: NULL context");
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return NSB_OK;
+  return check_dev_err(ctx);
 }
 
 extern "C" int nsb_rank(nsb_context_t ctx, int *rank, int *nranks) {
@@ -307,6 +342,7 @@ extern "C" int nsb_layout_destroy(nsb_layout_t L) {
   if (!L) return NSB_OK;
   cudaSetDevice(L->ctx->device);
   cudaStreamSynchronize(L->ctx->stream);
+  clear_step_graphs(L->ctx);
   if (L->w_d) cudaFree(L->w_d);
   delete L;
   return NSB_OK;
@@ -366,6 +402,7 @@ extern "C" int nsb_basis_destroy(nsb_basis_t B) {
   if (!B) return NSB_OK;
   cudaSetDevice(B->lay->ctx->device);
   cudaStreamSynchronize(B->lay->ctx->stream);
+  clear_step_graphs(B->lay->ctx);
   if (B->v_d) cudaFree(B->v_d);
   delete B;
   return NSB_OK;

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "nekstab_b200.h"
@@ -65,7 +67,21 @@ struct nsb_context_s {
   double *mail_d = nullptr;            // own mailbox (cudaMalloc, IPC-exported)
   size_t mail_bytes = 0, halo_bytes = 0;
   double *peer_mail[kMaxPeers] = {};   // every rank's mailbox mapped here ([rank] = own)
-  uint64_t ar_seq = 0, hx_seq = 0;     // sequence numbers of the all-reduces / halo exchanges
+  size_t halo_used = 0;                // bump allocator over the halo area (doubles); one region set per mesh
+  int halo_users = 0;                  // meshes holding a region; the allocator rewinds when the last one goes
+  // device-side state of the kernel tails (nsb_tail.cuh): last-CTA tickets, the DGKS second-pass flag, the
+  // sequence number of the peer-memory all-reduces (device-resident so that a step replays as a CUDA graph)
+  unsigned int *ticket_d = nullptr;    // [8], zero between launches
+  int *flag_d = nullptr;               // [4]
+  unsigned long long *seq_d = nullptr; // [2]
+  int *dev_err = nullptr;              // mapped pinned word the kernels set on a spin timeout (host address)
+  int *dev_err_d = nullptr;            // its device address
+  // whole Arnoldi steps captured as CUDA graphs (nsb_krylov.cu), keyed by (basis, operator, step, mode)
+  bool use_graph = true;               // NSB_GRAPH=0: plain launches
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  std::map<std::tuple<const void *, const void *, int, int>, StepGraph> step_graphs;
+  double *hstage = nullptr;            // pinned staging of the H columns of one factorisation
+  size_t hstage_elems = 0;
   // pipelined host upload (nsb_orth.cu): h1 computed chunk by chunk while the vector arrives
   std::vector<cudaEvent_t> chunk_ev;
   int h1_ready_k = -1;
@@ -80,6 +96,8 @@ struct nsb_context_s {
   bool rotate_simple = false;  // NSB_ROTATE_SIMPLE=1: first (untiled) rotation kernel
   int ax_stages = 0;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernels (0: default; DMMA: = warp groups pins one buffer per group)
   bool fused_priv = true;      // NSB_FUSED_PRIV=0: per-block warp reduction in the fused kernel's second projection
+  bool fused_allwarps = true;  // NSB_FUSED_ALLWARPS=0: warp 0 alone combines the row sums (two barriers per block)
+  bool tail = true;            // NSB_TAIL=0: separate reduce / all-reduce / add launches (round-1 structure)
   bool ax_dmma = true;         // NSB_AX_DMMA=0: vector-FMA contraction in the ring kernel instead of DMMA
   bool ax_ring = true;         // NSB_AX_RING=0: warp-per-element kernel instead of the TMA ring (N = 7)
   bool prof = false;
@@ -149,6 +167,10 @@ struct nsb_sem_s {
   double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z per system, d)
   double *diagA_d = nullptr;     // diagonal of A per local point (setprec), computed at the first solve
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
+  unsigned long long *hx_seq_d = nullptr;  // device sequence number of this mesh's halo exchanges
+  int64_t halo_flag_off = -1;    // offset (doubles, from the halo base) of this mesh's flag words [2][P] in MY mailbox
+  std::vector<int64_t> peer_flag_off;   // the same offset in every peer's mailbox
+  int64_t halo_region_doubles = 0;      // size of this mesh's reservation in the halo area
   // dealiased convection (nsb_conv.cu): lxd Gauss-Legendre points per direction
   int lxd = 0;
   double *J_d = nullptr, *Dg_d = nullptr;     // [lxd][lx] GLL -> GL interpolation, [lxd][lxd] derivative on GL
@@ -192,6 +214,8 @@ int ensure_partial(nsb_context_t ctx, int64_t rows);
 int comm_init(nsb_context_t ctx, const void *unique_id);
 int comm_destroy(nsb_context_t ctx);
 int allreduce_sum_d(nsb_context_t ctx, double *buf_d, int n);  // on ctx->stream, in place
+int check_dev_err(nsb_context_t ctx);                          // NSB_ECUDA if a kernel reported a spin timeout
+void clear_step_graphs(nsb_context_t ctx);                     // any handle a captured step refers to went away
 int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int nf, cudaStream_t st);
 int exchange_setup(nsb_sem_t sem);
 int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st);  // pack -> peer stores -> flags -> wait -> add

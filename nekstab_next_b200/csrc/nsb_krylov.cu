@@ -7,6 +7,7 @@
 #include <complex>
 #include <cstring>
 #include <numeric>
+#include <tuple>
 #include <vector>
 
 #include "nsb_internal.h"
@@ -224,6 +225,59 @@ extern "C" int nsb_select_eigenvalues(int *selected, int *cnt, const double *val
 // ------------------------------------------------------------------------------------------------
 // Arnoldi  (core/krylov_decomposition.f90:2-99)
 // ------------------------------------------------------------------------------------------------
+namespace {
+
+// One Arnoldi step {f = M q_m ; orthonormalise ; H column -> pinned staging} enqueued on the context stream.
+int enqueue_step(nsb_basis_t Q, nsb_op_t op, int m, int orth_mode, double *h_dst) {
+  NSB_CHECK(nsb_op_apply(op, Q, m, Q, m + 1));   // f written straight into column m+1 (saves the k_copy of :81)
+  return nsb_orthonormalize_async(Q, m + 1, m + 1, orth_mode, h_dst);
+}
+
+// The same step as a CUDA graph, captured the first time (basis, operator, m, mode) is seen and replayed
+// afterwards: everything a step needs at run time -- all-reduce sequence numbers, the DGKS decision, the
+// halo-exchange slots -- lives in device memory, so the captured kernels are valid for every replay.
+int step_graph(nsb_basis_t Q, nsb_op_t op, int m, int orth_mode, double *h_dst) {
+  nsb_context_t ctx = Q->lay->ctx;
+  const auto key = std::make_tuple((const void *)Q, (const void *)op, m, orth_mode);
+  auto it = ctx->step_graphs.find(key);
+  if (it == ctx->step_graphs.end()) {
+    cudaSetDevice(ctx->device);
+    const int64_t l0 = ctx->launches;
+    const int64_t n0 = op->napply;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->use_graph = false;
+      return enqueue_step(Q, op, m, orth_mode, h_dst);
+    }
+    const int rc = enqueue_step(Q, op, m, orth_mode, h_dst);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    const int64_t nl = ctx->launches - l0;
+    ctx->launches = l0;
+    op->napply = n0;
+    cudaGraphExec_t exec = nullptr;
+    if (rc == NSB_OK && e == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+      nsb_context_s::StepGraph sg;
+      sg.exec = exec;
+      sg.launches = nl;
+      it = ctx->step_graphs.emplace(key, sg).first;
+    }
+    if (g) cudaGraphDestroy(g);
+    if (it == ctx->step_graphs.end()) {   // capture not possible here: plain launches from now on
+      cudaGetLastError();
+      if (rc != NSB_OK) return rc;
+      ctx->use_graph = false;
+      return enqueue_step(Q, op, m, orth_mode, h_dst);
+    }
+  }
+  NSB_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
+  ctx->launches += it->second.launches;
+  op->napply++;
+  return NSB_OK;
+}
+
+}  // namespace
+
 extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int orth_mode, double *H,
                            int ldh) {
   NSB_REQUIRE(Q && op && H, "nsb_arnoldi: NULL argument");
@@ -231,22 +285,32 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
               "nsb_arnoldi: steps %d..%d need %d columns, basis has %d", mstart, mend, mend + 2, Q->ncols);
   NSB_REQUIRE(ldh >= mend + 2, "nsb_arnoldi: ldh=%d < %d", ldh, mend + 2);
   NSB_REQUIRE(mend + 1 <= kMaxK, "nsb_arnoldi: Krylov dimension above %d", kMaxK);
+  NSB_REQUIRE(orth_mode >= 0 && orth_mode <= 2, "nsb_arnoldi: unknown orthogonalisation mode %d", orth_mode);
   nsb_context_t ctx = Q->lay->ctx;
-  const int nsteps = mend - mstart + 1;
-  // device-resident operators (SEM, or compositions of them) allow a factorisation without host syncs
+  // device-resident operators (SEM, or compositions of them) allow a factorisation without host syncs: the
+  // DGKS decision is taken on the device as well, so all three orthogonalisation modes qualify
   bool dev_op = op->kind == 0;
   if (op->kind == 2) dev_op = op->outer->kind == 0 && op->inner->kind == 0;
-  const bool async = (orth_mode == NSB_ORTH_CGS2 || orth_mode == NSB_ORTH_MGS2_REF) && dev_op;
-  const size_t stride = (size_t)mend + 2;
-  double *hbuf = nullptr;
-  if (async) NSB_CHECK(nsb_host_alloc((void **)&hbuf, (int64_t)(sizeof(double) * stride * nsteps)));
+  const bool async = dev_op;
+  const size_t stride = kMaxK + 8;
+  if (async && !ctx->hstage) {   // pinned staging of the H columns, one fixed slot per step index
+    NSB_CHECK(nsb_host_alloc((void **)&ctx->hstage, (int64_t)(sizeof(double) * stride * stride)));
+    ctx->hstage_elems = stride * stride;
+  }
+  double *hbuf = ctx->hstage;
+  // whole steps as CUDA graphs: single rank, or every collective of the step on the peer-memory path
+  bool graphs = async && ctx->use_graph && !ctx->prof && orth_mode != NSB_ORTH_MGS2_REF;
+  if (graphs && ctx->nranks > 1) {
+    const nsb_op_t parts[2] = {op->kind == 2 ? op->outer : op, op->kind == 2 ? op->inner : op};
+    for (nsb_op_t part : parts) graphs = graphs && ctx->p2p && part->sem && part->sem->p2p_halo;
+  }
   int rc = NSB_OK;
   for (int m = mstart; m <= mend && rc == NSB_OK; ++m) {
-    // f = M q_m, written straight into column m+1 (saves the k_copy of :81)
     if (op->kind == 1 && orth_mode == NSB_ORTH_CGS2 && ctx->pipeline_upload) {
       // host operator: download q_m, call the host matvec, then upload f in row chunks with the
       // first projection running on every chunk as it lands
       nsb_layout_t L = Q->lay;
+      NSB_REQUIRE(L == op->lay, "nsb_arnoldi: host operator built for another layout");
       std::vector<const double *> pin(L->nfields);
       std::vector<double *> pout(L->nfields), pdl(L->nfields);
       for (int f = 0; f < L->nfields; ++f) {
@@ -265,18 +329,18 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
       }
       std::vector<const double *> pup(pout.begin(), pout.end());
       rc = upload_multidot_pipelined(Q, m + 1, pup.data(), tout, m + 1);
+      if (rc == NSB_OK) rc = nsb_orthonormalize(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, nullptr);
+    } else if (async) {
+      rc = (graphs && ctx->use_graph) ? step_graph(Q, op, m, orth_mode, hbuf + stride * m)
+                                      : enqueue_step(Q, op, m, orth_mode, hbuf + stride * m);
+      continue;
     } else {
       rc = nsb_op_apply(op, Q, m, Q, m + 1);
+      if (rc == NSB_OK) rc = nsb_orthonormalize(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, nullptr);
     }
-    if (rc != NSB_OK) break;
-    if (async) {
-      rc = nsb_orthonormalize_async(Q, m + 1, m + 1, orth_mode, hbuf + stride * (m - mstart));
-    } else {
-      rc = nsb_orthonormalize(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, nullptr);
-      if (rc == NSB_OK && !(H[(size_t)m * ldh + m + 1] > 0.0)) {
-        set_error("nsb_arnoldi: breakdown at step %d (residual norm %g)", m, H[(size_t)m * ldh + m + 1]);
-        rc = NSB_EBREAKDOWN;
-      }
+    if (rc == NSB_OK && !(H[(size_t)m * ldh + m + 1] > 0.0)) {
+      set_error("nsb_arnoldi: breakdown at step %d (residual norm %g)", m, H[(size_t)m * ldh + m + 1]);
+      rc = NSB_EBREAKDOWN;
     }
   }
   if (async) {
@@ -285,9 +349,10 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
       set_error("nsb_arnoldi: %s", cudaGetErrorString(e));
       rc = NSB_ECUDA;
     }
+    if (rc == NSB_OK) rc = check_dev_err(ctx);
     if (rc == NSB_OK)
       for (int m = mstart; m <= mend; ++m) {
-        const double *h = hbuf + stride * (m - mstart);
+        const double *h = hbuf + stride * m;
         memcpy(H + (size_t)m * ldh, h, sizeof(double) * (m + 2));
         for (int i = 0; i < m + 2; ++i)
           if (std::isnan(h[i])) {
@@ -299,9 +364,18 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
           rc = NSB_EBREAKDOWN;
         }
       }
-    nsb_host_free(hbuf);
   }
   return rc;
+}
+
+// Projection passes the DGKS orthogonalisation took in the steps mstart..mend of the LAST device-resident
+// nsb_arnoldi call on this basis' context (1 or 2 per step; 2 for every step in the other modes).
+extern "C" int nsb_arnoldi_passes(nsb_basis_t Q, int mstart, int mend, int orth_mode, int *passes) {
+  NSB_REQUIRE(Q && passes && mstart >= 0 && mend >= mstart && mend + 1 <= kMaxK, "nsb_arnoldi_passes: bad argument");
+  nsb_context_t ctx = Q->lay->ctx;
+  for (int m = mstart; m <= mend; ++m)
+    passes[m - mstart] = (orth_mode == NSB_ORTH_DGKS && ctx->hstage) ? (int)ctx->hstage[(kMaxK + 8) * (size_t)m + m + 2] : 2;
+  return NSB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@
 
 #include "nsb_internal.h"
 #include "nsb_device.cuh"
+#include "nsb_tail.cuh"
 
 using namespace nsb;
 
@@ -66,8 +67,9 @@ template <bool WITH_NORM>
 __global__ void __launch_bounds__(NT, 2)
 multidot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ w,
                 const double *__restrict__ W, int64_t nchunks, double *__restrict__ partial,
-                int pstride) {
+                int pstride, const __grid_constant__ OrthTail tail) {
   extern __shared__ double accS[];  // [NT/32][kpad]
+  if (tail.skip_flag && *tail.skip_flag == 0) return;   // DGKS: second projection not needed
   const int kpad = (k + KT) & ~(KT - 1);  // room for the norm slot too
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (NT / 32) * kpad; i += NT) accS[i] = 0.0;
@@ -129,6 +131,7 @@ multidot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *_
     for (int wp = 0; wp < NT / 32; ++wp) s += accS[wp * kpad + j];
     partial[(size_t)blockIdx.x * pstride + j] = s;
   }
+  orth_tail(tail);
 }
 
 // MODE 0: w -= V h          (rows [0, nrows))        [+ partial norm over rows < ndot if WITH_NORM]
@@ -137,8 +140,9 @@ template <int MODE, bool WITH_NORM>
 __global__ void __launch_bounds__(NT, 2)
 update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h,
               double *__restrict__ w, const double *__restrict__ W, int64_t nchunks,
-              int64_t ndot_chunks, double *__restrict__ partial) {
+              int64_t ndot_chunks, double *__restrict__ partial, const __grid_constant__ OrthTail tail) {
   extern __shared__ double hS[];
+  if (tail.skip_flag && *tail.skip_flag == 0) return;   // DGKS: second projection not needed
   for (int j = threadIdx.x; j < k; j += NT) hS[j] = h[j];
   __syncthreads();
   double nrm = 0.0;
@@ -201,7 +205,15 @@ update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__r
   if (WITH_NORM) {
     nrm = block_reduce_sum<NT>(nrm);
     if (threadIdx.x == 0) partial[blockIdx.x] = nrm;
+    orth_tail(tail);
   }
+}
+
+// tail bookkeeping as a kernel of its own: NCCL transport (the all-reduce is a host-enqueued NCCL call
+// between the sweep and this) and the NSB_TAIL=0 launch structure
+__global__ void __launch_bounds__(NT) orth_post_kernel(const __grid_constant__ OrthTail tail) {
+  if (tail.skip_flag && *tail.skip_flag == 0) return;
+  orth_post_ops(tail);
 }
 
 // w *= 1/sqrt(nrm2[0]);  h_out[k] = sqrt(nrm2[0])   (k_normalize, core/krylov_subspace.f90:75-92)
@@ -383,7 +395,8 @@ __global__ void __launch_bounds__(NT)
 fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h1,
                         double *__restrict__ w, const double *__restrict__ W, int64_t nblocks,
                         int64_t ndot_blocks, double *__restrict__ partial, int pstride,
-                        const __grid_constant__ CUtensorMap tmap, int kbox, int nbox) {
+                        const __grid_constant__ CUtensorMap tmap, int kbox, int nbox,
+                        const __grid_constant__ OrthTail tail) {
   constexpr int RP = RC / 2;      // row pairs per block
   constexpr int CG = NT / RP;     // column groups in pass A
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -518,6 +531,7 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
     for (int wp = 0; wp < NT / 32; ++wp) s += accS[wp * kpad + j];
     partial[(size_t)blockIdx.x * pstride + j] = s;
   }
+  orth_tail(tail);
 }
 
 // ---- fused update + multidot: 2-D TMA prefetch + register retention ---------------------------
@@ -528,20 +542,25 @@ fused_update_dot_kernel(const double *__restrict__ V, int64_t ld, int k, const d
 // Block = 64 rows; warp c owns the columns j = c (mod 8), lane l the row pair l; NJ = ceil(k/8).
 // PRIV: the second projection accumulates in lane-private registers over the CTA's blocks and crosses
 // lanes once at the end, instead of one warp_reduce8 per 8 columns and block.
-template <int NJ, bool WITH_NORM, bool PRIV>
+// ALLW: every warp completes the row sums itself (8 shared loads of the other warps' partials, w and W of its
+// lane's row pair loaded by all warps, L1 hits for seven of them) instead of waiting for warp 0 to do it:
+// one CTA barrier per 64-row block instead of two, and no serial section.  The partial-sum buffer is
+// double-buffered by block parity -- a warp can only write buffer b again after passing the barrier of the
+// block in between, which every warp reaches after it has read buffer b.
+template <int NJ, bool WITH_NORM, bool PRIV, bool ALLW>
 __global__ void __launch_bounds__(NT, 2)
 fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ w,
                      const double *__restrict__ W, int64_t nblocks, int64_t ndot_blocks,
                      double *__restrict__ partial, int pstride, const __grid_constant__ CUtensorMap tmap,
-                     int kbox, int nbox) {
+                     int kbox, int nbox, const __grid_constant__ OrthTail tail) {
   constexpr int RC = 64, NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kst = kbox * nbox;
   double *sV0 = reinterpret_cast<double *>(smem_raw);            // 2 x [kst][RC]
   double *accS = sV0 + 2 * (size_t)kst * RC;                     // [NW * NJ] column sums (+ norm)
   double *hS = accS + NW * NJ + 8;                               // [NW * NJ]
-  double2 *sP = reinterpret_cast<double2 *>(hS + NW * NJ);       // [NW][32]
-  double2 *sWW = sP + NW * 32;                                   // [32]
+  double2 *sP = reinterpret_cast<double2 *>(hS + NW * NJ);       // [2][NW][32]
+  double2 *sWW = sP + 2 * NW * 32;                               // [32]
   uint64_t *bar = reinterpret_cast<uint64_t *>(sWW + 32);        // [2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int j = tid; j < NW * NJ + 8; j += NT) accS[j] = 0.0;
@@ -574,7 +593,10 @@ fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ 
     const double *sV = sV0 + (size_t)stage * kst * RC;
     const bool in_dot = blk < ndot_blocks;
     double2 wv = make_double2(0.0, 0.0), Wv = make_double2(0.0, 0.0);
-    if (warp == 0) {
+    if (ALLW) {
+      wv = *reinterpret_cast<const double2 *>(w + r);
+      if (in_dot) Wv = __ldg(reinterpret_cast<const double2 *>(W + r));
+    } else if (warp == 0) {
       wv = *reinterpret_cast<const double2 *>(w + r);
       if (in_dot) Wv = ld_stream(reinterpret_cast<const double2 *>(W + r));
     }
@@ -590,26 +612,45 @@ fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ 
       a.x = fma(v[jj].x, hj, a.x);
       a.y = fma(v[jj].y, hj, a.y);
     }
-    sP[warp * 32 + lane] = a;
+    double2 *sPb = sP + (ALLW ? stage * NW * 32 : 0);   // stage alternates with the block parity of this CTA
+    sPb[warp * 32 + lane] = a;
     __syncthreads();
-    if (warp == 0) {
-      double2 s = sP[lane];
+    double2 ww;
+    if (ALLW) {
+      double2 s = sPb[lane];
 #pragma unroll
       for (int c = 1; c < NW; ++c) {
-        const double2 t = sP[c * 32 + lane];
+        const double2 t = sPb[c * 32 + lane];
         s.x += t.x;
         s.y += t.y;
       }
       wv.x -= s.x;
       wv.y -= s.y;
-      *reinterpret_cast<double2 *>(w + r) = wv;
-      const double2 ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
-      sWW[lane] = ww;
-      if (WITH_NORM) nrm += ww.x * wv.x + ww.y * wv.y;
+      ww = make_double2(Wv.x * wv.x, Wv.y * wv.y);
+      if (warp == 0) {
+        *reinterpret_cast<double2 *>(w + r) = wv;
+        if (WITH_NORM) nrm += ww.x * wv.x + ww.y * wv.y;
+      }
+    } else {
+      if (warp == 0) {
+        double2 s = sPb[lane];
+#pragma unroll
+        for (int c = 1; c < NW; ++c) {
+          const double2 t = sPb[c * 32 + lane];
+          s.x += t.x;
+          s.y += t.y;
+        }
+        wv.x -= s.x;
+        wv.y -= s.y;
+        *reinterpret_cast<double2 *>(w + r) = wv;
+        const double2 w2 = make_double2(Wv.x * wv.x, Wv.y * wv.y);
+        sWW[lane] = w2;
+        if (WITH_NORM) nrm += w2.x * wv.x + w2.y * wv.y;
+      }
+      __syncthreads();
+      ww = sWW[lane];
     }
-    __syncthreads();
     if (in_dot) {
-      const double2 ww = sWW[lane];
       if constexpr (PRIV) {
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) accp[jj] = fma(v[jj].x, ww.x, fma(v[jj].y, ww.y, accp[jj]));
@@ -647,13 +688,14 @@ fused_tma_reg_kernel(int k, const double *__restrict__ h1, double *__restrict__ 
   __syncthreads();
   for (int j = tid; j < k; j += NT) partial[(size_t)blockIdx.x * pstride + j] = accS[j];
   if (WITH_NORM && tid == 0) partial[(size_t)blockIdx.x * pstride + k] = accS[NW * NJ];
+  orth_tail(tail);
 }
 
 inline size_t fused_tma_reg_smem(int k, int nj) {
   int kbox, nbox;
   kbox = 0; nbox = (k + 255) / 256; kbox = (k + nbox - 1) / nbox;
   const size_t kst = (size_t)kbox * nbox;
-  return sizeof(double) * (2 * kst * 64 + 2 * 8 * nj + 8) + sizeof(double2) * (8 * 32 + 32) + 32;
+  return sizeof(double) * (2 * kst * 64 + 2 * 8 * nj + 8) + sizeof(double2) * (2 * 8 * 32 + 32) + 32;
 }
 
 // Large-k variant (209 <= k <= 440): 32-row blocks, 16 warps (512 threads), lane = one row,
@@ -663,7 +705,7 @@ __global__ void __launch_bounds__(512, 1)
 fused_tma_reg32_kernel(int k, const double *__restrict__ h1, double *__restrict__ w,
                        const double *__restrict__ W, int64_t nblocks, int64_t ndot_blocks,
                        double *__restrict__ partial, int pstride, const __grid_constant__ CUtensorMap tmap,
-                       int kbox, int nbox) {
+                       int kbox, int nbox, const __grid_constant__ OrthTail tail) {
   constexpr int RC = 32, NW = 16, NTH = 512;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int kst = kbox * nbox;
@@ -748,6 +790,7 @@ fused_tma_reg32_kernel(int k, const double *__restrict__ h1, double *__restrict_
   __syncthreads();
   for (int j = tid; j < k; j += NTH) partial[(size_t)blockIdx.x * pstride + j] = accS[j];
   if (WITH_NORM && tid == 0) partial[(size_t)blockIdx.x * pstride + k] = accS[NW * NJ];
+  orth_tail(tail);
 }
 
 inline size_t fused_tma_reg32_smem(int k, int nj) {
@@ -812,6 +855,63 @@ inline int persistent_grid(nsb_context_t ctx, int64_t nchunks) {
   return (int)(nchunks < g ? nchunks : g);
 }
 
+// What the last CTA of a sweep does with its reduced vector (nsb_tail.cuh)
+struct TailSpec {
+  double *out = nullptr;
+  double *hsum = nullptr;
+  int hsum_op = 0, norm_op = 0;
+  const int *skip_flag = nullptr;
+  double *passes_out = nullptr;
+};
+
+OrthTail make_tail(nsb_context_t ctx, const TailSpec &sp, int k, int kout, int pstride) {
+  OrthTail t;
+  t.partial = ctx->partial_d;
+  t.pstride = pstride;
+  t.ticket = ctx->tail ? ctx->ticket_d : nullptr;
+  t.out = sp.out;
+  t.hsum = sp.hsum;
+  t.scal = ctx->hvec_d + 3 * (kMaxK + 8);
+  t.flag = ctx->flag_d;
+  t.passes_out = sp.passes_out;
+  t.skip_flag = sp.skip_flag;
+  t.k = k;
+  t.kout = kout;
+  t.hsum_op = sp.hsum_op;
+  t.norm_op = sp.norm_op;
+  t.comm.P = ctx->nranks;
+  t.comm.rank = ctx->rank;
+  t.comm.seq = ctx->seq_d;
+  t.comm.err = ctx->dev_err_d;
+  for (int r = 0; r < nsb_context_s::kMaxPeers; ++r) t.comm.mail.p[r] = r < ctx->nranks ? ctx->peer_mail[r] : nullptr;
+  t.exchange = (ctx->tail && ctx->nranks > 1 && ctx->p2p && kout <= ARN) ? 1 : 0;
+  return t;
+}
+
+// Whatever of {reduce, all-reduce, bookkeeping} the kernel's own tail did not do.
+int finish_tail(nsb_context_t ctx, const OrthTail &t, int grid) {
+  if (t.kout == 0) return NSB_OK;
+  bool post = false;
+  if (!t.ticket) {   // NSB_TAIL=0: the launch structure of round 1
+    ProfScope ps(ctx, PC_SMALL, 8.0 * grid * t.kout);
+    reduce_partials_kernel<<<(t.kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(t.partial, grid, t.pstride, t.kout,
+                                                                              t.out, 0, nullptr);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, t.out, t.kout));
+    post = true;
+  } else if (ctx->nranks > 1 && !t.exchange) {   // NCCL transport
+    NSB_CHECK(allreduce_sum_d(ctx, t.out, t.kout));
+    post = true;
+  }
+  if (post && (t.hsum_op || t.norm_op)) {
+    orth_post_kernel<<<1, NT, 0, ctx->stream>>>(t);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+  }
+  return NSB_OK;
+}
+
 // Row-range variant used by the pipelined upload: rows [r0, r1) only, partial sums written from
 // partial row `prow` on; returns the number of partial rows produced (no second-stage reduction).
 int launch_multidot_rows(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *w, const double *W,
@@ -824,7 +924,7 @@ int launch_multidot_rows(nsb_context_t ctx, const double *V, int64_t ld, int k, 
   cudaSetDevice(ctx->device);
   ProfScope ps(ctx, PC_MULTIDOT, 8.0 * (double)(r1 - r0) * (k + 2));
   multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V + r0, ld, k, w + r0, W + r0, nchunks,
-                                                         ctx->partial_d + (size_t)prow * pstride, pstride);
+                                                         ctx->partial_d + (size_t)prow * pstride, pstride, OrthTail());
   ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   *nrows_out = grid;
@@ -832,8 +932,7 @@ int launch_multidot_rows(nsb_context_t ctx, const double *V, int64_t ld, int k, 
 }
 
 int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *w,
-                    const double *W, int64_t ndot, double *h_d, bool with_norm, double *hsum_d,
-                    int64_t nalg = -1) {
+                    const double *W, int64_t ndot, bool with_norm, const TailSpec &sp, int64_t nalg = -1) {
   const int64_t nchunks = ndot / CHUNK;
   const int grid = persistent_grid(ctx, nchunks);
   const int kpad = (k + KT) & ~(KT - 1);
@@ -841,29 +940,24 @@ int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const
   const int pstride = kMaxK + 8;
   NSB_CHECK(ensure_partial(ctx, grid));
   cudaSetDevice(ctx->device);
+  const int kout = with_norm ? k + 1 : k;
+  const OrthTail tail = make_tail(ctx, sp, k, kout, pstride);
   {
     // algorithmic bytes: V once (k columns), w and W once
     ProfScope ps(ctx, PC_MULTIDOT, 8.0 * (double)(nalg >= 0 ? nalg : ndot) * (k + 2));
     if (with_norm)
-      multidot_kernel<true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+      multidot_kernel<true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride, tail);
     else
-      multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride);
+      multidot_kernel<false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, w, W, nchunks, ctx->partial_d, pstride, tail);
   }
-  const int kout = with_norm ? k + 1 : k;
-  if (kout == 0) return NSB_OK;
-  {
-    ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
-    reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(
-        ctx->partial_d, grid, pstride, kout, h_d, hsum_d != nullptr, hsum_d);
-  }
-  ctx->launches += 2;
+  ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
-  return NSB_OK;
+  return finish_tail(ctx, tail, grid);
 }
 
 template <int MODE>
 int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h_d, double *w,
-                  const double *W, int64_t nrows, int64_t ndot, bool with_norm, double *nrm2_d,
+                  const double *W, int64_t nrows, int64_t ndot, bool with_norm, const TailSpec &sp,
                   int64_t nalg = -1, int64_t nalg_dot = -1) {
   const int64_t nchunks = nrows / CHUNK;
   const int grid = persistent_grid(ctx, nchunks);
@@ -872,28 +966,30 @@ int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const d
   // algorithmic bytes: V once, w read + written (MODE 0) or written (MODE 1), W once with the norm
   const double na = (double)(nalg >= 0 ? nalg : nrows), nd = (double)(nalg_dot >= 0 ? nalg_dot : ndot);
   const double bytes = 8.0 * (na * (k + (MODE == 0 ? 2 : 1)) + (with_norm ? nd : 0.0));
-  if (with_norm) {
-    {
-      ProfScope ps(ctx, MODE == 0 ? PC_UPDATE : PC_GEMV, bytes);
-      update_kernel<MODE, true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
-                                                                ctx->partial_d);
-    }
-    ProfScope ps(ctx, PC_SMALL, 8.0 * grid);
-    reduce_partials_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partial_d, grid, 1, 1, nrm2_d, 0, nullptr);
-    ctx->launches += 2;
-  } else {
+  // the norm is the only thing this kernel reduces: one partial per CTA, coefficient count 0
+  const OrthTail tail = make_tail(ctx, sp, 0, with_norm ? 1 : 0, 1);
+  {
     ProfScope ps(ctx, MODE == 0 ? PC_UPDATE : PC_GEMV, bytes);
-    update_kernel<MODE, false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
-                                                               ctx->partial_d);
-    ctx->launches += 1;
+    if (with_norm)
+      update_kernel<MODE, true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
+                                                                ctx->partial_d, tail);
+    else
+      update_kernel<MODE, false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
+                                                                 ctx->partial_d, tail);
   }
+  ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
-  return NSB_OK;
+  return finish_tail(ctx, tail, grid);
 }
 
 int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h1_d, double *w,
-                 const double *W, int64_t nrows, int64_t ndot, double *h2_d, bool with_norm, int64_t nalg,
+                 const double *W, int64_t nrows, int64_t ndot, bool with_norm, const TailSpec &sp, int64_t nalg,
                  int64_t nalg_dot) {
+  const int pstride = kMaxK + 8;
+  const int kout = with_norm ? k + 1 : k;
+  const OrthTail tail = make_tail(ctx, sp, k, kout, pstride);
+  int grid = 0;
+  cudaSetDevice(ctx->device);
   if (ctx->fused_loader == 3 && k >= ctx->fused_reg_min_k && k <= 8 * 26 &&
       fused_tma_reg_smem(k, (k + 7) / 8) <= 226 * 1024) {
     // 2-D TMA prefetch + register retention, 64-row blocks
@@ -906,18 +1002,20 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
     CUtensorMap tmap;
     NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, 64, kbox));
     const int64_t g = (int64_t)ctx->num_sms * 2;
-    const int grid = (int)(nblocks < g ? nblocks : g);
-    const int pstride = kMaxK + 8;
+    grid = (int)(nblocks < g ? nblocks : g);
     NSB_CHECK(ensure_partial(ctx, grid));
-    cudaSetDevice(ctx->device);
-    {
-      ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+    ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+#define LAUNCH_TR4(NJ, NORM, PRIV, ALLW)                                                                \
+  do {                                                                                                  \
+    NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg_kernel<NJ, NORM, PRIV, ALLW>,                           \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    fused_tma_reg_kernel<NJ, NORM, PRIV, ALLW><<<grid, NT, smem, ctx->stream>>>(                        \
+        k, h1_d, w, W, nblocks, ndot_blocks, ctx->partial_d, pstride, tmap, kbox, nbox, tail);          \
+  } while (0)
 #define LAUNCH_TR3(NJ, NORM, PRIV)                                                                      \
   do {                                                                                                  \
-    NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg_kernel<NJ, NORM, PRIV>,                                 \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    fused_tma_reg_kernel<NJ, NORM, PRIV><<<grid, NT, smem, ctx->stream>>>(                              \
-        k, h1_d, w, W, nblocks, ndot_blocks, ctx->partial_d, pstride, tmap, kbox, nbox);                \
+    if (ctx->fused_allwarps) LAUNCH_TR4(NJ, NORM, PRIV, true);                                          \
+    else LAUNCH_TR4(NJ, NORM, PRIV, false);                                                             \
   } while (0)
 #define LAUNCH_TR2(NJ, NORM)                                                                            \
   do {                                                                                                  \
@@ -925,31 +1023,21 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
     else LAUNCH_TR3(NJ, NORM, false);                                                                   \
   } while (0)
 #define LAUNCH_TR(NJ) do { if (with_norm) LAUNCH_TR2(NJ, true); else LAUNCH_TR2(NJ, false); } while (0)
-      switch (nj) {
-        case 4: LAUNCH_TR(4); break;
-        case 7: LAUNCH_TR(7); break;
-        case 10: LAUNCH_TR(10); break;
-        case 13: LAUNCH_TR(13); break;
-        case 16: LAUNCH_TR(16); break;
-        case 20: LAUNCH_TR(20); break;
-        default: LAUNCH_TR(26); break;
-      }
+    switch (nj) {
+      case 4: LAUNCH_TR(4); break;
+      case 7: LAUNCH_TR(7); break;
+      case 10: LAUNCH_TR(10); break;
+      case 13: LAUNCH_TR(13); break;
+      case 16: LAUNCH_TR(16); break;
+      case 20: LAUNCH_TR(20); break;
+      default: LAUNCH_TR(26); break;
+    }
 #undef LAUNCH_TR
 #undef LAUNCH_TR2
 #undef LAUNCH_TR3
-    }
-    const int kout = with_norm ? k + 1 : k;
-    {
-      ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
-      reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
-                                                                               kout, h2_d, 0, nullptr);
-    }
-    ctx->launches += 2;
-    NSB_CUDA(cudaGetLastError());
-    return NSB_OK;
-  }
-  if (ctx->fused_loader == 3 && k > 8 * 26 && k <= 16 * 28 &&
-      fused_tma_reg32_smem(k, (k + 15) / 16) <= 226 * 1024) {
+#undef LAUNCH_TR4
+  } else if (ctx->fused_loader == 3 && k > 8 * 26 && k <= 16 * 28 &&
+             fused_tma_reg32_smem(k, (k + 15) / 16) <= 226 * 1024) {
     const int64_t nblocks = nrows / 32, ndot_blocks = ndot / 32;
     const int njr = (k + 15) / 16;
     const int nj = njr <= 16 ? 16 : njr <= 20 ? 20 : njr <= 24 ? 24 : 28;
@@ -958,58 +1046,42 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
     fused_boxes(k, &kbox, &nbox);
     CUtensorMap tmap;
     NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, 32, kbox));
-    const int grid = (int)(nblocks < ctx->num_sms ? nblocks : ctx->num_sms);
-    const int pstride = kMaxK + 8;
+    grid = (int)(nblocks < ctx->num_sms ? nblocks : ctx->num_sms);
     NSB_CHECK(ensure_partial(ctx, grid));
-    cudaSetDevice(ctx->device);
-    {
-      ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
+    ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
 #define LAUNCH_T32B(NJ, NORM)                                                                            \
   do {                                                                                                   \
     NSB_CUDA(cudaFuncSetAttribute(fused_tma_reg32_kernel<NJ, NORM>,                                      \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     fused_tma_reg32_kernel<NJ, NORM><<<grid, 512, smem, ctx->stream>>>(k, h1_d, w, W, nblocks, ndot_blocks, \
-                                                                      ctx->partial_d, pstride, tmap, kbox, nbox); \
+                                                                      ctx->partial_d, pstride, tmap, kbox, nbox, tail); \
   } while (0)
 #define LAUNCH_T32(NJ) do { if (with_norm) LAUNCH_T32B(NJ, true); else LAUNCH_T32B(NJ, false); } while (0)
-      switch (nj) {
-        case 16: LAUNCH_T32(16); break;
-        case 20: LAUNCH_T32(20); break;
-        case 24: LAUNCH_T32(24); break;
-        default: LAUNCH_T32(28); break;
-      }
+    switch (nj) {
+      case 16: LAUNCH_T32(16); break;
+      case 20: LAUNCH_T32(20); break;
+      case 24: LAUNCH_T32(24); break;
+      default: LAUNCH_T32(28); break;
+    }
 #undef LAUNCH_T32
 #undef LAUNCH_T32B
-    }
-    const int kout = with_norm ? k + 1 : k;
-    {
-      ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
-      reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
-                                                                               kout, h2_d, 0, nullptr);
-    }
-    ctx->launches += 2;
-    NSB_CUDA(cudaGetLastError());
-    return NSB_OK;
-  }
-  int rc = fused_rows(k);
-  NSB_REQUIRE(rc != 0, "fused update+dot: k=%d does not fit in shared memory", k);
-  if (ctx->fused_rc && fused_smem_bytes(ctx->fused_rc, k) <= 226 * 1024) rc = ctx->fused_rc;
-  const int loader = ctx->fused_loader;
-  const size_t smem = fused_smem_bytes(rc, k);
-  int kbox, nbox;
-  fused_boxes(k, &kbox, &nbox);
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
-  if (loader == 3) NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, rc, kbox));
-  const int64_t nblocks = nrows / rc, ndot_blocks = ndot / rc;
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-  const int64_t g = (int64_t)ctx->num_sms * per_sm;
-  const int grid = (int)(nblocks < g ? nblocks : g);
-  const int pstride = kMaxK + 8;
-  NSB_CHECK(ensure_partial(ctx, grid));
-  cudaSetDevice(ctx->device);
-  {
+  } else {
+    int rc = fused_rows(k);
+    NSB_REQUIRE(rc != 0, "fused update+dot: k=%d does not fit in shared memory", k);
+    if (ctx->fused_rc && fused_smem_bytes(ctx->fused_rc, k) <= 226 * 1024) rc = ctx->fused_rc;
+    const int loader = ctx->fused_loader;
+    const size_t smem = fused_smem_bytes(rc, k);
+    int kbox, nbox;
+    fused_boxes(k, &kbox, &nbox);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (loader == 3) NSB_CHECK(make_basis_tmap(&tmap, V, ld, k, rc, kbox));
+    const int64_t nblocks = nrows / rc, ndot_blocks = ndot / rc;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    const int64_t g = (int64_t)ctx->num_sms * per_sm;
+    grid = (int)(nblocks < g ? nblocks : g);
+    NSB_CHECK(ensure_partial(ctx, grid));
     // algorithmic bytes: V once, w read + written, W once
     ProfScope ps(ctx, PC_FUSED, 8.0 * ((double)nalg * (k + 2) + (double)nalg_dot));
 #define LAUNCH_FUSED2(RC, NORM, LD)                                                                     \
@@ -1017,7 +1089,7 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
     NSB_CUDA(cudaFuncSetAttribute(fused_update_dot_kernel<RC, NORM, LD>,                                \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     fused_update_dot_kernel<RC, NORM, LD><<<grid, NT, smem, ctx->stream>>>(                             \
-        V, ld, k, h1_d, w, W, nblocks, ndot_blocks, ctx->partial_d, pstride, tmap, kbox, nbox);         \
+        V, ld, k, h1_d, w, W, nblocks, ndot_blocks, ctx->partial_d, pstride, tmap, kbox, nbox, tail);   \
   } while (0)
 #define LAUNCH_FUSED(RC, NORM)                                                \
   do {                                                                        \
@@ -1030,15 +1102,9 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
 #undef LAUNCH_FUSED
 #undef LAUNCH_FUSED2
   }
-  const int kout = with_norm ? k + 1 : k;
-  {
-    ProfScope ps(ctx, PC_SMALL, 8.0 * grid * kout);
-    reduce_partials_kernel<<<(kout * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->partial_d, grid, pstride,
-                                                                             kout, h2_d, 0, nullptr);
-  }
-  ctx->launches += 2;
+  ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
-  return NSB_OK;
+  return finish_tail(ctx, tail, grid);
 }
 
 int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm2_d, double *hk_d) {
@@ -1117,14 +1183,15 @@ int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fie
 
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d) {
   nsb_layout_t L = b->lay;
-  NSB_CHECK(launch_multidot(L->ctx, b->v_d, L->ld, k, w_col_d, L->w_d, L->ndot, h_d, false, nullptr));
-  if (L->ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(L->ctx, h_d, k));
-  return NSB_OK;
+  TailSpec sp;
+  sp.out = h_d;
+  return launch_multidot(L->ctx, b->v_d, L->ld, k, w_col_d, L->w_d, L->ndot, false, sp);
 }
-}  // namespace nsb
 
-// Enqueue the whole orthonormalisation; on return ctx->hvec_d[2*(kMaxK+8) ...] holds h[0..k].
-static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_out) {
+// Enqueue the whole orthonormalisation (core/krylov_decomposition.f90:150-186) on the context stream; nothing
+// here waits for the device.  On completion hsum = ctx->hvec_d[2*(kMaxK+8) ...] holds h[0..k] (H(1:k+1,k)) and,
+// in DGKS mode, hsum[k+1] the number of projection passes taken.
+int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode) {
   nsb_layout_t L = B->lay;
   nsb_context_t ctx = L->ctx;
   const int S = kMaxK + 8;
@@ -1133,109 +1200,111 @@ static int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, int *passes_o
   double *w = B->col(col_w);
   const double *V = B->v_d;
   cudaSetDevice(ctx->device);
-  int passes = 2;
   struct ClearH1 {   // the pipelined h1 is valid for exactly one orthonormalisation
     nsb_context_t c;
     ~ClearH1() { c->h1_ready_k = -1; c->h1_ready_col = nullptr; }
   } clear_h1{ctx};
   if (k == 0 || mode == NSB_ORTH_MGS2_REF) { ctx->h1_ready_k = -1; }
-  auto add_into = [&](double *dst, const double *src, int n) -> int {
-    if (n <= 0) return NSB_OK;
-    add_vec_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dst, src, n);
-    ctx->launches++;
-    NSB_CUDA(cudaGetLastError());
-    return NSB_OK;
-  };
+  TailSpec norm_only;            // |w|^2 -> scal[0], what normalize_kernel divides by
+  norm_only.out = scal + 2;
+  norm_only.norm_op = 1;
   if (k == 0) {
     // nothing to project out: k_normalize only
-    NSB_CHECK(launch_multidot(ctx, w, L->ld, 0, w, L->w_d, L->ndot, scal, true, nullptr));
-    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
-    passes = 0;
+    NSB_CHECK(launch_multidot(ctx, w, L->ld, 0, w, L->w_d, L->ndot, true, norm_only));
   } else if (mode == NSB_ORTH_MGS2_REF) {
     // literal core/krylov_decomposition.f90:155-180: one column at a time, two sweeps
     NSB_CUDA(cudaMemsetAsync(hsum, 0, sizeof(double) * (k + 1), ctx->stream));
+    TailSpec none;
     for (int pass = 0; pass < 2; ++pass)
       for (int i = 0; i < k; ++i) {
-        NSB_CHECK(launch_multidot(ctx, B->col(i), L->ld, 1, w, L->w_d, L->ndot, h1, false, nullptr));
-        if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, 1));
-        NSB_CHECK(add_into(hsum + i, h1, 1));
-        NSB_CHECK(launch_update<0>(ctx, B->col(i), L->ld, 1, h1, w, L->w_d, L->ld, L->ndot, false, nullptr));
+        TailSpec sp;
+        sp.out = h1;
+        sp.hsum = hsum + i;     // H(i,k) = alpha (:166), H(i,k) += alpha (:178)
+        sp.hsum_op = 2;
+        NSB_CHECK(launch_multidot(ctx, B->col(i), L->ld, 1, w, L->w_d, L->ndot, false, sp));
+        NSB_CHECK(launch_update<0>(ctx, B->col(i), L->ld, 1, h1, w, L->w_d, L->ld, L->ndot, false, none));
       }
-    NSB_CHECK(launch_multidot(ctx, w, L->ld, 0, w, L->w_d, L->ndot, scal, true, nullptr));
-    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
+    NSB_CHECK(launch_multidot(ctx, w, L->ld, 0, w, L->w_d, L->ndot, true, norm_only));
   } else {
     const bool dgks = (mode == NSB_ORTH_DGKS);
     const bool fused = !ctx->no_fused &&
                        (fused_rows(k) != 0 || (ctx->fused_loader == 3 && k > 8 * 26 && k <= 16 * 28 &&
                                                fused_tma_reg32_smem(k, (k + 15) / 16) <= 226 * 1024));
-    // pass 1 (the norm of the incoming w rides along for the DGKS test); already done chunk by chunk
+    // pass 1 (DGKS: the norm of the incoming w rides along for the test); already done chunk by chunk
     // during the upload when the vector came from the host (upload_multidot_pipelined)
     const bool have_h1 = !dgks && ctx->h1_ready_k == k && ctx->h1_ready_col == w;
     if (!have_h1) {
-      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h1, dgks, nullptr, L->ndof_dot + 1));
-      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h1, dgks ? k + 1 : k));
+      TailSpec sp;
+      sp.out = h1;
+      sp.hsum = hsum;
+      sp.hsum_op = 1;                 // H(1:k,k) = h1
+      sp.norm_op = dgks ? 2 : 0;      // scal[1] = |w|^2
+      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, dgks, sp, L->ndof_dot + 1));
+    } else {
+      NSB_CUDA(cudaMemcpyAsync(hsum, h1, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    NSB_CUDA(cudaMemcpyAsync(hsum, h1, sizeof(double) * k, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int *skip = dgks ? ctx->flag_d : nullptr;   // second projection only when the device-side test asks for it
     if (fused) {
-      // w -= V h1 and h2 = V^T W w in one sweep over V (h2[k] = ||w'||^2 for the DGKS test)
-      NSB_CHECK(launch_fused(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, h2, dgks, L->nact, L->ndof_dot + 1));
-      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, dgks ? k + 1 : k));
+      // w -= V h1 and h2 = V^T W w in one sweep over V; its tail adds h2 into H -- in DGKS mode only if
+      // |w'| < |w| / sqrt 2, the decision being taken by the kernel's last CTA from h2[k] = |w'|^2
+      TailSpec sp;
+      sp.out = h2;
+      sp.hsum = hsum;
+      sp.hsum_op = 2;
+      sp.norm_op = dgks ? 3 : 0;
+      sp.passes_out = dgks ? hsum + k + 1 : nullptr;
+      NSB_CHECK(launch_fused(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, sp, L->nact, L->ndof_dot + 1));
     } else {
-      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, scal, L->nact, L->ndof_dot + 1));
-      if (dgks && ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
-    }
-    bool second = true;
-    if (dgks) {
-      const double *n1_d = fused ? h2 + k : scal;
-      NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S, h1 + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 3 * S + 1, n1_d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-      const double n0 = ctx->hpin[3 * S], n1 = ctx->hpin[3 * S + 1];
-      second = !(n1 >= 0.5 * n0);  // ||w'|| < ||w|| / sqrt 2  (also taken on NaN)
-      if (!second && fused)
-        NSB_CUDA(cudaMemcpyAsync(scal, h2 + k, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    if (second) {
-      if (!fused) {
-        NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, h2, false, nullptr, L->ndof_dot + 1));
-        if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, h2, k));
+      TailSpec su;                    // DGKS: |w'|^2 and the decision ride on the first update
+      if (dgks) {
+        su.out = scal + 2;
+        su.norm_op = 3;
+        su.passes_out = hsum + k + 1;
       }
-      NSB_CHECK(add_into(hsum, h2, k));
-      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, scal, L->nact, L->ndof_dot + 1));
-      if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, scal, 1));
-    } else {
-      passes = 1;
+      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, su, L->nact, L->ndof_dot + 1));
+      TailSpec sp;
+      sp.out = h2;
+      sp.hsum = hsum;
+      sp.hsum_op = 2;
+      sp.skip_flag = skip;
+      NSB_CHECK(launch_multidot(ctx, V, L->ld, k, w, L->w_d, L->ndot, false, sp, L->ndof_dot + 1));
     }
+    TailSpec sn = norm_only;
+    sn.skip_flag = skip;
+    NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, sn, L->nact, L->ndof_dot + 1));
   }
   NSB_CHECK(launch_normalize(ctx, w, L->ld, scal, hsum + k));
-  if (passes_out) *passes_out = passes;
+  return NSB_OK;
+}
+}  // namespace nsb
+
+static int orth_args_ok(nsb_basis_t B, int k, int col_w, int mode, const void *h) {
+  NSB_REQUIRE(B && h, "nsb_orthonormalize: NULL argument");
+  NSB_REQUIRE(k >= 0 && k <= kMaxK && k <= B->ncols, "nsb_orthonormalize: k=%d out of range", k);
+  NSB_REQUIRE(col_w >= k && col_w < B->ncols, "nsb_orthonormalize: col_w=%d must be >= k and < ncols", col_w);
+  NSB_REQUIRE(mode >= 0 && mode <= 2, "nsb_orthonormalize: unknown mode %d", mode);
   return NSB_OK;
 }
 
+// h_pinned receives h[0..k] and, in DGKS mode, the number of passes in h_pinned[k+1] (so it needs k+2 doubles).
 extern "C" int nsb_orthonormalize_async(nsb_basis_t B, int k, int col_w, int mode, double *h_pinned) {
-  NSB_REQUIRE(B && h_pinned, "nsb_orthonormalize_async: NULL argument");
-  NSB_REQUIRE(k >= 0 && k <= kMaxK && k <= B->ncols, "nsb_orthonormalize: k=%d out of range", k);
-  NSB_REQUIRE(col_w >= k && col_w < B->ncols, "nsb_orthonormalize: col_w=%d must be >= k and < ncols", col_w);
-  NSB_REQUIRE(mode == NSB_ORTH_CGS2 || mode == NSB_ORTH_MGS2_REF,
-              "nsb_orthonormalize_async: mode %d needs a host decision; use nsb_orthonormalize", mode);
+  NSB_CHECK(orth_args_ok(B, k, col_w, mode, h_pinned));
   nsb_context_t ctx = B->lay->ctx;
-  NSB_CHECK(orth_enqueue(B, k, col_w, mode, nullptr));
-  NSB_CUDA(cudaMemcpyAsync(h_pinned, ctx->hvec_d + 2 * (kMaxK + 8), sizeof(double) * (k + 1),
+  NSB_CHECK(orth_enqueue(B, k, col_w, mode));
+  NSB_CUDA(cudaMemcpyAsync(h_pinned, ctx->hvec_d + 2 * (kMaxK + 8),
+                           sizeof(double) * (k + 1 + (mode == NSB_ORTH_DGKS && k > 0 ? 1 : 0)),
                            cudaMemcpyDeviceToHost, ctx->stream));
   return NSB_OK;
 }
 
 extern "C" int nsb_orthonormalize(nsb_basis_t B, int k, int col_w, int mode, double *h, int *passes) {
-  NSB_REQUIRE(B && h, "nsb_orthonormalize: NULL argument");
-  NSB_REQUIRE(k >= 0 && k <= kMaxK && k <= B->ncols, "nsb_orthonormalize: k=%d out of range", k);
-  NSB_REQUIRE(col_w >= k && col_w < B->ncols, "nsb_orthonormalize: col_w=%d must be >= k and < ncols", col_w);
-  NSB_REQUIRE(mode >= 0 && mode <= 2, "nsb_orthonormalize: unknown mode %d", mode);
+  NSB_CHECK(orth_args_ok(B, k, col_w, mode, h));
   nsb_context_t ctx = B->lay->ctx;
-  NSB_CHECK(orth_enqueue(B, k, col_w, mode, passes));
-  NSB_CUDA(cudaMemcpyAsync(ctx->hpin, ctx->hvec_d + 2 * (kMaxK + 8), sizeof(double) * (k + 1),
-                           cudaMemcpyDeviceToHost, ctx->stream));
+  NSB_CHECK(nsb_orthonormalize_async(B, k, col_w, mode, ctx->hpin));
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  NSB_CHECK(check_dev_err(ctx));
   memcpy(h, ctx->hpin, sizeof(double) * (k + 1));
+  if (passes) *passes = k == 0 ? 0 : (mode == NSB_ORTH_DGKS ? (int)ctx->hpin[k + 1] : 2);
   for (int i = 0; i <= k; ++i)
     if (std::isnan(h[i])) {
       set_error("NaN detected in dot product");
@@ -1267,7 +1336,7 @@ extern "C" int nsb_basis_gemv(nsb_basis_t B, int k, const double *y, nsb_basis_t
   double *y_d = ctx->hvec_d + (kMaxK + 8);
   memcpy(ctx->hpin + (kMaxK + 8), y, sizeof(double) * k);
   NSB_CUDA(cudaMemcpyAsync(y_d, ctx->hpin + (kMaxK + 8), sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
-  NSB_CHECK(launch_update<1>(ctx, B->v_d, L->ld, k, y_d, bout->col(cout), L->w_d, L->ld, L->ndot, false, nullptr));
+  NSB_CHECK(launch_update<1>(ctx, B->v_d, L->ld, k, y_d, bout->col(cout), L->w_d, L->ld, L->ndot, false, TailSpec()));
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));  // hpin is reused by the next call
   return NSB_OK;
 }

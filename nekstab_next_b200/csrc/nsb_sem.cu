@@ -1388,6 +1388,13 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   if (!S) return NSB_OK;
   cudaSetDevice(S->ctx->device);
   cudaStreamSynchronize(S->ctx->stream);
+  cudaStreamSynchronize(S->ctx->copy_stream);
+  clear_step_graphs(S->ctx);
+  if (S->halo_flag_off >= 0 && --S->ctx->halo_users <= 0) {   // last mesh gone: the halo area is free again
+    S->ctx->halo_users = 0;
+    S->ctx->halo_used = 0;
+  }
+  if (S->hx_seq_d) cudaFree(S->hx_seq_d);
   for (auto &P : S->peers) {
     cudaFree(P.idx_d);
     cudaFree(P.send_d);
@@ -1800,6 +1807,8 @@ extern "C" int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op
 
 extern "C" int nsb_op_destroy(nsb_op_t op) {
   if (!op) return NSB_OK;
+  if (op->sem) clear_step_graphs(op->sem->ctx);
+  else if (op->lay) clear_step_graphs(op->lay->ctx);
   if (op->tmp) nsb_basis_destroy(op->tmp);
   if (op->c_d) cudaFree(op->c_d);
   for (double *p : op->hin) cudaFreeHost(p);
@@ -1828,6 +1837,7 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
     return nsb_op_apply(op->outer, op->tmp, 0, bout, cout);
   }
   if (op->kind == 1) {
+    NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: host operator built for another layout");
     nsb_layout_t L = bin->lay;
     std::vector<const double *> pin(L->nfields);
     std::vector<double *> pout(L->nfields), pdl(L->nfields);

@@ -1,0 +1,174 @@
+// Kernel tails: what used to be three extra launches per inner product (reduce_partials -> peer-memory
+// all-reduce -> add into H) now runs inside the sweep kernel itself.  Every CTA writes its partial row,
+// takes a ticket, and the CTA that draws the last ticket
+//   1. sums the partial rows in a fixed order (bitwise reproducible whichever CTA is last),
+//   2. for nranks > 1 exchanges the vector through the NVLink mailboxes (stores into every peer's slot,
+//      release flag, acquire spin, sum in rank order -> identical bits on every rank),
+//   3. applies the bookkeeping of update_hessenberg_matrix (core/krylov_decomposition.f90:155-186): H column
+//      accumulation, the norm for k_normalize, and the DGKS re-orthogonalisation decision -- on the device,
+//      so the Arnoldi loop has no host round trip and a whole step can be replayed as a CUDA graph.
+// The all-reduce sequence number lives in device memory for the same reason (a kernel skipped on the device
+// must not consume a number: the two mailbox slots rely on consecutive collectives alternating).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nsb_internal.h"
+#include "nsb_device.cuh"
+
+namespace nsb {
+
+constexpr int ARN = kMaxK + 8;                    // doubles per all-reduce vector slot
+struct PeerPtrs { double *p[nsb_context_s::kMaxPeers]; };
+
+// mailbox layout (in doubles): [ar data 2*P*ARN][ar flags 2*P][reserved 2*P][halo area ...]
+__host__ __device__ inline size_t mb_ar_data(int P, int slot, int r) { return ((size_t)slot * P + r) * ARN; }
+__host__ __device__ inline size_t mb_ar_flag(int P, int slot, int r) { return (size_t)2 * P * ARN + (size_t)slot * P + r; }
+__host__ __device__ inline size_t mb_halo_base(int P) { return (((size_t)2 * P * ARN + 4 * P) + 31) & ~(size_t)31; }
+
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// peer-written data: a coherent load (never the read-only / non-coherent path)
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Spin until *flag == seq.  Bounded: after kSpinLimitNs the device error word is set and the wait is
+// abandoned, so a peer that never arrives (lost rank, failed mapping) surfaces as an error at the next
+// synchronising call instead of a hung GPU.
+constexpr unsigned long long kSpinLimitNs = 120ull * 1000000000ull;
+enum DevErr { DEVERR_NONE = 0, DEVERR_ALLREDUCE_TIMEOUT = 1, DEVERR_HALO_TIMEOUT = 2 };
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool spin_until(const uint64_t *flag, uint64_t seq, int *err, int code) {
+  unsigned long long t0 = 0;
+  for (unsigned it = 0;; ++it) {
+    if (ld_acquire_sys(flag) == seq) return true;
+    if ((it & 1023u) == 1023u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kSpinLimitNs) break;
+    }
+  }
+  if (err) atomicExch_system(err, code);
+  return false;
+}
+
+// One CTA sums buf[0..n) over all ranks in place.  Called by every thread of the CTA.
+struct PeerComm {
+  int P = 1, rank = 0;
+  unsigned long long *seq = nullptr;   // device counter of the all-reduces issued on this context
+  int *err = nullptr;                  // device-visible error word
+  PeerPtrs mail;
+};
+
+__device__ __forceinline__ void p2p_allreduce_block(double *buf, int n, const PeerComm &c) {
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) s_seq = ++(*c.seq);   // a single CTA of a single kernel at a time touches the counter
+  __syncthreads();
+  const uint64_t seq = s_seq;
+  const int slot = (int)(seq & 1), P = c.P;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = buf[j];
+    for (int r = 0; r < P; ++r) c.mail.p[r][mb_ar_data(P, slot, c.rank) + j] = v;   // peer stores over NVLink
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < P) {
+    st_release_sys(reinterpret_cast<uint64_t *>(c.mail.p[threadIdx.x] + mb_ar_flag(P, slot, c.rank)), seq);
+    spin_until(reinterpret_cast<const uint64_t *>(c.mail.p[c.rank] + mb_ar_flag(P, slot, threadIdx.x)), seq, c.err,
+               DEVERR_ALLREDUCE_TIMEOUT);
+  }
+  __syncthreads();
+  const double *mine = c.mail.p[c.rank];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < P; ++r) s += ld_relaxed_sys(mine + mb_ar_data(P, slot, r) + j);
+    buf[j] = s;
+  }
+  __syncthreads();
+}
+
+// What the last CTA does with the reduced vector out[0..kout):  out[0..k) are projection coefficients, out[k]
+// (if kout == k + 1) a squared norm.
+//   hsum_op : 0 none, 1 hsum[0..k) = out, 2 hsum[0..k) += out
+//   norm_op : 0 none
+//             1 scal[0] = out[k]                      (norm^2 that normalize_kernel divides by)
+//             2 scal[1] = out[k]                      (|w|^2 before the first projection, kept for the DGKS test)
+//             3 DGKS decision: second = !(out[k] >= 0.5 scal[1])  (|w'| < |w| / sqrt 2, also taken on NaN);
+//               *flag = second; if (!second) scal[0] = out[k] and hsum_op is NOT applied (the second
+//               projection is dropped as a whole); *passes_out = number of passes (read back by the host)
+struct OrthTail {
+  double *partial = nullptr;   // [gridDim.x][pstride]
+  int pstride = 0;
+  unsigned int *ticket = nullptr;   // nullptr: no tail (the caller reduces the partial rows itself)
+  double *out = nullptr;
+  double *hsum = nullptr;
+  double *scal = nullptr;
+  int *flag = nullptr;
+  double *passes_out = nullptr;     // norm_op 3: number of projection passes taken (1.0 or 2.0), for the host
+  const int *skip_flag = nullptr;   // kernel (and tail) do nothing when *skip_flag == 0 (DGKS: pass not needed)
+  int k = 0, kout = 0;
+  int hsum_op = 0, norm_op = 0;
+  int exchange = 0;                 // 1: all-reduce through the peer mailboxes inside the tail
+  PeerComm comm;
+};
+
+__device__ __forceinline__ void orth_post_ops(const OrthTail &t) {
+  __shared__ int s_second;
+  if (threadIdx.x == 0) {
+    int second = 1;
+    if (t.norm_op == 1) t.scal[0] = t.out[t.k];
+    if (t.norm_op == 2) t.scal[1] = t.out[t.k];
+    if (t.norm_op == 3) {
+      const double n1 = t.out[t.k], n0 = t.scal[1];
+      second = !(n1 >= 0.5 * n0);
+      *t.flag = second;
+      if (!second) t.scal[0] = n1;
+      if (t.passes_out) *t.passes_out = second ? 2.0 : 1.0;
+    }
+    s_second = second;
+  }
+  __syncthreads();
+  if (t.hsum_op == 1)
+    for (int j = threadIdx.x; j < t.k; j += blockDim.x) t.hsum[j] = t.out[j];
+  if (t.hsum_op == 2 && s_second)
+    for (int j = threadIdx.x; j < t.k; j += blockDim.x) t.hsum[j] += t.out[j];
+}
+
+// Called by ALL threads of EVERY CTA after the CTA's partial row has been written with plain stores.
+__device__ __forceinline__ void orth_tail(const OrthTail &t) {
+  if (!t.ticket) return;
+  __shared__ unsigned int s_last;
+  __threadfence();                       // this CTA's partial row is visible device-wide before the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(t.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < t.kout; j += nw) {          // same summation order as reduce_partials_kernel
+    double s = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(t.partial + (size_t)b * t.pstride + j);
+    s = warp_reduce_sum(s);
+    if (lane == 0) t.out[j] = s;
+  }
+  if (threadIdx.x == 0) *t.ticket = 0;   // ready for the next launch (stream order)
+  __syncthreads();
+  if (t.exchange) p2p_allreduce_block(t.out, t.kout, t.comm);
+  if (t.comm.P > 1 && !t.exchange) return;   // NCCL transport: the host enqueues the all-reduce, then orth_post_kernel
+  orth_post_ops(t);
+}
+
+}  // namespace nsb

@@ -11,6 +11,19 @@ import numpy as np
 
 from .api import Sem, nek_dvector, k_normalize
 
+
+def hashed_field(glo: np.ndarray, component: int, seed: int = 0) -> np.ndarray:
+    """Pseudo-random values in [-1, 1) that depend only on the GLOBAL node id (splitmix64 finaliser): every
+    copy of a node gets the same value and the field does not depend on how the mesh is partitioned, so
+    runs on 1, 2, 4 and 8 ranks start from the same Krylov seed (bench.py's parity block relies on it)."""
+    with np.errstate(over='ignore'):
+        z = glo.astype(np.uint64) * np.uint64(3) + np.uint64(component) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+
 # (fc1, fc2, fc3) per velocity component, core/utils.f90:321-329
 NOISE_FC = ((3.0e4, -1.5e3, 0.5e5), (2.3e4, 2.3e3, -2.0e5), (2.0e4, 1.0e3, 1.0e5))
 
@@ -44,7 +57,9 @@ def seed_noise(sem: Sem, vec: nek_dvector, coords, e0: int = 0, extra_fields=0) 
     fields = noise_fields(coords, e0)
     vec.upload(fields + [None] * extra_fields)
     for f in range(len(fields)):
-        sem.dssum(vec, f)
+        sem.dssum(vec, f)              # opdssum ; opcolv VMULT      (core/utils.f90:338-339)
         sem.col2(vec, f, 'vmult')
-        sem.col2(vec, f, 'mask')
+        sem.dssum(vec, f)              # dsavg = dssum ; col2 vmult  (:341-343)
+        sem.col2(vec, f, 'vmult')
+        sem.col2(vec, f, 'mask')       # bcdirVC                      (:346)
     return k_normalize(vec)

@@ -90,6 +90,47 @@ def main():
     Hall = [None] * world
     dist.all_gather_object(Hall, H)
     errs['H_replicated'] = max(float(np.max(np.abs(h - Hall[0]))) for h in Hall)
+    # replay of the captured steps (peer-memory transport: the whole step is a CUDA graph) gives the same bits
+    Q[0].upload([f[sl] for f in q0.f], q0.time)
+    Hr = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(Q, Hr, 1, K, K, op)
+    errs['H_replay'] = float(np.max(np.abs(Hr - H)))
+    # DGKS: the re-orthogonalisation decision is taken on every rank's device from the all-reduced norms --
+    # all ranks must take the same branch (otherwise the next collective hangs or H diverges)
+    Q[0].upload([f[sl] for f in q0.f], q0.time)
+    Hd = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(Q, Hd, 1, K, K, op, nb.ORTH_DGKS)
+    errs['dgks_H'] = rel(Hd, Ho)
+    Gd = Q.gram(K + 1)
+    errs['dgks_orth'] = float(np.max(np.abs(Gd - np.eye(K + 1))))
+    pall = [None] * world
+    dist.all_gather_object(pall, (Hd, nb.arnoldi_passes(Q, 1, K, nb.ORTH_DGKS)))
+    errs['dgks_replicated'] = max(float(np.max(np.abs(h - pall[0][0]))) + float(np.max(np.abs(p - pall[0][1])))
+                                  for h, p in pall)
+    # a second mesh on the same context (velocity + pressure mesh in Nek) with a DIFFERENT neighbour set:
+    # slabs handed out in a permuted order, lower order; both meshes exchange alternately
+    perm = [0, 2, 1, 3][:world] if world == 4 else list(range(world))[::-1]
+    P2 = BoxProblem(nel=nel, N=3, deform=0.02, nfields=1, beta=-1e-3, seed=5)
+    s0, s1 = nb.mesh.partition_range(P2.shape[0], perm[rank], world, granule=per)
+    sl2 = slice(s0, s1)
+    sem2 = nb.Sem(ctx, 3, *(a[sl2] for a in P2.coords), mask=P2.mask[sl2], glo_num=P2.glo[sl2])
+    sem2.setup_exchange()
+    lay2 = nb.Layout(ctx, [sem2.npts], [True])
+    B2 = nb.Basis(lay2, 1)
+    errs['two_meshes'] = 0.0
+    for it in range(3):
+        ua, ub = P.rng.standard_normal(P.shape), P2.rng.standard_normal(P2.shape)
+        Q[0].upload([ua[sl], ua[sl]])
+        B2[0].upload([ub[sl2]])
+        sem.dssum(Q[0], 0)
+        sem2.dssum(B2[0], 0)
+        if it == 1:
+            sem2.dssum(B2[0], 0)          # uneven call counts: the sequence numbers are per mesh
+            ub = osem.dssum(ub, P2.glo)
+        errs['two_meshes'] = max(errs['two_meshes'], rel(Q[0].download()[0][0], osem.dssum(ua, P.glo)[sl].ravel()),
+                                 rel(B2[0].download()[0][0], osem.dssum(ub, P2.glo)[sl2].ravel()))
+    B2.close()
+    sem2.close()
     # Helmholtz solves side by side: interface exchange inside every iteration, CG scalars all-reduced
     rhs = [osem.dssum(P.bm1 * P.random_field(), P.glo) * P.mask for _ in range(nc)]
     Q[0].upload([r[sl] for r in rhs])
@@ -116,7 +157,8 @@ def main():
     step.close()
     Bv.close()
     tol = dict(binvm1=1e-12, vmult=0, dssum=1e-13, ax=1e-12, dot=1e-12, arnoldi_H=1e-10, arnoldi_Q=1e-9,
-               orth=1e-10, H_replicated=0, hmholtz=1e-8, stepper=1e-9)
+               orth=1e-10, H_replicated=0, hmholtz=1e-8, stepper=1e-9, H_replay=0, dgks_H=1e-10, dgks_orth=1e-10,
+               dgks_replicated=0, two_meshes=1e-13)
     bad = {k: v for k, v in errs.items() if not (v <= tol[k])}
     print(f'[rank {rank}/{world}] ' + ' '.join(f'{k}={v:.2e}' for k, v in errs.items()), flush=True)
     op.close()

@@ -48,6 +48,51 @@ def test_arnoldi_factorization(ctx, conv, mode):
     assert np.max(np.abs(lhs.f[0].ravel() - rhs)) < 1e-10
 
 
+def test_arnoldi_graph_replay_and_switches(ctx, monkeypatch):
+    """The device-resident loop replays captured CUDA graphs from the second factorisation on: bit-identical H,
+    launch counter advanced as if launched one by one; DGKS passes come back per step; the NSB_GRAPH=0 /
+    NSB_TAIL=0 launch structures (separate reduce / add launches) give the same bits."""
+    import nekstab_next_b200 as nb
+    K = 60
+    P = BoxProblem(nel=(3, 3, 3), N=7, deform=0.05, nfields=3, conv=True, seed=77)
+    q0 = P.random_kvec()
+    okr.k_normalize(P.octx(), q0)
+    Hs = {}
+    for tag, env in (('graph', {}), ('plain', {'NSB_GRAPH': '0'}), ('legacy', {'NSB_GRAPH': '0', 'NSB_TAIL': '0'}),
+                     ('twobarrier', {'NSB_FUSED_ALLWARPS': '0'})):
+        for kk, vv in env.items():
+            monkeypatch.setenv(kk, vv)
+        c2 = nb.Context(device=0)
+        lay, B, S, op = P.gpu(c2, K + 1)
+        runs = []
+        for rep in range(3):
+            upload(B[0], q0)
+            H = np.zeros((K + 1, K), order='F')
+            l0 = c2.launch_count()
+            nb.arnoldi_factorization(B, H, 1, K, K, op)
+            runs.append((H, c2.launch_count() - l0))
+        assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[1][0], runs[2][0])
+        assert runs[0][1] == runs[1][1] == runs[2][1] > 0
+        Hs[tag] = runs[0][0]
+        if tag == 'graph':
+            upload(B[0], q0)
+            Hd = np.zeros((K + 1, K), order='F')
+            nb.arnoldi_factorization(B, Hd, 1, K, K, op, nb.ORTH_DGKS)
+            passes = nb.arnoldi_passes(B, 1, K, nb.ORTH_DGKS)
+            assert passes.shape == (K,) and set(np.unique(passes)) <= {1, 2}
+            assert relerr(Hd[:12, :10], H[:12, :10]) <= 1e-11 and relerr(Hd, H) <= 1e-7
+            G = B.gram(K + 1)
+            assert np.max(np.abs(G - np.eye(K + 1))) < 1e-10
+        for o in (op, S, B, lay, c2):
+            o.close()
+        for kk in env:
+            monkeypatch.delenv(kk)
+    assert np.array_equal(Hs['graph'], Hs['plain'])
+    assert np.array_equal(Hs['graph'], Hs['legacy'])
+    assert relerr(Hs['twobarrier'][:12, :10], Hs['graph'][:12, :10]) <= 1e-13   # same arithmetic up to the row-sum order
+    assert relerr(Hs['twobarrier'], Hs['graph']) <= 1e-8
+
+
 def test_arnoldi_host_operator(ctx):
     """The drop-in case: the operator is the host's time-stepper, vectors cross PCIe each step."""
     import nekstab_next_b200 as nb

@@ -64,6 +64,41 @@ def test_orthonormalize_matches_mgs2(ctx, k, mode):
         o.close()
 
 
+@pytest.mark.parametrize('k', [5, 40, 70, 230, 500])
+def test_dgks_single_pass_when_no_cancellation(ctx, k):
+    """A vector with no large component in span(V): |w'| >= |w| / sqrt 2, the device-side test drops the second
+    projection (passes == 1), H = h1, and the third sweep exits at its first instruction."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, pressure=True, time_in_dot=True, seed=100 + k)
+    c = P.octx()
+    lay, B, semg, op = P.gpu(ctx, k + 1)
+    Q = build_basis(P, c, k)
+    f = P.random_kvec()
+    for i, q in enumerate(Q):
+        upload(B[i], q)
+    upload(B[k], f)
+    n0 = okr.k_norm(c, f)
+    H = np.zeros((k + 1, k))
+    fref = f.copy()
+    okr.update_hessenberg_matrix(c, H, fref, Q, k)          # two passes; the second only moves rounding errors
+    assert H[k, k - 1] >= n0 / np.sqrt(2) * 1.05, 'test premise: little cancellation'
+    h, passes = nb.orthonormalize(B, k, k, nb.ORTH_DGKS)
+    assert passes == 1
+    assert np.max(np.abs(h - H[:, k - 1])) <= 1e-12 * np.linalg.norm(H[:, k - 1])
+    # and the basis is still orthonormal to the north-star bound after ONE projection
+    G = B.gram(k + 1)
+    assert np.max(np.abs(G - np.eye(k + 1))) < 1e-10
+    # same vector, nearly dependent this time: two passes
+    f2 = P.random_kvec()
+    for q in Q[: max(1, k // 2)]:
+        okr.axpby(f2, 1.0, q, 50.0, skip_time=False)
+    upload(B[k], f2)
+    h2, passes2 = nb.orthonormalize(B, k, k, nb.ORTH_DGKS)
+    assert passes2 == 2
+    for o in (op, semg, B, lay):
+        o.close()
+
+
 def test_first_vector_only_normalises(ctx):
     import nekstab_next_b200 as nb
     P = BoxProblem(nel=(2, 2, 2), N=3, nfields=1, seed=2)

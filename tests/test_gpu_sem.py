@@ -79,6 +79,57 @@ def test_fused_operator_one_and_two_components_with_convection(ctx, nf):
         assert relerr(a, b.ravel()) <= TOL
 
 
+@pytest.mark.parametrize('nf', [1, 2])
+def test_fused_convective_operator_large_mesh(ctx, nf):
+    """axhelm3d_dmma8_kernel<1, conv> and <2, conv> on a 24^3-element mesh (7.1 M points): the ring protocol of
+    these instantiations (4 / 4 warp groups over 4 buffers) runs ~93 elements per CTA, i.e. dozens of mbarrier
+    phase flips per buffer -- the size at which the first ring protocol failed to launch."""
+    P = BoxProblem(nel=(24, 24, 24), N=7, deform=0.05, nfields=nf, conv=True, beta=-1e-4, seed=9)
+    lay, B, S, op = P.gpu(ctx, 2)
+    q = P.random_kvec()
+    upload(B[0], q)
+    op.matvec(B[0], B[1])
+    ref = P.omatvec(q)
+    got = download(B[1])
+    for a, b in zip(got.f, ref.f):
+        assert relerr(a, b.ravel()) <= TOL
+    for o in (op, S, B, lay):
+        o.close()
+
+
+def test_seed_noise_device_composition(ctx):
+    """op_add_noise (core/utils.f90:297-359): mth_rand noise -> opdssum -> opcolv VMULT -> dsavg -> bcdirVC,
+    the averaging and masking on the device, against the same composition of oracle pieces (independent dssum),
+    plus one value of mth_rand worked out by hand from the formula at :412-414."""
+    import nekstab_next_b200 as nb
+    from oracle import krylov as okr
+    P = BoxProblem(nel=(3, 2, 2), N=5, deform=0.03, nfields=3, seed=12)
+    lay, B, S, op = P.gpu(ctx, 1)
+    nrm = nb.seed.seed_noise(S, B[0], P.coords, e0=0)
+    raw = nb.seed.noise_fields(P.coords, 0)
+    ref = []
+    for c in range(3):
+        v = osem.dssum(raw[c], P.glo) * P.vmult
+        v = osem.dssum(v, P.glo) * P.vmult
+        ref.append(v * P.mask)
+    kv = okr.KVec(ref, 0.0)
+    nref = okr.k_normalize(P.octx(), kv)
+    assert abs(nrm - nref) <= 1e-12 * nref
+    got = download(B[0])
+    for a, b in zip(got.f, kv.f):
+        assert relerr(a, b.ravel()) <= 1e-12
+    # hand-evaluated: element 1, local point (2,1,1) -> ix=2, iy=1, iz=1, ieg=1
+    import math
+    x, y, z = (a[0, 0, 0, 1] for a in P.coords)
+    fc = (3.0e4, -1.5e3, 0.5e5)
+    r = fc[0] * (1 + x * math.sin(y)) + fc[1] * 2 * 1 + fc[2] * 2
+    r = fc[0] * (1 + z * math.sin(r)) + fc[1] * 1 * 2 + fc[2] * 1
+    r = math.cos(1.0e3 * math.sin(1.0e3 * math.sin(r)))
+    assert abs(raw[0][0, 0, 0, 1] - r) <= 1e-9       # cos/sin of arguments ~1e5: last digits depend on libm
+    for o in (op, S, B, lay):
+        o.close()
+
+
 @pytest.mark.parametrize('name', ['cyl', 'bfs'])
 def test_reference_meshes(ctx, name):
     """Config 1: the reference's own curved 2-D meshes (examples/cylinder, examples/back_fstep)."""
