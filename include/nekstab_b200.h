@@ -171,6 +171,12 @@ int nsb_vec_normalize(nsb_basis_t b, int col, double *alpha);
 #define NSB_ORTH_MGS2_REF 0
 #define NSB_ORTH_CGS2 1
 #define NSB_ORTH_DGKS 2
+/* Threshold of the DGKS test, 0 < eta < 1 (default 1/sqrt 2, Daniel-Gragg-Kaufman-Stewart): the second
+ * projection is taken when ||w'|| < eta ||w||.  One classical Gram-Schmidt pass against a basis that is
+ * orthonormal to rounding leaves an orthogonality error of O(eps / eta), so smaller values (0.1) still meet
+ * the 1e-10 bound while operators of the form I - tau L -- whose Krylov vectors always lose more than
+ * 1 - 1/sqrt 2 of their norm in the projection -- take one pass instead of two. */
+int nsb_set_dgks_eta(nsb_context_t ctx, double eta);
 int nsb_orthonormalize(nsb_basis_t b, int k, int col_w, int mode, double *h, int *passes);
 /* Asynchronous variant: h stays on the device until nsb_sync / the next synchronising call;
  * h_pinned must be memory from nsb_host_alloc with room for k + 2 doubles (h[0..k], and for NSB_ORTH_DGKS

@@ -59,6 +59,7 @@ PROTOTYPES = {
     'nsb_vec_dot': (C.c_int, [H, C.c_int, H, C.c_int, c_double_p]),
     'nsb_vec_norm': (C.c_int, [H, C.c_int, c_double_p]),
     'nsb_vec_normalize': (C.c_int, [H, C.c_int, c_double_p]),
+    'nsb_set_dgks_eta': (C.c_int, [H, C.c_double]),
     'nsb_orthonormalize': (C.c_int, [H, C.c_int, C.c_int, C.c_int, c_double_p, c_int_p]),
     'nsb_orthonormalize_async': (C.c_int, [H, C.c_int, C.c_int, C.c_int, c_double_p]),
     'nsb_host_alloc': (C.c_int, [c_void_pp, C.c_int64]),

@@ -103,6 +103,10 @@ class Context:
     def sync(self):
         check(self.lib.nsb_sync(self.h))
 
+    def set_dgks_eta(self, eta: float):
+        """DGKS threshold: second projection when |w'| < eta |w| (default 1/sqrt 2)."""
+        check(self.lib.nsb_set_dgks_eta(self.h, float(eta)))
+
     def launch_count(self) -> int:
         n = C.c_int64()
         check(self.lib.nsb_launch_count(self.h, C.byref(n)))

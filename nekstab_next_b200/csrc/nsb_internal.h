@@ -97,6 +97,7 @@ struct nsb_context_s {
   int ax_stages = 0;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernels (0: default; DMMA: = warp groups pins one buffer per group)
   bool fused_priv = true;      // NSB_FUSED_PRIV=0: per-block warp reduction in the fused kernel's second projection
   bool fused_allwarps = true;  // NSB_FUSED_ALLWARPS=0: warp 0 alone combines the row sums (two barriers per block)
+  double dgks_eta2 = 0.5;      // DGKS: second projection when |w'|^2 < eta^2 |w|^2 (nsb_set_dgks_eta; default eta = 1/sqrt 2)
   bool tail = true;            // NSB_TAIL=0: separate reduce / all-reduce / add launches (round-1 structure)
   bool ax_dmma = true;         // NSB_AX_DMMA=0: vector-FMA contraction in the ring kernel instead of DMMA
   bool ax_ring = true;         // NSB_AX_RING=0: warp-per-element kernel instead of the TMA ring (N = 7)

@@ -181,15 +181,25 @@ update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__r
         a3 = fma(vb[jj].y, hj, a3);
       }
     }
-    for (; j0 < k; ++j0) {
-      const double *p = vp + (int64_t)j0 * ld;
-      double2 a = ld_stream(reinterpret_cast<const double2 *>(p));
-      double2 b = ld_stream(reinterpret_cast<const double2 *>(p + 512));
-      const double hj = hS[j0];
-      a0 = fma(a.x, hj, a0);
-      a1 = fma(a.y, hj, a1);
-      a2 = fma(b.x, hj, a2);
-      a3 = fma(b.y, hj, a3);
+    if (j0 < k) {  // tail tile: all remaining columns requested at once (guarded), like the full tiles
+      double2 va[KT], vb[KT];
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj) {
+        va[jj] = vb[jj] = make_double2(0.0, 0.0);
+        if (j0 + jj < k) {
+          const double *p = vp + (int64_t)(j0 + jj) * ld;
+          va[jj] = ld_stream(reinterpret_cast<const double2 *>(p));
+          vb[jj] = ld_stream(reinterpret_cast<const double2 *>(p + 512));
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < KT; ++jj) {
+        const double hj = (j0 + jj < k) ? hS[j0 + jj] : 0.0;
+        a0 = fma(va[jj].x, hj, a0);
+        a1 = fma(va[jj].y, hj, a1);
+        a2 = fma(vb[jj].x, hj, a2);
+        a3 = fma(vb[jj].y, hj, a3);
+      }
     }
     if (MODE == 0) {
       wa.x -= a0; wa.y -= a1; wb.x -= a2; wb.y -= a3;
@@ -879,6 +889,7 @@ OrthTail make_tail(nsb_context_t ctx, const TailSpec &sp, int k, int kout, int p
   t.kout = kout;
   t.hsum_op = sp.hsum_op;
   t.norm_op = sp.norm_op;
+  t.eta2 = ctx->dgks_eta2;
   t.comm.P = ctx->nranks;
   t.comm.rank = ctx->rank;
   t.comm.seq = ctx->seq_d;
@@ -1310,6 +1321,13 @@ extern "C" int nsb_orthonormalize(nsb_basis_t B, int k, int col_w, int mode, dou
       set_error("NaN detected in dot product");
       return NSB_ENAN;
     }
+  return NSB_OK;
+}
+
+extern "C" int nsb_set_dgks_eta(nsb_context_t ctx, double eta) {
+  NSB_REQUIRE(ctx && eta > 0.0 && eta < 1.0, "nsb_set_dgks_eta: eta must lie in (0, 1)");
+  ctx->dgks_eta2 = eta * eta;
+  clear_step_graphs(ctx);   // the threshold is a kernel argument of the captured steps
   return NSB_OK;
 }
 

@@ -106,7 +106,8 @@ __device__ __forceinline__ void p2p_allreduce_block(double *buf, int n, const Pe
 //   norm_op : 0 none
 //             1 scal[0] = out[k]                      (norm^2 that normalize_kernel divides by)
 //             2 scal[1] = out[k]                      (|w|^2 before the first projection, kept for the DGKS test)
-//             3 DGKS decision: second = !(out[k] >= 0.5 scal[1])  (|w'| < |w| / sqrt 2, also taken on NaN);
+//             3 DGKS decision: second = !(out[k] >= eta^2 scal[1])  (|w'| < eta |w|, eta = 1/sqrt 2 by default;
+//               also taken on NaN);
 //               *flag = second; if (!second) scal[0] = out[k] and hsum_op is NOT applied (the second
 //               projection is dropped as a whole); *passes_out = number of passes (read back by the host)
 struct OrthTail {
@@ -122,6 +123,7 @@ struct OrthTail {
   int k = 0, kout = 0;
   int hsum_op = 0, norm_op = 0;
   int exchange = 0;                 // 1: all-reduce through the peer mailboxes inside the tail
+  double eta2 = 0.5;                // DGKS threshold eta^2 (|w'|^2 >= eta^2 |w|^2: one pass is enough)
   PeerComm comm;
 };
 
@@ -133,7 +135,7 @@ __device__ __forceinline__ void orth_post_ops(const OrthTail &t) {
     if (t.norm_op == 2) t.scal[1] = t.out[t.k];
     if (t.norm_op == 3) {
       const double n1 = t.out[t.k], n0 = t.scal[1];
-      second = !(n1 >= 0.5 * n0);
+      second = !(n1 >= t.eta2 * n0);
       *t.flag = second;
       if (!second) t.scal[0] = n1;
       if (t.passes_out) *t.passes_out = second ? 2.0 : 1.0;

@@ -74,6 +74,10 @@ def test_dgks_single_pass_when_no_cancellation(ctx, k):
     lay, B, semg, op = P.gpu(ctx, k + 1)
     Q = build_basis(P, c, k)
     f = P.random_kvec()
+    for _ in range(2):                      # f orthogonal to the basis, then a modest component back in
+        for q in Q:
+            okr.axpby(f, 1.0, q, -okr.k_dot(c, f, q), skip_time=False)
+    okr.axpby(f, 1.0, Q[0], 0.3 * okr.k_norm(c, f), skip_time=False)
     for i, q in enumerate(Q):
         upload(B[i], q)
     upload(B[k], f)
@@ -95,6 +99,12 @@ def test_dgks_single_pass_when_no_cancellation(ctx, k):
     upload(B[k], f2)
     h2, passes2 = nb.orthonormalize(B, k, k, nb.ORTH_DGKS)
     assert passes2 == 2
+    # the threshold is a context setting: with eta = 1e-4 the same vector needs one pass only
+    ctx.set_dgks_eta(1e-4)
+    upload(B[k], f2)
+    h3, passes3 = nb.orthonormalize(B, k, k, nb.ORTH_DGKS)
+    ctx.set_dgks_eta(1.0 / np.sqrt(2.0))
+    assert passes3 == 1 and np.max(np.abs(h3 - h2)) <= 1e-9 * np.linalg.norm(h2)
     for o in (op, semg, B, lay):
         o.close()
 
