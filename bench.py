@@ -436,6 +436,14 @@ def run_native(a):
         op.matvec(Q[i % K], Q[K])
     mv_ms = maxall(ctx.timer_stop()) / nmv
     matvec_gdofs = ndof / (mv_ms * 1e-3) / 1e9
+    # whole `ax` (axhelm + dssum + mask + binvm1) against its algorithmic minimum: u and w of every component,
+    # G1..G6, bm1 and bmask once per point
+    pk, _ = peaks()
+    mv_alg = 8.0 * (2 * nc + 8) * (ndof / nc)
+    matvec_roofline = dict(algorithmic_bytes=mv_alg, achieved_gbs=mv_alg / (mv_ms * 1e-3) / 1e9,
+                           frac=mv_alg / (mv_ms * 1e-3) / 1e9 / (pk * world),
+                           structure='axhelm of element slab s+1 overlapped with the L2-resident gather-scatter of slab s'
+                           if os.environ.get('NSB_AX_SLAB_MB', '48') not in ('0', '0.0') else 'one axhelm + one gather-scatter launch')
 
     # ---- per-kernel device times for the roofline (same factorisation, events around launches) --
     Q[0].download()  # keeps column 0 intact; nothing to do, just a sync point
@@ -531,7 +539,7 @@ def run_native(a):
                                 collectives=('NVLink peer-memory kernels (one-shot all-reduce, halo stores)' if p2p
                                              else 'NCCL' if world > 1 else 'none')),
                     arnoldi_ms_per_step=ms / a.steps / K, matvec_gdof_per_s=matvec_gdofs,
-                    matvec_ms=mv_ms, roofline=roofline, clocks=clocks, gpu_launches=int(launches),
+                    matvec_ms=mv_ms, matvec_roofline=matvec_roofline, roofline=roofline, clocks=clocks, gpu_launches=int(launches),
                     parity=parity, build_id=nb.build_id(),
                     build_mode='in-tree nvcc -gencode arch=compute_100a,code=sm_100a; content hash of csrc/ + '
                                'include/ embedded in the binary (nsb_build_id) and compared by build.stale()',

@@ -306,6 +306,7 @@ int exchange_setup(nsb_sem_t S) {
   const int64_t nloc = plan.n_local;
   // 4. reorder the gather-scatter lists accordingly
   std::vector<int64_t> off2(S->nshared + 1), gid2(S->nshared), inv(S->nshared);
+  std::vector<int32_t> slab2(S->node_slab.size());
   for (int64_t n = 0; n < S->nshared; ++n) inv[newpos[n]] = n;
   std::vector<int32_t> idx2(S->gs_idx_h.size());
   int64_t q = 0;
@@ -314,12 +315,15 @@ int exchange_setup(nsb_sem_t S) {
     off2[m] = q;
     for (int64_t t = S->gs_off_h[n]; t < S->gs_off_h[n + 1]; ++t) idx2[q++] = S->gs_idx_h[t];
     gid2[m] = S->node_gid[n];
+    if (!slab2.empty()) slab2[m] = S->node_slab[n];
   }
   off2[S->nshared] = q;
   S->gs_off_h.swap(off2);
   S->gs_idx_h.swap(idx2);
   S->node_gid.swap(gid2);
+  S->node_slab.swap(slab2);
   S->n_local = nloc;
+  compute_slab_ends(S);
   NSB_CUDA(cudaMemcpy(S->gs_off_d, S->gs_off_h.data(), sizeof(int64_t) * (S->nshared + 1), cudaMemcpyHostToDevice));
   NSB_CUDA(cudaMemcpy(S->gs_idx_d, S->gs_idx_h.data(), sizeof(int32_t) * S->gs_idx_h.size(), cudaMemcpyHostToDevice));
   const int64_t nifc = S->nshared - nloc;

@@ -164,6 +164,8 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   if (const char *e = getenv("NSB_GRAPH")) ctx->use_graph = e[0] != '0';
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  NSB_CUDA(cudaStreamCreateWithFlags(&ctx->gs_stream, cudaStreamNonBlocking));
+  if (const char *e = getenv("NSB_AX_SLAB_MB")) ctx->ax_slab_mb = atof(e);
   NSB_CUDA(cudaEventCreate(&ctx->ev0));
   NSB_CUDA(cudaEventCreate(&ctx->ev1));
   NSB_CUDA(cudaMalloc(&ctx->hvec_d, sizeof(double) * 4 * (kMaxK + 8)));
@@ -213,6 +215,7 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->gs_stream);
   delete ctx;
   return NSB_OK;
 }

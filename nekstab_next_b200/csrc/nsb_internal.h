@@ -49,6 +49,8 @@ struct nsb_context_s {
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t gs_stream = nullptr;    // gather-scatter of finished slabs, concurrent with the next slab's axhelm
+  double ax_slab_mb = 48.0;            // NSB_AX_SLAB_MB: u + w of one slab (3 fields) in MB; 0 = no slab pipeline
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   int num_sms = nsb::kNumSM;
@@ -138,6 +140,17 @@ struct nsb_sem_s {
   double *bm1_d = nullptr, *jac_d = nullptr, *binv_d = nullptr, *vmult_d = nullptr,
          *mask_d = nullptr, *bmask_d = nullptr;  // bmask = binvm1 * mask
   double *rst_d = nullptr;       // [dim*dim][npts] rx..tz (times jac), for the convective term
+  // element range of the axhelm launch in flight (launch_axhelm sets them; slab pipeline of the fused operator)
+  const double *ax_g = nullptr, *ax_bm1 = nullptr, *ax_bmask = nullptr;
+  int64_t ax_nel = 0;
+  // slab pipeline: elements [slab_e0[s], slab_e0[s+1]) ; private gather-scatter nodes whose LAST copy lies in
+  // slab s are [slab_node_end[s-1], slab_node_end[s]) -- their gather-scatter runs right after that slab's
+  // axhelm, while w and u of the slab are still in L2
+  int nslab = 1;
+  std::vector<int64_t> slab_e0, slab_node_end;
+  std::vector<int32_t> node_slab;        // slab of the last copy of every gs node
+  std::vector<cudaEvent_t> slab_ev;
+  cudaEvent_t ev_c = nullptr;
   double *D_d = nullptr;         // (N+1)^2, D[i + lx*j] = dxm1(i,j)
   std::vector<double> D_h, z_h, w_h;
   // gather-scatter: unique nodes owning >= 1 element-boundary point, CSR
@@ -222,7 +235,9 @@ int exchange_setup(nsb_sem_t sem);
 int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st);  // pack -> peer stores -> flags -> wait -> add
 // host-only plans (also reachable through nsb_host_gs_plan / nsb_host_exchange_plan for CPU tests)
 int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
-            std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult);
+            std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult,
+            int64_t slab_elems = 0, std::vector<int32_t> *node_slab = nullptr);
+void compute_slab_ends(nsb_sem_t S);
 struct ExchangePlan {
   std::vector<int64_t> newpos;                   // node -> position after the private/interface reorder
   int64_t n_local = 0;                           // private nodes

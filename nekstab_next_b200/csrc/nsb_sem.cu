@@ -617,7 +617,7 @@ __global__ void __launch_bounds__((NF * Dmma8Cfg<NF, CONV>::NG + 1) * 32, 1)
 axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
                       const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
                       const double *__restrict__ cv, double alpha, double beta,
-                      const double *__restrict__ bmask, int64_t fstride) {
+                      const double *__restrict__ bmask, int64_t fstride, int geo_evict_first) {
   using Cfg = Dmma8Cfg<NF, CONV>;
   constexpr int LX = 8, N2 = 64, N3 = 512, NG = Cfg::NG, NCW = NF * NG, PLANE = Cfg::PLANE;
   constexpr int NARR = Cfg::NARR;
@@ -641,6 +641,10 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
 
   if (wp == NCW) {
     // ===== producer warp: one lane per array =====
+    // slab pipeline: G, bm1, bmask and C are streamed once -> evict_first, so that u and w of the slab stay in
+    // L2 for the gather-scatter that follows on the second stream
+    const bool hint = geo_evict_first && lane < (CONV ? 11 : 8);
+    const uint64_t pol = l2_policy_evict_first();
     for (int64_t it = 0; it < nit; ++it) {
       const int s = (int)(it % NBUF);
       const uint32_t ph = (uint32_t)((it / NBUF) & 1);
@@ -656,7 +660,8 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
         else if (lane == 7) src = bmask + e * N3;
         else if (CONV && lane < 11) src = cv + (int64_t)(lane - 8) * npts + e * N3;
         else src = u + (int64_t)(lane - (CONV ? 11 : 8)) * fstride + e * N3;
-        tma_bulk_g2s(dst + lane * N3, src, N3 * sizeof(double), full + s);
+        if (hint) tma_bulk_g2s_hint(dst + lane * N3, src, N3 * sizeof(double), full + s, pol);
+        else tma_bulk_g2s(dst + lane * N3, src, N3 * sizeof(double), full + s);
       }
     }
     return;
@@ -802,8 +807,8 @@ int launch_ring8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, dou
   static_assert(smem <= 227 * 1024, "axhelm ring does not fit in shared memory");
   auto kfn = axhelm3d_ring8_kernel<NF, CONV, EPI, NSTAGE>;
   NSB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t grid = S->nel < S->ctx->num_sms ? S->nel : S->ctx->num_sms;
-  kfn<<<(unsigned)grid, (NF * NSTAGE + 1) * 32, smem, S->ctx->stream>>>(u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1,
+  const int64_t grid = S->ax_nel < S->ctx->num_sms ? S->ax_nel : S->ctx->num_sms;
+  kfn<<<(unsigned)grid, (NF * NSTAGE + 1) * 32, smem, S->ctx->stream>>>(u, w, S->ax_g, S->ax_bm1, S->ax_nel, S->npts, h1,
                                                                        h2, cv, alpha, beta, bmask, fstride);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
@@ -818,9 +823,10 @@ int launch_dmma8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, dou
   static_assert(smem <= 227 * 1024, "axhelm dmma ring does not fit in shared memory");
   auto kfn = axhelm3d_dmma8_kernel<NF, CONV, EPI, NBUF>;
   NSB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t grid = S->nel < S->ctx->num_sms ? S->nel : S->ctx->num_sms;
-  kfn<<<(unsigned)grid, (NF * Cfg::NG + 1) * 32, smem, S->ctx->stream>>>(u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1,
-                                                                       h2, cv, alpha, beta, bmask, fstride);
+  const int64_t grid = S->ax_nel < S->ctx->num_sms ? S->ax_nel : S->ctx->num_sms;
+  kfn<<<(unsigned)grid, (NF * Cfg::NG + 1) * 32, smem, S->ctx->stream>>>(u, w, S->ax_g, S->ax_bm1, S->ax_nel, S->npts, h1,
+                                                                       h2, cv, alpha, beta, bmask, fstride,
+                                                                       S->nslab > 1 && S->ax_nel < S->nel ? 1 : 0);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -1019,9 +1025,9 @@ template <int LX, bool CONV, int EPI>
 void launch_ax3d_t(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
                    const double *cv, double alpha, double beta, const double *bmask) {
   constexpr int EPC = (256 / (LX * LX) > 0 ? 256 / (LX * LX) : 1);
-  const int64_t grid = (S->nel + EPC - 1) / EPC;
+  const int64_t grid = (S->ax_nel + EPC - 1) / EPC;
   axhelm3d_kernel<LX, CONV, EPI><<<dim3((unsigned)grid, nf), EPC * LX * LX, 0, S->ctx->stream>>>(
-      u, w, S->g_d, S->bm1_d, S->D_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
+      u, w, S->ax_g, S->ax_bm1, S->D_d, S->ax_nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
 }
 
 template <bool CONV, int EPI>
@@ -1029,15 +1035,15 @@ int launch_ax3d(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride
                 const double *cv, double alpha, double beta, const double *bmask) {
   if (S->lx == 8 && !S->ctx->ax_generic && S->ctx->ax_ring && nf <= 3) {
     // bmask / bm1 are staged unconditionally: hand the kernel valid arrays even when unused
-    const double *bmk = bmask ? bmask : S->bmask_d;
+    const double *bmk = bmask ? bmask : S->ax_bmask;
     if (nf == 3) return launch_ring8<3, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmk);
     if (nf == 2) return launch_ring8<2, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmk);
     return launch_ring8<1, CONV, EPI>(S, u, w, fstride, h1, h2, cv, alpha, beta, bmk);
   }
   if (S->lx == 8 && !S->ctx->ax_generic) {
-    const int64_t grid = (S->nel + 3) / 4;
+    const int64_t grid = (S->ax_nel + 3) / 4;
     axhelm3d_warp8_kernel<CONV, EPI><<<dim3((unsigned)grid, nf), 128, 0, S->ctx->stream>>>(
-        u, w, S->g_d, S->bm1_d, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
+        u, w, S->ax_g, S->ax_bm1, S->ax_nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
     S->ctx->launches++;
     NSB_CUDA(cudaGetLastError());
     return NSB_OK;
@@ -1059,8 +1065,8 @@ template <bool CONV, int EPI>
 int launch_ax2d(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
                 const double *cv, double alpha, double beta, const double *bmask) {
   const int n2 = S->lx * S->lx;
-  axhelm2d_kernel<CONV, EPI><<<dim3((unsigned)S->nel, nf), n2, sizeof(double) * 4 * n2, S->ctx->stream>>>(
-      u, w, S->g_d, S->bm1_d, S->D_d, S->lx, S->nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
+  axhelm2d_kernel<CONV, EPI><<<dim3((unsigned)S->ax_nel, nf), n2, sizeof(double) * 4 * n2, S->ctx->stream>>>(
+      u, w, S->ax_g, S->ax_bm1, S->D_d, S->lx, S->ax_nel, S->npts, h1, h2, cv, alpha, beta, bmask, fstride);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -1068,8 +1074,20 @@ int launch_ax2d(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride
 
 // axhelm on nf fields that sit fstride doubles apart (velocity components of one column)
 int launch_axhelm(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
-                  const double *cv, int epi, double alpha, double beta, const double *bmask) {
+                  const double *cv, int epi, double alpha, double beta, const double *bmask, int64_t e0 = 0,
+                  int64_t ne = -1) {
   cudaSetDevice(S->ctx->device);
+  // element range [e0, e0 + ne) of this launch (the slab pipeline of the fused operator; default: all)
+  if (ne < 0) ne = S->nel - e0;
+  const int64_t nloc = S->npts / S->nel, sh = e0 * nloc;
+  u += sh;
+  w += sh;
+  if (cv) cv += sh;
+  if (bmask) bmask += sh;
+  S->ax_g = S->g_d + sh;
+  S->ax_bm1 = S->bm1_d + sh;
+  S->ax_bmask = S->bmask_d + sh;
+  S->ax_nel = ne;
   // algorithmic bytes per point: u, w, G1..G6 (G1,G2,G4 in 2-D), bm1 if h2 != 0, C if convecting,
   // bmask on element-interior points of the fused epilogue
   const double fint = std::pow((double)(S->lx - 2) / S->lx, S->dim);
@@ -1080,7 +1098,7 @@ int launch_axhelm(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstri
   const bool shared_geo = S->dim == 3 && S->lx == 8 && !S->ctx->ax_generic && S->ctx->ax_ring && nf <= 3;
   const double geo = 8.0 * (S->ng + (h2 != 0.0 ? 1 : 0) + (cv ? S->dim : 0) + (epi ? fint : 0.0));
   const double per_pt = shared_geo ? geo + 16.0 * nf : (geo + 16.0) * nf;
-  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)S->npts);
+  ProfScope ps(S->ctx, PC_AXHELM, per_pt * (double)(ne * nloc));
   if (S->dim == 3) {
     if (cv) return epi ? launch_ax3d<true, 1>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask)
                        : launch_ax3d<true, 0>(S, u, w, nf, fstride, h1, h2, cv, alpha, beta, bmask);
@@ -1161,6 +1179,63 @@ int launch_gs(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const do
   return NSB_OK;
 }
 
+// Fused operator w = alpha u + beta bmask QQ^T (h1 A + h2 B [+ C.grad]) u in element slabs: the axhelm of slab
+// s + 1 (main stream, DRAM-bound) runs while the gather-scatter of the nodes completed by slab s works out of
+// L2 on a second stream -- w and u of a slab are read and re-written by the gather-scatter before they leave
+// the cache, instead of crossing HBM a second time (ncu, round 1: 0.91 GB read + 0.36 GB written by gs_kernel
+// on top of the 1.86 GB of axhelm).  Interface nodes (multi-rank) take the exchange path after the last slab.
+int launch_ax_gs_pipelined(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                           const double *cv, double alpha, double beta) {
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  const double *bmask = S->bmask_d;
+  const bool multi = ctx->nranks > 1 && (S->nshared - S->n_local) > 0 && !S->peers.empty();
+  if (ctx->nranks > 1 && !S->exchange_ready) {
+    set_error("dssum: nsb_sem_setup_exchange has not been called on this multi-rank context");
+    return NSB_EINVAL;
+  }
+  for (int q = 0; q < S->nslab; ++q) {
+    const int64_t e0 = S->slab_e0[q], ne = S->slab_e0[q + 1] - e0;
+    NSB_CHECK(launch_axhelm(S, u, w, nf, fstride, h1, h2, cv, 1, alpha, beta, bmask, e0, ne));
+    const int64_t n0 = q ? S->slab_node_end[q - 1] : 0, n1 = S->slab_node_end[q];
+    if (n1 > n0) {
+      NSB_CUDA(cudaEventRecord(S->slab_ev[q], ctx->stream));
+      NSB_CUDA(cudaStreamWaitEvent(ctx->gs_stream, S->slab_ev[q], 0));
+      gs_launch<1>(S, ctx->gs_stream, w, n0, n1, nf, fstride, u, alpha, beta, bmask, nullptr, 0);
+    }
+  }
+  NSB_CUDA(cudaEventRecord(S->ev_c, ctx->gs_stream));
+  if (multi) {
+    NSB_REQUIRE(nf <= S->ns_fields, "dssum: %d fields in one call, interface buffers hold %d", nf, S->ns_fields);
+    const int64_t nloc = S->n_local, nifc = S->nshared - S->n_local;
+    cudaStream_t s2 = ctx->copy_stream;
+    double *ns = S->node_sum_d;
+    NSB_CUDA(cudaEventRecord(S->ev_a, ctx->stream));
+    NSB_CUDA(cudaStreamWaitEvent(s2, S->ev_a, 0));
+    gs_launch<2>(S, s2, w, nloc, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, ns, nifc);
+    if (S->p2p_halo) {
+      NSB_CHECK(halo_exchange_p2p(S, nf, s2));
+    } else {
+      for (auto &P : S->peers) {
+        pack_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.send_d, nifc);
+        ctx->launches++;
+      }
+      NSB_CUDA(cudaGetLastError());
+      NSB_CHECK(sendrecv_d(ctx, S->peers, nf, s2));
+      for (auto &P : S->peers) {
+        unpack_add_kernel<<<dim3(blocks_for(P.n), nf), 256, 0, s2>>>(ns, P.idx_d, P.n, P.recv_d, nifc);
+        ctx->launches++;
+      }
+    }
+    gs_launch<4>(S, s2, w, nloc, S->nshared, nf, fstride, u, alpha, beta, bmask, ns, nifc);
+    NSB_CUDA(cudaEventRecord(S->ev_b, s2));
+    NSB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_b, 0));
+  }
+  NSB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_c, 0));
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 int field_ptr(nsb_sem_t S, nsb_basis_t B, int col, int field, double **out, const char *who) {
   NSB_REQUIRE(S && B, "%s: NULL argument", who);
   NSB_REQUIRE(col >= 0 && col < B->ncols, "%s: column %d out of range", who, col);
@@ -1179,7 +1254,8 @@ namespace nsb {
 // Host plan of the gather-scatter: unique nodes owning at least one element-boundary point, CSR,
 // ordered by first local index so neighbouring threads touch neighbouring memory.
 int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
-            std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult) {
+            std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult, int64_t slab_elems,
+            std::vector<int32_t> *node_slab) {
   int64_t nloc = 1;
   for (int a = 0; a < dim; ++a) nloc *= lx;
   const int64_t npts = nel * nloc;
@@ -1205,8 +1281,16 @@ int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *
   grp_start.push_back((int64_t)bpts.size());
   std::vector<int64_t> order(ngrp);
   std::iota(order.begin(), order.end(), 0);
-  std::sort(order.begin(), order.end(),
-            [&](int64_t a, int64_t b) { return bpts[grp_start[a]] < bpts[grp_start[b]]; });
+  // slab pipeline: nodes grouped by the element slab of their LAST copy (all copies of such a node have been
+  // written once that slab's axhelm is done), by first local index inside a group
+  auto slab_of = [&](int64_t g) -> int64_t {
+    return slab_elems > 0 ? (bpts[grp_start[g + 1] - 1] / nloc) / slab_elems : 0;
+  };
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    const int64_t sa = slab_of(a), sb = slab_of(b);
+    return sa != sb ? sa < sb : bpts[grp_start[a]] < bpts[grp_start[b]];
+  });
+  if (node_slab) node_slab->resize(ngrp);
   off.assign(ngrp + 1, 0);
   idx.resize(bpts.size());
   gid.resize(ngrp);
@@ -1226,9 +1310,22 @@ int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *
       }
     }
     gid[n] = glo_num[bpts[grp_start[gI]]];
+    if (node_slab) (*node_slab)[n] = (int32_t)slab_of(gI);
   }
   off[ngrp] = w0;
   return NSB_OK;
+}
+
+// slab_node_end[s] = number of PRIVATE nodes (the first n_local ones, slab-sorted) whose last copy lies in a
+// slab <= s
+void compute_slab_ends(nsb_sem_t S) {
+  S->slab_node_end.assign(S->nslab, 0);
+  if (S->nslab <= 1) {
+    if (S->nslab == 1) S->slab_node_end[0] = S->n_local;
+    return;
+  }
+  for (int64_t n = 0; n < S->n_local; ++n) S->slab_node_end[S->node_slab[n]]++;
+  for (int s = 1; s < S->nslab; ++s) S->slab_node_end[s] += S->slab_node_end[s - 1];
 }
 }  // namespace nsb
 
@@ -1317,11 +1414,35 @@ extern "C" int nsb_sem_create(nsb_context_t ctx, int dim, int N, int64_t nel, co
   std::vector<int64_t> off;
   std::vector<int32_t> idx;
   std::vector<double> vm;
-  NSB_CHECK(nsb::gs_plan(dim, lx, nel, glo_num, mask, off, idx, S->node_gid, &vm));
+  // slab pipeline of the fused operator: slabs sized so that u and w of three fields of one slab (and its share
+  // of the streamed geometric factors) stay in the 126 MB L2 until the slab's gather-scatter has run
+  S->nslab = 1;
+  int64_t slab_elems = 0;
+  if (ctx->ax_slab_mb > 0.0) {
+    const double per_elem = 6.0 * 8.0 * (double)nloc;   // u + w, three fields
+    int64_t want = (int64_t)(ctx->ax_slab_mb * 1e6 / per_elem);
+    want = std::max<int64_t>(want, 4 * (int64_t)ctx->num_sms);
+    const int64_t ns = (nel + want - 1) / want;
+    if (ns >= 2) {
+      S->nslab = (int)std::min<int64_t>(ns, 256);
+      slab_elems = (nel + S->nslab - 1) / S->nslab;
+      S->nslab = (int)((nel + slab_elems - 1) / slab_elems);
+    }
+  }
+  S->slab_e0.assign(S->nslab + 1, 0);
+  for (int q = 0; q <= S->nslab; ++q) S->slab_e0[q] = S->nslab == 1 ? (q ? nel : 0) : std::min<int64_t>(nel, q * slab_elems);
+  NSB_CHECK(nsb::gs_plan(dim, lx, nel, glo_num, mask, off, idx, S->node_gid, &vm, slab_elems, &S->node_slab));
   const int64_t ngrp = (int64_t)S->node_gid.size();
   const int64_t w0 = (int64_t)idx.size();
   S->nshared = ngrp;
   S->n_local = ngrp;
+  nsb::compute_slab_ends(S);
+  for (int q = 0; q < S->nslab; ++q) {
+    cudaEvent_t e;
+    NSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    S->slab_ev.push_back(e);
+  }
+  NSB_CUDA(cudaEventCreateWithFlags(&S->ev_c, cudaEventDisableTiming));
   S->gs_nnz = w0;
   S->gs_off_h = off;
   S->gs_idx_h = idx;
@@ -1389,6 +1510,7 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   cudaSetDevice(S->ctx->device);
   cudaStreamSynchronize(S->ctx->stream);
   cudaStreamSynchronize(S->ctx->copy_stream);
+  cudaStreamSynchronize(S->ctx->gs_stream);
   clear_step_graphs(S->ctx);
   if (S->halo_flag_off >= 0 && --S->ctx->halo_users <= 0) {   // last mesh gone: the halo area is free again
     S->ctx->halo_users = 0;
@@ -1413,6 +1535,8 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   if (S->pcg_d) cudaFree(S->pcg_d);
   if (S->ev_a) cudaEventDestroy(S->ev_a);
   if (S->ev_b) cudaEventDestroy(S->ev_b);
+  if (S->ev_c) cudaEventDestroy(S->ev_c);
+  for (auto e : S->slab_ev) cudaEventDestroy(e);
   delete S;
   return NSB_OK;
 }
@@ -1874,8 +1998,12 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
     }
     NSB_CHECK(field_ptr(S, bin, cin, f, &u, "nsb_op_apply"));
     NSB_CHECK(field_ptr(S, bout, cout, f, &w, "nsb_op_apply"));
-    NSB_CHECK(launch_axhelm(S, u, w, step, fstride, op->h1, op->h2, op->c_d, 1, op->alpha, op->beta, S->bmask_d));
-    NSB_CHECK(launch_gs(S, w, step, fstride, 1, u, op->alpha, op->beta, S->bmask_d));
+    if (S->nslab > 1 && !L->ctx->prof && S->nshared > 0) {
+      NSB_CHECK(launch_ax_gs_pipelined(S, u, w, step, fstride, op->h1, op->h2, op->c_d, op->alpha, op->beta));
+    } else {   // one slab, or per-kernel profiling (the roofline table keeps axhelm and gather-scatter apart)
+      NSB_CHECK(launch_axhelm(S, u, w, step, fstride, op->h1, op->h2, op->c_d, 1, op->alpha, op->beta, S->bmask_d));
+      NSB_CHECK(launch_gs(S, w, step, fstride, 1, u, op->alpha, op->beta, S->bmask_d));
+    }
   }
   // the rows outside the operator are carried through unchanged: %time and the remaining fields
   // (pressure, scalars)
