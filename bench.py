@@ -443,7 +443,7 @@ def run_native(a):
     matvec_roofline = dict(algorithmic_bytes=mv_alg, achieved_gbs=mv_alg / (mv_ms * 1e-3) / 1e9,
                            frac=mv_alg / (mv_ms * 1e-3) / 1e9 / (pk * world),
                            structure='axhelm of element slab s+1 overlapped with the L2-resident gather-scatter of slab s'
-                           if os.environ.get('NSB_AX_SLAB_MB', '48') not in ('0', '0.0') else 'one axhelm + one gather-scatter launch')
+                           if os.environ.get('NSB_AX_SLAB_MB', '0') not in ('0', '0.0') else 'one axhelm + one gather-scatter launch')
 
     # ---- per-kernel device times for the roofline (same factorisation, events around launches) --
     Q[0].download()  # keeps column 0 intact; nothing to do, just a sync point

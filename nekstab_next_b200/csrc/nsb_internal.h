@@ -50,7 +50,8 @@ struct nsb_context_s {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t gs_stream = nullptr;    // gather-scatter of finished slabs, concurrent with the next slab's axhelm
-  double ax_slab_mb = 48.0;            // NSB_AX_SLAB_MB: u + w of one slab (3 fields) in MB; 0 = no slab pipeline
+  double ax_slab_mb = 0.0;             // NSB_AX_SLAB_MB: u + w of one slab (3 fields) in MB; 0 (default) = no slab pipeline
+                                       // (measured slower: profiles/ncu_r02_matvec_slabs.md)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   int num_sms = nsb::kNumSM;
