@@ -510,7 +510,7 @@ def run_native(a):
             calls[0] += 1
             return bufs[calls[0] % nbuf], t
 
-        hop = nb.host_operator(lay, host_matvec)
+        hop = nb.host_operator(lay, host_matvec, linear=True)   # linearised time-stepper: un-normalised hand-over allowed
         He = np.zeros((K + 1, K), order='F')
         nb.arnoldi_factorization(Q, He, 1, 3, K, hop, nb.ORTH_CGS2)        # warm-up
         barrier()
@@ -523,7 +523,8 @@ def run_native(a):
                    h2d_bytes_per_step=sumall(bytes_step) * K, d2h_bytes_per_step=sumall(bytes_step + 8 * (K + 1)) * K,
                    note='per bench step (= k_dim Arnoldi steps): each Arnoldi step downloads q_m, calls the host '
                         'matvec stand-in, uploads f from pinned host memory, orthonormalises on the GPU and '
-                        'reads H(:,m) back')
+                        'reads H(:,m) back; the operator is declared linear (nsb_op_set_linear), so the download of '
+                        'q_m+1 overlaps the third sweep of step m')
         hop.close()
 
     line = None

@@ -305,6 +305,12 @@ int nsb_op_create_sem(nsb_sem_t sem, int nfields_apply, double alpha, double bet
 typedef int (*nsb_host_matvec_fn)(void *user, const double *const *in_fields, double in_time,
                                   double **out_fields, double *out_time);
 int nsb_op_create_host(nsb_layout_t layout, nsb_host_matvec_fn fn, void *user, nsb_op_t *op);
+/* Declare a host operator LINEAR (M(a x) = a M(x) for every component, %time included): true for the linearised
+ * time-steppers of the eigenvalue / transient-growth analyses (core/linear_operators.f90:39-103), false for the
+ * nonlinear forward map of newton_krylov.  nsb_arnoldi then starts the download of q_m+1 while the last sweep
+ * of step m is still running: the callback receives the UN-NORMALISED vector beta q_m+1 and the library divides
+ * the returned vector by beta on the device.  H and the basis are the same to rounding. */
+int nsb_op_set_linear(nsb_op_t op, int linear);
 /* out = outer(inner(in)): the reference's composite maps are built this way from the basic solvers,
  * e.g. transient_growth_map = adjoint_linearized_map(forward_linearized_map(q))
  * (core/matvec.f90:478-495).  The component operators stay owned by the caller. */

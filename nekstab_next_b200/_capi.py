@@ -96,6 +96,7 @@ PROTOTYPES = {
     'nsb_op_create_sem': (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                     c_double_p, c_double_p, c_double_p, c_void_pp]),
     'nsb_op_create_host': (C.c_int, [H, HOST_MATVEC, C.c_void_p, c_void_pp]),
+    'nsb_op_set_linear': (C.c_int, [H, C.c_int]),
     'nsb_op_create_compose': (C.c_int, [H, H, H, c_void_pp]),
     'nsb_op_create_stepper': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                         C.c_double, C.c_int, c_void_pp]),

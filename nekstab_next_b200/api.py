@@ -498,9 +498,10 @@ def compose_operators(layout: Layout, outer: LinearOperator, inner: LinearOperat
     return LinearOperator(layout.lib, h, keep=(outer, inner))
 
 
-def host_operator(layout: Layout, fn) -> LinearOperator:
+def host_operator(layout: Layout, fn, linear: bool = False) -> LinearOperator:
     """Wrap a host matvec ``fn(fields_in, time_in) -> (fields_out, time_out)`` (the reference's
-    time-stepper lives on the host); vectors cross PCIe around every call."""
+    time-stepper lives on the host); vectors cross PCIe around every call.  ``linear=True`` declares
+    M(a x) = a M(x): the Arnoldi loop then hands over un-normalised vectors while its last sweep still runs."""
     lens = layout.field_len
 
     hold = {}
@@ -530,6 +531,8 @@ def host_operator(layout: Layout, fn) -> LinearOperator:
     cb = _capi.HOST_MATVEC(tramp)
     h = C.c_void_p()
     check(layout.lib.nsb_op_create_host(layout.h, cb, None, C.byref(h)))
+    if linear:
+        check(layout.lib.nsb_op_set_linear(h, 1))
     return LinearOperator(layout.lib, h, keep=cb)
 
 

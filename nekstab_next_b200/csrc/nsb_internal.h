@@ -205,6 +205,7 @@ struct nsb_op_s {
   nsb_host_matvec_fn fn = nullptr;
   void *user = nullptr;
   std::vector<double *> hin, hout;  // pinned staging buffers of the host operator
+  bool linear = false;              // nsb_op_set_linear: M(a x) = a M(x) may be used (un-normalised hand-over)
   int64_t napply = 0;
   // kind 3 (nsb_conv.cu): nsteps BDF3/EXT3 advection-diffusion steps; tmp holds the 7 work columns
   int slot = -1, nsteps = 0, maxit = 0;
@@ -248,5 +249,12 @@ int exchange_plan(int rank, int nranks, const std::vector<int64_t> &gid, const s
                   const int64_t *all_sorted, int64_t mx, ExchangePlan &plan);
 // implemented in nsb_orth.cu
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d);
-int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k);
+int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k,
+                              const double *scale_by_inv_d = nullptr);
+struct StreamOut {            // host (pinned) destinations of a vector streamed out chunk by chunk
+  double *const *fields;
+  double *time;
+};
+int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so);
+int orthonormalize_stream_out(nsb_basis_t B, int k, int col_w, int mode, double *h, const StreamOut *so);
 }  // namespace nsb

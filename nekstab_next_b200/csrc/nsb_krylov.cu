@@ -307,8 +307,10 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
   int rc = NSB_OK;
   for (int m = mstart; m <= mend && rc == NSB_OK; ++m) {
     if (op->kind == 1 && orth_mode == NSB_ORTH_CGS2 && ctx->pipeline_upload) {
-      // host operator: download q_m, call the host matvec, then upload f in row chunks with the
-      // first projection running on every chunk as it lands
+      // host operator: q_m goes to the host, the host matvec runs, f comes back in row chunks with the first
+      // projection running on every chunk as it lands.  For a LINEAR operator (nsb_op_set_linear) the download
+      // of q_m+1 already started during the third sweep of this step: the host then sees the un-normalised
+      // vector beta q and 1/beta is applied to the returned chunks on the device.
       nsb_layout_t L = Q->lay;
       NSB_REQUIRE(L == op->lay, "nsb_arnoldi: host operator built for another layout");
       std::vector<const double *> pin(L->nfields);
@@ -319,8 +321,19 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
         pout[f] = op->hout[f];
       }
       double tin = 0.0, tout = 0.0;
-      rc = nsb_vec_download(Q, m, pdl.data(), &tin);
-      if (rc != NSB_OK) break;
+      const bool streamed = op->linear && m > mstart;          // hin is being filled by the previous step
+      if (streamed) {
+        cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+        if (e != cudaSuccess) {
+          set_error("nsb_arnoldi: %s", cudaGetErrorString(e));
+          rc = NSB_ECUDA;
+          break;
+        }
+        tin = ctx->hpin[3 * (kMaxK + 8) + 9];
+      } else {
+        rc = nsb_vec_download(Q, m, pdl.data(), &tin);
+        if (rc != NSB_OK) break;
+      }
       op->napply++;
       if (op->fn(op->user, pin.data(), tin, pout.data(), &tout) != 0) {
         set_error("nsb_arnoldi: host matvec callback failed at step %d", m);
@@ -328,8 +341,16 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
         break;
       }
       std::vector<const double *> pup(pout.begin(), pout.end());
-      rc = upload_multidot_pipelined(Q, m + 1, pup.data(), tout, m + 1);
-      if (rc == NSB_OK) rc = nsb_orthonormalize(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, nullptr);
+      rc = upload_multidot_pipelined(Q, m + 1, pup.data(), tout, m + 1,
+                                     streamed ? ctx->hvec_d + 3 * (kMaxK + 8) + 3 : nullptr);
+      if (rc == NSB_OK) {
+        if (op->linear && m < mend) {
+          StreamOut so{pdl.data(), ctx->hpin + 3 * (kMaxK + 8) + 9};
+          rc = orthonormalize_stream_out(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, &so);
+        } else {
+          rc = nsb_orthonormalize(Q, m + 1, m + 1, orth_mode, H + (size_t)m * ldh, nullptr);
+        }
+      }
     } else if (async) {
       rc = (graphs && ctx->use_graph) ? step_graph(Q, op, m, orth_mode, hbuf + stride * m)
                                       : enqueue_step(Q, op, m, orth_mode, hbuf + stride * m);

@@ -229,10 +229,13 @@ __global__ void __launch_bounds__(NT) orth_post_kernel(const __grid_constant__ O
 // w *= 1/sqrt(nrm2[0]);  h_out[k] = sqrt(nrm2[0])   (k_normalize, core/krylov_subspace.f90:75-92)
 __global__ void __launch_bounds__(NT)
 normalize_kernel(double2 *__restrict__ w, int64_t n2, const double *__restrict__ nrm2,
-                 double *__restrict__ hk) {
+                 double *__restrict__ hk, double *__restrict__ keep) {
   const double beta = sqrt(nrm2[0]);
   const double inv = 1.0 / beta;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hk) *hk = beta;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (hk) *hk = beta;
+    if (keep) *keep = beta;    // survives the next step's H bookkeeping (host-operator pipeline)
+  }
   constexpr int U = 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n2; base += stride) {
@@ -247,6 +250,19 @@ normalize_kernel(double2 *__restrict__ w, int64_t n2, const double *__restrict__
       int64_t i = base + (int64_t)u * blockDim.x;
       if (i < n2) { v[u].x *= inv; v[u].y *= inv; w[i] = v[u]; }
     }
+  }
+}
+
+// rows *= 1 / *beta  (the vector a LINEAR host operator returned for an un-normalised input)
+__global__ void __launch_bounds__(NT)
+scale_rows_kernel(double2 *__restrict__ w, int64_t n2, const double *__restrict__ beta) {
+  const double inv = 1.0 / *beta;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    double2 v = w[i];
+    v.x *= inv;
+    v.y *= inv;
+    w[i] = v;
   }
 }
 
@@ -1124,7 +1140,8 @@ int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm
   int64_t cap = (int64_t)ctx->num_sms * 16;
   int grid = (int)(want < cap ? want : cap);
   ProfScope ps(ctx, PC_NORMALIZE, 16.0 * ld);
-  normalize_kernel<<<grid, NT, 0, ctx->stream>>>(reinterpret_cast<double2 *>(w), n2, nrm2_d, hk_d);
+  normalize_kernel<<<grid, NT, 0, ctx->stream>>>(reinterpret_cast<double2 *>(w), n2, nrm2_d, hk_d,
+                                                 ctx->hvec_d + 3 * (kMaxK + 8) + 3);
   ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -1136,7 +1153,8 @@ namespace nsb {
 // Host vector -> column col_w in row chunks on the copy stream; the first projection
 // h1 = V_k^T (W o w) of every chunk starts as soon as that chunk has landed, so the H2D transfer
 // of f (the output of the host's matvec) overlaps the first sweep over the basis.
-int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k) {
+int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k,
+                              const double *scale_by_inv_d) {
   nsb_layout_t L = B->lay;
   nsb_context_t ctx = L->ctx;
   cudaSetDevice(ctx->device);
@@ -1173,6 +1191,13 @@ int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fie
                                ctx->copy_stream));
     NSB_CUDA(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     NSB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+    if (scale_by_inv_d) {   // f = M(w'') / beta: the host saw the un-normalised vector
+      const int64_t n2 = (r1 - r0) / 2;
+      const int g = (int)std::min<int64_t>((n2 + NT - 1) / NT, (int64_t)ctx->num_sms * 8);
+      ProfScope ps(ctx, PC_BLAS1, 16.0 * (double)(r1 - r0));
+      scale_rows_kernel<<<g, NT, 0, ctx->stream>>>(reinterpret_cast<double2 *>(w + r0), n2, scale_by_inv_d);
+      ctx->launches++;
+    }
     const int64_t d1 = std::min<int64_t>(r1, L->ndot);
     if (k > 0 && d1 > r0) {
       int nr = 0;
@@ -1202,7 +1227,7 @@ int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d) 
 // Enqueue the whole orthonormalisation (core/krylov_decomposition.f90:150-186) on the context stream; nothing
 // here waits for the device.  On completion hsum = ctx->hvec_d[2*(kMaxK+8) ...] holds h[0..k] (H(1:k+1,k)) and,
 // in DGKS mode, hsum[k+1] the number of projection passes taken.
-int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode) {
+int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so) {
   nsb_layout_t L = B->lay;
   nsb_context_t ctx = L->ctx;
   const int S = kMaxK + 8;
@@ -1282,7 +1307,51 @@ int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode) {
     }
     TailSpec sn = norm_only;
     sn.skip_flag = skip;
-    NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, sn, L->nact, L->ndof_dot + 1));
+    if (so && !dgks) {
+      // Third sweep in row chunks; every finished chunk of w'' (un-normalised) starts its way to the host at
+      // once on the copy stream, so the download of the next Krylov vector overlaps this sweep and the
+      // normalisation instead of following them.
+      const int C = 8;
+      NSB_CHECK(ensure_partial(ctx, (int64_t)(C + 1) * ctx->num_sms * 2));
+      while ((int)ctx->chunk_ev.size() < C + 1) {
+        cudaEvent_t e;
+        NSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(e);
+      }
+      const int64_t nchk = L->ld / CHUNK;
+      int prow = 0;
+      for (int c = 0; c < C; ++c) {
+        const int64_t r0 = (nchk * c / C) * CHUNK, r1 = (nchk * (c + 1) / C) * CHUNK;
+        if (r1 <= r0) continue;
+        const int64_t rows_chunks = (r1 - r0) / CHUNK;
+        const int64_t ndot_rel = std::max<int64_t>(0, std::min<int64_t>(rows_chunks, (L->ndot - r0) / CHUNK));
+        const int grid = persistent_grid(ctx, rows_chunks);
+        {
+          ProfScope ps(ctx, PC_UPDATE, 8.0 * ((double)(r1 - r0) * (k + 2) + (double)ndot_rel * CHUNK));
+          update_kernel<0, true><<<grid, NT, sizeof(double) * k, ctx->stream>>>(
+              V + r0, L->ld, k, h2, w + r0, L->w_d + r0, rows_chunks, ndot_rel, ctx->partial_d + prow, OrthTail());
+        }
+        ctx->launches++;
+        prow += grid;
+        NSB_CUDA(cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
+        NSB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
+        for (int f = 0; f < L->nfields; ++f) {
+          const int64_t a = std::max<int64_t>(L->off[f], r0), b = std::min<int64_t>(L->off[f] + L->len[f], r1);
+          if (b <= a || !so->fields[f]) continue;
+          NSB_CUDA(cudaMemcpyAsync(so->fields[f] + (a - L->off[f]), w + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost,
+                                   ctx->copy_stream));
+        }
+        if (so->time && L->time_row >= r0 && L->time_row < r1)
+          NSB_CUDA(cudaMemcpyAsync(so->time, w + L->time_row, sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
+      NSB_CUDA(cudaGetLastError());
+      OrthTail t = make_tail(ctx, sn, 0, 1, 1);
+      t.ticket = nullptr;                       // the chunk launches reduce nothing themselves
+      t.exchange = 0;
+      NSB_CHECK(finish_tail(ctx, t, prow));
+    } else {
+      NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, sn, L->nact, L->ndof_dot + 1));
+    }
   }
   NSB_CHECK(launch_normalize(ctx, w, L->ld, scal, hsum + k));
   return NSB_OK;
@@ -1298,10 +1367,30 @@ static int orth_args_ok(nsb_basis_t B, int k, int col_w, int mode, const void *h
 }
 
 // h_pinned receives h[0..k] and, in DGKS mode, the number of passes in h_pinned[k+1] (so it needs k+2 doubles).
+namespace nsb {
+// nsb_orthonormalize with the un-normalised result streamed to the host while the last sweep runs (host-operator
+// Arnoldi loop, linear operators); synchronises the compute stream, not the copy stream.
+int orthonormalize_stream_out(nsb_basis_t B, int k, int col_w, int mode, double *h, const StreamOut *so) {
+  nsb_context_t ctx = B->lay->ctx;
+  NSB_CHECK(orth_enqueue(B, k, col_w, mode, so));
+  NSB_CUDA(cudaMemcpyAsync(ctx->hpin, ctx->hvec_d + 2 * (kMaxK + 8), sizeof(double) * (k + 1), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  NSB_CHECK(check_dev_err(ctx));
+  memcpy(h, ctx->hpin, sizeof(double) * (k + 1));
+  for (int i = 0; i <= k; ++i)
+    if (std::isnan(h[i])) {
+      set_error("NaN detected in dot product");
+      return NSB_ENAN;
+    }
+  return NSB_OK;
+}
+}  // namespace nsb
+
 extern "C" int nsb_orthonormalize_async(nsb_basis_t B, int k, int col_w, int mode, double *h_pinned) {
   NSB_CHECK(orth_args_ok(B, k, col_w, mode, h_pinned));
   nsb_context_t ctx = B->lay->ctx;
-  NSB_CHECK(orth_enqueue(B, k, col_w, mode));
+  NSB_CHECK(orth_enqueue(B, k, col_w, mode, nullptr));
   NSB_CUDA(cudaMemcpyAsync(h_pinned, ctx->hvec_d + 2 * (kMaxK + 8),
                            sizeof(double) * (k + 1 + (mode == NSB_ORTH_DGKS && k > 0 ? 1 : 0)),
                            cudaMemcpyDeviceToHost, ctx->stream));

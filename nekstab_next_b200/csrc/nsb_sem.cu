@@ -1913,6 +1913,14 @@ extern "C" int nsb_op_create_host(nsb_layout_t L, nsb_host_matvec_fn fn, void *u
 
 // out = outer(inner(in)): the reference's composite maps -- transient_growth_map = adjoint(forward(q))
 // (core/matvec.f90:478-495), newton_linearized_map etc. are built this way from the basic solvers.
+// A linear host operator (M(a x) = a M(x), %time included) lets the Arnoldi loop hand the un-normalised vector
+// over while its last sweep is still running and scale the result on the device (nsb_arnoldi).
+extern "C" int nsb_op_set_linear(nsb_op_t op, int linear) {
+  NSB_REQUIRE(op, "nsb_op_set_linear: NULL operator");
+  op->linear = linear != 0;
+  return NSB_OK;
+}
+
 extern "C" int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, nsb_op_t *out) {
   NSB_REQUIRE(layout && outer && inner && out, "nsb_op_create_compose: NULL argument");
   nsb_op_t op = new nsb_op_s();

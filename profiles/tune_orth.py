@@ -24,7 +24,7 @@ rng = np.random.default_rng(0)
 base = rng.standard_normal(1 << 20)
 for c in range(max(ks) + 1):
     Q[c].upload([np.resize(np.roll(base, 17 * c), a.n)])
-tag = ' '.join(f'{k}={os.environ[k]}' for k in ('NSB_FUSED_LOADER', 'NSB_FUSED_RC', 'NSB_NO_FUSED') if k in os.environ)
+tag = ' '.join(f'{k}={os.environ[k]}' for k in ('NSB_FUSED_LOADER', 'NSB_FUSED_RC', 'NSB_NO_FUSED', 'NSB_FUSED_ALLWARPS', 'NSB_TAIL') if k in os.environ)
 for k in ks:
     for _ in range(2):
         nb.orthonormalize(Q, k, k, nb.ORTH_CGS2)

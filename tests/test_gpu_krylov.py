@@ -93,18 +93,27 @@ def test_arnoldi_graph_replay_and_switches(ctx, monkeypatch):
     assert relerr(Hs['twobarrier'], Hs['graph']) <= 1e-8
 
 
-def test_arnoldi_host_operator(ctx):
-    """The drop-in case: the operator is the host's time-stepper, vectors cross PCIe each step."""
+@pytest.mark.parametrize('linear', [False, True])
+def test_arnoldi_host_operator(ctx, linear):
+    """The drop-in case: the operator is the host's time-stepper, vectors cross PCIe each step.  linear=True:
+    the un-normalised vector is streamed to the host while the third sweep runs (nsb_op_set_linear) -- the host
+    sees beta q, the library divides the result by beta; H and the basis agree with the oracle all the same.
+    Pressure and %time ride along (linear in all components)."""
     import nekstab_next_b200 as nb
-    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, seed=8)
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, pressure=linear, time_in_dot=linear, seed=8)
     c = P.octx()
     K = 8
     lay, B, S, op = P.gpu(ctx, K + 1)
+    seen = []
 
     def host_mv(fields, t):
-        return [P.m_apply_field(f.reshape(P.shape)).ravel() for f in fields], t
+        seen.append(float(np.sqrt(sum(np.sum(P.bm1.ravel() * f[:P.npts] ** 2) for f in fields[:2]) + (t * t if linear else 0))))
+        out = [P.m_apply_field(f.reshape(P.shape)).ravel() for f in fields[:2]]
+        if linear:
+            out.append(np.array(fields[2], copy=True))
+        return out, t
 
-    hop = nb.host_operator(lay, host_mv)
+    hop = nb.host_operator(lay, host_mv, linear=linear)
     q0 = seed(P, c)
     upload(B[0], q0)
     H = np.zeros((K + 1, K), order='F')
@@ -115,6 +124,16 @@ def test_arnoldi_host_operator(ctx):
     okr.arnoldi_factorization(c, P.omatvec, Qo, Ho, 1, K, K)
     assert np.max(np.abs(H - Ho)) <= 1e-11 * np.max(np.abs(Ho))
     assert hop.count() == K
+    got = download(B[K])
+    for a, b in zip(got.f, Qo[K].f):
+        assert np.max(np.abs(a - b.ravel())) <= 1e-10 * max(np.max(np.abs(b)), 1e-300)
+    assert abs(got.time - Qo[K].time) <= 1e-10
+    G = B.gram(K + 1)
+    assert np.max(np.abs(G - np.eye(K + 1))) < 1e-10
+    if linear:   # from the second step on the host was handed beta q_m, |beta q_m| = H(m+1, m)
+        assert abs(seen[0] - 1.0) < 1e-12
+        for m in range(1, K):
+            assert abs(seen[m] - H[m, m - 1]) <= 1e-10 * H[m, m - 1]
 
 
 def test_krylov_schur_matches_oracle(ctx):
