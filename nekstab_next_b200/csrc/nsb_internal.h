@@ -144,6 +144,8 @@ struct nsb_sem_s {
   // element range of the axhelm launch in flight (launch_axhelm sets them; slab pipeline of the fused operator)
   const double *ax_g = nullptr, *ax_bm1 = nullptr, *ax_bmask = nullptr;
   int64_t ax_nel = 0;
+  double *ax_dotp = nullptr;     // request: the axhelm launch also leaves partial sums of (w_raw, u) per field here
+  int ax_dot_rows = 0;           // answer: rows of [rows][nf] partials written (0: this kernel variant cannot)
   // slab pipeline: elements [slab_e0[s], slab_e0[s+1]) ; private gather-scatter nodes whose LAST copy lies in
   // slab s are [slab_node_end[s-1], slab_node_end[s]) -- their gather-scatter runs right after that slab's
   // axhelm, while w and u of the slab are still in L2

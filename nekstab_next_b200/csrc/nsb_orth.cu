@@ -1191,7 +1191,7 @@ int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fie
                                ctx->copy_stream));
     NSB_CUDA(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
     NSB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
-    if (scale_by_inv_d) {   // f = M(w'') / beta: the host saw the un-normalised vector
+    if (scale_by_inv_d && r1 > r0) {   // f = M(w'') / beta: the host saw the un-normalised vector
       const int64_t n2 = (r1 - r0) / 2;
       const int g = (int)std::min<int64_t>((n2 + NT - 1) / NT, (int64_t)ctx->num_sms * 8);
       ProfScope ps(ctx, PC_BLAS1, 16.0 * (double)(r1 - r0));

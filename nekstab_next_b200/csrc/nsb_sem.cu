@@ -617,7 +617,8 @@ __global__ void __launch_bounds__((NF * Dmma8Cfg<NF, CONV>::NG + 1) * 32, 1)
 axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, const double *__restrict__ g,
                       const double *__restrict__ bm1, int64_t nel, int64_t npts, double h1, double h2,
                       const double *__restrict__ cv, double alpha, double beta,
-                      const double *__restrict__ bmask, int64_t fstride, int geo_evict_first) {
+                      const double *__restrict__ bmask, int64_t fstride, int geo_evict_first,
+                      double *__restrict__ dotp) {
   using Cfg = Dmma8Cfg<NF, CONV>;
   constexpr int LX = 8, N2 = 64, N3 = 512, NG = Cfg::NG, NCW = NF * NG, PLANE = Cfg::PLANE;
   constexpr int NARR = Cfg::NARR;
@@ -694,6 +695,9 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
   // element-boundary flags of the two points (i = 2t, 2t+1 ; j = gq)
   const bool bj = (gq == 0 || gq == LX - 1);
   const bool bx = bj || (2 * t == 0), by = bj || (2 * t + 1 == LX - 1);
+  // (w, u) over this warp's points: for a continuous u the sum over local points of w_raw u equals the assembled
+  // inner product (QQ^T w, u)_mult -- the (w, p) of the conjugate-gradient iteration without a pass of its own
+  double dacc = 0.0;
   for (int64_t it = grp; it < nit; it += NG) {
     const int64_t e = blockIdx.x + it * gridDim.x;
     const int s = (int)(it % NBUF);
@@ -787,10 +791,15 @@ axhelm3d_dmma8_kernel(const double *__restrict__ u, double *__restrict__ w, cons
         if (!(bx || kb)) v.x = alpha * uk[k].x + beta * mk.x * v.x;
         if (!(by || kb)) v.y = alpha * uk[k].y + beta * mk.y * v.y;
       }
+      if (EPI == 0) dacc = fma(v.x, uk[k].x, fma(v.y, uk[k].y, dacc));
       *reinterpret_cast<double2 *>(we + p) = v;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the buffer
+  }
+  if (EPI == 0 && dotp) {                    // partial[(cta * NG + group)][field]
+    dacc = warp_reduce_sum(dacc);
+    if (lane == 0) dotp[((size_t)blockIdx.x * NG + grp) * NF + f] = dacc;
   }
 }
 
@@ -826,7 +835,9 @@ int launch_dmma8_s(nsb_sem_t S, const double *u, double *w, int64_t fstride, dou
   const int64_t grid = S->ax_nel < S->ctx->num_sms ? S->ax_nel : S->ctx->num_sms;
   kfn<<<(unsigned)grid, (NF * Cfg::NG + 1) * 32, smem, S->ctx->stream>>>(u, w, S->ax_g, S->ax_bm1, S->ax_nel, S->npts, h1,
                                                                        h2, cv, alpha, beta, bmask, fstride,
-                                                                       S->nslab > 1 && S->ax_nel < S->nel ? 1 : 0);
+                                                                       S->nslab > 1 && S->ax_nel < S->nel ? 1 : 0,
+                                                                       EPI == 0 ? S->ax_dotp : nullptr);
+  if (EPI == 0 && S->ax_dotp) S->ax_dot_rows = (int)grid * Cfg::NG;
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -1644,34 +1655,37 @@ __global__ void axpby_fields_kernel(double *__restrict__ out, const double *__re
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) out[t] = a * x[t] + b * y[t];
 }
 
-// Per-field scalars of the batched solver, passed by value (up to kPcgFields systems at once)
+// Scalars of the batched solver (up to kPcgFields systems at once).  They LIVE ON THE DEVICE: alpha, beta and
+// the stopping decisions are computed by one-thread-per-system kernels between the sweeps, so an iteration is
+// a fixed sequence of launches without a host round trip; the host polls the state every few iterations.
 constexpr int kPcgFields = 3;
-struct PcgScal {
-  double v[kPcgFields];
+struct PcgState {
+  double rtz1[kPcgFields], rtz2[kPcgFields], r0[kPcgFields], rn[kPcgFields], alpha[kPcgFields], beta[kPcgFields];
+  int done[kPcgFields], itf[kPcgFields];
+  int it, all_done;
 };
 
-// z = d r ; partial[f] += r z mult      (grid.y = field; the work vectors have field stride n)
+// r = mask f ; partial[f] += r (d r) mult     (z = d r is never stored)
 __global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict__ f, int64_t fs_f, double *__restrict__ r,
-                                                       double *__restrict__ z, const double *__restrict__ d,
-                                                       const double *__restrict__ mask, const double *__restrict__ mult,
-                                                       int64_t n, int nf, double *__restrict__ partial) {
+                                                       const double *__restrict__ d, const double *__restrict__ mask,
+                                                       const double *__restrict__ mult, int64_t n, int nf,
+                                                       double *__restrict__ partial) {
   const int fi = blockIdx.y;
   const double *ff = f + (int64_t)fi * fs_f;
-  double *rr = r + (int64_t)fi * n, *zz = z + (int64_t)fi * n;
+  double *rr = r + (int64_t)fi * n;
   double acc = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
     const double rv = ff[t] * mask[t];        // the right-hand side lives in the masked space
     const double zv = d[t] * rv;
     rr[t] = rv;
-    zz[t] = zv;
     acc = fma(rv * zv, mult[t], acc);
   }
   acc = block_reduce_sum<256>(acc);
   if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + fi] = acc;
 }
 
-// partial[f] = sum w p mult
+// partial[f] = sum w p mult   (kernels that cannot fold the product into their epilogue)
 __global__ void __launch_bounds__(256) pcg_dot_kernel(const double *__restrict__ w, const double *__restrict__ p,
                                                       const double *__restrict__ mult, int64_t n, int nf,
                                                       double *__restrict__ partial) {
@@ -1685,50 +1699,139 @@ __global__ void __launch_bounds__(256) pcg_dot_kernel(const double *__restrict__
   if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + fi] = acc;
 }
 
-// x += alpha p ; r -= alpha w ; z = d r ; partial[f] = r z mult     (one pass over five vectors per field)
+// x += alpha p ; r -= alpha w ; partial[f] = r (d r) mult -- all systems of a point in one thread, so d and mult
+// are read once per point; per system the arithmetic (and its order) does not depend on how many run side by side
+template <int NF>
 __global__ void __launch_bounds__(256) pcg_update_kernel(double *__restrict__ x, int64_t fs_x, double *__restrict__ r,
-                                                         double *__restrict__ z, const double *__restrict__ p,
-                                                         const double *__restrict__ w, const double *__restrict__ d,
-                                                         const double *__restrict__ mult, PcgScal alpha, int64_t n,
-                                                         int nf, double *__restrict__ partial) {
-  const int fi = blockIdx.y;
-  const double al = alpha.v[fi];
-  double *xx = x + (int64_t)fi * fs_x, *rr = r + (int64_t)fi * n, *zz = z + (int64_t)fi * n;
-  const double *pp = p + (int64_t)fi * n, *ww = w + (int64_t)fi * n;
-  double acc = 0.0;
+                                                         const double *__restrict__ p, const double *__restrict__ w,
+                                                         const double *__restrict__ d, const double *__restrict__ mult,
+                                                         const PcgState *__restrict__ st, int64_t n,
+                                                         double *__restrict__ partial) {
+  double al[NF], acc[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    al[f] = st->alpha[f];
+    acc[f] = 0.0;
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-    xx[t] = fma(al, pp[t], xx[t]);
-    const double rv = fma(-al, ww[t], rr[t]);
-    rr[t] = rv;
-    const double zv = d[t] * rv;
-    zz[t] = zv;
-    acc = fma(rv * zv, mult[t], acc);
+    const double dv = ld_stream1(d + t), mv = ld_stream1(mult + t);
+    double xv[NF], rv[NF], pv[NF], wv[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      xv[f] = x[(int64_t)f * fs_x + t];
+      rv[f] = r[(int64_t)f * n + t];
+      pv[f] = ld_stream1(p + (int64_t)f * n + t);
+      wv[f] = ld_stream1(w + (int64_t)f * n + t);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      x[(int64_t)f * fs_x + t] = fma(al[f], pv[f], xv[f]);
+      const double rn = fma(-al[f], wv[f], rv[f]);
+      r[(int64_t)f * n + t] = rn;
+      const double zv = dv * rn;
+      acc[f] = fma(rn * zv, mv, acc[f]);
+    }
   }
-  acc = block_reduce_sum<256>(acc);
-  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * nf + fi] = acc;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const double s = block_reduce_sum<256>(acc[f]);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * NF + f] = s;
+  }
 }
 
-// p = z + beta p
-__global__ void pcg_p_kernel(double *__restrict__ p, const double *__restrict__ z, PcgScal beta, int64_t n) {
-  const int fi = blockIdx.y;
-  const double be = beta.v[fi];
-  double *pp = p + (int64_t)fi * n;
-  const double *zz = z + (int64_t)fi * n;
+// p = d r + beta p
+template <int NF>
+__global__ void __launch_bounds__(256) pcg_p_kernel(double *__restrict__ p, const double *__restrict__ r,
+                                                    const double *__restrict__ d, const PcgState *__restrict__ st,
+                                                    int64_t n) {
+  double be[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) be[f] = st->beta[f];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) pp[t] = fma(be, pp[t], zz[t]);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const double dv = ld_stream1(d + t);
+    double pv[NF], rv[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      pv[f] = p[(int64_t)f * n + t];
+      rv[f] = ld_stream1(r + (int64_t)f * n + t);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) p[(int64_t)f * n + t] = fma(be[f], pv[f], dv * rv[f]);
+  }
 }
 
-// partial[grid][nf] -> nf host scalars (summed over ranks)
-int reduce_scalars(nsb_context_t ctx, int nblk, int nf, double *out_host) {
-  double *out_d = ctx->hvec_d + 3 * (kMaxK + 8) + 16;
-  reduce_partials_kernel<<<1, 32 * kPcgFields, 0, ctx->stream>>>(ctx->partial_d, nblk, nf, nf, out_d, 0, nullptr);
+// ---- the scalar recurrences of cggo, one thread per system ----
+__global__ void pcg_begin_kernel(PcgState *st, const double *__restrict__ red, int nf, int maxit) {
+  const int g = threadIdx.x;
+  if (g < kPcgFields) {
+    st->rtz1[g] = g < nf ? red[g] : 0.0;
+    st->rtz2[g] = 1.0;
+    st->r0[g] = -1.0;
+    st->rn[g] = 0.0;
+    st->alpha[g] = 0.0;
+    st->beta[g] = 0.0;
+    st->done[g] = g < nf ? 0 : 1;
+    st->itf[g] = maxit;
+  }
+  if (g == 0) {
+    st->it = 1;
+    st->all_done = 0;
+  }
+}
+
+// after rho = (w, p): alpha = rtz1 / rho; a non-positive rho ends the system (round-off level / singular)
+__global__ void pcg_alpha_kernel(PcgState *st, const double *__restrict__ red, int nf) {
+  const int g = threadIdx.x;
+  if (g >= kPcgFields) return;
+  double al = 0.0;
+  if (g < nf && !st->done[g]) {
+    const double rho = red[g];
+    if (!(rho > 0.0)) {
+      st->done[g] = 1;
+      st->itf[g] = st->it;
+    } else {
+      al = st->rtz1[g] / rho;
+    }
+  }
+  st->alpha[g] = al;
+}
+
+// after rtz_new = (r, d r): shift, stopping test on sqrt((r, D r)) relative to the first one, beta of the next
+// iteration (0 for a finished system: it is frozen, its x no longer changes)
+__global__ void pcg_conv_kernel(PcgState *st, const double *__restrict__ red, int nf, double tol) {
+  __shared__ int s_done[kPcgFields];
+  const int g = threadIdx.x;
+  if (g < kPcgFields) {
+    if (g < nf && !st->done[g]) {
+      st->rtz2[g] = st->rtz1[g];
+      st->rtz1[g] = red[g];
+      st->rn[g] = sqrt(fabs(st->rtz1[g]));
+      if (st->r0[g] < 0.0) st->r0[g] = sqrt(fabs(st->rtz2[g]));
+      if (st->rn[g] <= tol * st->r0[g]) {
+        st->done[g] = 1;
+        st->itf[g] = st->it;
+      }
+    }
+    st->beta[g] = (g < nf && !st->done[g]) ? st->rtz1[g] / st->rtz2[g] : 0.0;
+    s_done[g] = st->done[g];
+  }
+  __syncthreads();
+  if (g == 0) {
+    int all = 1;
+    for (int q = 0; q < kPcgFields; ++q) all = all && s_done[q];
+    st->all_done = all;
+    st->it += 1;
+  }
+}
+
+// partial[rows][nf] -> red[nf] on the device (summed over ranks)
+int reduce_scalars_d(nsb_context_t ctx, int rows, int nf, double *red_d) {
+  reduce_partials_kernel<<<1, 32 * kPcgFields, 0, ctx->stream>>>(ctx->partial_d, rows, nf, nf, red_d, 0, nullptr);
   ctx->launches++;
   NSB_CUDA(cudaGetLastError());
-  if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, out_d, nf));
-  NSB_CUDA(cudaMemcpyAsync(ctx->hpin + 16, out_d, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
-  NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int f = 0; f < nf; ++f) out_host[f] = ctx->hpin[16 + f];
+  if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, red_d, nf));
   return NSB_OK;
 }
 
@@ -1736,10 +1839,13 @@ int reduce_scalars(nsb_context_t ctx, int nblk, int nf, double *out_host) {
 
 // nf independent systems (h1 A + h2 B) x_f = rhs_f solved side by side: the matrix-vector product reads
 // the geometric factors once for all of them (one axhelm + one gather-scatter launch per iteration),
-// every system keeps its own alpha / beta / convergence test and is frozen (alpha = 0) once converged,
-// so each follows exactly the iteration sequence it would follow alone.
+// every system keeps its own alpha / beta / convergence test and is frozen (alpha = beta = 0) once converged,
+// so each follows the iteration sequence it would follow alone.
 // Nek masks w after the dssum; that pass is skipped here: d carries the mask, so z, p and x stay zero on
 // the masked nodes whatever r collects there, and every inner product has an exact zero factor there.
+// Per iteration: p = d r + beta p | w = H p with (w, p) accumulated in the axhelm epilogue | dssum |
+// x += alpha p, r -= alpha w, (r, d r) -- four sweeps, z never stored, no host synchronisation; the host looks
+// at the device-side state every kPcgPoll iterations (a converged system idles with alpha = beta = 0 meanwhile).
 extern "C" int nsb_sem_hmholtz_vec(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, int field0,
                                    int nf, double h1, double h2, double tol, int maxit, int *iters, double *res) {
   NSB_REQUIRE(S && brhs && bx, "nsb_sem_hmholtz: NULL argument");
@@ -1764,12 +1870,16 @@ extern "C" int nsb_sem_hmholtz_vec(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_
   cudaStream_t st = ctx->stream;
   const int64_t n = S->npts;
   const size_t nb = sizeof(double) * n;
-  if (!S->pcg_d) NSB_CUDA(cudaMalloc(&S->pcg_d, nb * (4 * kPcgFields + 1)));
-  double *r = S->pcg_d, *p = r + kPcgFields * n, *w = p + kPcgFields * n, *z = w + kPcgFields * n,
-         *d = z + kPcgFields * n;
+  constexpr int kPcgPoll = 4;
+  if (!S->pcg_d) NSB_CUDA(cudaMalloc(&S->pcg_d, nb * (3 * kPcgFields + 1) + sizeof(PcgState) + 64));
+  double *r = S->pcg_d, *p = r + kPcgFields * n, *w = p + kPcgFields * n, *d = w + kPcgFields * n;
+  PcgState *state = reinterpret_cast<PcgState *>(d + n);
+  double *red = ctx->hvec_d + 3 * (kMaxK + 8) + 16;
+  PcgState *hstate = reinterpret_cast<PcgState *>(ctx->hpin + 3 * (kMaxK + 8) + 32);   // pinned mirror
+  static_assert(sizeof(PcgState) <= sizeof(double) * (kMaxK + 8 - 32), "PcgState must fit the pinned scratch");
   const int grid = ctx->num_sms * 8;
   const dim3 g2(grid, nf);
-  NSB_CHECK(ensure_partial(ctx, grid));
+  NSB_CHECK(ensure_partial(ctx, std::max(grid, ctx->num_sms * 8)));
   // setprec: d = mask / dssum(h1 diag(A) + h2 bm1); diag(A) depends on the mesh only and is kept
   if (!S->diagA_d) {
     NSB_CUDA(cudaMalloc(&S->diagA_d, nb));
@@ -1784,65 +1894,52 @@ extern "C" int nsb_sem_hmholtz_vec(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_
   ctx->launches += 2;
   for (int g = 0; g < nf; ++g) NSB_CUDA(cudaMemsetAsync(x + g * fs_x, 0, nb, st));
   NSB_CUDA(cudaMemsetAsync(p, 0, nb * nf, st));
-  pcg_init_kernel<<<g2, 256, 0, st>>>(f, fs_f, r, z, d, S->mask_d, S->vmult_d, n, nf, ctx->partial_d);
+  pcg_init_kernel<<<g2, 256, 0, st>>>(f, fs_f, r, d, S->mask_d, S->vmult_d, n, nf, ctx->partial_d);
   ctx->launches++;
-  double rtz1[kPcgFields], rtz2[kPcgFields], rho[kPcgFields], r0[kPcgFields], rn[kPcgFields];
-  bool done[kPcgFields];
-  int itf[kPcgFields];
-  NSB_CHECK(reduce_scalars(ctx, grid, nf, rtz1));
-  for (int g = 0; g < nf; ++g) {
-    rtz2[g] = 1.0;
-    r0[g] = -1.0;
-    rn[g] = 0.0;
-    done[g] = false;
-    itf[g] = maxit;
-  }
+  NSB_CHECK(reduce_scalars_d(ctx, grid, nf, red));
+  pcg_begin_kernel<<<1, 32, 0, st>>>(state, red, nf, maxit);
+  ctx->launches++;
+  auto poll = [&]() -> int {
+    NSB_CUDA(cudaMemcpyAsync(hstate, state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+    NSB_CUDA(cudaStreamSynchronize(st));
+    return check_dev_err(ctx);
+  };
   for (int it = 1; it <= maxit; ++it) {
-    PcgScal beta, alpha;
-    for (int g = 0; g < kPcgFields; ++g) beta.v[g] = (g < nf && it > 1 && !done[g]) ? rtz1[g] / rtz2[g] : 0.0;
-    pcg_p_kernel<<<g2, 256, 0, st>>>(p, z, beta, n);                                     // p = z + beta p
+    if (nf == 1) pcg_p_kernel<1><<<grid, 256, 0, st>>>(p, r, d, state, n);               // p = d r + beta p
+    else if (nf == 2) pcg_p_kernel<2><<<grid, 256, 0, st>>>(p, r, d, state, n);
+    else pcg_p_kernel<3><<<grid, 256, 0, st>>>(p, r, d, state, n);
     ctx->launches++;
-    NSB_CHECK(launch_axhelm(S, p, w, nf, n, h1, h2, nullptr, 0, 0, 0, nullptr));         // w = H p
+    S->ax_dotp = ctx->partial_d;                                                         // w = H p and (w_raw, p)
+    S->ax_dot_rows = 0;
+    int rc = launch_axhelm(S, p, w, nf, n, h1, h2, nullptr, 0, 0, 0, nullptr);
+    S->ax_dotp = nullptr;
+    NSB_CHECK(rc);
+    const int dot_rows = S->ax_dot_rows;
+    if (dot_rows > 0) NSB_CHECK(reduce_scalars_d(ctx, dot_rows, nf, red));               // before the dssum reuses nothing of it
     NSB_CHECK(launch_gs(S, w, nf, n, 0, nullptr, 0, 0, nullptr));                        // dssum
-    pcg_dot_kernel<<<g2, 256, 0, st>>>(w, p, S->vmult_d, n, nf, ctx->partial_d);         // rho = (w, p)
-    ctx->launches++;
-    NSB_CHECK(reduce_scalars(ctx, grid, nf, rho));
-    bool any = false;
-    for (int g = 0; g < kPcgFields; ++g) {
-      alpha.v[g] = 0.0;
-      if (g >= nf || done[g]) continue;
-      if (!(rho[g] > 0.0)) {                                                             // converged to round-off / singular
-        done[g] = true;
-        itf[g] = it;
-        continue;
-      }
-      alpha.v[g] = rtz1[g] / rho[g];
-      any = true;
+    if (dot_rows == 0) {
+      pcg_dot_kernel<<<g2, 256, 0, st>>>(w, p, S->vmult_d, n, nf, ctx->partial_d);       // rho = (w, p)_mult
+      ctx->launches++;
+      NSB_CHECK(reduce_scalars_d(ctx, grid, nf, red));
     }
-    if (!any) break;
-    pcg_update_kernel<<<g2, 256, 0, st>>>(x, fs_x, r, z, p, w, d, S->vmult_d, alpha, n, nf, ctx->partial_d);
+    pcg_alpha_kernel<<<1, 32, 0, st>>>(state, red, nf);
+    if (nf == 1) pcg_update_kernel<1><<<grid, 256, 0, st>>>(x, fs_x, r, p, w, d, S->vmult_d, state, n, ctx->partial_d);
+    else if (nf == 2) pcg_update_kernel<2><<<grid, 256, 0, st>>>(x, fs_x, r, p, w, d, S->vmult_d, state, n, ctx->partial_d);
+    else pcg_update_kernel<3><<<grid, 256, 0, st>>>(x, fs_x, r, p, w, d, S->vmult_d, state, n, ctx->partial_d);
+    ctx->launches += 2;
+    NSB_CHECK(reduce_scalars_d(ctx, grid, nf, red));
+    pcg_conv_kernel<<<1, 32, 0, st>>>(state, red, nf, tol);
     ctx->launches++;
-    double rtzn[kPcgFields];
-    NSB_CHECK(reduce_scalars(ctx, grid, nf, rtzn));
-    bool all = true;
-    for (int g = 0; g < nf; ++g) {
-      if (done[g]) continue;
-      rtz2[g] = rtz1[g];
-      rtz1[g] = rtzn[g];
-      // convergence on the preconditioned residual norm sqrt((r, D r)) relative to the first one
-      rn[g] = std::sqrt(std::fabs(rtz1[g]));
-      if (r0[g] < 0.0) r0[g] = std::sqrt(std::fabs(rtz2[g]));
-      if (rn[g] <= tol * r0[g]) {
-        done[g] = true;
-        itf[g] = it;
-      }
-      all = all && done[g];
+    NSB_CUDA(cudaGetLastError());
+    if (it % kPcgPoll == 0 || it == maxit) {
+      NSB_CHECK(poll());
+      if (hstate->all_done) break;
     }
-    if (all) break;
   }
+  NSB_CHECK(poll());
   for (int g = 0; g < nf; ++g) {
-    if (iters) iters[g] = itf[g];
-    if (res) res[g] = r0[g] > 0.0 ? rn[g] / r0[g] : 0.0;
+    if (iters) iters[g] = hstate->itf[g];
+    if (res) res[g] = hstate->r0[g] > 0.0 ? hstate->rn[g] / hstate->r0[g] : 0.0;
   }
   return NSB_OK;
 }

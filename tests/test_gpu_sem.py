@@ -202,5 +202,7 @@ def test_helmholtz_pcg_three_systems_side_by_side(ctx):
         assert relerr(xs[f].reshape(P.shape), xo) <= 1e-8
         it1, _ = S.hmholtz(B[0], B[2], f, h1, h2, tol=1e-11, maxit=400)
         single_its.append(it1)
-        assert np.array_equal(B[2].download()[0][f], xs[f])      # bit-identical to the stand-alone solve
-    assert its == single_its and len(set(its)) > 1               # the systems stop at different iterations
+        # same iterates as the stand-alone solve up to the summation order of (w, p): that inner product is
+        # accumulated in the axhelm epilogue, whose element-to-warp assignment depends on the number of systems
+        assert relerr(B[2].download()[0][f], xs[f]) <= 1e-10
+    assert all(abs(a - b) <= 1 for a, b in zip(its, single_its)) and len(set(its)) > 1   # they stop at different iterations
