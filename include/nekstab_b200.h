@@ -410,6 +410,27 @@ int nsb_ts_gmres(nsb_basis_t Q, nsb_op_t op, nsb_basis_t brhs, int crhs, nsb_bas
                  int maxiter, int ksize, double tol, int orth_mode, int *calls,
                  double *residual_hist, int *nhist);
 
+/* ---------------------------------------------------------------------------------------------
+ * Krylov checkpoint / restart wire formats of the reference (host files <-> device basis).
+ * ------------------------------------------------------------------------------------------- */
+/* HES<session>%04d: H(1:k+1,1:k) row by row as list-directed text (core/eigensolvers.f90:837-843). */
+int nsb_hessenberg_write(const char *path, const double *H, int ldh, int k);
+/* The restart read of core/eigensolvers.f90:246-266: the file holds (mstart+1) x mstart values; the leading
+ * block of the (k_dim+1) x k_dim matrix H is filled (subsampled to k_dim columns when k_dim < mstart). */
+int nsb_hessenberg_read(const char *path, int k_dim, int mstart, double *H, int ldh);
+/* One Nek5000 field file (KRY<session>0.f%05d written by outpost2, core/eigensolvers.f90:803-809) into
+ * column col: velocity -> layout fields ufield0.., pressure -> pfield, temperature -> tfield (-1: skip).
+ * lglel = 1-based global ids of this rank's elements (Nek's LGLEL; NULL: the file's first nel_local elements).
+ * %time of the column is left zero like load_files does (core/IO.f90:60-68); the header's time -> *time_out. */
+int nsb_fld_read_into(nsb_basis_t b, int col, const char *path, const int64_t *lglel, int64_t nel_local,
+                      int ufield0, int pfield, int tfield, double *time_out);
+/* The restart branch of krylov_schur (core/eigensolvers.f90:240-285): H from HES<session><mstart>, Krylov
+ * vectors 1..mstart+1 from KRY<session>0.f00001.. into columns 0..mstart; *mstart_next = 0-based index of the
+ * next Arnoldi step (pass it to nsb_arnoldi / continue nsb_krylov_schur's loop from there). */
+int nsb_restart_load(nsb_basis_t Q, const char *dir, const char *session, int mstart, int k_dim,
+                     const int64_t *lglel, int64_t nel_local, int ufield0, int pfield, int tfield, double *H,
+                     int ldh, int *mstart_next);
+
 #ifdef __cplusplus
 }
 #endif

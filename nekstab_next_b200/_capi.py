@@ -124,6 +124,11 @@ PROTOTYPES = {
     'nsb_ritz_vector': (C.c_int, [H, C.c_int, c_double_p, H, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
     'nsb_svds': (C.c_int, [H, H, H, H, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p, C.c_int, c_double_p,
                            c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
+    'nsb_hessenberg_write': (C.c_int, [C.c_char_p, c_double_p, C.c_int, C.c_int]),
+    'nsb_hessenberg_read': (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_double_p, C.c_int]),
+    'nsb_fld_read_into': (C.c_int, [H, C.c_int, C.c_char_p, c_i64_p, C.c_int64, C.c_int, C.c_int, C.c_int, c_double_p]),
+    'nsb_restart_load': (C.c_int, [H, C.c_char_p, C.c_char_p, C.c_int, C.c_int, c_i64_p, C.c_int64, C.c_int, C.c_int,
+                                   C.c_int, c_double_p, C.c_int, c_int_p]),
     'nsb_ts_gmres': (C.c_int, [H, H, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                c_int_p, c_double_p, c_int_p]),
 }

@@ -724,3 +724,41 @@ def ts_gmres(Q: Basis, op: LinearOperator, rhs: nek_dvector, sol: nek_dvector, m
     check(Q.lib.nsb_ts_gmres(Q.h, op.h, rhs.basis.h, rhs.col, sol.basis.h, sol.col, maxiter, ksize,
                              tol, orth_mode, C.byref(calls), _dp(hist), C.byref(nh)))
     return hist[:nh.value].copy(), calls.value
+
+
+# ------------------------------------------------------------------------------------------------
+# restart wire formats through the C ABI (the Python module `checkpoint` holds the writers / spectra files)
+# ------------------------------------------------------------------------------------------------
+def hessenberg_write(path, H: np.ndarray, k: int):
+    Hf = np.asfortranarray(H, dtype=np.float64)
+    check(_capi.load().nsb_hessenberg_write(str(path).encode(), _dp(Hf), Hf.shape[0], int(k)))
+
+
+def hessenberg_read(path, k_dim: int, mstart: int) -> np.ndarray:
+    H = np.zeros((k_dim + 1, k_dim), order='F')
+    check(_capi.load().nsb_hessenberg_read(str(path).encode(), int(k_dim), int(mstart), _dp(H), k_dim + 1))
+    return H
+
+
+def fld_read_into(vec: nek_dvector, path, nel_local: int, ufield0: int = 0, pfield: int = -1, tfield: int = -1,
+                  lglel=None) -> float:
+    """Nek field file -> device vector (load_fld + the copies of load_files, core/IO.f90:58-68); returns the
+    header's time."""
+    t = C.c_double()
+    lg = None if lglel is None else np.ascontiguousarray(lglel, dtype=np.int64)
+    check(vec.basis.lib.nsb_fld_read_into(vec.basis.h, vec.col, str(path).encode(),
+                                          None if lg is None else lg.ctypes.data_as(c_i64_p), int(nel_local),
+                                          int(ufield0), int(pfield), int(tfield), C.byref(t)))
+    return t.value
+
+
+def restart_load(Q: Basis, directory, session: str, mstart: int, k_dim: int, nel_local: int, ufield0: int = 0,
+                 pfield: int = -1, tfield: int = -1, lglel=None):
+    """The restart branch of krylov_schur (core/eigensolvers.f90:240-285); returns (H, next 1-based mstart)."""
+    H = np.zeros((k_dim + 1, k_dim), order='F')
+    nxt = C.c_int()
+    lg = None if lglel is None else np.ascontiguousarray(lglel, dtype=np.int64)
+    check(Q.lib.nsb_restart_load(Q.h, str(directory).encode(), session.encode(), int(mstart), int(k_dim),
+                                 None if lg is None else lg.ctypes.data_as(c_i64_p), int(nel_local), int(ufield0),
+                                 int(pfield), int(tfield), _dp(H), k_dim + 1, C.byref(nxt)))
+    return H, nxt.value + 1

@@ -1349,6 +1349,9 @@ int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so)
       t.ticket = nullptr;                       // the chunk launches reduce nothing themselves
       t.exchange = 0;
       NSB_CHECK(finish_tail(ctx, t, prow));
+      // the normalisation rescales w in place: it must not start before the last chunk has left for the host
+      NSB_CUDA(cudaEventRecord(ctx->chunk_ev[C], ctx->copy_stream));
+      NSB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[C], 0));
     } else {
       NSB_CHECK(launch_update<0>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, true, sn, L->nact, L->ndof_dot + 1));
     }

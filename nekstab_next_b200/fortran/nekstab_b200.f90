@@ -9,9 +9,17 @@
 !!   type nek_dvector          <- real_nek_vector (core/nek_vectors.f90:20-31),
 !!                                krylov_vector   (core/krylov_subspace.f90:12-17)
 !!   k_dot, k_norm, ...        <- core/krylov_subspace.f90:26-209
-!!   arnoldi_factorization     <- core/krylov_decomposition.f90:2
-!!   krylov_schur (driver part)<- core/eigensolvers.f90:120
-!!   ts_gmres                  <- core/newton_krylov.f90:170
+!!   arnoldi_factorization(Q, H, mstart, mend, ksize)   <- core/krylov_decomposition.f90:2   (same signature)
+!!   update_hessenberg_matrix(H, f, q, k)               <- core/krylov_decomposition.f90:103 (same signature)
+!!   k_matmul(dq, Q, yvec, k)                           <- core/krylov_subspace.f90:163      (same signature)
+!!   schur_condensation(mstart, H, Q, ksize)            <- core/eigensolvers.f90:363         (same signature)
+!!   ts_gmres(rhs, sol, maxiter, ksize, calls)          <- core/newton_krylov.f90:170        (same signature)
+!!   krylov_schur (driver part)                         <- core/eigensolvers.f90:120
+!! The reference routines find the linear operator through `matvec` (core/matvec.f90:56) and their tolerances
+!! in the NEKSTAB commons; here the operator is the module variable nsb_current_op (set with nsb_set_operator
+!! where the reference calls prepare_linearized_solver) and schur_del / schur_tgt / the GMRES tolerance are the
+!! module variables below, so the CALL SITES core/eigensolvers.f90:297,318 and core/newton_krylov.f90:125,252
+!! compile unchanged once Q is declared `type(nek_dvector)` and bound to the device basis (nsb_bind_basis).
 module nekstab_b200
    use, intrinsic :: iso_c_binding
    implicit none
@@ -37,6 +45,21 @@ module nekstab_b200
       procedure, pass(self), public :: axpby => dv_axpby
    end type nek_dvector
 
+   !> State the reference keeps in commons / finds through `matvec`: the operator every solver below applies,
+   !! the orthogonalisation mode, Schur parameters (core/NEKSTAB: schur_del, schur_tgt) and the GMRES tolerance
+   !! (max(param(21), param(22)), core/newton_krylov.f90:232).
+   type(c_ptr), save, public :: nsb_current_op = c_null_ptr
+   integer(c_int), save, public :: nsb_orth_mode = NSB_ORTH_CGS2
+   real(c_double), save, public :: nsb_schur_del = 0.10d0, nsb_gmres_tol = 1.0d-8
+   integer, save, public :: nsb_schur_tgt = 2
+
+   !> k_matmul keeps the reference's four-argument form; the three-argument form uses the module basis nsb_Q.
+   interface k_matmul
+      module procedure k_matmul_q, k_matmul_d
+   end interface k_matmul
+
+   public :: nsb_set_operator, nsb_bind_basis
+   public :: arnoldi_factorization, update_hessenberg_matrix, schur_condensation, ts_gmres
    public :: nsb_check, nsb_startup, nsb_shutdown, nsb_upload, nsb_download
    public :: nsb_p2p_mailbox_create, nsb_p2p_mailbox_connect
    public :: k_dot, k_norm, k_normalize, k_cmult, k_add2, k_sub2, k_sub3, k_zero, k_copy, k_matmul
@@ -502,6 +525,51 @@ module nekstab_b200
          real(c_double) :: A(lda, *), U(m, *), S(*), V(n, *)
          integer(c_int) :: ierr
       end function
+      function nsb_set_dgks_eta(ctx, eta) bind(C, name='nsb_set_dgks_eta') result(ierr)
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: ctx
+         real(c_double), value :: eta
+         integer(c_int) :: ierr
+      end function
+      function nsb_op_set_linear(op, linear) bind(C, name='nsb_op_set_linear') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: op
+         integer(c_int), value :: linear
+         integer(c_int) :: ierr
+      end function
+      function nsb_arnoldi_passes(Q, mstart, mend, orth_mode, passes) bind(C, name='nsb_arnoldi_passes') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: Q
+         integer(c_int), value :: mstart, mend, orth_mode
+         integer(c_int) :: passes(*)
+         integer(c_int) :: ierr
+      end function
+      function nsb_hessenberg_write(path, H, ldh, k) bind(C, name='nsb_hessenberg_write') result(ierr)
+         import :: c_int, c_double, c_char
+         character(kind=c_char) :: path(*)
+         integer(c_int), value :: ldh, k
+         real(c_double) :: H(ldh, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_hessenberg_read(path, k_dim, mstart, H, ldh) bind(C, name='nsb_hessenberg_read') result(ierr)
+         import :: c_int, c_double, c_char
+         character(kind=c_char) :: path(*)
+         integer(c_int), value :: k_dim, mstart, ldh
+         real(c_double) :: H(ldh, *)
+         integer(c_int) :: ierr
+      end function
+      function nsb_restart_load(Q, dir, session, mstart, k_dim, lglel, nel_local, ufield0, pfield, tfield, H, ldh, &
+                                mstart_next) bind(C, name='nsb_restart_load') result(ierr)
+         import :: c_int, c_int64_t, c_double, c_char, c_ptr
+         type(c_ptr), value :: Q
+         character(kind=c_char) :: dir(*), session(*)
+         integer(c_int), value :: mstart, k_dim, ufield0, pfield, tfield, ldh
+         integer(c_int64_t) :: lglel(*)
+         integer(c_int64_t), value :: nel_local
+         real(c_double) :: H(ldh, *)
+         integer(c_int) :: mstart_next
+         integer(c_int) :: ierr
+      end function
       function nsb_select_eigenvalues(selected, cnt, vals, delta, nev, n) bind(C, name='nsb_select_eigenvalues') &
          result(ierr)
          import :: c_int, c_double, c_double_complex
@@ -518,6 +586,8 @@ module nekstab_b200
    public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose
    public :: nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues
+   public :: nsb_set_dgks_eta, nsb_op_set_linear, nsb_arnoldi_passes, nsb_hessenberg_write, nsb_hessenberg_read
+   public :: nsb_restart_load
 
 
 contains
@@ -687,12 +757,116 @@ contains
    end subroutine k_copy
 
    !> dq = Q(1:k) * yvec (core/krylov_subspace.f90:163-209); Q is the device basis.
-   subroutine k_matmul(dq, yvec, k)
+   subroutine k_matmul_d(dq, yvec, k)
       type(nek_dvector), intent(inout) :: dq
       integer, intent(in) :: k
       real(c_double), intent(in) :: yvec(k)
       call nsb_check(nsb_basis_gemv(nsb_Q, int(k, c_int), yvec, dq%basis, dq%col), 'k_matmul')
-   end subroutine k_matmul
+   end subroutine k_matmul_d
+
+   ! ---- the reference's own signatures --------------------------------------------------------
+   !> Where the reference calls prepare_linearized_solver / selects the operator behind `matvec`
+   !! (core/matvec.f90:56-146): every solver below applies this handle (nsb_op_create_host wraps the host
+   !! time-stepper, nsb_op_create_sem / _stepper / _compose are device operators).
+   subroutine nsb_set_operator(op)
+      type(c_ptr), intent(in) :: op
+      nsb_current_op = op
+   end subroutine nsb_set_operator
+
+   !> Q(i) <- column i-1 of `basis`: the replacement of allocate(Q(k_dim+1)) (core/eigensolvers.f90:149) --
+   !! the array of vectors the reference passes around becomes a view of the device-resident basis.
+   subroutine nsb_bind_basis(Q, basis, ncols)
+      integer, intent(in) :: ncols
+      type(nek_dvector), intent(out) :: Q(ncols)
+      type(c_ptr), intent(in) :: basis
+      integer :: i
+      do i = 1, ncols
+         Q(i)%basis = basis
+         Q(i)%col = int(i - 1, c_int)
+      end do
+   end subroutine nsb_bind_basis
+
+   !> Q must be consecutive columns of one device basis, Q(1) its column 0 (nsb_bind_basis).
+   subroutine nsb_require_view(Q, n, where)
+      integer, intent(in) :: n
+      type(nek_dvector), intent(in) :: Q(n)
+      character(len=*), intent(in) :: where
+      integer :: i
+      do i = 1, n
+         if (.not. c_associated(Q(i)%basis, Q(1)%basis) .or. Q(i)%col /= i - 1) then
+            write (6, *) where, ': Q is not a view of one device basis (use nsb_bind_basis)'
+            call nek_end
+         end if
+      end do
+   end subroutine nsb_require_view
+
+   !> arnoldi_factorization(Q, H, mstart, mend, ksize) -- core/krylov_decomposition.f90:2-99, same arguments.
+   subroutine arnoldi_factorization(Q, H, mstart, mend, ksize)
+      integer, intent(in) :: mstart, mend, ksize
+      type(nek_dvector), dimension(ksize + 1) :: Q
+      real(c_double), dimension(ksize + 1, ksize) :: H
+      if (ksize == 0) then                                  ! core/krylov_decomposition.f90:59-62
+         write (6, *) 'Krylov base dimension == 0! Increase it.'
+         call nek_end
+      end if
+      call nsb_require_view(Q, ksize + 1, 'arnoldi_factorization')
+      call nsb_check(nsb_arnoldi(Q(1)%basis, nsb_current_op, int(mstart - 1, c_int), int(mend - 1, c_int), &
+                                 nsb_orth_mode, H, int(ksize + 1, c_int)), 'arnoldi_factorization')
+   end subroutine arnoldi_factorization
+
+   !> update_hessenberg_matrix(H, f, q, k) -- core/krylov_decomposition.f90:103-189, same arguments; f must be
+   !! a column of q's basis at or behind column k (it is orthonormalised in place against q(1:k)).
+   subroutine update_hessenberg_matrix(H, f, q, k)
+      integer, intent(in) :: k
+      real(c_double), dimension(k + 1, k) :: H
+      type(nek_dvector) :: f
+      type(nek_dvector), dimension(k) :: q
+      real(c_double) :: h_col(k + 1)
+      integer(c_int) :: passes
+      call nsb_require_view(q, k, 'update_hessenberg_matrix')
+      if (.not. c_associated(f%basis, q(1)%basis)) then
+         write (6, *) 'update_hessenberg_matrix: f must live in the basis of q'
+         call nek_end
+      end if
+      call nsb_check(nsb_orthonormalize(f%basis, int(k, c_int), f%col, nsb_orth_mode, h_col, passes), &
+                     'update_hessenberg_matrix')
+      H(1:k + 1, k) = h_col
+   end subroutine update_hessenberg_matrix
+
+   !> k_matmul(dq, Q, yvec, k) -- core/krylov_subspace.f90:163-209, same arguments.
+   subroutine k_matmul_q(dq, Q, yvec, k)
+      integer, intent(in) :: k
+      type(nek_dvector) :: dq
+      type(nek_dvector), dimension(k) :: Q
+      real(c_double), dimension(k) :: yvec
+      call nsb_require_view(Q, k, 'k_matmul')
+      call nsb_check(nsb_basis_gemv(Q(1)%basis, int(k, c_int), yvec, dq%basis, dq%col), 'k_matmul')
+   end subroutine k_matmul_q
+
+   !> schur_condensation(mstart, H, Q, ksize) -- core/eigensolvers.f90:363-468, same arguments; schur_del and
+   !! schur_tgt come from the module variables (the reference reads them from the NEKSTAB commons).
+   subroutine schur_condensation(mstart, H, Q, ksize)
+      integer, intent(inout) :: mstart
+      integer, intent(in) :: ksize
+      real(c_double), dimension(ksize + 1, ksize), intent(inout) :: H
+      type(nek_dvector), dimension(ksize + 1) :: Q
+      integer(c_int) :: m
+      call nsb_require_view(Q, ksize + 1, 'schur_condensation')
+      m = int(mstart - 1, c_int)
+      call nsb_check(nsb_schur_condensation(Q(1)%basis, m, H, int(ksize + 1, c_int), int(ksize, c_int), &
+                                            nsb_schur_del, int(nsb_schur_tgt, c_int)), 'schur_condensation')
+      mstart = m + 1
+   end subroutine schur_condensation
+
+   !> ts_gmres(rhs, sol, maxiter, ksize, calls) -- core/newton_krylov.f90:170-299, same arguments.  The reference
+   !! allocates its Krylov basis inside; here the module basis nsb_Q (>= ksize + 2 columns) is used.
+   subroutine ts_gmres(rhs, sol, maxiter, ksize, calls)
+      type(nek_dvector), intent(in) :: rhs
+      type(nek_dvector), intent(inout) :: sol
+      integer, intent(in) :: maxiter, ksize
+      integer, intent(out) :: calls
+      call ts_gmres_d(nsb_current_op, rhs, sol, maxiter, ksize, nsb_gmres_tol, calls)
+   end subroutine ts_gmres
 
    ! ---- solver entry points -------------------------------------------------------------------
    !> arnoldi_factorization(Q, H, mstart, mend, ksize) (core/krylov_decomposition.f90:2-99):

@@ -110,3 +110,67 @@ def test_singvals_roundtrip(tmp_path):
     assert np.allclose(s2, sig ** 2, rtol=1e-7) and np.allclose(r2, res, rtol=1e-7)
     lines = open(p).read().splitlines()
     assert all(len(ln) == 30 for ln in lines) and lines[0].split()[0] == '0.6315198E+05'
+
+
+def test_hessenberg_through_the_c_abi(tmp_path, lib):
+    """nsb_hessenberg_write / nsb_hessenberg_read (host-only entry points) against the Python module and the
+    reference's list-directed layout, incl. Fortran D exponents and the k_dim < mstart subsampling."""
+    import nekstab_next_b200 as nb
+    rng = np.random.default_rng(3)
+    k = 9
+    H = np.asfortranarray(np.triu(rng.standard_normal((k + 1, k)), -1))
+    p = tmp_path / ck.hessenberg_name('1cyl', k)
+    nb.hessenberg_write(p, H, k)
+    assert np.array_equal(ck.read_hessenberg(p, k, k), H)                 # C writer -> Python reader, exact
+    assert np.array_equal(nb.hessenberg_read(p, k, k), H)                 # C writer -> C reader, exact
+    H12 = nb.hessenberg_read(p, 12, k)                                    # restart into a larger space
+    assert H12.shape == (13, 12) and np.array_equal(H12[:k + 1, :k], H) and not H12[:, k:].any()
+    H5 = nb.hessenberg_read(p, 5, k)                                      # subsampling, k_dim < mstart
+    assert np.array_equal(H5, H[:6, :5])
+    q = tmp_path / 'HESfortran0003'                                       # what write(67,*) can look like
+    q.write_text('  1.5D+00 -2.25d-01, 3.0\n 4.0   5.0E0 6.0\n7 8 9\n 10 11 12\n')
+    Hf = nb.hessenberg_read(q, 3, 3)
+    assert np.array_equal(Hf, np.array([[1.5, -0.225, 3], [4, 5, 6], [7, 8, 9], [10, 11, 12]]))
+    with pytest.raises(nb.NsbError):
+        nb.hessenberg_read(q, 3, 4)                                       # wrong number of values
+
+
+@pytest.mark.gpu
+def test_restart_from_reference_wire_formats(ctx, tmp_path):
+    """The restart branch of krylov_schur (core/eigensolvers.f90:240-285) through the C ABI: a factorisation
+    interrupted after mstart steps, checkpointed as HES<session>%04d + KRY<session>0.f%05d (Nek field files,
+    fp64, elements stored in a permuted order), reloaded into a fresh basis and continued gives the H of the
+    uninterrupted run."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).parent))
+    import nekstab_next_b200 as nb
+    from helpers import BoxProblem, upload, download
+    from oracle import krylov as okr
+    P = BoxProblem(nel=(3, 2, 2), N=4, nfields=3, conv=True, seed=17)
+    c = P.octx()
+    K, ms = 10, 6
+    lay, B, S, op = P.gpu(ctx, K + 1)
+    q0 = P.random_kvec()
+    okr.k_normalize(c, q0)
+    upload(B[0], q0)
+    Hfull = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(B, Hfull, 1, K, K, op)
+    nel, lx = P.shape[0], P.shape[-1]
+    perm = np.random.default_rng(1).permutation(nel)            # file order != local order
+    for i in range(ms + 1):                                      # outpost of the first ms + 1 Krylov vectors
+        v = download(B[i], P.shape)
+        ck.write_fld(tmp_path / ck.field_name('KRY', 'box', i + 1), dict(u=[f[perm] for f in v.f[:3]]), lx, lx, lx,
+                     time=0.5 * (i + 1), elmap=perm + 1)
+    nb.hessenberg_write(tmp_path / ck.hessenberg_name('box', ms), Hfull, ms)
+    B2 = nb.Basis(lay, K + 1)
+    t = nb.fld_read_into(B2[K], tmp_path / ck.field_name('KRY', 'box', 2), nel, lglel=np.arange(1, nel + 1))
+    assert abs(t - 1.0) < 1e-12
+    assert np.array_equal(B2[K].download()[0][1], B[1].download()[0][1])   # exact: fp64 file, elements re-ordered
+    H, mnext = nb.restart_load(B2, tmp_path, 'box', ms, K, nel, lglel=np.arange(1, nel + 1))
+    assert mnext == ms + 1 and np.array_equal(H[:ms + 1, :ms], Hfull[:ms + 1, :ms])
+    nb.arnoldi_factorization(B2, H, mnext, K, K, op)
+    assert np.max(np.abs(H - Hfull)) <= 1e-13 * np.max(np.abs(Hfull))
+    with pytest.raises(nb.NsbError):                              # an element the file does not hold
+        nb.fld_read_into(B2[K], tmp_path / ck.field_name('KRY', 'box', 2), nel, lglel=np.arange(2, nel + 2))
+    for o in (B2, op, S, B, lay):
+        o.close()
