@@ -280,6 +280,10 @@ int nsb_dealias_matrices(int N, int lxd, double *zd, double *wd, double *J, doub
 int nsb_sem_set_convect(nsb_sem_t sem, int slot, nsb_basis_t b, int col, int field0);
 int nsb_sem_convect(nsb_sem_t sem, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
                     int field0, int nf, double scale, int accumulate);
+/* The exact transpose of nsb_sem_convect as a matrix on the local points: sum_p v_p (C u)_p = sum_p u_p (C^T v)_p;
+ * the convective term of the discrete adjoint time-stepper below. */
+int nsb_sem_convect_t(nsb_sem_t sem, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
+                      int field0, int nf, double scale, int accumulate);
 /* EXT / BDF sums of the same step ([UPSTREAM-RECALL] perturb.f makextp + makebdfp) in one pass over
  * fields field0..field0+nf-1 of columns of b:
  *   ta = ab[1] e1 + ab[2] e2 ; e2 <- e1 ; e1 <- bf ; bf <- ab[0] bf + ta ;
@@ -325,6 +329,14 @@ int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, n
  * step is not available. */
 int nsb_op_create_stepper(nsb_sem_t sem, nsb_layout_t layout, int nfields_apply, int slot, double kappa,
                           double rho, double dt, int nsteps, double tol, int maxit, nsb_op_t *op);
+/* exponential_prop%rmatvec (core/linear_operators.f90:84-103) for the same step sequence: the DISCRETE adjoint of
+ * the operator nsb_op_create_stepper builds with respect to the BM1 inner product,
+ *     <A u, v>_B = <u, A^+ v>_B   for continuous, masked u, v  (to rounding and the Helmholtz tolerance),
+ * obtained by running the transposed BDF/EXT recurrence backwards in time (transposed dealiased convection,
+ * the same symmetric Helmholtz solves).  Together they make transient_growth_map = A^+ A (core/matvec.f90:478-495,
+ * nsb_op_create_compose) and nsb_svds device-resident.  Same arguments as nsb_op_create_stepper. */
+int nsb_op_create_stepper_adjoint(nsb_sem_t sem, nsb_layout_t layout, int nfields_apply, int slot, double kappa,
+                                  double rho, double dt, int nsteps, double tol, int maxit, nsb_op_t *op);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_op_count(nsb_op_t op, int64_t *napply);

@@ -91,6 +91,7 @@ PROTOTYPES = {
     'nsb_sem_dealias_setup': (C.c_int, [H, C.c_int]),
     'nsb_sem_set_convect': (C.c_int, [H, C.c_int, H, C.c_int, C.c_int]),
     'nsb_sem_convect': (C.c_int, [H, C.c_int, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
+    'nsb_sem_convect_t': (C.c_int, [H, C.c_int, H, C.c_int, H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
     'nsb_sem_bdf_ext': (C.c_int, [H, H, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, c_double_p,
                                   c_double_p, C.c_double]),
     'nsb_op_create_sem': (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -100,6 +101,8 @@ PROTOTYPES = {
     'nsb_op_create_compose': (C.c_int, [H, H, H, c_void_pp]),
     'nsb_op_create_stepper': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                         C.c_double, C.c_int, c_void_pp]),
+    'nsb_op_create_stepper_adjoint': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                C.c_double, C.c_int, c_void_pp]),
     'nsb_op_destroy': (C.c_int, [H]),
     'nsb_op_apply': (C.c_int, [H, H, C.c_int, H, C.c_int]),
     'nsb_op_count': (C.c_int, [H, c_i64_p]),

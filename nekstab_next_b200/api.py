@@ -423,6 +423,12 @@ class Sem:
         check(self.lib.nsb_sem_convect(self.h, int(slot), vin.basis.h, vin.col, vout.basis.h, vout.col,
                                        int(field0), int(nf), float(scale), int(accumulate)))
 
+    def convect_t(self, slot: int, vin: nek_dvector, vout: nek_dvector, field0: int = 0, nf: int = 1,
+                  scale: float = 1.0, accumulate: bool = False):
+        """Exact transpose of ``convect`` on the local points (convective term of the adjoint stepper)."""
+        check(self.lib.nsb_sem_convect_t(self.h, int(slot), vin.basis.h, vin.col, vout.basis.h, vout.col,
+                                         int(field0), int(nf), float(scale), int(accumulate)))
+
     def bdf_ext(self, bf: nek_dvector, e1: nek_dvector, e2: nek_dvector, vlag, ab, bd, rho_over_dt: float,
                 field0: int = 0, nf: int = 1):
         """makextp + makebdfp in one pass; all vectors are columns of the same basis, vlag[0] = current."""
@@ -482,12 +488,13 @@ def sem_operator(sem: Sem, nfields: int, alpha: float, beta: float, h1: float, h
 
 
 def stepper_operator(sem: Sem, layout: Layout, nfields: int, slot: int, kappa: float, dt: float, nsteps: int,
-                     rho: float = 1.0, tol: float = 1e-12, maxit: int = 1000) -> LinearOperator:
+                     rho: float = 1.0, tol: float = 1e-12, maxit: int = 1000, adjoint: bool = False) -> LinearOperator:
     """Device time-stepper operator: nsteps BDF3/EXT3 advection-diffusion steps from a cold start (the structure
     of exponential_prop%matvec, core/linear_operators.f90:225-274, for Nek's scalar step); slot -1 = no flow."""
     h = C.c_void_p()
-    check(sem.lib.nsb_op_create_stepper(sem.h, layout.h, int(nfields), int(slot), float(kappa), float(rho),
-                                        float(dt), int(nsteps), float(tol), int(maxit), C.byref(h)))
+    create = sem.lib.nsb_op_create_stepper_adjoint if adjoint else sem.lib.nsb_op_create_stepper
+    check(create(sem.h, layout.h, int(nfields), int(slot), float(kappa), float(rho),
+                 float(dt), int(nsteps), float(tol), int(maxit), C.byref(h)))
     return LinearOperator(sem.lib, h, keep=(sem, layout))
 
 

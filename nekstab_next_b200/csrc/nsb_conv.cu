@@ -277,7 +277,11 @@ set_convect_kernel(const double *__restrict__ v, int64_t fstride, int64_t nfine,
 }
 
 // convect_new: out (+)= scale * J^T [ (c . grad_rst)(J u) ];  CTA = (element, field), field fastest
-template <int LX, int LD>
+// ADJ: the exact transpose, out (+)= scale * J^T [ D_r^T (c_r o J u) + D_s^T (c_s o J u) + D_t^T (c_t o J u) ]
+// (the factors are applied before the differentiation and the derivative matrix is read transposed) -- the
+// convective term of the discrete adjoint of the time-stepper (exponential_prop%rmatvec,
+// core/linear_operators.f90:84-103)
+template <int LX, int LD, bool ADJ>
 __global__ void __launch_bounds__(LD * LD)
 convect_kernel(const double *__restrict__ u, double *__restrict__ out, int64_t fstride_in, int64_t fstride_out,
                int64_t nfine, int nf, const double *__restrict__ cf, double scale, int accumulate) {
@@ -296,13 +300,13 @@ convect_kernel(const double *__restrict__ u, double *__restrict__ out, int64_t f
   {                                                          // r: line (K, J) = tid along I
     double in[LD];
 #pragma unroll
-    for (int I = 0; I < LD; ++I) in[I] = uf[tid * L::LDp + I];
+    for (int I = 0; I < LD; ++I) in[I] = ADJ ? cr[tid * LD + I] * uf[tid * L::LDp + I] : uf[tid * L::LDp + I];
 #pragma unroll
     for (int I = 0; I < LD; ++I) {
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[I * LD + m], in[m], s);
-      wf[tid * L::LDp + I] = cr[tid * LD + I] * s;
+      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[ADJ ? m * LD + I : I * LD + m], in[m], s);
+      wf[tid * L::LDp + I] = ADJ ? s : cr[tid * LD + I] * s;
     }
   }
   __syncthreads();
@@ -310,25 +314,30 @@ convect_kernel(const double *__restrict__ u, double *__restrict__ out, int64_t f
     const int K = tid / LD, I = tid % LD;
     double in[LD];
 #pragma unroll
-    for (int Jx = 0; Jx < LD; ++Jx) in[Jx] = uf[(K * LD + Jx) * L::LDp + I];
+    for (int Jx = 0; Jx < LD; ++Jx)
+      in[Jx] = ADJ ? cs[(K * LD + Jx) * LD + I] * uf[(K * LD + Jx) * L::LDp + I] : uf[(K * LD + Jx) * L::LDp + I];
 #pragma unroll
     for (int Jx = 0; Jx < LD; ++Jx) {
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[Jx * LD + m], in[m], s);
-      wf[(K * LD + Jx) * L::LDp + I] += cs[(K * LD + Jx) * LD + I] * s;
+      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[ADJ ? m * LD + Jx : Jx * LD + m], in[m], s);
+      wf[(K * LD + Jx) * L::LDp + I] += ADJ ? s : cs[(K * LD + Jx) * LD + I] * s;
     }
   }
   __syncthreads();
   {                                                          // t: line (J, I) along K, from the registers
     const int Jx = tid / LD, I = tid % LD;
     double w[LD];
+    if (ADJ) {
+#pragma unroll
+      for (int K = 0; K < LD; ++K) col[K] *= ct[(K * LD + Jx) * LD + I];
+    }
 #pragma unroll
     for (int K = 0; K < LD; ++K) {
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[K * LD + m], col[m], s);
-      w[K] = wf[(K * LD + Jx) * L::LDp + I] + ct[(K * LD + Jx) * LD + I] * s;
+      for (int m = 0; m < LD; ++m) s = fma(c_convD<LX, LD>[ADJ ? m * LD + K : K * LD + m], col[m], s);
+      w[K] = wf[(K * LD + Jx) * L::LDp + I] + (ADJ ? s : ct[(K * LD + Jx) * LD + I] * s);
     }
     // project back along k at once: the thread owns the whole (J, I) column of w
     double *b2 = uf;                                         // [k][J][I], uf is dead (other threads' s/r reads are done)
@@ -405,6 +414,7 @@ __device__ __forceinline__ void load_mats2(int lx, int ld, double *sm, const dou
 // mode 0: rxf[a][e] = (w_I w_J) J(rst[a][e]), grid (nel, 4)
 // mode 1: c_a = sum_b rxf[2a+b] J(v_b), grid (nel, 1)
 // mode 2: out (+)= scale J^T[(c . grad)(J u)], grid (nel, nf)
+// mode 3: the transpose of mode 2, out (+)= scale J^T[D_r^T (c_r o J u) + D_s^T (c_s o J u)]
 __global__ void __launch_bounds__(128)
 conv2d_kernel(int mode, int lx, int ld, const double *__restrict__ in, double *__restrict__ out, int64_t npts,
               int64_t nfine, int64_t fs_in, int64_t fs_out, const double *__restrict__ Jg,
@@ -447,11 +457,19 @@ conv2d_kernel(int mode, int lx, int ld, const double *__restrict__ in, double *_
   for (int o = threadIdx.x; o < nf2; o += blockDim.x) {
     const int I = o % ld, Jx = o / ld;
     double ur = 0.0, us = 0.0;
-    for (int m = 0; m < ld; ++m) {
-      ur = fma(Dg[I * ld + m], uf[Jx * ld + m], ur);
-      us = fma(Dg[Jx * ld + m], uf[m * ld + I], us);
+    if (mode == 3) {
+      for (int m = 0; m < ld; ++m) {
+        ur = fma(Dg[m * ld + I], cr[Jx * ld + m] * uf[Jx * ld + m], ur);
+        us = fma(Dg[m * ld + Jx], cs[m * ld + I] * uf[m * ld + I], us);
+      }
+      wf[o] = ur + us;
+    } else {
+      for (int m = 0; m < ld; ++m) {
+        ur = fma(Dg[I * ld + m], uf[Jx * ld + m], ur);
+        us = fma(Dg[Jx * ld + m], uf[m * ld + I], us);
+      }
+      wf[o] = cr[o] * ur + cs[o] * us;
     }
-    wf[o] = cr[o] * ur + cs[o] * us;
   }
   __syncthreads();
   double *p1 = uf;                                               // [J][i]
@@ -525,7 +543,8 @@ int dealias_setup_t(nsb_sem_t S, const double *wd_d, const double *J_h, const do
   NSB_CUDA(cudaMemcpyToSymbol(c_convD<LX, LD>, Dg_h, sizeof(double) * LD * LD));
   NSB_CUDA(cudaFuncSetAttribute(dealias_rx_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NSB_CUDA(cudaFuncSetAttribute(set_convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-  NSB_CUDA(cudaFuncSetAttribute(convect_kernel<LX, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+  NSB_CUDA(cudaFuncSetAttribute(convect_kernel<LX, LD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+  NSB_CUDA(cudaFuncSetAttribute(convect_kernel<LX, LD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
   dealias_rx_kernel<LX, LD><<<dim3((unsigned)S->nel, 9), 256, smem, S->ctx->stream>>>(S->rst_d, S->npts, nfine, S->J_d,
                                                                                   S->Dg_d, wd_d, S->rxf_d);
   S->ctx->launches++;
@@ -545,10 +564,14 @@ int set_convect_t(nsb_sem_t S, const double *v, int64_t fstride, double *cf) {
 
 template <int LX, int LD>
 int convect_t(nsb_sem_t S, const double *u, double *out, int64_t fsi, int64_t fso, int nf, const double *cf,
-              double scale, int accumulate) {
+              double scale, int accumulate, bool adj) {
   using LL = LineSmem<LX, LD>;
-  convect_kernel<LX, LD><<<(unsigned)(S->nel * nf), LL::NT, sizeof(double) * LL::TOTAL, S->ctx->stream>>>(
-      u, out, fsi, fso, S->nel * (int64_t)(LD * LD * LD), nf, cf, scale, accumulate);
+  if (adj)
+    convect_kernel<LX, LD, true><<<(unsigned)(S->nel * nf), LL::NT, sizeof(double) * LL::TOTAL, S->ctx->stream>>>(
+        u, out, fsi, fso, S->nel * (int64_t)(LD * LD * LD), nf, cf, scale, accumulate);
+  else
+    convect_kernel<LX, LD, false><<<(unsigned)(S->nel * nf), LL::NT, sizeof(double) * LL::TOTAL, S->ctx->stream>>>(
+        u, out, fsi, fso, S->nel * (int64_t)(LD * LD * LD), nf, cf, scale, accumulate);
   S->ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -657,8 +680,23 @@ extern "C" int nsb_sem_set_convect(nsb_sem_t S, int slot, nsb_basis_t B, int col
 #undef CALL_SC
 }
 
+static int convect_impl(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout, int field0, int nf,
+                        double scale, int accumulate, bool adj);
+
 extern "C" int nsb_sem_convect(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
                                int field0, int nf, double scale, int accumulate) {
+  return convect_impl(S, slot, bin, cin, bout, cout, field0, nf, scale, accumulate, false);
+}
+
+// The exact transpose of nsb_sem_convect (as a matrix on the local points of a field): for all u, v
+//   sum_p v_p (C u)_p = sum_p u_p (C^T v)_p .   It is the convective term of the discrete adjoint stepper.
+extern "C" int nsb_sem_convect_t(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout,
+                                 int field0, int nf, double scale, int accumulate) {
+  return convect_impl(S, slot, bin, cin, bout, cout, field0, nf, scale, accumulate, true);
+}
+
+static int convect_impl(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout, int field0, int nf,
+                        double scale, int accumulate, bool adj) {
   NSB_REQUIRE(S && bin && bout, "nsb_sem_convect: NULL argument");
   NSB_REQUIRE(slot == 0 || slot == 1, "nsb_sem_convect: slot %d (0 or 1)", slot);
   NSB_REQUIRE(S->lxd > 0 && S->cfine_d[slot], "nsb_sem_convect: slot %d has no convecting field (nsb_sem_set_convect)",
@@ -672,13 +710,13 @@ extern "C" int nsb_sem_convect(nsb_sem_t S, int slot, nsb_basis_t bin, int cin, 
   const double *cf = S->cfine_d[slot];
   if (S->dim == 2) {
     conv2d_kernel<<<dim3((unsigned)S->nel, nf), 128, conv2d_smem(S->lx, S->lxd), S->ctx->stream>>>(
-        2, S->lx, S->lxd, u, w, S->npts, S->nel * (int64_t)S->lxd * S->lxd, fsi, fso, S->J_d, S->Dg_d, nullptr, cf, scale,
-        accumulate);
+        adj ? 3 : 2, S->lx, S->lxd, u, w, S->npts, S->nel * (int64_t)S->lxd * S->lxd, fsi, fso, S->J_d, S->Dg_d, nullptr, cf,
+        scale, accumulate);
     S->ctx->launches++;
     NSB_CUDA(cudaGetLastError());
     return NSB_OK;
   }
-#define CALL_CV(A, B) convect_t<A, B>(S, u, w, fsi, fso, nf, cf, scale, accumulate)
+#define CALL_CV(A, B) convect_t<A, B>(S, u, w, fsi, fso, nf, cf, scale, accumulate, adj)
   NSB_CONV_DISPATCH(S, CALL_CV);
 #undef CALL_CV
 }
@@ -760,8 +798,100 @@ extern "C" int nsb_op_create_stepper(nsb_sem_t S, nsb_layout_t layout, int nfiel
   return NSB_OK;
 }
 
+extern "C" int nsb_op_create_stepper_adjoint(nsb_sem_t S, nsb_layout_t layout, int nfields_apply, int slot,
+                                             double kappa, double rho, double dt, int nsteps, double tol, int maxit,
+                                             nsb_op_t *out) {
+  NSB_CHECK(nsb_op_create_stepper(S, layout, nfields_apply, slot, kappa, rho, dt, nsteps, tol, maxit, out));
+  (*out)->adjoint = true;
+  return NSB_OK;
+}
+
+namespace {
+// y += a ct + b bm1 g   on nf equally spaced fields
+__global__ void __launch_bounds__(256)
+adj_accum_kernel(double *__restrict__ y, const double *__restrict__ ct, const double *__restrict__ g,
+                 const double *__restrict__ bm1, int64_t npts, int64_t fstride, double a, double b) {
+  const int64_t off = (int64_t)blockIdx.y * fstride;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = off + p;
+    y[q] = y[q] + a * (ct ? ct[q] : 0.0) + b * bm1[p] * g[q];
+  }
+}
+
+// out = c1 * c2 * in  (pointwise, c1 / c2 mesh arrays)
+__global__ void __launch_bounds__(256)
+scale2_kernel(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ c1,
+              const double *__restrict__ c2, int64_t npts, int64_t fs_out, int64_t fs_in) {
+  const int64_t oo = (int64_t)blockIdx.y * fs_out, oi = (int64_t)blockIdx.y * fs_in;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x)
+    out[oo + p] = (c1 ? c1[p] : 1.0) * (c2 ? c2[p] : 1.0) * in[oi + p];
+}
+}  // namespace
+
+// The DISCRETE adjoint of stepper_apply with respect to the BM1 inner product: for continuous masked u, v
+//     <A u, v>_B = <u, A^+ v>_B        (to rounding and the Helmholtz tolerance),
+// A^+ = B_a^-1 A^T B_a.  With x^n = S_n [ sum_j ab_j E^(n-1-j) + (rho/dt) B sum_i bd_(i+1) x^(n-1-i) ],
+// E^m = -rho C x^m, S_n = hmholtz o dssum (symmetric), the transposed recurrence runs backwards in time on dual
+// vectors y^m kept in local right-hand-side form:
+//     y^N = B v ;  for n = N .. 1:  g = S_n y^n ;  y^(n-1-j) += ab_j (-rho C^T g) + (rho/dt) bd_(j+1) B g  (j < order_n)
+//     A^+ v = binvm1 mask dssum(y^0).
+// Same kernels as the forward step plus the transposed convection (exponential_prop%rmatvec,
+// core/linear_operators.f90:84-103, for Nek's scalar step).
+static int stepper_apply_adjoint(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  nsb_sem_t S = op->sem;
+  nsb_basis_t W = op->tmp;
+  nsb_layout_t L = op->lay;
+  nsb_context_t ctx = L->ctx;
+  const int nfa = op->nfields_apply;
+  const int N = op->nsteps;
+  const int64_t fs = nfa > 1 ? L->off[1] - L->off[0] : 0;
+  for (int f = 1; f < nfa; ++f) NSB_REQUIRE(L->off[f] - L->off[f - 1] == fs, "stepper adjoint: fields are not equally spaced");
+  for (int c = 0; c < 7; ++c) NSB_CHECK(nsb_vec_zero(W, c));
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const dim3 grid(ctx->num_sms * 8, nfa);
+  // columns: y[0..3] rolling duals (y[n mod 4] = y^n), 4 = right-hand side / g, 5 = C^T g, 6 = solution
+  const int crhs = 4, cct = 5, cg = 6;
+  auto ycol = [&](int n) { return ((n % 4) + 4) % 4; };
+  scale2_kernel<<<grid, 256, 0, st>>>(W->col(ycol(N)) + L->off[0], bin->col(cin) + L->off[0], S->bm1_d, nullptr, S->npts, fs, fs);
+  ctx->launches++;
+  for (int n = N; n >= 1; --n) {
+    const int o = n < 3 ? n : 3;
+    NSB_CHECK(nsb_vec_copy(W, crhs, W, ycol(n)));
+    for (int f = 0; f < nfa; ++f) NSB_CHECK(nsb_sem_dssum(S, W, crhs, f));
+    for (int f = 0; f < nfa; f += 3) {
+      const int nb3 = nfa - f < 3 ? nfa - f : 3;
+      int it[3] = {0, 0, 0};
+      double res[3];
+      NSB_CHECK(nsb_sem_hmholtz_vec(S, W, crhs, W, cg, f, nb3, op->kappa, op->rho * kBD[o][0] / op->dt, op->tol, op->maxit,
+                                    it, res));
+      for (int g = 0; g < nb3; ++g) op->helm_iters += it[g];
+    }
+    NSB_CHECK(nsb_vec_zero(W, ycol(n)));                    // y^n is consumed; the slot becomes y^(n-4)
+    if (op->slot >= 0) NSB_CHECK(nsb_sem_convect_t(S, op->slot, W, cg, W, cct, 0, nfa, -op->rho, 0));
+    for (int j = 0; j < o; ++j) {
+      const int m = n - 1 - j;
+      if (m < 0) continue;                                   // cold start: x^m = 0 for m < 0
+      adj_accum_kernel<<<grid, 256, 0, st>>>(W->col(ycol(m)) + L->off[0], op->slot >= 0 ? W->col(cct) + L->off[0] : nullptr,
+                                             W->col(cg) + L->off[0], S->bm1_d, S->npts, fs, kAB[o][j],
+                                             op->rho / op->dt * kBD[o][j + 1]);
+      ctx->launches++;
+    }
+    NSB_CUDA(cudaGetLastError());
+  }
+  NSB_CHECK(nsb_vec_copy(W, crhs, W, ycol(0)));
+  for (int f = 0; f < nfa; ++f) NSB_CHECK(nsb_sem_dssum(S, W, crhs, f));
+  NSB_CHECK(nsb_vec_copy(bout, cout, bin, cin));             // fields outside the operator and %time carried through
+  scale2_kernel<<<grid, 256, 0, st>>>(bout->col(cout) + L->off[0], W->col(crhs) + L->off[0], S->binv_d, S->mask_d, S->npts, fs,
+                                      fs);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 int nsb::stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
   NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: time-stepper operator built for another layout");
+  if (op->adjoint) return stepper_apply_adjoint(op, bin, cin, bout, cout);
   nsb_sem_t S = op->sem;
   nsb_basis_t W = op->tmp;
   nsb_layout_t L = op->lay;

@@ -213,6 +213,7 @@ struct nsb_op_s {
   int slot = -1, nsteps = 0, maxit = 0;
   double kappa = 0, rho = 1, dt = 0, tol = 0;
   int64_t helm_iters = 0;        // Helmholtz iterations spent so far
+  bool adjoint = false;          // kind 3: apply the discrete BM1-adjoint of the stepper (rmatvec)
 };
 
 namespace nsb {

@@ -428,3 +428,61 @@ def bdf_ext(bf, e1, e2, vlag, bm1, ab, bd, rho_over_dt):
         tb = tb + bd[i + 1] * bm1 * vlag[i]
     bf += rho_over_dt * tb
     return bf
+
+
+# ----------------------------------------------------------------------------
+# Transposed pieces and the discrete adjoint of the scalar time-stepper
+# (exponential_prop%rmatvec, core/linear_operators.f90:84-103, for Nek's scalar step cdscal [UPSTREAM-RECALL])
+# ----------------------------------------------------------------------------
+BD = {1: (1.0, 1.0, 0.0, 0.0), 2: (1.5, 2.0, -0.5, 0.0), 3: (11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0)}
+AB = {1: (1.0, 0.0, 0.0), 2: (2.0, -1.0, 0.0), 3: (3.0, -3.0, 1.0)}
+
+
+def grad_rst_t(ws, d):
+    """Transpose of grad_rst: sum_a D_a^T w_a."""
+    if ws[0].ndim == 4:
+        return (np.einsum('li,ekjl->ekji', d, ws[0]) + np.einsum('lj,ekli->ekji', d, ws[1])
+                + np.einsum('lk,elji->ekji', d, ws[2]))
+    return np.einsum('li,ejl->eji', d, ws[0]) + np.einsum('lj,eli->eji', d, ws[1])
+
+
+def convect_dealiased_t(v, cf, dl):
+    """Exact transpose of convect_dealiased on the local points: J^T sum_a D_a^T (c_a o J v)."""
+    vf = interp_fine(v, dl['J'])
+    return project_coarse(grad_rst_t([c * vf for c in cf], dl['Dg']), dl['J'])
+
+
+def scalar_steps(glo, mask, geo, n, cf, dl, T0, kappa, dt, nsteps, rho=1.0, tol=1e-13):
+    """nsteps BDF/EXT steps (order ramp 1, 2, 3) of rho dT/dt + rho (U.grad) T = kappa lap T from a cold start:
+    bq = -rho C T ; makextp / makebdfp ; dssum ; hmholtz.  cf = None: no convection."""
+    d = dgll(n)
+    lag = [T0.copy(), 0 * T0, 0 * T0]
+    e1, e2 = 0 * T0, 0 * T0
+    for s in range(1, nsteps + 1):
+        o = min(s, 3)
+        bq = -rho * convect_dealiased(lag[0], cf, dl) if cf is not None else 0 * T0
+        bdf_ext(bq, e1, e2, lag[:o], geo['bm1'], AB[o], BD[o], rho / dt)
+        Tn, _, _ = cggo(dssum(bq, glo), geo['g'], d, glo, mask, geo['bm1'], kappa, rho * BD[o][0] / dt, tol=tol, maxit=2000)
+        lag = [Tn, lag[0], lag[1]]
+    return lag[0]
+
+
+def scalar_steps_adjoint(glo, mask, geo, n, cf, dl, v, kappa, dt, nsteps, rho=1.0, tol=1e-13):
+    """Discrete BM1-adjoint of scalar_steps: <A u, w>_B = <u, A^+ w>_B for continuous masked u, w.  The transposed
+    recurrence runs backwards on duals y^m in local right-hand-side form:
+        y^N = B v ; for s = N..1: g = hmholtz(dssum(y^s)) ; y^(s-1-j) += ab_j (-rho C^T g) + (rho/dt) bd_(j+1) B g ;
+        A^+ v = binvm1 mask dssum(y^0)."""
+    d = dgll(n)
+    bm1 = geo['bm1']
+    y = {nsteps: bm1 * v}
+    for s in range(nsteps, 0, -1):
+        o = min(s, 3)
+        g, _, _ = cggo(dssum(y.pop(s, 0 * v), glo), geo['g'], d, glo, mask, bm1, kappa, rho * BD[o][0] / dt, tol=tol,
+                       maxit=2000)
+        ct = -rho * convect_dealiased_t(g, cf, dl) if cf is not None else 0 * v
+        for j in range(o):
+            m = s - 1 - j
+            if m < 0:
+                continue
+            y[m] = y.get(m, 0 * v) + AB[o][j] * ct + (rho / dt) * BD[o][j + 1] * bm1 * g
+    return dssum(y.get(0, 0 * v), glo) * mask / dssum(bm1, glo)

@@ -344,3 +344,155 @@ def test_stepper_operator_leading_growth_rate(ctx):
     tau = dt * nsteps
     assert abs(np.log(lead.real) / tau + lam) <= 0.02 * lam      # time-discretisation error of the start-up steps
     op.close(); Q.close(); sem.close()
+
+
+# ---- the adjoint side: transposed convection, discrete adjoint stepper, device-resident svds ------------------
+@pytest.mark.parametrize('nel,N', [((2, 2, 2), 7), ((2, 3, 2), 5), ((3, 2), 5)])
+def test_transposed_convection_matches_oracle_and_is_the_transpose(ctx, nel, N):
+    """nsb_sem_convect_t vs the oracle's convect_dealiased_t, and sum v (C u) = sum u (C^T v) on the device."""
+    import nekstab_next_b200 as nb
+    dim = len(nel)
+    if dim == 3:
+        x, y, z, glo, geo = _mesh(nel, N, 0.04)
+        coords = (x, y, z)
+        vel = [np.sin(np.pi * x) * np.cos(np.pi * y), -np.cos(np.pi * x) * np.sin(np.pi * y), 0.2 * np.sin(np.pi * z)]
+    else:
+        x, y, glo = osem.box_mesh_2d(*nel, N, deform=0.04)
+        geo = osem.geometry(N, x, y)
+        coords = (x, y, None)
+        vel = [1.0 + 0.3 * np.sin(np.pi * y), 0.4 * np.cos(np.pi * x)]
+    dl = osem.dealias_setup(N, 3 * (N + 1) // 2, geo['rst'])
+    cf = osem.set_convect(vel, dl)
+    rng = np.random.default_rng(11)
+    u, v = rng.standard_normal(x.shape), rng.standard_normal(x.shape)
+    sem = nb.Sem(ctx, N, *coords, mask=None, glo_num=glo)
+    nv = len(vel)
+    lay = nb.Layout(ctx, [x.size] * nv, [True] * nv)
+    lay.set_weight([geo['bm1']] * nv)
+    B = nb.Basis(lay, 4)
+    sem.dealias_setup()
+    B[0].upload(vel)
+    sem.set_convect(0, B[0])
+    B[1].upload([u] + [0 * u] * (nv - 1))
+    B[2].upload([v] + [0 * u] * (nv - 1))
+    sem.convect(0, B[1], B[3], field0=0, nf=1)
+    Cu = B[3].download()[0][0].reshape(x.shape)
+    sem.convect_t(0, B[2], B[3], field0=0, nf=1)
+    Ctv = B[3].download()[0][0].reshape(x.shape)
+    assert relerr(Ctv, osem.convect_dealiased_t(v, cf, dl)) <= 1e-12
+    assert abs(np.sum(v * Cu) - np.sum(u * Ctv)) <= 1e-12 * np.sqrt(np.sum(Cu * Cu) * np.sum(v * v))
+    B.close(); sem.close()
+
+
+def _bfs_problem():
+    import json
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / 'golden'
+    N = json.loads((gold / 'known_answers.json').read_text())['bfs']['N']
+    g = np.load(gold / 'bfs_mesh.npz')
+    x, y, glo = g['x'], g['y'], g['glo'].astype(np.int64)
+    geo = osem.geometry(N, x, y)
+    # Dirichlet on the walls / inflow like the reference's v1mask: here every node on the domain boundary
+    mult = osem.multiplicity(glo)
+    lx = N + 1
+    edge = np.zeros(x.shape, dtype=bool)
+    edge[:, 0, :] = edge[:, -1, :] = edge[:, :, 0] = edge[:, :, -1] = True
+    # an element-edge node that belongs to one element only along a whole edge lies on the domain boundary
+    bnd = np.zeros(x.shape)
+    face_ids = [(slice(None), 0, slice(None)), (slice(None), lx - 1, slice(None)),
+                (slice(None), slice(None), 0), (slice(None), slice(None), lx - 1)]
+    for fi in face_ids:
+        mid = mult[fi][:, lx // 2]                       # multiplicity of the mid-edge node: 1 = domain boundary
+        sel = np.zeros(x.shape)
+        sel[fi] = (mid == 1)[:, None]
+        bnd = np.maximum(bnd, sel)
+    mask = 1.0 - np.minimum(osem.dssum(bnd, glo), 1.0)
+    return N, x, y, glo, geo, mask, [g['u'], g['v']]
+
+
+@pytest.mark.parametrize('case', ['box3d', 'bfs'])
+def test_adjoint_stepper_is_the_discrete_adjoint(ctx, case):
+    """nsb_op_create_stepper_adjoint: A^+ v against the oracle's discrete adjoint, and <A u, v>_B = <u, A^+ v>_B to
+    1e-10 on the device -- on a deformed 3-D box with a Taylor-Green-like flow and on the reference's
+    backward-facing-step mesh with its own base flow (tests/golden/bfs_mesh.npz)."""
+    import nekstab_next_b200 as nb
+    if case == 'box3d':
+        N, kappa, dt, nsteps = 7, 0.05, 5e-3, 4
+        x, y, z, glo, geo = _mesh((2, 2, 2), N, 0.04)
+        x0, y0, z0, _ = osem.box_mesh(2, 2, 2, N)
+        mask = osem.boundary_mask_box(None, x0, y0, z0)
+        vel = [np.sin(np.pi * x) * np.cos(np.pi * y), -np.cos(np.pi * x) * np.sin(np.pi * y), 0.2 * np.sin(np.pi * z)]
+        coords = (x, y, z)
+    else:
+        N, x, y, glo, geo, mask, vel = _bfs_problem()
+        kappa, dt, nsteps = 0.02, 2e-3, 4
+        coords = (x, y, None)
+    dl = osem.dealias_setup(N, 3 * (N + 1) // 2, geo['rst'])
+    cf = osem.set_convect(vel, dl)
+    rng = np.random.default_rng(8)
+    vm = 1.0 / osem.multiplicity(glo)
+    u = osem.dssum(rng.standard_normal(x.shape), glo) * vm * mask
+    v = osem.dssum(rng.standard_normal(x.shape), glo) * vm * mask
+    sem = nb.Sem(ctx, N, *coords, mask=mask, glo_num=glo)
+    nv = len(vel)
+    layv = nb.Layout(ctx, [x.size] * nv, [True] * nv)
+    Bv = nb.Basis(layv, 1)
+    sem.dealias_setup()
+    Bv[0].upload(vel)
+    sem.set_convect(0, Bv[0])
+    lay = nb.Layout(ctx, [x.size], [True])
+    lay.set_weight([geo['bm1']])
+    Q = nb.Basis(lay, 4)
+    fwd = nb.stepper_operator(sem, lay, 1, 0, kappa, dt, nsteps, tol=1e-14, maxit=3000)
+    adj = nb.stepper_operator(sem, lay, 1, 0, kappa, dt, nsteps, tol=1e-14, maxit=3000, adjoint=True)
+    Q[0].upload([u]); Q[1].upload([v])
+    fwd.matvec(Q[0], Q[2])
+    adj.matvec(Q[1], Q[3])
+    Atv = Q[3].download()[0][0].reshape(x.shape)
+    ref = osem.scalar_steps_adjoint(glo, mask, geo, N, cf, dl, v, kappa, dt, nsteps, tol=1e-14)
+    assert relerr(Atv, ref) <= 1e-9
+    lhs, rhs = nb.k_dot(Q[2], Q[1]), nb.k_dot(Q[0], Q[3])
+    assert abs(lhs - rhs) <= 1e-10 * nb.k_norm(Q[0]) * nb.k_norm(Q[1])
+    for o in (fwd, adj, Q, Bv, sem):
+        o.close()
+
+
+def test_svds_device_resident_transient_growth(ctx):
+    """transient_growth_analysis (core/linear_stab.f90:112) with both A and A^+ on the device: nsb_svds over the
+    forward / adjoint stepper pair against the oracle's svds over the oracle steppers; the leading singular value
+    squared is the optimal energy gain G(tau) of the advection-diffusion problem."""
+    import nekstab_next_b200 as nb
+    from oracle import krylov as okr
+    N, kappa, dt, nsteps, K = 5, 0.05, 5e-3, 3, 6
+    x, y, z, glo, geo = _mesh((2, 2, 2), N, 0.04)
+    x0, y0, z0, _ = osem.box_mesh(2, 2, 2, N)
+    mask = osem.boundary_mask_box(None, x0, y0, z0)
+    vel = [np.sin(np.pi * x) * np.cos(np.pi * y), -np.cos(np.pi * x) * np.sin(np.pi * y), 0.2 * np.sin(np.pi * z)]
+    dl = osem.dealias_setup(N, 3 * (N + 1) // 2, geo['rst'])
+    cf = osem.set_convect(vel, dl)
+    c = okr.Ctx(bm1s=geo['bm1'], in_dot=[True], time_in_dot=False)
+    rng = np.random.default_rng(2)
+    u0 = okr.KVec([osem.dssum(rng.standard_normal(x.shape), glo) / osem.multiplicity(glo) * mask], 0.0)
+    okr.k_normalize(c, u0)
+    so, _, _, reso, ko, _ = okr.svds(
+        c, lambda q: okr.KVec([osem.scalar_steps(glo, mask, geo, N, cf, dl, q.f[0], kappa, dt, nsteps)], q.time),
+        lambda q: okr.KVec([osem.scalar_steps_adjoint(glo, mask, geo, N, cf, dl, q.f[0], kappa, dt, nsteps)], q.time),
+        u0, K, 2, 1e-12)
+    sem = nb.Sem(ctx, N, x, y, z, mask=mask, glo_num=glo)
+    layv = nb.Layout(ctx, [x.size] * 3, [True] * 3)
+    Bv = nb.Basis(layv, 1)
+    sem.dealias_setup()
+    Bv[0].upload(vel)
+    sem.set_convect(0, Bv[0])
+    lay = nb.Layout(ctx, [x.size], [True])
+    lay.set_weight([geo['bm1']])
+    U, V = nb.Basis(lay, K + 1), nb.Basis(lay, K)
+    fwd = nb.stepper_operator(sem, lay, 1, 0, kappa, dt, nsteps, tol=1e-13)
+    adj = nb.stepper_operator(sem, lay, 1, 0, kappa, dt, nsteps, tol=1e-13, adjoint=True)
+    U[0].upload(u0.f)
+    sig, uv, vv, res, k, nconv, Bm = nb.svds(U, V, fwd, adj, K, 2, 1e-12)
+    assert k == ko
+    assert np.max(np.abs(sig[:3] - so[:3])) <= 1e-8 * so[0]
+    assert np.all(np.diff(sig) <= 1e-14) and sig[0] < 1.0          # a decaying problem: gain below one
+    for o in (fwd, adj, U, V, Bv, sem):
+        o.close()

@@ -100,3 +100,38 @@ def test_oracle_svds_against_dense_svd_in_the_weighted_inner_product():
     ref = np.linalg.svd(np.sqrt(w)[:, None] * A / np.sqrt(w)[None, :], compute_uv=False)
     conv = np.sort(sig[res < 1e-10])[::-1]
     assert len(conv) >= 3 and np.allclose(conv[:3], ref[:3], rtol=1e-9)
+
+
+def test_adjoint_stepper_oracle_is_the_discrete_adjoint():
+    """Pins the oracle's adjoint pieces independently of the GPU: convect_dealiased_t is the exact transpose of
+    convect_dealiased, and scalar_steps_adjoint satisfies <A u, v>_B = <u, A^+ v>_B (continuous, masked u, v) for
+    the BDF/EXT stepper with its order ramp, in 3-D and 2-D."""
+    from oracle import sem as osem
+    rng = np.random.default_rng(4)
+    for dim in (3, 2):
+        N = 3
+        if dim == 3:
+            x, y, z, glo = osem.box_mesh(2, 2, 2, N, deform=0.04)
+            x0, y0, z0, _ = osem.box_mesh(2, 2, 2, N)
+            mask = osem.boundary_mask_box(None, x0, y0, z0)
+            geo = osem.geometry(N, x, y, z)
+            vel = [np.sin(np.pi * x) * np.cos(np.pi * y), -np.cos(np.pi * x) * np.sin(np.pi * y), 0.3 * np.sin(np.pi * z)]
+        else:
+            x, y, glo = osem.box_mesh_2d(3, 2, N, deform=0.04)
+            x0, y0, _ = osem.box_mesh_2d(3, 2, N)
+            mask = osem.boundary_mask_box(None, x0, y0, None, lengths=(1.0, 1.0))
+            geo = osem.geometry(N, x, y)
+            vel = [1.0 + 0.3 * np.sin(np.pi * y), 0.4 * np.cos(np.pi * x)]
+        dl = osem.dealias_setup(N, 3 * (N + 1) // 2, geo['rst'])
+        cf = osem.set_convect(vel, dl)
+        a, b = rng.standard_normal(x.shape), rng.standard_normal(x.shape)
+        lhs, rhs = np.sum(b * osem.convect_dealiased(a, cf, dl)), np.sum(a * osem.convect_dealiased_t(b, cf, dl))
+        assert abs(lhs - rhs) <= 1e-12 * np.sqrt(np.sum(a * a) * np.sum(b * b)) * np.max(np.abs(cf[0]))
+        vm = 1.0 / osem.multiplicity(glo)
+        u = osem.dssum(rng.standard_normal(x.shape), glo) * vm * mask
+        v = osem.dssum(rng.standard_normal(x.shape), glo) * vm * mask
+        for nsteps in (1, 2, 4):
+            Au = osem.scalar_steps(glo, mask, geo, N, cf, dl, u, 0.05, 5e-3, nsteps)
+            Atv = osem.scalar_steps_adjoint(glo, mask, geo, N, cf, dl, v, 0.05, 5e-3, nsteps)
+            l, r = np.sum(geo['bm1'] * Au * v), np.sum(geo['bm1'] * u * Atv)
+            assert abs(l - r) <= 1e-10 * np.sqrt(np.sum(geo['bm1'] * u * u) * np.sum(geo['bm1'] * v * v)), (dim, nsteps, l, r)
