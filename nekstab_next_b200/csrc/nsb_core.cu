@@ -159,6 +159,7 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   if (const char *e = getenv("NSB_AX_DMMA")) ctx->ax_dmma = e[0] != '0';
   if (const char *e = getenv("NSB_PIPELINE_UPLOAD")) ctx->pipeline_upload = e[0] != '0';
   if (const char *e = getenv("NSB_ROTATE_SIMPLE")) ctx->rotate_simple = e[0] == '1';
+  if (const char *e = getenv("NSB_ROTATE_DMMA")) ctx->rotate_dmma = e[0] != '0';
   if (const char *e = getenv("NSB_FUSED_ALLWARPS")) ctx->fused_allwarps = e[0] != '0';
   if (const char *e = getenv("NSB_TAIL")) ctx->tail = e[0] != '0';
   if (const char *e = getenv("NSB_GRAPH")) ctx->use_graph = e[0] != '0';
@@ -200,6 +201,7 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
   comm_destroy(ctx);
   clear_step_graphs(ctx);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  if (ctx->rot_d) cudaFree(ctx->rot_d);
   if (ctx->ticket_d) cudaFree(ctx->ticket_d);
   if (ctx->flag_d) cudaFree(ctx->flag_d);
   if (ctx->seq_d) cudaFree(ctx->seq_d);

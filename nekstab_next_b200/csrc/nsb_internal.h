@@ -97,6 +97,9 @@ struct nsb_context_s {
   int fused_reg_min_k = 54;    // NSB_FUSED_REG_MIN_K: smallest k for the register-retention variant
   bool ax_generic = false;     // NSB_AX_GENERIC=1: use the generic-order axhelm kernel for N = 7 too
   bool rotate_simple = false;  // NSB_ROTATE_SIMPLE=1: first (untiled) rotation kernel
+  bool rotate_dmma = true;     // NSB_ROTATE_DMMA=0: register-tiled FMA rotation instead of the fp64 tensor-core kernel
+  double *rot_d = nullptr;     // Z and the saved %time row of nsb_basis_rotate
+  size_t rot_elems = 0;
   int ax_stages = 0;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernels (0: default; DMMA: = warp groups pins one buffer per group)
   bool fused_priv = true;      // NSB_FUSED_PRIV=0: per-block warp reduction in the fused kernel's second projection
   bool fused_allwarps = true;  // NSB_FUSED_ALLWARPS=0: warp 0 alone combines the row sums (two barriers per block)

@@ -394,6 +394,81 @@ rotate_tiled_kernel(double *__restrict__ V, int64_t ld, int k, const double *__r
   }
 }
 
+
+// ---- basis rotation on the fp64 tensor cores ---------------------------------------------------
+// V(:,0:k) <- V(:,0:k) Z is the one compute-bound contraction of the path (2 n k^2 flop for 16 n k bytes).
+// mma.m8n8k4.f64 with M = rows, K = input columns j, N = output columns c: lane (g, t) supplies
+//   A[g][t] = V[r0+g, j0+t]  -- loaded straight from global memory (8 consecutive rows of 4 columns: eight fully
+//                               used 32-byte sectors per fragment), no shared-memory staging of V at all;
+//   B[t][g] = Z[j0+t, c0+g]  -- from shared memory, column pitch = 4 (mod 16) so the 64-bit loads of a half warp
+//                               hit 16 different bank pairs;
+// and owns D[g][2t..2t+1] = out[r0+g, c0+2t..].  A warp holds RS = 2 slabs of 8 rows x k columns entirely in
+// registers (all A fragments are loaded before the first store, so the in-place update needs no barrier and no
+// second buffer), and re-uses every B fragment for both slabs.
+__device__ __forceinline__ void dmma884_acc(double2 &d, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(d.x), "+d"(d.y)
+      : "d"(a), "d"(b));
+}
+
+template <int NT8>   // ceil(k / 8) <= NT8
+__global__ void __launch_bounds__(NT, 1)
+rotate_dmma_kernel(double *__restrict__ V, int64_t ld, int k, const double *__restrict__ Z, int ldz, int zp,
+                   int64_t nslab2) {
+  constexpr int RS = 2, NJ4 = 2 * NT8, CH = 7;
+  extern __shared__ __align__(16) double zs[];   // [NT8 * 8][zp], zero padded
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < NT8 * 8 * zp; i += NT) {
+    const int c = i / zp, j = i % zp;
+    zs[i] = (c < k && j < k) ? Z[(int64_t)c * ldz + j] : 0.0;
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * (NT / 32);
+  for (int64_t sl = (int64_t)blockIdx.x * (NT / 32) + warp; sl < nslab2; sl += stride) {
+    const int64_t r0 = sl * (8 * RS);
+    double a[RS][NJ4];
+#pragma unroll
+    for (int q = 0; q < RS; ++q)
+#pragma unroll
+      for (int js = 0; js < NJ4; ++js) {
+        const int j = 4 * js + t;
+        a[q][js] = j < k ? V[(int64_t)j * ld + r0 + 8 * q + g] : 0.0;   // coherent load: the kernel rewrites V
+      }
+    // output column tiles in chunks of CH: the accumulators of one chunk live in registers next to the A
+    // fragments of the whole slab (all of V's rows were read above, so storing a chunk early is safe)
+#pragma unroll
+    for (int c0 = 0; c0 < NT8; c0 += CH) {
+      double2 acc[RS][CH];
+#pragma unroll
+      for (int q = 0; q < RS; ++q)
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc) acc[q][cc] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int js = 0; js < NJ4; ++js) {
+        if (4 * js < k) {
+#pragma unroll
+          for (int cc = 0; cc < CH; ++cc) {
+            if (c0 + cc < NT8) {
+              const double b = zs[((c0 + cc) * 8 + g) * zp + 4 * js + t];
+#pragma unroll
+              for (int q = 0; q < RS; ++q) dmma884_acc(acc[q][cc], a[q][js], b);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RS; ++q)
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc) {
+          const int c = (c0 + cc) * 8 + 2 * t;
+          double *dst = V + r0 + 8 * q + g;
+          if (c0 + cc < NT8 && c < k) dst[(int64_t)c * ld] = acc[q][cc].x;
+          if (c0 + cc < NT8 && c + 1 < k) dst[(int64_t)(c + 1) * ld] = acc[q][cc].y;
+        }
+    }
+  }
+}
+
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
@@ -1457,14 +1532,47 @@ extern "C" int nsb_basis_rotate(nsb_basis_t B, int k, const double *Z, int ldz, 
   nsb_layout_t L = B->lay;
   nsb_context_t ctx = L->ctx;
   cudaSetDevice(ctx->device);
-  double *Z_d = nullptr, *tsave = nullptr;
-  NSB_CUDA(cudaMalloc(&Z_d, sizeof(double) * (size_t)k * k));
+  // Z and the saved %time row live in a scratch buffer kept by the context (no allocation per restart)
+  const size_t need = (size_t)k * k + (size_t)k;
+  if (ctx->rot_elems < need) {
+    NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->rot_d) cudaFree(ctx->rot_d);
+    ctx->rot_d = nullptr;
+    NSB_CUDA(cudaMalloc(&ctx->rot_d, sizeof(double) * need));
+    ctx->rot_elems = need;
+  }
+  double *Z_d = ctx->rot_d, *tsave = rotate_time ? nullptr : ctx->rot_d + (size_t)k * k;
   NSB_CUDA(cudaMemcpy2DAsync(Z_d, sizeof(double) * k, Z, sizeof(double) * ldz, sizeof(double) * k, k,
                              cudaMemcpyHostToDevice, ctx->stream));
-  if (!rotate_time) {
-    NSB_CUDA(cudaMalloc(&tsave, sizeof(double) * k));
+  if (!rotate_time)
     NSB_CUDA(cudaMemcpy2DAsync(tsave, sizeof(double), B->v_d + L->time_row, sizeof(double) * L->ld,
                                sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
+  // fp64 tensor-core kernel: k <= 104, whole slabs of 16 rows (ld is a multiple of 1024)
+  if (k <= 104 && ctx->rotate_dmma && !ctx->rotate_simple) {
+    const int nt8 = (k + 7) / 8 <= 7 ? 7 : 13;
+    int zp = 8 * nt8;
+    zp += (4 - zp % 16 + 16) % 16;                      // column pitch = 4 (mod 16): conflict-free B loads
+    const size_t smem = sizeof(double) * (size_t)nt8 * 8 * zp;
+    const int64_t nslab2 = L->ld / 16;
+    const int64_t want = (nslab2 + NT / 32 - 1) / (NT / 32);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * 2);
+    {
+      ProfScope ps(ctx, PC_ROTATE, 16.0 * (double)L->nact * k);
+      if (nt8 == 7) {
+        NSB_CUDA(cudaFuncSetAttribute(rotate_dmma_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rotate_dmma_kernel<7><<<grid, NT, smem, ctx->stream>>>(B->v_d, L->ld, k, Z_d, k, zp, nslab2);
+      } else {
+        NSB_CUDA(cudaFuncSetAttribute(rotate_dmma_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rotate_dmma_kernel<13><<<grid, NT, smem, ctx->stream>>>(B->v_d, L->ld, k, Z_d, k, zp, nslab2);
+      }
+    }
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    if (!rotate_time)
+      NSB_CUDA(cudaMemcpy2DAsync(B->v_d + L->time_row, sizeof(double) * L->ld, tsave, sizeof(double),
+                                 sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
+    NSB_CUDA(cudaStreamSynchronize(ctx->stream));     // Z is the caller's host memory
+    return NSB_OK;
   }
   // register-tiled kernel when the panel plus (part of) Z fit in shared memory
   {
@@ -1495,8 +1603,6 @@ extern "C" int nsb_basis_rotate(nsb_basis_t B, int k, const double *Z, int ldz, 
         NSB_CUDA(cudaMemcpy2DAsync(B->v_d + L->time_row, sizeof(double) * L->ld, tsave, sizeof(double),
                                    sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
       NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-      cudaFree(Z_d);
-      if (tsave) cudaFree(tsave);
       return NSB_OK;
     }
   }
@@ -1528,7 +1634,5 @@ extern "C" int nsb_basis_rotate(nsb_basis_t B, int k, const double *Z, int ldz, 
     NSB_CUDA(cudaMemcpy2DAsync(B->v_d + L->time_row, sizeof(double) * L->ld, tsave, sizeof(double),
                                sizeof(double), k, cudaMemcpyDeviceToDevice, ctx->stream));
   NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(Z_d);
-  if (tsave) cudaFree(tsave);
   return NSB_OK;
 }

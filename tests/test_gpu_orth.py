@@ -170,3 +170,37 @@ def test_weighted_qr_matches_qr_dec(ctx):
     for j in range(k):
         rec = sum(R[i, j] * download(B[i]).f[0] for i in range(j + 1))
         assert np.max(np.abs(rec - X[j].f[0].ravel())) <= 1e-11 * max(np.max(np.abs(X[j].f[0])), 1.0)
+
+
+@pytest.mark.parametrize('k', [5, 37, 56, 57, 100, 104, 105, 130])
+def test_basis_rotation_all_kernel_variants(ctx, k):
+    """Q(:,1:k) <- Q(:,1:k) Z (schur_condensation, core/eigensolvers.f90:433-442): k <= 104 runs on the fp64 tensor
+    cores (two template sizes, k not a multiple of 4 / 8 included), larger k on the register-tiled kernel; pressure
+    rows and pads are rotated too, %time only on request, columns >= k stay untouched."""
+    import nekstab_next_b200 as nb
+    rng = np.random.default_rng(k)
+    n, npr = 3000, 700
+    lay = nb.Layout(ctx, [n, n, npr], [True, True, False], time_in_dot=True)
+    lay.set_weight([np.ones(n), np.ones(n)])
+    B = nb.Basis(lay, k + 2)
+    cols = [[rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(npr)] for _ in range(k + 2)]
+    times = rng.standard_normal(k + 2)
+    for c in range(k + 2):
+        B[c].upload(cols[c], times[c])
+    Z = rng.standard_normal((k, k))
+    for rot_t in (False, True):
+        B.rotate(k, Z, rotate_time=rot_t)
+        for f in range(3):
+            M = np.stack([cols[c][f] for c in range(k)], axis=1) @ Z
+            for c in (0, k // 2, k - 1):
+                assert relerr(B[c].download()[0][f], M[:, c]) <= 1e-13
+            for c in range(k):
+                cols[c][f] = M[:, c]
+        if rot_t:
+            times[:k] = times[:k] @ Z
+        for c in (0, k - 1):
+            assert abs(B[c].download()[1] - times[c]) <= 1e-12 * max(1.0, abs(times[c]))
+    for c in (k, k + 1):
+        got, t = B[c].download()
+        assert np.array_equal(got[0], cols[c][0]) and np.array_equal(got[2], cols[c][2]) and t == times[c]
+    B.close(); lay.close()
