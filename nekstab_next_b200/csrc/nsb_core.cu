@@ -202,6 +202,7 @@ extern "C" int nsb_finalize(nsb_context_t ctx) {
   clear_step_graphs(ctx);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
   if (ctx->rot_d) cudaFree(ctx->rot_d);
+  if (ctx->gram_d) cudaFree(ctx->gram_d);
   if (ctx->ticket_d) cudaFree(ctx->ticket_d);
   if (ctx->flag_d) cudaFree(ctx->flag_d);
   if (ctx->seq_d) cudaFree(ctx->seq_d);

@@ -98,6 +98,8 @@ struct nsb_context_s {
   bool ax_generic = false;     // NSB_AX_GENERIC=1: use the generic-order axhelm kernel for N = 7 too
   bool rotate_simple = false;  // NSB_ROTATE_SIMPLE=1: first (untiled) rotation kernel
   bool rotate_dmma = true;     // NSB_ROTATE_DMMA=0: register-tiled FMA rotation instead of the fp64 tensor-core kernel
+  double *gram_d = nullptr;    // per-CTA tile sums of nsb_basis_gram
+  size_t gram_elems = 0;
   double *rot_d = nullptr;     // Z and the saved %time row of nsb_basis_rotate
   size_t rot_elems = 0;
   int ax_stages = 0;           // NSB_AX_STAGES: ring depth of the N = 7 axhelm kernels (0: default; DMMA: = warp groups pins one buffer per group)

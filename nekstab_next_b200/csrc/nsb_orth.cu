@@ -469,6 +469,103 @@ rotate_dmma_kernel(double *__restrict__ V, int64_t ld, int k, const double *__re
   }
 }
 
+
+// ---- Gram matrix G = V^T W V in ONE pass over V, on the fp64 tensor cores -----------------------
+// The orthonormality check of the reference (orthonormality.dat, core/eigensolvers.f90:335-345).  Round 1 ran
+// one multi-column dot per column (V crossed HBM k times: 4.1 TB at the benchmark size).  Here a block
+// G[P-panel, Q-panel] of up to 104 x 104 entries is formed while the two column panels stream by once:
+// mma.m8n8k4.f64 with the contraction over ROWS -- lane (g, t) loads V[r0 + t, c0 + g] straight from global
+// memory (the element that is A[g][t] of (W o V)^T for column group c0 and B[t][g] of V for the same group, so
+// one load serves both operands); a warp owns a fixed set of 8 x 8 output tiles (compile-time tile list per
+// warp), all eight warps of a CTA walk the same 4-row slabs (seven of them hit L1).  Diagonal blocks compute
+// the upper triangle only.  Per-CTA tile sums go to a partial buffer and are added in a fixed order.
+constexpr int kGramNG = 13;                                   // column groups of 8 per panel (104 columns)
+
+template <bool DIAG>
+struct GramTiles {
+  static constexpr int count = DIAG ? kGramNG * (kGramNG + 1) / 2 : kGramNG * kGramNG;
+  __host__ __device__ static constexpr int row(int t) {
+    if (!DIAG) return t / kGramNG;
+    int i = 0, rem = t;
+    while (rem >= kGramNG - i) { rem -= kGramNG - i; ++i; }
+    return i;
+  }
+  __host__ __device__ static constexpr int col(int t) {
+    if (!DIAG) return t % kGramNG;
+    int i = 0, rem = t;
+    while (rem >= kGramNG - i) { rem -= kGramNG - i; ++i; }
+    return i + rem;
+  }
+};
+
+// compile-time unrolled loops over this warp's tiles: the fragment indices must be constants (register arrays)
+template <bool DIAG, int WARP, int Q, int NMINE>
+__device__ __forceinline__ void gram_mma_tiles(double2 (&acc)[NMINE], const double (&fa)[kGramNG],
+                                               const double (&fb)[kGramNG], double wv) {
+  if constexpr (Q < NMINE) {
+    constexpr int tile = WARP + (NT / 32) * Q;
+    constexpr int ti = GramTiles<DIAG>::row(tile), tj = GramTiles<DIAG>::col(tile);
+    dmma884_acc(acc[Q], wv * fa[ti], DIAG ? fa[tj] : fb[tj]);
+    gram_mma_tiles<DIAG, WARP, Q + 1, NMINE>(acc, fa, fb, wv);
+  }
+}
+
+template <bool DIAG, int WARP>
+__device__ __forceinline__ void gram_warp(const double *__restrict__ Va, const double *__restrict__ Vb, int64_t ld, int ka,
+                                          int kb, const double *__restrict__ W, int64_t nslabs, double *__restrict__ out) {
+  using T = GramTiles<DIAG>;
+  constexpr int NW = NT / 32, NMINE = (T::count - WARP + NW - 1) / NW;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double2 acc[NMINE];
+#pragma unroll
+  for (int q = 0; q < NMINE; ++q) acc[q] = make_double2(0.0, 0.0);
+  for (int64_t sl = blockIdx.x; sl < nslabs; sl += gridDim.x) {
+    const int64_t r = sl * 4 + t;
+    const double wv = W[r];
+    double fa[kGramNG], fb[kGramNG];
+#pragma unroll
+    for (int c = 0; c < kGramNG; ++c) {
+      const int ca = 8 * c + g;
+      fa[c] = ca < ka ? Va[(int64_t)ca * ld + r] : 0.0;
+      fb[c] = (!DIAG && ca < kb) ? Vb[(int64_t)ca * ld + r] : 0.0;
+    }
+    gram_mma_tiles<DIAG, WARP, 0, NMINE>(acc, fa, fb, wv);
+  }
+#pragma unroll
+  for (int q = 0; q < NMINE; ++q) {
+    const int tile = WARP + NW * q;
+    double *o = out + ((size_t)blockIdx.x * T::count + tile) * 64 + g * 8 + 2 * t;
+    o[0] = acc[q].x;
+    o[1] = acc[q].y;
+  }
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(NT, DIAG ? 2 : 1)
+gram_dmma_kernel(const double *__restrict__ Va, const double *__restrict__ Vb, int64_t ld, int ka, int kb,
+                 const double *__restrict__ W, int64_t nslabs, double *__restrict__ out) {
+  switch (threadIdx.x >> 5) {
+    case 0: gram_warp<DIAG, 0>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    case 1: gram_warp<DIAG, 1>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    case 2: gram_warp<DIAG, 2>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    case 3: gram_warp<DIAG, 3>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    case 4: gram_warp<DIAG, 4>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    case 5: gram_warp<DIAG, 5>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    case 6: gram_warp<DIAG, 6>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+    default: gram_warp<DIAG, 7>(Va, Vb, ld, ka, kb, W, nslabs, out); break;
+  }
+}
+
+// out[e] = sum over CTAs of part[cta * n + e], fixed order
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double *__restrict__ part, int nblk, int64_t n,
+                                                          double *__restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * n + e];
+  out[e] = s;
+}
+
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
@@ -1500,13 +1597,62 @@ extern "C" int nsb_set_dgks_eta(nsb_context_t ctx, double eta) {
 
 extern "C" int nsb_basis_gram(nsb_basis_t B, int k, double *G, int ldg) {
   NSB_REQUIRE(B && G && k >= 1 && k <= B->ncols && k <= kMaxK && ldg >= k, "nsb_basis_gram: bad argument");
-  nsb_context_t ctx = B->lay->ctx;
-  for (int j = 0; j < k; ++j) {
-    NSB_CHECK(weighted_multidot(B, k, B->col(j), ctx->hvec_d));
-    NSB_CUDA(cudaMemcpyAsync(ctx->hpin, ctx->hvec_d, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = L->ctx;
+  cudaSetDevice(ctx->device);
+  constexpr int PW = 8 * kGramNG;                               // panel width, 104 columns
+  const int np = (k + PW - 1) / PW;
+  const int64_t nslabs = L->ndot / 4;                           // the inner product covers rows [0, ndot)
+  const int grid = (int)std::min<int64_t>(nslabs, (int64_t)ctx->num_sms * 2);
+  const int64_t nfull = (int64_t)GramTiles<false>::count * 64;  // entries of one (off-diagonal) block
+  // partial tile sums of every CTA + the reduced block, in a scratch buffer kept by the context
+  const size_t need = (size_t)grid * nfull + nfull;
+  if (ctx->gram_elems < need) {
     NSB_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(G + (size_t)j * ldg, ctx->hpin, sizeof(double) * k);
+    if (ctx->gram_d) cudaFree(ctx->gram_d);
+    ctx->gram_d = nullptr;
+    NSB_CUDA(cudaMalloc(&ctx->gram_d, sizeof(double) * need));
+    ctx->gram_elems = need;
   }
+  double *part = ctx->gram_d, *blk = ctx->gram_d + (size_t)grid * nfull;
+  std::vector<double> host((size_t)nfull);
+  for (int P = 0; P < np; ++P)
+    for (int Q = P; Q < np; ++Q) {
+      const bool diag = P == Q;
+      const int ka = std::min(PW, k - P * PW), kb = std::min(PW, k - Q * PW);
+      const int ntiles = diag ? GramTiles<true>::count : GramTiles<false>::count;
+      const int64_t n = (int64_t)ntiles * 64;
+      const int gridv = diag ? grid : (int)std::min<int64_t>(nslabs, (int64_t)ctx->num_sms);   // 1 CTA / SM off the diagonal
+      {
+        // algorithmic bytes: the two column panels and W once
+        ProfScope ps(ctx, PC_MULTIDOT, 8.0 * (double)(L->ndof_dot + 1) * (diag ? ka + 1 : ka + kb + 1));
+        if (diag)
+          gram_dmma_kernel<true><<<gridv, NT, 0, ctx->stream>>>(B->col(P * PW), B->col(Q * PW), L->ld, ka, kb, L->w_d, nslabs, part);
+        else
+          gram_dmma_kernel<false><<<gridv, NT, 0, ctx->stream>>>(B->col(P * PW), B->col(Q * PW), L->ld, ka, kb, L->w_d, nslabs, part);
+      }
+      gram_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(part, gridv, n, blk);
+      ctx->launches += 2;
+      NSB_CUDA(cudaGetLastError());
+      if (ctx->nranks > 1)
+        for (int64_t o = 0; o < n; o += kMaxK) NSB_CHECK(allreduce_sum_d(ctx, blk + o, (int)std::min<int64_t>(kMaxK, n - o)));
+      NSB_CUDA(cudaMemcpyAsync(host.data(), blk, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      NSB_CUDA(cudaStreamSynchronize(ctx->stream));
+      NSB_CHECK(check_dev_err(ctx));
+      for (int tIdx = 0; tIdx < ntiles; ++tIdx) {
+        const int ti = diag ? GramTiles<true>::row(tIdx) : GramTiles<false>::row(tIdx);
+        const int tj = diag ? GramTiles<true>::col(tIdx) : GramTiles<false>::col(tIdx);
+        for (int a = 0; a < 8; ++a)
+          for (int b = 0; b < 8; ++b) {
+            const int i = P * PW + ti * 8 + a, j = Q * PW + tj * 8 + b;
+            if (i >= k || j >= k || ti * 8 + a >= ka || tj * 8 + b >= kb) continue;
+            const double v = host[(size_t)tIdx * 64 + a * 8 + b];
+            if (diag && ti == tj && b < a) continue;            // the strict lower part of a diagonal tile is mirrored
+            G[(size_t)j * ldg + i] = v;
+            G[(size_t)i * ldg + j] = v;
+          }
+      }
+    }
   return NSB_OK;
 }
 
