@@ -169,6 +169,129 @@ int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st) {
   return NSB_OK;
 }
 
+
+// ---- fused interface path of the gather-scatter (peer-memory transport) --------------------------
+// send : one thread per interface node -- sum its local copies (all nf fields), keep the sum in node_sum and
+//        store it straight into the mailbox region of every peer sharing the node; the CTA drawing the last
+//        ticket bumps the mesh's sequence number and release-stores it into the peers' flag words.
+// recv : thread 0 of every CTA waits for all neighbours' flags (bounded), then one thread per interface node adds
+//        the neighbours' contributions in ascending rank order (bitwise the same on both sides of an interface)
+//        and scatters the result (plain dssum or the fused operator tail alpha u + beta bmask sum).
+// Two launches instead of 3 + 2 P (sum, pack x P, flags, wait+unpack x P, scatter).
+struct HaloPeers {
+  double *dst[nsb_context_s::kMaxPeers];            // my region in the peer's mailbox (slot 0)
+  const double *src[nsb_context_s::kMaxPeers];      // the peer's region in my mailbox (slot 0)
+  uint64_t *flag_out[nsb_context_s::kMaxPeers];     // my flag word in the peer's mailbox (slot 0)
+  const uint64_t *flag_in[nsb_context_s::kMaxPeers];
+  int64_t n[nsb_context_s::kMaxPeers];              // nodes shared with the peer
+  int npeers, P, ns_fields;
+};
+
+__global__ void __launch_bounds__(256)
+halo_send_kernel(const double *__restrict__ v, const int64_t *__restrict__ off, const int32_t *__restrict__ idx,
+                 int64_t n0, int64_t nifc, int nf, int64_t fstride, double *__restrict__ node_sum,
+                 const int32_t *__restrict__ poff, const int64_t *__restrict__ pent, HaloPeers hp,
+                 unsigned long long *seq_d, unsigned int *ticket) {
+  const int slot = (int)((*seq_d + 1ull) & 1ull);
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < nifc) {
+    const int64_t a = off[n0 + m], b = off[n0 + m + 1];
+    const int pa = poff[m], pb = poff[m + 1];
+    for (int f = 0; f < nf; ++f) {
+      const double *vf = v + (int64_t)f * fstride;
+      double sum = 0.0;
+      for (int64_t q = a; q < b; ++q) sum += vf[idx[q]];
+      node_sum[(int64_t)f * nifc + m] = sum;
+      for (int e = pa; e < pb; ++e) {
+        const int64_t ent = pent[e];
+        const int pi = (int)(ent >> 32);
+        const int64_t pos = ent & 0xffffffffll;
+        hp.dst[pi][(int64_t)slot * hp.ns_fields * hp.n[pi] + (int64_t)f * hp.n[pi] + pos] = sum;   // peer store
+      }
+    }
+  }
+  __shared__ unsigned int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) {
+    s_seq = ++(*seq_d);
+    *ticket = 0;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < hp.npeers) st_release_sys(hp.flag_out[threadIdx.x] + (s_seq & 1) * hp.P, s_seq);
+}
+
+template <int EPI>   // 3: v <- sum ; 4: v <- alpha uin + beta bnode sum
+__global__ void __launch_bounds__(256)
+halo_recv_kernel(double *__restrict__ v, const int64_t *__restrict__ off, const int32_t *__restrict__ idx, int64_t n0,
+                 int64_t nifc, int nf, int64_t fstride, const double *__restrict__ node_sum,
+                 const int32_t *__restrict__ poff, const int64_t *__restrict__ pent, HaloPeers hp,
+                 const unsigned long long *__restrict__ seq_d, int *err, const double *__restrict__ uin, double alpha,
+                 double beta, const double *__restrict__ bnode, const double *__restrict__ bmask) {
+  const uint64_t seq = *seq_d;
+  const int slot = (int)(seq & 1);
+  if ((int)threadIdx.x < hp.npeers) spin_until(hp.flag_in[threadIdx.x] + (size_t)slot * hp.P, seq, err, DEVERR_HALO_TIMEOUT);
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nifc) return;
+  const int64_t a = off[n0 + m], b = off[n0 + m + 1];
+  const int pa = poff[m], pb = poff[m + 1];
+  for (int f = 0; f < nf; ++f) {
+    double sum = node_sum[(int64_t)f * nifc + m];
+    for (int e = pa; e < pb; ++e) {                 // entries are stored in ascending peer rank
+      const int64_t ent = pent[e];
+      const int pi = (int)(ent >> 32);
+      const int64_t pos = ent & 0xffffffffll;
+      sum += ld_relaxed_sys(hp.src[pi] + (int64_t)slot * hp.ns_fields * hp.n[pi] + (int64_t)f * hp.n[pi] + pos);
+    }
+    double *vf = v + (int64_t)f * fstride;
+    for (int64_t q = a; q < b; ++q) {
+      const int32_t p = idx[q];
+      if (EPI == 3) vf[p] = sum;
+      else vf[p] = alpha * uin[(int64_t)f * fstride + p] + beta * (bnode ? bnode[n0 + m] : bmask[p]) * sum;
+    }
+  }
+}
+
+int halo_exchange_fused(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const double *uin, double alpha,
+                        double beta, const double *bmask, cudaStream_t st) {
+  nsb_context_t ctx = S->ctx;
+  const int P = ctx->nranks;
+  const int64_t nifc = S->nshared - S->n_local;
+  HaloPeers hp;
+  hp.npeers = (int)S->peers.size();
+  hp.P = P;
+  hp.ns_fields = S->ns_fields;
+  for (int i = 0; i < hp.npeers; ++i) {
+    const auto &Pr = S->peers[i];
+    hp.dst[i] = ctx->peer_mail[Pr.rank] + mb_halo_base(P) + Pr.peer_off;
+    hp.src[i] = ctx->mail_d + mb_halo_base(P) + Pr.my_off;
+    hp.flag_out[i] = reinterpret_cast<uint64_t *>(ctx->peer_mail[Pr.rank] + mb_halo_base(P) + S->peer_flag_off[Pr.rank]) + ctx->rank;
+    hp.flag_in[i] = reinterpret_cast<const uint64_t *>(ctx->mail_d + mb_halo_base(P) + S->halo_flag_off) + Pr.rank;
+    hp.n[i] = Pr.n;
+  }
+  const unsigned nb = (unsigned)((nifc + 255) / 256);
+  halo_send_kernel<<<nb, 256, 0, st>>>(v, S->gs_off_d, S->gs_idx_d, S->n_local, nifc, nf, fstride, S->node_sum_d,
+                                      S->ifc_poff_d, S->ifc_pent_d, hp, S->hx_seq_d, S->hx_ticket_d);
+  const double *bnode = (bmask && bmask == S->bmask_d) ? S->bnode_d : nullptr;
+  if (epi == 0)
+    halo_recv_kernel<3><<<nb, 256, 0, st>>>(v, S->gs_off_d, S->gs_idx_d, S->n_local, nifc, nf, fstride, S->node_sum_d,
+                                           S->ifc_poff_d, S->ifc_pent_d, hp, S->hx_seq_d, ctx->dev_err_d, nullptr, 0.0,
+                                           0.0, nullptr, nullptr);
+  else
+    halo_recv_kernel<4><<<nb, 256, 0, st>>>(v, S->gs_off_d, S->gs_idx_d, S->n_local, nifc, nf, fstride, S->node_sum_d,
+                                           S->ifc_poff_d, S->ifc_pent_d, hp, S->hx_seq_d, ctx->dev_err_d, uin, alpha, beta,
+                                           bnode, bmask);
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 int comm_init(nsb_context_t ctx, const void *unique_id) {
   NSB_CHECK(load_nccl());
   static_assert(sizeof(ncclUniqueId) <= NSB_UNIQUE_ID_BYTES, "unique id size");
@@ -341,6 +464,35 @@ int exchange_setup(nsb_sem_t S) {
     NSB_CUDA(cudaMalloc(&Pr.recv_d, sizeof(double) * Pr.n * S->ns_fields));
     NSB_CUDA(cudaMemcpy(Pr.idx_d, nodes.data(), sizeof(int32_t) * Pr.n, cudaMemcpyHostToDevice));
     S->peers.push_back(Pr);
+  }
+  // per interface node: the peers sharing it and its position in each peer's packed list (ascending peer rank),
+  // for the fused send / recv kernels
+  {
+    std::vector<std::vector<int64_t>> ent((size_t)(nifc > 0 ? nifc : 0));
+    for (size_t pi = 0; pi < S->peers.size(); ++pi) {
+      const std::vector<int32_t> &nodes = plan.peer_nodes[S->peers[pi].rank];
+      for (size_t t = 0; t < nodes.size(); ++t) ent[nodes[t]].push_back(((int64_t)pi << 32) | (int64_t)t);
+    }
+    std::vector<int32_t> poff((size_t)nifc + 1, 0);
+    std::vector<int64_t> pent;
+    for (int64_t m = 0; m < nifc; ++m) {
+      poff[m] = (int32_t)pent.size();
+      pent.insert(pent.end(), ent[m].begin(), ent[m].end());
+    }
+    poff[nifc] = (int32_t)pent.size();
+    if (S->ifc_poff_d) cudaFree(S->ifc_poff_d);
+    if (S->ifc_pent_d) cudaFree(S->ifc_pent_d);
+    S->ifc_poff_d = nullptr;
+    S->ifc_pent_d = nullptr;
+    NSB_CUDA(cudaMalloc(&S->ifc_poff_d, sizeof(int32_t) * poff.size()));
+    NSB_CUDA(cudaMalloc(&S->ifc_pent_d, sizeof(int64_t) * (pent.empty() ? 1 : pent.size())));
+    NSB_CUDA(cudaMemcpy(S->ifc_poff_d, poff.data(), sizeof(int32_t) * poff.size(), cudaMemcpyHostToDevice));
+    if (!pent.empty())
+      NSB_CUDA(cudaMemcpy(S->ifc_pent_d, pent.data(), sizeof(int64_t) * pent.size(), cudaMemcpyHostToDevice));
+    if (!S->hx_ticket_d) {
+      NSB_CUDA(cudaMalloc(&S->hx_ticket_d, sizeof(unsigned int)));
+      NSB_CUDA(cudaMemset(S->hx_ticket_d, 0, sizeof(unsigned int)));
+    }
   }
   // 5. peer-memory halo: reserve this mesh's flag words and one data region per peer in MY mailbox (bump
   //    allocator over the halo area, so several meshes on one context never overlap) and tell every peer

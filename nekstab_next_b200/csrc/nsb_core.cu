@@ -162,6 +162,7 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   if (const char *e = getenv("NSB_ROTATE_DMMA")) ctx->rotate_dmma = e[0] != '0';
   if (const char *e = getenv("NSB_FUSED_ALLWARPS")) ctx->fused_allwarps = e[0] != '0';
   if (const char *e = getenv("NSB_TAIL")) ctx->tail = e[0] != '0';
+  if (const char *e = getenv("NSB_HALO_FUSED")) ctx->halo_fused = e[0] != '0';
   if (const char *e = getenv("NSB_GRAPH")) ctx->use_graph = e[0] != '0';
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   NSB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

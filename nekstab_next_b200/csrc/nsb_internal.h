@@ -106,6 +106,7 @@ struct nsb_context_s {
   bool fused_priv = true;      // NSB_FUSED_PRIV=0: per-block warp reduction in the fused kernel's second projection
   bool fused_allwarps = true;  // NSB_FUSED_ALLWARPS=0: warp 0 alone combines the row sums (two barriers per block)
   double dgks_eta2 = 0.5;      // DGKS: second projection when |w'|^2 < eta^2 |w|^2 (nsb_set_dgks_eta; default eta = 1/sqrt 2)
+  bool halo_fused = true;      // NSB_HALO_FUSED=0: sum / pack / flags / unpack / scatter as separate launches
   bool tail = true;            // NSB_TAIL=0: separate reduce / all-reduce / add launches (round-1 structure)
   bool ax_dmma = true;         // NSB_AX_DMMA=0: vector-FMA contraction in the ring kernel instead of DMMA
   bool ax_ring = true;         // NSB_AX_RING=0: warp-per-element kernel instead of the TMA ring (N = 7)
@@ -190,6 +191,9 @@ struct nsb_sem_s {
   double *diagA_d = nullptr;     // diagonal of A per local point (setprec), computed at the first solve
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
   unsigned long long *hx_seq_d = nullptr;  // device sequence number of this mesh's halo exchanges
+  unsigned int *hx_ticket_d = nullptr;     // last-CTA ticket of the fused send kernel
+  int32_t *ifc_poff_d = nullptr;           // per interface node: CSR offsets into ifc_pent_d
+  int64_t *ifc_pent_d = nullptr;           // (peer index << 32 | position in that peer's packed list), ascending rank
   int64_t halo_flag_off = -1;    // offset (doubles, from the halo base) of this mesh's flag words [2][P] in MY mailbox
   std::vector<int64_t> peer_flag_off;   // the same offset in every peer's mailbox
   int64_t halo_region_doubles = 0;      // size of this mesh's reservation in the halo area
@@ -243,6 +247,9 @@ void clear_step_graphs(nsb_context_t ctx);                     // any handle a c
 int sendrecv_d(nsb_context_t ctx, const std::vector<nsb_sem_s::Peer> &peers, int nf, cudaStream_t st);
 int exchange_setup(nsb_sem_t sem);
 int halo_exchange_p2p(nsb_sem_t S, int nf, cudaStream_t st);  // pack -> peer stores -> flags -> wait -> add
+// sum + peer stores + flags in one kernel, wait + add + scatter in a second (peer-memory transport)
+int halo_exchange_fused(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const double *uin, double alpha,
+                        double beta, const double *bmask, cudaStream_t st);
 // host-only plans (also reachable through nsb_host_gs_plan / nsb_host_exchange_plan for CPU tests)
 int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
             std::vector<int32_t> &idx, std::vector<int64_t> &gid, std::vector<double> *vmult,

@@ -1164,6 +1164,16 @@ int launch_gs(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const do
   double *ns = S->node_sum_d;
   NSB_CUDA(cudaEventRecord(S->ev_a, ctx->stream));
   NSB_CUDA(cudaStreamWaitEvent(s2, S->ev_a, 0));
+  if (S->p2p_halo && ctx->halo_fused) {
+    // peer-memory transport: two kernels for the whole interface path
+    NSB_CHECK(halo_exchange_fused(S, v, nf, fstride, epi, uin, alpha, beta, bmask, s2));
+    NSB_CUDA(cudaEventRecord(S->ev_b, s2));
+    if (epi == 0) gs_launch<0>(S, ctx->stream, v, 0, nloc, nf, fstride, nullptr, 0, 0, nullptr, nullptr, 0);
+    else gs_launch<1>(S, ctx->stream, v, 0, nloc, nf, fstride, uin, alpha, beta, bmask, nullptr, 0);
+    NSB_CUDA(cudaStreamWaitEvent(ctx->stream, S->ev_b, 0));
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
   gs_launch<2>(S, s2, v, nloc, S->nshared, nf, fstride, nullptr, 0, 0, nullptr, ns, nifc);
   if (S->p2p_halo) {
     NSB_CHECK(halo_exchange_p2p(S, nf, s2));   // stores into the peers' mailboxes, no NCCL launch
@@ -1528,6 +1538,9 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
     S->ctx->halo_used = 0;
   }
   if (S->hx_seq_d) cudaFree(S->hx_seq_d);
+  if (S->hx_ticket_d) cudaFree(S->hx_ticket_d);
+  if (S->ifc_poff_d) cudaFree(S->ifc_poff_d);
+  if (S->ifc_pent_d) cudaFree(S->ifc_pent_d);
   for (auto &P : S->peers) {
     cudaFree(P.idx_d);
     cudaFree(P.send_d);

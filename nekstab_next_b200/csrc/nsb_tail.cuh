@@ -160,11 +160,31 @@ __device__ __forceinline__ void orth_tail(const OrthTail &t) {
   if (!s_last) return;
   __threadfence();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < t.kout; j += nw) {          // same summation order as reduce_partials_kernel
-    double s = 0.0;
-    for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(t.partial + (size_t)b * t.pstride + j);
-    s = warp_reduce_sum(s);
-    if (lane == 0) t.out[j] = s;
+  // Same summation order as reduce_partials_kernel (per lane the rows b = lane, lane + 32, ... in turn, then the
+  // shuffle tree), but a warp takes FOUR columns per round and the row loop is unrolled, so 16 independent L2
+  // loads are in flight per lane: one warp walking one column with dependent loads cost ~50 us per k-column
+  // tail (8 GPUs, round 2: multidot / fused 12-16 % over 1/8 of their single-GPU time, update -- a one-column
+  // tail -- exactly on it).  Columns past kout are read (inside the partial buffer) and dropped.
+  for (int j0 = 4 * warp; j0 < t.kout; j0 += 4 * nw) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+    for (unsigned b = lane; b < gridDim.x; b += 32) {
+      const double *p = t.partial + (size_t)b * t.pstride + j0;
+      s0 += __ldcg(p);
+      s1 += __ldcg(p + 1);
+      s2 += __ldcg(p + 2);
+      s3 += __ldcg(p + 3);
+    }
+    s0 = warp_reduce_sum(s0);
+    s1 = warp_reduce_sum(s1);
+    s2 = warp_reduce_sum(s2);
+    s3 = warp_reduce_sum(s3);
+    if (lane == 0) {
+      t.out[j0] = s0;
+      if (j0 + 1 < t.kout) t.out[j0 + 1] = s1;
+      if (j0 + 2 < t.kout) t.out[j0 + 2] = s2;
+      if (j0 + 3 < t.kout) t.out[j0 + 3] = s3;
+    }
   }
   if (threadIdx.x == 0) *t.ticket = 0;   // ready for the next launch (stream order)
   __syncthreads();
