@@ -114,6 +114,21 @@ int nsb_layout_info(nsb_layout_t layout, int64_t *ld, int64_t *ndot, int64_t *nd
  * same pointer several times to reuse bm1s for vx, vy, vz like the reference does. */
 int nsb_layout_set_weight(nsb_layout_t layout, const double *const *weight_per_dot_field);
 
+/* C0 layout (optional): the first n_c0 fields are CONTINUOUS fields on `sem`'s mesh and are stored once per
+ * distinct node instead of once per element-local point (Nek duplicates shared nodes: 16.78 M local points for
+ * 11.39 M nodes on the 32^3, N = 7 box).  For continuous fields the reference's inner product
+ * sum_local a bm1s b (core/krylov_subspace.f90:40-49) equals sum_nodes a (QQ^T bm1s) b, which is what the
+ * kernels then compute -- every sweep over the basis moves 32 % fewer bytes, results are the same to rounding.
+ * The host side is unchanged: field_len[] are the element-local lengths, nsb_layout_set_weight takes the
+ * element-local bm1s, nsb_vec_upload / nsb_vec_download exchange element-local arrays (upload keeps the first
+ * copy of a shared node -- the field must be continuous; use nsb_layout_create for anything else).  Device
+ * operators: nsb_op_create_sem works on the layout's mesh; the time-stepper pieces need the element-local layout.
+ * Call after nsb_sem_setup_exchange. */
+int nsb_layout_create_c0(nsb_context_t ctx, nsb_sem_t sem, int nfields, const int64_t *field_len,
+                         const int *field_in_dot, int time_in_dot, int n_c0, nsb_layout_t *layout);
+/* n_c0 (0 for an element-local layout) and the rows stored per C0 field */
+int nsb_layout_is_c0(nsb_layout_t layout, int *n_c0, int64_t *stored_rows_per_field);
+
 /* ---------------------------------------------------------------------------------------------
  * Basis: device-resident column-major tall-skinny fp64 array V[ld, ncols]; a (basis, col) pair
  * is one nek_dvector.  Replaces allocate(Q(k_dim+1)) (core/eigensolvers.f90:149,

@@ -40,6 +40,8 @@ PROTOTYPES = {
     'nsb_allreduce_host': (C.c_int, [H, c_double_p, C.c_int]),
     'nsb_flush_l2': (C.c_int, [H]),
     'nsb_layout_create': (C.c_int, [H, C.c_int, c_i64_p, c_int_p, C.c_int, c_void_pp]),
+    'nsb_layout_create_c0': (C.c_int, [H, H, C.c_int, c_i64_p, c_int_p, C.c_int, C.c_int, c_void_pp]),
+    'nsb_layout_is_c0': (C.c_int, [H, c_int_p, c_i64_p]),
     'nsb_layout_destroy': (C.c_int, [H]),
     'nsb_layout_info': (C.c_int, [H, c_i64_p, c_i64_p, c_i64_p]),
     'nsb_layout_set_weight': (C.c_int, [H, c_dpp]),

@@ -154,7 +154,9 @@ class Layout:
     """Field lengths of one state vector {vx, vy, [vz], [pr], [t..]} + which enter the dot."""
 
     def __init__(self, ctx: Context, field_len: Sequence[int], field_in_dot: Sequence[bool],
-                 time_in_dot: bool = False):
+                 time_in_dot: bool = False, c0_sem: 'Optional[Sem]' = None, n_c0: int = 0):
+        """``c0_sem`` / ``n_c0``: store the first n_c0 (continuous) fields on the distinct nodes of that mesh
+        (nsb_layout_create_c0); field_len stays the element-local length, the host interface is unchanged."""
         self.ctx, self.lib = ctx, ctx.lib
         self.field_len = [int(n) for n in field_len]
         self.field_in_dot = [bool(b) for b in field_in_dot]
@@ -162,8 +164,16 @@ class Layout:
         fl = (C.c_int64 * self.nfields)(*self.field_len)
         fd = (C.c_int * self.nfields)(*[int(b) for b in self.field_in_dot])
         h = C.c_void_p()
-        check(self.lib.nsb_layout_create(ctx.h, self.nfields, fl, fd, int(time_in_dot), C.byref(h)))
+        if c0_sem is not None:
+            check(self.lib.nsb_layout_create_c0(ctx.h, c0_sem.h, self.nfields, fl, fd, int(time_in_dot),
+                                                int(n_c0 or self.nfields), C.byref(h)))
+            self._keep = c0_sem
+        else:
+            check(self.lib.nsb_layout_create(ctx.h, self.nfields, fl, fd, int(time_in_dot), C.byref(h)))
         self.h = h
+        nc0, rows = C.c_int(), C.c_int64()
+        check(self.lib.nsb_layout_is_c0(h, C.byref(nc0), C.byref(rows)))
+        self.n_c0, self.c0_rows = nc0.value, rows.value
         ld, ndot, ndof = C.c_int64(), C.c_int64(), C.c_int64()
         check(self.lib.nsb_layout_info(h, C.byref(ld), C.byref(ndot), C.byref(ndof)))
         self.ld, self.ndot, self.ndof_dot = ld.value, ndot.value, ndof.value

@@ -226,7 +226,8 @@ halo_send_kernel(const double *__restrict__ v, const int64_t *__restrict__ off, 
   if ((int)threadIdx.x < hp.npeers) st_release_sys(hp.flag_out[threadIdx.x] + (s_seq & 1) * hp.P, s_seq);
 }
 
-template <int EPI>   // 3: v <- sum ; 4: v <- alpha uin + beta bnode sum
+// 3: v <- sum ; 4: v <- alpha uin + beta bnode sum ; 5 (C0 layout): wu[node] <- alpha uu[node] + beta bnode sum
+template <int EPI>
 __global__ void __launch_bounds__(256)
 halo_recv_kernel(double *__restrict__ v, const int64_t *__restrict__ off, const int32_t *__restrict__ idx, int64_t n0,
                  int64_t nifc, int nf, int64_t fstride, const double *__restrict__ node_sum,
@@ -249,12 +250,53 @@ halo_recv_kernel(double *__restrict__ v, const int64_t *__restrict__ off, const 
       const int64_t pos = ent & 0xffffffffll;
       sum += ld_relaxed_sys(hp.src[pi] + (int64_t)slot * hp.ns_fields * hp.n[pi] + (int64_t)f * hp.n[pi] + pos);
     }
+    if (EPI == 5) {       // v / uin point at the first interface node of the unique layout, fstride = its field stride
+      v[(int64_t)f * fstride + m] = alpha * uin[(int64_t)f * fstride + m] + beta * bnode[n0 + m] * sum;
+      continue;
+    }
     double *vf = v + (int64_t)f * fstride;
     for (int64_t q = a; q < b; ++q) {
       const int32_t p = idx[q];
       if (EPI == 3) vf[p] = sum;
       else vf[p] = alpha * uin[(int64_t)f * fstride + p] + beta * (bnode ? bnode[n0 + m] : bmask[p]) * sum;
     }
+  }
+}
+
+static void fill_halo_peers(nsb_sem_t S, HaloPeers &hp);
+
+// C0 layout: the copies are read from the element-local scratch, the assembled interface nodes are written to the
+// unique layout (wu / uu point at boundary node 0 of field 0)
+int halo_exchange_fused_c0(nsb_sem_t S, const double *wloc, int nf, int64_t fs_loc, double *wu, const double *uu,
+                           int64_t fs_u, double alpha, double beta, cudaStream_t st) {
+  nsb_context_t ctx = S->ctx;
+  const int64_t nifc = S->nshared - S->n_local;
+  HaloPeers hp;
+  fill_halo_peers(S, hp);
+  const unsigned nb = (unsigned)((nifc + 255) / 256);
+  halo_send_kernel<<<nb, 256, 0, st>>>(wloc, S->gs_off_d, S->gs_idx_d, S->n_local, nifc, nf, fs_loc, S->node_sum_d,
+                                      S->ifc_poff_d, S->ifc_pent_d, hp, S->hx_seq_d, S->hx_ticket_d);
+  halo_recv_kernel<5><<<nb, 256, 0, st>>>(wu + S->n_local, S->gs_off_d, S->gs_idx_d, S->n_local, nifc, nf, fs_u, S->node_sum_d,
+                                         S->ifc_poff_d, S->ifc_pent_d, hp, S->hx_seq_d, ctx->dev_err_d, uu + S->n_local, alpha,
+                                         beta, S->bnode_d, nullptr);
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+static void fill_halo_peers(nsb_sem_t S, HaloPeers &hp) {
+  nsb_context_t ctx = S->ctx;
+  const int P = ctx->nranks;
+  hp.npeers = (int)S->peers.size();
+  hp.P = P;
+  hp.ns_fields = S->ns_fields;
+  for (int i = 0; i < hp.npeers; ++i) {
+    const auto &Pr = S->peers[i];
+    hp.dst[i] = ctx->peer_mail[Pr.rank] + mb_halo_base(P) + Pr.peer_off;
+    hp.src[i] = ctx->mail_d + mb_halo_base(P) + Pr.my_off;
+    hp.flag_out[i] = reinterpret_cast<uint64_t *>(ctx->peer_mail[Pr.rank] + mb_halo_base(P) + S->peer_flag_off[Pr.rank]) + ctx->rank;
+    hp.flag_in[i] = reinterpret_cast<const uint64_t *>(ctx->mail_d + mb_halo_base(P) + S->halo_flag_off) + Pr.rank;
+    hp.n[i] = Pr.n;
   }
 }
 

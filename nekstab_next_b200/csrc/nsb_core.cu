@@ -309,6 +309,7 @@ extern "C" int nsb_layout_create(nsb_context_t ctx, int nfields, const int64_t *
   L->ctx = ctx;
   L->nfields = nfields;
   L->len.assign(field_len, field_len + nfields);
+  L->hlen = L->len;
   L->in_dot.assign(field_in_dot, field_in_dot + nfields);
   L->off.assign(nfields, 0);
   L->time_in_dot = time_in_dot ? 1 : 0;
@@ -371,8 +372,12 @@ extern "C" int nsb_layout_set_weight(nsb_layout_t L, const double *const *w) {
   for (int f = 0; f < L->nfields; ++f) {
     if (!L->in_dot[f]) continue;
     NSB_REQUIRE(w[j] != nullptr, "nsb_layout_set_weight: weight %d is NULL", j);
-    NSB_CUDA(cudaMemcpyAsync(L->w_d + L->off[f], w[j], sizeof(double) * L->len[f],
-                             cudaMemcpyHostToDevice, ctx->stream));
+    if (f < L->c0_nfields) {
+      NSB_CHECK(c0_set_weight(L, f, w[j]));          // assembled weight on the distinct nodes
+    } else {
+      NSB_CUDA(cudaMemcpyAsync(L->w_d + L->off[f], w[j], sizeof(double) * L->len[f],
+                               cudaMemcpyHostToDevice, ctx->stream));
+    }
     ++j;
   }
   // %time enters the dot once globally: weight 1 on rank 0 only (the reference adds
@@ -440,7 +445,8 @@ extern "C" int nsb_vec_upload(nsb_basis_t B, int col, const double *const *field
   cudaSetDevice(L->ctx->device);
   double *c = B->col(col);
   NSB_CUDA(cudaMemsetAsync(c, 0, sizeof(double) * L->ld, s));
-  for (int f = 0; f < L->nfields; ++f) {
+  if (L->c0_nfields) NSB_CHECK(c0_upload(B, col, fields));
+  for (int f = L->c0_nfields; f < L->nfields; ++f) {
     if (!fields[f] || L->len[f] == 0) continue;
     NSB_CUDA(cudaMemcpyAsync(c + L->off[f], fields[f], sizeof(double) * L->len[f],
                              cudaMemcpyHostToDevice, s));
@@ -456,8 +462,9 @@ extern "C" int nsb_vec_download(nsb_basis_t B, int col, double *const *fields, d
   cudaStream_t s = L->ctx->stream;
   cudaSetDevice(L->ctx->device);
   const double *c = B->col(col);
+  if (fields && L->c0_nfields) NSB_CHECK(c0_download(B, col, fields));
   if (fields)
-    for (int f = 0; f < L->nfields; ++f) {
+    for (int f = L->c0_nfields; f < L->nfields; ++f) {
       if (!fields[f] || L->len[f] == 0) continue;
       NSB_CUDA(cudaMemcpyAsync(fields[f], c + L->off[f], sizeof(double) * L->len[f],
                                cudaMemcpyDeviceToHost, s));

@@ -119,7 +119,10 @@ struct nsb_context_s {
 struct nsb_layout_s {
   nsb_context_t ctx = nullptr;
   int nfields = 0;
-  std::vector<int64_t> len;      // active length of each field
+  std::vector<int64_t> len;      // stored length of each field (rows in a column)
+  std::vector<int64_t> hlen;     // length of the host-side array of each field (differs for C0 fields)
+  nsb_sem_t c0_sem = nullptr;    // C0 layout (nsb_c0.cu): fields [0, c0_nfields) live on the distinct nodes of this mesh
+  int c0_nfields = 0;
   std::vector<int> in_dot;
   std::vector<int64_t> off;      // row offset of each field inside a column
   int time_in_dot = 0;
@@ -187,6 +190,8 @@ struct nsb_sem_s {
   std::vector<Peer> peers;
   std::vector<int64_t> glo_h;    // kept for exchange setup
   bool exchange_ready = false;
+  double *c0_scratch_d = nullptr;   // element-local scratch of the C0 layout (2 x nf x npts)
+  size_t c0_scratch_elems = 0;
   double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z per system, d)
   double *diagA_d = nullptr;     // diagonal of A per local point (setprec), computed at the first solve
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes
@@ -262,6 +267,16 @@ struct ExchangePlan {
 };
 int exchange_plan(int rank, int nranks, const std::vector<int64_t> &gid, const std::vector<int64_t> &cnt,
                   const int64_t *all_sorted, int64_t mx, ExchangePlan &plan);
+// implemented in nsb_c0.cu (unique-node storage) / nsb_sem.cu / nsb_comm.cu
+int c0_upload(nsb_basis_t B, int col, const double *const *fields);
+int c0_download(nsb_basis_t B, int col, double *const *fields);
+int c0_set_weight(nsb_layout_t L, int f, const double *w_host);
+int c0_apply_sem(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
+int64_t c0_nint(nsb_sem_t S);
+int launch_axhelm_ext(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                      const double *cv, int epi, double alpha, double beta, const double *bmask);
+int halo_exchange_fused_c0(nsb_sem_t S, const double *wloc, int nf, int64_t fs_loc, double *wu, const double *uu,
+                           int64_t fs_u, double alpha, double beta, cudaStream_t st);
 // implemented in nsb_orth.cu
 int weighted_multidot(nsb_basis_t b, int k, const double *w_col_d, double *h_d);
 int upload_multidot_pipelined(nsb_basis_t B, int col_w, const double *const *fields, double time, int k,

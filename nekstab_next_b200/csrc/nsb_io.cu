@@ -168,9 +168,9 @@ extern "C" int nsb_fld_read_into(nsb_basis_t B, int col, const char *path, const
     for (int c = 0; c < ncomp; ++c) {
       const int f = dest_fields ? dest_fields[c] : -1;
       if (f < 0) continue;
-      NSB_REQUIRE(f < L->nfields && L->len[f] == nel_local * npt,
+      NSB_REQUIRE(f < L->nfields && L->hlen[f] == nel_local * npt,
                   "nsb_fld_read_into: layout field %d has %lld entries, file gives %lld", f,
-                  (long long)(f < L->nfields ? L->len[f] : -1), (long long)(nel_local * npt));
+                  (long long)(f < L->nfields ? L->hlen[f] : -1), (long long)(nel_local * npt));
       host[f].resize((size_t)(nel_local * npt));
       for (int64_t e = 0; e < nel_local; ++e) {
         const size_t base = off + ((size_t)pos_of_local[e] * ncomp + c) * npt * wd;

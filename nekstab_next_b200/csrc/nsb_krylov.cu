@@ -306,7 +306,7 @@ extern "C" int nsb_arnoldi(nsb_basis_t Q, nsb_op_t op, int mstart, int mend, int
   }
   int rc = NSB_OK;
   for (int m = mstart; m <= mend && rc == NSB_OK; ++m) {
-    if (op->kind == 1 && orth_mode == NSB_ORTH_CGS2 && ctx->pipeline_upload) {
+    if (op->kind == 1 && orth_mode == NSB_ORTH_CGS2 && ctx->pipeline_upload && !Q->lay->c0_sem) {
       // host operator: q_m goes to the host, the host matvec runs, f comes back in row chunks with the first
       // projection running on every chunk as it lands.  For a LINEAR operator (nsb_op_set_linear) the download
       // of q_m+1 already started during the third sweep of this step: the host then sees the un-normalised

@@ -1272,6 +1272,10 @@ int field_ptr(nsb_sem_t S, nsb_basis_t B, int col, int field, double **out, cons
 }  // namespace
 
 namespace nsb {
+int launch_axhelm_ext(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
+                      const double *cv, int epi, double alpha, double beta, const double *bmask) {
+  return launch_axhelm(S, u, w, nf, fstride, h1, h2, cv, epi, alpha, beta, bmask);
+}
 // Host plan of the gather-scatter: unique nodes owning at least one element-boundary point, CSR,
 // ordered by first local index so neighbouring threads touch neighbouring memory.
 int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
@@ -1557,6 +1561,7 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   for (double *q : {S->J_d, S->Dg_d, S->rxf_d, S->cfine_d[0], S->cfine_d[1]})
     if (q) cudaFree(q);
   if (S->pcg_d) cudaFree(S->pcg_d);
+  if (S->c0_scratch_d) cudaFree(S->c0_scratch_d);
   if (S->ev_a) cudaEventDestroy(S->ev_a);
   if (S->ev_b) cudaEventDestroy(S->ev_b);
   if (S->ev_c) cudaEventDestroy(S->ev_c);
@@ -2013,7 +2018,7 @@ extern "C" int nsb_op_create_host(nsb_layout_t L, nsb_host_matvec_fn fn, void *u
   op->hout.assign(L->nfields, nullptr);
   cudaSetDevice(L->ctx->device);
   for (int f = 0; f < L->nfields; ++f) {
-    const size_t nb = sizeof(double) * (size_t)(L->len[f] > 0 ? L->len[f] : 1);
+    const size_t nb = sizeof(double) * (size_t)(L->hlen[f] > 0 ? L->hlen[f] : 1);   // host-side (element-local) size
     NSB_CUDA(cudaMallocHost((void **)&op->hin[f], nb));
     NSB_CUDA(cudaMallocHost((void **)&op->hout[f], nb));
   }
@@ -2101,6 +2106,10 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
   nsb_layout_t L = bin->lay;
   NSB_REQUIRE(op->nfields_apply <= L->nfields, "nsb_op_apply: operator covers %d fields, layout has %d",
               op->nfields_apply, L->nfields);
+  if (L->c0_sem) {
+    NSB_REQUIRE(L->c0_sem == S, "nsb_op_apply: the C0 layout was built on another mesh");
+    return c0_apply_sem(op, bin, cin, bout, cout);
+  }
   // the applied fields are equally long, hence equally spaced inside a column: one batched
   // launch per kernel (grid.y = field) and one interface exchange for all components
   const int nfa = op->nfields_apply;
