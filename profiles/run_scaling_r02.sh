@@ -8,7 +8,7 @@ bash profiles/run_multirank_r02.sh "4 8" $OUT
 run_bench() {  # gpus tag env...
   local n=$1 tag=$2; shift 2
   env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
-    --master-port $((29800 + n)) bench.py --gpus $n --steps 3 --warmup 3 --no-e2e --no-dgks --no-cpu --no-single-rank-check \
+    --master-port $((29800 + n)) bench.py --gpus $n --steps 3 --warmup 3 --no-e2e --no-dgks --no-cpu --no-c0 --no-single-rank-check \
     > $OUT/bench_${n}gpu_$tag.json 2> $OUT/bench_${n}gpu_$tag.err
   python - <<PY
 import json
