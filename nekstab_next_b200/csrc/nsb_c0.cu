@@ -71,6 +71,43 @@ c0_boundary_kernel(double *__restrict__ uni, double *__restrict__ loc, const int
   }
 }
 
+// loc[p] = uni[l2u[p]]: one thread per local point, coalesced writes of whole rows, the index read once for all
+// fields (the scatter form -- one thread per node writing its copies -- left every 32-byte sector of the
+// element-local scratch to be completed by several threads at different times)
+__global__ void __launch_bounds__(256)
+c0_gather_kernel(const double *__restrict__ uni, double *__restrict__ loc, const int32_t *__restrict__ l2u, int64_t npts,
+                 int nf, int64_t fs_uni, int64_t fs_loc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    const int32_t q = __ldg(l2u + p);
+    for (int f = 0; f < nf; ++f) loc[(int64_t)f * fs_loc + p] = __ldg(uni + (int64_t)f * fs_uni + q);
+  }
+}
+
+// local point -> unique row (interior rows by arithmetic, boundary rows from the gather-scatter lists)
+int ensure_l2u(nsb_sem_t S) {
+  if (S->c0_l2u_d && S->c0_l2u_nshared == S->nshared && S->c0_l2u_nlocal == S->n_local) return NSB_OK;
+  cudaSetDevice(S->ctx->device);
+  const int64_t nint = c0_nint(S), nloc = S->npts / S->nel;
+  const int lx = S->lx, m = lx - 2, NI = (int)(S->nel ? nint / S->nel : 0);
+  std::vector<int32_t> l2u((size_t)S->npts, -1);
+  for (int64_t e = 0; e < S->nel; ++e)
+    for (int r = 0; r < NI; ++r) {
+      const int i = r % m, j = (r / m) % m, k = S->dim == 3 ? r / (m * m) : 0;
+      const int64_t p = e * nloc + (S->dim == 3 ? ((int64_t)(k + 1) * lx + (j + 1)) * lx + (i + 1) : (int64_t)(j + 1) * lx + (i + 1));
+      l2u[p] = (int32_t)(e * NI + r);
+    }
+  for (int64_t n = 0; n < S->nshared; ++n)
+    for (int64_t q = S->gs_off_h[n]; q < S->gs_off_h[n + 1]; ++q) l2u[S->gs_idx_h[q]] = (int32_t)(nint + n);
+  if (S->c0_l2u_d) cudaFree(S->c0_l2u_d);
+  S->c0_l2u_d = nullptr;
+  NSB_CUDA(cudaMalloc(&S->c0_l2u_d, sizeof(int32_t) * S->npts));
+  NSB_CUDA(cudaMemcpy(S->c0_l2u_d, l2u.data(), sizeof(int32_t) * S->npts, cudaMemcpyHostToDevice));
+  S->c0_l2u_nshared = S->nshared;
+  S->c0_l2u_nlocal = S->n_local;
+  return NSB_OK;
+}
+
 int ensure_scratch(nsb_sem_t S, int nf) {
   const size_t need = (size_t)2 * nf * S->npts;
   if (S->c0_scratch_elems >= need) return NSB_OK;
@@ -124,15 +161,11 @@ int c0_expand(nsb_sem_t S, const double *uni, int64_t fs_uni, double *loc, int64
   cudaSetDevice(ctx->device);
   const int64_t nint = c0_nint(S);
   const int m = S->lx - 2, NI = (int)(nint / S->nel), nloc = (int)(S->npts / S->nel);
-  ProfScope ps(ctx, PC_GS, 8.0 * nf * (double)(nint + S->nshared + S->npts) + 4.0 * (double)S->gs_nnz);
-  if (nint > 0)
-    c0_interior_kernel<0><<<nblk(nint), 256, 0, ctx->stream>>>(const_cast<double *>(uni), loc, nint, NI, m, S->lx, nloc, S->dim,
-                                                              nf, fs_uni, fs_loc);
-  if (S->nshared > 0)
-    c0_boundary_kernel<0><<<nblk(S->nshared), 256, 0, ctx->stream>>>(const_cast<double *>(uni) + nint, loc, S->gs_off_d,
-                                                                    S->gs_idx_d, 0, S->nshared, nf, fs_uni, fs_loc, nullptr, 0,
-                                                                    0, nullptr);
-  ctx->launches += 2;
+  ProfScope ps(ctx, PC_GS, 8.0 * nf * (double)(nint + S->nshared + S->npts) + 4.0 * (double)S->npts);
+  (void)m; (void)NI; (void)nloc;
+  NSB_CHECK(ensure_l2u(S));
+  c0_gather_kernel<<<ctx->num_sms * 16, 256, 0, ctx->stream>>>(uni, loc, S->c0_l2u_d, S->npts, nf, fs_uni, fs_loc);
+  ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
 }
@@ -250,6 +283,7 @@ extern "C" int nsb_layout_create_c0(nsb_context_t ctx, nsb_sem_t sem, int nfield
     stored[f] = nuni;
   }
   NSB_CHECK(ensure_scratch(sem, std::min(n_c0, 3)));   // not inside a captured Arnoldi step later on
+  NSB_CHECK(ensure_l2u(sem));
   NSB_CHECK(nsb_layout_create(ctx, nfields, stored.data(), field_in_dot, time_in_dot, layout));
   (*layout)->c0_sem = sem;
   (*layout)->c0_nfields = n_c0;

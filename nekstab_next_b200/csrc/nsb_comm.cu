@@ -585,6 +585,7 @@ int exchange_setup(nsb_sem_t S) {
       S->p2p_halo = true;
     }
   }
+  S->c0_l2u_nshared = -1;   // the node order changed: the C0 index map is rebuilt on next use
   clear_step_graphs(ctx);
   return NSB_OK;
 }

@@ -192,6 +192,8 @@ struct nsb_sem_s {
   bool exchange_ready = false;
   double *c0_scratch_d = nullptr;   // element-local scratch of the C0 layout (2 x nf x npts)
   size_t c0_scratch_elems = 0;
+  int32_t *c0_l2u_d = nullptr;      // local point -> row of the unique layout
+  int64_t c0_l2u_nshared = -1, c0_l2u_nlocal = -1;
   double *pcg_d = nullptr;       // work vectors of nsb_sem_hmholtz (r, p, w, z per system, d)
   double *diagA_d = nullptr;     // diagonal of A per local point (setprec), computed at the first solve
   bool p2p_halo = false;         // interface data is written straight into the peers' mailboxes

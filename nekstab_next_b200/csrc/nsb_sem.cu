@@ -1562,6 +1562,7 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
     if (q) cudaFree(q);
   if (S->pcg_d) cudaFree(S->pcg_d);
   if (S->c0_scratch_d) cudaFree(S->c0_scratch_d);
+  if (S->c0_l2u_d) cudaFree(S->c0_l2u_d);
   if (S->ev_a) cudaEventDestroy(S->ev_a);
   if (S->ev_b) cudaEventDestroy(S->ev_b);
   if (S->ev_c) cudaEventDestroy(S->ev_c);
