@@ -92,6 +92,7 @@ struct nsb_context_s {
   bool pipeline_upload = true;   // NSB_PIPELINE_UPLOAD=0: plain upload, then the usual first sweep
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
   bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
+  bool fold_norm = true;       // NSB_FOLD_NORM=0: explicit norm reduction in the third sweep + normalize_kernel
   int fused_loader = 3;        // NSB_FUSED_LOADER: 1 cp.async, 3 TMA 2-D tensor loads (default)
   int fused_rc = 0;            // NSB_FUSED_RC: force rows per block (tuning)
   int fused_reg_min_k = 54;    // NSB_FUSED_REG_MIN_K: smallest k for the register-retention variant

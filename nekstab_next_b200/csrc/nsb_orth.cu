@@ -136,16 +136,20 @@ multidot_kernel(const double *__restrict__ V, int64_t ld, int k, const double *_
 
 // MODE 0: w -= V h          (rows [0, nrows))        [+ partial norm over rows < ndot if WITH_NORM]
 // MODE 1: out = V y         (k_matmul)
+// MODE 2: w = (w - V h) / sqrt(*scale2)   (third sweep of CGS2 with the folded normalisation: scale2 = beta^2 is
+//         already known from the second projection, nsb_tail.cuh norm_op 4)
 template <int MODE, bool WITH_NORM>
 __global__ void __launch_bounds__(NT, 2)
 update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ h,
               double *__restrict__ w, const double *__restrict__ W, int64_t nchunks,
-              int64_t ndot_chunks, double *__restrict__ partial, const __grid_constant__ OrthTail tail) {
+              int64_t ndot_chunks, double *__restrict__ partial, const __grid_constant__ OrthTail tail,
+              const double *__restrict__ scale2 = nullptr) {
   extern __shared__ double hS[];
   if (tail.skip_flag && *tail.skip_flag == 0) return;   // DGKS: second projection not needed
   for (int j = threadIdx.x; j < k; j += NT) hS[j] = h[j];
   __syncthreads();
   double nrm = 0.0;
+  const double inv = (MODE == 2) ? 1.0 / sqrt(*scale2) : 1.0;
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int64_t r0 = chunk * CHUNK + 2 * threadIdx.x;
     const double *vp = V + r0;
@@ -154,7 +158,7 @@ update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__r
     // w (and W for the norm) are requested before the sweep over the columns, so the
     // read-modify-write at the end of the chunk does not wait on a fresh load
     double2 wa = make_double2(0.0, 0.0), wb = wa, Wa = wa, Wb = wa;
-    if (MODE == 0) {
+    if (MODE != 1) {
       wa = *wpa;
       wb = *wpb;
       if (WITH_NORM && chunk < ndot_chunks) {
@@ -207,6 +211,9 @@ update_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__r
       *wpb = wb;
       if (WITH_NORM && chunk < ndot_chunks)
         nrm += Wa.x * wa.x * wa.x + Wa.y * wa.y * wa.y + Wb.x * wb.x * wb.x + Wb.y * wb.y * wb.y;
+    } else if (MODE == 2) {
+      *wpa = make_double2((wa.x - a0) * inv, (wa.y - a1) * inv);
+      *wpb = make_double2((wb.x - a2) * inv, (wb.y - a3) * inv);
     } else {
       *wpa = make_double2(a0, a1);
       *wpb = make_double2(a2, a3);
@@ -1157,24 +1164,24 @@ int launch_multidot(nsb_context_t ctx, const double *V, int64_t ld, int k, const
 template <int MODE>
 int launch_update(nsb_context_t ctx, const double *V, int64_t ld, int k, const double *h_d, double *w,
                   const double *W, int64_t nrows, int64_t ndot, bool with_norm, const TailSpec &sp,
-                  int64_t nalg = -1, int64_t nalg_dot = -1) {
+                  int64_t nalg = -1, int64_t nalg_dot = -1, const double *scale2_d = nullptr) {
   const int64_t nchunks = nrows / CHUNK;
   const int grid = persistent_grid(ctx, nchunks);
   const size_t smem = sizeof(double) * (k > 0 ? k : 1);
   cudaSetDevice(ctx->device);
   // algorithmic bytes: V once, w read + written (MODE 0) or written (MODE 1), W once with the norm
   const double na = (double)(nalg >= 0 ? nalg : nrows), nd = (double)(nalg_dot >= 0 ? nalg_dot : ndot);
-  const double bytes = 8.0 * (na * (k + (MODE == 0 ? 2 : 1)) + (with_norm ? nd : 0.0));
+  const double bytes = 8.0 * (na * (k + (MODE != 1 ? 2 : 1)) + (with_norm ? nd : 0.0));
   // the norm is the only thing this kernel reduces: one partial per CTA, coefficient count 0
   const OrthTail tail = make_tail(ctx, sp, 0, with_norm ? 1 : 0, 1);
   {
-    ProfScope ps(ctx, MODE == 0 ? PC_UPDATE : PC_GEMV, bytes);
+    ProfScope ps(ctx, MODE != 1 ? PC_UPDATE : PC_GEMV, bytes);
     if (with_norm)
       update_kernel<MODE, true><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
-                                                                ctx->partial_d, tail);
+                                                                ctx->partial_d, tail, scale2_d);
     else
       update_kernel<MODE, false><<<grid, NT, smem, ctx->stream>>>(V, ld, k, h_d, w, W, nchunks, ndot / CHUNK,
-                                                                 ctx->partial_d, tail);
+                                                                 ctx->partial_d, tail, scale2_d);
   }
   ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
@@ -1441,6 +1448,11 @@ int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so)
     // pass 1 (DGKS: the norm of the incoming w rides along for the test); already done chunk by chunk
     // during the upload when the vector came from the host (upload_multidot_pipelined)
     const bool have_h1 = !dgks && ctx->h1_ready_k == k && ctx->h1_ready_col == w;
+    // CGS2 with the normalisation folded into the third sweep (nsb_tail.cuh, norm_op 4): |w'|^2 rides along with
+    // h2, beta^2 = |w'|^2 - |h2|^2, and the last sweep writes the normalised vector -- two reductions per step
+    // instead of three and no normalize_kernel.  Not with the streamed download (it sends w'' before beta is
+    // needed) and not in DGKS mode (whether a second projection happens is decided by the same reduction).
+    const bool fold = fused && !dgks && !so && ctx->fold_norm;
     if (!have_h1) {
       TailSpec sp;
       sp.out = h1;
@@ -1459,9 +1471,14 @@ int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so)
       sp.out = h2;
       sp.hsum = hsum;
       sp.hsum_op = 2;
-      sp.norm_op = dgks ? 3 : 0;
+      sp.norm_op = dgks ? 3 : fold ? 4 : 0;
       sp.passes_out = dgks ? hsum + k + 1 : nullptr;
-      NSB_CHECK(launch_fused(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks, sp, L->nact, L->ndof_dot + 1));
+      NSB_CHECK(launch_fused(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks || fold, sp, L->nact,
+                             L->ndof_dot + 1));
+      if (fold) {
+        NSB_CHECK(launch_update<2>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, false, TailSpec(), L->nact, 0, scal));
+        return NSB_OK;
+      }
     } else {
       TailSpec su;                    // DGKS: |w'|^2 and the decision ride on the first update
       if (dgks) {

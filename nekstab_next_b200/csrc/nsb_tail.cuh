@@ -110,6 +110,11 @@ __device__ __forceinline__ void p2p_allreduce_block(double *buf, int n, const Pe
 //               also taken on NaN);
 //               *flag = second; if (!second) scal[0] = out[k] and hsum_op is NOT applied (the second
 //               projection is dropped as a whole); *passes_out = number of passes (read back by the host)
+//             4 folded normalisation (CGS2): out[k] = |w'|^2 rode along with the second projection h2 = out[0..k);
+//               because V is B-orthonormal, |w' - V h2|^2 = |w'|^2 - |h2|^2, so the norm of the FINAL vector is
+//               known before the third sweep: scal[0] = beta^2 = max(out[k] - sum_j out[j]^2, 0), hsum[k] = beta
+//               (H(k+1,k)), scal[3] = beta.  The third sweep then writes (w' - V h2) / beta directly: no norm
+//               reduction, no third all-reduce and no separate normalisation pass.
 struct OrthTail {
   double *partial = nullptr;   // [gridDim.x][pstride]
   int pstride = 0;
@@ -141,6 +146,26 @@ __device__ __forceinline__ void orth_post_ops(const OrthTail &t) {
       if (t.passes_out) *t.passes_out = second ? 2.0 : 1.0;
     }
     s_second = second;
+  }
+  if (t.norm_op == 4) {
+    // |h2|^2 with a fixed summation order (thread-strided, shuffle tree, warp partials in turn)
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < t.k; j += blockDim.x) s = fma(t.out[j], t.out[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double h2n = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) h2n += s_red[i];
+      double b2 = t.out[t.k] - h2n;
+      b2 = b2 > 0.0 ? b2 : (b2 == b2 ? 0.0 : b2);   // rounding below zero = breakdown (beta = 0); NaN propagates
+      const double beta = sqrt(b2);
+      t.scal[0] = b2;
+      t.scal[3] = beta;
+      t.hsum[t.k] = beta;
+    }
   }
   __syncthreads();
   if (t.hsum_op == 1)

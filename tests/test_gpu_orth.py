@@ -109,6 +109,48 @@ def test_dgks_single_pass_when_no_cancellation(ctx, k):
         o.close()
 
 
+@pytest.mark.parametrize('k', [6, 40, 100, 230])
+@pytest.mark.parametrize('near_dependent', [False, True])
+def test_folded_norm_equals_measured_norm(ctx, monkeypatch, k, near_dependent):
+    """CGS2 takes H(k+1,k) from the second projection (beta^2 = |w'|^2 - |h2|^2, nsb_tail.cuh norm_op 4) and writes
+    the normalised vector in the third sweep; NSB_FOLD_NORM=0 measures |w''| with a third reduction and runs
+    normalize_kernel, like k_normalize of the reference (core/krylov_subspace.f90:75-92).  Same numbers -- also
+    when f is dependent on the basis to 1e-9 (beta eight orders below |f|)."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, pressure=True, time_in_dot=True, seed=300 + k)
+    c = P.octx()
+    Q = build_basis(P, c, k)
+    f = P.random_kvec()
+    if near_dependent:
+        okr.axpby(f, 1e-9, Q[0], 0.0, skip_time=False)
+    for i, q in enumerate(Q[: max(1, k // 2)]):
+        okr.axpby(f, 1.0, q, 50.0 / (1 + i), skip_time=False)
+    res = {}
+    for fold in ('1', '0'):
+        monkeypatch.setenv('NSB_FOLD_NORM', fold)
+        c2 = nb.Context(device=0)
+        lay, B, semg, op = P.gpu(c2, k + 1)
+        for i, q in enumerate(Q):
+            upload(B[i], q)
+        upload(B[k], f)
+        l0 = c2.launch_count()
+        h, _ = nb.orthonormalize(B, k, k, nb.ORTH_CGS2)
+        res[fold] = (h.copy(), download(B[k]), c2.launch_count() - l0, B.gram(k + 1))
+        for o in (op, semg, B, lay, c2):
+            o.close()
+    monkeypatch.delenv('NSB_FOLD_NORM')
+    (h1, q1, n1, G1), (h0, q0, n0, G0) = res['1'], res['0']
+    if k <= 420:                       # beyond that the unfused pair runs and nothing is folded
+        assert n1 == n0 - 1            # no normalize_kernel
+    assert np.array_equal(h1[:k], h0[:k])
+    assert abs(h1[k] - h0[k]) <= 1e-13 * abs(h0[k]) if not near_dependent else abs(h1[k] - h0[k]) <= 1e-6 * abs(h0[k])
+    tol = 1e-13 if not near_dependent else 1e-6
+    for x, y in zip(q1.f, q0.f):
+        assert np.max(np.abs(x - y)) <= tol * np.max(np.abs(y))
+    assert abs(G1[k, k] - 1.0) <= (1e-13 if not near_dependent else 1e-6)
+    assert np.max(np.abs(G1[:k, k])) < 1e-10 or near_dependent
+
+
 def test_first_vector_only_normalises(ctx):
     import nekstab_next_b200 as nb
     P = BoxProblem(nel=(2, 2, 2), N=3, nfields=1, seed=2)
