@@ -571,10 +571,20 @@ def run_native(a):
             bufs.append(fs)
         calls = [0]
 
+        noise = rng.standard_normal((K + 8, 4096))
+
         def host_matvec(fields, t):
-            # stand-in for the reference's host time-stepper: returns host-resident vectors
+            # stand-in for the reference's host time-stepper: returns host-resident vectors.  The three pinned
+            # buffers are recycled, but every call rewrites a 4096-entry window with fresh numbers, so each returned
+            # vector has a component outside the span of the earlier ones (a non-degenerate Arnoldi process; the
+            # first version returned the same three vectors in turn and every step from the fourth on was an exact
+            # breakdown that only the measured norm of rounding noise kept going).
             calls[0] += 1
-            return bufs[calls[0] % nbuf], t
+            out = bufs[calls[0] % nbuf]
+            j = calls[0] % noise.shape[0]
+            for f in range(nc):
+                out[f][j * 4096:(j + 1) * 4096] = noise[j] * (f + 1)
+            return out, t
 
         hop = nb.host_operator(lay, host_matvec, linear=True)   # linearised time-stepper: un-normalised hand-over allowed
         He = np.zeros((K + 1, K), order='F')

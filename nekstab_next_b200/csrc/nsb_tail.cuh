@@ -112,7 +112,7 @@ __device__ __forceinline__ void p2p_allreduce_block(double *buf, int n, const Pe
 //               projection is dropped as a whole); *passes_out = number of passes (read back by the host)
 //             4 folded normalisation (CGS2): out[k] = |w'|^2 rode along with the second projection h2 = out[0..k);
 //               because V is B-orthonormal, |w' - V h2|^2 = |w'|^2 - |h2|^2, so the norm of the FINAL vector is
-//               known before the third sweep: scal[0] = beta^2 = max(out[k] - sum_j out[j]^2, 0), hsum[k] = beta
+//               known before the third sweep: scal[0] = beta^2 = out[k] - sum_j out[j]^2, hsum[k] = beta
 //               (H(k+1,k)), scal[3] = beta.  The third sweep then writes (w' - V h2) / beta directly: no norm
 //               reduction, no third all-reduce and no separate normalisation pass.
 struct OrthTail {
@@ -159,8 +159,15 @@ __device__ __forceinline__ void orth_post_ops(const OrthTail &t) {
     if (threadIdx.x == 0) {
       double h2n = 0.0;
       for (int i = 0; i < (int)(blockDim.x >> 5); ++i) h2n += s_red[i];
-      double b2 = t.out[t.k] - h2n;
-      b2 = b2 > 0.0 ? b2 : (b2 == b2 ? 0.0 : b2);   // rounding below zero = breakdown (beta = 0); NaN propagates
+      // The identity loses accuracy only as beta^2 / |w'|^2 -> 0 (relative error ~ eps |w'|^2 / beta^2), i.e. when the
+      // second projection removed w' altogether: w' was rounding noise (f in span(V) to working precision).  The
+      // reference measures the norm of that noise and carries on; here beta is kept at the rounding level of |w'|
+      // (never below eps |w'|), so the step neither divides by zero nor reports a breakdown the reference would
+      // not see.  |w'| = 0 exactly still gives beta = 0 (NSB_EBREAKDOWN); NaN propagates.
+      const double n1 = t.out[t.k];
+      double b2 = n1 - h2n;
+      const double floor2 = 4.930380657631324e-32 * n1;   // (2^-52)^2 |w'|^2
+      if (b2 == b2 && !(b2 > floor2)) b2 = floor2;
       const double beta = sqrt(b2);
       t.scal[0] = b2;
       t.scal[3] = beta;
