@@ -1,0 +1,189 @@
+"""CPU restatement (numpy) of the pressure-coupled perturbation step that sits inside ``nek_advance`` -- the body of
+``exponential_prop%matvec`` (core/linear_operators.f90:225-274: ``nopcopy`` of the Krylov vector into vxp/vyp/vzp/prp,
+``nek_advance`` for tau/dt steps from a cold start, copy of the final state back).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  parity unpinned: Nek5000 is not vendored with the reference
+(SURVEY.md section 2.3), so everything here is [UPSTREAM-RECALL] of Nek5000's P_N - P_N-2 perturbation path
+(perturb.f: perturbv -> advabp, makextp, makebdfp, cresvipp, ophinv, incomprp;  navier1.f: opdiv / multd, opgradt / cdtp,
+cdabdtp, opbinv, ortho;  coef.f: geom2 / map12) restated from its published formulation (Maday-Patera-Ronquist
+splitting with the consistent Poisson operator E = D B^-1 D^T), and pinned only by independent mathematics in
+tests/test_oracle_ns.py: adjointness <D u, p> = <u, D^T p>, exactness of D on polynomial fields, symmetry and null
+space of E, discrete incompressibility of every step, linearity and temporal convergence order of the stepper.
+
+Meshes: velocity on lx1 = N+1 Gauss-Lobatto-Legendre points per direction (C0 across elements), pressure on
+lx2 = lx1 - 2 Gauss-Legendre points (element-local, discontinuous).  Arrays are element-local, (e, k, j, i) / (e, j, i).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import sem as osem
+
+
+# ----------------------------------------------------------------------------
+# Pressure mesh  (coef.f geom2: rxm2 = map12(rxm1) ..., bm2 = w3m2 * jacm2)
+# ----------------------------------------------------------------------------
+def pressure_setup(n, geo):
+    """Interpolation / derivative matrices GLL(lx1) -> GL(lx2) and the metrics on the pressure mesh.
+
+    I12[I, i] = l_i(z2_I) (ixm12), D12 = I12 D (dxm12: derivative of the GLL interpolant at the Gauss points),
+    rx2[a*dim+b] = w3m2 * map12(J dr_a/dx_b) -- the Gauss weights folded in, as multd's final col2(dx, w3m2)."""
+    lx1, lx2 = n + 1, n - 1
+    z1, _ = osem.gll(n)
+    z2, w2 = osem.gl(lx2)
+    I12 = osem.interp_matrix(z1, z2)
+    D12 = I12 @ osem.dgll(n)
+    rst = geo['rst']
+    dim = 3 if len(rst) == 9 else 2
+    w3 = w2[:, None, None] * w2[None, :, None] * w2[None, None, :] if dim == 3 else w2[:, None] * w2[None, :]
+    rx2 = [osem.interp_fine(m, I12) * w3[None] for m in rst]
+    bm2 = osem.interp_fine(geo['jac'], I12) * w3[None]
+    return dict(I12=I12, D12=D12, rx2=rx2, bm2=bm2, dim=dim, lx1=lx1, lx2=lx2)
+
+
+def _grad12(u, ps):
+    """d u / d r_a evaluated on the pressure mesh (multd: dxm12 in direction a, ixm12 in the others)."""
+    I, D = ps['I12'], ps['D12']
+    if ps['dim'] == 3:
+        return (np.einsum('Kk,Jj,Ii,ekji->eKJI', I, I, D, u, optimize=True),
+                np.einsum('Kk,Jj,Ii,ekji->eKJI', I, D, I, u, optimize=True),
+                np.einsum('Kk,Jj,Ii,ekji->eKJI', D, I, I, u, optimize=True))
+    return (np.einsum('Jj,Ii,eji->eJI', I, D, u, optimize=True),
+            np.einsum('Jj,Ii,eji->eJI', D, I, u, optimize=True))
+
+
+def _grad12_t(ws, ps):
+    """Transpose of _grad12: sum_a T_a^T w_a (cdtp)."""
+    I, D = ps['I12'], ps['D12']
+    if ps['dim'] == 3:
+        return (np.einsum('Kk,Jj,Ii,eKJI->ekji', I, I, D, ws[0], optimize=True)
+                + np.einsum('Kk,Jj,Ii,eKJI->ekji', I, D, I, ws[1], optimize=True)
+                + np.einsum('Kk,Jj,Ii,eKJI->ekji', D, I, I, ws[2], optimize=True))
+    return (np.einsum('Jj,Ii,eJI->eji', I, D, ws[0], optimize=True)
+            + np.einsum('Jj,Ii,eJI->eji', D, I, ws[1], optimize=True))
+
+
+def opdiv(vel, ps):
+    """opdiv / multd: (D u)_q = w_q sum_b sum_a (J dr_a/dx_b)_q (du_b/dr_a)_q  = int q div u on the Gauss points."""
+    d = ps['dim']
+    out = 0.0
+    for b in range(d):
+        g = _grad12(vel[b], ps)
+        for a in range(d):
+            out = out + ps['rx2'][a * d + b] * g[a]
+    return out
+
+
+def opgradt(p, ps):
+    """opgradt / cdtp: the exact transpose of opdiv, element-local (no dssum): (D^T p)_b = sum_a T_a^T (rx2[a,b] p)."""
+    d = ps['dim']
+    return [_grad12_t([ps['rx2'][a * d + b] * p for a in range(d)], ps) for b in range(d)]
+
+
+def opbinv(ws, glo, mask, binv):
+    """opbinv: mask, dssum, multiply by the assembled inverse mass matrix."""
+    return [osem.dssum(w, glo) * mask * binv for w in ws]
+
+
+def ortho(p):
+    """ortho: remove the mean over all pressure points (all-Dirichlet velocity: E has the constants as null space)."""
+    return p - np.mean(p)
+
+
+def cdabdtp(p, ps, glo, mask, binv):
+    """E p = D B^-1 D^T p  (cdabdtp without the h2inv scaling, which the caller applies to the right-hand side)."""
+    return opdiv(opbinv(opgradt(p, ps), glo, mask, binv), ps)
+
+
+def esolve(rhs, ps, glo, mask, binv, tol=1e-10, maxit=2000, mean_free=True):
+    """E dp = rhs by conjugate gradients preconditioned with the inverse pressure mass matrix (uzawa / uzprec without
+    the Schwarz part): z = r / bm2 ; rtz = sum r z ; p = z + beta p ; w = E p ; alpha = rtz / sum w p.
+    Stops on sqrt(rtz) <= tol * sqrt(rtz_0).  Returns (dp, iterations, residual drop)."""
+    minv = 1.0 / ps['bm2']
+    x = np.zeros_like(rhs)
+    p = np.zeros_like(rhs)
+    r = ortho(rhs) if mean_free else rhs.copy()
+    z = minv * r
+    if mean_free:
+        z = ortho(z)
+    rtz1, rtz2 = float(np.sum(r * z)), 1.0
+    r0, rn, it = -1.0, 0.0, 0
+    if not rtz1 > 0.0:
+        return x, 0, 0.0
+    for it in range(1, maxit + 1):
+        beta = 0.0 if it == 1 else rtz1 / rtz2
+        p = z + beta * p
+        w = cdabdtp(p, ps, glo, mask, binv)
+        rho = float(np.sum(w * p))
+        if not rho > 0.0:
+            break
+        alpha = rtz1 / rho
+        x = x + alpha * p
+        r = r - alpha * w
+        z = minv * r
+        if mean_free:
+            z = ortho(z)
+        rtz2, rtz1 = rtz1, float(np.sum(r * z))
+        rn = np.sqrt(abs(rtz1))
+        if r0 < 0.0:
+            r0 = np.sqrt(abs(rtz2))
+        if rn <= tol * r0:
+            break
+    return x, it, (rn / r0 if r0 > 0 else 0.0)
+
+
+# ----------------------------------------------------------------------------
+# The perturbation step  (perturb.f perturbv: advabp, makextp, makebdfp, cresvipp + ophinv, incomprp)
+# ----------------------------------------------------------------------------
+def advabp(vel, base, cf_base, dl):
+    """Explicit term of the linearised momentum equation, local weak form (mass matrix inside the dealiased
+    quadrature):  bf_b = -[ (U . grad) v_b + (v . grad) U_b ]."""
+    cf_v = osem.set_convect(vel, dl)
+    return [-(osem.convect_dealiased(vel[b], cf_base, dl) + osem.convect_dealiased(base[b], cf_v, dl))
+            for b in range(len(vel))]
+
+
+def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=True,
+             maxit=4000, info=None):
+    """nsteps BDF/EXT steps (order ramp 1, 2, 3, cold start) of the linearised incompressible Navier-Stokes equations
+        dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v ,  div v = 0
+    in the P_N - P_N-2 splitting:
+        bf   = EXT(-B C(v)) + (1/dt) B sum_i bd_i v^(n-i)                       (advabp, makextp, makebdfp)
+        p*   = p^(n-1)            (order 1, 2)   |   2 p^(n-1) - p^(n-2)       (order 3; extrapprp)
+        v*   = H^-1 mask dssum(bf + D^T p*),   H = nu A + (bd_0/dt) B           (cresvipp + ophinv)
+        E dp = -(bd_0/dt) D v* ;  v = v* + (dt/bd_0) B^-1 D^T dp ;  p = p* + dp (incomprp)
+    base = None: Stokes.  Returns (velocity list, pressure)."""
+    d = osem.dgll(n)
+    dim = ps['dim']
+    bm1 = geo['bm1']
+    binv = 1.0 / osem.dssum(bm1, glo)
+    cf_base = osem.set_convect(base, dl) if base is not None else None
+    lag = [[v.copy() for v in vel0]] + [[0 * v for v in vel0] for _ in range(2)]
+    e1 = [0 * v for v in vel0]
+    e2 = [0 * v for v in vel0]
+    p, plag = pr0.copy(), 0 * pr0
+    its_v = its_p = 0
+    for s in range(1, nsteps + 1):
+        o = min(s, 3)
+        bd0 = osem.BD[o][0]
+        bf = advabp(lag[0], base, cf_base, dl) if base is not None else [0 * v for v in vel0]
+        for b in range(dim):
+            osem.bdf_ext(bf[b], e1[b], e2[b], [lag[i][b] for i in range(o)], bm1, osem.AB[o], osem.BD[o], 1.0 / dt)
+        pstar = p if o < 3 else 2.0 * p - plag
+        gt = opgradt(pstar, ps)
+        vstar = []
+        for b in range(dim):
+            x, it, _ = osem.cggo(osem.dssum(bf[b] + gt[b], glo), geo['g'], d, glo, mask, bm1, nu, bd0 / dt, tol=tol_v,
+                                 maxit=maxit)
+            its_v += it
+            vstar.append(x)
+        rhs = -(bd0 / dt) * opdiv(vstar, ps)
+        dp, it, _ = esolve(rhs, ps, glo, mask, binv, tol=tol_p, maxit=maxit, mean_free=mean_free)
+        its_p += it
+        corr = opbinv(opgradt(dp, ps), glo, mask, binv)
+        vnew = [vstar[b] + (dt / bd0) * corr[b] for b in range(dim)]
+        plag, p = p, pstar + dp
+        lag = [vnew, lag[0], lag[1]]
+    if info is not None:
+        info.update(helmholtz_iterations=its_v, pressure_iterations=its_p)
+    return lag[0], p
