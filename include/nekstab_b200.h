@@ -341,7 +341,7 @@ int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, n
  * applied independently to the first nfields_apply fields; U = the convecting field in `slot`
  * (nsb_sem_set_convect; -1: no convection).  Each step = nsb_sem_convect, nsb_sem_bdf_ext,
  * nsb_sem_dssum, nsb_sem_hmholtz(kappa, rho bd1/dt, tol, maxit).  The pressure-coupled velocity
- * step is not available. */
+ * step is nsb_op_create_ns_stepper below. */
 int nsb_op_create_stepper(nsb_sem_t sem, nsb_layout_t layout, int nfields_apply, int slot, double kappa,
                           double rho, double dt, int nsteps, double tol, int maxit, nsb_op_t *op);
 /* exponential_prop%rmatvec (core/linear_operators.f90:84-103) for the same step sequence: the DISCRETE adjoint of
@@ -352,6 +352,44 @@ int nsb_op_create_stepper(nsb_sem_t sem, nsb_layout_t layout, int nfields_apply,
  * nsb_op_create_compose) and nsb_svds device-resident.  Same arguments as nsb_op_create_stepper. */
 int nsb_op_create_stepper_adjoint(nsb_sem_t sem, nsb_layout_t layout, int nfields_apply, int slot, double kappa,
                                   double rho, double dt, int nsteps, double tol, int maxit, nsb_op_t *op);
+/* ---- pressure-coupled perturbation step (the body of nek_advance reached from exponential_prop%matvec,
+ * core/linear_operators.f90:225-274, :247) for Nek5000's P_N - P_N-2 formulation [UPSTREAM-RECALL perturb.f
+ * perturbv / incomprp, navier1.f opdiv / opgradt / cdabdtp / uzawa, coef.f geom2; parity unpinned] -------------
+ * Velocity on the lx1 = N+1 GLL mesh (fields 0..dim-1 of a column, equally long), pressure on lx2 = lx1-2
+ * Gauss-Legendre points per direction and element (field dim of the column, nsb_sem_npres() values; nekStab keeps it
+ * in the Krylov vector and out of the inner product, core/nek_vectors.f90:20-31).
+ *   pressure_matrices : host-only; z2, w2 [lx2], I12, D12 [lx2][lx1] row-major (ixm12, dxm12)
+ *   pressure_setup    : metrics on the pressure mesh (rxm2 = w3m2 map12(rxm1), bm2) -- needs N >= 3
+ *   pressure_get      : which 0: rx2 [dim*dim][n2], 1: 1 / bm2 [n2]
+ *   opdiv             : out(pressure) = D in(velocity),  (D u)_q = w_q sum_ab (J dr_a/dx_b)_q (du_b/dr_a)_q
+ *   opgradt           : out(velocity, element-local, no dssum) = D^T in(pressure)
+ *   cdabdtp           : out = E in,  E = D (binvm1 mask QQ^T) D^T  (consistent Poisson operator)
+ *   esolve            : E x = rhs by CG preconditioned with 1 / bm2 (uzawa without the Schwarz part); stops when
+ *                       sqrt(r.z) <= tol sqrt(r0.z0); mean_free != 0 removes the mean of the right-hand side and of
+ *                       every preconditioned residual (Nek's ortho for all-Dirichlet velocity; exact on affine
+ *                       elements, where E 1 = 0 -- on deformed elements E is regular and mean_free = 0 solves it as
+ *                       it stands).  CG scalars stay on the device; the host polls a flag every 8 iterations. */
+int nsb_pressure_matrices(int N, double *z2, double *w2, double *I12, double *D12);
+int nsb_sem_pressure_setup(nsb_sem_t sem);
+int64_t nsb_sem_npres(nsb_sem_t sem);
+int nsb_sem_pressure_get(nsb_sem_t sem, int which, double *out);
+int nsb_sem_opdiv(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
+int nsb_sem_opgradt(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
+int nsb_sem_cdabdtp(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
+int nsb_sem_esolve(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, double tol, int maxit,
+                   int mean_free, int *iters, double *res);
+/* exponential_prop%matvec for the linearised incompressible Navier-Stokes equations, device-resident:
+ *     dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v,   div v = 0,   v = 0 where the mesh mask is 0.
+ * The input vector's velocity and pressure start nsteps BDF/EXT steps (order ramp 1, 2, 3 -- the reference restarts
+ * the time-stepper for every matvec); per step: advabp (dealiased, both convection slots of the mesh are used),
+ * makextp / makebdfp, H v* = QQ^T (bf + D^T p*), E dp = -(bd0/dt) D v*, v = v* + (dt/bd0) B^-1 D^T dp, p = p* + dp
+ * with p* = p^(n-1) (third step on: 2 p^(n-1) - p^(n-2)).  base / col_base: the base flow U (velocity fields of that
+ * column, same layout; nsb_sem_dealias_setup first), NULL = Stokes.  The output vector receives the final velocity
+ * and pressure; other fields and %time are carried through.  nsb_op_ns_iterations: Helmholtz / pressure iterations
+ * spent so far. */
+int nsb_op_create_ns_stepper(nsb_sem_t sem, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu, double dt,
+                             int nsteps, double tol_v, double tol_p, int maxit, int mean_free, nsb_op_t *op);
+int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_op_count(nsb_op_t op, int64_t *napply);

@@ -105,6 +105,17 @@ PROTOTYPES = {
                                         C.c_double, C.c_int, c_void_pp]),
     'nsb_op_create_stepper_adjoint': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                                 C.c_double, C.c_int, c_void_pp]),
+    'nsb_pressure_matrices': (C.c_int, [C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    'nsb_sem_pressure_setup': (C.c_int, [H]),
+    'nsb_sem_npres': (C.c_int64, [H]),
+    'nsb_sem_pressure_get': (C.c_int, [H, C.c_int, c_double_p]),
+    'nsb_sem_opdiv': (C.c_int, [H, H, C.c_int, H, C.c_int]),
+    'nsb_sem_opgradt': (C.c_int, [H, H, C.c_int, H, C.c_int]),
+    'nsb_sem_cdabdtp': (C.c_int, [H, H, C.c_int, H, C.c_int]),
+    'nsb_sem_esolve': (C.c_int, [H, H, C.c_int, H, C.c_int, C.c_double, C.c_int, C.c_int, c_int_p, c_double_p]),
+    'nsb_op_create_ns_stepper': (C.c_int, [H, H, H, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                           C.c_int, C.c_int, c_void_pp]),
+    'nsb_op_ns_iterations': (C.c_int, [H, c_i64_p, c_i64_p]),
     'nsb_op_destroy': (C.c_int, [H]),
     'nsb_op_apply': (C.c_int, [H, H, C.c_int, H, C.c_int]),
     'nsb_op_count': (C.c_int, [H, c_i64_p]),

@@ -418,6 +418,39 @@ class Sem:
     def ax(self, vin: nek_dvector, vout: nek_dvector, field: int, h1: float, h2: float):
         check(self.lib.nsb_sem_ax(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col, field, h1, h2))
 
+    # -- pressure mesh of the P_N - P_N-2 splitting ([UPSTREAM-RECALL] navier1.f opdiv / opgradt / cdabdtp / uzawa) --
+    def pressure_setup(self) -> int:
+        """Metrics on the lx2 = lx1 - 2 Gauss-Legendre mesh; returns the number of pressure points of this rank."""
+        check(self.lib.nsb_sem_pressure_setup(self.h))
+        self.n2 = int(self.lib.nsb_sem_npres(self.h))
+        return self.n2
+
+    def pressure_get(self, name: str) -> np.ndarray:
+        n2 = int(self.lib.nsb_sem_npres(self.h))
+        which = dict(rx2=0, bm2inv=1)[name]
+        out = np.empty(self.dim * self.dim * n2 if which == 0 else n2)
+        check(self.lib.nsb_sem_pressure_get(self.h, which, _dp(out)))
+        return out.reshape(self.dim * self.dim, n2) if which == 0 else out
+
+    def opdiv(self, vin: nek_dvector, vout: nek_dvector):
+        """opdiv: pressure field of vout <- D (velocity fields of vin)."""
+        check(self.lib.nsb_sem_opdiv(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col))
+
+    def opgradt(self, vin: nek_dvector, vout: nek_dvector):
+        """opgradt: velocity fields of vout <- D^T (pressure field of vin), element-local."""
+        check(self.lib.nsb_sem_opgradt(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col))
+
+    def cdabdtp(self, vin: nek_dvector, vout: nek_dvector):
+        """cdabdtp: pressure field of vout <- D B^-1 D^T (pressure field of vin)."""
+        check(self.lib.nsb_sem_cdabdtp(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col))
+
+    def esolve(self, rhs: nek_dvector, x: nek_dvector, tol: float = 1e-10, maxit: int = 2000, mean_free: bool = True):
+        """E x = rhs on the pressure fields (CG, 1 / bm2 preconditioner); returns (iterations, residual drop)."""
+        it, res = C.c_int(), C.c_double()
+        check(self.lib.nsb_sem_esolve(self.h, rhs.basis.h, rhs.col, x.basis.h, x.col, float(tol), int(maxit),
+                                      int(bool(mean_free)), C.byref(it), C.byref(res)))
+        return it.value, res.value
+
     # -- time-stepper pieces around ax (SURVEY.md section 8 f-3; [UPSTREAM-RECALL] convect.f, perturb.f) --
     def dealias_setup(self, lxd: int = 0):
         """Fine-mesh metrics for the dealiased convection (lxd Gauss-Legendre points; 0 = 3 lx1 / 2)."""
@@ -506,6 +539,36 @@ def stepper_operator(sem: Sem, layout: Layout, nfields: int, slot: int, kappa: f
     check(create(sem.h, layout.h, int(nfields), int(slot), float(kappa), float(rho),
                  float(dt), int(nsteps), float(tol), int(maxit), C.byref(h)))
     return LinearOperator(sem.lib, h, keep=(sem, layout))
+
+
+def ns_stepper_operator(sem: Sem, layout: Layout, base: nek_dvector | None, nu: float, dt: float, nsteps: int,
+                        tol_v: float = 1e-12, tol_p: float = 1e-12, maxit: int = 4000,
+                        mean_free: bool = True) -> LinearOperator:
+    """exponential_prop%matvec for the linearised incompressible Navier-Stokes equations on the device
+    (core/linear_operators.f90:225-274): nsteps pressure-coupled BDF/EXT steps of the P_N - P_N-2 splitting from a
+    cold start.  Layout: fields 0..dim-1 velocity, field dim pressure; base = the base flow (None: Stokes)."""
+    h = C.c_void_p()
+    check(sem.lib.nsb_op_create_ns_stepper(sem.h, layout.h, base.basis.h if base is not None else None,
+                                           base.col if base is not None else 0, float(nu), float(dt), int(nsteps),
+                                           float(tol_v), float(tol_p), int(maxit), int(bool(mean_free)), C.byref(h)))
+    return LinearOperator(sem.lib, h, keep=(sem, layout))
+
+
+def ns_iterations(op: LinearOperator):
+    """(Helmholtz iterations, pressure iterations) a Navier-Stokes stepper operator has spent so far."""
+    a, b = C.c_int64(), C.c_int64()
+    check(op.lib.nsb_op_ns_iterations(op.h, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def pressure_matrices(N: int):
+    """Host-only: (z2, w2, I12, D12) of the lx2 = N - 1 Gauss-Legendre pressure mesh (ixm12, dxm12)."""
+    from ._capi import load
+    lib = load()
+    l1, l2 = N + 1, N - 1
+    z2, w2, I12, D12 = np.empty(l2), np.empty(l2), np.empty((l2, l1)), np.empty((l2, l1))
+    check(lib.nsb_pressure_matrices(int(N), _dp(z2), _dp(w2), _dp(I12), _dp(D12)))
+    return z2, w2, I12, D12
 
 
 def compose_operators(layout: Layout, outer: LinearOperator, inner: LinearOperator) -> LinearOperator:

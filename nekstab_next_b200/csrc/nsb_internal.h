@@ -210,6 +210,14 @@ struct nsb_sem_s {
   double *J_d = nullptr, *Dg_d = nullptr;     // [lxd][lx] GLL -> GL interpolation, [lxd][lxd] derivative on GL
   double *rxf_d = nullptr;                    // [9][nel lxd^3] Gauss weights x metrics on the fine mesh
   double *cfine_d[2] = {nullptr, nullptr};    // [3][nel lxd^3] contravariant convecting fields (two slots)
+  // pressure mesh of the P_N - P_N-2 splitting (nsb_ns.cu): lx2 = lx - 2 Gauss-Legendre points per direction
+  int lx2 = 0;
+  int64_t n2 = 0;                             // nel * lx2^dim pressure points on this rank
+  double *i12_d = nullptr, *d12_d = nullptr;  // [lx2][lx] GLL -> GL interpolation, derivative at the Gauss points
+  double *rx2_d = nullptr;                    // [dim*dim][n2] Gauss weights x metrics on the pressure mesh
+  double *bm2inv_d = nullptr;                 // [n2] 1 / (w3m2 jacm2)
+  double *ns_work_d = nullptr;                // pressure CG: r, p, w [n2 each] + dim velocity-shaped fields
+  double *ns_state_d = nullptr;               // device scalars of the pressure CG
 };
 
 struct nsb_op_s {
@@ -231,10 +239,17 @@ struct nsb_op_s {
   double kappa = 0, rho = 1, dt = 0, tol = 0;
   int64_t helm_iters = 0;        // Helmholtz iterations spent so far
   bool adjoint = false;          // kind 3: apply the discrete BM1-adjoint of the stepper (rmatvec)
+  // kind 4 (nsb_ns.cu): pressure-coupled perturbation step (linearised Navier-Stokes, P_N - P_N-2)
+  double nu = 0, tol_p = 0;
+  int mean_free = 0;
+  bool has_base = false;         // base flow in column 8 of tmp, its contravariant field in convection slot 0
+  int64_t pres_iters = 0;        // pressure iterations spent so far
 };
 
 namespace nsb {
 int stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);   // nsb_conv.cu
+int ns_stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);   // nsb_ns.cu
+void ns_free(nsb_sem_t S);                                                                // nsb_ns.cu
 enum ProfClass { PC_MULTIDOT = 0, PC_UPDATE, PC_NORMALIZE, PC_AXHELM, PC_GS, PC_BLAS1, PC_SMALL,
                  PC_ROTATE, PC_GEMV, PC_DOT, PC_FUSED, PC_COUNT };
 // RAII: records a start event now and a stop event at scope exit on the context stream
@@ -278,6 +293,9 @@ int c0_apply_sem(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int co
 int64_t c0_nint(nsb_sem_t S);
 int launch_axhelm_ext(nsb_sem_t S, const double *u, double *w, int nf, int64_t fstride, double h1, double h2,
                       const double *cv, int epi, double alpha, double beta, const double *bmask);
+// gather-scatter of nf equally spaced fields incl. the inter-rank exchange (epi 0: dssum; 1: alpha uin + beta bmask sum)
+int launch_gs_ext(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const double *uin, double alpha, double beta,
+                  const double *bmask);
 int halo_exchange_fused_c0(nsb_sem_t S, const double *wloc, int nf, int64_t fs_loc, double *wu, const double *uu,
                            int64_t fs_u, double alpha, double beta, cudaStream_t st);
 // implemented in nsb_orth.cu

@@ -1,0 +1,777 @@
+// Pressure-coupled perturbation step on the device: what nek_advance does between the nopcopy calls of
+// exponential_prop%matvec (core/linear_operators.f90:225-274), for Nek5000's P_N - P_N-2 formulation
+// [UPSTREAM-RECALL perturb.f: perturbv -> advabp, makextp, makebdfp, cresvipp + ophinv, incomprp;  navier1.f: opdiv /
+// multd, opgradt / cdtp, cdabdtp, opbinv, ortho, uzawa;  coef.f: geom2 / map12].  Nek5000 is not vendored with the
+// reference: the kernels are checked against a CPU restatement of those routines held by the test suite, which is pinned
+// by independent mathematics only (tests/test_gpu_ns.py); parity unpinned.
+//
+//   velocity : lx1 = N + 1 Gauss-Lobatto-Legendre points per direction, C0, fields 0..dim-1 of a column
+//   pressure : lx2 = lx1 - 2 Gauss-Legendre points, element-local, field `dim` of a column (nekStab keeps the
+//              pressure in the Krylov vector and out of the inner product, core/nek_vectors.f90:20-31)
+//
+//   D  (opdiv)   (D u)_q   = w_q sum_b sum_a (J dr_a/dx_b)_q (du_b/dr_a)_q         one CTA per element, sum-factorised
+//   D^T (opgradt) exact transpose of D, element-local                              the same stages backwards
+//   E  (cdabdtp)  D B^-1 D^T  with B^-1 = binvm1 mask QQ^T                          opgradt -> gather-scatter -> opdiv
+//   esolve        E dp = g by CG preconditioned with 1 / bm2, CG scalars on the device, polled every 8 iterations
+//   step          bf = EXT(-B C(v)) + BDF ; v* = H^-1 QQ^T (bf + D^T p*) ; E dp = -(bd0/dt) D v* ;
+//                 v = v* + (dt/bd0) B^-1 D^T dp ; p = p* + dp
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "nsb_internal.h"
+#include "nsb_quadrature.h"
+#include "nsb_device.cuh"
+
+using namespace nsb;
+
+namespace {
+
+constexpr int NT_NS = 256;
+constexpr int MAXQ = 4;   // pressure points of an element per thread (lx2^dim <= MAXQ * NT_NS)
+
+// out[(o * no + O) * inner + x] (+)= sum_l M(O, l) in[(o * nl + l) * inner + x],  M(O, l) = TR ? M[l * no + O] : M[O * nl + l]
+// -- one tensor-product stage along the middle axis of an [outer][nl][inner] array, whole CTA.
+template <bool TR, bool ACC>
+__device__ __forceinline__ void stage(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ M,
+                                      int outer, int no, int nl, int inner) {
+  const int total = outer * no * inner;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int x = t % inner, O = (t / inner) % no, o = t / (inner * no);
+    const double *src = in + (size_t)o * nl * inner + x;
+    double s = 0.0;
+    for (int l = 0; l < nl; ++l) s = fma(TR ? M[l * no + O] : M[O * nl + l], src[(size_t)l * inner], s);
+    if (ACC) out[t] += s;
+    else out[t] = s;
+  }
+}
+
+struct NsDims {
+  int dim, l1, l2;
+  int n1e, n2e;   // points per element on the two meshes
+};
+
+// shared-memory plan (doubles): I12 | D12 | u [n1e] | A, B [lz1 ly1 l2 each] | AA, AD, BA [lz1 l2 l2 each] | G_r, G_s, G_t [n2e each]
+__host__ __device__ inline int ns_smem_doubles(int dim, int l1, int l2) {
+  const int lz1 = dim == 3 ? l1 : 1;
+  const int n1e = l1 * l1 * lz1, n2e = l2 * l2 * (dim == 3 ? l2 : 1);
+  return 2 * l2 * l1 + n1e + 2 * lz1 * l1 * l2 + 3 * lz1 * l2 * l2 + 3 * n2e;
+}
+
+// (D u): vel = dim equally spaced fields (stride fs) -> pressure array.  out = scale * D u; optional partial sums of
+// out * dotw per CTA (pressure CG: (E p, p)).
+__global__ void __launch_bounds__(NT_NS)
+opdiv_kernel(NsDims d, const double *__restrict__ vel, int64_t fs, const double *__restrict__ rx2, int64_t n2,
+             const double *__restrict__ I12g, const double *__restrict__ D12g, double scale, double *__restrict__ out,
+             const double *__restrict__ dotw, double *__restrict__ dot_partial, const int *__restrict__ done) {
+  if (done && *done) return;
+  extern __shared__ double sm[];
+  const int l1 = d.l1, l2 = d.l2, dim = d.dim, lz1 = dim == 3 ? l1 : 1;
+  double *I12 = sm, *D12 = I12 + l2 * l1, *u = D12 + l2 * l1, *A = u + d.n1e, *B = A + lz1 * l1 * l2,
+         *AA = B + lz1 * l1 * l2, *AD = AA + lz1 * l2 * l2, *BA = AD + lz1 * l2 * l2;
+  for (int t = threadIdx.x; t < l2 * l1; t += blockDim.x) {
+    I12[t] = I12g[t];
+    D12[t] = D12g[t];
+  }
+  const int64_t e = blockIdx.x;
+  double acc[MAXQ];
+#pragma unroll
+  for (int m = 0; m < MAXQ; ++m) acc[m] = 0.0;
+  for (int b = 0; b < dim; ++b) {
+    __syncthreads();
+    const double *ub = vel + (int64_t)b * fs + e * d.n1e;
+    for (int t = threadIdx.x; t < d.n1e; t += blockDim.x) u[t] = ub[t];
+    __syncthreads();
+    stage<false, false>(A, u, I12, lz1 * l1, l2, l1, 1);        // r: interpolate / differentiate
+    stage<false, false>(B, u, D12, lz1 * l1, l2, l1, 1);
+    __syncthreads();
+    stage<false, false>(AA, A, I12, lz1, l2, l1, l2);           // s
+    stage<false, false>(AD, A, D12, lz1, l2, l1, l2);
+    stage<false, false>(BA, B, I12, lz1, l2, l1, l2);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MAXQ; ++m) {
+      const int q = threadIdx.x + m * NT_NS;
+      if (q >= d.n2e) break;
+      double ur, us, ut = 0.0;
+      if (dim == 3) {
+        const int K = q / (l2 * l2), ji = q % (l2 * l2);
+        ur = us = 0.0;
+        for (int k = 0; k < l1; ++k) {
+          const double ik = I12[K * l1 + k], dk = D12[K * l1 + k];
+          ur = fma(ik, BA[k * l2 * l2 + ji], ur);
+          us = fma(ik, AD[k * l2 * l2 + ji], us);
+          ut = fma(dk, AA[k * l2 * l2 + ji], ut);
+        }
+      } else {
+        ur = BA[q];
+        us = AD[q];
+      }
+      const int64_t g = e * d.n2e + q;
+      double s = rx2[(int64_t)(0 * dim + b) * n2 + g] * ur + rx2[(int64_t)(1 * dim + b) * n2 + g] * us;
+      if (dim == 3) s += rx2[(int64_t)(2 * dim + b) * n2 + g] * ut;
+      acc[m] += s;
+    }
+  }
+  double dot = 0.0;
+#pragma unroll
+  for (int m = 0; m < MAXQ; ++m) {
+    const int q = threadIdx.x + m * NT_NS;
+    if (q >= d.n2e) break;
+    const int64_t g = e * d.n2e + q;
+    const double v = scale * acc[m];
+    out[g] = v;
+    if (dotw) dot += v * dotw[g];
+  }
+  if (dot_partial) {
+    dot = block_reduce_sum<NT_NS>(dot);
+    if (threadIdx.x == 0) dot_partial[blockIdx.x] = dot;
+  }
+}
+
+// (D^T p), element-local.  Epilogue per point x of velocity field b:
+//   epi 0 : out = alpha * uin + beta * w                        (all points; uin may be null)
+//   epi 1 : element-interior points  out = alpha * uin + beta * bmask * w,  element-boundary points  out = w
+//           (the gather-scatter with the same alpha / beta / bmask finishes those: B^-1 D^T p and v* + c B^-1 D^T dp)
+__global__ void __launch_bounds__(NT_NS)
+opgradt_kernel(NsDims d, const double *__restrict__ p, const double *__restrict__ rx2, int64_t n2,
+               const double *__restrict__ I12g, const double *__restrict__ D12g, double *out, int64_t fs,
+               int epi, const double *uin, double alpha, double beta, const double *__restrict__ bmask,
+               const int *__restrict__ done) {
+  if (done && *done) return;
+  extern __shared__ double sm[];
+  const int l1 = d.l1, l2 = d.l2, dim = d.dim, lz1 = dim == 3 ? l1 : 1;
+  double *I12 = sm, *D12 = I12 + l2 * l1, *w = D12 + l2 * l1, *A = w + d.n1e, *B = A + lz1 * l1 * l2,
+         *AA = B + lz1 * l1 * l2, *AD = AA + lz1 * l2 * l2, *BA = AD + lz1 * l2 * l2, *Gr = BA + lz1 * l2 * l2,
+         *Gs = Gr + d.n2e, *Gt = Gs + d.n2e;
+  for (int t = threadIdx.x; t < l2 * l1; t += blockDim.x) {
+    I12[t] = I12g[t];
+    D12[t] = D12g[t];
+  }
+  const int64_t e = blockIdx.x;
+  for (int b = 0; b < dim; ++b) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < d.n2e; q += blockDim.x) {
+      const int64_t g = e * d.n2e + q;
+      const double pq = p[g];
+      Gr[q] = rx2[(int64_t)(0 * dim + b) * n2 + g] * pq;
+      Gs[q] = rx2[(int64_t)(1 * dim + b) * n2 + g] * pq;
+      if (dim == 3) Gt[q] = rx2[(int64_t)(2 * dim + b) * n2 + g] * pq;
+    }
+    __syncthreads();
+    if (dim == 3) {   // t, transposed: [K][J I] -> [k][J I]
+      stage<true, false>(BA, Gr, I12, 1, l1, l2, l2 * l2);
+      stage<true, false>(AD, Gs, I12, 1, l1, l2, l2 * l2);
+      stage<true, false>(AA, Gt, D12, 1, l1, l2, l2 * l2);
+      __syncthreads();
+    }
+    const double *ba = dim == 3 ? BA : Gr, *ad = dim == 3 ? AD : Gs;
+    stage<true, false>(B, ba, I12, lz1, l1, l2, l2);            // s, transposed: [k][J][I] -> [k][j][I]
+    stage<true, false>(A, ad, D12, lz1, l1, l2, l2);
+    if (dim == 3) {
+      __syncthreads();
+      stage<true, true>(A, AA, I12, lz1, l1, l2, l2);
+    }
+    __syncthreads();
+    stage<true, false>(w, B, D12, lz1 * l1, l1, l2, 1);         // r, transposed: [k j][I] -> [k j][i]
+    __syncthreads();
+    stage<true, true>(w, A, I12, lz1 * l1, l1, l2, 1);
+    __syncthreads();
+    double *ob = out + (int64_t)b * fs + e * d.n1e;
+    const double *ui = uin ? uin + (int64_t)b * fs + e * d.n1e : nullptr;
+    for (int t = threadIdx.x; t < d.n1e; t += blockDim.x) {
+      const double v = w[t];
+      if (epi == 0) {
+        ob[t] = (ui ? alpha * ui[t] : 0.0) + beta * v;
+      } else {
+        const int i = t % l1, j = (t / l1) % l1, k = t / (l1 * l1);
+        const bool bnd = i == 0 || i == l1 - 1 || j == 0 || j == l1 - 1 || (dim == 3 && (k == 0 || k == l1 - 1));
+        ob[t] = bnd ? v : (ui ? alpha * ui[t] : 0.0) + beta * bmask[e * d.n1e + t] * v;
+      }
+    }
+  }
+}
+
+// map12: element-local field on the velocity mesh -> pressure mesh, times scale[q % n2e] (the Gauss weights)
+__global__ void __launch_bounds__(NT_NS)
+map12_kernel(NsDims d, const double *__restrict__ in, const double *__restrict__ I12g, const double *__restrict__ w3,
+             double *__restrict__ out, int invert) {
+  extern __shared__ double sm[];
+  const int l1 = d.l1, l2 = d.l2, dim = d.dim, lz1 = dim == 3 ? l1 : 1;
+  double *I12 = sm, *u = I12 + 2 * l2 * l1, *A = u + d.n1e, *AA = A + 2 * lz1 * l1 * l2;
+  for (int t = threadIdx.x; t < l2 * l1; t += blockDim.x) I12[t] = I12g[t];
+  const int64_t e = blockIdx.x;
+  for (int t = threadIdx.x; t < d.n1e; t += blockDim.x) u[t] = in[e * d.n1e + t];
+  __syncthreads();
+  stage<false, false>(A, u, I12, lz1 * l1, l2, l1, 1);
+  __syncthreads();
+  stage<false, false>(AA, A, I12, lz1, l2, l1, l2);
+  __syncthreads();
+  for (int q = threadIdx.x; q < d.n2e; q += blockDim.x) {
+    double v;
+    if (dim == 3) {
+      const int K = q / (l2 * l2), ji = q % (l2 * l2);
+      v = 0.0;
+      for (int k = 0; k < l1; ++k) v = fma(I12[K * l1 + k], AA[k * l2 * l2 + ji], v);
+    } else {
+      v = AA[q];
+    }
+    v *= w3[q];
+    out[e * d.n2e + q] = invert ? 1.0 / v : v;
+  }
+}
+
+// ---- pressure CG: device state ------------------------------------------------------------------------
+struct PcgP {
+  double rtz1, rtz2, r0, rn, mean_z, sums[4];   // sums: 0 (w,p) | 1 sum r minv r | 2 sum minv r | 3 sum r
+  double ntot;                                  // pressure points over all ranks
+  int it, done, mean_free, pad;
+};
+
+__global__ void reduce_rows_kernel(const double *__restrict__ partial, int rows, int ncol, double *__restrict__ out,
+                                   const int *__restrict__ done) {
+  if (done && *done) return;
+  // one warp per column, fixed order
+  const int c = blockIdx.x, lane = threadIdx.x;
+  double s = 0.0;
+  for (int r = lane; r < rows; r += 32) s += partial[(size_t)r * ncol + c];
+  s = warp_reduce_sum(s);
+  if (lane == 0) out[c] = s;
+}
+
+// r = rhs - mean(rhs) (mean_free) ; x = 0 ; p = 0 ; partial sums of r minv r, minv r, r
+__global__ void __launch_bounds__(NT_NS)
+pcg_init_kernel(const double *__restrict__ rhs, const double *__restrict__ minv, int64_t n2, double mean_rhs,
+                const double *__restrict__ sum_rhs, double ntot, int mean_free, double *__restrict__ r,
+                double *__restrict__ x, double *__restrict__ p, double *__restrict__ partial) {
+  const double mr = mean_free ? (sum_rhs ? *sum_rhs / ntot : mean_rhs) : 0.0;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = rhs[i] - mr, zi = minv[i] * ri;
+    r[i] = ri;
+    x[i] = 0.0;
+    p[i] = 0.0;
+    s1 = fma(ri, zi, s1);
+    s2 += zi;
+    s3 += ri;
+  }
+  s1 = block_reduce_sum<NT_NS>(s1);
+  s2 = block_reduce_sum<NT_NS>(s2);
+  s3 = block_reduce_sum<NT_NS>(s3);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x * 3 + 0] = s1;
+    partial[blockIdx.x * 3 + 1] = s2;
+    partial[blockIdx.x * 3 + 2] = s3;
+  }
+}
+
+__global__ void sum_kernel(const double *__restrict__ a, int64_t n, double *__restrict__ partial) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i];
+  s = block_reduce_sum<NT_NS>(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// after a residual reduction: rtz2 <- rtz1 ; rtz1 <- (r, z) with z = minv r - mean(minv r) ; stopping test
+__global__ void pcg_after_r_kernel(PcgP *st, double tol, int first) {
+  if (st->done) return;
+  const double mz = st->mean_free ? st->sums[2] / st->ntot : 0.0;
+  const double rtz = st->sums[1] - mz * st->sums[3];
+  st->mean_z = mz;
+  if (first) {
+    st->rtz1 = rtz;
+    st->rtz2 = 1.0;
+    st->r0 = -1.0;
+    st->rn = 0.0;
+    st->it = 0;
+    if (!(rtz > 0.0)) st->done = 1;
+    return;
+  }
+  st->rtz2 = st->rtz1;
+  st->rtz1 = rtz;
+  st->rn = sqrt(fabs(rtz));
+  if (st->r0 < 0.0) st->r0 = sqrt(fabs(st->rtz2));
+  if (st->rn <= tol * st->r0) st->done = 1;
+}
+
+// p = (minv r - mean_z) + beta p ; it += 1
+__global__ void __launch_bounds__(NT_NS)
+pcg_p_kernel(PcgP *st, const double *__restrict__ r, const double *__restrict__ minv, double *__restrict__ p, int64_t n2) {
+  if (st->done) return;
+  const double beta = st->it == 0 ? 0.0 : st->rtz1 / st->rtz2, mz = st->mean_z;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = (minv[i] * r[i] - mz) + beta * p[i];
+}
+
+// rho = (w, p): not positive -> stop (before the update, like Nek's cggo / uzawa) ; else it += 1
+__global__ void pcg_after_w_kernel(PcgP *st) {
+  if (st->done) return;
+  st->it += 1;
+  if (!(st->sums[0] > 0.0)) st->done = 1;
+}
+
+// x += alpha p ; r -= alpha w ; partial sums of r minv r, minv r, r
+__global__ void __launch_bounds__(NT_NS)
+pcg_xr_kernel(const PcgP *st, const double *__restrict__ p, const double *__restrict__ w, const double *__restrict__ minv,
+              double *__restrict__ x, double *__restrict__ r, int64_t n2, double *__restrict__ partial) {
+  if (st->done) return;
+  const double alpha = st->rtz1 / st->sums[0];
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, w[i], r[i]), zi = minv[i] * ri;
+    r[i] = ri;
+    s1 = fma(ri, zi, s1);
+    s2 += zi;
+    s3 += ri;
+  }
+  s1 = block_reduce_sum<NT_NS>(s1);
+  s2 = block_reduce_sum<NT_NS>(s2);
+  s3 = block_reduce_sum<NT_NS>(s3);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x * 3 + 0] = s1;
+    partial[blockIdx.x * 3 + 1] = s2;
+    partial[blockIdx.x * 3 + 2] = s3;
+  }
+}
+
+// out = a + c * b on n entries (pressure update p* + dp, extrapolation 2 p - plag)
+__global__ void lin2_kernel(double *__restrict__ out, const double *__restrict__ a, double ca, const double *__restrict__ b,
+                            double cb, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ca * a[i] + cb * b[i];
+}
+
+NsDims ns_dims(nsb_sem_t S) {
+  NsDims d;
+  d.dim = S->dim;
+  d.l1 = S->lx;
+  d.l2 = S->lx2;
+  d.n1e = S->lx * S->lx * (S->dim == 3 ? S->lx : 1);
+  d.n2e = S->lx2 * S->lx2 * (S->dim == 3 ? S->lx2 : 1);
+  return d;
+}
+
+size_t ns_smem(nsb_sem_t S) { return sizeof(double) * ns_smem_doubles(S->dim, S->lx, S->lx2); }
+
+int launch_opdiv(nsb_sem_t S, const double *vel, int64_t fs, double scale, double *out, const double *dotw,
+                 double *dot_partial, const int *done) {
+  nsb_context_t ctx = S->ctx;
+  // algorithmic bytes: dim velocity fields and dim^2 metric arrays read, one pressure array written
+  ProfScope ps(ctx, PC_AXHELM, 8.0 * ((double)S->dim * S->npts + ((double)S->dim * S->dim + 1.0) * S->n2));
+  opdiv_kernel<<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), vel, fs, S->rx2_d, S->n2, S->i12_d,
+                                                                    S->d12_d, scale, out, dotw, dot_partial, done);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+int launch_opgradt(nsb_sem_t S, const double *p, double *out, int64_t fs, int epi, const double *uin, double alpha,
+                   double beta, const int *done) {
+  nsb_context_t ctx = S->ctx;
+  ProfScope ps(ctx, PC_AXHELM, 8.0 * ((double)S->dim * S->npts * (uin ? 2.0 : 1.0) + ((double)S->dim * S->dim + 1.0) * S->n2));
+  opgradt_kernel<<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), p, S->rx2_d, S->n2, S->i12_d, S->d12_d,
+                                                                      out, fs, epi, uin, alpha, beta, S->bmask_d, done);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+// out = alpha uin + beta B^-1 D^T p  on the dim velocity fields at `out` (uin may alias out only when alpha == 0)
+int launch_binv_gradt(nsb_sem_t S, const double *p, double *out, int64_t fs, const double *uin, double alpha, double beta,
+                      const int *done) {
+  NSB_CHECK(launch_opgradt(S, p, out, fs, 1, uin, alpha, beta, done));
+  return launch_gs_ext(S, out, S->dim, fs, 1, uin ? uin : out, uin ? alpha : 0.0, beta, S->bmask_d);
+}
+
+// velocity-shaped scratch of the mesh: dim fields of npts after the three pressure work vectors
+double *ns_vel_scratch(nsb_sem_t S) { return S->ns_work_d + 3 * ((S->n2 + 31) & ~(int64_t)31); }
+
+int pressure_ptr(nsb_sem_t S, nsb_basis_t B, int col, double **out, const char *who) {
+  NSB_REQUIRE(S && B, "%s: NULL argument", who);
+  NSB_REQUIRE(S->lx2 > 0, "%s: call nsb_sem_pressure_setup first", who);
+  NSB_REQUIRE(col >= 0 && col < B->ncols, "%s: column %d out of range", who, col);
+  nsb_layout_t L = B->lay;
+  NSB_REQUIRE(L->ctx == S->ctx, "%s: basis and mesh live on different contexts", who);
+  NSB_REQUIRE(!L->c0_sem, "%s: the C0 storage layout is not supported by the time-stepper pieces", who);
+  NSB_REQUIRE(L->nfields > S->dim && L->len[S->dim] == S->n2,
+              "%s: field %d of the layout must be the pressure (%lld Gauss points on this mesh)", who, S->dim,
+              (long long)S->n2);
+  *out = B->col(col) + L->off[S->dim];
+  return NSB_OK;
+}
+
+int velocity_ptr(nsb_sem_t S, nsb_basis_t B, int col, double **out, int64_t *fs, const char *who) {
+  NSB_REQUIRE(S && B, "%s: NULL argument", who);
+  NSB_REQUIRE(S->lx2 > 0, "%s: call nsb_sem_pressure_setup first", who);
+  NSB_REQUIRE(col >= 0 && col < B->ncols, "%s: column %d out of range", who, col);
+  nsb_layout_t L = B->lay;
+  NSB_REQUIRE(L->ctx == S->ctx, "%s: basis and mesh live on different contexts", who);
+  NSB_REQUIRE(!L->c0_sem, "%s: the C0 storage layout is not supported by the time-stepper pieces", who);
+  NSB_REQUIRE(L->nfields >= S->dim, "%s: the layout has %d fields, the velocity needs %d", who, L->nfields, S->dim);
+  const int64_t s = S->dim > 1 ? L->off[1] - L->off[0] : 0;
+  for (int f = 0; f < S->dim; ++f) {
+    NSB_REQUIRE(L->len[f] == S->npts, "%s: field %d has %lld points, mesh has %lld", who, f, (long long)L->len[f],
+                (long long)S->npts);
+    NSB_REQUIRE(f == 0 || L->off[f] - L->off[f - 1] == s, "%s: velocity fields are not equally spaced", who);
+  }
+  *out = B->col(col) + L->off[0];
+  *fs = s;
+  return NSB_OK;
+}
+
+// E dp = rhs on device arrays; x receives dp.  Host involvement: one 4-byte poll every 8 iterations.
+int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, int mean_free, int *iters, double *res) {
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int64_t n2 = S->n2, n2p = (n2 + 31) & ~(int64_t)31;
+  double *r = S->ns_work_d, *p = r + n2p, *w = p + n2p, *wv = ns_vel_scratch(S);
+  PcgP *state = reinterpret_cast<PcgP *>(S->ns_state_d);
+  double *sums = S->ns_state_d + offsetof(PcgP, sums) / sizeof(double);
+  const int *done = reinterpret_cast<const int *>(reinterpret_cast<const char *>(state) + offsetof(PcgP, done));
+  const int grid = (int)std::min<int64_t>((n2 + NT_NS - 1) / NT_NS, (int64_t)ctx->num_sms * 8);
+  NSB_CHECK(ensure_partial(ctx, std::max<int64_t>((3 * (int64_t)grid + kMaxK + 7) / (kMaxK + 8) + 1,
+                                                  (S->nel + kMaxK + 7) / (kMaxK + 8) + 1)));
+  double *partial = ctx->partial_d;
+  double ntot = (double)n2;
+  PcgP h0;
+  memset(&h0, 0, sizeof(h0));
+  h0.mean_free = mean_free;
+  if (ctx->nranks > 1) {
+    // total number of pressure points: one all-reduce of a device scalar through the state block
+    h0.ntot = ntot;
+    NSB_CUDA(cudaMemcpyAsync(state, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+    NSB_CHECK(allreduce_sum_d(ctx, S->ns_state_d + offsetof(PcgP, ntot) / sizeof(double), 1));
+    NSB_CUDA(cudaMemcpyAsync(&ntot, S->ns_state_d + offsetof(PcgP, ntot) / sizeof(double), sizeof(double),
+                             cudaMemcpyDeviceToHost, st));
+    NSB_CUDA(cudaStreamSynchronize(st));
+  }
+  h0.ntot = ntot;
+  NSB_CUDA(cudaMemcpyAsync(state, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+  double *sum_rhs = nullptr;
+  if (mean_free) {   // mean of the right-hand side over all ranks -> sums[3], read by the init kernel
+    sum_kernel<<<grid, NT_NS, 0, st>>>(rhs, n2, partial);
+    reduce_rows_kernel<<<1, 32, 0, st>>>(partial, grid, 1, sums + 3, nullptr);
+    ctx->launches += 2;
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 3, 1));
+    sum_rhs = sums + 3;
+  }
+  pcg_init_kernel<<<grid, NT_NS, 0, st>>>(rhs, S->bm2inv_d, n2, 0.0, sum_rhs, ntot, mean_free, r, x, p, partial);
+  reduce_rows_kernel<<<3, 32, 0, st>>>(partial, grid, 3, sums + 1, nullptr);
+  ctx->launches += 2;
+  if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 1, 3));
+  pcg_after_r_kernel<<<1, 1, 0, st>>>(state, tol, 1);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  const int64_t fs = S->npts;
+  PcgP *hst = reinterpret_cast<PcgP *>(ctx->hpin + 3 * (kMaxK + 8) + 64);
+  for (int it = 1; it <= maxit; ++it) {
+    pcg_p_kernel<<<grid, NT_NS, 0, st>>>(state, r, S->bm2inv_d, p, n2);
+    ctx->launches++;
+    NSB_CHECK(launch_binv_gradt(S, p, wv, fs, nullptr, 0.0, 1.0, done));           // wv = B^-1 D^T p
+    NSB_CHECK(launch_opdiv(S, wv, fs, 1.0, w, p, partial, done));                 // w = D wv, partial (w, p)
+    reduce_rows_kernel<<<1, 32, 0, st>>>(partial, (int)S->nel, 1, sums, done);
+    ctx->launches++;
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums, 1));
+    pcg_after_w_kernel<<<1, 1, 0, st>>>(state);
+    pcg_xr_kernel<<<grid, NT_NS, 0, st>>>(state, p, w, S->bm2inv_d, x, r, n2, partial);
+    reduce_rows_kernel<<<3, 32, 0, st>>>(partial, grid, 3, sums + 1, done);
+    ctx->launches += 3;
+    if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 1, 3));
+    pcg_after_r_kernel<<<1, 1, 0, st>>>(state, tol, 0);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    if (it % 8 == 0 || it == maxit) {
+      NSB_CUDA(cudaMemcpyAsync(hst, state, sizeof(PcgP), cudaMemcpyDeviceToHost, st));
+      NSB_CUDA(cudaStreamSynchronize(st));
+      if (hst->done) break;
+    }
+  }
+  NSB_CUDA(cudaMemcpyAsync(hst, state, sizeof(PcgP), cudaMemcpyDeviceToHost, st));
+  NSB_CUDA(cudaStreamSynchronize(st));
+  NSB_CHECK(check_dev_err(ctx));
+  if (iters) *iters = hst->it;
+  if (res) *res = hst->r0 > 0.0 ? hst->rn / hst->r0 : 0.0;
+  return NSB_OK;
+}
+
+const double kBDn[4][4] = {{0, 0, 0, 0}, {1.0, 1.0, 0, 0}, {1.5, 2.0, -0.5, 0}, {11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0}};
+const double kABn[4][3] = {{0, 0, 0}, {1.0, 0, 0}, {2.0, -1.0, 0}, {3.0, -3.0, 1.0}};
+
+}  // namespace
+
+void nsb::ns_free(nsb_sem_t S) {
+  for (double *q : {S->i12_d, S->d12_d, S->rx2_d, S->bm2inv_d, S->ns_work_d, S->ns_state_d})
+    if (q) cudaFree(q);
+  S->i12_d = S->d12_d = S->rx2_d = S->bm2inv_d = S->ns_work_d = S->ns_state_d = nullptr;
+  S->lx2 = 0;
+}
+
+// Host-only: the matrices of the pressure mesh (compared with an independent construction by the CPU tests).
+extern "C" int nsb_pressure_matrices(int N, double *z2, double *w2, double *I12, double *D12) {
+  NSB_REQUIRE(N >= 3 && N <= 15, "nsb_pressure_matrices: N=%d (3..15)", N);
+  const int l1 = N + 1, l2 = N - 1;
+  std::vector<double> z1(l1), w1(l1), D(l1 * l1), zz, ww;
+  NSB_CHECK(nsb_gll(N, z1.data(), w1.data(), D.data()));   // D[i + l1 * j] = dxm1(i, j)
+  gauss_legendre(l2, zz, ww);
+  const std::vector<double> J = interp_matrix(z1, zz);      // [l2][l1]
+  for (int I = 0; I < l2; ++I) {
+    if (z2) z2[I] = zz[I];
+    if (w2) w2[I] = ww[I];
+    for (int i = 0; i < l1; ++i) {
+      if (I12) I12[I * l1 + i] = J[(size_t)I * l1 + i];
+      if (D12) {
+        double s = 0.0;
+        for (int m = 0; m < l1; ++m) s += J[(size_t)I * l1 + m] * D[m + l1 * i];
+        D12[I * l1 + i] = s;
+      }
+    }
+  }
+  return NSB_OK;
+}
+
+extern "C" int nsb_sem_pressure_setup(nsb_sem_t S) {
+  NSB_REQUIRE(S, "nsb_sem_pressure_setup: NULL argument");
+  NSB_REQUIRE(S->N >= 3, "nsb_sem_pressure_setup: P_N - P_N-2 needs N >= 3 (N = %d)", S->N);
+  if (S->lx2 > 0) return NSB_OK;
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  const int l1 = S->lx, l2 = l1 - 2, dim = S->dim;
+  const int n2e = l2 * l2 * (dim == 3 ? l2 : 1);
+  NSB_REQUIRE(n2e <= MAXQ * NT_NS, "nsb_sem_pressure_setup: N=%d not supported in %d-D", S->N, dim);
+  std::vector<double> z2(l2), w2(l2), I12(l2 * l1), D12(l2 * l1), w3(n2e);
+  NSB_CHECK(nsb_pressure_matrices(S->N, z2.data(), w2.data(), I12.data(), D12.data()));
+  for (int q = 0; q < n2e; ++q) {
+    const int i = q % l2, j = (q / l2) % l2, k = q / (l2 * l2);
+    w3[q] = w2[i] * w2[j] * (dim == 3 ? w2[k] : 1.0);
+  }
+  S->lx2 = l2;
+  S->n2 = S->nel * n2e;
+  const int64_t n2p = (S->n2 + 31) & ~(int64_t)31;
+  double *w3_d = nullptr;
+  auto fail = [&](const char *what) {
+    if (w3_d) cudaFree(w3_d);
+    ns_free(S);
+    set_error("nsb_sem_pressure_setup: %s", what);
+    return NSB_ECUDA;
+  };
+  if (cudaMalloc(&S->i12_d, sizeof(double) * l2 * l1) != cudaSuccess ||
+      cudaMalloc(&S->d12_d, sizeof(double) * l2 * l1) != cudaSuccess ||
+      cudaMalloc(&S->rx2_d, sizeof(double) * dim * dim * std::max<int64_t>(S->n2, 1)) != cudaSuccess ||
+      cudaMalloc(&S->bm2inv_d, sizeof(double) * std::max<int64_t>(S->n2, 1)) != cudaSuccess ||
+      cudaMalloc(&S->ns_work_d, sizeof(double) * (3 * n2p + dim * std::max<int64_t>(S->npts, 1))) != cudaSuccess ||
+      cudaMalloc(&S->ns_state_d, sizeof(PcgP)) != cudaSuccess || cudaMalloc(&w3_d, sizeof(double) * n2e) != cudaSuccess)
+    return fail("out of device memory");
+  S->lx2 = l2;
+  cudaStream_t st = ctx->stream;
+  NSB_CUDA(cudaMemcpyAsync(S->i12_d, I12.data(), sizeof(double) * l2 * l1, cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(S->d12_d, D12.data(), sizeof(double) * l2 * l1, cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(w3_d, w3.data(), sizeof(double) * n2e, cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemsetAsync(S->ns_state_d, 0, sizeof(PcgP), st));
+  const size_t smem = ns_smem(S);
+  NSB_CUDA(cudaFuncSetAttribute(opdiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(opgradt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(map12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (S->nel > 0) {
+    const NsDims d = ns_dims(S);
+    for (int m = 0; m < dim * dim; ++m)   // rxm2 = w3m2 * map12(rxm1)
+      map12_kernel<<<(unsigned)S->nel, NT_NS, smem, st>>>(d, S->rst_d + (int64_t)m * S->npts, S->i12_d, w3_d,
+                                                         S->rx2_d + (int64_t)m * S->n2, 0);
+    map12_kernel<<<(unsigned)S->nel, NT_NS, smem, st>>>(d, S->jac_d, S->i12_d, w3_d, S->bm2inv_d, 1);
+    ctx->launches += dim * dim + 1;
+  }
+  NSB_CUDA(cudaGetLastError());
+  NSB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(w3_d);
+  return NSB_OK;
+}
+
+extern "C" int64_t nsb_sem_npres(nsb_sem_t S) { return (S && S->lx2 > 0) ? S->n2 : -1; }
+
+// which: 0 rx2 [dim*dim][n2], 1 bm2inv [n2]
+extern "C" int nsb_sem_pressure_get(nsb_sem_t S, int which, double *out) {
+  NSB_REQUIRE(S && out && S->lx2 > 0, "nsb_sem_pressure_get: bad argument (nsb_sem_pressure_setup first)");
+  NSB_REQUIRE(which == 0 || which == 1, "nsb_sem_pressure_get: unknown selector %d", which);
+  cudaSetDevice(S->ctx->device);
+  NSB_CUDA(cudaStreamSynchronize(S->ctx->stream));
+  const size_t n = which == 0 ? (size_t)S->dim * S->dim * S->n2 : (size_t)S->n2;
+  NSB_CUDA(cudaMemcpy(out, which == 0 ? S->rx2_d : S->bm2inv_d, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return NSB_OK;
+}
+
+extern "C" int nsb_sem_opdiv(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  double *v, *p;
+  int64_t fs;
+  NSB_CHECK(velocity_ptr(S, bin, cin, &v, &fs, "nsb_sem_opdiv"));
+  NSB_CHECK(pressure_ptr(S, bout, cout, &p, "nsb_sem_opdiv"));
+  cudaSetDevice(S->ctx->device);
+  return launch_opdiv(S, v, fs, 1.0, p, nullptr, nullptr, nullptr);
+}
+
+extern "C" int nsb_sem_opgradt(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  double *v, *p;
+  int64_t fs;
+  NSB_CHECK(pressure_ptr(S, bin, cin, &p, "nsb_sem_opgradt"));
+  NSB_CHECK(velocity_ptr(S, bout, cout, &v, &fs, "nsb_sem_opgradt"));
+  cudaSetDevice(S->ctx->device);
+  return launch_opgradt(S, p, v, fs, 0, nullptr, 0.0, 1.0, nullptr);
+}
+
+extern "C" int nsb_sem_cdabdtp(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  double *pi, *po;
+  NSB_CHECK(pressure_ptr(S, bin, cin, &pi, "nsb_sem_cdabdtp"));
+  NSB_CHECK(pressure_ptr(S, bout, cout, &po, "nsb_sem_cdabdtp"));
+  NSB_REQUIRE(S->exchange_ready || S->ctx->nranks == 1, "nsb_sem_cdabdtp: call nsb_sem_setup_exchange first");
+  cudaSetDevice(S->ctx->device);
+  double *wv = ns_vel_scratch(S);
+  NSB_CHECK(launch_binv_gradt(S, pi, wv, S->npts, nullptr, 0.0, 1.0, nullptr));
+  return launch_opdiv(S, wv, S->npts, 1.0, po, nullptr, nullptr, nullptr);
+}
+
+extern "C" int nsb_sem_esolve(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, double tol, int maxit,
+                              int mean_free, int *iters, double *res) {
+  double *rhs, *x;
+  NSB_CHECK(pressure_ptr(S, brhs, crhs, &rhs, "nsb_sem_esolve"));
+  NSB_CHECK(pressure_ptr(S, bx, cx, &x, "nsb_sem_esolve"));
+  NSB_REQUIRE(rhs != x, "nsb_sem_esolve: right-hand side and solution are the same vector");
+  NSB_REQUIRE(tol > 0.0 && maxit >= 1, "nsb_sem_esolve: bad tolerance / iteration limit");
+  NSB_REQUIRE(S->exchange_ready || S->ctx->nranks == 1, "nsb_sem_esolve: call nsb_sem_setup_exchange first");
+  return esolve_d(S, rhs, x, tol, maxit, mean_free, iters, res);
+}
+
+// Operator handle with the structure of exponential_prop%matvec for the linearised Navier-Stokes equations:
+// fields 0..dim-1 of the layout are the velocity, field dim the pressure (lx2 mesh); the input vector's velocity AND
+// pressure start nsteps BDF/EXT steps (order ramp 1, 2, 3: the reference restarts the time-stepper for every
+// matvec), the output vector receives the final velocity and pressure.  base/col_base: base flow U (velocity fields
+// of that column), NULL for the Stokes operator.  Uses both convection slots of the mesh (0: U, 1: v).
+extern "C" int nsb_op_create_ns_stepper(nsb_sem_t S, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu,
+                                        double dt, int nsteps, double tol_v, double tol_p, int maxit, int mean_free,
+                                        nsb_op_t *out) {
+  NSB_REQUIRE(S && layout && out, "nsb_op_create_ns_stepper: NULL argument");
+  NSB_REQUIRE(nu > 0.0 && dt > 0.0 && nsteps >= 1 && maxit >= 1 && tol_v > 0.0 && tol_p > 0.0,
+              "nsb_op_create_ns_stepper: bad parameter");
+  NSB_REQUIRE(layout->ctx == S->ctx, "nsb_op_create_ns_stepper: layout and mesh live on different contexts");
+  NSB_REQUIRE(S->exchange_ready, "nsb_op_create_ns_stepper: call nsb_sem_setup_exchange first");
+  NSB_CHECK(nsb_sem_pressure_setup(S));
+  NSB_REQUIRE(!layout->c0_sem, "nsb_op_create_ns_stepper: the C0 storage layout is not supported");
+  NSB_REQUIRE(layout->nfields > S->dim && layout->len[S->dim] == S->n2,
+              "nsb_op_create_ns_stepper: field %d of the layout must be the pressure (%lld Gauss points)", S->dim,
+              (long long)S->n2);
+  for (int f = 0; f < S->dim; ++f)
+    NSB_REQUIRE(layout->len[f] == S->npts, "nsb_op_create_ns_stepper: field %d has %lld points, mesh has %lld", f,
+                (long long)layout->len[f], (long long)S->npts);
+  if (base) {
+    NSB_REQUIRE(base->lay == layout && col_base >= 0 && col_base < base->ncols,
+                "nsb_op_create_ns_stepper: the base flow must be a column of a basis with the same layout");
+    NSB_REQUIRE(S->lxd > 0, "nsb_op_create_ns_stepper: call nsb_sem_dealias_setup first");
+  }
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 4;
+  op->sem = S;
+  op->lay = layout;
+  op->nfields_apply = S->dim + 1;
+  op->nu = nu;
+  op->dt = dt;
+  op->nsteps = nsteps;
+  op->tol = tol_v;
+  op->tol_p = tol_p;
+  op->maxit = maxit;
+  op->mean_free = mean_free;
+  op->has_base = base != nullptr;
+  int r = nsb_basis_create(layout, 10, &op->tmp);
+  if (r == NSB_OK && base) {
+    r = nsb_vec_copy(op->tmp, 9, base, col_base);
+    if (r == NSB_OK) r = nsb_sem_set_convect(S, 0, op->tmp, 9, 0);
+  }
+  if (r != NSB_OK) {
+    if (op->tmp) nsb_basis_destroy(op->tmp);
+    delete op;
+    return r;
+  }
+  *out = op;
+  return NSB_OK;
+}
+
+extern "C" int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure) {
+  NSB_REQUIRE(op && op->kind == 4, "nsb_op_ns_iterations: not a Navier-Stokes stepper operator");
+  if (helmholtz) *helmholtz = op->helm_iters;
+  if (pressure) *pressure = op->pres_iters;
+  return NSB_OK;
+}
+
+int nsb::ns_stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: time-stepper operator built for another layout");
+  nsb_sem_t S = op->sem;
+  nsb_basis_t W = op->tmp;
+  nsb_layout_t L = op->lay;
+  nsb_context_t ctx = L->ctx;
+  const int dim = S->dim;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  // work columns of W.  velocity fields: lag[3] rolling (0, 1, 2 + the free one), 4 bf, 5 e1, 6 e2, 7 v*, 9 U
+  //                     pressure field:  col 0 p, 1 plag, 2 p*, 3 rhs of E, 4 dp
+  for (int c = 0; c < 9; ++c) NSB_CHECK(nsb_vec_zero(W, c));
+  int lag[3] = {0, 1, 2}, nw = 3;
+  const int bf = 4, e1 = 5, e2 = 6, vs = 7, cU = 9;
+  const int64_t fs = dim > 1 ? L->off[1] - L->off[0] : 0;
+  const int64_t n2 = S->n2;
+  const int g2 = (int)std::min<int64_t>((n2 + 255) / 256 + 1, (int64_t)ctx->num_sms * 8);
+  auto vel = [&](int c) { return W->col(c) + L->off[0]; };
+  auto prs = [&](int c) { return W->col(c) + L->off[dim]; };
+  // cold start: velocity and pressure of the input vector
+  for (int f = 0; f < dim; ++f)
+    NSB_CUDA(cudaMemcpyAsync(vel(lag[0]) + f * fs, bin->col(cin) + L->off[f], sizeof(double) * S->npts,
+                             cudaMemcpyDeviceToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(prs(0), bin->col(cin) + L->off[dim], sizeof(double) * n2, cudaMemcpyDeviceToDevice, st));
+  for (int n = 1; n <= op->nsteps; ++n) {
+    const int o = n < 3 ? n : 3;
+    const double bd0 = kBDn[o][0];
+    // advabp: bf = -[(U.grad) v + (v.grad) U], mass matrix inside the dealiased quadrature
+    if (op->has_base) {
+      NSB_CHECK(nsb_sem_convect(S, 0, W, lag[0], W, bf, 0, dim, -1.0, 0));
+      NSB_CHECK(nsb_sem_set_convect(S, 1, W, lag[0], 0));
+      NSB_CHECK(nsb_sem_convect(S, 1, W, cU, W, bf, 0, dim, -1.0, 1));
+    } else {
+      for (int f = 0; f < dim; ++f) NSB_CUDA(cudaMemsetAsync(vel(bf) + f * fs, 0, sizeof(double) * S->npts, st));
+    }
+    NSB_CHECK(nsb_sem_bdf_ext(S, W, bf, e1, e2, lag, o, 0, dim, kABn[o], kBDn[o], 1.0 / op->dt));
+    // p* (extrapprp): p^(n-1), from the third step on 2 p^(n-1) - p^(n-2)
+    lin2_kernel<<<g2, 256, 0, st>>>(prs(2), prs(0), o < 3 ? 1.0 : 2.0, prs(1), o < 3 ? 0.0 : -1.0, n2);
+    ctx->launches++;
+    // cresvipp + ophinv in the non-incremental form: H v* = QQ^T (bf + D^T p*)
+    NSB_CHECK(launch_opgradt(S, prs(2), vel(bf), fs, 0, vel(bf), 1.0, 1.0, nullptr));
+    NSB_CHECK(launch_gs_ext(S, vel(bf), dim, fs, 0, nullptr, 0.0, 0.0, nullptr));
+    {
+      int it[3] = {0, 0, 0};
+      double res[3];
+      NSB_CHECK(nsb_sem_hmholtz_vec(S, W, bf, W, vs, 0, dim, op->nu, bd0 / op->dt, op->tol, op->maxit, it, res));
+      for (int g = 0; g < dim; ++g) op->helm_iters += it[g];
+    }
+    // incomprp: E dp = -(bd0/dt) D v* ; v = v* + (dt/bd0) B^-1 D^T dp ; p = p* + dp
+    NSB_CHECK(launch_opdiv(S, vel(vs), fs, -bd0 / op->dt, prs(3), nullptr, nullptr, nullptr));
+    {
+      int it = 0;
+      double res = 0.0;
+      NSB_CHECK(esolve_d(S, prs(3), prs(4), op->tol_p, op->maxit, op->mean_free, &it, &res));
+      op->pres_iters += it;
+    }
+    NSB_CHECK(launch_binv_gradt(S, prs(4), vel(nw), fs, vel(vs), 1.0, op->dt / bd0, nullptr));
+    NSB_CUDA(cudaMemcpyAsync(prs(1), prs(0), sizeof(double) * n2, cudaMemcpyDeviceToDevice, st));
+    lin2_kernel<<<g2, 256, 0, st>>>(prs(0), prs(2), 1.0, prs(4), 1.0, n2);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    const int freed = lag[2];
+    lag[2] = lag[1];
+    lag[1] = lag[0];
+    lag[0] = nw;
+    nw = freed;
+  }
+  // fields outside the operator and %time are carried through
+  NSB_CHECK(nsb_vec_copy(bout, cout, bin, cin));
+  for (int f = 0; f < dim; ++f)
+    NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->off[f], vel(lag[0]) + f * fs, sizeof(double) * S->npts,
+                             cudaMemcpyDeviceToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(bout->col(cout) + L->off[dim], prs(0), sizeof(double) * n2, cudaMemcpyDeviceToDevice, st));
+  return NSB_OK;
+}

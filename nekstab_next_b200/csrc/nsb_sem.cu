@@ -1276,6 +1276,10 @@ int launch_axhelm_ext(nsb_sem_t S, const double *u, double *w, int nf, int64_t f
                       const double *cv, int epi, double alpha, double beta, const double *bmask) {
   return launch_axhelm(S, u, w, nf, fstride, h1, h2, cv, epi, alpha, beta, bmask);
 }
+int launch_gs_ext(nsb_sem_t S, double *v, int nf, int64_t fstride, int epi, const double *uin, double alpha, double beta,
+                  const double *bmask) {
+  return launch_gs(S, v, nf, fstride, epi, uin, alpha, beta, bmask);
+}
 // Host plan of the gather-scatter: unique nodes owning at least one element-boundary point, CSR,
 // ordered by first local index so neighbouring threads touch neighbouring memory.
 int gs_plan(int dim, int lx, int64_t nel, const int64_t *glo_num, const double *mask, std::vector<int64_t> &off,
@@ -1561,6 +1565,7 @@ extern "C" int nsb_sem_destroy(nsb_sem_t S) {
   for (double *q : {S->J_d, S->Dg_d, S->rxf_d, S->cfine_d[0], S->cfine_d[1]})
     if (q) cudaFree(q);
   if (S->pcg_d) cudaFree(S->pcg_d);
+  ns_free(S);
   if (S->c0_scratch_d) cudaFree(S->c0_scratch_d);
   if (S->c0_l2u_d) cudaFree(S->c0_l2u_d);
   if (S->ev_a) cudaEventDestroy(S->ev_a);
@@ -2079,6 +2084,7 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
   NSB_REQUIRE(!(bin == bout && cin == cout), "nsb_op_apply: in-place application is not supported");
   op->napply++;
   if (op->kind == 3) return nsb::stepper_apply(op, bin, cin, bout, cout);
+  if (op->kind == 4) return nsb::ns_stepper_apply(op, bin, cin, bout, cout);
   if (op->kind == 2) {
     NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: composite operator built for another layout");
     NSB_CHECK(nsb_op_apply(op->inner, bin, cin, op->tmp, 0));

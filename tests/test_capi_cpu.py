@@ -201,3 +201,17 @@ def test_seed_noise_matches_reference_formula():
     r = fc[0] * (1 + 0.0) + fc[1] * 1 + fc[2] * 1
     r = fc[0] * (1 + 0.0 * np.sin(r)) + fc[1] * 1 + fc[2] * 1
     assert abs(seed.noise_fields((x, y, z))[0][0, 0, 0, 0] - np.cos(1e3 * np.sin(1e3 * np.sin(r)))) < 1e-12
+
+
+def test_pressure_mesh_matrices_match_oracle():
+    """nsb_pressure_matrices (host-only): ixm12 / dxm12 of the P_N - P_N-2 pressure mesh vs the oracle's."""
+    import nekstab_next_b200 as nb
+    from oracle import sem as osem
+    for N in (3, 4, 5, 7, 9):
+        z2, w2, I12, D12 = nb.pressure_matrices(N)
+        zo, wo = osem.gl(N - 1)
+        z1, _ = osem.gll(N)
+        Io = osem.interp_matrix(z1, zo)
+        assert np.max(np.abs(z2 - zo)) <= 1e-14 and np.max(np.abs(w2 - wo)) <= 1e-14
+        assert np.max(np.abs(I12 - Io)) <= 1e-13
+        assert np.max(np.abs(D12 - Io @ osem.dgll(N))) <= 1e-11

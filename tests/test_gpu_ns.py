@@ -1,0 +1,220 @@
+"""The pressure-coupled perturbation step on the device (nsb_ns.cu) against the oracle restatement of Nek5000's
+P_N - P_N-2 path (oracle/ns.py, [UPSTREAM-RECALL], parity unpinned; the oracle itself is pinned by independent
+mathematics in tests/test_oracle_ns.py).  fp64: kernels 1e-12 relative, solves to their tolerances."""
+import numpy as np
+import pytest
+
+from helpers import relerr
+from oracle import ns as ons
+from oracle import sem as osem
+from oracle import krylov as okr
+
+pytestmark = pytest.mark.gpu
+
+
+class NsProblem:
+    def __init__(self, nel, N, deform=0.04, seed=0):
+        self.dim, self.N = len(nel), N
+        if self.dim == 3:
+            x, y, z, glo = osem.box_mesh(*nel, N, deform=deform)
+            x0, y0, z0, _ = osem.box_mesh(*nel, N)
+            self.coords = (x, y, z)
+            self.mask = osem.boundary_mask_box(None, x0, y0, z0)
+            tp = 2 * np.pi
+            self.base = [np.sin(tp * x) * np.cos(tp * y) * np.cos(tp * z), -np.cos(tp * x) * np.sin(tp * y) * np.cos(tp * z),
+                         0.3 + 0 * x]
+        else:
+            x, y, glo = osem.box_mesh_2d(*nel, N, deform=deform)
+            x0, y0, _ = osem.box_mesh_2d(*nel, N)
+            self.coords = (x, y)
+            self.mask = osem.boundary_mask_box(None, x0, y0, None, lengths=(1.0, 1.0))
+            self.base = [1.0 + 0.3 * np.sin(np.pi * y), 0.4 * np.cos(np.pi * x)]
+        self.glo = glo
+        self.geo = osem.geometry(N, *self.coords)
+        self.ps = ons.pressure_setup(N, self.geo)
+        self.lxd = 8 if (N == 4 and self.dim == 3) else 3 * (N + 1) // 2
+        self.dl = osem.dealias_setup(N, self.lxd, self.geo['rst'])
+        self.binv = 1.0 / osem.dssum(self.geo['bm1'], glo)
+        self.vmult = 1.0 / osem.multiplicity(glo)
+        self.shape, self.pshape = x.shape, self.ps['bm2'].shape
+        self.npts, self.n2 = x.size, self.ps['bm2'].size
+        self.rng = np.random.default_rng(seed)
+
+    def vel(self):
+        return [osem.dssum(self.rng.standard_normal(self.shape), self.glo) * self.vmult * self.mask
+                for _ in range(self.dim)]
+
+    def pres(self):
+        return self.rng.standard_normal(self.pshape)
+
+    def gpu(self, ctx, ncols):
+        import nekstab_next_b200 as nb
+        z = self.coords[2] if self.dim == 3 else None
+        sem = nb.Sem(ctx, self.N, self.coords[0], self.coords[1], z, mask=self.mask, glo_num=self.glo)
+        assert sem.pressure_setup() == self.n2
+        lay = nb.Layout(ctx, [self.npts] * self.dim + [self.n2], [True] * self.dim + [False])
+        lay.set_weight([self.geo['bm1']] * self.dim)
+        return sem, lay, nb.Basis(lay, ncols)
+
+    def up(self, vec, vel, p):
+        vec.upload(list(vel) + [p])
+
+    def down(self, vec):
+        f, _ = vec.download()
+        return [a.reshape(self.shape) for a in f[:self.dim]], f[self.dim].reshape(self.pshape)
+
+
+CASES = [((2, 2, 2), 7), ((2, 2, 1), 4), ((1, 2, 2), 5), ((3, 2), 5), ((2, 3), 7), ((2, 2), 3)]
+
+
+@pytest.mark.parametrize('nel,N', CASES)
+def test_pressure_metrics_and_div_gradt(ctx, nel, N):
+    P = NsProblem(nel, N, seed=N)
+    sem, lay, B = P.gpu(ctx, 3)
+    d = P.dim
+    rx2 = sem.pressure_get('rx2')
+    for m in range(d * d):
+        assert relerr(rx2[m].reshape(P.pshape), P.ps['rx2'][m]) <= 1e-12
+    assert relerr(sem.pressure_get('bm2inv').reshape(P.pshape), 1.0 / P.ps['bm2']) <= 1e-12
+    vel = [P.rng.standard_normal(P.shape) for _ in range(d)]
+    p = P.pres()
+    P.up(B[0], vel, p)
+    sem.opdiv(B[0], B[1])
+    _, dv = P.down(B[1])
+    assert relerr(dv, ons.opdiv(vel, P.ps)) <= 1e-12
+    sem.opgradt(B[0], B[2])
+    gt, _ = P.down(B[2])
+    ref = ons.opgradt(p, P.ps)
+    for a, b in zip(gt, ref):
+        assert relerr(a, b) <= 1e-12
+    # transposition on the device: sum (D u) p = sum u (D^T p)
+    lhs = float(np.sum(dv * p))
+    rhs = float(sum(np.sum(a * v) for a, v in zip(gt, vel)))
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)
+    for o in (B, lay, sem):
+        o.close()
+
+
+@pytest.mark.parametrize('nel,N', [((2, 2, 2), 7), ((2, 2, 2), 4), ((3, 3), 5)])
+def test_consistent_poisson_operator_and_solve(ctx, nel, N):
+    P = NsProblem(nel, N, seed=20 + N)
+    sem, lay, B = P.gpu(ctx, 3)
+    zero = [0 * P.coords[0]] * P.dim
+    p = P.pres()
+    P.up(B[0], zero, p)
+    sem.cdabdtp(B[0], B[1])
+    _, Ep = P.down(B[1])
+    ref = ons.cdabdtp(p, P.ps, P.glo, P.mask, P.binv)
+    assert relerr(Ep, ref) <= 1e-12
+    # E x = E p: the solve gives back p up to the near-null component; compare with the oracle's iteration instead
+    for mean_free in (False, True):
+        xo, ito, dropo = ons.esolve(ref, P.ps, P.glo, P.mask, P.binv, tol=1e-11, maxit=3000, mean_free=mean_free)
+        P.up(B[1], zero, ref)
+        it, drop = sem.esolve(B[1], B[2], tol=1e-11, maxit=3000, mean_free=mean_free)
+        _, x = P.down(B[2])
+        assert abs(it - ito) <= 3 and drop <= 1e-11
+        # the constant is the (near-)null vector of E: its coefficient is not determined to the solver tolerance
+        assert relerr(x - x.mean(), xo - xo.mean()) <= 1e-8
+    for o in (B, lay, sem):
+        o.close()
+
+
+@pytest.mark.parametrize('nel,N,conv', [((2, 2, 2), 7, True), ((2, 2, 2), 4, True), ((3, 3), 5, True), ((2, 2), 7, False)])
+def test_ns_stepper_matches_oracle(ctx, nel, N, conv):
+    import nekstab_next_b200 as nb
+    P = NsProblem(nel, N, seed=40 + N)
+    sem, lay, B = P.gpu(ctx, 3)
+    nu, dt, nsteps = 0.05, 2e-3, 4
+    v0, p0 = P.vel(), P.pres()
+    info = {}
+    vo, po = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base if conv else None, v0, p0, nu, dt, nsteps,
+                          mean_free=False, info=info)
+    base = None
+    if conv:
+        sem.dealias_setup()
+        P.up(B[2], P.base, 0 * p0)
+        base = B[2]
+    op = nb.ns_stepper_operator(sem, lay, base, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False)
+    P.up(B[0], v0, p0)
+    op.matvec(B[0], B[1])
+    v, p = P.down(B[1])
+    scale = max(np.max(np.abs(a)) for a in vo)
+    for a, b in zip(v, vo):
+        assert np.max(np.abs(a - b)) <= 1e-9 * scale
+    # pressure up to the constant: on deformed elements E is regular with a tiny eigenvalue for the constant mode,
+    # so the mean of p drifts with the solver's rounding and is irrelevant to the velocity (D^T 1 ~ 0)
+    pm, pom = p - p.mean(), po - po.mean()
+    assert np.max(np.abs(pm - pom)) <= 1e-7 * np.max(np.abs(pom))
+    assert np.max(np.abs(ons.opdiv(v, P.ps))) <= 1e-9 * scale          # discretely incompressible
+    ih, ip = nb.ns_iterations(op)
+    assert abs(ih - info['helmholtz_iterations']) <= 3 * P.dim * nsteps
+    assert abs(ip - info['pressure_iterations']) <= 3 * nsteps
+    # a second application starts from a cold state again
+    op.matvec(B[0], B[1])
+    v2, p2 = P.down(B[1])
+    for a, b in zip(v2, v):
+        assert np.array_equal(a, b)
+    assert op.count() == 2
+    for o in (op, B, lay, sem):
+        o.close()
+
+
+def test_ns_stepper_arnoldi_matches_oracle(ctx):
+    """Arnoldi on the linearised Navier-Stokes propagator, device-resident (exponential_prop%matvec under
+    arnoldi_factorization): H against the oracle's Arnoldi on the oracle's propagator; the pressure rides in the
+    vector outside the inner product."""
+    import nekstab_next_b200 as nb
+    N, K, nsteps, nu, dt = 5, 4, 3, 0.05, 4e-3
+    P = NsProblem((3, 3), N, seed=7)
+    c = okr.Ctx(bm1s=P.geo['bm1'], in_dot=[True, True, False], time_in_dot=False)
+
+    def omatvec(q):
+        v, p = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base, [q.f[0], q.f[1]], q.f[2], nu, dt, nsteps,
+                            mean_free=False)
+        return okr.KVec(v + [p], q.time)
+
+    seed = okr.KVec(P.vel() + [0 * P.pres()], 0.0)
+    okr.k_normalize(c, seed)
+    Qo = [okr.k_zero_like(seed) for _ in range(K + 1)]
+    okr.k_copy(Qo[0], seed)
+    Ho = np.zeros((K + 1, K))
+    okr.arnoldi_factorization(c, omatvec, Qo, Ho, 1, K, K)
+
+    sem, lay, Q = P.gpu(ctx, K + 2)
+    sem.dealias_setup()
+    P.up(Q[K + 1], P.base, 0 * P.pres())
+    op = nb.ns_stepper_operator(sem, lay, Q[K + 1], nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False)
+    Q[0].upload([a.ravel() for a in seed.f])
+    H = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(Q, H, 1, K, K, op)
+    assert np.max(np.abs(H - Ho)) <= 1e-8 * np.max(np.abs(Ho))
+    G = Q.gram(K + 1)
+    assert np.max(np.abs(G - np.eye(K + 1))) < 1e-10
+    for o in (op, Q, lay, sem):
+        o.close()
+
+
+def test_ns_error_paths(ctx):
+    import nekstab_next_b200 as nb
+    P = NsProblem((2, 2), 5)
+    z = None
+    sem = nb.Sem(ctx, P.N, P.coords[0], P.coords[1], z, mask=P.mask, glo_num=P.glo)
+    lay_bad = nb.Layout(ctx, [P.npts] * 2, [True] * 2)
+    B = nb.Basis(lay_bad, 2)
+    with pytest.raises(nb.NsbError):          # pressure mesh not set up
+        sem.opdiv(B[0], B[1])
+    sem.pressure_setup()
+    with pytest.raises(nb.NsbError):          # layout without a pressure field
+        sem.opdiv(B[0], B[1])
+    with pytest.raises(nb.NsbError):
+        nb.ns_stepper_operator(sem, lay_bad, None, 0.1, 1e-3, 2)
+    lay = nb.Layout(ctx, [P.npts] * 2 + [P.n2], [True, True, False])
+    with pytest.raises(nb.NsbError):          # bad parameter
+        nb.ns_stepper_operator(sem, lay, None, -1.0, 1e-3, 2)
+    B2 = nb.Basis(lay, 2)
+    with pytest.raises(nb.NsbError):          # base flow without the dealiasing set-up
+        nb.ns_stepper_operator(sem, lay, B2[0], 0.1, 1e-3, 2)
+    with pytest.raises(nb.NsbError):          # right-hand side and solution alias
+        sem.esolve(B2[0], B2[0])
+    for o in (B2, B, lay, lay_bad, sem):
+        o.close()
