@@ -155,8 +155,34 @@ def main():
     Tref = _oracle_scalar_steps(*P.coords, P.glo, P.mask, P.geo, vel, T0, 0.05, 4e-3, 3, N=N)
     errs['stepper'] = rel(Q[1].download()[0][0], Tref[sl].ravel())
     step.close()
+    # the pressure-coupled step: D^T p -> interface exchange -> D inside every pressure iteration, CG scalars all-reduced
+    from oracle import ns as ons
+    ps = ons.pressure_setup(N, P.geo)
+    dl = osem.dealias_setup(N, 3 * (N + 1) // 2, P.geo['rst'])
+    n2loc = sem.pressure_setup()
+    n2e = ps['bm2'][0].size
+    assert n2loc == (e1 - e0) * n2e
+    layn = nb.Layout(ctx, [npts] * 3 + [n2loc], [True] * 3 + [False])
+    Bn = nb.Basis(layn, 3)
+    v0 = [P.random_field() for _ in range(3)]
+    p0 = P.rng.standard_normal(ps['bm2'].shape)
+    vo, po = ons.ns_steps(P.glo, P.mask, P.geo, N, ps, dl, vel, v0, p0, 0.05, 4e-3, 3, mean_free=False)
+    Bn[2].upload([v[sl] for v in vel] + [0 * p0[sl]])
+    nsop = nb.ns_stepper_operator(sem, layn, Bn[2], 0.05, 4e-3, 3, tol_v=1e-13, tol_p=1e-13, mean_free=False)
+    Bn[0].upload([v[sl] for v in v0] + [p0[sl]])
+    nsop.matvec(Bn[0], Bn[1])
+    fo = Bn[1].download()[0]
+    scale = max(np.max(np.abs(a)) for a in vo)
+    errs['ns_stepper'] = max(float(np.max(np.abs(fo[b] - vo[b][sl].ravel()))) / scale for b in range(3))
+    pm = po - po.mean()
+    pall_ = [None] * world
+    dist.all_gather_object(pall_, fo[3])
+    pg = np.concatenate(pall_)
+    errs['ns_pressure'] = float(np.max(np.abs((pg - pg.mean()) - pm.ravel())) / np.max(np.abs(pm)))
+    nsop.close()
+    Bn.close()
     Bv.close()
-    tol = dict(binvm1=1e-12, vmult=0, dssum=1e-13, ax=1e-12, dot=1e-12, arnoldi_H=1e-10, arnoldi_Q=1e-9,
+    tol = dict(ns_stepper=1e-9, ns_pressure=1e-6, binvm1=1e-12, vmult=0, dssum=1e-13, ax=1e-12, dot=1e-12, arnoldi_H=1e-10, arnoldi_Q=1e-9,
                orth=1e-10, H_replicated=0, hmholtz=1e-8, stepper=1e-9, H_replay=0, dgks_H=1e-10, dgks_orth=1e-10,
                dgks_replicated=0, two_meshes=1e-13)
     bad = {k: v for k, v in errs.items() if not (v <= tol[k])}
