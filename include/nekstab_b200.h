@@ -368,7 +368,14 @@ int nsb_op_create_stepper_adjoint(nsb_sem_t sem, nsb_layout_t layout, int nfield
  *                       sqrt(r.z) <= tol sqrt(r0.z0); mean_free != 0 removes the mean of the right-hand side and of
  *                       every preconditioned residual (Nek's ortho for all-Dirichlet velocity; exact on affine
  *                       elements, where E 1 = 0 -- on deformed elements E is regular and mean_free = 0 solves it as
- *                       it stands).  CG scalars stay on the device; the host polls a flag every 8 iterations. */
+ *                       it stands).  CG scalars stay on the device; the host polls a flag every 8 iterations.
+ *                       precond 0: 1 / bm2 (uzprec without the Schwarz part; O(1000) iterations on large meshes).
+ *                       precond 1: two levels -- element-wise fast-diagonalisation solves (the local solves of Nek's
+ *                       Schwarz preconditioner, fast.f / hsmg.f, without overlap: every element replaced by the box
+ *                       with its mean edge lengths) plus a coarse correction on one constant per element
+ *                       (E_c = R E R^T, sparse, Jacobi-CG on the device); iteration count independent of the number
+ *                       of elements (about 60 at tol 1e-8).  On a multi-rank context the coarse level couples the
+ *                       elements of a rank only. */
 int nsb_pressure_matrices(int N, double *z2, double *w2, double *I12, double *D12);
 int nsb_sem_pressure_setup(nsb_sem_t sem);
 int64_t nsb_sem_npres(nsb_sem_t sem);
@@ -377,7 +384,7 @@ int nsb_sem_opdiv(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int
 int nsb_sem_opgradt(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_sem_cdabdtp(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_sem_esolve(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, double tol, int maxit,
-                   int mean_free, int *iters, double *res);
+                   int mean_free, int precond, int *iters, double *res);
 /* exponential_prop%matvec for the linearised incompressible Navier-Stokes equations, device-resident:
  *     dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v,   div v = 0,   v = 0 where the mesh mask is 0.
  * The input vector's velocity and pressure start nsteps BDF/EXT steps (order ramp 1, 2, 3 -- the reference restarts
@@ -388,7 +395,8 @@ int nsb_sem_esolve(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, in
  * and pressure; other fields and %time are carried through.  nsb_op_ns_iterations: Helmholtz / pressure iterations
  * spent so far. */
 int nsb_op_create_ns_stepper(nsb_sem_t sem, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu, double dt,
-                             int nsteps, double tol_v, double tol_p, int maxit, int mean_free, nsb_op_t *op);
+                             int nsteps, double tol_v, double tol_p, int maxit, int mean_free, int precond,
+                             nsb_op_t *op);
 int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);

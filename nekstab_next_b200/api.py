@@ -444,11 +444,13 @@ class Sem:
         """cdabdtp: pressure field of vout <- D B^-1 D^T (pressure field of vin)."""
         check(self.lib.nsb_sem_cdabdtp(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col))
 
-    def esolve(self, rhs: nek_dvector, x: nek_dvector, tol: float = 1e-10, maxit: int = 2000, mean_free: bool = True):
-        """E x = rhs on the pressure fields (CG, 1 / bm2 preconditioner); returns (iterations, residual drop)."""
+    def esolve(self, rhs: nek_dvector, x: nek_dvector, tol: float = 1e-10, maxit: int = 2000, mean_free: bool = True,
+               precond: int = 1):
+        """E x = rhs on the pressure fields by preconditioned CG (precond 0: 1 / bm2; 1: element-wise fast
+        diagonalisation + coarse level); returns (iterations, residual drop)."""
         it, res = C.c_int(), C.c_double()
         check(self.lib.nsb_sem_esolve(self.h, rhs.basis.h, rhs.col, x.basis.h, x.col, float(tol), int(maxit),
-                                      int(bool(mean_free)), C.byref(it), C.byref(res)))
+                                      int(bool(mean_free)), int(precond), C.byref(it), C.byref(res)))
         return it.value, res.value
 
     # -- time-stepper pieces around ax (SURVEY.md section 8 f-3; [UPSTREAM-RECALL] convect.f, perturb.f) --
@@ -543,14 +545,15 @@ def stepper_operator(sem: Sem, layout: Layout, nfields: int, slot: int, kappa: f
 
 def ns_stepper_operator(sem: Sem, layout: Layout, base: nek_dvector | None, nu: float, dt: float, nsteps: int,
                         tol_v: float = 1e-12, tol_p: float = 1e-12, maxit: int = 4000,
-                        mean_free: bool = True) -> LinearOperator:
+                        mean_free: bool = True, precond: int = 1) -> LinearOperator:
     """exponential_prop%matvec for the linearised incompressible Navier-Stokes equations on the device
     (core/linear_operators.f90:225-274): nsteps pressure-coupled BDF/EXT steps of the P_N - P_N-2 splitting from a
     cold start.  Layout: fields 0..dim-1 velocity, field dim pressure; base = the base flow (None: Stokes)."""
     h = C.c_void_p()
     check(sem.lib.nsb_op_create_ns_stepper(sem.h, layout.h, base.basis.h if base is not None else None,
                                            base.col if base is not None else 0, float(nu), float(dt), int(nsteps),
-                                           float(tol_v), float(tol_p), int(maxit), int(bool(mean_free)), C.byref(h)))
+                                           float(tol_v), float(tol_p), int(maxit), int(bool(mean_free)), int(precond),
+                                           C.byref(h)))
     return LinearOperator(sem.lib, h, keep=(sem, layout))
 
 

@@ -92,6 +92,7 @@ struct nsb_context_s {
   bool pipeline_upload = true;   // NSB_PIPELINE_UPLOAD=0: plain upload, then the usual first sweep
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
   bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
+  bool ns_no_coarse = false;   // NSB_NS_NO_COARSE=1: pressure preconditioner without the coarse level (A/B numbers)
   bool fold_norm = true;       // NSB_FOLD_NORM=0: explicit norm reduction in the third sweep + normalize_kernel
   int fused_loader = 3;        // NSB_FUSED_LOADER: 1 cp.async, 3 TMA 2-D tensor loads (default)
   int fused_rc = 0;            // NSB_FUSED_RC: force rows per block (tuning)
@@ -218,6 +219,14 @@ struct nsb_sem_s {
   double *bm2inv_d = nullptr;                 // [n2] 1 / (w3m2 jacm2)
   double *ns_work_d = nullptr;                // pressure CG: r, p, w [n2 each] + dim velocity-shaped fields
   double *ns_state_d = nullptr;               // device scalars of the pressure CG
+  // two-level preconditioner of the pressure operator (set up by the first solve that asks for it)
+  double *fdm_S_d = nullptr, *fdm_lam_d = nullptr;   // [lx2][lx2] 1-D generalised eigenvectors, [lx2] eigenvalues
+  double *fdm_c_d = nullptr;                  // [nel][3] direction weights of the element-wise solves
+  int *cc_rowptr_d = nullptr, *cc_col_d = nullptr;   // coarse operator (one constant per element), CSR
+  double *cc_val_d = nullptr, *cc_dinv_d = nullptr, *cc_vec_d = nullptr, *cc_partial_d = nullptr, *cc_state_d = nullptr;
+  int64_t cc_nnz = 0;
+  int cc_maxit = 400;                         // most coarse CG iterations enqueued per application
+  int cc_launch = 400;                        // currently enqueued (stops early on the device; adapted at every poll)
 };
 
 struct nsb_op_s {
@@ -241,7 +250,7 @@ struct nsb_op_s {
   bool adjoint = false;          // kind 3: apply the discrete BM1-adjoint of the stepper (rmatvec)
   // kind 4 (nsb_ns.cu): pressure-coupled perturbation step (linearised Navier-Stokes, P_N - P_N-2)
   double nu = 0, tol_p = 0;
-  int mean_free = 0;
+  int mean_free = 0, precond = 0;
   bool has_base = false;         // base flow in column 8 of tmp, its contravariant field in convection slot 0
   int64_t pres_iters = 0;        // pressure iterations spent so far
 };

@@ -223,7 +223,7 @@ map12_kernel(NsDims d, const double *__restrict__ in, const double *__restrict__
 
 // ---- pressure CG: device state ------------------------------------------------------------------------
 struct PcgP {
-  double rtz1, rtz2, r0, rn, mean_z, sums[4];   // sums: 0 (w,p) | 1 sum r minv r | 2 sum minv r | 3 sum r
+  double rtz1, rtz2, r0, rn, mean_z, sums[4];   // sums: 0 (w,p) | 1 sum r z | 2 sum z | 3 sum r   (z = M^-1 r)
   double ntot;                                  // pressure points over all ranks
   int it, done, mean_free, pad;
 };
@@ -239,18 +239,39 @@ __global__ void reduce_rows_kernel(const double *__restrict__ partial, int rows,
   if (lane == 0) out[c] = s;
 }
 
-// r = rhs - mean(rhs) (mean_free) ; x = 0 ; p = 0 ; partial sums of r minv r, minv r, r
+// r = rhs - mean(rhs) (mean_free) ; x = 0 ; p = 0
 __global__ void __launch_bounds__(NT_NS)
-pcg_init_kernel(const double *__restrict__ rhs, const double *__restrict__ minv, int64_t n2, double mean_rhs,
-                const double *__restrict__ sum_rhs, double ntot, int mean_free, double *__restrict__ r,
-                double *__restrict__ x, double *__restrict__ p, double *__restrict__ partial) {
-  const double mr = mean_free ? (sum_rhs ? *sum_rhs / ntot : mean_rhs) : 0.0;
-  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+pcg_init_kernel(const double *__restrict__ rhs, int64_t n2, const double *__restrict__ sum_rhs, double ntot,
+                int mean_free, double *__restrict__ r, double *__restrict__ x, double *__restrict__ p) {
+  const double mr = (mean_free && sum_rhs) ? *sum_rhs / ntot : 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
-    const double ri = rhs[i] - mr, zi = minv[i] * ri;
-    r[i] = ri;
+    r[i] = rhs[i] - mr;
     x[i] = 0.0;
     p[i] = 0.0;
+  }
+}
+
+__global__ void sum_kernel(const double *__restrict__ a, int64_t n, double *__restrict__ partial) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i];
+  s = block_reduce_sum<NT_NS>(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Last stage of either preconditioner: z = minv r (minv given: uzprec's diagonal) or z += zc[element] (the coarse
+// correction on top of the element-wise solves; zc may be null), and the partial sums (r, z), sum z, sum r.
+__global__ void __launch_bounds__(NT_NS)
+precond_sums_kernel(const int *__restrict__ done, const double *__restrict__ r, const double *__restrict__ minv,
+                    const double *__restrict__ zc, int n2e, double *__restrict__ z, int64_t n2,
+                    double *__restrict__ partial) {
+  if (*done) return;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i];
+    double zi;
+    if (minv) zi = minv[i] * ri;
+    else zi = z[i] + (zc ? zc[i / n2e] : 0.0);
+    z[i] = zi;
     s1 = fma(ri, zi, s1);
     s2 += zi;
     s3 += ri;
@@ -265,14 +286,7 @@ pcg_init_kernel(const double *__restrict__ rhs, const double *__restrict__ minv,
   }
 }
 
-__global__ void sum_kernel(const double *__restrict__ a, int64_t n, double *__restrict__ partial) {
-  double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i];
-  s = block_reduce_sum<NT_NS>(s);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-
-// after a residual reduction: rtz2 <- rtz1 ; rtz1 <- (r, z) with z = minv r - mean(minv r) ; stopping test
+// after a residual reduction: rtz2 <- rtz1 ; rtz1 <- (r, z - mean z) ; stopping test
 __global__ void pcg_after_r_kernel(PcgP *st, double tol, int first) {
   if (st->done) return;
   const double mz = st->mean_free ? st->sums[2] / st->ntot : 0.0;
@@ -294,13 +308,13 @@ __global__ void pcg_after_r_kernel(PcgP *st, double tol, int first) {
   if (st->rn <= tol * st->r0) st->done = 1;
 }
 
-// p = (minv r - mean_z) + beta p ; it += 1
+// p = (z - mean_z) + beta p
 __global__ void __launch_bounds__(NT_NS)
-pcg_p_kernel(PcgP *st, const double *__restrict__ r, const double *__restrict__ minv, double *__restrict__ p, int64_t n2) {
+pcg_p_kernel(const PcgP *st, const double *__restrict__ z, double *__restrict__ p, int64_t n2) {
   if (st->done) return;
   const double beta = st->it == 0 ? 0.0 : st->rtz1 / st->rtz2, mz = st->mean_z;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = (minv[i] * r[i] - mz) + beta * p[i];
+    p[i] = (z[i] - mz) + beta * p[i];
 }
 
 // rho = (w, p): not positive -> stop (before the update, like Nek's cggo / uzawa) ; else it += 1
@@ -310,29 +324,257 @@ __global__ void pcg_after_w_kernel(PcgP *st) {
   if (!(st->sums[0] > 0.0)) st->done = 1;
 }
 
-// x += alpha p ; r -= alpha w ; partial sums of r minv r, minv r, r
+// x += alpha p ; r -= alpha w
 __global__ void __launch_bounds__(NT_NS)
-pcg_xr_kernel(const PcgP *st, const double *__restrict__ p, const double *__restrict__ w, const double *__restrict__ minv,
-              double *__restrict__ x, double *__restrict__ r, int64_t n2, double *__restrict__ partial) {
+pcg_xr_kernel(const PcgP *st, const double *__restrict__ p, const double *__restrict__ w, double *__restrict__ x,
+              double *__restrict__ r, int64_t n2) {
   if (st->done) return;
   const double alpha = st->rtz1 / st->sums[0];
-  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
     x[i] = fma(alpha, p[i], x[i]);
-    const double ri = fma(-alpha, w[i], r[i]), zi = minv[i] * ri;
-    r[i] = ri;
-    s1 = fma(ri, zi, s1);
-    s2 += zi;
-    s3 += ri;
+    r[i] = fma(-alpha, w[i], r[i]);
   }
-  s1 = block_reduce_sum<NT_NS>(s1);
-  s2 = block_reduce_sum<NT_NS>(s2);
-  s3 = block_reduce_sum<NT_NS>(s3);
+}
+
+// ---- two-level preconditioner for E ------------------------------------------------------------------------
+// Fine level: element-wise fast diagonalisation -- the local solves of Nek's Schwarz preconditioner [UPSTREAM-RECALL
+// fast.f / hsmg.f] without overlap.  Every element is replaced by the box with its mean edge lengths, where
+//   E_e = sum_a c_a (E^ in direction a) x (M^ in the others),  E^ = D^ b^-1 D^T,  M^ = I^ b^-1 I^T   (1-D, lx2 x lx2),
+//   E^ S = M^ S Lambda, S^T M^ S = 1   =>   E_e^-1 = (S x S x S) diag(1 / sum_a c_a lambda_ia) (S x S x S)^T.
+// Coarse level: one constant per element, E_c = R E R^T (sparse, elements sharing a velocity node), Jacobi-CG on the
+// device with its scalars in device memory (no host involvement).
+
+// c[e][a] = (2 / L_a) prod_{o != a} (L_o / 2),  L_a = 2 / mean_e(|J grad r_a| / J)
+__global__ void __launch_bounds__(NT_NS)
+elem_scales_kernel(NsDims d, const double *__restrict__ rst, const double *__restrict__ jac, int64_t npts,
+                   double *__restrict__ c) {
+  const int64_t e = blockIdx.x;
+  double L[3] = {2.0, 2.0, 2.0};
+  for (int a = 0; a < d.dim; ++a) {
+    double s = 0.0;
+    for (int t = threadIdx.x; t < d.n1e; t += blockDim.x) {
+      const int64_t p = e * d.n1e + t;
+      double g = 0.0;
+      for (int b = 0; b < d.dim; ++b) {
+        const double v = rst[(int64_t)(a * d.dim + b) * npts + p];
+        g = fma(v, v, g);
+      }
+      s += sqrt(g) / jac[p];
+    }
+    s = block_reduce_sum<NT_NS>(s);
+    __shared__ double sh;
+    if (threadIdx.x == 0) sh = s;
+    __syncthreads();
+    L[a] = 2.0 / (sh / d.n1e);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (int a = 0; a < d.dim; ++a) {
+      double v = 2.0 / L[a];
+      for (int o = 0; o < d.dim; ++o)
+        if (o != a) v *= 0.5 * L[o];
+      c[e * 3 + a] = v;
+    }
+}
+
+// z_e = E_e^-1 r_e ; rc[e] = sum of r_e (restriction to the coarse space)
+__global__ void __launch_bounds__(NT_NS)
+fdm_kernel(NsDims d, const int *__restrict__ done, const double *__restrict__ r, const double *__restrict__ Sg,
+           const double *__restrict__ lamg, const double *__restrict__ c, double *__restrict__ z,
+           double *__restrict__ rc) {
+  if (*done) return;
+  extern __shared__ double sm[];
+  const int l2 = d.l2, dim = d.dim, lz2 = dim == 3 ? l2 : 1;
+  double *Sm = sm, *lam = Sm + l2 * l2, *b0 = lam + l2, *b1 = b0 + d.n2e;
+  for (int t = threadIdx.x; t < l2 * l2; t += blockDim.x) Sm[t] = Sg[t];
+  if (threadIdx.x < l2) lam[threadIdx.x] = lamg[threadIdx.x];
+  const int64_t e = blockIdx.x;
+  double s = 0.0;
+  for (int t = threadIdx.x; t < d.n2e; t += blockDim.x) {
+    const double v = r[e * d.n2e + t];
+    b0[t] = v;
+    s += v;
+  }
+  s = block_reduce_sum<NT_NS>(s);   // contains the barriers that publish Sm, lam, b0
+  if (threadIdx.x == 0 && rc) rc[e] = s;
+  __syncthreads();
+  stage<true, false>(b1, b0, Sm, lz2 * l2, l2, l2, 1);
+  __syncthreads();
+  stage<true, false>(b0, b1, Sm, lz2, l2, l2, l2);
+  __syncthreads();
+  double *cur = b0, *oth = b1;
+  if (dim == 3) {
+    stage<true, false>(b1, b0, Sm, 1, l2, l2, l2 * l2);
+    __syncthreads();
+    cur = b1;
+    oth = b0;
+  }
+  const double cr = c[e * 3 + 0], cs = c[e * 3 + 1], ct = dim == 3 ? c[e * 3 + 2] : 0.0;
+  for (int t = threadIdx.x; t < d.n2e; t += blockDim.x) {
+    const int i = t % l2, j = (t / l2) % l2, k = t / (l2 * l2);
+    cur[t] /= cr * lam[i] + cs * lam[j] + (dim == 3 ? ct * lam[k] : 0.0);
+  }
+  __syncthreads();
+  if (dim == 3) {
+    stage<false, false>(oth, cur, Sm, 1, l2, l2, l2 * l2);
+    __syncthreads();
+    double *t_ = cur;
+    cur = oth;
+    oth = t_;
+  }
+  stage<false, false>(oth, cur, Sm, lz2, l2, l2, l2);
+  __syncthreads();
+  stage<false, false>(cur, oth, Sm, lz2 * l2, l2, l2, 1);
+  __syncthreads();
+  for (int t = threadIdx.x; t < d.n2e; t += blockDim.x) z[e * d.n2e + t] = cur[t];
+}
+
+// Coarse Jacobi-CG in the mean-free subspace:  P E_c P x = P rc,  P = 1 - 11^T / n  (E_c 1 = 0 on affine elements and
+// nearly so on deformed ones: the projection keeps the solve -- and with it the preconditioner -- a fixed linear,
+// symmetric operator).  z = P dinv r is never stored: (r, z) = sum r dinv r - mean(dinv r) sum r.
+// State: rtz[2] (double-buffered across iterations), rtz0, done.
+struct CcState {
+  double rtz[2], rtz0, mz[2];
+  int done, it;
+};
+
+// every CTA sums the [n][3] partials in the same fixed order: identical scalars everywhere, no extra launch
+__device__ __forceinline__ void sum_partials3(const double *__restrict__ partial, int n, double (&out)[3]) {
+  __shared__ double red[3][NT_NS / 32];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s0 += partial[3 * i];
+    s1 += partial[3 * i + 1];
+    s2 += partial[3 * i + 2];
+  }
+  s0 = warp_reduce_sum(s0);
+  s1 = warp_reduce_sum(s1);
+  s2 = warp_reduce_sum(s2);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s0;
+    red[1][threadIdx.x >> 5] = s1;
+    red[2][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  out[0] = out[1] = out[2] = 0.0;
+  for (int i = 0; i < NT_NS / 32; ++i) {
+    out[0] += red[0][i];
+    out[1] += red[1][i];
+    out[2] += red[2][i];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void store_partials3(double *__restrict__ partial, double a, double b, double c) {
+  a = block_reduce_sum<NT_NS>(a);
+  b = block_reduce_sum<NT_NS>(b);
+  c = block_reduce_sum<NT_NS>(c);
   if (threadIdx.x == 0) {
-    partial[blockIdx.x * 3 + 0] = s1;
-    partial[blockIdx.x * 3 + 1] = s2;
-    partial[blockIdx.x * 3 + 2] = s3;
+    partial[3 * blockIdx.x] = a;
+    partial[3 * blockIdx.x + 1] = b;
+    partial[3 * blockIdx.x + 2] = c;
   }
+}
+
+__global__ void __launch_bounds__(NT_NS)
+cc_sum_kernel(const int *__restrict__ odone, const double *__restrict__ rc, int n, double *__restrict__ partial) {
+  if (*odone) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  store_partials3(partial, i < n ? rc[i] : 0.0, 0.0, 0.0);
+}
+
+// r = rc - mean ; x = 0 ; p = 0 ; partials (r dinv r, dinv r, r)
+__global__ void __launch_bounds__(NT_NS)
+cc_init_kernel(const int *__restrict__ odone, const double *__restrict__ rc, int n, const double *__restrict__ partial_in,
+               const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
+               double *__restrict__ partial_out, CcState *st) {
+  if (*odone) return;
+  double s[3];
+  sum_partials3(partial_in, gridDim.x, s);
+  const double mean = s[0] / n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ri = 0.0, zi = 0.0;
+  if (i < n) {
+    ri = rc[i] - mean;
+    zi = dinv[i] * ri;
+    r[i] = ri;
+    x[i] = 0.0;
+    p[i] = 0.0;
+  }
+  store_partials3(partial_out, ri * zi, zi, ri);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->done = 0;
+    st->it = 0;
+    st->rtz0 = -1.0;
+  }
+}
+
+// (first the direction of this iteration)  p = (dinv r - mz) + beta p ;  w = E_c p ; partial (p, w).
+// The direction update lives here, not at the end of the previous iteration, so that p is complete before any row of
+// the product reads it: a separate kernel computes the product.
+__global__ void __launch_bounds__(NT_NS)
+cc_dir_kernel(const int *__restrict__ odone, CcState *st, int it, const double *__restrict__ r,
+              const double *__restrict__ dinv, int n, double *__restrict__ p, const double *__restrict__ partial_rz,
+              double tol) {
+  if (*odone || st->done) return;
+  double s[3];
+  sum_partials3(partial_rz, gridDim.x, s);
+  const double mz = s[1] / n;
+  const double rtzn = s[0] - mz * s[2];
+  const double rtz = it == 0 ? 1.0 : st->rtz[it & 1];
+  const double rtz0 = it == 0 ? rtzn : st->rtz0;
+  const bool stop = !(rtzn > tol * tol * rtz0) || !(rtz > 0.0);
+  const double beta = it == 0 ? 0.0 : rtzn / rtz;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !stop) p[i] = fma(beta, p[i], dinv[i] * r[i] - mz);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->rtz[(it + 1) & 1] = rtzn;
+    if (it == 0) st->rtz0 = rtzn;
+    st->it = it;
+    if (stop) st->done = 1;     // read by the NEXT kernels only (this kernel read it at its first instruction)
+  }
+}
+
+__global__ void __launch_bounds__(NT_NS)
+cc_spmv_kernel(const int *__restrict__ odone, const CcState *st, const int *__restrict__ rowptr,
+               const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ p, int n,
+               double *__restrict__ w, double *__restrict__ partial_pw) {
+  if (*odone || st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double pw = 0.0;
+  if (i < n) {
+    double sv = 0.0;
+    for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) sv = fma(val[q], p[col[q]], sv);
+    w[i] = sv;
+    pw = sv * p[i];
+  }
+  store_partials3(partial_pw, pw, 0.0, 0.0);
+}
+
+// alpha = rtz / (p, w) ; x += alpha p ; r -= alpha w ; partials (r dinv r, dinv r, r)
+__global__ void __launch_bounds__(NT_NS)
+cc_update_kernel(const int *__restrict__ odone, const CcState *st, int it, const double *__restrict__ p,
+                 const double *__restrict__ w, const double *__restrict__ dinv, int n, double *__restrict__ x,
+                 double *__restrict__ r, const double *__restrict__ partial_pw, double *__restrict__ partial_rz) {
+  if (*odone || st->done) return;
+  double s[3];
+  sum_partials3(partial_pw, gridDim.x, s);
+  const double pw = s[0], rtz = st->rtz[(it + 1) & 1];
+  if (!(pw > 0.0)) {                           // nothing (left) to solve: the same decision in every CTA
+    store_partials3(partial_rz, 0.0, 0.0, 0.0);
+    return;
+  }
+  const double alpha = rtz / pw;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ri = 0.0, zi = 0.0;
+  if (i < n) {
+    x[i] = fma(alpha, p[i], x[i]);
+    ri = fma(-alpha, w[i], r[i]);
+    r[i] = ri;
+    zi = dinv[i] * ri;
+  }
+  store_partials3(partial_rz, ri * zi, zi, ri);
 }
 
 // out = a + c * b on n entries (pressure update p* + dp, extrapolation 2 p - plag)
@@ -384,8 +626,8 @@ int launch_binv_gradt(nsb_sem_t S, const double *p, double *out, int64_t fs, con
   return launch_gs_ext(S, out, S->dim, fs, 1, uin ? uin : out, uin ? alpha : 0.0, beta, S->bmask_d);
 }
 
-// velocity-shaped scratch of the mesh: dim fields of npts after the three pressure work vectors
-double *ns_vel_scratch(nsb_sem_t S) { return S->ns_work_d + 3 * ((S->n2 + 31) & ~(int64_t)31); }
+// velocity-shaped scratch of the mesh: dim fields of npts after the four pressure work vectors (r, p, w, z)
+double *ns_vel_scratch(nsb_sem_t S) { return S->ns_work_d + 4 * ((S->n2 + 31) & ~(int64_t)31); }
 
 int pressure_ptr(nsb_sem_t S, nsb_basis_t B, int col, double **out, const char *who) {
   NSB_REQUIRE(S && B, "%s: NULL argument", who);
@@ -420,19 +662,254 @@ int velocity_ptr(nsb_sem_t S, nsb_basis_t B, int col, double **out, int64_t *fs,
   return NSB_OK;
 }
 
-// E dp = rhs on device arrays; x receives dp.  Host involvement: one 4-byte poll every 8 iterations.
-int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, int mean_free, int *iters, double *res) {
+size_t fdm_smem(nsb_sem_t S);
+
+// symmetric-definite generalised eigenproblem A s = lambda B s, n <= 16, by Cholesky + cyclic Jacobi:
+// S[I * n + m] = component I of eigenvector m, S^T B S = 1.
+int sym_gen_eig(int n, const std::vector<double> &A, const std::vector<double> &B, std::vector<double> &S,
+                std::vector<double> &lam) {
+  std::vector<double> L(n * n, 0.0), C(n * n, 0.0), Y(n * n, 0.0), T(n * n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = B[i * n + j];
+      for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
+      if (i == j) {
+        if (!(s > 0.0)) return NSB_EINVAL;
+        L[i * n + i] = std::sqrt(s);
+      } else {
+        L[i * n + j] = s / L[j * n + j];
+      }
+    }
+  // T = L^-1 A ; C = T L^-T
+  for (int c = 0; c < n; ++c)
+    for (int i = 0; i < n; ++i) {
+      double s = A[i * n + c];
+      for (int k = 0; k < i; ++k) s -= L[i * n + k] * T[k * n + c];
+      T[i * n + c] = s / L[i * n + i];
+    }
+  for (int r = 0; r < n; ++r)
+    for (int i = 0; i < n; ++i) {
+      double s = T[r * n + i];
+      for (int k = 0; k < i; ++k) s -= L[i * n + k] * C[r * n + k];
+      C[r * n + i] = s / L[i * n + i];
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) C[i * n + j] = C[j * n + i] = 0.5 * (C[i * n + j] + C[j * n + i]);
+  for (int i = 0; i < n; ++i) Y[i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dia = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i == j ? dia : off) += C[i * n + j] * C[i * n + j];
+    if (off <= 1e-30 * dia) break;
+    for (int pq = 0; pq < n; ++pq)
+      for (int q = pq + 1; q < n; ++q) {
+        const int p_ = pq;
+        const double apq = C[p_ * n + q];
+        if (apq == 0.0) continue;
+        const double th = (C[q * n + q] - C[p_ * n + p_]) / (2.0 * apq);
+        const double t = (th >= 0.0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < n; ++k) {
+          const double ckp = C[k * n + p_], ckq = C[k * n + q];
+          C[k * n + p_] = cs * ckp - sn * ckq;
+          C[k * n + q] = sn * ckp + cs * ckq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double cpk = C[p_ * n + k], cqk = C[q * n + k];
+          C[p_ * n + k] = cs * cpk - sn * cqk;
+          C[q * n + k] = sn * cpk + cs * cqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double ykp = Y[k * n + p_], ykq = Y[k * n + q];
+          Y[k * n + p_] = cs * ykp - sn * ykq;
+          Y[k * n + q] = sn * ykp + cs * ykq;
+        }
+      }
+  }
+  lam.resize(n);
+  S.assign(n * n, 0.0);
+  for (int m = 0; m < n; ++m) lam[m] = C[m * n + m];
+  // S = L^-T Y
+  for (int m = 0; m < n; ++m)
+    for (int i = n - 1; i >= 0; --i) {
+      double s = Y[i * n + m];
+      for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * S[k * n + m];
+      S[i * n + m] = s / L[i * n + i];
+    }
+  return NSB_OK;
+}
+
+// One-time set-up of the two-level preconditioner (first solve that asks for it).
+int fdm_setup(nsb_sem_t S) {
+  if (S->fdm_S_d) return NSB_OK;
+  nsb_context_t ctx = S->ctx;
+  cudaStream_t st = ctx->stream;
+  const int l1 = S->lx, l2 = S->lx2, dim = S->dim;
+  const NsDims d = ns_dims(S);
+  // 1-D operators on the reference element
+  std::vector<double> z2(l2), w2(l2), I12(l2 * l1), D12(l2 * l1);
+  NSB_CHECK(nsb_pressure_matrices(S->N, z2.data(), w2.data(), I12.data(), D12.data()));
+  std::vector<double> b(S->w_h);
+  NSB_REQUIRE((int)b.size() == l1, "fdm_setup: GLL weights missing");
+  b[0] *= 2.0;
+  b[l1 - 1] *= 2.0;
+  std::vector<double> Eh(l2 * l2, 0.0), Mh(l2 * l2, 0.0), Sm, lam;
+  for (int I = 0; I < l2; ++I)
+    for (int J = 0; J < l2; ++J) {
+      double se = 0.0, smm = 0.0;
+      for (int i = 0; i < l1; ++i) {
+        se += w2[I] * D12[I * l1 + i] * w2[J] * D12[J * l1 + i] / b[i];
+        smm += w2[I] * I12[I * l1 + i] * w2[J] * I12[J * l1 + i] / b[i];
+      }
+      Eh[I * l2 + J] = se;
+      Mh[I * l2 + J] = smm;
+    }
+  NSB_REQUIRE(sym_gen_eig(l2, Eh, Mh, Sm, lam) == NSB_OK, "fdm_setup: the 1-D mass operator is not positive definite");
+  const int64_t nelp = std::max<int64_t>(S->nel, 1);
+  NSB_CUDA(cudaMalloc(&S->fdm_S_d, sizeof(double) * l2 * l2));
+  NSB_CUDA(cudaMalloc(&S->fdm_lam_d, sizeof(double) * l2));
+  NSB_CUDA(cudaMalloc(&S->fdm_c_d, sizeof(double) * 3 * nelp));
+  NSB_CUDA(cudaMemcpyAsync(S->fdm_S_d, Sm.data(), sizeof(double) * l2 * l2, cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(S->fdm_lam_d, lam.data(), sizeof(double) * l2, cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaFuncSetAttribute(fdm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fdm_smem(S)));
+  if (S->nel > 0) {
+    elem_scales_kernel<<<(unsigned)S->nel, NT_NS, 0, st>>>(d, S->rst_d, S->jac_d, S->npts, S->fdm_c_d);
+    ctx->launches++;
+  }
+  NSB_CUDA(cudaGetLastError());
+  // coarse operator E_c[f, e] = sum over shared velocity nodes n of bmask_n g_f(n) . g_e(n),  g_e = D^T 1_e
+  const int64_t n2p = (S->n2 + 31) & ~(int64_t)31;
+  double *ones = S->ns_work_d + 3 * n2p, *wv = ns_vel_scratch(S);   // z doubles as the all-ones pressure
+  {
+    std::vector<double> h1v((size_t)std::max<int64_t>(S->n2, 1), 1.0);
+    NSB_CUDA(cudaMemcpyAsync(ones, h1v.data(), sizeof(double) * S->n2, cudaMemcpyHostToDevice, st));
+    NSB_CUDA(cudaStreamSynchronize(st));
+  }
+  NSB_CHECK(launch_opgradt(S, ones, wv, S->npts, 0, nullptr, 0.0, 1.0, nullptr));
+  std::vector<double> g((size_t)dim * S->npts), bm((size_t)S->npts);
+  NSB_CUDA(cudaMemcpyAsync(g.data(), wv, sizeof(double) * dim * S->npts, cudaMemcpyDeviceToHost, st));
+  NSB_CUDA(cudaMemcpyAsync(bm.data(), S->bmask_d, sizeof(double) * S->npts, cudaMemcpyDeviceToHost, st));
+  NSB_CUDA(cudaStreamSynchronize(st));
+  const int n = (int)S->nel;
+  std::vector<double> diag(n, 0.0);
+  for (int64_t x = 0; x < S->npts; ++x) {
+    double s = 0.0;
+    for (int bb = 0; bb < dim; ++bb) s += g[(size_t)bb * S->npts + x] * g[(size_t)bb * S->npts + x];
+    diag[x / d.n1e] += bm[x] * s;
+  }
+  std::vector<std::vector<std::pair<int, double>>> rows(n);
+  auto add = [&](int r_, int c_, double v) {
+    for (auto &pr : rows[r_])
+      if (pr.first == c_) {
+        pr.second += v;
+        return;
+      }
+    rows[r_].push_back({c_, v});
+  };
+  NSB_REQUIRE((int64_t)S->gs_off_h.size() == S->nshared + 1, "fdm_setup: host copy of the gather-scatter lists missing");
+  for (int64_t nd = 0; nd < S->nshared; ++nd)
+    for (int64_t qa = S->gs_off_h[nd]; qa < S->gs_off_h[nd + 1]; ++qa)
+      for (int64_t qb = qa + 1; qb < S->gs_off_h[nd + 1]; ++qb) {
+        const int64_t xa = S->gs_idx_h[qa], xb = S->gs_idx_h[qb];
+        double v = 0.0;
+        for (int bb = 0; bb < dim; ++bb) v += g[(size_t)bb * S->npts + xa] * g[(size_t)bb * S->npts + xb];
+        v *= bm[xa];
+        const int ea = (int)(xa / d.n1e), eb = (int)(xb / d.n1e);
+        if (ea == eb) diag[ea] += 2.0 * v;
+        else {
+          add(ea, eb, v);
+          add(eb, ea, v);
+        }
+      }
+  std::vector<int> rowptr(n + 1, 0), col;
+  std::vector<double> val, dinv(std::max(n, 1), 0.0);
+  for (int e = 0; e < n; ++e) {
+    col.push_back(e);
+    val.push_back(diag[e]);
+    for (auto &pr : rows[e]) {
+      col.push_back(pr.first);
+      val.push_back(pr.second);
+    }
+    rowptr[e + 1] = (int)col.size();
+    dinv[e] = diag[e] > 0.0 ? 1.0 / diag[e] : 0.0;
+  }
+  S->cc_nnz = (int64_t)col.size();
+  const int nb = (n + NT_NS - 1) / NT_NS;
+  const int64_t np = ((int64_t)n + 31) & ~(int64_t)31;
+  NSB_CUDA(cudaMalloc(&S->cc_rowptr_d, sizeof(int) * (n + 1)));
+  NSB_CUDA(cudaMalloc(&S->cc_col_d, sizeof(int) * std::max<size_t>(col.size(), 1)));
+  NSB_CUDA(cudaMalloc(&S->cc_val_d, sizeof(double) * std::max<size_t>(val.size(), 1)));
+  NSB_CUDA(cudaMalloc(&S->cc_dinv_d, sizeof(double) * std::max(n, 1)));
+  NSB_CUDA(cudaMalloc(&S->cc_vec_d, sizeof(double) * 5 * std::max<int64_t>(np, 32)));
+  NSB_CUDA(cudaMalloc(&S->cc_partial_d, sizeof(double) * 6 * std::max(nb, 1)));
+  NSB_CUDA(cudaMalloc(&S->cc_state_d, sizeof(CcState)));
+  NSB_CUDA(cudaMemcpyAsync(S->cc_rowptr_d, rowptr.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(S->cc_col_d, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(S->cc_val_d, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemcpyAsync(S->cc_dinv_d, dinv.data(), sizeof(double) * std::max(n, 1), cudaMemcpyHostToDevice, st));
+  NSB_CUDA(cudaMemsetAsync(S->cc_state_d, 0, sizeof(CcState), st));
+  NSB_CUDA(cudaStreamSynchronize(st));
+  return NSB_OK;
+}
+
+size_t fdm_smem(nsb_sem_t S) {
+  const int l2 = S->lx2, n2e = l2 * l2 * (S->dim == 3 ? l2 : 1);
+  return sizeof(double) * (l2 * l2 + l2 + 2 * n2e);
+}
+
+// z = M^-1 r and the partial sums (r, z), sum z, sum r in partial[grid][3].
+//   precond 0 : 1 / bm2 (Nek's uzprec without the Schwarz part)
+//   precond 1 : element-wise fast diagonalisation + coarse correction on the element constants
+int precondition(nsb_sem_t S, int precond, const int *done, const double *r, double *z, int grid, double *partial) {
+  nsb_context_t ctx = S->ctx;
+  cudaStream_t st = ctx->stream;
+  const NsDims d = ns_dims(S);
+  if (precond == 0) {
+    precond_sums_kernel<<<grid, NT_NS, 0, st>>>(done, r, S->bm2inv_d, nullptr, d.n2e, z, S->n2, partial);
+    ctx->launches++;
+    NSB_CUDA(cudaGetLastError());
+    return NSB_OK;
+  }
+  const int n = (int)S->nel, nb = (n + NT_NS - 1) / NT_NS;
+  const int64_t np = ((int64_t)n + 31) & ~(int64_t)31;
+  double *xc = S->cc_vec_d, *rc = xc + np, *pc = rc + np, *wc = pc + np, *rr = wc + np;
+  double *pa = S->cc_partial_d, *pb = pa + 3 * nb;
+  CcState *cs = reinterpret_cast<CcState *>(S->cc_state_d);
+  fdm_kernel<<<(unsigned)S->nel, NT_NS, fdm_smem(S), st>>>(d, done, r, S->fdm_S_d, S->fdm_lam_d, S->fdm_c_d, z, rr);
+  ctx->launches++;
+  const bool coarse = S->cc_nnz > 0 && !ctx->ns_no_coarse;
+  if (coarse) {
+    cc_sum_kernel<<<nb, NT_NS, 0, st>>>(done, rr, n, pa);
+    cc_init_kernel<<<nb, NT_NS, 0, st>>>(done, rr, n, pa, S->cc_dinv_d, xc, rc, pc, pb, cs);
+    ctx->launches += 2;
+    for (int it = 0; it < S->cc_launch; ++it) {
+      cc_dir_kernel<<<nb, NT_NS, 0, st>>>(done, cs, it, rc, S->cc_dinv_d, n, pc, pb, 1e-10);
+      cc_spmv_kernel<<<nb, NT_NS, 0, st>>>(done, cs, S->cc_rowptr_d, S->cc_col_d, S->cc_val_d, pc, n, wc, pa);
+      cc_update_kernel<<<nb, NT_NS, 0, st>>>(done, cs, it, pc, wc, S->cc_dinv_d, n, xc, rc, pa, pb);
+      ctx->launches += 3;
+    }
+  }
+  precond_sums_kernel<<<grid, NT_NS, 0, st>>>(done, r, nullptr, coarse ? xc : nullptr, d.n2e, z, S->n2, partial);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
+// E dp = rhs on device arrays; x receives dp.  Host involvement: one poll of the state block every 8 iterations.
+int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, int mean_free, int precond, int *iters,
+             double *res) {
   nsb_context_t ctx = S->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   const int64_t n2 = S->n2, n2p = (n2 + 31) & ~(int64_t)31;
-  double *r = S->ns_work_d, *p = r + n2p, *w = p + n2p, *wv = ns_vel_scratch(S);
+  double *r = S->ns_work_d, *p = r + n2p, *w = p + n2p, *z = w + n2p, *wv = ns_vel_scratch(S);
   PcgP *state = reinterpret_cast<PcgP *>(S->ns_state_d);
   double *sums = S->ns_state_d + offsetof(PcgP, sums) / sizeof(double);
   const int *done = reinterpret_cast<const int *>(reinterpret_cast<const char *>(state) + offsetof(PcgP, done));
-  const int grid = (int)std::min<int64_t>((n2 + NT_NS - 1) / NT_NS, (int64_t)ctx->num_sms * 8);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n2 + NT_NS - 1) / NT_NS, (int64_t)ctx->num_sms * 8));
   NSB_CHECK(ensure_partial(ctx, std::max<int64_t>((3 * (int64_t)grid + kMaxK + 7) / (kMaxK + 8) + 1,
                                                   (S->nel + kMaxK + 7) / (kMaxK + 8) + 1)));
+  if (precond == 1) NSB_CHECK(fdm_setup(S));
   double *partial = ctx->partial_d;
   double ntot = (double)n2;
   PcgP h0;
@@ -457,9 +934,11 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 3, 1));
     sum_rhs = sums + 3;
   }
-  pcg_init_kernel<<<grid, NT_NS, 0, st>>>(rhs, S->bm2inv_d, n2, 0.0, sum_rhs, ntot, mean_free, r, x, p, partial);
+  pcg_init_kernel<<<grid, NT_NS, 0, st>>>(rhs, n2, sum_rhs, ntot, mean_free, r, x, p);
+  ctx->launches++;
+  NSB_CHECK(precondition(S, precond, done, r, z, grid, partial));
   reduce_rows_kernel<<<3, 32, 0, st>>>(partial, grid, 3, sums + 1, nullptr);
-  ctx->launches += 2;
+  ctx->launches++;
   if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 1, 3));
   pcg_after_r_kernel<<<1, 1, 0, st>>>(state, tol, 1);
   ctx->launches++;
@@ -467,7 +946,7 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
   const int64_t fs = S->npts;
   PcgP *hst = reinterpret_cast<PcgP *>(ctx->hpin + 3 * (kMaxK + 8) + 64);
   for (int it = 1; it <= maxit; ++it) {
-    pcg_p_kernel<<<grid, NT_NS, 0, st>>>(state, r, S->bm2inv_d, p, n2);
+    pcg_p_kernel<<<grid, NT_NS, 0, st>>>(state, z, p, n2);
     ctx->launches++;
     NSB_CHECK(launch_binv_gradt(S, p, wv, fs, nullptr, 0.0, 1.0, done));           // wv = B^-1 D^T p
     NSB_CHECK(launch_opdiv(S, wv, fs, 1.0, w, p, partial, done));                 // w = D wv, partial (w, p)
@@ -475,17 +954,27 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
     ctx->launches++;
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums, 1));
     pcg_after_w_kernel<<<1, 1, 0, st>>>(state);
-    pcg_xr_kernel<<<grid, NT_NS, 0, st>>>(state, p, w, S->bm2inv_d, x, r, n2, partial);
+    pcg_xr_kernel<<<grid, NT_NS, 0, st>>>(state, p, w, x, r, n2);
+    ctx->launches += 2;
+    NSB_CHECK(precondition(S, precond, done, r, z, grid, partial));
     reduce_rows_kernel<<<3, 32, 0, st>>>(partial, grid, 3, sums + 1, done);
-    ctx->launches += 3;
+    ctx->launches++;
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 1, 3));
     pcg_after_r_kernel<<<1, 1, 0, st>>>(state, tol, 0);
     ctx->launches++;
     NSB_CUDA(cudaGetLastError());
     if (it % 8 == 0 || it == maxit) {
       NSB_CUDA(cudaMemcpyAsync(hst, state, sizeof(PcgP), cudaMemcpyDeviceToHost, st));
+      CcState *hcs = reinterpret_cast<CcState *>(hst + 1);
+      const bool two_level = precond == 1 && S->cc_nnz > 0 && !ctx->ns_no_coarse;
+      if (two_level) NSB_CUDA(cudaMemcpyAsync(hcs, S->cc_state_d, sizeof(CcState), cudaMemcpyDeviceToHost, st));
       NSB_CUDA(cudaStreamSynchronize(st));
       if (hst->done) break;
+      if (two_level) {
+        // the coarse solve stops on the device; enqueue a quarter more iterations than the last one used (all of
+        // cc_maxit while it still runs out of them)
+        S->cc_launch = hcs->done ? std::min(S->cc_maxit, hcs->it + hcs->it / 4 + 8) : S->cc_maxit;
+      }
     }
   }
   NSB_CUDA(cudaMemcpyAsync(hst, state, sizeof(PcgP), cudaMemcpyDeviceToHost, st));
@@ -502,9 +991,15 @@ const double kABn[4][3] = {{0, 0, 0}, {1.0, 0, 0}, {2.0, -1.0, 0}, {3.0, -3.0, 1
 }  // namespace
 
 void nsb::ns_free(nsb_sem_t S) {
-  for (double *q : {S->i12_d, S->d12_d, S->rx2_d, S->bm2inv_d, S->ns_work_d, S->ns_state_d})
+  for (double *q : {S->i12_d, S->d12_d, S->rx2_d, S->bm2inv_d, S->ns_work_d, S->ns_state_d, S->fdm_S_d, S->fdm_lam_d,
+                    S->fdm_c_d, S->cc_val_d, S->cc_dinv_d, S->cc_vec_d, S->cc_partial_d, S->cc_state_d})
     if (q) cudaFree(q);
+  if (S->cc_rowptr_d) cudaFree(S->cc_rowptr_d);
+  if (S->cc_col_d) cudaFree(S->cc_col_d);
   S->i12_d = S->d12_d = S->rx2_d = S->bm2inv_d = S->ns_work_d = S->ns_state_d = nullptr;
+  S->fdm_S_d = S->fdm_lam_d = S->fdm_c_d = S->cc_val_d = S->cc_dinv_d = S->cc_vec_d = S->cc_partial_d = S->cc_state_d = nullptr;
+  S->cc_rowptr_d = S->cc_col_d = nullptr;
+  S->cc_nnz = 0;
   S->lx2 = 0;
 }
 
@@ -560,7 +1055,7 @@ extern "C" int nsb_sem_pressure_setup(nsb_sem_t S) {
       cudaMalloc(&S->d12_d, sizeof(double) * l2 * l1) != cudaSuccess ||
       cudaMalloc(&S->rx2_d, sizeof(double) * dim * dim * std::max<int64_t>(S->n2, 1)) != cudaSuccess ||
       cudaMalloc(&S->bm2inv_d, sizeof(double) * std::max<int64_t>(S->n2, 1)) != cudaSuccess ||
-      cudaMalloc(&S->ns_work_d, sizeof(double) * (3 * n2p + dim * std::max<int64_t>(S->npts, 1))) != cudaSuccess ||
+      cudaMalloc(&S->ns_work_d, sizeof(double) * (4 * n2p + dim * std::max<int64_t>(S->npts, 1))) != cudaSuccess ||
       cudaMalloc(&S->ns_state_d, sizeof(PcgP)) != cudaSuccess || cudaMalloc(&w3_d, sizeof(double) * n2e) != cudaSuccess)
     return fail("out of device memory");
   S->lx2 = l2;
@@ -630,14 +1125,15 @@ extern "C" int nsb_sem_cdabdtp(nsb_sem_t S, nsb_basis_t bin, int cin, nsb_basis_
 }
 
 extern "C" int nsb_sem_esolve(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, double tol, int maxit,
-                              int mean_free, int *iters, double *res) {
+                              int mean_free, int precond, int *iters, double *res) {
   double *rhs, *x;
   NSB_CHECK(pressure_ptr(S, brhs, crhs, &rhs, "nsb_sem_esolve"));
   NSB_CHECK(pressure_ptr(S, bx, cx, &x, "nsb_sem_esolve"));
   NSB_REQUIRE(rhs != x, "nsb_sem_esolve: right-hand side and solution are the same vector");
   NSB_REQUIRE(tol > 0.0 && maxit >= 1, "nsb_sem_esolve: bad tolerance / iteration limit");
+  NSB_REQUIRE(precond == 0 || precond == 1, "nsb_sem_esolve: unknown preconditioner %d", precond);
   NSB_REQUIRE(S->exchange_ready || S->ctx->nranks == 1, "nsb_sem_esolve: call nsb_sem_setup_exchange first");
-  return esolve_d(S, rhs, x, tol, maxit, mean_free, iters, res);
+  return esolve_d(S, rhs, x, tol, maxit, mean_free, precond, iters, res);
 }
 
 // Operator handle with the structure of exponential_prop%matvec for the linearised Navier-Stokes equations:
@@ -647,9 +1143,10 @@ extern "C" int nsb_sem_esolve(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis
 // of that column), NULL for the Stokes operator.  Uses both convection slots of the mesh (0: U, 1: v).
 extern "C" int nsb_op_create_ns_stepper(nsb_sem_t S, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu,
                                         double dt, int nsteps, double tol_v, double tol_p, int maxit, int mean_free,
-                                        nsb_op_t *out) {
+                                        int precond, nsb_op_t *out) {
   NSB_REQUIRE(S && layout && out, "nsb_op_create_ns_stepper: NULL argument");
-  NSB_REQUIRE(nu > 0.0 && dt > 0.0 && nsteps >= 1 && maxit >= 1 && tol_v > 0.0 && tol_p > 0.0,
+  NSB_REQUIRE(nu > 0.0 && dt > 0.0 && nsteps >= 1 && maxit >= 1 && tol_v > 0.0 && tol_p > 0.0 &&
+                  (precond == 0 || precond == 1),
               "nsb_op_create_ns_stepper: bad parameter");
   NSB_REQUIRE(layout->ctx == S->ctx, "nsb_op_create_ns_stepper: layout and mesh live on different contexts");
   NSB_REQUIRE(S->exchange_ready, "nsb_op_create_ns_stepper: call nsb_sem_setup_exchange first");
@@ -678,6 +1175,7 @@ extern "C" int nsb_op_create_ns_stepper(nsb_sem_t S, nsb_layout_t layout, nsb_ba
   op->tol_p = tol_p;
   op->maxit = maxit;
   op->mean_free = mean_free;
+  op->precond = precond;
   op->has_base = base != nullptr;
   int r = nsb_basis_create(layout, 10, &op->tmp);
   if (r == NSB_OK && base) {
@@ -753,7 +1251,7 @@ int nsb::ns_stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bou
     {
       int it = 0;
       double res = 0.0;
-      NSB_CHECK(esolve_d(S, prs(3), prs(4), op->tol_p, op->maxit, op->mean_free, &it, &res));
+      NSB_CHECK(esolve_d(S, prs(3), prs(4), op->tol_p, op->maxit, op->mean_free, op->precond, &it, &res));
       op->pres_iters += it;
     }
     NSB_CHECK(launch_binv_gradt(S, prs(4), vel(nw), fs, vel(vs), 1.0, op->dt / bd0, nullptr));

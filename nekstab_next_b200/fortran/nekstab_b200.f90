@@ -474,11 +474,12 @@ module nekstab_b200
          type(c_ptr), value :: sem
          integer(c_int) :: ierr
       end function
-      function nsb_op_create_ns_stepper(sem, layout, base, col_base, nu, dt, nsteps, tol_v, tol_p, maxit, mean_free, op) &
+      function nsb_op_create_ns_stepper(sem, layout, base, col_base, nu, dt, nsteps, tol_v, tol_p, maxit, mean_free, &
+                                        precond, op) &
          bind(C, name='nsb_op_create_ns_stepper') result(ierr)
          import :: c_int, c_ptr, c_double
          type(c_ptr), value :: sem, layout, base       !< base = c_null_ptr: Stokes operator
-         integer(c_int), value :: col_base, nsteps, maxit, mean_free
+         integer(c_int), value :: col_base, nsteps, maxit, mean_free, precond
          real(c_double), value :: nu, dt, tol_v, tol_p
          type(c_ptr) :: op
          integer(c_int) :: ierr

@@ -95,11 +95,93 @@ def cdabdtp(p, ps, glo, mask, binv):
     return opdiv(opbinv(opgradt(p, ps), glo, mask, binv), ps)
 
 
-def esolve(rhs, ps, glo, mask, binv, tol=1e-10, maxit=2000, mean_free=True):
-    """E dp = rhs by conjugate gradients preconditioned with the inverse pressure mass matrix (uzawa / uzprec without
-    the Schwarz part): z = r / bm2 ; rtz = sum r z ; p = z + beta p ; w = E p ; alpha = rtz / sum w p.
-    Stops on sqrt(rtz) <= tol * sqrt(rtz_0).  Returns (dp, iterations, residual drop)."""
-    minv = 1.0 / ps['bm2']
+def fdm_setup(n, geo, ps):
+    """Element-wise fast-diagonalisation preconditioner for E (the local solves of Nek's Schwarz preconditioner,
+    fast.f / hsmg.f, without overlap and without the coarse grid): every element is replaced by the box with its mean
+    edge lengths L_a = 2 / mean(|J grad r_a| / J), on which E_e = sum_a c_a (E^ in direction a) x (M^ in the others) with
+    the 1-D operators  E^ = D^ b^-1 D^T,  M^ = I^ b^-1 I^T  (D^ = w2 o D12, I^ = w2 o I12, b^ = GLL weights with the two
+    end weights doubled = assembled with an equal neighbour).  E^ S = M^ S Lambda, S^T M^ S = 1 gives
+    E_e^-1 = (S x S x S) diag(1 / sum_a c_a lambda_ia) (S x S x S)^T."""
+    import scipy.linalg as sla
+    d = ps['dim']
+    _, w1 = osem.gll(n)
+    _, w2 = osem.gl(n - 1)
+    b = w1.copy()
+    b[0] *= 2.0
+    b[-1] *= 2.0
+    Dh = w2[:, None] * ps['D12']
+    Ih = w2[:, None] * ps['I12']
+    Eh = (Dh / b) @ Dh.T
+    Mh = (Ih / b) @ Ih.T
+    lam, S = sla.eigh(Eh, Mh)
+    rst, jac = geo['rst'], geo['jac']
+    ne = jac.shape[0]
+    L = np.zeros((ne, d))
+    for a in range(d):
+        g = np.sqrt(sum(rst[a * d + bb] ** 2 for bb in range(d))) / jac
+        L[:, a] = 2.0 / g.reshape(ne, -1).mean(axis=1)
+    c = np.zeros((ne, d))
+    for a in range(d):
+        c[:, a] = 2.0 / L[:, a]
+        for o in range(d):
+            if o != a:
+                c[:, a] *= L[:, o] / 2.0
+    if d == 3:   # den[e, K, J, I] = c_r lam_I + c_s lam_J + c_t lam_K
+        den = (c[:, 0, None, None, None] * lam[None, None, None, :] + c[:, 1, None, None, None] * lam[None, None, :, None]
+               + c[:, 2, None, None, None] * lam[None, :, None, None])
+    else:
+        den = c[:, 0, None, None] * lam[None, None, :] + c[:, 1, None, None] * lam[None, :, None]
+    return dict(S=S, lam=lam, L=L, c=c, den=den, dim=d, coarse=None)
+
+
+def coarse_setup(fd, ps, glo, mask, binv):
+    """Coarse level of the preconditioner: one constant per element, E_c = R E R^T with R = sum over the element's
+    pressure points.  With g_e = D^T 1_e (element-local), E_c[f, e] = sum over the velocity nodes n shared by e and f of
+    binvm1_n mask_n g_f(n) . g_e(n)  -- a sparse nel x nel matrix (elements that share a node).  Solved exactly here
+    (pseudo-inverse in the mean-free subspace); the device runs Jacobi-CG on it."""
+    import scipy.sparse as sp
+    d = ps['dim']
+    ones = np.ones_like(ps['bm2'])
+    g = opgradt(ones, ps)
+    ne = ones.shape[0]
+    nglob = int(glo.max()) + 1
+    rows = np.concatenate([glo.ravel() + b * nglob for b in range(d)])
+    cols = np.tile(np.repeat(np.arange(ne), glo[0].size), d)
+    vals = np.concatenate([g[b].ravel() for b in range(d)])
+    G = sp.csr_matrix((vals, (rows, cols)), shape=(d * nglob, ne))
+    wnode = np.zeros(nglob)
+    wnode[glo.ravel()] = (binv * mask).ravel()
+    Ec = (G.T @ sp.diags(np.tile(wnode, d)) @ G).toarray()
+    P = np.eye(ne) - 1.0 / ne
+    fd['coarse'] = dict(Ec=Ec, Ecp=P @ np.linalg.pinv(P @ Ec @ P, hermitian=True, rcond=1e-10) @ P)
+    return fd
+
+
+def fdm_apply(r, fd):
+    S = fd['S']
+    if fd['dim'] == 3:
+        t = np.einsum('Kk,Jj,Ii,eKJI->ekji', S, S, S, r, optimize=True) / fd['den']
+        z = np.einsum('Kk,Jj,Ii,ekji->eKJI', S, S, S, t, optimize=True)
+    else:
+        t = np.einsum('Jj,Ii,eJI->eji', S, S, r, optimize=True) / fd['den']
+        z = np.einsum('Jj,Ii,eji->eJI', S, S, t, optimize=True)
+    if fd.get('coarse') is not None:
+        ne = r.shape[0]
+        zc = fd['coarse']['Ecp'] @ r.reshape(ne, -1).sum(axis=1)
+        z = z + zc.reshape((ne,) + (1,) * (r.ndim - 1))
+    return z
+
+
+def esolve(rhs, ps, glo, mask, binv, tol=1e-10, maxit=2000, mean_free=True, fdm=None):
+    """E dp = rhs by preconditioned conjugate gradients: z = M^-1 r ; rtz = sum r z ; p = z + beta p ; w = E p ;
+    alpha = rtz / sum w p.  M^-1 = 1 / bm2 (uzawa / uzprec without the Schwarz part) or, with fdm = fdm_setup(..), the
+    element-wise fast-diagonalisation solve.  Stops on sqrt(rtz) <= tol * sqrt(rtz_0).
+    Returns (dp, iterations, residual drop)."""
+    if fdm is None:
+        bminv = 1.0 / ps['bm2']
+        minv = _Diag(bminv)
+    else:
+        minv = _Fdm(fdm)
     x = np.zeros_like(rhs)
     p = np.zeros_like(rhs)
     r = ortho(rhs) if mean_free else rhs.copy()
@@ -132,6 +214,22 @@ def esolve(rhs, ps, glo, mask, binv, tol=1e-10, maxit=2000, mean_free=True):
     return x, it, (rn / r0 if r0 > 0 else 0.0)
 
 
+class _Diag:
+    def __init__(self, d):
+        self.d = d
+
+    def __mul__(self, r):
+        return self.d * r
+
+
+class _Fdm:
+    def __init__(self, fd):
+        self.fd = fd
+
+    def __mul__(self, r):
+        return fdm_apply(r, self.fd)
+
+
 # ----------------------------------------------------------------------------
 # The perturbation step  (perturb.f perturbv: advabp, makextp, makebdfp, cresvipp + ophinv, incomprp)
 # ----------------------------------------------------------------------------
@@ -144,7 +242,7 @@ def advabp(vel, base, cf_base, dl):
 
 
 def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=True,
-             maxit=4000, info=None):
+             maxit=4000, info=None, fdm=None):
     """nsteps BDF/EXT steps (order ramp 1, 2, 3, cold start) of the linearised incompressible Navier-Stokes equations
         dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v ,  div v = 0
     in the P_N - P_N-2 splitting:
@@ -178,7 +276,7 @@ def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1
             its_v += it
             vstar.append(x)
         rhs = -(bd0 / dt) * opdiv(vstar, ps)
-        dp, it, _ = esolve(rhs, ps, glo, mask, binv, tol=tol_p, maxit=maxit, mean_free=mean_free)
+        dp, it, _ = esolve(rhs, ps, glo, mask, binv, tol=tol_p, maxit=maxit, mean_free=mean_free, fdm=fdm)
         its_p += it
         corr = opbinv(opgradt(dp, ps), glo, mask, binv)
         vnew = [vstar[b] + (dt / bd0) * corr[b] for b in range(dim)]

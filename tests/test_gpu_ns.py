@@ -106,35 +106,47 @@ def test_consistent_poisson_operator_and_solve(ctx, nel, N):
     _, Ep = P.down(B[1])
     ref = ons.cdabdtp(p, P.ps, P.glo, P.mask, P.binv)
     assert relerr(Ep, ref) <= 1e-12
-    # E x = E p: the solve gives back p up to the near-null component; compare with the oracle's iteration instead
-    for mean_free in (False, True):
-        xo, ito, dropo = ons.esolve(ref, P.ps, P.glo, P.mask, P.binv, tol=1e-11, maxit=3000, mean_free=mean_free)
-        P.up(B[1], zero, ref)
-        it, drop = sem.esolve(B[1], B[2], tol=1e-11, maxit=3000, mean_free=mean_free)
-        _, x = P.down(B[2])
-        assert abs(it - ito) <= 3 and drop <= 1e-11
-        # the constant is the (near-)null vector of E: its coefficient is not determined to the solver tolerance
-        assert relerr(x - x.mean(), xo - xo.mean()) <= 1e-8
+    # E x = E p with both preconditioners, against the oracle's iteration with the same preconditioner
+    fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv)
+    for precond in (0, 1):
+        for mean_free in (False, True):
+            xo, ito, dropo = ons.esolve(ref, P.ps, P.glo, P.mask, P.binv, tol=1e-11, maxit=3000, mean_free=mean_free,
+                                        fdm=fd if precond else None)
+            P.up(B[1], zero, ref)
+            it, drop = sem.esolve(B[1], B[2], tol=1e-11, maxit=3000, mean_free=mean_free, precond=precond)
+            _, x = P.down(B[2])
+            # precond 1: the device solves the coarse problem by CG to 1e-10, the oracle by a pseudo-inverse: the
+            # iteration counts agree to a few per cent, the solutions to the tolerance
+            assert abs(it - ito) <= (3 if precond == 0 else 3 + 0.12 * ito) and drop <= 1e-11, (precond, mean_free, it, ito, drop)
+            # the constant is the (near-)null vector of E: its coefficient is not determined to the solver tolerance
+            assert relerr(x - x.mean(), xo - xo.mean()) <= 1e-8
+            if precond == 1 and mean_free:
+                assert it < 0.6 * it_diag, 'the two-level preconditioner should at least halve the iteration count'
+            if precond == 0 and mean_free:
+                it_diag = it
     for o in (B, lay, sem):
         o.close()
 
 
-@pytest.mark.parametrize('nel,N,conv', [((2, 2, 2), 7, True), ((2, 2, 2), 4, True), ((3, 3), 5, True), ((2, 2), 7, False)])
-def test_ns_stepper_matches_oracle(ctx, nel, N, conv):
+@pytest.mark.parametrize('nel,N,conv,precond', [((2, 2, 2), 7, True, 1), ((2, 2, 2), 4, True, 1), ((3, 3), 5, True, 1),
+                                                ((2, 2), 7, False, 1), ((2, 2, 2), 4, True, 0), ((3, 3), 5, True, 0)])
+def test_ns_stepper_matches_oracle(ctx, nel, N, conv, precond):
     import nekstab_next_b200 as nb
     P = NsProblem(nel, N, seed=40 + N)
     sem, lay, B = P.gpu(ctx, 3)
     nu, dt, nsteps = 0.05, 2e-3, 4
     v0, p0 = P.vel(), P.pres()
     info = {}
+    fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv) if precond else None
     vo, po = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base if conv else None, v0, p0, nu, dt, nsteps,
-                          mean_free=False, info=info)
+                          mean_free=False, info=info, fdm=fd)
     base = None
     if conv:
         sem.dealias_setup()
         P.up(B[2], P.base, 0 * p0)
         base = B[2]
-    op = nb.ns_stepper_operator(sem, lay, base, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False)
+    op = nb.ns_stepper_operator(sem, lay, base, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False,
+                                precond=precond)
     P.up(B[0], v0, p0)
     op.matvec(B[0], B[1])
     v, p = P.down(B[1])
@@ -148,7 +160,7 @@ def test_ns_stepper_matches_oracle(ctx, nel, N, conv):
     assert np.max(np.abs(ons.opdiv(v, P.ps))) <= 1e-9 * scale          # discretely incompressible
     ih, ip = nb.ns_iterations(op)
     assert abs(ih - info['helmholtz_iterations']) <= 3 * P.dim * nsteps
-    assert abs(ip - info['pressure_iterations']) <= 3 * nsteps
+    assert abs(ip - info['pressure_iterations']) <= 4 * nsteps + (0.12 * info['pressure_iterations'] if precond else 0)
     # a second application starts from a cold state again
     op.matvec(B[0], B[1])
     v2, p2 = P.down(B[1])
