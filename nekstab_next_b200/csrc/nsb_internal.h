@@ -225,6 +225,7 @@ struct nsb_sem_s {
   int *cc_rowptr_d = nullptr, *cc_col_d = nullptr;   // coarse operator (one constant per element), CSR
   double *cc_val_d = nullptr, *cc_dinv_d = nullptr, *cc_vec_d = nullptr, *cc_partial_d = nullptr, *cc_state_d = nullptr;
   int64_t cc_nnz = 0;
+  int cc_width = 0;                           // ELL width of the coarse operator
   int cc_maxit = 400;                         // most coarse CG iterations enqueued per application
   int cc_launch = 400;                        // currently enqueued (stops early on the device; adapted at every poll)
 };

@@ -40,6 +40,7 @@ __device__ __forceinline__ void stage(double *__restrict__ out, const double *__
     const int x = t % inner, O = (t / inner) % no, o = t / (inner * no);
     const double *src = in + (size_t)o * nl * inner + x;
     double s = 0.0;
+#pragma unroll 8
     for (int l = 0; l < nl; ++l) s = fma(TR ? M[l * no + O] : M[O * nl + l], src[(size_t)l * inner], s);
     if (ACC) out[t] += s;
     else out[t] = s;
@@ -60,13 +61,18 @@ __host__ __device__ inline int ns_smem_doubles(int dim, int l1, int l2) {
 
 // (D u): vel = dim equally spaced fields (stride fs) -> pressure array.  out = scale * D u; optional partial sums of
 // out * dotw per CTA (pressure CG: (E p, p)).
+template <int TL1, int TDIM>
 __global__ void __launch_bounds__(NT_NS)
 opdiv_kernel(NsDims d, const double *__restrict__ vel, int64_t fs, const double *__restrict__ rx2, int64_t n2,
              const double *__restrict__ I12g, const double *__restrict__ D12g, double scale, double *__restrict__ out,
              const double *__restrict__ dotw, double *__restrict__ dot_partial, const int *__restrict__ done) {
   if (done && *done) return;
   extern __shared__ double sm[];
-  const int l1 = d.l1, l2 = d.l2, dim = d.dim, lz1 = dim == 3 ? l1 : 1;
+  const int l1 = TL1 ? TL1 : d.l1, l2 = TL1 ? TL1 - 2 : d.l2, dim = TDIM ? TDIM : d.dim, lz1 = dim == 3 ? l1 : 1;
+  if (TL1) {
+    d.n1e = l1 * l1 * lz1;
+    d.n2e = l2 * l2 * (dim == 3 ? l2 : 1);
+  }
   double *I12 = sm, *D12 = I12 + l2 * l1, *u = D12 + l2 * l1, *A = u + d.n1e, *B = A + lz1 * l1 * l2,
          *AA = B + lz1 * l1 * l2, *AD = AA + lz1 * l2 * l2, *BA = AD + lz1 * l2 * l2;
   for (int t = threadIdx.x; t < l2 * l1; t += blockDim.x) {
@@ -133,6 +139,7 @@ opdiv_kernel(NsDims d, const double *__restrict__ vel, int64_t fs, const double 
 //   epi 0 : out = alpha * uin + beta * w                        (all points; uin may be null)
 //   epi 1 : element-interior points  out = alpha * uin + beta * bmask * w,  element-boundary points  out = w
 //           (the gather-scatter with the same alpha / beta / bmask finishes those: B^-1 D^T p and v* + c B^-1 D^T dp)
+template <int TL1, int TDIM>
 __global__ void __launch_bounds__(NT_NS)
 opgradt_kernel(NsDims d, const double *__restrict__ p, const double *__restrict__ rx2, int64_t n2,
                const double *__restrict__ I12g, const double *__restrict__ D12g, double *out, int64_t fs,
@@ -140,7 +147,11 @@ opgradt_kernel(NsDims d, const double *__restrict__ p, const double *__restrict_
                const int *__restrict__ done) {
   if (done && *done) return;
   extern __shared__ double sm[];
-  const int l1 = d.l1, l2 = d.l2, dim = d.dim, lz1 = dim == 3 ? l1 : 1;
+  const int l1 = TL1 ? TL1 : d.l1, l2 = TL1 ? TL1 - 2 : d.l2, dim = TDIM ? TDIM : d.dim, lz1 = dim == 3 ? l1 : 1;
+  if (TL1) {
+    d.n1e = l1 * l1 * lz1;
+    d.n2e = l2 * l2 * (dim == 3 ? l2 : 1);
+  }
   double *I12 = sm, *D12 = I12 + l2 * l1, *w = D12 + l2 * l1, *A = w + d.n1e, *B = A + lz1 * l1 * l2,
          *AA = B + lz1 * l1 * l2, *AD = AA + lz1 * l2 * l2, *BA = AD + lz1 * l2 * l2, *Gr = BA + lz1 * l2 * l2,
          *Gs = Gr + d.n2e, *Gt = Gs + d.n2e;
@@ -231,12 +242,12 @@ struct PcgP {
 __global__ void reduce_rows_kernel(const double *__restrict__ partial, int rows, int ncol, double *__restrict__ out,
                                    const int *__restrict__ done) {
   if (done && *done) return;
-  // one warp per column, fixed order
-  const int c = blockIdx.x, lane = threadIdx.x;
+  // one CTA per column, fixed order (thread-strided sums, shuffle tree, warp partials in turn)
+  const int c = blockIdx.x;
   double s = 0.0;
-  for (int r = lane; r < rows; r += 32) s += partial[(size_t)r * ncol + c];
-  s = warp_reduce_sum(s);
-  if (lane == 0) out[c] = s;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) s += partial[(size_t)r * ncol + c];
+  s = block_reduce_sum<NT_NS>(s);
+  if (threadIdx.x == 0) out[c] = s;
 }
 
 // r = rhs - mean(rhs) (mean_free) ; x = 0 ; p = 0
@@ -536,16 +547,18 @@ cc_dir_kernel(const int *__restrict__ odone, CcState *st, int it, const double *
   }
 }
 
+// E_c in ELL storage: entry k of row i at [k * n + i] (neighbouring threads read neighbouring words); rows are padded
+// with zero coefficients on their own diagonal index.
 __global__ void __launch_bounds__(NT_NS)
-cc_spmv_kernel(const int *__restrict__ odone, const CcState *st, const int *__restrict__ rowptr,
-               const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ p, int n,
-               double *__restrict__ w, double *__restrict__ partial_pw) {
+cc_spmv_kernel(const int *__restrict__ odone, const CcState *st, int width, const int *__restrict__ col,
+               const double *__restrict__ val, const double *__restrict__ p, int n, double *__restrict__ w,
+               double *__restrict__ partial_pw) {
   if (*odone || st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double pw = 0.0;
   if (i < n) {
     double sv = 0.0;
-    for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) sv = fma(val[q], p[col[q]], sv);
+    for (int k = 0; k < width; ++k) sv = fma(val[(size_t)k * n + i], p[col[(size_t)k * n + i]], sv);
     w[i] = sv;
     pw = sv * p[i];
   }
@@ -601,8 +614,12 @@ int launch_opdiv(nsb_sem_t S, const double *vel, int64_t fs, double scale, doubl
   nsb_context_t ctx = S->ctx;
   // algorithmic bytes: dim velocity fields and dim^2 metric arrays read, one pressure array written
   ProfScope ps(ctx, PC_AXHELM, 8.0 * ((double)S->dim * S->npts + ((double)S->dim * S->dim + 1.0) * S->n2));
-  opdiv_kernel<<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), vel, fs, S->rx2_d, S->n2, S->i12_d,
-                                                                    S->d12_d, scale, out, dotw, dot_partial, done);
+  if (S->lx == 8 && S->dim == 3)
+    opdiv_kernel<8, 3><<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), vel, fs, S->rx2_d, S->n2, S->i12_d,
+                                                                            S->d12_d, scale, out, dotw, dot_partial, done);
+  else
+    opdiv_kernel<0, 0><<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), vel, fs, S->rx2_d, S->n2, S->i12_d,
+                                                                            S->d12_d, scale, out, dotw, dot_partial, done);
   ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -612,8 +629,14 @@ int launch_opgradt(nsb_sem_t S, const double *p, double *out, int64_t fs, int ep
                    double beta, const int *done) {
   nsb_context_t ctx = S->ctx;
   ProfScope ps(ctx, PC_AXHELM, 8.0 * ((double)S->dim * S->npts * (uin ? 2.0 : 1.0) + ((double)S->dim * S->dim + 1.0) * S->n2));
-  opgradt_kernel<<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), p, S->rx2_d, S->n2, S->i12_d, S->d12_d,
-                                                                      out, fs, epi, uin, alpha, beta, S->bmask_d, done);
+  if (S->lx == 8 && S->dim == 3)
+    opgradt_kernel<8, 3><<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), p, S->rx2_d, S->n2, S->i12_d,
+                                                                              S->d12_d, out, fs, epi, uin, alpha, beta,
+                                                                              S->bmask_d, done);
+  else
+    opgradt_kernel<0, 0><<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), p, S->rx2_d, S->n2, S->i12_d,
+                                                                              S->d12_d, out, fs, epi, uin, alpha, beta,
+                                                                              S->bmask_d, done);
   ctx->launches++;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -821,29 +844,29 @@ int fdm_setup(nsb_sem_t S) {
           add(eb, ea, v);
         }
       }
-  std::vector<int> rowptr(n + 1, 0), col;
-  std::vector<double> val, dinv(std::max(n, 1), 0.0);
+  int width = 1;
+  for (int e = 0; e < n; ++e) width = std::max<int>(width, 1 + (int)rows[e].size());
+  std::vector<int> col((size_t)width * std::max(n, 1));
+  std::vector<double> val((size_t)width * std::max(n, 1), 0.0), dinv(std::max(n, 1), 0.0);
   for (int e = 0; e < n; ++e) {
-    col.push_back(e);
-    val.push_back(diag[e]);
-    for (auto &pr : rows[e]) {
-      col.push_back(pr.first);
-      val.push_back(pr.second);
+    for (int k = 0; k < width; ++k) col[(size_t)k * n + e] = e;
+    val[e] = diag[e];
+    for (size_t k = 0; k < rows[e].size(); ++k) {
+      col[(k + 1) * n + e] = rows[e][k].first;
+      val[(k + 1) * n + e] = rows[e][k].second;
     }
-    rowptr[e + 1] = (int)col.size();
     dinv[e] = diag[e] > 0.0 ? 1.0 / diag[e] : 0.0;
   }
-  S->cc_nnz = (int64_t)col.size();
+  S->cc_nnz = (int64_t)width * n;
+  S->cc_width = width;
   const int nb = (n + NT_NS - 1) / NT_NS;
   const int64_t np = ((int64_t)n + 31) & ~(int64_t)31;
-  NSB_CUDA(cudaMalloc(&S->cc_rowptr_d, sizeof(int) * (n + 1)));
   NSB_CUDA(cudaMalloc(&S->cc_col_d, sizeof(int) * std::max<size_t>(col.size(), 1)));
   NSB_CUDA(cudaMalloc(&S->cc_val_d, sizeof(double) * std::max<size_t>(val.size(), 1)));
   NSB_CUDA(cudaMalloc(&S->cc_dinv_d, sizeof(double) * std::max(n, 1)));
   NSB_CUDA(cudaMalloc(&S->cc_vec_d, sizeof(double) * 5 * std::max<int64_t>(np, 32)));
   NSB_CUDA(cudaMalloc(&S->cc_partial_d, sizeof(double) * 6 * std::max(nb, 1)));
   NSB_CUDA(cudaMalloc(&S->cc_state_d, sizeof(CcState)));
-  NSB_CUDA(cudaMemcpyAsync(S->cc_rowptr_d, rowptr.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemcpyAsync(S->cc_col_d, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemcpyAsync(S->cc_val_d, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemcpyAsync(S->cc_dinv_d, dinv.data(), sizeof(double) * std::max(n, 1), cudaMemcpyHostToDevice, st));
@@ -860,7 +883,8 @@ size_t fdm_smem(nsb_sem_t S) {
 // z = M^-1 r and the partial sums (r, z), sum z, sum r in partial[grid][3].
 //   precond 0 : 1 / bm2 (Nek's uzprec without the Schwarz part)
 //   precond 1 : element-wise fast diagonalisation + coarse correction on the element constants
-int precondition(nsb_sem_t S, int precond, const int *done, const double *r, double *z, int grid, double *partial) {
+int precondition(nsb_sem_t S, int precond, const int *done, const double *r, double *z, int grid, double *partial,
+                 double tol) {
   nsb_context_t ctx = S->ctx;
   cudaStream_t st = ctx->stream;
   const NsDims d = ns_dims(S);
@@ -878,13 +902,16 @@ int precondition(nsb_sem_t S, int precond, const int *done, const double *r, dou
   fdm_kernel<<<(unsigned)S->nel, NT_NS, fdm_smem(S), st>>>(d, done, r, S->fdm_S_d, S->fdm_lam_d, S->fdm_c_d, z, rr);
   ctx->launches++;
   const bool coarse = S->cc_nnz > 0 && !ctx->ns_no_coarse;
+  // the coarse solve is part of a preconditioner CG takes for a fixed linear map: two orders below the outer
+  // tolerance, at most 1e-6, at least 1e-10
+  const double ctol = std::max(1e-10, std::min(1e-6, 1e-2 * tol));
   if (coarse) {
     cc_sum_kernel<<<nb, NT_NS, 0, st>>>(done, rr, n, pa);
     cc_init_kernel<<<nb, NT_NS, 0, st>>>(done, rr, n, pa, S->cc_dinv_d, xc, rc, pc, pb, cs);
     ctx->launches += 2;
     for (int it = 0; it < S->cc_launch; ++it) {
-      cc_dir_kernel<<<nb, NT_NS, 0, st>>>(done, cs, it, rc, S->cc_dinv_d, n, pc, pb, 1e-10);
-      cc_spmv_kernel<<<nb, NT_NS, 0, st>>>(done, cs, S->cc_rowptr_d, S->cc_col_d, S->cc_val_d, pc, n, wc, pa);
+      cc_dir_kernel<<<nb, NT_NS, 0, st>>>(done, cs, it, rc, S->cc_dinv_d, n, pc, pb, ctol);
+      cc_spmv_kernel<<<nb, NT_NS, 0, st>>>(done, cs, S->cc_width, S->cc_col_d, S->cc_val_d, pc, n, wc, pa);
       cc_update_kernel<<<nb, NT_NS, 0, st>>>(done, cs, it, pc, wc, S->cc_dinv_d, n, xc, rc, pa, pb);
       ctx->launches += 3;
     }
@@ -929,15 +956,15 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
   double *sum_rhs = nullptr;
   if (mean_free) {   // mean of the right-hand side over all ranks -> sums[3], read by the init kernel
     sum_kernel<<<grid, NT_NS, 0, st>>>(rhs, n2, partial);
-    reduce_rows_kernel<<<1, 32, 0, st>>>(partial, grid, 1, sums + 3, nullptr);
+    reduce_rows_kernel<<<1, NT_NS, 0, st>>>(partial, grid, 1, sums + 3, nullptr);
     ctx->launches += 2;
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 3, 1));
     sum_rhs = sums + 3;
   }
   pcg_init_kernel<<<grid, NT_NS, 0, st>>>(rhs, n2, sum_rhs, ntot, mean_free, r, x, p);
   ctx->launches++;
-  NSB_CHECK(precondition(S, precond, done, r, z, grid, partial));
-  reduce_rows_kernel<<<3, 32, 0, st>>>(partial, grid, 3, sums + 1, nullptr);
+  NSB_CHECK(precondition(S, precond, done, r, z, grid, partial, tol));
+  reduce_rows_kernel<<<3, NT_NS, 0, st>>>(partial, grid, 3, sums + 1, nullptr);
   ctx->launches++;
   if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 1, 3));
   pcg_after_r_kernel<<<1, 1, 0, st>>>(state, tol, 1);
@@ -950,14 +977,14 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
     ctx->launches++;
     NSB_CHECK(launch_binv_gradt(S, p, wv, fs, nullptr, 0.0, 1.0, done));           // wv = B^-1 D^T p
     NSB_CHECK(launch_opdiv(S, wv, fs, 1.0, w, p, partial, done));                 // w = D wv, partial (w, p)
-    reduce_rows_kernel<<<1, 32, 0, st>>>(partial, (int)S->nel, 1, sums, done);
+    reduce_rows_kernel<<<1, NT_NS, 0, st>>>(partial, (int)S->nel, 1, sums, done);
     ctx->launches++;
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums, 1));
     pcg_after_w_kernel<<<1, 1, 0, st>>>(state);
     pcg_xr_kernel<<<grid, NT_NS, 0, st>>>(state, p, w, x, r, n2);
     ctx->launches += 2;
-    NSB_CHECK(precondition(S, precond, done, r, z, grid, partial));
-    reduce_rows_kernel<<<3, 32, 0, st>>>(partial, grid, 3, sums + 1, done);
+    NSB_CHECK(precondition(S, precond, done, r, z, grid, partial, tol));
+    reduce_rows_kernel<<<3, NT_NS, 0, st>>>(partial, grid, 3, sums + 1, done);
     ctx->launches++;
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums + 1, 3));
     pcg_after_r_kernel<<<1, 1, 0, st>>>(state, tol, 0);
@@ -1065,8 +1092,10 @@ extern "C" int nsb_sem_pressure_setup(nsb_sem_t S) {
   NSB_CUDA(cudaMemcpyAsync(w3_d, w3.data(), sizeof(double) * n2e, cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemsetAsync(S->ns_state_d, 0, sizeof(PcgP), st));
   const size_t smem = ns_smem(S);
-  NSB_CUDA(cudaFuncSetAttribute(opdiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NSB_CUDA(cudaFuncSetAttribute(opgradt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(opdiv_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(opgradt_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(opdiv_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NSB_CUDA(cudaFuncSetAttribute(opgradt_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NSB_CUDA(cudaFuncSetAttribute(map12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (S->nel > 0) {
     const NsDims d = ns_dims(S);

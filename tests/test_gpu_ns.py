@@ -96,8 +96,11 @@ def test_pressure_metrics_and_div_gradt(ctx, nel, N):
 
 
 @pytest.mark.parametrize('nel,N', [((2, 2, 2), 7), ((2, 2, 2), 4), ((3, 3), 5)])
-def test_consistent_poisson_operator_and_solve(ctx, nel, N):
-    P = NsProblem(nel, N, seed=20 + N)
+@pytest.mark.parametrize('mean_free', [False, True])
+def test_consistent_poisson_operator_and_solve(ctx, nel, N, mean_free):
+    # mean_free (Nek's ortho) belongs to affine elements, where E 1 = 0 exactly; on deformed ones E is regular and
+    # removing the mean leaves an O(1e-6) inconsistency at which the residual of any preconditioned iteration stalls
+    P = NsProblem(nel, N, deform=0.0 if mean_free else 0.04, seed=20 + N)
     sem, lay, B = P.gpu(ctx, 3)
     zero = [0 * P.coords[0]] * P.dim
     p = P.pres()
@@ -108,22 +111,20 @@ def test_consistent_poisson_operator_and_solve(ctx, nel, N):
     assert relerr(Ep, ref) <= 1e-12
     # E x = E p with both preconditioners, against the oracle's iteration with the same preconditioner
     fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv)
+    its = {}
     for precond in (0, 1):
-        for mean_free in (False, True):
-            xo, ito, dropo = ons.esolve(ref, P.ps, P.glo, P.mask, P.binv, tol=1e-11, maxit=3000, mean_free=mean_free,
-                                        fdm=fd if precond else None)
-            P.up(B[1], zero, ref)
-            it, drop = sem.esolve(B[1], B[2], tol=1e-11, maxit=3000, mean_free=mean_free, precond=precond)
-            _, x = P.down(B[2])
-            # precond 1: the device solves the coarse problem by CG to 1e-10, the oracle by a pseudo-inverse: the
-            # iteration counts agree to a few per cent, the solutions to the tolerance
-            assert abs(it - ito) <= (3 if precond == 0 else 3 + 0.12 * ito) and drop <= 1e-11, (precond, mean_free, it, ito, drop)
-            # the constant is the (near-)null vector of E: its coefficient is not determined to the solver tolerance
-            assert relerr(x - x.mean(), xo - xo.mean()) <= 1e-8
-            if precond == 1 and mean_free:
-                assert it < 0.6 * it_diag, 'the two-level preconditioner should at least halve the iteration count'
-            if precond == 0 and mean_free:
-                it_diag = it
+        xo, ito, dropo = ons.esolve(ref, P.ps, P.glo, P.mask, P.binv, tol=1e-11, maxit=3000, mean_free=mean_free,
+                                    fdm=fd if precond else None)
+        P.up(B[1], zero, ref)
+        it, drop = sem.esolve(B[1], B[2], tol=1e-11, maxit=3000, mean_free=mean_free, precond=precond)
+        _, x = P.down(B[2])
+        # precond 1: the device solves the coarse problem by CG to 1e-10, the oracle by a pseudo-inverse: the
+        # iteration counts agree to a few per cent, the solutions to the tolerance
+        assert abs(it - ito) <= (3 if precond == 0 else 3 + 0.12 * ito) and drop <= 1e-11, (precond, it, ito, drop)
+        # the constant is the (near-)null vector of E: its coefficient is not determined to the solver tolerance
+        assert relerr(x - x.mean(), xo - xo.mean()) <= 1e-8
+        its[precond] = it
+    assert its[1] < 0.6 * its[0], 'the two-level preconditioner should at least halve the iteration count'
     for o in (B, lay, sem):
         o.close()
 
