@@ -372,6 +372,8 @@ class Sem:
         self.N, self.lx = N, N + 1
         self.shape = x.shape
         self.nel = x.shape[0]
+        if glo_num is None:
+            raise ValueError('Sem: glo_num (Nek\'s global node numbering of every local point) is required')
         glo = np.ascontiguousarray(glo_num, dtype=np.int64)
         h = C.c_void_p()
         check(self.lib.nsb_sem_create(ctx.h, self.dim, N, self.nel, _dp(x), _dp(_f64(y)),

@@ -7,6 +7,7 @@ OUT=gpurun_out/${1:-r2ev}
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee $OUT/summary.txt
 tail -3 $OUT/pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt
 timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
 timeout 600 python bench.py --impl reference > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?" | tee -a $OUT/summary.txt
 # launch list: per-launch gpu time of the same command (serialised, cold cache: shares only)
@@ -22,4 +23,6 @@ echo "ncu full rc=$?" | tee -a $OUT/summary.txt
 ncu -i $OUT/prof_hot_k100.ncu-rep --page raw --csv \
   --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active \
   > $OUT/hot_k100_raw.csv 2>/dev/null
+timeout 300 python profiles/run_ns_stepper.py --nelx 32 --nsteps 3 2>&1 | grep -v "^\[build" > $OUT/run_ns_stepper_32.txt
+timeout 300 python profiles/run_ns_stepper.py --nelx 16 --nsteps 5 2>&1 | grep -v "^\[build" > $OUT/run_ns_stepper_16.txt
 cat $OUT/summary.txt
