@@ -29,6 +29,7 @@ unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
 classes = [('axhelm3d', 'axhelm', None), ('gs_kernel', 'gather_scatter', None),
            ('multidot_kernel', 'multidot', 8.0 * n * (k + 2)),
            ('fused_', 'fused_update_dot', 8.0 * (n * (k + 2) + n)),
+           ('update_kernel<2', 'update', 8.0 * n * (k + 2)),          # third sweep with the folded normalisation: no W
            ('update_kernel', 'update', 8.0 * (n * (k + 2) + n)),
            ('normalize_kernel', 'normalize', 16.0 * n)]
 rows = list(csv.reader(open(a.csv)))
