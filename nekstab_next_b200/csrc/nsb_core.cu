@@ -151,6 +151,7 @@ extern "C" int nsb_init(int device, int rank, int nranks, const void *unique_id,
   if (const char *e = getenv("NSB_NO_FUSED")) ctx->no_fused = e[0] == '1';
   if (const char *e = getenv("NSB_FOLD_NORM")) ctx->fold_norm = e[0] != '0';
   if (const char *e = getenv("NSB_NS_NO_COARSE")) ctx->ns_no_coarse = e[0] == '1';
+  if (const char *e = getenv("NSB_NS_GENERIC")) ctx->ns_generic = e[0] == '1';
   if (const char *e = getenv("NSB_FUSED_LOADER")) ctx->fused_loader = atoi(e);
   if (const char *e = getenv("NSB_FUSED_RC")) ctx->fused_rc = atoi(e);
   if (const char *e = getenv("NSB_FUSED_REG_MIN_K")) ctx->fused_reg_min_k = atoi(e);

@@ -92,6 +92,7 @@ struct nsb_context_s {
   bool pipeline_upload = true;   // NSB_PIPELINE_UPLOAD=0: plain upload, then the usual first sweep
   // per-kernel-class device timing (bench / roofline): events around every launch when enabled
   bool no_fused = false;       // NSB_NO_FUSED=1: CGS2 with separate update / multidot kernels
+  bool ns_generic = false;     // NSB_NS_GENERIC=1: generic opdiv / opgradt kernels, multi-launch coarse solve (A/B numbers)
   bool ns_no_coarse = false;   // NSB_NS_NO_COARSE=1: pressure preconditioner without the coarse level (A/B numbers)
   bool fold_norm = true;       // NSB_FOLD_NORM=0: explicit norm reduction in the third sweep + normalize_kernel
   int fused_loader = 3;        // NSB_FUSED_LOADER: 1 cp.async, 3 TMA 2-D tensor loads (default)
@@ -225,6 +226,7 @@ struct nsb_sem_s {
   int *cc_rowptr_d = nullptr, *cc_col_d = nullptr;   // coarse operator (one constant per element), CSR
   double *cc_val_d = nullptr, *cc_dinv_d = nullptr, *cc_vec_d = nullptr, *cc_partial_d = nullptr, *cc_state_d = nullptr;
   int64_t cc_nnz = 0;
+  bool cc_coop = false;                       // the coarse solve runs as one cooperative kernel
   int cc_width = 0;                           // ELL width of the coarse operator
   int cc_maxit = 400;                         // most coarse CG iterations enqueued per application
   int cc_launch = 400;                        // currently enqueued (stops early on the device; adapted at every poll)

@@ -23,7 +23,10 @@
 #include "nsb_quadrature.h"
 #include "nsb_device.cuh"
 
+#include <cooperative_groups.h>
+
 using namespace nsb;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -200,6 +203,218 @@ opgradt_kernel(NsDims d, const double *__restrict__ p, const double *__restrict_
         ob[t] = bnd ? v : (ui ? alpha * ui[t] : 0.0) + beta * bmask[e * d.n1e + t] * v;
       }
     }
+  }
+}
+
+// ---- (lx1, lx2) = (8, 6), 3-D: line-per-thread formulation ---------------------------------------------------
+// The generic kernels above spend their time in shared memory (two loads per FMA, one point per thread per stage).
+// Here a thread owns a whole grid line: the eight / six values of the line sit in registers, the interpolation and
+// derivative matrices come from constant memory (warp-uniform index: broadcast), and shared memory only carries the
+// intermediates from one direction to the next -- an order of magnitude fewer shared-memory accesses.  Two elements
+// per CTA, 64 threads each: 64 (k, j) lines in r, 48 (k, I) lines in s, 36 (J, I) lines in t.
+__constant__ double c_I12[48], c_D12[48];   // [6][8] row-major, N = 7
+
+constexpr int T8_NT = 128, T8_EPC = 2;
+constexpr int T8_AB = 8 * 8 * 6, T8_C = 8 * 6 * 6;
+constexpr int T8_SMEM = T8_EPC * (2 * T8_AB + 3 * T8_C);   // doubles
+
+__global__ void __launch_bounds__(T8_NT)
+opdiv8_kernel(int64_t nel, const double *__restrict__ vel, int64_t fs, const double *__restrict__ rx2, int64_t n2,
+              double scale, double *__restrict__ out, const double *__restrict__ dotw,
+              double *__restrict__ dot_partial, const int *__restrict__ done) {
+  if (done && *done) return;
+  __shared__ double sm[T8_SMEM];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int64_t e = (int64_t)blockIdx.x * T8_EPC + g;
+  const bool live = e < nel;
+  double *A = sm + g * (2 * T8_AB + 3 * T8_C), *B = A + T8_AB, *AA = B + T8_AB, *AD = AA + T8_C, *BA = AD + T8_C;
+  double acc[6];
+#pragma unroll
+  for (int K = 0; K < 6; ++K) acc[K] = 0.0;
+  for (int b = 0; b < 3; ++b) {
+    if (live) {   // r: line (k, j) = t
+      const double2 *up = reinterpret_cast<const double2 *>(vel + (int64_t)b * fs + e * 512 + t * 8);
+      double u[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2 v = up[q];
+        u[2 * q] = v.x;
+        u[2 * q + 1] = v.y;
+      }
+#pragma unroll
+      for (int I = 0; I < 6; ++I) {
+        double a = 0.0, d = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a = fma(c_I12[I * 8 + i], u[i], a);
+          d = fma(c_D12[I * 8 + i], u[i], d);
+        }
+        A[t * 6 + I] = a;
+        B[t * 6 + I] = d;
+      }
+    }
+    __syncthreads();
+    if (live && t < 48) {   // s: line (k, I)
+      const int k = t / 6, I = t % 6;
+      double a[8], d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = A[(k * 8 + j) * 6 + I];
+        d[j] = B[(k * 8 + j) * 6 + I];
+      }
+#pragma unroll
+      for (int J = 0; J < 6; ++J) {
+        double aa = 0.0, ad = 0.0, ba = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          aa = fma(c_I12[J * 8 + j], a[j], aa);
+          ad = fma(c_D12[J * 8 + j], a[j], ad);
+          ba = fma(c_I12[J * 8 + j], d[j], ba);
+        }
+        AA[(k * 6 + J) * 6 + I] = aa;
+        AD[(k * 6 + J) * 6 + I] = ad;
+        BA[(k * 6 + J) * 6 + I] = ba;
+      }
+    }
+    __syncthreads();
+    if (live && t < 36) {   // t: line (J, I); point (K, J, I) = K * 36 + t
+      double aa[8], ad[8], ba[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        aa[k] = AA[k * 36 + t];
+        ad[k] = AD[k * 36 + t];
+        ba[k] = BA[k * 36 + t];
+      }
+      const double *r0 = rx2 + (int64_t)(0 * 3 + b) * n2 + e * 216 + t;
+      const double *r1 = rx2 + (int64_t)(1 * 3 + b) * n2 + e * 216 + t;
+      const double *r2 = rx2 + (int64_t)(2 * 3 + b) * n2 + e * 216 + t;
+#pragma unroll
+      for (int K = 0; K < 6; ++K) {
+        double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          ur = fma(c_I12[K * 8 + k], ba[k], ur);
+          us = fma(c_I12[K * 8 + k], ad[k], us);
+          ut = fma(c_D12[K * 8 + k], aa[k], ut);
+        }
+        acc[K] += r0[K * 36] * ur + r1[K * 36] * us + r2[K * 36] * ut;
+      }
+    }
+    __syncthreads();
+  }
+  double dot = 0.0;
+  if (live && t < 36) {
+#pragma unroll
+    for (int K = 0; K < 6; ++K) {
+      const int64_t q = e * 216 + K * 36 + t;
+      const double v = scale * acc[K];
+      out[q] = v;
+      if (dotw) dot += v * dotw[q];
+    }
+  }
+  if (dot_partial) {
+    dot = block_reduce_sum<T8_NT>(dot);
+    if (threadIdx.x == 0) dot_partial[blockIdx.x] = dot;
+  }
+}
+
+__global__ void __launch_bounds__(T8_NT)
+opgradt8_kernel(int64_t nel, const double *__restrict__ p, const double *__restrict__ rx2, int64_t n2, double *out,
+                int64_t fs, int epi, const double *uin, double alpha, double beta, const double *__restrict__ bmask,
+                const int *__restrict__ done) {
+  if (done && *done) return;
+  __shared__ double sm[T8_SMEM];
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int64_t e = (int64_t)blockIdx.x * T8_EPC + g;
+  const bool live = e < nel;
+  double *A = sm + g * (2 * T8_AB + 3 * T8_C), *B = A + T8_AB, *AA = B + T8_AB, *AD = AA + T8_C, *BA = AD + T8_C;
+  double pq[6];
+  if (live && t < 36) {
+#pragma unroll
+    for (int K = 0; K < 6; ++K) pq[K] = p[e * 216 + K * 36 + t];
+  }
+  for (int b = 0; b < 3; ++b) {
+    if (live && t < 36) {   // t, transposed: line (J, I)
+      const double *r0 = rx2 + (int64_t)(0 * 3 + b) * n2 + e * 216 + t;
+      const double *r1 = rx2 + (int64_t)(1 * 3 + b) * n2 + e * 216 + t;
+      const double *r2 = rx2 + (int64_t)(2 * 3 + b) * n2 + e * 216 + t;
+      double gr[6], gs[6], gt[6];
+#pragma unroll
+      for (int K = 0; K < 6; ++K) {
+        gr[K] = r0[K * 36] * pq[K];
+        gs[K] = r1[K * 36] * pq[K];
+        gt[K] = r2[K * 36] * pq[K];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        double ba = 0.0, ad = 0.0, aa = 0.0;
+#pragma unroll
+        for (int K = 0; K < 6; ++K) {
+          ba = fma(c_I12[K * 8 + k], gr[K], ba);
+          ad = fma(c_I12[K * 8 + k], gs[K], ad);
+          aa = fma(c_D12[K * 8 + k], gt[K], aa);
+        }
+        BA[k * 36 + t] = ba;
+        AD[k * 36 + t] = ad;
+        AA[k * 36 + t] = aa;
+      }
+    }
+    __syncthreads();
+    if (live && t < 48) {   // s, transposed: line (k, I)
+      const int k = t / 6, I = t % 6;
+      double ba[6], ad[6], aa[6];
+#pragma unroll
+      for (int J = 0; J < 6; ++J) {
+        ba[J] = BA[(k * 6 + J) * 6 + I];
+        ad[J] = AD[(k * 6 + J) * 6 + I];
+        aa[J] = AA[(k * 6 + J) * 6 + I];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double bb = 0.0, a = 0.0;
+#pragma unroll
+        for (int J = 0; J < 6; ++J) {
+          bb = fma(c_I12[J * 8 + j], ba[J], bb);
+          a = fma(c_D12[J * 8 + j], ad[J], a);
+          a = fma(c_I12[J * 8 + j], aa[J], a);
+        }
+        B[(k * 8 + j) * 6 + I] = bb;
+        A[(k * 8 + j) * 6 + I] = a;
+      }
+    }
+    __syncthreads();
+    if (live) {   // r, transposed: line (k, j) = t, then the epilogue on its eight points
+      double bb[6], a[6];
+#pragma unroll
+      for (int I = 0; I < 6; ++I) {
+        bb[I] = B[t * 6 + I];
+        a[I] = A[t * 6 + I];
+      }
+      const int j = t & 7, k = t >> 3;
+      const bool edge_line = j == 0 || j == 7 || k == 0 || k == 7;
+      double *ob = out + (int64_t)b * fs + e * 512 + t * 8;
+      const double *ui = uin ? uin + (int64_t)b * fs + e * 512 + t * 8 : nullptr;
+      const double *bm = bmask + e * 512 + t * 8;
+      double w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int I = 0; I < 6; ++I) {
+          v = fma(c_D12[I * 8 + i], bb[I], v);
+          v = fma(c_I12[I * 8 + i], a[I], v);
+        }
+        if (epi == 0) {
+          v = (ui ? alpha * ui[i] : 0.0) + beta * v;
+        } else if (!(edge_line || i == 0 || i == 7)) {
+          v = (ui ? alpha * ui[i] : 0.0) + beta * bm[i] * v;
+        }
+        w[i] = v;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<double2 *>(ob)[q] = make_double2(w[2 * q], w[2 * q + 1]);
+    }
+    __syncthreads();
   }
 }
 
@@ -450,13 +665,15 @@ struct CcState {
 };
 
 // every CTA sums the [n][3] partials in the same fixed order: identical scalars everywhere, no extra launch
-__device__ __forceinline__ void sum_partials3(const double *__restrict__ partial, int n, double (&out)[3]) {
+// (loads with .cg: inside the cooperative kernel the partials are rewritten by other CTAs between grid barriers, so
+// they must come from L2, never from a stale L1 line or the non-coherent path)
+__device__ __forceinline__ void sum_partials3(const double *partial, int n, double (&out)[3]) {
   __shared__ double red[3][NT_NS / 32];
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s0 += partial[3 * i];
-    s1 += partial[3 * i + 1];
-    s2 += partial[3 * i + 2];
+    s0 += __ldcg(partial + 3 * i);
+    s1 += __ldcg(partial + 3 * i + 1);
+    s2 += __ldcg(partial + 3 * i + 2);
   }
   s0 = warp_reduce_sum(s0);
   s1 = warp_reduce_sum(s1);
@@ -590,6 +807,59 @@ cc_update_kernel(const int *__restrict__ odone, const CcState *st, int it, const
   store_partials3(partial_rz, ri * zi, zi, ri);
 }
 
+// The whole coarse solve as ONE cooperative kernel: a thread owns a row, its x / r / p entries stay in registers, p is
+// published for the product, and the three reductions of an iteration are grid-wide barriers instead of kernel
+// boundaries (the multi-launch version above spends 14 us per iteration on three 4-5 us launches; it remains for
+// grids that are not co-resident).  Same arithmetic, same fixed summation order: every CTA forms identical scalars,
+// so every thread of the grid takes the same exits.
+__global__ void __launch_bounds__(NT_NS)
+cc_solve_kernel(const int *__restrict__ odone, CcState *st, int width, const int *__restrict__ col,
+                const double *__restrict__ val, const double *__restrict__ dinv, const double *__restrict__ rc, int n,
+                double *__restrict__ x, double *p, double *pa, double *pb, double tol, int maxit) {
+  cg::grid_group grid = cg::this_grid();
+  if (*odone) return;                       // the same word for the whole grid, written by an earlier kernel
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  double s[3];
+  store_partials3(pa, live ? rc[i] : 0.0, 0.0, 0.0);
+  grid.sync();
+  sum_partials3(pa, gridDim.x, s);
+  const double di = live ? dinv[i] : 0.0;
+  double ri = live ? rc[i] - s[0] / n : 0.0, xi = 0.0, pi = 0.0;
+  store_partials3(pb, ri * di * ri, di * ri, ri);
+  grid.sync();
+  double rtz_old = 1.0, rtz0 = 0.0;
+  int it = 0;
+  for (; it < maxit; ++it) {
+    sum_partials3(pb, gridDim.x, s);
+    const double mz = s[1] / n, rtzn = s[0] - mz * s[2];
+    if (it == 0) rtz0 = rtzn;
+    if (!(rtzn > tol * tol * rtz0) || !(rtz_old > 0.0)) break;
+    const double beta = it == 0 ? 0.0 : rtzn / rtz_old;
+    pi = fma(beta, pi, di * ri - mz);
+    if (live) p[i] = pi;
+    grid.sync();                             // p complete
+    double wi = 0.0;
+    if (live)
+      for (int k = 0; k < width; ++k) wi = fma(val[(size_t)k * n + i], __ldcg(p + col[(size_t)k * n + i]), wi);
+    store_partials3(pa, live ? wi * pi : 0.0, 0.0, 0.0);
+    grid.sync();
+    sum_partials3(pa, gridDim.x, s);
+    if (!(s[0] > 0.0)) break;
+    const double alpha = rtzn / s[0];
+    xi = fma(alpha, pi, xi);
+    ri = fma(-alpha, wi, ri);
+    store_partials3(pb, ri * di * ri, di * ri, ri);
+    grid.sync();
+    rtz_old = rtzn;
+  }
+  if (live) x[i] = xi;
+  if (i == 0) {
+    st->it = it;
+    st->done = 1;
+  }
+}
+
 // out = a + c * b on n entries (pressure update p* + dp, extrapolation 2 p - plag)
 __global__ void lin2_kernel(double *__restrict__ out, const double *__restrict__ a, double ca, const double *__restrict__ b,
                             double cb, int64_t n) {
@@ -609,12 +879,20 @@ NsDims ns_dims(nsb_sem_t S) {
 
 size_t ns_smem(nsb_sem_t S) { return sizeof(double) * ns_smem_doubles(S->dim, S->lx, S->lx2); }
 
+// rows of dot partials an opdiv launch writes
+int opdiv_rows(nsb_sem_t S) {
+  return (S->lx == 8 && S->dim == 3 && !S->ctx->ns_generic) ? (int)((S->nel + T8_EPC - 1) / T8_EPC) : (int)S->nel;
+}
+
 int launch_opdiv(nsb_sem_t S, const double *vel, int64_t fs, double scale, double *out, const double *dotw,
                  double *dot_partial, const int *done) {
   nsb_context_t ctx = S->ctx;
   // algorithmic bytes: dim velocity fields and dim^2 metric arrays read, one pressure array written
   ProfScope ps(ctx, PC_AXHELM, 8.0 * ((double)S->dim * S->npts + ((double)S->dim * S->dim + 1.0) * S->n2));
-  if (S->lx == 8 && S->dim == 3)
+  if (S->lx == 8 && S->dim == 3 && !ctx->ns_generic)
+    opdiv8_kernel<<<(unsigned)((S->nel + T8_EPC - 1) / T8_EPC), T8_NT, 0, ctx->stream>>>(S->nel, vel, fs, S->rx2_d, S->n2,
+                                                                                       scale, out, dotw, dot_partial, done);
+  else if (S->lx == 8 && S->dim == 3)
     opdiv_kernel<8, 3><<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), vel, fs, S->rx2_d, S->n2, S->i12_d,
                                                                             S->d12_d, scale, out, dotw, dot_partial, done);
   else
@@ -629,7 +907,10 @@ int launch_opgradt(nsb_sem_t S, const double *p, double *out, int64_t fs, int ep
                    double beta, const int *done) {
   nsb_context_t ctx = S->ctx;
   ProfScope ps(ctx, PC_AXHELM, 8.0 * ((double)S->dim * S->npts * (uin ? 2.0 : 1.0) + ((double)S->dim * S->dim + 1.0) * S->n2));
-  if (S->lx == 8 && S->dim == 3)
+  if (S->lx == 8 && S->dim == 3 && !ctx->ns_generic)
+    opgradt8_kernel<<<(unsigned)((S->nel + T8_EPC - 1) / T8_EPC), T8_NT, 0, ctx->stream>>>(
+        S->nel, p, S->rx2_d, S->n2, out, fs, epi, uin, alpha, beta, S->bmask_d, done);
+  else if (S->lx == 8 && S->dim == 3)
     opgradt_kernel<8, 3><<<(unsigned)S->nel, NT_NS, ns_smem(S), ctx->stream>>>(ns_dims(S), p, S->rx2_d, S->n2, S->i12_d,
                                                                               S->d12_d, out, fs, epi, uin, alpha, beta,
                                                                               S->bmask_d, done);
@@ -872,6 +1153,11 @@ int fdm_setup(nsb_sem_t S) {
   NSB_CUDA(cudaMemcpyAsync(S->cc_dinv_d, dinv.data(), sizeof(double) * std::max(n, 1), cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemsetAsync(S->cc_state_d, 0, sizeof(CcState), st));
   NSB_CUDA(cudaStreamSynchronize(st));
+  // the one-kernel coarse solve needs the whole grid resident at once
+  int coop = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cc_solve_kernel, NT_NS, 0);
+  S->cc_coop = coop && nb >= 1 && nb <= per_sm * ctx->num_sms;
   return NSB_OK;
 }
 
@@ -905,7 +1191,16 @@ int precondition(nsb_sem_t S, int precond, const int *done, const double *r, dou
   // the coarse solve is part of a preconditioner CG takes for a fixed linear map: two orders below the outer
   // tolerance, at most 1e-6, at least 1e-10
   const double ctol = std::max(1e-10, std::min(1e-6, 1e-2 * tol));
-  if (coarse) {
+  if (coarse && S->cc_coop && !ctx->ns_generic) {
+    int width = S->cc_width, nn = n, mx = S->cc_maxit;
+    double tl = ctol;
+    const int *colp = S->cc_col_d;
+    const double *valp = S->cc_val_d, *dinvp = S->cc_dinv_d, *rrp = rr;
+    void *args[] = {(void *)&done, (void *)&cs, (void *)&width, (void *)&colp, (void *)&valp, (void *)&dinvp, (void *)&rrp,
+                    (void *)&nn, (void *)&xc, (void *)&pc, (void *)&pa, (void *)&pb, (void *)&tl, (void *)&mx};
+    NSB_CUDA(cudaLaunchCooperativeKernel((void *)cc_solve_kernel, dim3(nb), dim3(NT_NS), args, 0, st));
+    ctx->launches++;
+  } else if (coarse) {
     cc_sum_kernel<<<nb, NT_NS, 0, st>>>(done, rr, n, pa);
     cc_init_kernel<<<nb, NT_NS, 0, st>>>(done, rr, n, pa, S->cc_dinv_d, xc, rc, pc, pb, cs);
     ctx->launches += 2;
@@ -977,7 +1272,7 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
     ctx->launches++;
     NSB_CHECK(launch_binv_gradt(S, p, wv, fs, nullptr, 0.0, 1.0, done));           // wv = B^-1 D^T p
     NSB_CHECK(launch_opdiv(S, wv, fs, 1.0, w, p, partial, done));                 // w = D wv, partial (w, p)
-    reduce_rows_kernel<<<1, NT_NS, 0, st>>>(partial, (int)S->nel, 1, sums, done);
+    reduce_rows_kernel<<<1, NT_NS, 0, st>>>(partial, opdiv_rows(S), 1, sums, done);
     ctx->launches++;
     if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, sums, 1));
     pcg_after_w_kernel<<<1, 1, 0, st>>>(state);
@@ -993,7 +1288,7 @@ int esolve_d(nsb_sem_t S, const double *rhs, double *x, double tol, int maxit, i
     if (it % 8 == 0 || it == maxit) {
       NSB_CUDA(cudaMemcpyAsync(hst, state, sizeof(PcgP), cudaMemcpyDeviceToHost, st));
       CcState *hcs = reinterpret_cast<CcState *>(hst + 1);
-      const bool two_level = precond == 1 && S->cc_nnz > 0 && !ctx->ns_no_coarse;
+      const bool two_level = precond == 1 && S->cc_nnz > 0 && !ctx->ns_no_coarse && !(S->cc_coop && !ctx->ns_generic);
       if (two_level) NSB_CUDA(cudaMemcpyAsync(hcs, S->cc_state_d, sizeof(CcState), cudaMemcpyDeviceToHost, st));
       NSB_CUDA(cudaStreamSynchronize(st));
       if (hst->done) break;
@@ -1087,6 +1382,10 @@ extern "C" int nsb_sem_pressure_setup(nsb_sem_t S) {
     return fail("out of device memory");
   S->lx2 = l2;
   cudaStream_t st = ctx->stream;
+  if (l1 == 8) {   // constant-memory copies for the line-per-thread kernels (the values depend on N only)
+    NSB_CUDA(cudaMemcpyToSymbol(c_I12, I12.data(), sizeof(double) * 48));
+    NSB_CUDA(cudaMemcpyToSymbol(c_D12, D12.data(), sizeof(double) * 48));
+  }
   NSB_CUDA(cudaMemcpyAsync(S->i12_d, I12.data(), sizeof(double) * l2 * l1, cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemcpyAsync(S->d12_d, D12.data(), sizeof(double) * l2 * l1, cudaMemcpyHostToDevice, st));
   NSB_CUDA(cudaMemcpyAsync(w3_d, w3.data(), sizeof(double) * n2e, cudaMemcpyHostToDevice, st));
