@@ -78,9 +78,10 @@ def main():
                 t = torch.tensor([ms], dtype=torch.float64, device='cuda')
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
-            # algorithmic bytes of one CGS2 step with the fused middle sweep: 3 sweeps over V
+            # algorithmic bytes of one CGS2 step: three sweeps over V -- multidot 8 n (k+2), fused update+multidot+norm
+            # 8 n (k+3), update with the folded normalisation 8 n (k+2); no separate normalisation pass
             nn = nM * 1e6
-            bytes_alg = 8.0 * nn * (3 * k + 9)
+            bytes_alg = 8.0 * nn * (3 * k + 7)
             rows.append(dict(n_mdof=nM, k=k, feasible=True, cgs2_ms=round(ms, 4),
                              gbs_per_gpu=round(bytes_alg / world / (ms * 1e-3) / 1e9, 1),
                              gdof_per_s=round(nn / (ms * 1e-3) / 1e9, 3)))
@@ -91,8 +92,8 @@ def main():
     if rank == 0:
         out = dict(metric='cgs2_step_ms', n_gpus=world, dtype='f64', rows=rows,
                    note='one CGS2 orthonormalisation of a vector against k columns (multidot, fused '
-                        'update+multidot, update+norm, normalize; 3 all-reduces when n_gpus > 1); '
-                        'gbs_per_gpu = 8 n (3k+9) / n_gpus / time')
+                        'update+multidot+norm, update with the folded normalisation; 2 all-reduces when n_gpus > 1; '
+                        'k beyond the fused kernels: unfused pair + normalize); gbs_per_gpu = 8 n (3k+7) / n_gpus / time')
         s = json.dumps(out)
         if a.out:
             Path(a.out).write_text(s)

@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(NT) orth_post_kernel(const __grid_constant__ O
 // w *= 1/sqrt(nrm2[0]);  h_out[k] = sqrt(nrm2[0])   (k_normalize, core/krylov_subspace.f90:75-92)
 __global__ void __launch_bounds__(NT)
 normalize_kernel(double2 *__restrict__ w, int64_t n2, const double *__restrict__ nrm2,
-                 double *__restrict__ hk, double *__restrict__ keep) {
+                 double *__restrict__ hk, double *__restrict__ keep, const int *__restrict__ skip_if_set) {
+  if (skip_if_set && *skip_if_set) return;   // DGKS, second projection kept: the third sweep normalised already
   const double beta = sqrt(nrm2[0]);
   const double inv = 1.0 / beta;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1313,14 +1314,15 @@ int launch_fused(nsb_context_t ctx, const double *V, int64_t ld, int k, const do
   return finish_tail(ctx, tail, grid);
 }
 
-int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm2_d, double *hk_d) {
+int launch_normalize(nsb_context_t ctx, double *w, int64_t ld, const double *nrm2_d, double *hk_d,
+                     const int *skip_if_set = nullptr) {
   int64_t n2 = ld / 2;
   int64_t want = (n2 + 1023) / 1024;
   int64_t cap = (int64_t)ctx->num_sms * 16;
   int grid = (int)(want < cap ? want : cap);
   ProfScope ps(ctx, PC_NORMALIZE, 16.0 * ld);
   normalize_kernel<<<grid, NT, 0, ctx->stream>>>(reinterpret_cast<double2 *>(w), n2, nrm2_d, hk_d,
-                                                 ctx->hvec_d + 3 * (kMaxK + 8) + 3);
+                                                 ctx->hvec_d + 3 * (kMaxK + 8) + 3, skip_if_set);
   ctx->launches += 1;
   NSB_CUDA(cudaGetLastError());
   return NSB_OK;
@@ -1457,6 +1459,9 @@ int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so)
     // instead of three and no normalize_kernel.  Not with the streamed download (it sends w'' before beta is
     // needed) and not in DGKS mode (whether a second projection happens is decided by the same reduction).
     const bool fold = fused && !dgks && !so && ctx->fold_norm;
+    // DGKS: the same fold when the second projection is kept; when it is dropped beta = |w'| and only the
+    // normalisation pass runs (the sweep and the pass read the decision flag and one of them exits at once)
+    const bool fold_dgks = fused && dgks && !so && ctx->fold_norm;
     if (!have_h1) {
       TailSpec sp;
       sp.out = h1;
@@ -1475,12 +1480,19 @@ int orth_enqueue(nsb_basis_t B, int k, int col_w, int mode, const StreamOut *so)
       sp.out = h2;
       sp.hsum = hsum;
       sp.hsum_op = 2;
-      sp.norm_op = dgks ? 3 : fold ? 4 : 0;
+      sp.norm_op = dgks ? (fold_dgks ? 5 : 3) : fold ? 4 : 0;
       sp.passes_out = dgks ? hsum + k + 1 : nullptr;
       NSB_CHECK(launch_fused(ctx, V, L->ld, k, h1, w, L->w_d, L->ld, L->ndot, dgks || fold, sp, L->nact,
                              L->ndof_dot + 1));
       if (fold) {
         NSB_CHECK(launch_update<2>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, false, TailSpec(), L->nact, 0, scal));
+        return NSB_OK;
+      }
+      if (fold_dgks) {
+        TailSpec t2;
+        t2.skip_flag = skip;
+        NSB_CHECK(launch_update<2>(ctx, V, L->ld, k, h2, w, L->w_d, L->ld, L->ndot, false, t2, L->nact, 0, scal));
+        NSB_CHECK(launch_normalize(ctx, w, L->ld, scal, hsum + k, ctx->flag_d));
         return NSB_OK;
       }
     } else {

@@ -115,6 +115,8 @@ __device__ __forceinline__ void p2p_allreduce_block(double *buf, int n, const Pe
 //               known before the third sweep: scal[0] = beta^2 = out[k] - sum_j out[j]^2, hsum[k] = beta
 //               (H(k+1,k)), scal[3] = beta.  The third sweep then writes (w' - V h2) / beta directly: no norm
 //               reduction, no third all-reduce and no separate normalisation pass.
+//             5 norm_op 3 and 4 together (DGKS with the folded normalisation): decision as in 3; beta^2 as in 4 when the
+//               second projection is kept, |w'|^2 when it is dropped (then normalize_kernel runs instead of the sweep)
 struct OrthTail {
   double *partial = nullptr;   // [gridDim.x][pstride]
   int pstride = 0;
@@ -138,16 +140,16 @@ __device__ __forceinline__ void orth_post_ops(const OrthTail &t) {
     int second = 1;
     if (t.norm_op == 1) t.scal[0] = t.out[t.k];
     if (t.norm_op == 2) t.scal[1] = t.out[t.k];
-    if (t.norm_op == 3) {
+    if (t.norm_op == 3 || t.norm_op == 5) {
       const double n1 = t.out[t.k], n0 = t.scal[1];
       second = !(n1 >= t.eta2 * n0);
       *t.flag = second;
-      if (!second) t.scal[0] = n1;
+      if (!second && t.norm_op == 3) t.scal[0] = n1;
       if (t.passes_out) *t.passes_out = second ? 2.0 : 1.0;
     }
     s_second = second;
   }
-  if (t.norm_op == 4) {
+  if (t.norm_op == 4 || t.norm_op == 5) {
     // |h2|^2 with a fixed summation order (thread-strided, shuffle tree, warp partials in turn)
     __shared__ double s_red[32];
     double s = 0.0;
@@ -165,7 +167,8 @@ __device__ __forceinline__ void orth_post_ops(const OrthTail &t) {
       // (never below eps |w'|), so the step neither divides by zero nor reports a breakdown the reference would
       // not see.  |w'| = 0 exactly still gives beta = 0 (NSB_EBREAKDOWN); NaN propagates.
       const double n1 = t.out[t.k];
-      double b2 = n1 - h2n;
+      // norm_op 5 (DGKS): the second projection is dropped when |w'| >= eta |w| -- then beta = |w'|
+      double b2 = (t.norm_op == 4 || s_second) ? n1 - h2n : n1;
       const double floor2 = 4.930380657631324e-32 * n1;   // (2^-52)^2 |w'|^2
       if (b2 == b2 && !(b2 > floor2)) b2 = floor2;
       const double beta = sqrt(b2);
