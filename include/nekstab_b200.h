@@ -377,6 +377,9 @@ int nsb_op_create_stepper_adjoint(nsb_sem_t sem, nsb_layout_t layout, int nfield
  *                       of elements (about 60 at tol 1e-8).  On a multi-rank context the coarse level couples the
  *                       elements of a rank only. */
 int nsb_pressure_matrices(int N, double *z2, double *w2, double *I12, double *D12);
+/* host-only: 1-D generalised eigenpairs of the element-wise pressure solves (precond 1): E^ S = M^ S Lambda,
+ * S^T M^ S = 1, S [lx2][lx2] row-major (column m = eigenvector m), lam [lx2] */
+int nsb_fdm_matrices(int N, double *S, double *lam);
 int nsb_sem_pressure_setup(nsb_sem_t sem);
 int64_t nsb_sem_npres(nsb_sem_t sem);
 int nsb_sem_pressure_get(nsb_sem_t sem, int which, double *out);

@@ -106,6 +106,7 @@ PROTOTYPES = {
     'nsb_op_create_stepper_adjoint': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                                 C.c_double, C.c_int, c_void_pp]),
     'nsb_pressure_matrices': (C.c_int, [C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    'nsb_fdm_matrices': (C.c_int, [C.c_int, c_double_p, c_double_p]),
     'nsb_sem_pressure_setup': (C.c_int, [H]),
     'nsb_sem_npres': (C.c_int64, [H]),
     'nsb_sem_pressure_get': (C.c_int, [H, C.c_int, c_double_p]),

@@ -576,6 +576,14 @@ def pressure_matrices(N: int):
     return z2, w2, I12, D12
 
 
+def fdm_matrices(N: int):
+    """Host-only: (S, lam) of the element-wise pressure solves, E^ S = M^ S diag(lam), S^T M^ S = 1."""
+    l2 = N - 1
+    S, lam = np.empty((l2, l2)), np.empty(l2)
+    check(_capi.load().nsb_fdm_matrices(int(N), _dp(S), _dp(lam)))
+    return S, lam
+
+
 def compose_operators(layout: Layout, outer: LinearOperator, inner: LinearOperator) -> LinearOperator:
     """out = outer(inner(in)) -- e.g. transient_growth_map = adjoint(forward(q)) (core/matvec.f90:478-495)."""
     h = C.c_void_p()

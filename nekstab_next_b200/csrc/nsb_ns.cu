@@ -1043,21 +1043,15 @@ int sym_gen_eig(int n, const std::vector<double> &A, const std::vector<double> &
   return NSB_OK;
 }
 
-// One-time set-up of the two-level preconditioner (first solve that asks for it).
-int fdm_setup(nsb_sem_t S) {
-  if (S->fdm_S_d) return NSB_OK;
-  nsb_context_t ctx = S->ctx;
-  cudaStream_t st = ctx->stream;
-  const int l1 = S->lx, l2 = S->lx2, dim = S->dim;
-  const NsDims d = ns_dims(S);
-  // 1-D operators on the reference element
-  std::vector<double> z2(l2), w2(l2), I12(l2 * l1), D12(l2 * l1);
-  NSB_CHECK(nsb_pressure_matrices(S->N, z2.data(), w2.data(), I12.data(), D12.data()));
-  std::vector<double> b(S->w_h);
-  NSB_REQUIRE((int)b.size() == l1, "fdm_setup: GLL weights missing");
-  b[0] *= 2.0;
+// 1-D operators of the element-wise solves on the reference element and their generalised eigen-decomposition.
+int fdm_matrices_host(int N, std::vector<double> &Sm, std::vector<double> &lam) {
+  const int l1 = N + 1, l2 = N - 1;
+  std::vector<double> z2(l2), w2(l2), I12(l2 * l1), D12(l2 * l1), z1(l1), b(l1), D(l1 * l1);
+  NSB_CHECK(nsb_pressure_matrices(N, z2.data(), w2.data(), I12.data(), D12.data()));
+  NSB_CHECK(nsb_gll(N, z1.data(), b.data(), D.data()));
+  b[0] *= 2.0;            // end weights doubled: assembled with an equal neighbour
   b[l1 - 1] *= 2.0;
-  std::vector<double> Eh(l2 * l2, 0.0), Mh(l2 * l2, 0.0), Sm, lam;
+  std::vector<double> Eh(l2 * l2, 0.0), Mh(l2 * l2, 0.0);
   for (int I = 0; I < l2; ++I)
     for (int J = 0; J < l2; ++J) {
       double se = 0.0, smm = 0.0;
@@ -1068,7 +1062,19 @@ int fdm_setup(nsb_sem_t S) {
       Eh[I * l2 + J] = se;
       Mh[I * l2 + J] = smm;
     }
-  NSB_REQUIRE(sym_gen_eig(l2, Eh, Mh, Sm, lam) == NSB_OK, "fdm_setup: the 1-D mass operator is not positive definite");
+  NSB_REQUIRE(sym_gen_eig(l2, Eh, Mh, Sm, lam) == NSB_OK, "fdm: the 1-D mass operator is not positive definite");
+  return NSB_OK;
+}
+
+// One-time set-up of the two-level preconditioner (first solve that asks for it).
+int fdm_setup(nsb_sem_t S) {
+  if (S->fdm_S_d) return NSB_OK;
+  nsb_context_t ctx = S->ctx;
+  cudaStream_t st = ctx->stream;
+  const int l2 = S->lx2, dim = S->dim;
+  const NsDims d = ns_dims(S);
+  std::vector<double> Sm, lam;
+  NSB_CHECK(fdm_matrices_host(S->N, Sm, lam));
   const int64_t nelp = std::max<int64_t>(S->nel, 1);
   NSB_CUDA(cudaMalloc(&S->fdm_S_d, sizeof(double) * l2 * l2));
   NSB_CUDA(cudaMalloc(&S->fdm_lam_d, sizeof(double) * l2));
@@ -1345,6 +1351,17 @@ extern "C" int nsb_pressure_matrices(int N, double *z2, double *w2, double *I12,
       }
     }
   }
+  return NSB_OK;
+}
+
+// Host-only: the 1-D generalised eigenpairs of the element-wise pressure solves, E^ S = M^ S Lambda with S^T M^ S = 1
+// (S[I * lx2 + m] = component I of eigenvector m).
+extern "C" int nsb_fdm_matrices(int N, double *S, double *lam) {
+  NSB_REQUIRE(N >= 3 && N <= 15 && S && lam, "nsb_fdm_matrices: bad argument");
+  std::vector<double> Sm, lm;
+  NSB_CHECK(fdm_matrices_host(N, Sm, lm));
+  memcpy(S, Sm.data(), sizeof(double) * Sm.size());
+  memcpy(lam, lm.data(), sizeof(double) * lm.size());
   return NSB_OK;
 }
 

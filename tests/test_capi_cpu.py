@@ -215,3 +215,26 @@ def test_pressure_mesh_matrices_match_oracle():
         assert np.max(np.abs(z2 - zo)) <= 1e-14 and np.max(np.abs(w2 - wo)) <= 1e-14
         assert np.max(np.abs(I12 - Io)) <= 1e-13
         assert np.max(np.abs(D12 - Io @ osem.dgll(N))) <= 1e-11
+
+
+def test_fdm_eigenpairs_match_scipy():
+    """nsb_fdm_matrices (host-only; Cholesky + cyclic Jacobi in the library): the generalised eigenpairs of the 1-D
+    operators of the element-wise pressure solves vs scipy.linalg.eigh on the oracle's matrices."""
+    import scipy.linalg as sla
+    import nekstab_next_b200 as nb
+    from oracle import sem as osem
+    for N in (3, 4, 5, 7, 9, 11):
+        S, lam = nb.fdm_matrices(N)
+        z1, w1 = osem.gll(N)
+        z2, w2 = osem.gl(N - 1)
+        I12 = osem.interp_matrix(z1, z2)
+        D12 = I12 @ osem.dgll(N)
+        b = w1.copy()
+        b[0] *= 2.0
+        b[-1] *= 2.0
+        Eh = ((w2[:, None] * D12) / b) @ (w2[:, None] * D12).T
+        Mh = ((w2[:, None] * I12) / b) @ (w2[:, None] * I12).T
+        lo, _ = sla.eigh(Eh, Mh)
+        assert np.max(np.abs(np.sort(lam) - lo)) <= 1e-11 * np.max(np.abs(lo))
+        assert np.max(np.abs(S.T @ Mh @ S - np.eye(N - 1))) <= 1e-11
+        assert np.max(np.abs(S.T @ Eh @ S - np.diag(lam))) <= 1e-11 * np.max(np.abs(lo))
