@@ -2,13 +2,25 @@
 ``exponential_prop%matvec`` (core/linear_operators.f90:225-274: ``nopcopy`` of the Krylov vector into vxp/vyp/vzp/prp,
 ``nek_advance`` for tau/dt steps from a cold start, copy of the final state back).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  parity unpinned: Nek5000 is not vendored with the reference
-(SURVEY.md section 2.3), so everything here is [UPSTREAM-RECALL] of Nek5000's P_N - P_N-2 perturbation path
-(perturb.f: perturbv -> advabp, makextp, makebdfp, cresvipp, ophinv, incomprp;  navier1.f: opdiv / multd, opgradt / cdtp,
-cdabdtp, opbinv, ortho;  coef.f: geom2 / map12) restated from its published formulation (Maday-Patera-Ronquist
-splitting with the consistent Poisson operator E = D B^-1 D^T), and pinned only by independent mathematics in
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Nek5000 is not vendored with the reference (SURVEY.md section
+2.3), so everything here is [UPSTREAM-RECALL] of Nek5000's P_N - P_N-2 perturbation path (perturb.f: perturbv ->
+advabp, makextp, makebdfp, cresvipp, ophinv, incomprp;  navier1.f: opdiv / multd, opgradt / cdtp, cdabdtp, opbinv,
+ortho;  coef.f: geom2 / map12) restated from its published formulation (Maday-Patera-Ronquist splitting with the
+consistent Poisson operator E = D B^-1 D^T).
+
+Pinning.  The SPATIAL operators are pinned against data the un-vendored solver itself produced: the reference's base
+flows (examples/cylinder/BF_1cyl0.f00001, examples/back_fstep/baseflow/BF_bfs0.f00001; velocity and pressure
+committed in tests/golden/*_mesh.npz) are converged steady states of exactly this discretisation (lx2 = lx1 - 2,
+lxd = 9), and with the operators of this file they satisfy its discrete equations to the tolerances they were
+computed with -- max |D U| / bm2 = 7e-10 (cylinder; 6e-2 for a collocation divergence on the GLL mesh), assembled
+momentum residual B C(U) U + nu A U - D^T p = 7e-6 of its largest term (O(1) with the other sign of the pressure
+term, x 30 with 1.1 nu): tests/test_oracle_fixtures.py, and through the CUDA kernels tests/test_gpu_ns.py.  That
+fixes opdiv, opgradt (mesh, metrics, weights, sign, scaling) and, with them, the dealiased convection and axhelm of
+oracle/sem.py.  The TIME discretisation (BDF/EXT coefficients, the splitting and the pressure extrapolation) has no
+reference data to meet and remains parity unpinned; it is held by independent mathematics in
 tests/test_oracle_ns.py: adjointness <D u, p> = <u, D^T p>, exactness of D on polynomial fields, symmetry and null
-space of E, discrete incompressibility of every step, linearity and temporal convergence order of the stepper.
+space of E, discrete incompressibility of every step, linearity and temporal convergence order of the stepper.  The
+pressure solver and its preconditioner are solvers: any converged one returns the same dp.
 
 Meshes: velocity on lx1 = N+1 Gauss-Lobatto-Legendre points per direction (C0 across elements), pressure on
 lx2 = lx1 - 2 Gauss-Legendre points (element-local, discontinuous).  Arrays are element-local, (e, k, j, i) / (e, j, i).

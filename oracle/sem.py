@@ -325,7 +325,8 @@ def cggo(rhs, g, d, glo, mask, bm1, h1, h2, tol=1e-10, maxit=500):
 
 # ----------------------------------------------------------------------------
 # Dealiased convection  ([UPSTREAM-RECALL] Nek5000 convect.f: set_dealias_rx, set_convect_new,
-# convect_new, intp_rstd, grad_rst on the lxd Gauss-Legendre mesh; parity unpinned)
+# convect_new, intp_rstd, grad_rst on the lxd Gauss-Legendre mesh.  Pinned, together with axhelm and the geometry, by
+# the steady momentum balance of the reference's own base flows: tests/test_oracle_fixtures.py, oracle/ns.py header)
 # ----------------------------------------------------------------------------
 def gl(n: int):
     """n Gauss-Legendre nodes and weights on [-1, 1] (Nek zwgl)."""

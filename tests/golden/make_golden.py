@@ -1,7 +1,8 @@
 """Generate the committed golden fixtures from the reference's own field files.
 
 Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
-Only mesh coordinates and the base-flow velocity are extracted (data, not source code); the known
+Only mesh coordinates, the base-flow velocity and its pressure (as the file holds it: on the velocity mesh,
+where Nek's output routine interpolates it to) are extracted (data, not source code); the known
 answers are recomputed by the oracle and cross-checked against SURVEY.md section 8c.
 """
 import json
@@ -36,7 +37,7 @@ for name, (path, sum_bm1, uu, nloc, nuniq) in CASES.items():
     assert abs(got['uu'] - uu) < 1e-9 * uu, (name, got)
     assert got['nlocal'] == nloc and got['nunique'] == nuniq, (name, got)
     known[name] = got
-    np.savez_compressed(Path(__file__).parent / f'{name}_mesh.npz', x=x, y=y, u=u, v=v,
+    np.savez_compressed(Path(__file__).parent / f'{name}_mesh.npz', x=x, y=y, u=u, v=v, p=f['p'],
                         glo=glo.astype(np.int32))
     print(name, got)
 (Path(__file__).parent / 'known_answers.json').write_text(json.dumps(known, indent=1))

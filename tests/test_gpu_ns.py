@@ -232,3 +232,49 @@ def test_ns_error_paths(ctx):
         sem.esolve(B2[0], B2[0])
     for o in (B2, B, lay, lay_bad, sem):
         o.close()
+
+
+@pytest.mark.parametrize('name,nu,div_tol,mom_tol', [('cyl', 1.0 / 50.0, 1e-8, 3e-5), ('bfs', 1.0 / 500.0, 2e-5, 3e-4)])
+def test_reference_base_flow_satisfies_the_discrete_equations_on_the_device(ctx, name, nu, div_tol, mom_tol):
+    """The reference's own base flows (computed by Nek5000 in P_N - P_N-2 with lxd = 9 dealiasing; committed as
+    tests/golden/*_mesh.npz) through the CUDA kernels: discrete continuity D U = 0 on the pressure mesh and the
+    assembled steady momentum residual B C(U) U + nu A U - D^T p = 0 off the domain boundary, to the solver
+    tolerances of those files -- opdiv, opgradt, the dealiased convection, axhelm and dssum pinned against data of
+    the un-vendored solver (the CPU twin of this test: tests/test_oracle_fixtures.py)."""
+    import nekstab_next_b200 as nb
+    from pathlib import Path
+    from test_oracle_fixtures import _domain_boundary
+    g = np.load(Path(__file__).parent / 'golden' / f'{name}_mesh.npz')
+    x, y, u, v, pm1 = g['x'], g['y'], g['u'], g['v'], g['p']
+    glo = g['glo'].astype(np.int64)
+    N = x.shape[-1] - 1
+    geo = osem.geometry(N, x, y)
+    ps = ons.pressure_setup(N, geo)
+    p2 = osem.interp_fine(pm1, ps['I12'])
+    sem = nb.Sem(ctx, N, x, y, None, mask=None, glo_num=glo)
+    n2 = sem.pressure_setup()
+    lay = nb.Layout(ctx, [x.size, x.size, n2], [True, True, False])
+    B = nb.Basis(lay, 5)
+    B[0].upload([u, v, p2])
+    sem.opdiv(B[0], B[1])
+    Du = B[1].download()[0][2].reshape(p2.shape)
+    # vs the oracle: the values are O(1e-10) sums of O(1) terms, so the bar is absolute, in units of those terms
+    term = np.max(ps['bm2']) * max(np.max(np.abs(u)), np.max(np.abs(v))) * (N + 1) ** 2
+    assert np.max(np.abs(Du - ons.opdiv([u, v], ps))) <= 1e-14 * term
+    assert np.max(np.abs(Du / ps['bm2'])) <= div_tol                       # vs Nek: discretely divergence-free
+    sem.dealias_setup(9)
+    sem.set_convect(0, B[0])
+    sem.convect(0, B[0], B[2], field0=0, nf=2)
+    for f in range(2):
+        sem.axhelm(B[0], B[3], f, nu, 0.0)
+    sem.opgradt(B[0], B[4])
+    conv, visc, gt = (B[c].download()[0] for c in (2, 3, 4))
+    inner = ~_domain_boundary(glo)
+    worst = scale = 0.0
+    for f in range(2):
+        r = (conv[f] + visc[f] - gt[f]).reshape(x.shape)
+        worst = max(worst, float(np.max(np.abs(osem.dssum(r, glo) * inner))))
+        scale = max(scale, *(float(np.max(np.abs(osem.dssum(t[f].reshape(x.shape), glo) * inner))) for t in (conv, visc, gt)))
+    assert worst <= mom_tol * scale, (worst, scale)
+    for o in (B, lay, sem):
+        o.close()

@@ -134,3 +134,69 @@ def test_mgs2_orthonormal_and_ritz():
         lhs = P.omatvec(Q[j]).f[0]
         rhs = sum(H[i, j] * Q[i].f[0] for i in range(j + 2))
         assert np.max(np.abs(lhs - rhs)) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The reference's base flows were computed by Nek5000 itself (P_N - P_N-2, lx2 = lx1 - 2, dealiasing on lxd = 9 Gauss
+# points: examples/cylinder/SIZE:13-15, 1cyl.par; examples/back_fstep/baseflow/SIZE, bfs.par).  A converged steady
+# state of THAT discretisation satisfies THAT discretisation's equations to its solver tolerances:
+#     D U = 0                                    (discrete continuity on the pressure mesh)
+#     QQ^T [ B C(U) U + nu A U - D^T p ] = 0      (discrete momentum at every node off the domain boundary)
+# Evaluating them with the oracle's restatements of opdiv / opgradt / convect_new / axhelm / dssum therefore pins
+# those restatements -- their meshes, metrics, quadrature weights, signs and scalings -- against data produced by the
+# un-vendored solver.  Negative controls show the test discriminates: a collocation divergence on the GLL mesh, the
+# other sign of the pressure term, another viscosity.
+# ----------------------------------------------------------------------------------------------------------------
+def _domain_boundary(glo):
+    """True on every node of an element edge that no other element shares (2-D)."""
+    mult = sem.multiplicity(glo)
+    mid = glo.shape[2] // 2
+    bnd = np.zeros(int(glo.max()) + 1, bool)
+    for edge, probe in ((np.s_[:, 0, :], np.s_[:, 0, mid]), (np.s_[:, -1, :], np.s_[:, -1, mid]),
+                        (np.s_[:, :, 0], np.s_[:, mid, 0]), (np.s_[:, :, -1], np.s_[:, mid, -1])):
+        bnd[glo[edge][mult[probe] == 1].ravel()] = True
+    return bnd[glo]
+
+
+BASEFLOW = {'cyl': dict(nu=1.0 / 50.0, div=1e-8, mom=3e-5), 'bfs': dict(nu=1.0 / 500.0, div=2e-5, mom=3e-4)}
+
+
+@pytest.mark.parametrize('name', ['cyl', 'bfs'])
+def test_reference_base_flow_satisfies_the_discrete_equations(name):
+    from oracle import ns as ons
+    g = np.load(GOLD / f'{name}_mesh.npz')
+    x, y, u, v, pm1 = g['x'], g['y'], g['u'], g['v'], g['p']
+    N, cfg = KNOWN[name]['N'], BASEFLOW[name]
+    glo = g['glo'].astype(np.int64)
+    geo = sem.geometry(N, x, y)
+    ps = ons.pressure_setup(N, geo)
+    assert ps['lx2'] == 4
+    # continuity: pointwise divergence on the Gauss points, |U| = O(1)
+    Du = ons.opdiv([u, v], ps) / ps['bm2']
+    assert np.max(np.abs(Du)) <= cfg['div'], np.max(np.abs(Du))
+    d = sem.dgll(N)
+    ur, us = sem.grad_rst(u, d)
+    vr, vs = sem.grad_rst(v, d)
+    rx, ry, sx, sy = geo['rst']
+    colloc = (rx * ur + sx * us + ry * vr + sy * vs) / geo['jac']
+    assert np.max(np.abs(colloc)) >= 1e-2                       # control: not "any consistent divergence is tiny"
+    # momentum: the file holds the pressure interpolated to the velocity mesh (a polynomial of degree lx2 - 1 per
+    # element), so interpolating it back to the Gauss points is exact
+    p2 = sem.interp_fine(pm1, ps['I12'])
+    dl = sem.dealias_setup(N, 9, geo['rst'])
+    cf = sem.set_convect([u, v], dl)
+    gt = ons.opgradt(p2, ps)
+    inner = ~_domain_boundary(glo)
+
+    def residual(nu, sign):
+        worst, scale = 0.0, 0.0
+        for b, a in enumerate((u, v)):
+            conv = sem.convect_dealiased(a, cf, dl)
+            visc = sem.axhelm(a, geo['g'], d, nu, 0.0, geo['bm1'])
+            worst = max(worst, float(np.max(np.abs(sem.dssum(conv + visc - sign * gt[b], glo) * inner))))
+            scale = max(scale, *(float(np.max(np.abs(sem.dssum(t, glo) * inner))) for t in (conv, visc, gt[b])))
+        return worst / scale
+
+    assert residual(cfg['nu'], 1.0) <= cfg['mom']
+    assert residual(cfg['nu'], -1.0) >= 0.5                     # control: the sign of D^T p
+    assert residual(1.1 * cfg['nu'], 1.0) >= 30 * residual(cfg['nu'], 1.0)   # control: the viscosity
