@@ -400,6 +400,14 @@ int nsb_sem_esolve(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, in
 int nsb_op_create_ns_stepper(nsb_sem_t sem, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu, double dt,
                              int nsteps, double tol_v, double tol_p, int maxit, int mean_free, int precond,
                              nsb_op_t *op);
+/* exponential_prop%rmatvec (core/linear_operators.f90:84-103) for the same equations: Nek's stepper in adjoint mode --
+ * the same splitting on the continuous adjoint equations, explicit term +(U.grad) w - sum_c w_c grad U_c (transport
+ * term dealiased, base-flow-gradient term pointwise with gradm1 of U).  Dual to the forward operator up to the
+ * discretisation error (first order in dt), as in the reference; with nsb_op_create_compose it gives the
+ * transient-growth map of core/matvec.f90:478-495 for the Navier-Stokes equations, device-resident.  Same arguments. */
+int nsb_op_create_ns_stepper_adjoint(nsb_sem_t sem, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu,
+                                     double dt, int nsteps, double tol_v, double tol_p, int maxit, int mean_free,
+                                     int precond, nsb_op_t *op);
 int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);

@@ -547,15 +547,16 @@ def stepper_operator(sem: Sem, layout: Layout, nfields: int, slot: int, kappa: f
 
 def ns_stepper_operator(sem: Sem, layout: Layout, base: nek_dvector | None, nu: float, dt: float, nsteps: int,
                         tol_v: float = 1e-12, tol_p: float = 1e-12, maxit: int = 4000,
-                        mean_free: bool = True, precond: int = 1) -> LinearOperator:
+                        mean_free: bool = True, precond: int = 1, adjoint: bool = False) -> LinearOperator:
     """exponential_prop%matvec for the linearised incompressible Navier-Stokes equations on the device
     (core/linear_operators.f90:225-274): nsteps pressure-coupled BDF/EXT steps of the P_N - P_N-2 splitting from a
-    cold start.  Layout: fields 0..dim-1 velocity, field dim pressure; base = the base flow (None: Stokes)."""
+    cold start.  Layout: fields 0..dim-1 velocity, field dim pressure; base = the base flow (None: Stokes);
+    adjoint = True: %rmatvec, the same stepper on the adjoint equations."""
     h = C.c_void_p()
-    check(sem.lib.nsb_op_create_ns_stepper(sem.h, layout.h, base.basis.h if base is not None else None,
-                                           base.col if base is not None else 0, float(nu), float(dt), int(nsteps),
-                                           float(tol_v), float(tol_p), int(maxit), int(bool(mean_free)), int(precond),
-                                           C.byref(h)))
+    create = sem.lib.nsb_op_create_ns_stepper_adjoint if adjoint else sem.lib.nsb_op_create_ns_stepper
+    check(create(sem.h, layout.h, base.basis.h if base is not None else None,
+                 base.col if base is not None else 0, float(nu), float(dt), int(nsteps),
+                 float(tol_v), float(tol_p), int(maxit), int(bool(mean_free)), int(precond), C.byref(h)))
     return LinearOperator(sem.lib, h, keep=(sem, layout))
 
 

@@ -867,6 +867,51 @@ __global__ void lin2_kernel(double *__restrict__ out, const double *__restrict__
     out[i] = ca * a[i] + cb * b[i];
 }
 
+// G[c * dim + b] = bm1 * dU_c / dx_b on the GLL points (collocation, Nek's gradm1), once per operator: the
+// base-flow-gradient term of the adjoint equations.
+__global__ void __launch_bounds__(256)
+grad_base_kernel(int dim, int lx, const double *__restrict__ U, int64_t fs, const double *__restrict__ rst,
+                 const double *__restrict__ bm1, const double *__restrict__ jac, const double *__restrict__ D,
+                 int64_t npts, double *__restrict__ G) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  int nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  const int64_t e0 = p / nloc * nloc;
+  const int loc = (int)(p - e0);
+  const int i = loc % lx, j = (loc / lx) % lx, k = dim == 3 ? loc / (lx * lx) : 0;
+  const double w3 = bm1[p] / jac[p];
+  for (int c = 0; c < dim; ++c) {
+    const double *u = U + (int64_t)c * fs + e0;
+    double g[3] = {0.0, 0.0, 0.0};
+    for (int l = 0; l < lx; ++l) {   // D[i + lx * l] = dxm1(i, l)
+      g[0] = fma(D[i + lx * l], u[l + lx * (j + lx * k)], g[0]);
+      g[1] = fma(D[j + lx * l], u[i + lx * (l + lx * k)], g[1]);
+      if (dim == 3) g[2] = fma(D[k + lx * l], u[i + lx * (j + lx * l)], g[2]);
+    }
+    for (int b = 0; b < dim; ++b) {
+      double s = 0.0;
+      for (int a = 0; a < dim; ++a) s = fma(rst[(int64_t)(a * dim + b) * npts + p], g[a], s);
+      G[(int64_t)(c * dim + b) * npts + p] = s * w3;
+    }
+  }
+}
+
+// bf_b -= sum_c G[c][b] v_c   (pointwise)
+__global__ void __launch_bounds__(256)
+adj_gradterm_kernel(int dim, const double *__restrict__ G, const double *__restrict__ v, int64_t fs, int64_t npts,
+                    double *__restrict__ bf) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x) {
+    double vc[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < dim; ++c) vc[c] = v[(int64_t)c * fs + p];
+    for (int b = 0; b < dim; ++b) {
+      double s = 0.0;
+      for (int c = 0; c < dim; ++c) s = fma(G[(int64_t)(c * dim + b) * npts + p], vc[c], s);
+      bf[(int64_t)b * fs + p] -= s;
+    }
+  }
+}
+
 NsDims ns_dims(nsb_sem_t S) {
   NsDims d;
   d.dim = S->dim;
@@ -1536,6 +1581,36 @@ extern "C" int nsb_op_create_ns_stepper(nsb_sem_t S, nsb_layout_t layout, nsb_ba
   return NSB_OK;
 }
 
+// exponential_prop%rmatvec (core/linear_operators.f90:84-103) for the same equations: Nek's stepper in adjoint mode,
+// i.e. the same BDF/EXT splitting on the continuous adjoint equations
+//     -dw/dt ... :  dw/dt - (U.grad) w + sum_c w_c grad U_c = -grad q + nu lap w,  div w = 0
+// -- the explicit term becomes +(U.grad) w (dealiased, like the forward one) - sum_c w_c grad U_c (pointwise on the
+// GLL mesh with gradm1 of the base flow, computed once here).  <A v, w>_B = <v, A+ w>_B then holds up to the
+// discretisation error (first order in dt), not to rounding (tests/test_gpu_ns.py).
+extern "C" int nsb_op_create_ns_stepper_adjoint(nsb_sem_t S, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu,
+                                                double dt, int nsteps, double tol_v, double tol_p, int maxit,
+                                                int mean_free, int precond, nsb_op_t *out) {
+  NSB_CHECK(nsb_op_create_ns_stepper(S, layout, base, col_base, nu, dt, nsteps, tol_v, tol_p, maxit, mean_free, precond, out));
+  nsb_op_t op = *out;
+  op->adjoint = true;
+  if (!op->has_base) return NSB_OK;
+  nsb_context_t ctx = S->ctx;
+  cudaSetDevice(ctx->device);
+  const int dim = S->dim;
+  if (cudaMalloc(&op->c_d, sizeof(double) * dim * dim * S->npts) != cudaSuccess) {
+    nsb_op_destroy(op);
+    *out = nullptr;
+    set_error("nsb_op_create_ns_stepper_adjoint: out of device memory");
+    return NSB_ECUDA;
+  }
+  const int64_t fs = dim > 1 ? layout->off[1] - layout->off[0] : 0;
+  grad_base_kernel<<<(unsigned)((S->npts + 255) / 256), 256, 0, ctx->stream>>>(
+      dim, S->lx, op->tmp->col(9) + layout->off[0], fs, S->rst_d, S->bm1_d, S->jac_d, S->D_d, S->npts, op->c_d);
+  ctx->launches++;
+  NSB_CUDA(cudaGetLastError());
+  return NSB_OK;
+}
+
 extern "C" int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure) {
   NSB_REQUIRE(op && op->kind == 4, "nsb_op_ns_iterations: not a Navier-Stokes stepper operator");
   if (helmholtz) *helmholtz = op->helm_iters;
@@ -1571,7 +1646,12 @@ int nsb::ns_stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bou
     const int o = n < 3 ? n : 3;
     const double bd0 = kBDn[o][0];
     // advabp: bf = -[(U.grad) v + (v.grad) U], mass matrix inside the dealiased quadrature
-    if (op->has_base) {
+    if (op->has_base && op->adjoint) {
+      // adjoint advabp: +(U.grad) w - sum_c w_c grad U_c
+      NSB_CHECK(nsb_sem_convect(S, 0, W, lag[0], W, bf, 0, dim, 1.0, 0));
+      adj_gradterm_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(dim, op->c_d, vel(lag[0]), fs, S->npts, vel(bf));
+      ctx->launches++;
+    } else if (op->has_base) {
       NSB_CHECK(nsb_sem_convect(S, 0, W, lag[0], W, bf, 0, dim, -1.0, 0));
       NSB_CHECK(nsb_sem_set_convect(S, 1, W, lag[0], 0));
       NSB_CHECK(nsb_sem_convect(S, 1, W, cU, W, bf, 0, dim, -1.0, 1));

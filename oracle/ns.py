@@ -253,8 +253,29 @@ def advabp(vel, base, cf_base, dl):
             for b in range(len(vel))]
 
 
+def grad_base(base, geo, n):
+    """bm1 * dU_c/dx_b on the GLL points (collocation, gradm1): G[c][b]."""
+    d = osem.dgll(n)
+    dim = len(base)
+    rst, w3 = geo['rst'], geo['bm1'] / geo['jac']
+    G = []
+    for c in range(dim):
+        g = osem.grad_rst(base[c], d)
+        G.append([sum(rst[a * dim + b] * g[a] for a in range(dim)) * w3 for b in range(dim)])
+    return G
+
+
+def advabp_adjoint(vel, cf_base, G, dl):
+    """Explicit term of the ADJOINT linearised momentum equation (advabp with ifadj; exponential_prop%rmatvec,
+    core/linear_operators.f90:84-103, runs Nek's stepper in that mode): the continuous adjoint of
+    -(U.grad) v - (v.grad) U is  +(U.grad) w - sum_c w_c grad U_c ; the transport term on the dealiased mesh like the
+    forward one, the base-flow-gradient term pointwise on the GLL mesh."""
+    dim = len(vel)
+    return [osem.convect_dealiased(vel[b], cf_base, dl) - sum(G[c][b] * vel[c] for c in range(dim)) for b in range(dim)]
+
+
 def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=True,
-             maxit=4000, info=None, fdm=None):
+             maxit=4000, info=None, fdm=None, adjoint=False):
     """nsteps BDF/EXT steps (order ramp 1, 2, 3, cold start) of the linearised incompressible Navier-Stokes equations
         dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v ,  div v = 0
     in the P_N - P_N-2 splitting:
@@ -262,12 +283,14 @@ def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1
         p*   = p^(n-1)            (order 1, 2)   |   2 p^(n-1) - p^(n-2)       (order 3; extrapprp)
         v*   = H^-1 mask dssum(bf + D^T p*),   H = nu A + (bd_0/dt) B           (cresvipp + ophinv)
         E dp = -(bd_0/dt) D v* ;  v = v* + (dt/bd_0) B^-1 D^T dp ;  p = p* + dp (incomprp)
-    base = None: Stokes.  Returns (velocity list, pressure)."""
+    base = None: Stokes.  adjoint = True: the same stepper on the adjoint equations (explicit term advabp_adjoint), what
+    Nek runs for exponential_prop%rmatvec.  Returns (velocity list, pressure)."""
     d = osem.dgll(n)
     dim = ps['dim']
     bm1 = geo['bm1']
     binv = 1.0 / osem.dssum(bm1, glo)
     cf_base = osem.set_convect(base, dl) if base is not None else None
+    G = grad_base(base, geo, n) if (adjoint and base is not None) else None
     lag = [[v.copy() for v in vel0]] + [[0 * v for v in vel0] for _ in range(2)]
     e1 = [0 * v for v in vel0]
     e2 = [0 * v for v in vel0]
@@ -276,7 +299,12 @@ def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1
     for s in range(1, nsteps + 1):
         o = min(s, 3)
         bd0 = osem.BD[o][0]
-        bf = advabp(lag[0], base, cf_base, dl) if base is not None else [0 * v for v in vel0]
+        if base is None:
+            bf = [0 * v for v in vel0]
+        elif adjoint:
+            bf = advabp_adjoint(lag[0], cf_base, G, dl)
+        else:
+            bf = advabp(lag[0], base, cf_base, dl)
         for b in range(dim):
             osem.bdf_ext(bf[b], e1[b], e2[b], [lag[i][b] for i in range(o)], bm1, osem.AB[o], osem.BD[o], 1.0 / dt)
         pstar = p if o < 3 else 2.0 * p - plag

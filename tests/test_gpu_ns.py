@@ -278,3 +278,50 @@ def test_reference_base_flow_satisfies_the_discrete_equations_on_the_device(ctx,
     assert worst <= mom_tol * scale, (worst, scale)
     for o in (B, lay, sem):
         o.close()
+
+
+@pytest.mark.parametrize('nel,N', [((3, 3), 5), ((2, 2, 2), 4)])
+def test_ns_adjoint_stepper_matches_oracle(ctx, nel, N):
+    """exponential_prop%rmatvec on the device: the stepper on the adjoint equations against the oracle's, and the
+    duality <A v, w>_B = <v, A+ w>_B up to the discretisation error through the device operators."""
+    import nekstab_next_b200 as nb
+    P = NsProblem(nel, N, seed=60 + N)
+    sem, lay, B = P.gpu(ctx, 6)
+    nu, dt, nsteps = 0.05, 2e-3, 4
+    # smooth, solenoidal, no-slip fields (stream function sin^2 sin^2): the duality below is a statement about resolved fields
+    c = P.coords
+    pi = np.pi
+
+    def solenoidal(kx, ky):
+        sz = np.sin(pi * c[2]) ** 2 if P.dim == 3 else 1.0
+        f = [np.sin(kx * pi * c[0]) ** 2 * ky * pi * np.sin(2 * ky * pi * c[1]) * sz,
+             -kx * pi * np.sin(2 * kx * pi * c[0]) * np.sin(ky * pi * c[1]) ** 2 * sz]
+        return f + ([0 * c[0]] if P.dim == 3 else [])
+
+    v0, w0, p0 = solenoidal(1, 1), solenoidal(1, 2), 0 * P.pres()
+    fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv)
+    wo, qo = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base, w0, p0, nu, dt, nsteps, mean_free=False, fdm=fd,
+                          adjoint=True)
+    sem.dealias_setup()
+    P.up(B[5], P.base, p0)
+    fwd = nb.ns_stepper_operator(sem, lay, B[5], nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False)
+    adj = nb.ns_stepper_operator(sem, lay, B[5], nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False, adjoint=True)
+    P.up(B[0], v0, p0)
+    P.up(B[1], w0, p0)
+    fwd.matvec(B[0], B[2])
+    adj.matvec(B[1], B[3])
+    w, q = P.down(B[3])
+    scale = max(np.max(np.abs(a)) for a in wo)
+    for a, b in zip(w, wo):
+        assert np.max(np.abs(a - b)) <= 1e-9 * scale
+    assert np.max(np.abs(ons.opdiv(w, P.ps))) <= 1e-9 * scale
+    lhs, rhs = nb.k_dot(B[2], B[1]), nb.k_dot(B[0], B[3])           # <A v, w>_B, <v, A+ w>_B  (pressure is outside the dot)
+    fwd.matvec(B[1], B[4])
+    wrong = nb.k_dot(B[0], B[4])
+    assert abs(lhs - rhs) <= 2e-3 * abs(lhs) and abs(lhs - wrong) > 3 * abs(lhs - rhs), (lhs, rhs, wrong)
+    # the composition A+ A (transient_growth_map, core/matvec.f90:478-495) under a Krylov driver
+    tg = nb.compose_operators(lay, adj, fwd)
+    tg.matvec(B[0], B[4])
+    assert nb.k_dot(B[0], B[4]) > 0.0                               # <v, A+ A v> ~ |A v|^2
+    for o in (tg, fwd, adj, B, lay, sem):
+        o.close()
