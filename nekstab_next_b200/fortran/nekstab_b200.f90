@@ -484,6 +484,17 @@ module nekstab_b200
          type(c_ptr) :: op
          integer(c_int) :: ierr
       end function
+      !> exponential_prop%rmatvec (core/linear_operators.f90:84-103): the same stepper in adjoint mode
+      function nsb_op_create_ns_stepper_adjoint(sem, layout, base, col_base, nu, dt, nsteps, tol_v, tol_p, maxit, &
+                                                mean_free, precond, op) &
+         bind(C, name='nsb_op_create_ns_stepper_adjoint') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, layout, base
+         integer(c_int), value :: col_base, nsteps, maxit, mean_free, precond
+         real(c_double), value :: nu, dt, tol_v, tol_p
+         type(c_ptr) :: op
+         integer(c_int) :: ierr
+      end function
       function nsb_op_create_compose(layout, outer, inner, op) bind(C, name='nsb_op_create_compose') result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: layout, outer, inner
@@ -599,7 +610,7 @@ module nekstab_b200
    public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
    public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_hmholtz_vec, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
    public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose
-   public :: nsb_sem_pressure_setup, nsb_op_create_ns_stepper
+   public :: nsb_sem_pressure_setup, nsb_op_create_ns_stepper, nsb_op_create_ns_stepper_adjoint
    public :: nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues
    public :: nsb_set_dgks_eta, nsb_op_set_linear, nsb_arnoldi_passes, nsb_hessenberg_write, nsb_hessenberg_read
