@@ -334,6 +334,12 @@ int nsb_op_set_linear(nsb_op_t op, int linear);
  * e.g. transient_growth_map = adjoint_linearized_map(forward_linearized_map(q))
  * (core/matvec.f90:478-495).  The component operators stay owned by the caller. */
 int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, nsb_op_t *op);
+/* out = alpha A(in) + beta B(in); A or B = NULL stands for the identity.  LightKrylov's axpby_linop / identity_linop
+ * as the reference combines them for the resolvent's S = I - exp(TL) (core/linear_operators.f90:364-403), and the
+ * legacy maps made from the basic solvers with k_sub2 / k_cmult: newton_linearized_map = exp(TL) - I
+ * (core/matvec.f90:520-541; what ts_gmres / newton_krylov iterate on) and ts_force_sensitivity_map = I - exp(TL)^+
+ * (core/matvec.f90:499-516).  All fields and %time take part, like k_sub2.  A and B stay owned by the caller. */
+int nsb_op_create_axpby(nsb_layout_t layout, nsb_op_t A, nsb_op_t B, double alpha, double beta, nsb_op_t *op);
 /* Device time-stepper operator, the structure of exponential_prop%matvec
  * (core/linear_operators.f90:225-274: integrate over tau from a cold start, return the final state) for
  * Nek's scalar step cdscal [UPSTREAM-RECALL]: nsteps BDF/EXT steps (order ramp 1, 2, 3) of

@@ -592,6 +592,17 @@ def compose_operators(layout: Layout, outer: LinearOperator, inner: LinearOperat
     return LinearOperator(layout.lib, h, keep=(outer, inner))
 
 
+def axpby_operator(layout: Layout, A: LinearOperator | None, B: LinearOperator | None, alpha: float,
+                   beta: float) -> LinearOperator:
+    """out = alpha A(in) + beta B(in), None = identity (LightKrylov's axpby_linop / identity_linop,
+    core/linear_operators.f90:364-403): newton_linearized_map = axpby_operator(lay, A, None, 1, -1)
+    (core/matvec.f90:520-541), ts_force_sensitivity_map = axpby_operator(lay, None, A_adj, 1, -1) (:499-516)."""
+    h = C.c_void_p()
+    check(layout.lib.nsb_op_create_axpby(layout.h, A.h if A is not None else None, B.h if B is not None else None,
+                                         float(alpha), float(beta), C.byref(h)))
+    return LinearOperator(layout.lib, h, keep=(layout, A, B))
+
+
 def host_operator(layout: Layout, fn, linear: bool = False) -> LinearOperator:
     """Wrap a host matvec ``fn(fields_in, time_in) -> (fields_out, time_out)`` (the reference's
     time-stepper lives on the host); vectors cross PCIe around every call.  ``linear=True`` declares

@@ -233,7 +233,7 @@ struct nsb_sem_s {
 };
 
 struct nsb_op_s {
-  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.)), 3 device time-stepper
+  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.)), 3 / 4 device time-steppers, 5 alpha outer + beta inner
   nsb_op_t outer = nullptr, inner = nullptr;
   nsb_basis_t tmp = nullptr;     // work vector of the composition
   nsb_sem_t sem = nullptr;

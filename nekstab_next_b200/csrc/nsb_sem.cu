@@ -2058,6 +2058,32 @@ extern "C" int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op
   return NSB_OK;
 }
 
+// out = alpha A(in) + beta B(in), NULL = the identity: LightKrylov's axpby_linop / identity_linop as the reference
+// uses them for the resolvent's S = I - exp(TL) (core/linear_operators.f90:364-403) [UPSTREAM-RECALL for the type
+// itself], and the legacy maps built from the basic solvers with k_sub2 / k_cmult: newton_linearized_map
+// = exp(TL) - I (core/matvec.f90:520-541) and ts_force_sensitivity_map = I - exp(TL)+ (core/matvec.f90:499-516).
+// Every field of the vector and %time take part, like k_sub2 (core/krylov_subspace.f90:117-128).
+extern "C" int nsb_op_create_axpby(nsb_layout_t layout, nsb_op_t A, nsb_op_t B, double alpha, double beta,
+                                   nsb_op_t *out) {
+  NSB_REQUIRE(layout && out, "nsb_op_create_axpby: NULL argument");
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 5;
+  op->lay = layout;
+  op->outer = A;
+  op->inner = B;
+  op->alpha = alpha;
+  op->beta = beta;
+  if (B) {
+    int r = nsb_basis_create(layout, 1, &op->tmp);
+    if (r != NSB_OK) {
+      delete op;
+      return r;
+    }
+  }
+  *out = op;
+  return NSB_OK;
+}
+
 extern "C" int nsb_op_destroy(nsb_op_t op) {
   if (!op) return NSB_OK;
   if (op->sem) clear_step_graphs(op->sem->ctx);
@@ -2089,6 +2115,14 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
     NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: composite operator built for another layout");
     NSB_CHECK(nsb_op_apply(op->inner, bin, cin, op->tmp, 0));
     return nsb_op_apply(op->outer, op->tmp, 0, bout, cout);
+  }
+  if (op->kind == 5) {
+    NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: axpby operator built for another layout");
+    if (op->outer) NSB_CHECK(nsb_op_apply(op->outer, bin, cin, bout, cout));
+    else NSB_CHECK(nsb_vec_copy(bout, cout, bin, cin));
+    if (!op->inner) return nsb_vec_axpby(bout, cout, op->alpha, bin, cin, op->beta, 0);
+    NSB_CHECK(nsb_op_apply(op->inner, bin, cin, op->tmp, 0));
+    return nsb_vec_axpby(bout, cout, op->alpha, op->tmp, 0, op->beta, 0);
   }
   if (op->kind == 1) {
     NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: host operator built for another layout");

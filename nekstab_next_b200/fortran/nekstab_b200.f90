@@ -501,6 +501,15 @@ module nekstab_b200
          type(c_ptr) :: op
          integer(c_int) :: ierr
       end function
+      !> alpha A + beta B, c_null_ptr = identity: LightKrylov's axpby_linop (core/linear_operators.f90:403),
+      !! newton_linearized_map / ts_force_sensitivity_map of core/matvec.f90:499-541
+      function nsb_op_create_axpby(layout, A, B, alpha, beta, op) bind(C, name='nsb_op_create_axpby') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: layout, A, B
+         real(c_double), value :: alpha, beta
+         type(c_ptr) :: op
+         integer(c_int) :: ierr
+      end function
       function nsb_op_apply(op, bin, cin, bout, cout) bind(C, name='nsb_op_apply') result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: op, bin, bout
@@ -609,7 +618,7 @@ module nekstab_b200
    public :: nsb_sync, nsb_vec_norm, nsb_orthonormalize, nsb_basis_gram, nsb_basis_qr, nsb_basis_rotate
    public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
    public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_hmholtz_vec, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
-   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose
+   public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose, nsb_op_create_axpby
    public :: nsb_sem_pressure_setup, nsb_op_create_ns_stepper, nsb_op_create_ns_stepper_adjoint
    public :: nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues

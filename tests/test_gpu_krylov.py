@@ -218,6 +218,61 @@ def test_ts_gmres(ctx):
     assert hist[-1] < hist[0]
 
 
+def test_axpby_operator_and_newton_map(ctx):
+    """alpha A + beta B with NULL = identity (LightKrylov's axpby_linop, core/linear_operators.f90:403): the legacy
+    newton_linearized_map = exp(TL) - I (core/matvec.f90:520-541: forward map, then k_sub2 over every field and %time)
+    under ts_gmres against the oracle iterating on the same map, and ts_force_sensitivity_map = I - A (:499-516)."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, alpha=1.0, pressure=True, time_in_dot=True, seed=23)
+    c = P.octx()
+    ks = 10
+    lay, B, S, op = P.gpu(ctx, ks + 2)
+    W = nb.Basis(lay, 4)
+    x = P.random_kvec()
+    upload(W[0], x)
+    Mx = P.omatvec(x)
+    newton = nb.axpby_operator(lay, op, None, 1.0, -1.0)           # M - I
+    sens = nb.axpby_operator(lay, None, op, 1.0, -1.0)             # I - M
+    mm = nb.compose_operators(lay, op, op)
+    comb = nb.axpby_operator(lay, mm, op, 0.5, -2.0)               # 0.5 M M - 2 M
+    newton.matvec(W[0], W[1])
+    sens.matvec(W[0], W[2])
+    comb.matvec(W[0], W[3])
+    MMx = P.omatvec(Mx)
+    g1, g2, g3 = download(W[1]), download(W[2]), download(W[3])
+    for i in range(len(x.f)):
+        scale = np.max(np.abs(Mx.f[i])) + 1e-300
+        assert np.max(np.abs(g1.f[i] - (Mx.f[i] - x.f[i]).ravel())) <= 1e-13 * scale
+        assert np.max(np.abs(g2.f[i] - (x.f[i] - Mx.f[i]).ravel())) <= 1e-13 * scale
+        assert np.max(np.abs(g3.f[i] - (0.5 * MMx.f[i] - 2.0 * Mx.f[i]).ravel())) <= 1e-13 * scale
+    assert abs(g1.time) <= 1e-15 and abs(g2.time) <= 1e-15 and abs(g3.time + 1.5 * x.time) <= 1e-14 * abs(x.time)
+    assert np.max(np.abs(g1.f[2])) == 0.0                          # the pressure is carried through M: (M - I) p = 0
+    assert newton.count() == 1 and op.count() == 5
+
+    def newton_map(q):                                             # core/matvec.f90:531-541
+        f = P.omatvec(q)
+        okr.k_sub2(f, q)
+        return f
+
+    rhs = newton_map(P.random_kvec())                              # in the range: pressure and %time rows are zero
+    upload(W[0], rhs)
+    tol = 1e-18
+    sol_ref, hist_ref, calls_ref = okr.ts_gmres(c, newton_map, rhs, maxiter=4, ksize=ks, tol=tol)
+    hist, calls = nb.ts_gmres(B, newton, W[0], W[1], maxiter=4, ksize=ks, tol=tol)
+    assert calls == calls_ref and len(hist) == len(hist_ref)
+    got = download(W[1])
+    for a, b in zip(got.f[:2], sol_ref.f[:2]):
+        assert relerr(a, b.ravel()) <= 1e-8
+    assert np.allclose(hist, hist_ref, rtol=1e-6, atol=1e-300)
+    with pytest.raises(nb.NsbError):                               # built for another layout
+        lay2 = nb.Layout(ctx, [P.npts], [True])
+        lay2.set_weight([P.bm1])
+        B2 = nb.Basis(lay2, 2)
+        newton.matvec(B2[0], B2[1])
+    for o in (comb, mm, sens, newton):
+        o.close()
+
+
 def test_eigs_stepwise(ctx):
     """The LightKrylov-path eigensolver (core/linear_stab.f90:66): same stopping step, same Ritz values."""
     import nekstab_next_b200 as nb

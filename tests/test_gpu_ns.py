@@ -325,3 +325,59 @@ def test_ns_adjoint_stepper_matches_oracle(ctx, nel, N):
     assert nb.k_dot(B[0], B[4]) > 0.0                               # <v, A+ A v> ~ |A v|^2
     for o in (tg, fwd, adj, B, lay, sem):
         o.close()
+
+
+def test_transient_growth_and_newton_map_on_the_ns_propagators(ctx):
+    """What transient_growth_analysis and newton_krylov iterate on, device-resident for the Navier-Stokes equations:
+    svds(A, A+) (core/linear_stab.f90:112) with the forward and adjoint-mode steppers against the oracle's
+    bidiagonalisation on the oracle's propagators, and ts_gmres on newton_linearized_map = exp(TL) - I
+    (core/matvec.f90:520-541, nsb_op_create_axpby) against the oracle's GMRES on the same map."""
+    import nekstab_next_b200 as nb
+    N, kd, nsteps, nu, dt = 5, 3, 3, 0.05, 4e-3
+    P = NsProblem((3, 3), N, seed=9)
+    c = okr.Ctx(bm1s=P.geo['bm1'], in_dot=[True, True, False], time_in_dot=False)
+    fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv)
+
+    def propagate(q, adjoint):
+        v, p = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base, [q.f[0], q.f[1]], q.f[2], nu, dt, nsteps,
+                            mean_free=False, fdm=fd, adjoint=adjoint)
+        return okr.KVec(v + [p], q.time)
+
+    def newton_map(q):
+        f = propagate(q, False)
+        okr.k_sub2(f, q)
+        return f
+
+    u0 = okr.KVec(P.vel() + [0 * P.pres()], 0.0)
+    okr.k_normalize(c, u0)
+    tol = 1e-14                                                     # never met: kd full steps on both sides
+    sig_o, uv_o, vv_o, res_o, k_o, B_o = okr.svds(c, lambda q: propagate(q, False), lambda q: propagate(q, True),
+                                                  u0.copy(), kd, nev=1, tol=tol)
+    rhs = okr.KVec(P.vel() + [0 * P.pres()], 0.0)
+    sol_o, hist_o, calls_o = okr.ts_gmres(c, newton_map, rhs, maxiter=1, ksize=3, tol=1e-30)
+
+    sem, lay, U = P.gpu(ctx, kd + 2)
+    V = nb.Basis(lay, kd)
+    W = nb.Basis(lay, 3)
+    sem.dealias_setup()
+    P.up(W[2], P.base, 0 * P.pres())
+    kw = dict(tol_v=1e-13, tol_p=1e-13, mean_free=False)
+    fwd = nb.ns_stepper_operator(sem, lay, W[2], nu, dt, nsteps, **kw)
+    adj = nb.ns_stepper_operator(sem, lay, W[2], nu, dt, nsteps, adjoint=True, **kw)
+    U[0].upload([a.ravel() for a in u0.f])
+    sig, uv, vv, res, k, nconv, B = nb.svds(U, V, fwd, adj, kd, nev=1, tol=tol)
+    assert k == k_o == kd
+    assert np.max(np.abs(B[:k + 1, :k] - B_o[:k + 1, :k])) <= 1e-8 * np.max(np.abs(B_o))
+    assert np.allclose(sig, sig_o, rtol=1e-7)
+    assert sig[0] < 1.0                                            # viscous decay over a short horizon: no growth
+    for basis, ncol in ((U, k + 1), (V, k)):
+        assert np.max(np.abs(basis.gram(ncol) - np.eye(ncol))) < 1e-10
+    newton = nb.axpby_operator(lay, fwd, None, 1.0, -1.0)
+    W[0].upload([a.ravel() for a in rhs.f])
+    hist, calls = nb.ts_gmres(U, newton, W[0], W[1], maxiter=1, ksize=3, tol=1e-30)
+    assert calls == calls_o and np.allclose(hist, hist_o, rtol=1e-6)
+    dv, _ = P.down(W[1])
+    for a, b in zip(dv, sol_o.f[:2]):
+        assert np.max(np.abs(a - b)) <= 1e-7 * np.max(np.abs(b))
+    for o in (newton, fwd, adj, W, V, U, lay, sem):
+        o.close()
