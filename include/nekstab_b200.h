@@ -340,6 +340,12 @@ int nsb_op_create_compose(nsb_layout_t layout, nsb_op_t outer, nsb_op_t inner, n
  * (core/matvec.f90:520-541; what ts_gmres / newton_krylov iterate on) and ts_force_sensitivity_map = I - exp(TL)^+
  * (core/matvec.f90:499-516).  All fields and %time take part, like k_sub2.  A and B stay owned by the caller. */
 int nsb_op_create_axpby(nsb_layout_t layout, nsb_op_t A, nsb_op_t B, double alpha, double beta, nsb_op_t *op);
+/* forward_finite_difference_map (core/matvec.f90:246-379, iffindiff): the linearised forward map as finite differences
+ * of a NONLINEAR map F (any operator handle; in the reference the nonlinear Nek stepper, i.e. a host callback) about
+ * the base state X = column col_base of base:  f = (1/eps0) sum_i coef_i F(X + amp_i eps0 q),  eps0 = 1e-6 |X|;
+ * order (findiff_order) 2: amp (1,-1), coef (1,-1)/2;  4: amp (1,-1,2,-2), coef (8,-8,-1,1)/12.  X is read at every
+ * application and stays owned by the caller; combine with nsb_op_create_axpby for newton_linearized_map. */
+int nsb_op_create_frechet_fd(nsb_layout_t layout, nsb_op_t F, nsb_basis_t base, int col_base, int order, nsb_op_t *op);
 /* Device time-stepper operator, the structure of exponential_prop%matvec
  * (core/linear_operators.f90:225-274: integrate over tau from a cold start, return the final state) for
  * Nek's scalar step cdscal [UPSTREAM-RECALL]: nsteps BDF/EXT steps (order ramp 1, 2, 3) of

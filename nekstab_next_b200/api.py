@@ -603,6 +603,14 @@ def axpby_operator(layout: Layout, A: LinearOperator | None, B: LinearOperator |
     return LinearOperator(layout.lib, h, keep=(layout, A, B))
 
 
+def frechet_operator(layout: Layout, F: LinearOperator, base: nek_dvector, order: int = 2) -> LinearOperator:
+    """forward_finite_difference_map (core/matvec.f90:246-379): finite-difference approximation of the Frechet
+    derivative of the nonlinear map F about ``base`` (read at every application), findiff_order 2 or 4."""
+    h = C.c_void_p()
+    check(layout.lib.nsb_op_create_frechet_fd(layout.h, F.h, base.basis.h, base.col, int(order), C.byref(h)))
+    return LinearOperator(layout.lib, h, keep=(layout, F, base.basis))
+
+
 def host_operator(layout: Layout, fn, linear: bool = False) -> LinearOperator:
     """Wrap a host matvec ``fn(fields_in, time_in) -> (fields_out, time_out)`` (the reference's
     time-stepper lives on the host); vectors cross PCIe around every call.  ``linear=True`` declares

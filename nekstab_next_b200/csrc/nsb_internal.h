@@ -233,7 +233,8 @@ struct nsb_sem_s {
 };
 
 struct nsb_op_s {
-  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.)), 3 / 4 device time-steppers, 5 alpha outer + beta inner
+  int kind = 0;                  // 0 sem, 1 host callback, 2 composition outer(inner(.)), 3 / 4 device time-steppers, 5 alpha outer + beta inner,
+                                 // 6 finite-difference Frechet derivative of outer about (base_b, base_c)
   nsb_op_t outer = nullptr, inner = nullptr;
   nsb_basis_t tmp = nullptr;     // work vector of the composition
   nsb_sem_t sem = nullptr;
@@ -256,6 +257,9 @@ struct nsb_op_s {
   int mean_free = 0, precond = 0;
   bool has_base = false;         // base flow in column 8 of tmp, its contravariant field in convection slot 0
   int64_t pres_iters = 0;        // pressure iterations spent so far
+  // kind 6: forward_finite_difference_map (core/matvec.f90:246-379)
+  nsb_basis_t base_b = nullptr;
+  int base_c = 0, fd_order = 2;
 };
 
 namespace nsb {

@@ -2084,6 +2084,58 @@ extern "C" int nsb_op_create_axpby(nsb_layout_t layout, nsb_op_t A, nsb_op_t B, 
   return NSB_OK;
 }
 
+// forward_finite_difference_map (core/matvec.f90:246-379): the linearised forward map approximated by finite
+// differences of a NONLINEAR map F (the reference's nonlinear Nek stepper; here any operator handle, typically a host
+// callback) about the base state X:
+//     f = (1/eps0) sum_i coef_i F(X + amp_i eps0 q),   eps0 = 1e-6 |X|   (k_norm, :276-277)
+// order 2: amp = (1, -1), coef = (1, -1)/2 ; order 4: amp = (1, -1, 2, -2), coef = (8, -8, -1, 1)/12  (:279-289).
+// Same order of operations as the reference: pert = amp q (:322-323), X + pert (:326-327), work = coef F (:367-368),
+// f += work (:369), f *= 1/eps0 (:374).  The base state stays owned by the caller and is read at every application
+// (newton_krylov updates it between linear solves).
+extern "C" int nsb_op_create_frechet_fd(nsb_layout_t layout, nsb_op_t F, nsb_basis_t base, int col_base, int order,
+                                        nsb_op_t *out) {
+  NSB_REQUIRE(layout && F && base && out, "nsb_op_create_frechet_fd: NULL argument");
+  NSB_REQUIRE(order == 2 || order == 4, "nsb_op_create_frechet_fd: findiff_order = %d (2 or 4)", order);
+  NSB_REQUIRE(base->lay == layout, "nsb_op_create_frechet_fd: base state has another layout");
+  NSB_REQUIRE(col_base >= 0 && col_base < base->ncols, "nsb_op_create_frechet_fd: column out of range");
+  nsb_op_t op = new nsb_op_s();
+  op->kind = 6;
+  op->lay = layout;
+  op->outer = F;
+  op->base_b = base;
+  op->base_c = col_base;
+  op->fd_order = order;
+  int r = nsb_basis_create(layout, 2, &op->tmp);
+  if (r != NSB_OK) {
+    delete op;
+    return r;
+  }
+  *out = op;
+  return NSB_OK;
+}
+
+namespace {
+int frechet_fd_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout) {
+  static const double amp2[2] = {1.0, -1.0}, coef2[2] = {0.5, -0.5};
+  static const double amp4[4] = {1.0, -1.0, 2.0, -2.0}, coef4[4] = {8.0 / 12.0, -8.0 / 12.0, -1.0 / 12.0, 1.0 / 12.0};
+  const double *amp = op->fd_order == 2 ? amp2 : amp4, *coef = op->fd_order == 2 ? coef2 : coef4;
+  double xnorm = 0.0;
+  NSB_CHECK(nsb_vec_norm(op->base_b, op->base_c, &xnorm));
+  NSB_REQUIRE(xnorm > 0.0, "forward_finite_difference_map: the base state has zero norm");
+  const double eps0 = 1e-6 * xnorm;
+  NSB_CHECK(nsb_vec_zero(bout, cout));
+  for (int i = 0; i < op->fd_order; ++i) {
+    NSB_CHECK(nsb_vec_copy(op->tmp, 0, bin, cin));
+    NSB_CHECK(nsb_vec_scal(op->tmp, 0, amp[i] * eps0));
+    NSB_CHECK(nsb_vec_add2(op->tmp, 0, op->base_b, op->base_c));
+    NSB_CHECK(nsb_op_apply(op->outer, op->tmp, 0, op->tmp, 1));
+    NSB_CHECK(nsb_vec_scal(op->tmp, 1, coef[i]));
+    NSB_CHECK(nsb_vec_add2(bout, cout, op->tmp, 1));
+  }
+  return nsb_vec_scal(bout, cout, 1.0 / eps0);
+}
+}  // namespace
+
 extern "C" int nsb_op_destroy(nsb_op_t op) {
   if (!op) return NSB_OK;
   if (op->sem) clear_step_graphs(op->sem->ctx);
@@ -2115,6 +2167,10 @@ extern "C" int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t b
     NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: composite operator built for another layout");
     NSB_CHECK(nsb_op_apply(op->inner, bin, cin, op->tmp, 0));
     return nsb_op_apply(op->outer, op->tmp, 0, bout, cout);
+  }
+  if (op->kind == 6) {
+    NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: finite-difference operator built for another layout");
+    return frechet_fd_apply(op, bin, cin, bout, cout);
   }
   if (op->kind == 5) {
     NSB_REQUIRE(bin->lay == op->lay, "nsb_op_apply: axpby operator built for another layout");

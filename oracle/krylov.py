@@ -120,6 +120,31 @@ def k_matmul(Q: Sequence[KVec], yvec: np.ndarray, k: int) -> KVec:
     return dq
 
 
+def forward_finite_difference_map(ctx, F: Callable[[KVec], KVec], base: KVec, q: KVec, order: int = 2) -> KVec:
+    """core/matvec.f90:246-379: the linearised forward map as finite differences of the nonlinear map F about the
+    base state: eps0 = 1e-6 |base| (:276-277), amplitudes / coefficients of :279-289, the loop of :319-371
+    (pert = amp q; F(base + pert); work *= coef; f += work) and the final 1/eps0 (:374)."""
+    eps0 = 1e-6 * k_norm(ctx, base)
+    if order == 2:
+        amp, coef = np.array([1.0, -1.0]), np.array([1.0, -1.0]) / 2.0
+    elif order == 4:
+        amp, coef = np.array([1.0, -1.0, 2.0, -2.0]), np.array([8.0, -8.0, -1.0, 1.0]) / 12.0
+    else:
+        raise ValueError('findiff_order is 2 or 4')
+    amp = amp * eps0
+    f = k_zero_like(q)
+    for a, cf in zip(amp, coef):
+        pert = q.copy()
+        k_cmult(pert, float(a))
+        x = base.copy()
+        k_add2(x, pert)
+        work = F(x)
+        k_cmult(work, float(cf))
+        k_add2(f, work)
+    k_cmult(f, 1.0 / eps0)
+    return f
+
+
 # ----------------------------------------------------------------------------
 # Arnoldi  (core/krylov_decomposition.f90)
 # ----------------------------------------------------------------------------

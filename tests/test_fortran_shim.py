@@ -151,3 +151,129 @@ def test_solver_entry_points_keep_the_reference_signatures():
             txt = (ref / fname).read_text().lower()
             m = re.search(rf'subroutine\s+{name}\s*\(([^)]*)\)', txt)
             assert m and [a.strip() for a in m.group(1).split(',')] == [a.strip() for a in args.split(',')], name
+
+
+def _joined_code(src):
+    """Free-form source with comments stripped and continuation lines joined."""
+    out, buf = [], ''
+    for raw in src.splitlines():
+        line, quote = '', None
+        for ch in raw:                       # drop `!` comments outside character literals
+            if quote:
+                quote = None if ch == quote else quote
+            elif ch in '\'"':
+                quote = ch
+            elif ch == '!':
+                break
+            line += ch
+        line = line.rstrip()
+        if buf and line.lstrip().startswith('&'):
+            line = line.lstrip()[1:]
+        if line.endswith('&'):
+            buf += line[:-1] + ' '
+            continue
+        out.append(buf + line)
+        buf = ''
+    return out
+
+
+def _call_args(text, start):
+    """Top-level arguments of the parenthesised list opening at text[start] == '('."""
+    depth, args, cur, quote = 0, [], '', None
+    for i in range(start, len(text)):
+        ch = text[i]
+        if quote:
+            cur += ch
+            quote = None if ch == quote else quote
+            continue
+        if ch in '\'"':
+            quote = ch
+            cur += ch
+        elif ch in '([':
+            depth += 1
+            cur += ch if depth > 1 else ''
+        elif ch in ')]':
+            depth -= 1
+            if depth == 0:
+                if cur.strip():
+                    args.append(cur.strip())
+                return args
+            cur += ch
+        elif ch == ',' and depth == 1:
+            args.append(cur.strip())
+            cur = ''
+        else:
+            cur += ch
+    raise AssertionError('unbalanced parentheses')
+
+
+def test_call_sites_pass_as_many_arguments_as_the_interfaces_take():
+    """What the missing compiler would reject first: every reference to a bind(C) function inside the module's and the
+    adapter's procedures hands over exactly the dummies its interface block declares."""
+    src = (F90 / 'nekstab_b200.f90').read_text()
+    arity = {c: len(a) for c, (_, a, _) in fortran_interfaces(src).items()}
+    checked = 0
+    for f in F90.glob('*.f90'):
+        lines = _joined_code(f.read_text())
+        inside_interface = False
+        for ln in lines:
+            low = ln.strip().lower()
+            if re.match(r'interface\b', low):
+                inside_interface = True
+            elif re.match(r'end\s+interface\b', low):
+                inside_interface = False
+            if inside_interface or re.match(r'(public|private)\b', low):
+                continue
+            for m in re.finditer(r'\b(nsb_\w+)\s*\(', ln):
+                name = m.group(1)
+                if name not in arity:
+                    continue                                   # module procedures such as nsb_check(ierr, where)
+                got = _call_args(ln, m.end() - 1)
+                assert len(got) == arity[name], f'{f.name}: `{ln.strip()}` passes {len(got)} arguments, ' \
+                                                f'{name} takes {arity[name]}'
+                checked += 1
+    assert checked >= 40
+
+
+def test_an_independent_parser_reads_the_module():
+    """numpy.f2py's Fortran front end (the parser f2py builds wrappers from) reads the module: the same bind(C)
+    functions with the same dummy lists as the regular-expression reader above finds, by-value attributes included."""
+    from numpy.f2py import crackfortran
+    import contextlib
+    import io
+    import os
+    crackfortran.verbose = 0
+    cwd = os.getcwd()
+    with contextlib.redirect_stdout(io.StringIO()):
+        try:
+            tree = crackfortran.crackfortran([str(F90 / 'nekstab_b200.f90')])
+        finally:
+            os.chdir(cwd)
+    assert len(tree) == 1 and tree[0]['block'] == 'module' and tree[0]['name'] == 'nekstab_b200'
+    found = {}
+    for blk in tree[0]['body']:
+        if blk['block'] != 'interface':
+            continue
+        for fn in blk['body']:
+            if fn['block'] == 'function' and fn['name'].startswith('nsb_'):
+                found[fn['name']] = fn
+    ifs = fortran_interfaces((F90 / 'nekstab_b200.f90').read_text())
+    assert set(found) == set(ifs)
+    protos = c_prototypes()
+    rename = lambda a: a[:-3] if a.endswith('_bn') else a          # f2py renames dummies that shadow intrinsics
+    for name, fn in found.items():
+        _, args, decl = ifs[name]
+        assert [rename(a) for a in fn['args']] == [a.lower() for a in args], name
+        assert len(fn['args']) == len(protos[name]), name
+        for a, cp in zip(fn['args'], protos[name]):
+            var = fn['vars'][a]
+            by_value = 'value' in var.get('attrspec', [])
+            if '*' not in cp:
+                assert by_value, f'{name}: {a} must be passed by value'
+                ctype = ' '.join(cp.replace('const', '').split()[:-1])
+                want = {'int': ('integer', 'c_int'), 'double': ('real', 'c_double'), 'int64_t': ('integer', 'c_int64_t'),
+                        'uint64_t': ('integer', 'c_int64_t')}.get(ctype)
+                if want:
+                    assert var['typespec'] == want[0] and var['kindselector']['kind'] == want[1], (name, a, var)
+                else:
+                    assert var['typespec'] == 'type' and var['typename'] in ('c_ptr', 'c_funptr'), (name, a, var)

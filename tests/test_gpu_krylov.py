@@ -273,6 +273,54 @@ def test_axpby_operator_and_newton_map(ctx):
         o.close()
 
 
+@pytest.mark.parametrize('order', [2, 4])
+def test_frechet_finite_difference_operator(ctx, order):
+    """forward_finite_difference_map (core/matvec.f90:246-379, iffindiff): finite differences of a nonlinear host map
+    about a base state kept on the device, against the literal restatement and the analytic Jacobian; then as the
+    Jacobian of newton_linearized_map (minus the identity) under one Arnoldi step."""
+    import nekstab_next_b200 as nb
+    P = BoxProblem(nel=(2, 2, 2), N=4, nfields=2, alpha=1.0, seed=29 + order)
+    c = P.octx()
+    lay, B, S, op = P.gpu(ctx, 6)
+
+    def F(x):                                                      # nonlinear map: M x + 0.3 x^3 (pointwise)
+        y = P.omatvec(x)
+        for a, b in zip(y.f, x.f):
+            a += 0.3 * b ** 3
+        return y
+
+    def host_F(fields, t):
+        y = F(okr.KVec([f.reshape(P.shape).copy() for f in fields], t))
+        return [a.ravel() for a in y.f], y.time
+
+    Fop = nb.host_operator(lay, host_F)
+    X, q = P.random_kvec(), P.random_kvec()
+    upload(B[0], X)
+    upload(B[1], q)
+    J = nb.frechet_operator(lay, Fop, B[0], order)
+    J.matvec(B[1], B[2])
+    got = download(B[2], P.shape)
+    ref = okr.forward_finite_difference_map(c, F, X, q, order)
+    exact = P.omatvec(q)
+    for a, b, x in zip(exact.f, q.f, X.f):
+        a += 0.9 * x * x * b
+    for g, r, e in zip(got.f, ref.f, exact.f):
+        assert relerr(g, r) <= 1e-9
+        assert relerr(g, e) <= 1e-7
+    assert Fop.count() == order and J.count() == 1
+    newton = nb.axpby_operator(lay, J, None, 1.0, -1.0)            # Jacobian of the fixed-point residual F(x) - x
+    upload(B[3], q)
+    beta = nb.k_normalize(B[3])
+    newton.matvec(B[3], B[4])
+    w = download(B[4], P.shape)
+    for g, e, b in zip(w.f, exact.f, q.f):
+        assert relerr(g, (e - b) / beta) <= 1e-7
+    with pytest.raises(nb.NsbError):
+        nb.frechet_operator(lay, Fop, B[0], 3)
+    for o in (newton, J, Fop):
+        o.close()
+
+
 def test_eigs_stepwise(ctx):
     """The LightKrylov-path eigensolver (core/linear_stab.f90:66): same stopping step, same Ritz values."""
     import nekstab_next_b200 as nb

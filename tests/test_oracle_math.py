@@ -2,6 +2,7 @@
 against independent mathematics on the CPU: Gauss-Legendre dealiasing operators, EXT/BDF coefficients,
 the LightKrylov-style eigs / svds drivers against numpy's dense solvers."""
 import numpy as np
+import pytest
 
 from oracle import krylov as okr
 from oracle import sem as osem
@@ -135,3 +136,27 @@ def test_adjoint_stepper_oracle_is_the_discrete_adjoint():
             Atv = osem.scalar_steps_adjoint(glo, mask, geo, N, cf, dl, v, 0.05, 5e-3, nsteps)
             l, r = np.sum(geo['bm1'] * Au * v), np.sum(geo['bm1'] * u * Atv)
             assert abs(l - r) <= 1e-10 * np.sqrt(np.sum(geo['bm1'] * u * u) * np.sum(geo['bm1'] * v * v)), (dim, nsteps, l, r)
+
+
+@pytest.mark.parametrize('order', [2, 4])
+def test_finite_difference_frechet_map(order):
+    """forward_finite_difference_map (core/matvec.f90:246-379): for F(x) = A x + 0.3 x^3 the differences reproduce
+    the Jacobian A q + 0.9 X^2 q up to the truncation error (eps0^2 and eps0^4, both below rounding here) and the
+    rounding noise 1e-16 |F| / eps0; a linear map is reproduced whatever the base state."""
+    from oracle import krylov as okr
+    rng = np.random.default_rng(5 + order)
+    n = 200
+    A = rng.standard_normal((n, n)) / np.sqrt(n)
+    c = okr.Ctx(bm1s=rng.uniform(0.5, 1.5, n), in_dot=[True], time_in_dot=True)
+    X = okr.KVec([rng.standard_normal(n)], 0.7)
+    q = okr.KVec([rng.standard_normal(n)], -0.2)
+    F = lambda x: okr.KVec([A @ x.f[0] + 0.3 * x.f[0] ** 3], 2.0 * x.time)
+    f = okr.forward_finite_difference_map(c, F, X, q, order)
+    exact = A @ q.f[0] + 0.9 * X.f[0] ** 2 * q.f[0]
+    assert np.max(np.abs(f.f[0] - exact)) <= 1e-8 * np.max(np.abs(exact))
+    assert abs(f.time - 2.0 * q.time) <= 1e-8
+    L = lambda x: okr.KVec([A @ x.f[0]], x.time)
+    g = okr.forward_finite_difference_map(c, L, X, q, order)
+    assert np.max(np.abs(g.f[0] - A @ q.f[0])) <= 1e-8 * np.max(np.abs(A @ q.f[0]))
+    with pytest.raises(ValueError):
+        okr.forward_finite_difference_map(c, F, X, q, 3)
