@@ -420,6 +420,12 @@ int nsb_op_create_ns_stepper(nsb_sem_t sem, nsb_layout_t layout, nsb_basis_t bas
 int nsb_op_create_ns_stepper_adjoint(nsb_sem_t sem, nsb_layout_t layout, nsb_basis_t base, int col_base, double nu,
                                      double dt, int nsteps, double tol_v, double tol_p, int maxit, int mean_free,
                                      int precond, nsb_op_t *op);
+/* Time-periodic base flow (Floquet analysis / Newton for periodic orbits): the stored orbit uor / vor / wor(:, istep) of
+ * core/linear_operators.f90:254-275 and core/matvec.f90:347-362 as a run of columns of a device basis with the
+ * operator's layout -- step n of every application linearises about column col0 + (n-1) stride (the reference's step
+ * istep runs with uor(:, istep-1), uor(:, 0) = ubase; stride -1 walks the orbit backwards).  For operators created
+ * with a base flow, forward or adjoint; orbit = NULL returns to the steady base flow.  The basis stays the caller's. */
+int nsb_op_ns_set_orbit(nsb_op_t op, nsb_basis_t orbit, int col0, int stride);
 int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure);
 int nsb_op_destroy(nsb_op_t op);
 int nsb_op_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);

@@ -121,6 +121,7 @@ PROTOTYPES = {
                                            C.c_int, C.c_int, C.c_int, c_void_pp]),
     'nsb_op_create_ns_stepper_adjoint': (C.c_int, [H, H, H, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
                                                    C.c_double, C.c_int, C.c_int, C.c_int, c_void_pp]),
+    'nsb_op_ns_set_orbit': (C.c_int, [H, H, C.c_int, C.c_int]),
     'nsb_op_ns_iterations': (C.c_int, [H, c_i64_p, c_i64_p]),
     'nsb_op_destroy': (C.c_int, [H]),
     'nsb_op_apply': (C.c_int, [H, H, C.c_int, H, C.c_int]),

@@ -560,6 +560,13 @@ def ns_stepper_operator(sem: Sem, layout: Layout, base: nek_dvector | None, nu: 
     return LinearOperator(sem.lib, h, keep=(sem, layout))
 
 
+def ns_set_orbit(op: LinearOperator, orbit: Basis | None, col0: int = 0, stride: int = 1):
+    """Time-periodic base flow: step n of the Navier-Stokes stepper linearises about column col0 + (n-1) stride of
+    ``orbit`` (the stored uor / vor / wor of core/linear_operators.f90:254-275); None: the steady base flow again."""
+    check(op.lib.nsb_op_ns_set_orbit(op.h, orbit.h if orbit is not None else None, int(col0), int(stride)))
+    op._keep = (op._keep, orbit)
+
+
 def ns_iterations(op: LinearOperator):
     """(Helmholtz iterations, pressure iterations) a Navier-Stokes stepper operator has spent so far."""
     a, b = C.c_int64(), C.c_int64()

@@ -257,6 +257,9 @@ struct nsb_op_s {
   int mean_free = 0, precond = 0;
   bool has_base = false;         // base flow in column 8 of tmp, its contravariant field in convection slot 0
   int64_t pres_iters = 0;        // pressure iterations spent so far
+  nsb_basis_t orbit_b = nullptr; // kind 4: time-periodic base flow, step n linearises about column orbit_c0 + (n-1) orbit_stride
+  int orbit_c0 = 0, orbit_stride = 1;
+  bool c_dirty = false;          // kind 4, adjoint: c_d holds the gradient of an orbit column, not of the steady base flow
   // kind 6: forward_finite_difference_map (core/matvec.f90:246-379)
   nsb_basis_t base_b = nullptr;
   int base_c = 0, fd_order = 2;

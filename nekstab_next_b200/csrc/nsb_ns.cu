@@ -1611,6 +1611,29 @@ extern "C" int nsb_op_create_ns_stepper_adjoint(nsb_sem_t S, nsb_layout_t layout
   return NSB_OK;
 }
 
+// Time-periodic base flows (Floquet analysis, Newton for periodic orbits): the reference stores the orbit of the
+// nonlinear solution, uor / vor / wor(:, istep), and copies it into vx after every step of the linearised solver
+// (core/linear_operators.f90:254-275, core/matvec.f90:347-362), so step istep linearises about uor(:, istep-1) with
+// uor(:, 0) = ubase.  Here the orbit is a run of columns of a device basis: step n uses column col0 + (n-1) stride
+// (stride -1 walks it backwards for the adjoint).  orbit = NULL: back to the steady base flow of the constructor.
+extern "C" int nsb_op_ns_set_orbit(nsb_op_t op, nsb_basis_t orbit, int col0, int stride) {
+  NSB_REQUIRE(op && op->kind == 4, "nsb_op_ns_set_orbit: not a Navier-Stokes stepper operator");
+  if (!orbit) {
+    op->orbit_b = nullptr;
+    return NSB_OK;
+  }
+  NSB_REQUIRE(op->has_base, "nsb_op_ns_set_orbit: the operator was created without a base flow (Stokes)");
+  NSB_REQUIRE(orbit->lay == op->lay, "nsb_op_ns_set_orbit: the orbit must be stored in a basis with the operator's layout");
+  const int last = col0 + (op->nsteps - 1) * stride;
+  NSB_REQUIRE(col0 >= 0 && col0 < orbit->ncols && last >= 0 && last < orbit->ncols,
+              "nsb_op_ns_set_orbit: %d steps from column %d with stride %d leave the basis (%d columns)", op->nsteps, col0,
+              stride, orbit->ncols);
+  op->orbit_b = orbit;
+  op->orbit_c0 = col0;
+  op->orbit_stride = stride;
+  return NSB_OK;
+}
+
 extern "C" int nsb_op_ns_iterations(nsb_op_t op, int64_t *helmholtz, int64_t *pressure) {
   NSB_REQUIRE(op && op->kind == 4, "nsb_op_ns_iterations: not a Navier-Stokes stepper operator");
   if (helmholtz) *helmholtz = op->helm_iters;
@@ -1642,9 +1665,33 @@ int nsb::ns_stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bou
     NSB_CUDA(cudaMemcpyAsync(vel(lag[0]) + f * fs, bin->col(cin) + L->off[f], sizeof(double) * S->npts,
                              cudaMemcpyDeviceToDevice, st));
   NSB_CUDA(cudaMemcpyAsync(prs(0), bin->col(cin) + L->off[dim], sizeof(double) * n2, cudaMemcpyDeviceToDevice, st));
+  // the base flow this step linearises about: the steady one (column cU of W) or a column of the stored orbit.  Slot 0
+  // of the mesh is shared by every operator built on it, so it is refreshed at every application.
+  nsb_basis_t Ub = W;
+  int Uc = cU;
+  auto set_base = [&](bool grad) -> int {
+    NSB_CHECK(nsb_sem_set_convect(S, 0, Ub, Uc, 0));
+    if (grad && op->adjoint) {
+      grad_base_kernel<<<(unsigned)((S->npts + 255) / 256), 256, 0, st>>>(dim, S->lx, Ub->col(Uc) + L->off[0], fs, S->rst_d,
+                                                                        S->bm1_d, S->jac_d, S->D_d, S->npts, op->c_d);
+      ctx->launches++;
+      NSB_CUDA(cudaGetLastError());
+    }
+    return NSB_OK;
+  };
+  if (op->has_base && !op->orbit_b) {
+    NSB_CHECK(set_base(op->c_dirty));
+    op->c_dirty = false;
+  }
   for (int n = 1; n <= op->nsteps; ++n) {
     const int o = n < 3 ? n : 3;
     const double bd0 = kBDn[o][0];
+    if (op->has_base && op->orbit_b) {
+      Ub = op->orbit_b;
+      Uc = op->orbit_c0 + (n - 1) * op->orbit_stride;
+      NSB_CHECK(set_base(true));
+      op->c_dirty = true;          // the gradient of the steady base flow has to be rebuilt once the orbit is dropped
+    }
     // advabp: bf = -[(U.grad) v + (v.grad) U], mass matrix inside the dealiased quadrature
     if (op->has_base && op->adjoint) {
       // adjoint advabp: +(U.grad) w - sum_c w_c grad U_c
@@ -1654,7 +1701,7 @@ int nsb::ns_stepper_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bou
     } else if (op->has_base) {
       NSB_CHECK(nsb_sem_convect(S, 0, W, lag[0], W, bf, 0, dim, -1.0, 0));
       NSB_CHECK(nsb_sem_set_convect(S, 1, W, lag[0], 0));
-      NSB_CHECK(nsb_sem_convect(S, 1, W, cU, W, bf, 0, dim, -1.0, 1));
+      NSB_CHECK(nsb_sem_convect(S, 1, Ub, Uc, W, bf, 0, dim, -1.0, 1));
     } else {
       for (int f = 0; f < dim; ++f) NSB_CUDA(cudaMemsetAsync(vel(bf) + f * fs, 0, sizeof(double) * S->npts, st));
     }

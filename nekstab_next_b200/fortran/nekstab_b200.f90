@@ -495,6 +495,13 @@ module nekstab_b200
          type(c_ptr) :: op
          integer(c_int) :: ierr
       end function
+      !> stored orbit of a time-periodic base flow (core/linear_operators.f90:254-275): step n uses column col0 + (n-1) stride
+      function nsb_op_ns_set_orbit(op, orbit, col0, stride) bind(C, name='nsb_op_ns_set_orbit') result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: op, orbit
+         integer(c_int), value :: col0, stride
+         integer(c_int) :: ierr
+      end function
       function nsb_op_create_compose(layout, outer, inner, op) bind(C, name='nsb_op_create_compose') result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: layout, outer, inner
@@ -628,7 +635,7 @@ module nekstab_b200
    public :: nsb_sem_create, nsb_sem_destroy, nsb_sem_setup_exchange, nsb_sem_axhelm, nsb_sem_ax, nsb_sem_dssum
    public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_hmholtz_vec, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
    public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose, nsb_op_create_axpby
-   public :: nsb_op_create_frechet_fd
+   public :: nsb_op_create_frechet_fd, nsb_op_ns_set_orbit
    public :: nsb_sem_pressure_setup, nsb_op_create_ns_stepper, nsb_op_create_ns_stepper_adjoint
    public :: nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues

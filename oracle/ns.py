@@ -275,7 +275,7 @@ def advabp_adjoint(vel, cf_base, G, dl):
 
 
 def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=True,
-             maxit=4000, info=None, fdm=None, adjoint=False):
+             maxit=4000, info=None, fdm=None, adjoint=False, orbit=None):
     """nsteps BDF/EXT steps (order ramp 1, 2, 3, cold start) of the linearised incompressible Navier-Stokes equations
         dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v ,  div v = 0
     in the P_N - P_N-2 splitting:
@@ -284,7 +284,10 @@ def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1
         v*   = H^-1 mask dssum(bf + D^T p*),   H = nu A + (bd_0/dt) B           (cresvipp + ophinv)
         E dp = -(bd_0/dt) D v* ;  v = v* + (dt/bd_0) B^-1 D^T dp ;  p = p* + dp (incomprp)
     base = None: Stokes.  adjoint = True: the same stepper on the adjoint equations (explicit term advabp_adjoint), what
-    Nek runs for exponential_prop%rmatvec.  Returns (velocity list, pressure)."""
+    Nek runs for exponential_prop%rmatvec.  orbit = [U_1, ..., U_nsteps]: the base flow step s linearises about
+    (time-periodic base flows: the stored orbit uor / vor / wor of core/linear_operators.f90:254-275 -- step istep runs
+    with what was copied into vx after step istep-1, i.e. U_1 = ubase, U_s = uor(:, s-1)); `base` is then unused.
+    Returns (velocity list, pressure)."""
     d = osem.dgll(n)
     dim = ps['dim']
     bm1 = geo['bm1']
@@ -299,6 +302,10 @@ def ns_steps(glo, mask, geo, n, ps, dl, base, vel0, pr0, nu, dt, nsteps, tol_v=1
     for s in range(1, nsteps + 1):
         o = min(s, 3)
         bd0 = osem.BD[o][0]
+        if orbit is not None:
+            base = orbit[s - 1]
+            cf_base = osem.set_convect(base, dl)
+            G = grad_base(base, geo, n) if adjoint else None
         if base is None:
             bf = [0 * v for v in vel0]
         elif adjoint:

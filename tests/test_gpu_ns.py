@@ -381,3 +381,64 @@ def test_transient_growth_and_newton_map_on_the_ns_propagators(ctx):
         assert np.max(np.abs(a - b)) <= 1e-7 * np.max(np.abs(b))
     for o in (newton, fwd, adj, W, V, U, lay, sem):
         o.close()
+
+
+@pytest.mark.parametrize('adjoint', [False, True])
+def test_ns_stepper_with_a_stored_orbit(ctx, adjoint):
+    """Time-periodic base flow (the stored orbit uor / vor / wor of core/linear_operators.f90:254-275): every step
+    linearises about its own column.  Against the oracle stepping through the same orbit; an orbit of identical
+    columns reproduces the steady operator bit for bit, and so does dropping the orbit again."""
+    import nekstab_next_b200 as nb
+    N, nsteps, nu, dt = 5, 4, 0.05, 2e-3
+    P = NsProblem((3, 3), N, seed=41)
+    orbit = [[(1.0 + 0.3 * np.sin(0.9 * s)) * P.base[0] + 0.05 * s * P.coords[1],
+              (1.0 - 0.2 * s) * P.base[1] + 0.1 * np.cos(s + P.coords[0])] for s in range(nsteps)]
+    v0, p0 = P.vel(), 0 * P.pres()
+    fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv)
+    vo, po = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base, v0, p0, nu, dt, nsteps, mean_free=False, fdm=fd,
+                          adjoint=adjoint, orbit=orbit)
+    vr, _ = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base, v0, p0, nu, dt, nsteps, mean_free=False, fdm=fd,
+                         adjoint=adjoint, orbit=orbit[::-1])
+    sem, lay, B = P.gpu(ctx, 5)
+    O = nb.Basis(lay, nsteps)
+    sem.dealias_setup()
+    P.up(B[4], P.base, p0)
+    op = nb.ns_stepper_operator(sem, lay, B[4], nu, dt, nsteps, tol_v=1e-13, tol_p=1e-13, mean_free=False, adjoint=adjoint)
+    P.up(B[0], v0, p0)
+    op.matvec(B[0], B[1])                                           # steady base flow
+    for s in range(nsteps):
+        P.up(O[s], orbit[s], p0)
+    nb.ns_set_orbit(op, O, 0, 1)
+    op.matvec(B[0], B[2])
+    v, p = P.down(B[2])
+    scale = max(np.max(np.abs(a)) for a in vo)
+    for a, b in zip(v, vo):
+        assert np.max(np.abs(a - b)) <= 1e-9 * scale
+    steady, _ = P.down(B[1])
+    assert max(np.max(np.abs(a - b)) for a, b in zip(v, steady)) > 1e-4 * scale       # the orbit matters
+    nb.ns_set_orbit(op, O, nsteps - 1, -1)                          # walked backwards
+    op.matvec(B[0], B[2])
+    v, _ = P.down(B[2])
+    for a, b in zip(v, vr):
+        assert np.max(np.abs(a - b)) <= 1e-9 * scale
+    for s in range(nsteps):                                         # an orbit that stands still
+        P.up(O[s], P.base, p0)
+    nb.ns_set_orbit(op, O, 0, 1)
+    op.matvec(B[0], B[2])
+    f1, _ = B[1].download()
+    f2, _ = B[2].download()
+    assert all(np.array_equal(a, b) for a, b in zip(f1, f2))
+    for s in range(nsteps):
+        P.up(O[s], orbit[s], p0)
+    op.matvec(B[0], B[3])                                           # leaves the gradient of the last orbit column behind
+    nb.ns_set_orbit(op, None)
+    op.matvec(B[0], B[2])
+    f2, _ = B[2].download()
+    assert all(np.array_equal(a, b) for a, b in zip(f1, f2))
+    with pytest.raises(nb.NsbError):                                # the orbit is shorter than the operator's horizon
+        nb.ns_set_orbit(op, O, 1, 1)
+    stokes = nb.ns_stepper_operator(sem, lay, None, nu, dt, nsteps)
+    with pytest.raises(nb.NsbError):
+        nb.ns_set_orbit(stokes, O, 0, 1)
+    for o in (stokes, op, O, B, lay, sem):
+        o.close()

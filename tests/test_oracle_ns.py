@@ -209,3 +209,35 @@ def test_adjoint_stepper_is_dual_to_the_forward_one():
     lhs, rhs, wrong = dot(Av, w0), dot(v0, Atw), dot(v0, Aw)
     assert abs(lhs - rhs) <= 1e-5 * abs(lhs), (lhs, rhs)
     assert abs(lhs - wrong) >= 1000 * abs(lhs - rhs), (lhs, rhs, wrong)
+
+
+@pytest.mark.parametrize('adjoint', [False, True])
+def test_stored_orbit_of_a_time_periodic_base_flow(adjoint):
+    """ns_steps(orbit=...): every step linearises about its own base flow (core/linear_operators.f90:254-275).  An
+    orbit that stands still is the steady stepper bit for bit; the map stays linear in the perturbation; and the
+    result depends on the orbit only through the steps actually taken (changing the column of a later step than the
+    horizon's last does nothing, changing the first one does)."""
+    N = 5
+    m = setup(2, (2, 2), N, deform=0.03)
+    x, y = m['coords']
+    base = [1.0 + 0.3 * np.sin(np.pi * y), 0.4 * np.cos(np.pi * x)]
+    rng = np.random.default_rng(11)
+    vmult = 1.0 / osem.multiplicity(m['glo'])
+    field = lambda: osem.dssum(rng.standard_normal(x.shape), m['glo']) * vmult * m['mask']
+    v0, w0, p0 = [field(), field()], [field(), field()], 0 * m['ps']['bm2']
+    nu, dt, nst = 0.05, 2e-3, 3
+    run = lambda q, orb: ons.ns_steps(m['glo'], m['mask'], m['geo'], N, m['ps'], m['dl'], base, q, p0, nu, dt, nst,
+                                      mean_free=False, adjoint=adjoint, orbit=orb)[0]
+    still = run(v0, [base] * nst)
+    steady = run(v0, None)
+    assert all(np.array_equal(a, b) for a, b in zip(still, steady))
+    orbit = [[(1.0 + 0.2 * s) * base[0], base[1] + 0.1 * s * x] for s in range(nst)]
+    a, b = run(v0, orbit), run(w0, orbit)
+    c = run([2.0 * p - 0.5 * q for p, q in zip(v0, w0)], orbit)
+    scale = max(np.max(np.abs(f)) for f in a)
+    assert max(np.max(np.abs(f - (2.0 * p - 0.5 * q))) for f, p, q in zip(c, a, b)) <= 1e-9 * scale
+    assert max(np.max(np.abs(p - q)) for p, q in zip(a, steady)) > 1e-5 * scale
+    longer = run(v0, orbit + [[0 * x, 0 * x]])
+    assert all(np.array_equal(p, q) for p, q in zip(a, longer))
+    other = run(v0, [[0 * x, 0 * x]] + orbit[1:])
+    assert max(np.max(np.abs(p - q)) for p, q in zip(a, other)) > 1e-5 * scale
