@@ -346,6 +346,8 @@ int nsb_op_create_axpby(nsb_layout_t layout, nsb_op_t A, nsb_op_t B, double alph
  * order (findiff_order) 2: amp (1,-1), coef (1,-1)/2;  4: amp (1,-1,2,-2), coef (8,-8,-1,1)/12.  X is read at every
  * application and stays owned by the caller; combine with nsb_op_create_axpby for newton_linearized_map. */
 int nsb_op_create_frechet_fd(nsb_layout_t layout, nsb_op_t F, nsb_basis_t base, int col_base, int order, nsb_op_t *op);
+/* epsilon_base (core/main.f90:16, default 1e-6; the new API's eps0 = epsilon_base |X|, core/linear_operators.f90:192). */
+int nsb_op_frechet_set_epsilon(nsb_op_t op, double epsilon_base);
 /* Device time-stepper operator, the structure of exponential_prop%matvec
  * (core/linear_operators.f90:225-274: integrate over tau from a cold start, return the final state) for
  * Nek's scalar step cdscal [UPSTREAM-RECALL]: nsteps BDF/EXT steps (order ramp 1, 2, 3) of

@@ -103,6 +103,7 @@ PROTOTYPES = {
     'nsb_op_create_compose': (C.c_int, [H, H, H, c_void_pp]),
     'nsb_op_create_axpby': (C.c_int, [H, H, H, C.c_double, C.c_double, c_void_pp]),
     'nsb_op_create_frechet_fd': (C.c_int, [H, H, H, C.c_int, C.c_int, c_void_pp]),
+    'nsb_op_frechet_set_epsilon': (C.c_int, [H, C.c_double]),
     'nsb_op_create_stepper': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                         C.c_double, C.c_int, c_void_pp]),
     'nsb_op_create_stepper_adjoint': (C.c_int, [H, H, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,

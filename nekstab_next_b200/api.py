@@ -610,11 +610,14 @@ def axpby_operator(layout: Layout, A: LinearOperator | None, B: LinearOperator |
     return LinearOperator(layout.lib, h, keep=(layout, A, B))
 
 
-def frechet_operator(layout: Layout, F: LinearOperator, base: nek_dvector, order: int = 2) -> LinearOperator:
+def frechet_operator(layout: Layout, F: LinearOperator, base: nek_dvector, order: int = 2,
+                     epsilon_base: float | None = None) -> LinearOperator:
     """forward_finite_difference_map (core/matvec.f90:246-379): finite-difference approximation of the Frechet
     derivative of the nonlinear map F about ``base`` (read at every application), findiff_order 2 or 4."""
     h = C.c_void_p()
     check(layout.lib.nsb_op_create_frechet_fd(layout.h, F.h, base.basis.h, base.col, int(order), C.byref(h)))
+    if epsilon_base is not None:
+        check(layout.lib.nsb_op_frechet_set_epsilon(h, float(epsilon_base)))
     return LinearOperator(layout.lib, h, keep=(layout, F, base.basis))
 
 

@@ -2105,12 +2105,21 @@ extern "C" int nsb_op_create_frechet_fd(nsb_layout_t layout, nsb_op_t F, nsb_bas
   op->base_b = base;
   op->base_c = col_base;
   op->fd_order = order;
+  op->h1 = 1e-6;   // epsilon_base (core/main.f90:16)
   int r = nsb_basis_create(layout, 2, &op->tmp);
   if (r != NSB_OK) {
     delete op;
     return r;
   }
   *out = op;
+  return NSB_OK;
+}
+
+// epsilon_base of the reference (core/main.f90:16, default 1e-6; core/linear_operators.f90:192): eps0 = epsilon_base |X|
+extern "C" int nsb_op_frechet_set_epsilon(nsb_op_t op, double epsilon_base) {
+  NSB_REQUIRE(op && op->kind == 6, "nsb_op_frechet_set_epsilon: not a finite-difference operator");
+  NSB_REQUIRE(epsilon_base > 0.0, "nsb_op_frechet_set_epsilon: epsilon_base = %g", epsilon_base);
+  op->h1 = epsilon_base;
   return NSB_OK;
 }
 
@@ -2122,7 +2131,7 @@ int frechet_fd_apply(nsb_op_t op, nsb_basis_t bin, int cin, nsb_basis_t bout, in
   double xnorm = 0.0;
   NSB_CHECK(nsb_vec_norm(op->base_b, op->base_c, &xnorm));
   NSB_REQUIRE(xnorm > 0.0, "forward_finite_difference_map: the base state has zero norm");
-  const double eps0 = 1e-6 * xnorm;
+  const double eps0 = op->h1 * xnorm;   // op->h1 = epsilon_base
   NSB_CHECK(nsb_vec_zero(bout, cout));
   for (int i = 0; i < op->fd_order; ++i) {
     NSB_CHECK(nsb_vec_copy(op->tmp, 0, bin, cin));

@@ -120,11 +120,12 @@ def k_matmul(Q: Sequence[KVec], yvec: np.ndarray, k: int) -> KVec:
     return dq
 
 
-def forward_finite_difference_map(ctx, F: Callable[[KVec], KVec], base: KVec, q: KVec, order: int = 2) -> KVec:
+def forward_finite_difference_map(ctx, F: Callable[[KVec], KVec], base: KVec, q: KVec, order: int = 2,
+                                  epsilon_base: float = 1e-6) -> KVec:
     """core/matvec.f90:246-379: the linearised forward map as finite differences of the nonlinear map F about the
     base state: eps0 = 1e-6 |base| (:276-277), amplitudes / coefficients of :279-289, the loop of :319-371
     (pert = amp q; F(base + pert); work *= coef; f += work) and the final 1/eps0 (:374)."""
-    eps0 = 1e-6 * k_norm(ctx, base)
+    eps0 = epsilon_base * k_norm(ctx, base)          # epsilon_base: core/main.f90:16
     if order == 2:
         amp, coef = np.array([1.0, -1.0]), np.array([1.0, -1.0]) / 2.0
     elif order == 4:

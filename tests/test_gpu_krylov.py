@@ -308,6 +308,12 @@ def test_frechet_finite_difference_operator(ctx, order):
         assert relerr(g, r) <= 1e-9
         assert relerr(g, e) <= 1e-7
     assert Fop.count() == order and J.count() == 1
+    J5 = nb.frechet_operator(lay, Fop, B[0], order, epsilon_base=1e-5)      # epsilon_base of core/main.f90:16
+    J5.matvec(B[1], B[5])
+    ref5 = okr.forward_finite_difference_map(c, F, X, q, order, epsilon_base=1e-5)
+    for g, r in zip(download(B[5], P.shape).f, ref5.f):
+        assert relerr(g, r) <= 1e-9
+    J5.close()
     newton = nb.axpby_operator(lay, J, None, 1.0, -1.0)            # Jacobian of the fixed-point residual F(x) - x
     upload(B[3], q)
     beta = nb.k_normalize(B[3])
