@@ -402,6 +402,10 @@ int nsb_sem_opgradt(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, i
 int nsb_sem_cdabdtp(nsb_sem_t sem, nsb_basis_t bin, int cin, nsb_basis_t bout, int cout);
 int nsb_sem_esolve(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, int cx, double tol, int maxit,
                    int mean_free, int precond, int *iters, double *res);
+/* norm_grad (core/utils.f90:446-486): sum_c sum_b glsc3(du_c/dx_b, bm1s, du_c/dx_b) of the velocity fields 0..dim-1 of
+ * (b, col), gradm1 collocation derivatives, the layout's weight, summed over all ranks; NOT a square root -- the
+ * number outpost_ks compares with 1.1 to skip spurious Ritz vectors (core/eigensolvers.f90:587-594). */
+int nsb_sem_norm_grad(nsb_sem_t sem, nsb_basis_t b, int col, double *norma);
 /* exponential_prop%matvec for the linearised incompressible Navier-Stokes equations, device-resident:
  *     dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v,   div v = 0,   v = 0 where the mesh mask is 0.
  * The input vector's velocity and pressure start nsteps BDF/EXT steps (order ramp 1, 2, 3 -- the reference restarts

@@ -434,6 +434,13 @@ class Sem:
         check(self.lib.nsb_sem_pressure_get(self.h, which, _dp(out)))
         return out.reshape(self.dim * self.dim, n2) if which == 0 else out
 
+    def norm_grad(self, vec: nek_dvector) -> float:
+        """norm_grad (core/utils.f90:446-486): sum_c sum_b (du_c/dx_b, du_c/dx_b)_bm1s of the velocity fields, no
+        square root -- the spurious-mode measure of outpost_ks."""
+        a = C.c_double()
+        check(self.lib.nsb_sem_norm_grad(self.h, vec.basis.h, vec.col, C.byref(a)))
+        return a.value
+
     def opdiv(self, vin: nek_dvector, vout: nek_dvector):
         """opdiv: pressure field of vout <- D (velocity fields of vin)."""
         check(self.lib.nsb_sem_opdiv(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col))
@@ -805,6 +812,42 @@ def ritz_vector(Q: Basis, k: int, y, out_re: nek_dvector, out_im: nek_dvector, n
     check(Q.lib.nsb_ritz_vector(Q.h, int(k), yc.ctypes.data_as(c_double_p), out_re.basis.h, out_re.col, out_im.col,
                                 int(normalize), C.byref(ar), C.byref(ai)))
     return ar.value, ai.value
+
+
+def outpost_ks(Q: Basis, sem: Sem, k: int, vals, vecs, converged: int, work: Basis, speriod: float,
+               maxmodes: int = 20, spurious_limit: float = 1.1, on_mode=None):
+    """The device side of outpost_ks (core/eigensolvers.f90:553-618): for each of the first ``converged`` Ritz pairs
+    assemble fp = Q(:,1:k) vecs(:,i) (real part -> work[0], imaginary part -> work[1]), measure |Re|, |Im| and
+    norm_grad of both parts, skip the pair as spurious when either norm_grad exceeds 1.1 (:591-594), otherwise scale
+    both parts by 1/sqrt(|Re|^2 + |Im|^2) (:584-585, 607-614) and hand them to ``on_mode(outp, work[0], work[1])``
+    (the reference writes the field files here).  At most maxmodes modes are kept (:556-559).  Returns one dict per
+    converged pair: index, kept, norms, norm_grads, sigma / omega = log_transform(val) / speriod (:598-603)."""
+    vals = np.asarray(vals, dtype=np.complex128)
+    vecs = np.asarray(vecs, dtype=np.complex128)
+    out, outp = [], 0
+    for i in range(int(converged)):
+        if outp >= maxmodes:
+            out.append(dict(index=i, kept=False, reason='maxmodes'))
+            continue
+        ar, ai = ritz_vector(Q, k, vecs[:k, i], work[0], work[1], normalize=False)
+        gr, gi = sem.norm_grad(work[0]), sem.norm_grad(work[1])
+        lam = np.log(vals[i])
+        if vals[i].imag == 0:
+            lam = complex(lam.real, 0.0)                           # log_transform, core/eigensolvers.f90:860-869
+        rec = dict(index=i, norms=(ar, ai), norm_grads=(gr, gi), sigma=lam.real / speriod, omega=lam.imag / speriod)
+        if gr > spurious_limit or gi > spurious_limit:
+            rec.update(kept=False, reason='spurious')
+            out.append(rec)
+            continue
+        beta = 1.0 / np.sqrt(ar * ar + ai * ai)
+        work[0].scal(beta)
+        work[1].scal(beta)
+        outp += 1
+        rec.update(kept=True, outp=outp)
+        if on_mode is not None:
+            on_mode(outp, work[0], work[1])
+        out.append(rec)
+    return out
 
 
 def svd(A):

@@ -912,6 +912,42 @@ adj_gradterm_kernel(int dim, const double *__restrict__ G, const double *__restr
   }
 }
 
+// norm_grad (core/utils.f90:446-486): sum over velocity components c and directions b of glsc3(du_c/dx_b, bm1s,
+// du_c/dx_b) with the collocation derivatives of gradm1 -- the quantity outpost_ks compares with 1.1 to drop
+// spurious Ritz vectors (core/eigensolvers.f90:587-594).  Partial sums per CTA, fixed order.
+__global__ void __launch_bounds__(NT_NS)
+norm_grad_kernel(int dim, int lx, const double *__restrict__ U, int64_t fs, const double *__restrict__ rst,
+                 const double *__restrict__ jac, const double *__restrict__ D, const double *__restrict__ w, int64_t npts,
+                 double *__restrict__ partial) {
+  int nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  double acc = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = p / nloc * nloc;
+    const int loc = (int)(p - e0);
+    const int i = loc % lx, j = (loc / lx) % lx, k = dim == 3 ? loc / (lx * lx) : 0;
+    const double ji = 1.0 / jac[p];
+    for (int c = 0; c < dim; ++c) {
+      const double *u = U + (int64_t)c * fs + e0;
+      double g[3] = {0.0, 0.0, 0.0};
+      for (int l = 0; l < lx; ++l) {   // D[i + lx * l] = dxm1(i, l)
+        g[0] = fma(D[i + lx * l], u[l + lx * (j + lx * k)], g[0]);
+        g[1] = fma(D[j + lx * l], u[i + lx * (l + lx * k)], g[1]);
+        if (dim == 3) g[2] = fma(D[k + lx * l], u[i + lx * (j + lx * l)], g[2]);
+      }
+      const double wp = w[(int64_t)c * fs + p];
+      for (int b = 0; b < dim; ++b) {
+        double d = 0.0;
+        for (int a = 0; a < dim; ++a) d = fma(rst[(int64_t)(a * dim + b) * npts + p], g[a], d);
+        d *= ji;
+        acc = fma(wp * d, d, acc);
+      }
+    }
+  }
+  acc = block_reduce_sum<NT_NS>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 NsDims ns_dims(nsb_sem_t S) {
   NsDims d;
   d.dim = S->dim;
@@ -1524,6 +1560,37 @@ extern "C" int nsb_sem_esolve(nsb_sem_t S, nsb_basis_t brhs, int crhs, nsb_basis
   NSB_REQUIRE(precond == 0 || precond == 1, "nsb_sem_esolve: unknown preconditioner %d", precond);
   NSB_REQUIRE(S->exchange_ready || S->ctx->nranks == 1, "nsb_sem_esolve: call nsb_sem_setup_exchange first");
   return esolve_d(S, rhs, x, tol, maxit, mean_free, precond, iters, res);
+}
+
+// norm_grad of the velocity fields of (b, col) (core/utils.f90:446-486; the spurious-mode filter of outpost_ks,
+// core/eigensolvers.f90:587-594): sum_c sum_b (du_c/dx_b, du_c/dx_b)_w with the layout's weight (bm1s) -- not the
+// square root, exactly what the reference compares with 1.1.  Summed over all ranks.
+extern "C" int nsb_sem_norm_grad(nsb_sem_t S, nsb_basis_t B, int col, double *norma) {
+  NSB_REQUIRE(S && B && norma, "nsb_sem_norm_grad: NULL argument");
+  NSB_REQUIRE(col >= 0 && col < B->ncols, "nsb_sem_norm_grad: column %d out of range", col);
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = S->ctx;
+  NSB_REQUIRE(L->ctx == ctx, "nsb_sem_norm_grad: basis and mesh live on different contexts");
+  NSB_REQUIRE(!L->c0_sem, "nsb_sem_norm_grad: the C0 storage layout is not supported");
+  NSB_REQUIRE(L->nfields >= S->dim, "nsb_sem_norm_grad: the layout has %d fields, the velocity needs %d", L->nfields, S->dim);
+  const int64_t fs = S->dim > 1 ? L->off[1] - L->off[0] : 0;
+  for (int f = 0; f < S->dim; ++f) {
+    NSB_REQUIRE(L->len[f] == S->npts && L->in_dot[f], "nsb_sem_norm_grad: field %d is not a weighted velocity field of the mesh", f);
+    NSB_REQUIRE(f == 0 || L->off[f] - L->off[f - 1] == fs, "nsb_sem_norm_grad: velocity fields are not equally spaced");
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((S->npts + NT_NS - 1) / NT_NS, (int64_t)ctx->num_sms * 8));
+  NSB_CHECK(ensure_partial(ctx, (grid + kMaxK + 7) / (kMaxK + 8) + 1));
+  norm_grad_kernel<<<grid, NT_NS, 0, st>>>(S->dim, S->lx, B->col(col) + L->off[0], fs, S->rst_d, S->jac_d, S->D_d,
+                                           L->w_d + L->off[0], S->npts, ctx->partial_d);
+  reduce_rows_kernel<<<1, NT_NS, 0, st>>>(ctx->partial_d, grid, 1, ctx->hvec_d, nullptr);
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, ctx->hvec_d, 1));
+  NSB_CUDA(cudaMemcpyAsync(norma, ctx->hvec_d, sizeof(double), cudaMemcpyDeviceToHost, st));
+  NSB_CUDA(cudaStreamSynchronize(st));
+  return check_dev_err(ctx);
 }
 
 // Operator handle with the structure of exponential_prop%matvec for the linearised Navier-Stokes equations:

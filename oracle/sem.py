@@ -266,6 +266,26 @@ def glsc3(a, b, mult):
     return float(np.sum(a.ravel() * b.ravel() * mult.ravel()))
 
 
+def gradm1(u, geo, d):
+    """[UPSTREAM-RECALL] navier5.f gradm1: physical-space collocation derivatives on the GLL points,
+    du/dx_b = sum_a (rst[a][b] / jac) du/dr_a  (rst already holds one factor jac, `jacmi` removes it)."""
+    g = grad_rst(u, d)
+    dim = len(g)
+    return [sum(geo['rst'][a * dim + b] * g[a] for a in range(dim)) / geo['jac'] for b in range(dim)]
+
+
+def norm_grad(vel, geo, n, bm1s):
+    """core/utils.f90:446-486: sum_c sum_b glsc3(du_c/dx_b, bm1s, du_c/dx_b) -- no square root; the number outpost_ks
+    compares with 1.1 to drop spurious Ritz vectors (core/eigensolvers.f90:587-594).  2-D: the four terms of :470-471,
+    3-D: all nine (:473-479)."""
+    d = dgll(n)
+    norma = 0.0
+    for u in vel:
+        for du in gradm1(u, geo, d):
+            norma += glsc3(du, du, bm1s)
+    return norma
+
+
 def convect(u, vel, rst, d):
     """Pointwise (times jac) convective derivative  jac * (U . grad) u  via local_grad3."""
     if u.ndim == 4:

@@ -402,6 +402,68 @@ def test_svds_host_operator_pair(ctx):
     assert min(np.linalg.norm(x - Uo[:, 0]), np.linalg.norm(x + Uo[:, 0])) < 1e-7
 
 
+@pytest.mark.parametrize('nel,N', [((2, 2, 2), 4), ((3, 2), 5)])
+def test_norm_grad_and_outpost_ks(ctx, nel, N):
+    """norm_grad (core/utils.f90:446-486) on the device against the restatement, and the device side of outpost_ks
+    (core/eigensolvers.f90:553-618): Ritz vectors, their norms and gradient norms, the spurious-mode filter, the
+    maxmodes cap and the unit scaling of what is kept -- against the same steps done with the oracle on the host."""
+    import nekstab_next_b200 as nb
+    from oracle import sem as osem
+    dim = len(nel)
+    P = BoxProblem(nel=nel, N=N, nfields=dim, conv=True, seed=37)
+    c = P.octx()
+    K = 8
+    lay, B, S, op = P.gpu(ctx, K + 1)
+    W = nb.Basis(lay, 2)
+    x = P.random_kvec()
+    upload(W[0], x)
+    ref = osem.norm_grad(x.f, P.geo, N, P.bm1)
+    assert abs(S.norm_grad(W[0]) - ref) <= 1e-12 * ref
+    q0 = seed(P, c)
+    upload(B[0], q0)
+    H = np.zeros((K + 1, K), order='F')
+    nb.arnoldi_factorization(B, H, 1, K, K, op)
+    vecs, vals = nb.eig(H[:K, :K])
+    Qh = [download(B[j], P.shape) for j in range(K)]
+    want = []
+    for i in range(K):
+        re = okr.k_matmul(Qh, np.ascontiguousarray(vecs[:, i].real), K)
+        im = okr.k_matmul(Qh, np.ascontiguousarray(vecs[:, i].imag), K)
+        want.append((okr.k_norm(c, re), okr.k_norm(c, im), osem.norm_grad(re.f, P.geo, N, P.bm1),
+                     osem.norm_grad(im.f, P.geo, N, P.bm1), re, im))
+    limit = float(np.median([max(w[2], w[3]) for w in want]))      # half of the pairs count as spurious
+    speriod, maxmodes = 0.5, 3
+    modes = []
+    recs = nb.outpost_ks(B, S, K, vals, vecs, K, W, speriod, maxmodes=maxmodes, spurious_limit=limit,
+                         on_mode=lambda n, re, im: modes.append((n, download(re, P.shape), download(im, P.shape))))
+    assert len(recs) == K
+    outp = 0
+    for i, (rec, w) in enumerate(zip(recs, want)):
+        if outp >= maxmodes:
+            assert not rec['kept'] and rec['reason'] == 'maxmodes'
+            continue
+        assert np.allclose(rec['norms'], w[:2], rtol=1e-10, atol=1e-13)
+        assert np.allclose(rec['norm_grads'], w[2:4], rtol=1e-9, atol=1e-11)
+        lam = np.log(vals[i])
+        assert abs(rec['sigma'] - lam.real / speriod) <= 1e-14 and abs(rec['omega'] - lam.imag / speriod) <= 1e-14
+        spurious = w[2] > limit or w[3] > limit
+        assert rec['kept'] == (not spurious)
+        if rec['kept']:
+            outp += 1
+            n, re, im = modes[outp - 1]
+            beta = 1.0 / np.sqrt(w[0] ** 2 + w[1] ** 2)
+            assert n == outp
+            for a, b in zip(re.f + im.f, w[4].f + w[5].f):
+                assert np.max(np.abs(a - beta * b)) <= 1e-11
+            assert abs(okr.k_norm(c, re) ** 2 + okr.k_norm(c, im) ** 2 - 1.0) <= 1e-12
+    assert outp == len(modes) == min(maxmodes, sum(1 for w in want if not (w[2] > limit or w[3] > limit)))
+    lay2 = nb.Layout(ctx, [P.npts // 2], [True])
+    lay2.set_weight([np.ones(P.npts // 2)])
+    B2 = nb.Basis(lay2, 1)
+    with pytest.raises(nb.NsbError):                               # not the velocity fields of this mesh
+        S.norm_grad(B2[0])
+
+
 def test_ritz_vector_assembly(ctx):
     """fp = Q y with complex y (core/eigensolvers.f90:565-585): real / imaginary parts and the unit scaling."""
     import nekstab_next_b200 as nb

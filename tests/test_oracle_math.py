@@ -160,3 +160,32 @@ def test_finite_difference_frechet_map(order):
     assert np.max(np.abs(g.f[0] - A @ q.f[0])) <= 1e-8 * np.max(np.abs(A @ q.f[0]))
     with pytest.raises(ValueError):
         okr.forward_finite_difference_map(c, F, X, q, 3)
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+def test_norm_grad_integrates_polynomial_gradients_exactly(dim):
+    """norm_grad (core/utils.f90:446-486) on a deformed mesh: for polynomial fields the collocation derivatives are
+    the exact ones wherever the mapping is affine, and on the unit box
+    int (d(x^2 y)/dx)^2 + (d(x^2 y)/dy)^2 = 4/9 + 1/5; with the smooth deformation the GLL rule converges to it."""
+    N = 7
+    if dim == 2:
+        x, y, _ = osem.box_mesh_2d(2, 3, N, deform=0.0)
+        coords, u, v = (x, y), x * x * y, 0 * x
+        exact = 4.0 / 9.0 + 1.0 / 5.0
+    else:
+        x, y, z, _ = osem.box_mesh(2, 2, 2, N, deform=0.0)
+        coords, u, v = (x, y, z), x * x * y * z, z ** 3
+        # |grad(x^2 y z)|^2 + |grad z^3|^2 over the unit cube: 4/27 + 1/15 + 1/15 + 9/5
+        exact = 4.0 / 27.0 + 2.0 / 15.0 + 9.0 / 5.0
+    geo = osem.geometry(N, *coords)
+    vel = [u, v] + ([0 * u] if dim == 3 else [])
+    assert abs(osem.norm_grad(vel, geo, N, geo['bm1']) - exact) <= 1e-12
+    # a sponge-like weight (bm1s zeroed where x > 0.5) only counts the rest of the domain
+    half = osem.norm_grad([u] + [0 * u] * (dim - 1), geo, N, geo['bm1'] * (coords[0] <= 0.5 + 1e-12))
+    full = osem.norm_grad([u] + [0 * u] * (dim - 1), geo, N, geo['bm1'])
+    assert 0.0 < half < full
+    # deformed elements: the same integral up to the quadrature error of the mapped integrand
+    if dim == 2:
+        xd, yd, _ = osem.box_mesh_2d(2, 3, N, deform=0.03)
+        geod = osem.geometry(N, xd, yd)
+        assert abs(osem.norm_grad([xd * xd * yd, 0 * xd], geod, N, geod['bm1']) - exact) <= 1e-8
