@@ -406,6 +406,11 @@ int nsb_sem_esolve(nsb_sem_t sem, nsb_basis_t brhs, int crhs, nsb_basis_t bx, in
  * (b, col), gradm1 collocation derivatives, the layout's weight, summed over all ranks; NOT a square root -- the
  * number outpost_ks compares with 1.1 to skip spurious Ritz vectors (core/eigensolvers.f90:587-594). */
 int nsb_sem_norm_grad(nsb_sem_t sem, nsb_basis_t b, int col, double *norma);
+/* compute_cfl(cfl, vx, vy, vz, dt) ([UPSTREAM-RECALL] Nek5000; call sites core/linear_stab.f90:222,231) of the velocity
+ * fields of (b, col): max over the GLL points of dt (|u.grad r| / dr_i + |u.grad s| / ds_j [+ |u.grad t| / dt_k]), over
+ * all ranks.  set_linear_solver derives the stepper's dt and nsteps from it: dt = ctarg / cfl(dt = 1),
+ * nsteps = ceiling(T / dt), dt = T / nsteps (core/linear_stab.f90:220-236). */
+int nsb_sem_cfl(nsb_sem_t sem, nsb_basis_t b, int col, double dt, double *cfl);
 /* exponential_prop%matvec for the linearised incompressible Navier-Stokes equations, device-resident:
  *     dv/dt + (U.grad) v + (v.grad) U = -grad p + nu lap v,   div v = 0,   v = 0 where the mesh mask is 0.
  * The input vector's velocity and pressure start nsteps BDF/EXT steps (order ramp 1, 2, 3 -- the reference restarts

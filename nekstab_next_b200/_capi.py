@@ -119,6 +119,7 @@ PROTOTYPES = {
     'nsb_sem_esolve': (C.c_int, [H, H, C.c_int, H, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_int_p,
                                  c_double_p]),
     'nsb_sem_norm_grad': (C.c_int, [H, H, C.c_int, c_double_p]),
+    'nsb_sem_cfl': (C.c_int, [H, H, C.c_int, C.c_double, c_double_p]),
     'nsb_op_create_ns_stepper': (C.c_int, [H, H, H, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                            C.c_int, C.c_int, C.c_int, c_void_pp]),
     'nsb_op_create_ns_stepper_adjoint': (C.c_int, [H, H, H, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,

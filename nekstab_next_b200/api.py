@@ -441,6 +441,12 @@ class Sem:
         check(self.lib.nsb_sem_norm_grad(self.h, vec.basis.h, vec.col, C.byref(a)))
         return a.value
 
+    def compute_cfl(self, vec: nek_dvector, dt: float = 1.0) -> float:
+        """compute_cfl(cfl, vx, vy, vz, dt) of the velocity fields (call sites core/linear_stab.f90:222,231)."""
+        a = C.c_double()
+        check(self.lib.nsb_sem_cfl(self.h, vec.basis.h, vec.col, float(dt), C.byref(a)))
+        return a.value
+
     def opdiv(self, vin: nek_dvector, vout: nek_dvector):
         """opdiv: pressure field of vout <- D (velocity fields of vin)."""
         check(self.lib.nsb_sem_opdiv(self.h, vin.basis.h, vin.col, vout.basis.h, vout.col))
@@ -848,6 +854,19 @@ def outpost_ks(Q: Basis, sem: Sem, k: int, vals, vecs, converged: int, work: Bas
             on_mode(outp, work[0], work[1])
         out.append(rec)
     return out
+
+
+def set_linear_solver(sem: Sem, base: nek_dvector, T: float, ctarg: float = 0.5):
+    """The time step of the linearised solver as set_linear_solver chooses it (core/linear_stab.f90:214-236): target
+    CFL above 1 is limited to 0.5; dt = ctarg / compute_cfl(base, 1); nsteps = ceiling(T / dt); dt = T / nsteps.
+    Returns (dt, nsteps, cfl at that dt)."""
+    import math
+    if ctarg > 1.0:
+        ctarg = 0.5
+    dt = ctarg / sem.compute_cfl(base, 1.0)
+    nsteps = int(math.ceil(T / dt))
+    dt = T / nsteps
+    return dt, nsteps, sem.compute_cfl(base, dt)
 
 
 def svd(A):

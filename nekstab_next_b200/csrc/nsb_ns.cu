@@ -948,6 +948,56 @@ norm_grad_kernel(int dim, int lx, const double *__restrict__ U, int64_t fs, cons
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// compute_cfl ([UPSTREAM-RECALL] Nek5000 navier4.f; call sites core/linear_stab.f90:222,231): per GLL point
+//     dt ( |u.grad r| / dr_i + |u.grad s| / ds_j + |u.grad t| / dt_k ),   u.grad r = (u rx + v ry + w rz) / jac,
+// dr_i = the reference-space spacing getdr builds (one-sided at the ends, centred inside); the maximum per CTA.
+// dri[0..lx): 1 / dr_i.
+struct CflDri {
+  double v[16];
+};
+__global__ void __launch_bounds__(NT_NS)
+cfl_kernel(int dim, int lx, const double *__restrict__ U, int64_t fs, const double *__restrict__ rst,
+           const double *__restrict__ jac, CflDri dri, double dt, int64_t npts, double *__restrict__ partial) {
+  int nloc = 1;
+  for (int a = 0; a < dim; ++a) nloc *= lx;
+  double cfl = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x) {
+    const int loc = (int)(p % nloc);
+    const int ijk[3] = {loc % lx, (loc / lx) % lx, dim == 3 ? loc / (lx * lx) : 0};
+    const double ji = 1.0 / jac[p];
+    double u[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < dim; ++c) u[c] = U[(int64_t)c * fs + p];
+    double m = 0.0;
+    for (int a = 0; a < dim; ++a) {
+      double ua = 0.0;
+      for (int b = 0; b < dim; ++b) ua += u[b] * rst[(int64_t)(a * dim + b) * npts + p];
+      m += fabs(dt * (ua * ji) * dri.v[ijk[a]]);
+    }
+    cfl = fmax(cfl, m);
+  }
+  __shared__ double red[NT_NS / 32];
+  for (int o = 16; o > 0; o >>= 1) cfl = fmax(cfl, __shfl_xor_sync(0xffffffffu, cfl, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cfl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < NT_NS / 32; ++i) cfl = fmax(cfl, red[i]);
+    partial[blockIdx.x] = cfl;
+  }
+}
+
+__global__ void max_rows_kernel(const double *__restrict__ partial, int rows, double *__restrict__ out) {
+  double m = 0.0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) m = fmax(m, partial[r]);
+  __shared__ double red[NT_NS / 32];
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < NT_NS / 32; ++i) m = fmax(m, red[i]);
+    *out = m;
+  }
+}
+
 NsDims ns_dims(nsb_sem_t S) {
   NsDims d;
   d.dim = S->dim;
@@ -1591,6 +1641,54 @@ extern "C" int nsb_sem_norm_grad(nsb_sem_t S, nsb_basis_t B, int col, double *no
   NSB_CUDA(cudaMemcpyAsync(norma, ctx->hvec_d, sizeof(double), cudaMemcpyDeviceToHost, st));
   NSB_CUDA(cudaStreamSynchronize(st));
   return check_dev_err(ctx);
+}
+
+// compute_cfl(cfl, vx, vy, vz, dt) for the velocity fields of (b, col): what set_linear_solver derives the time step and
+// the number of steps of the linearised solver from (core/linear_stab.f90:220-236: dt = ctarg / compute_cfl(.., 1),
+// nsteps = ceiling(T / dt), dt = T / nsteps).  Maximum over all ranks (each rank's value in its own slot of a summed
+// vector: the library's only collective is a sum).
+extern "C" int nsb_sem_cfl(nsb_sem_t S, nsb_basis_t B, int col, double dt, double *cfl) {
+  NSB_REQUIRE(S && B && cfl, "nsb_sem_cfl: NULL argument");
+  NSB_REQUIRE(col >= 0 && col < B->ncols, "nsb_sem_cfl: column %d out of range", col);
+  nsb_layout_t L = B->lay;
+  nsb_context_t ctx = S->ctx;
+  NSB_REQUIRE(L->ctx == ctx, "nsb_sem_cfl: basis and mesh live on different contexts");
+  NSB_REQUIRE(!L->c0_sem, "nsb_sem_cfl: the C0 storage layout is not supported");
+  NSB_REQUIRE(L->nfields >= S->dim, "nsb_sem_cfl: the layout has %d fields, the velocity needs %d", L->nfields, S->dim);
+  NSB_REQUIRE(S->lx <= 16, "nsb_sem_cfl: lx1 = %d above 16", S->lx);
+  const int64_t fs = S->dim > 1 ? L->off[1] - L->off[0] : 0;
+  for (int f = 0; f < S->dim; ++f) {
+    NSB_REQUIRE(L->len[f] == S->npts, "nsb_sem_cfl: field %d is not a velocity field of the mesh", f);
+    NSB_REQUIRE(f == 0 || L->off[f] - L->off[f - 1] == fs, "nsb_sem_cfl: velocity fields are not equally spaced");
+  }
+  std::vector<double> z(S->lx), w(S->lx), D((size_t)S->lx * S->lx);
+  NSB_CHECK(nsb_gll(S->N, z.data(), w.data(), D.data()));
+  CflDri dri;
+  memset(&dri, 0, sizeof(dri));
+  const int lx = S->lx;
+  dri.v[0] = 1.0 / (z[1] - z[0]);                                   // getdr: one-sided at the ends,
+  for (int i = 1; i < lx - 1; ++i) dri.v[i] = 1.0 / (0.5 * (z[i + 1] - z[i - 1]));   // centred inside
+  dri.v[lx - 1] = 1.0 / (z[lx - 1] - z[lx - 2]);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((S->npts + NT_NS - 1) / NT_NS, (int64_t)ctx->num_sms * 8));
+  NSB_CHECK(ensure_partial(ctx, (grid + kMaxK + 7) / (kMaxK + 8) + 1));
+  NSB_REQUIRE(ctx->nranks <= kMaxK, "nsb_sem_cfl: %d ranks", ctx->nranks);
+  NSB_CUDA(cudaMemsetAsync(ctx->hvec_d, 0, sizeof(double) * ctx->nranks, st));
+  cfl_kernel<<<grid, NT_NS, 0, st>>>(S->dim, lx, B->col(col) + L->off[0], fs, S->rst_d, S->jac_d, dri, dt, S->npts,
+                                     ctx->partial_d);
+  max_rows_kernel<<<1, NT_NS, 0, st>>>(ctx->partial_d, grid, ctx->hvec_d + ctx->rank);
+  ctx->launches += 2;
+  NSB_CUDA(cudaGetLastError());
+  if (ctx->nranks > 1) NSB_CHECK(allreduce_sum_d(ctx, ctx->hvec_d, ctx->nranks));
+  std::vector<double> all(ctx->nranks);
+  NSB_CUDA(cudaMemcpyAsync(all.data(), ctx->hvec_d, sizeof(double) * ctx->nranks, cudaMemcpyDeviceToHost, st));
+  NSB_CUDA(cudaStreamSynchronize(st));
+  NSB_CHECK(check_dev_err(ctx));
+  double m = 0.0;
+  for (double a : all) m = a > m ? a : m;
+  *cfl = m;
+  return NSB_OK;
 }
 
 // Operator handle with the structure of exponential_prop%matvec for the linearised Navier-Stokes equations:

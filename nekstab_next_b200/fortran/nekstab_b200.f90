@@ -510,6 +510,15 @@ module nekstab_b200
          real(c_double) :: norma
          integer(c_int) :: ierr
       end function
+      !> compute_cfl(cfl, vx, vy, vz, dt) of the velocity fields of (b, col) (core/linear_stab.f90:222,231)
+      function nsb_sem_cfl(sem, b, col, dt, cfl) bind(C, name='nsb_sem_cfl') result(ierr)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: sem, b
+         integer(c_int), value :: col
+         real(c_double), value :: dt
+         real(c_double) :: cfl
+         integer(c_int) :: ierr
+      end function
       function nsb_op_create_compose(layout, outer, inner, op) bind(C, name='nsb_op_create_compose') result(ierr)
          import :: c_int, c_ptr
          type(c_ptr), value :: layout, outer, inner
@@ -650,6 +659,7 @@ module nekstab_b200
    public :: nsb_sem_col2, nsb_sem_hmholtz, nsb_sem_hmholtz_vec, nsb_sem_dealias_setup, nsb_sem_set_convect, nsb_sem_convect
    public :: nsb_sem_bdf_ext, nsb_op_create_sem, nsb_op_create_stepper, nsb_op_create_compose, nsb_op_create_axpby
    public :: nsb_op_create_frechet_fd, nsb_op_frechet_set_epsilon, nsb_op_ns_set_orbit, nsb_sem_norm_grad
+   public :: nsb_sem_cfl
    public :: nsb_sem_pressure_setup, nsb_op_create_ns_stepper, nsb_op_create_ns_stepper_adjoint
    public :: nsb_op_apply, nsb_op_destroy, nsb_op_count
    public :: nsb_eig, nsb_schur, nsb_ordschur, nsb_lstsq, nsb_svd, nsb_select_eigenvalues

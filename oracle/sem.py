@@ -286,6 +286,25 @@ def norm_grad(vel, geo, n, bm1s):
     return norma
 
 
+def compute_cfl(vel, geo, n, dt):
+    """[UPSTREAM-RECALL] Nek5000 compute_cfl + getdr (call sites core/linear_stab.f90:222,231): the maximum over the
+    GLL points of dt (|u.grad r| dri_i + |u.grad s| dsi_j [+ |u.grad t| dti_k]), u.grad r = (u rx + v ry + w rz) / jac
+    (rst holds the metrics times jac), dr_i = z_2 - z_1 at the ends and (z_i+1 - z_i-1) / 2 inside."""
+    z, _ = gll(n)
+    dr = np.empty(n + 1)
+    dr[0], dr[n] = z[1] - z[0], z[n] - z[n - 1]
+    dr[1:n] = 0.5 * (z[2:] - z[:-2])
+    dri = 1.0 / dr
+    dim = len(vel)
+    total = 0.0
+    for a in range(dim):
+        ua = sum(vel[b] * geo['rst'][a * dim + b] for b in range(dim)) / geo['jac']
+        shape = [1] * ua.ndim
+        shape[ua.ndim - 1 - a] = n + 1                             # axis of direction a: i fastest (last axis)
+        total = total + np.abs(dt * ua * dri.reshape(shape))
+    return float(np.max(total))
+
+
 def convect(u, vel, rst, d):
     """Pointwise (times jac) convective derivative  jac * (U . grad) u  via local_grad3."""
     if u.ndim == 4:

@@ -464,6 +464,31 @@ def test_norm_grad_and_outpost_ks(ctx, nel, N):
         S.norm_grad(B2[0])
 
 
+@pytest.mark.parametrize('nel,N', [((2, 3, 2), 4), ((3, 2), 7)])
+def test_compute_cfl_and_set_linear_solver(ctx, nel, N):
+    """compute_cfl on the device against the restatement (deformed elements, random velocity), and the time step /
+    step count set_linear_solver derives from it (core/linear_stab.f90:214-236)."""
+    import math
+    import nekstab_next_b200 as nb
+    from oracle import sem as osem
+    dim = len(nel)
+    P = BoxProblem(nel=nel, N=N, nfields=dim, seed=43)
+    lay, B, S, op = P.gpu(ctx, 2)
+    U = P.random_kvec()
+    upload(B[0], U)
+    for dt in (1.0, 3e-3):
+        ref = osem.compute_cfl(U.f, P.geo, N, dt)
+        assert abs(S.compute_cfl(B[0], dt) - ref) <= 1e-12 * ref
+    T, ctarg = 0.37, 0.5
+    dt, nsteps, cfl = nb.set_linear_solver(S, B[0], T, ctarg)
+    dt0 = ctarg / osem.compute_cfl(U.f, P.geo, N, 1.0)
+    assert nsteps == math.ceil(T / dt0) and abs(dt - T / nsteps) <= 1e-15 and dt <= dt0 * (1 + 1e-12)
+    assert abs(cfl - osem.compute_cfl(U.f, P.geo, N, dt)) <= 1e-12 * cfl and cfl <= ctarg * (1 + 1e-12)
+    assert nb.set_linear_solver(S, B[0], T, 2.0)[1] == nsteps          # a target above 1 is limited to 0.5
+    upload(B[1], okr.k_zero_like(U))
+    assert S.compute_cfl(B[1], 1.0) == 0.0
+
+
 def test_ritz_vector_assembly(ctx):
     """fp = Q y with complex y (core/eigensolvers.f90:565-585): real / imaginary parts and the unit scaling."""
     import nekstab_next_b200 as nb

@@ -189,3 +189,31 @@ def test_norm_grad_integrates_polynomial_gradients_exactly(dim):
         xd, yd, _ = osem.box_mesh_2d(2, 3, N, deform=0.03)
         geod = osem.geometry(N, xd, yd)
         assert abs(osem.norm_grad([xd * xd * yd, 0 * xd], geod, N, geod['bm1']) - exact) <= 1e-8
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+def test_compute_cfl_of_uniform_flows_on_affine_elements(dim):
+    """compute_cfl on a box of equal elements of size h: u.grad r = 2 u / h, so a uniform flow U gives
+    dt sum_a (2 |U_a| / h_a) max_i(1 / dr_i) with the largest 1 / dr at the end points, 1 / (z_2 - z_1); linear in dt and
+    in the velocity; a flow along one axis only sees that axis' spacing."""
+    N = 6
+    z, _ = osem.gll(N)
+    end = 1.0 / (z[1] - z[0])
+    if dim == 2:
+        x, y, _ = osem.box_mesh_2d(4, 2, N, deform=0.0)
+        coords, h, U = (x, y), (0.25, 0.5), (1.5, -0.7)
+    else:
+        x, y, z3, _ = osem.box_mesh(2, 4, 1, N, deform=0.0)
+        coords, h, U = (x, y, z3), (0.5, 0.25, 1.0), (0.3, -1.1, 2.0)
+    geo = osem.geometry(N, *coords)
+    vel = [u + 0 * coords[0] for u in U]
+    dt = 0.01
+    exact = dt * sum(2.0 * abs(u) / ha for u, ha in zip(U, h)) * end
+    assert abs(osem.compute_cfl(vel, geo, N, dt) - exact) <= 1e-12 * exact
+    assert abs(osem.compute_cfl(vel, geo, N, 3 * dt) - 3 * exact) <= 1e-12 * exact
+    one = [vel[0]] + [0 * v for v in vel[1:]]
+    assert abs(osem.compute_cfl(one, geo, N, dt) - dt * 2.0 * abs(U[0]) / h[0] * end) <= 1e-12 * exact
+    # a flow that vanishes at the element ends and peaks inside meets the centred spacing there
+    bump = [np.where(np.isclose(np.abs(np.mod(coords[0] / h[0], 1.0) - 0.5), 0.5), 0.0, 1.0)] + [0 * v for v in vel[1:]]
+    inner = 1.0 / (0.5 * (z[2] - z[0]))
+    assert abs(osem.compute_cfl(bump, geo, N, dt) - dt * 2.0 / h[0] * inner) <= 1e-12
