@@ -12,6 +12,6 @@ from .api import (  # noqa: F401
     k_zero, k_copy, k_matmul, orthonormalize, arnoldi_factorization, eig, schur, ordschur, lstsq,
     select_eigenvalues, schur_condensation, krylov_schur, arnoldi_passes, build_id, hessenberg_write, hessenberg_read, fld_read_into, restart_load, eigs, newton_krylov, ritz_vector, outpost_ks, set_linear_solver, svd, svds, ts_gmres, set_lapack_from_scipy, KSResult,
 )
-from . import mesh, seed, checkpoint  # noqa: F401
+from . import mesh, seed, checkpoint, linear_stab  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith('_')]

@@ -442,3 +442,85 @@ def test_ns_stepper_with_a_stored_orbit(ctx, adjoint):
         nb.ns_set_orbit(stokes, O, 0, 1)
     for o in (stokes, op, O, B, lay, sem):
         o.close()
+
+
+def test_linear_stability_and_transient_growth_drivers(ctx, tmp_path):
+    """The analysis drivers of core/linear_stab.f90 through the mirror (set_linear_solver from compute_cfl,
+    exponential_prop = the Navier-Stokes steppers, eigs / svds, spectrum files, get_vec) against the same sequence done
+    with the oracle: direct and adjoint eigenvalue analyses, a periodic one on a standing orbit, transient growth."""
+    import math
+    import nekstab_next_b200 as nb
+    from nekstab_next_b200 import linear_stab, checkpoint
+    N, kd, nu, T = 5, 4, 0.05, 0.03
+    P = NsProblem((3, 3), N, seed=51)
+    c = okr.Ctx(bm1s=P.geo['bm1'], in_dot=[True, True, False], time_in_dot=False)
+    fd = ons.coarse_setup(ons.fdm_setup(N, P.geo, P.ps), P.ps, P.glo, P.mask, P.binv)
+    dt0 = 0.5 / osem.compute_cfl(P.base, P.geo, N, 1.0)
+    nsteps = math.ceil(T / dt0)
+    dt = T / nsteps
+    assert nsteps >= 2
+
+    def propagate(q, adjoint):
+        v, p = ons.ns_steps(P.glo, P.mask, P.geo, N, P.ps, P.dl, P.base, [q.f[0], q.f[1]], q.f[2], nu, dt, nsteps,
+                            mean_free=False, fdm=fd, adjoint=adjoint)
+        return okr.KVec(v + [p], q.time)
+
+    seed = okr.KVec(P.vel() + [0 * P.pres()], 0.0)
+    u0 = seed.copy()
+    okr.k_normalize(c, u0)
+    tol = 1e-14                                                    # never met: kd full steps everywhere
+    sem, lay, X = P.gpu(ctx, kd + 1)
+    V = nb.Basis(lay, kd)
+    W = nb.Basis(lay, 3)
+    sem.dealias_setup()
+    P.up(W[2], P.base, 0 * P.pres())
+    kw = dict(k_dim=kd, schur_tgt=1, eigen_tol=tol, solver=dict(tol_v=1e-13, tol_p=1e-13, mean_free=False))
+    for stype, adj in (('direct', False), ('adjoint', True)):
+        vals_o, vecs_o, res_o, k_o, H_o = okr.eigs(c, lambda q: propagate(q, adj), u0.copy(), kd, nev=1, tol=tol)
+        X[0].upload([a.ravel() for a in seed.f])
+        modes = []
+        r = linear_stab.linear_stability_analysis(
+            sem, lay, X, W[2], nu, T, 'steady', stype, work=W, outdir=tmp_path, maxmodes=2,
+            on_mode=lambda i, re, im: modes.append((i, re.download()[0], im.download()[0])), **kw)
+        assert r['k'] == k_o == kd and r['nsteps'] == nsteps and abs(r['dt'] - dt) <= 1e-15 and r['matvecs'] == kd
+        assert np.max(np.abs(r['H'][:kd + 1, :kd] - H_o[:kd + 1, :kd])) <= 1e-8 * np.max(np.abs(H_o))
+        for v in vals_o:
+            assert np.min(np.abs(r['eigvals'] - v)) <= 1e-6 * abs(v)
+        assert np.allclose(r['eigvals_ns'], checkpoint.log_transform(r['eigvals']) / T)
+        ev = 'a' if adj else 'd'
+        fv, fr = checkpoint.read_spectrum(tmp_path / f'Spectrum_H{ev}.dat')
+        assert np.allclose(fv, r['eigvals'], rtol=1e-6, atol=1e-12) and np.allclose(fr, r['residuals'], rtol=1e-6, atol=1e-12)   # E15.7
+        fv, _ = checkpoint.read_spectrum(tmp_path / f'Spectrum_NS{ev}.dat')
+        assert np.allclose(fv, r['eigvals_ns'], rtol=1e-6, atol=1e-6)
+        Xh = [X[j].download()[0] for j in range(kd)]
+        assert [m[0] for m in modes] == [1, 2]
+        for i, re, im in modes:                                    # get_vec: X(1:k) Re(y), X(1:k) Im(y)
+            y = r['eigvecs'][:kd, i - 1]
+            for f in range(3):
+                assert np.max(np.abs(re[f] - sum(y[j].real * Xh[j][f] for j in range(kd)))) <= 1e-12
+                assert np.max(np.abs(im[f] - sum(y[j].imag * Xh[j][f] for j in range(kd)))) <= 1e-12
+        if not adj:
+            H_steady = r['H'].copy()
+    # periodic base flow that stands still: the same factorisation through the stored-orbit path
+    O = nb.Basis(lay, nsteps)
+    for s in range(nsteps):
+        P.up(O[s], P.base, 0 * P.pres())
+    X[0].upload([a.ravel() for a in seed.f])
+    r = linear_stab.linear_stability_analysis(sem, lay, X, W[2], nu, T, 'periodic', 'direct', orbit=O, **kw)
+    assert np.max(np.abs(r['H'] - H_steady)) <= 1e-13 * np.max(np.abs(H_steady))
+    with pytest.raises(ValueError):
+        linear_stab.linear_stability_analysis(sem, lay, X, W[2], nu, T, 'periodic', 'direct', **kw)
+    # transient growth
+    sig_o, uv_o, vv_o, res_o, k_o, B_o = okr.svds(c, lambda q: propagate(q, False), lambda q: propagate(q, True),
+                                                  u0.copy(), kd, nev=1, tol=tol)
+    X[0].upload([a.ravel() for a in seed.f])
+    pairs = []
+    r = linear_stab.transient_growth_analysis(sem, lay, X, V, W[2], nu, T, 'steady', work=W, outdir=tmp_path, maxmodes=1,
+                                              on_mode=lambda i, u, v: pairs.append((nb.k_norm(u), nb.k_norm(v))), **kw)
+    assert r['k'] == k_o
+    assert np.allclose(r['gains'], sig_o ** 2, rtol=1e-6)
+    g, _ = checkpoint.read_singvals(tmp_path / 'Spectrum_Sp.dat')
+    assert np.allclose(g, r['gains'], rtol=1e-6)
+    assert len(pairs) == 1 and abs(pairs[0][0] - 1.0) <= 1e-10 and abs(pairs[0][1] - 1.0) <= 1e-10   # unit singular vectors
+    for o in (O, W, V, X, lay, sem):
+        o.close()
