@@ -41,3 +41,18 @@ for name, (path, sum_bm1, uu, nloc, nuniq) in CASES.items():
                         glo=glo.astype(np.int32))
     print(name, got)
 (Path(__file__).parent / 'known_answers.json').write_text(json.dumps(known, indent=1))
+
+# boundary-condition tables of the same cases from their .re2 files (element, side, 5 parameters, type), with the
+# element order of the field file the mesh fixture was taken from: what dirichlet_mask builds v1mask from
+from nekstab_next_b200 import mesh  # noqa: E402
+
+RE2 = {'cyl': REF / 'cylinder/1cyl.re2', 'bfs': REF / 'back_fstep/baseflow/bfs.re2'}
+for name, path in RE2.items():
+    r = mesh.read_re2(path)
+    bcs = r['bcs'][0]
+    elmap = nekfld.read_fld(CASES[name][0])['elmap']
+    np.savez_compressed(Path(__file__).parent / f'{name}_bc.npz', nel=r['nel'], elmap=elmap.astype(np.int32),
+                        elem=np.array([b[0] for b in bcs], dtype=np.int32),
+                        side=np.array([b[1] for b in bcs], dtype=np.int8),
+                        params=np.array([b[2] for b in bcs]), type=np.array([b[3] for b in bcs]))
+    print(name, 'boundary faces', len(bcs))
