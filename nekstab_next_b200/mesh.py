@@ -178,3 +178,46 @@ def dirichlet_mask(re2: dict, lx: int, types=('W  ', 'v  ', 'V  '), ids=(), fiel
         np.minimum.at(lowest, g, mask.reshape(-1))
         mask = lowest[g].reshape(mask.shape)
     return mask
+
+
+def periodic_glo_num(glo, re2: dict, coords, lx: int, field: int = 0, elements=None):
+    """Global numbering with the partners of periodic faces ('P  ': parameters 1 and 2 = partner element and side)
+    identified, as Nek's numbering has them: the points of a face are matched with those of its partner by their
+    position along the face (the coordinates tangential to it), the two ids are merged, and the merged classes are
+    renumbered 0 .. n-1.  coords = (x, y[, z]) of the local points; elements as in dirichlet_mask.  Partners that are
+    not local are left alone (a multi-rank caller merges on the global numbering before partitioning)."""
+    ndim = re2['ndim']
+    glo = np.asarray(glo)
+    elements = np.arange(1, re2['nel'] + 1) if elements is None else np.asarray(elements, dtype=np.int64)
+    local = {int(g): l for l, g in enumerate(elements)}
+    parent = np.arange(int(glo.max()) + 1)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    for e, side, params, typ in re2['bcs'][field]:
+        pe, ps = int(params[0]), int(params[1])
+        if typ != 'P  ' or e not in local or pe not in local:
+            continue
+        mine = (local[e],) + face_nodes(lx, ndim, side)
+        theirs = (local[pe],) + face_nodes(lx, ndim, ps)
+        # tangential coordinates: those that agree between the two faces (the normal one differs by the period)
+        keys = []
+        for c in coords:
+            a, b = np.asarray(c)[mine].ravel(), np.asarray(c)[theirs].ravel()
+            if abs(np.sort(a) - np.sort(b)).max() <= 1e-6 * max(1.0, abs(a).max()):
+                keys.append((a, b))
+        if not keys:
+            raise ValueError(f'periodic faces ({e}, {side}) and ({pe}, {ps}) share no tangential coordinate')
+        oa = np.lexsort([np.round(k[0], 6) for k in keys])
+        ob = np.lexsort([np.round(k[1], 6) for k in keys])
+        for a, b in zip(glo[mine].ravel()[oa], glo[theirs].ravel()[ob]):
+            ra, rb = find(int(a)), find(int(b))
+            if ra != rb:
+                parent[rb] = ra
+    roots = np.array([find(a) for a in range(parent.size)])
+    _, new = np.unique(roots, return_inverse=True)
+    return new[glo].astype(np.int64)

@@ -140,3 +140,74 @@ def test_face_nodes_numbering():
     b = np.arange(lx ** 3).reshape(lx, lx, lx)                   # (k, j, i)
     assert b[mesh.face_nodes(lx, 3, 5)].tolist() == b[0].tolist() and b[mesh.face_nodes(lx, 3, 6)].tolist() == b[-1].tolist()
     assert b[mesh.face_nodes(lx, 3, 2)].tolist() == b[:, :, -1].tolist()
+
+
+BASEFLOW = {'cyl': dict(nu=1.0 / 50.0, kw=dict(types=('W  ', 'v  ')), tol=3e-5, outflow=('O  ',)),
+            'bfs': dict(nu=1.0 / 500.0, kw=dict(types=(), ids=(3, 4)), tol=3e-4, outflow=(2,))}
+
+
+@pytest.mark.parametrize('name', ['cyl', 'bfs'])
+def test_base_flow_balances_momentum_up_to_the_outflow_and_periodic_boundaries(name):
+    """The reference's base flows with the boundary conditions of their .re2 files: the discrete steady momentum
+    balance QQ^T [B C(U) U + nu A U - D^T p] = 0 (oracle restatements of Nek's operators, as in
+    tests/test_oracle_fixtures.py) holds at EVERY node the velocity mask leaves free -- on the outflow boundary, where
+    'O' is the natural condition of that weak form and nothing is masked, and on the periodic boundary once the
+    numbering identifies the partners -- as well as in the interior.  This pins the reader, the mask, the periodic
+    numbering and the treatment of outflow by leaving the boundary unmasked against data computed by Nek5000 itself.
+    Control: without the periodic identification the balance fails on the periodic faces."""
+    import json
+    from oracle import ns as ons, sem
+    cfg = BASEFLOW[name]
+    g = np.load(GOLD / f'{name}_mesh.npz')
+    t = np.load(GOLD / f'{name}_bc.npz')
+    N = json.loads((GOLD / 'known_answers.json').read_text())[name]['N']
+    lx = N + 1
+    x, y, u, v, pm1 = g['x'], g['y'], g['u'], g['v'], g['p']
+    re2 = dict(ndim=2, nel=int(t['nel']),
+               bcs=[[(int(e), int(s), p, str(ty)) for e, s, p, ty in zip(t['elem'], t['side'], t['params'], t['type'])]])
+    order = t['elmap']
+    loc = {int(gid): l for l, gid in enumerate(order)}
+    glo = g['glo'].astype(np.int64)
+    glop = mesh.periodic_glo_num(glo, re2, (x, y), lx, elements=order)
+    nper = sum(1 for b in re2['bcs'][0] if b[3] == 'P  ')
+    if name == 'cyl':
+        assert nper == 132 and glop.max() + 1 == glo.max() + 1 - (66 * N + 1)      # one line of 66 elements folded
+    else:
+        assert nper == 0 and np.array_equal(glop, glo)
+
+    def faces(kinds):
+        m = np.zeros(x.shape, bool)
+        for e, s, p, ty in re2['bcs'][0]:
+            if ty in kinds or (ty == 'MSH' and int(p[4]) in kinds):
+                m[(loc[e],) + mesh.face_nodes(lx, 2, s)] = True
+        return m
+
+    outflow, periodic = faces(cfg['outflow']), faces(('P  ',))
+    assert outflow.sum() > 0
+    geo = sem.geometry(N, x, y)
+    ps = ons.pressure_setup(N, geo)
+    dl = sem.dealias_setup(N, 9, geo['rst'])
+    cf = sem.set_convect([u, v], dl)
+    gt = ons.opgradt(sem.interp_fine(pm1, ps['I12']), ps)
+    d = sem.dgll(N)
+
+    def residual(numbering):
+        mask = mesh.dirichlet_mask(re2, lx, elements=order, glo=numbering, **cfg['kw'])
+        assert mask[outflow & ~faces(('W  ', 'v  ', 3, 4))].all()                    # the outflow boundary is left free
+        worst = dict(all=0.0, outflow=0.0, periodic=0.0)
+        scale = 0.0
+        for b, a in enumerate((u, v)):
+            conv = sem.convect_dealiased(a, cf, dl)
+            visc = sem.axhelm(a, geo['g'], d, cfg['nu'], 0.0, geo['bm1'])
+            r = np.abs(sem.dssum(conv + visc - gt[b], numbering) * mask)
+            scale = max(scale, *(float(np.max(np.abs(sem.dssum(term, numbering) * mask))) for term in (conv, visc, gt[b])))
+            worst['all'] = max(worst['all'], float(r.max()))
+            worst['outflow'] = max(worst['outflow'], float(r[outflow].max()))
+            if periodic.any():
+                worst['periodic'] = max(worst['periodic'], float(r[periodic].max()))
+        return {k: w / scale for k, w in worst.items()}
+
+    res = residual(glop)
+    assert res['all'] <= cfg['tol'] and res['outflow'] <= cfg['tol'] and res['periodic'] <= cfg['tol'], res
+    if name == 'cyl':
+        assert residual(glo)['periodic'] >= 1000 * max(res['periodic'], 1e-9)
