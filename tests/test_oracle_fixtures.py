@@ -231,3 +231,36 @@ def test_third_base_flow_straight_from_the_reference_tree():
     assert residual(1.0 / 40.0) <= 2e-4
     assert residual(1.0 / 50.0) >= 5e-2
     assert np.max(np.abs(ons.opdiv([u, v], ps) / ps['bm2'])) <= 5e-5
+
+
+@pytest.mark.skipif(not (REF / 'back_fstep/transient_growth/BF_bfs0.f00001').exists(), reason='reference tree not present')
+def test_fourth_base_flow_straight_from_the_reference_tree():
+    """examples/back_fstep/transient_growth/BF_bfs0.f00001 (single precision; the base flow of BASELINE.json
+    configs[2]): the momentum balance holds with nu = 1/500 (9e-5 of its largest term) and fails by three orders of
+    magnitude with 1/450 or 1/550; discrete continuity to 4e-6."""
+    from oracle import ns as ons
+    f = nekfld.read_fld(REF / 'back_fstep/transient_growth/BF_bfs0.f00001')
+    assert f['wdsize'] == 4
+    (x, y), (u, v), pm1 = f['x'], f['u'], f['p']
+    N = f['nx'] - 1
+    glo = sem.glo_num_from_coords((x, y))
+    geo = sem.geometry(N, x, y)
+    ps = ons.pressure_setup(N, geo)
+    dl = sem.dealias_setup(N, 9, geo['rst'])
+    gt = ons.opgradt(sem.interp_fine(pm1, ps['I12']), ps)
+    cf = sem.set_convect([u, v], dl)
+    d = sem.dgll(N)
+    inner = ~_domain_boundary(glo)
+
+    def residual(nu):
+        worst = scale = 0.0
+        for b, a in enumerate((u, v)):
+            conv = sem.convect_dealiased(a, cf, dl)
+            visc = sem.axhelm(a, geo['g'], d, nu, 0.0, geo['bm1'])
+            worst = max(worst, float(np.max(np.abs(sem.dssum(conv + visc - gt[b], glo) * inner))))
+            scale = max(scale, *(float(np.max(np.abs(sem.dssum(t, glo) * inner))) for t in (conv, visc, gt[b])))
+        return worst / scale
+
+    assert residual(1.0 / 500.0) <= 3e-4
+    assert residual(1.0 / 450.0) >= 3e-2 and residual(1.0 / 550.0) >= 3e-2
+    assert np.max(np.abs(ons.opdiv([u, v], ps) / ps['bm2'])) <= 2e-5
